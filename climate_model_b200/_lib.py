@@ -1,0 +1,110 @@
+"""ctypes binding of libdyncore.so (include/dyncore.h).
+
+The product path has NO CPU fallback: if the CUDA library is missing or cannot be loaded
+this module raises.  (The CPU test-suite injects tests/emu/libdyncore_emu.so, a host
+emulation built from the same kernel bodies, through `use_library`; nothing in this package
+does that by itself.)
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+DEFAULT_LIBRARY = os.path.join(_HERE, 'libdyncore.so')
+
+_dp = ctypes.POINTER(ctypes.c_double)
+
+GRID_FIELDS_2D = ['A', 'dxjs', 'dyis', 'corf', 'corf_is', 'lat_rad', 'lat_is_rad', 'dlon_rad',
+                  'dlat_rad']
+GRID_FIELDS_1D = ['sigma_vb', 'dsigma', 'UVFLX_dif_coef', 'POTT_dif_coef', 'moist_dif_coef']
+
+DC_NK_2D, DC_NK_NZ, DC_NK_NZS = 0, 1, 2
+
+
+class GridDesc(ctypes.Structure):
+    """dc_grid_desc (include/dyncore.h)"""
+    _fields_ = ([('nx', ctypes.c_int), ('ny', ctypes.c_int), ('nz', ctypes.c_int),
+                 ('j0', ctypes.c_int), ('j1', ctypes.c_int), ('i_moist', ctypes.c_int),
+                 ('dt', ctypes.c_double), ('pair_top', ctypes.c_double)] +
+                [(n, _dp) for n in GRID_FIELDS_2D + GRID_FIELDS_1D])
+
+
+class DyncoreError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__('libdyncore error %d: %s' % (code, message))
+        self.code = code
+
+
+_lib = None
+_lib_path = None
+
+_ENTRIES = ['dc_continuity', 'dc_momentum', 'dc_temperature', 'dc_moisture',
+            'dc_compute_tendencies', 'dc_euler_forward', 'dc_primary_diag', 'dc_secondary_diag']
+
+
+def _declare(lib):
+    vp = ctypes.c_void_p
+    lib.dc_last_error.restype = ctypes.c_char_p
+    lib.dc_is_cuda.restype = ctypes.c_int
+    lib.dc_create.argtypes = [ctypes.POINTER(GridDesc), ctypes.POINTER(vp)]
+    lib.dc_destroy.argtypes = [vp]
+    lib.dc_get_layout.argtypes = [vp] + [ctypes.POINTER(ctypes.c_int)] * 3
+    lib.dc_num_fields.restype = ctypes.c_int
+    lib.dc_field_name.argtypes = [ctypes.c_int]
+    lib.dc_field_name.restype = ctypes.c_char_p
+    lib.dc_field_id.argtypes = [ctypes.c_char_p]
+    lib.dc_field_info.argtypes = [ctypes.c_int] + [ctypes.POINTER(ctypes.c_int)] * 3
+    lib.dc_bind_field.argtypes = [vp, ctypes.c_int, vp, ctypes.c_size_t]
+    for e in _ENTRIES:
+        getattr(lib, e).argtypes = [vp, vp]
+    lib.dc_exchange_bc.argtypes = [vp, ctypes.c_int, vp]
+    lib.dc_step_matsuno.argtypes = [vp, ctypes.c_int, vp]
+    lib.dc_launch_count.argtypes = [vp]
+    lib.dc_launch_count.restype = ctypes.c_longlong
+    for opt in ('dc_set_band_comm', 'dc_halo_exchange'):
+        if hasattr(lib, opt):
+            getattr(lib, opt).restype = ctypes.c_int
+    return lib
+
+
+def use_library(path):
+    """load a specific build of the library (tests: the host emulation)"""
+    global _lib, _lib_path
+    _lib = _declare(ctypes.CDLL(path))
+    _lib_path = path
+    return _lib
+
+
+def lib():
+    """the loaded library; loads climate_model_b200/libdyncore.so on first use"""
+    if _lib is None:
+        if not os.path.exists(DEFAULT_LIBRARY):
+            raise ImportError(
+                'climate_model_b200/libdyncore.so is missing: build it with '
+                '`python -c "import __graft_entry__ as g; g.build()"` (nvcc, sm_100a). '
+                'There is no CPU fallback.')
+        use_library(DEFAULT_LIBRARY)
+    return _lib
+
+
+def library_path():
+    return _lib_path
+
+
+def is_cuda():
+    return bool(lib().dc_is_cuda())
+
+
+def check(code):
+    if code != 0:
+        raise DyncoreError(code, lib().dc_last_error().decode())
+
+
+def field_table():
+    """{name: (id, stgx, stgy, nk_kind)} from the library's registry"""
+    L = lib()
+    out = {}
+    for i in range(L.dc_num_fields()):
+        sx, sy, nk = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        check(L.dc_field_info(i, ctypes.byref(sx), ctypes.byref(sy), ctypes.byref(nk)))
+        out[L.dc_field_name(i).decode()] = (i, sx.value, sy.value, nk.value)
+    return out

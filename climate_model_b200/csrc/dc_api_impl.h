@@ -1,0 +1,542 @@
+// dc_api_impl.h -- implementation of the C ABI in include/dyncore.h, written against a
+// small backend interface so that the SAME code drives
+//   - the CUDA kernels (dyncore.cu: the product), and
+//   - the host emulation of the kernel bodies (tests/emu/emu_dyncore.cpp: CPU tests only).
+// The including file must define, before including this header:
+//   DC_BACKEND_IS_CUDA                         0 / 1
+//   int  dcb_malloc(void **p, size_t n);       int dcb_free(void *p);
+//   int  dcb_h2d(void *dst, const void *src, size_t n);
+//   int  dcb_d2d_async(void *dst, const void *src, size_t n, void *stream);
+//   int  dcb_last_error();                     (0 = ok; backend error code otherwise)
+//   const char *dcb_error_string(int code);
+//   template <class Body> void dcb_launch(const Body &b, int i0, int i1, int j0, int j1,
+//                                         void *stream);   // body(i, j) for the closed box
+#pragma once
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/dyncore.h"
+#include "dc_geom.h"
+#include "dc_kernels.h"
+
+namespace dc {
+
+static thread_local std::string g_last_error;
+
+static int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+struct FieldInfo {
+    const char *name;
+    int stgx, stgy, nk_kind;
+};
+
+// dyn-core subset of main_fields.py:233-470 (fdict): staggering and vertical extent
+static const FieldInfo g_field_info[F_COUNT] = {
+    {"COLP", 0, 0, DC_NK_2D},       {"COLP_OLD", 0, 0, DC_NK_2D},
+    {"COLP_NEW", 0, 0, DC_NK_2D},   {"dCOLPdt", 0, 0, DC_NK_2D},
+    {"HSURF", 0, 0, DC_NK_2D},      {"UWIND", 1, 0, DC_NK_NZ},
+    {"UWIND_OLD", 1, 0, DC_NK_NZ},  {"VWIND", 0, 1, DC_NK_NZ},
+    {"VWIND_OLD", 0, 1, DC_NK_NZ},  {"WWIND", 0, 0, DC_NK_NZS},
+    {"POTT", 0, 0, DC_NK_NZ},       {"POTT_OLD", 0, 0, DC_NK_NZ},
+    {"QV", 0, 0, DC_NK_NZ},         {"QV_OLD", 0, 0, DC_NK_NZ},
+    {"QC", 0, 0, DC_NK_NZ},         {"QC_OLD", 0, 0, DC_NK_NZ},
+    {"UFLX", 1, 0, DC_NK_NZ},       {"VFLX", 0, 1, DC_NK_NZ},
+    {"FLXDIV", 0, 0, DC_NK_NZ},     {"BFLX", 0, 0, DC_NK_NZ},
+    {"CFLX", 1, 1, DC_NK_NZ},       {"DFLX", 0, 1, DC_NK_NZ},
+    {"EFLX", 0, 1, DC_NK_NZ},       {"RFLX", 0, 0, DC_NK_NZ},
+    {"QFLX", 1, 1, DC_NK_NZ},       {"SFLX", 1, 0, DC_NK_NZ},
+    {"TFLX", 1, 0, DC_NK_NZ},       {"WWIND_UWIND", 1, 0, DC_NK_NZS},
+    {"WWIND_VWIND", 0, 1, DC_NK_NZS}, {"dUFLXdt", 1, 0, DC_NK_NZ},
+    {"dVFLXdt", 0, 1, DC_NK_NZ},    {"dPOTTdt", 0, 0, DC_NK_NZ},
+    {"dQVdt", 0, 0, DC_NK_NZ},      {"dQCdt", 0, 0, DC_NK_NZ},
+    {"PHI", 0, 0, DC_NK_NZ},        {"PHIVB", 0, 0, DC_NK_NZS},
+    {"PVTF", 0, 0, DC_NK_NZ},       {"PVTFVB", 0, 0, DC_NK_NZS},
+    {"POTTVB", 0, 0, DC_NK_NZS},    {"TAIR", 0, 0, DC_NK_NZ},
+    {"TAIRVB", 0, 0, DC_NK_NZS},    {"PAIR", 0, 0, DC_NK_NZ},
+    {"PAIRVB", 0, 0, DC_NK_NZS},    {"RHO", 0, 0, DC_NK_NZ},
+    {"RHOVB", 0, 0, DC_NK_NZS},     {"WINDX", 0, 0, DC_NK_NZ},
+    {"WINDY", 0, 0, DC_NK_NZ},      {"WIND", 0, 0, DC_NK_NZ},
+};
+
+}  // namespace dc
+
+struct dc_handle {
+    dc::Geom g;
+    dc::Fields f;
+    void *geom_buf;       // one device allocation holding all per-row / per-level arrays
+    long long launches;
+    double **slot(int id) { return reinterpret_cast<double **>(&f) + id; }
+    double *const *slot(int id) const { return reinterpret_cast<double *const *>(&f) + id; }
+};
+
+namespace dc {
+
+static int nk_of(const Geom &g, int id)
+{
+    switch (g_field_info[id].nk_kind) {
+        case DC_NK_2D: return 1;
+        case DC_NK_NZ: return g.nz;
+        default: return g.nz + 1;
+    }
+}
+
+static int backend_status(const char *what)
+{
+    int e = dcb_last_error();
+    if (e) return fail(e, "%s: %s", what, dcb_error_string(e));
+    return DC_OK;
+}
+
+// fields an entry needs; checked before any launch so a missing binding fails loudly
+static int need(const dc_handle *h, const char *entry, const std::vector<int> &ids)
+{
+    for (int id : ids)
+        if (*h->slot(id) == nullptr)
+            return fail(DC_ERR_UNBOUND, "%s: field %s is not bound", entry,
+                        g_field_info[id].name);
+    return DC_OK;
+}
+
+template <class Body>
+static void launch(dc_handle *h, const Body &b, int i0, int i1, int j0, int j1, void *stream)
+{
+    if (i1 < i0 || j1 < j0) return;
+    dcb_launch(b, i0, i1, j0, j1, stream);
+    h->launches++;
+}
+
+// one i-invariant row value of a reference-layout 2-D host array (fnx, fny), checked
+static int row_values(const double *a, int fnx, int fny, int i_lo, int i_hi, const char *name,
+                      std::vector<double> &out)
+{
+    out.assign(fny, 0.);
+    for (int j = 0; j < fny; j++) {
+        const double v = a[(size_t)i_lo * fny + j];
+        for (int i = i_lo; i <= i_hi && i < fnx; i++)
+            if (memcmp(&a[(size_t)i * fny + j], &v, sizeof v) != 0)
+                return fail(DC_ERR_SHAPE,
+                            "grid field %s varies with longitude at row %d (i=%d): only regular "
+                            "lat-lon grids are supported",
+                            name, j, i);
+        out[j] = v;
+    }
+    return DC_OK;
+}
+
+static int do_continuity(dc_handle *h, bool store_flxdiv, void *stream)
+{
+    const Fields &f = h->f;
+    const Geom &g = h->g;
+    if (store_flxdiv) {
+        ContinuityBody<true> b{g,      f.UWIND,  f.VWIND, f.COLP,     f.COLP_OLD, f.UFLX,
+                               f.VFLX, f.FLXDIV, f.WWIND, f.COLP_NEW, f.dCOLPdt};
+        launch(h, b, 1, g.nx, 1, g.ny, stream);
+    } else {
+        ContinuityBody<false> b{g,      f.UWIND,  f.VWIND, f.COLP,     f.COLP_OLD, f.UFLX,
+                                f.VFLX, f.FLXDIV, f.WWIND, f.COLP_NEW, f.dCOLPdt};
+        launch(h, b, 1, g.nx, 1, g.ny, stream);
+    }
+    return DC_OK;
+}
+
+static int do_momentum(dc_handle *h, void *stream)
+{
+    const Fields &f = h->f;
+    const Geom &g = h->g;
+    PrepBody p{g,      f.UWIND, f.VWIND, f.WWIND, f.UFLX, f.VFLX, f.COLP_NEW, f.WWIND_UWIND,
+               f.WWIND_VWIND, f.BFLX, f.CFLX, f.DFLX, f.EFLX, f.RFLX, f.QFLX, f.SFLX, f.TFLX};
+    launch(h, p, 1, g.nx + 1, 1, g.ny + 1, stream);
+    UFLXTendencyBody u{g,      f.UFLX, f.UWIND, f.VWIND, f.BFLX,   f.CFLX,        f.DFLX, f.EFLX,
+                       f.PHI,  f.COLP, f.POTT,  f.PVTF,  f.PVTFVB, f.WWIND_UWIND, f.dUFLXdt};
+    launch(h, u, 1, g.nx, 1, g.ny, stream);
+    VFLXTendencyBody v{g,      f.VFLX, f.UWIND, f.VWIND, f.RFLX,   f.SFLX,        f.TFLX, f.QFLX,
+                       f.PHI,  f.COLP, f.POTT,  f.PVTF,  f.PVTFVB, f.WWIND_VWIND, f.dVFLXdt};
+    launch(h, v, 1, g.nx, 2, g.ny, stream);
+    return DC_OK;
+}
+
+static int do_temperature(dc_handle *h, void *stream)
+{
+    const Fields &f = h->f;
+    const Geom &g = h->g;
+    POTTTendencyBody b{g, f.POTT, f.UFLX, f.VFLX, f.COLP, f.POTTVB, f.WWIND, f.COLP_NEW,
+                       f.dPOTTdt};
+    launch(h, b, 1, g.nx, 1, g.ny, stream);
+    return DC_OK;
+}
+
+static int do_moisture(dc_handle *h, void *stream)
+{
+    const Fields &f = h->f;
+    const Geom &g = h->g;
+    if (!g.i_moist) return DC_OK;
+    MoistTendencyBody b{g, f.QV, f.QC, f.UFLX, f.VFLX, f.COLP, f.WWIND, f.COLP_NEW, f.dQVdt,
+                        f.dQCdt};
+    launch(h, b, 1, g.nx, 1, g.ny, stream);
+    return DC_OK;
+}
+
+static int do_euler_forward(dc_handle *h, void *stream)
+{
+    const Fields &f = h->f;
+    const Geom &g = h->g;
+    TimestepBody b{g,         f.COLP,    f.COLP_OLD, f.UWIND_OLD, f.dUFLXdt, f.VWIND_OLD,
+                   f.dVFLXdt, f.POTT_OLD, f.dPOTTdt, f.QV_OLD,    f.dQVdt,   f.QC_OLD,
+                   f.dQCdt,   f.UWIND,   f.VWIND,    f.POTT,      f.QV,      f.QC};
+    launch(h, b, 1, g.nx, 1, g.ny, stream);
+    return DC_OK;
+}
+
+static int do_primary_diag(dc_handle *h, void *stream)
+{
+    const Fields &f = h->f;
+    const Geom &g = h->g;
+    PrimaryDiagBody b{g, f.COLP, f.POTT, f.HSURF, f.PVTF, f.PVTFVB, f.PHI, f.PHIVB, f.POTTVB};
+    launch(h, b, 0, g.nx + 1, 0, g.ny + 1, stream);
+    return DC_OK;
+}
+
+static const std::vector<int> NEED_CONT = {F_UWIND, F_VWIND, F_COLP, F_COLP_OLD, F_UFLX,
+                                                     F_VFLX,  F_WWIND, F_COLP_NEW, F_dCOLPdt};
+static const std::vector<int> NEED_MOM = {
+    F_UWIND, F_VWIND, F_WWIND, F_UFLX, F_VFLX, F_COLP, F_COLP_NEW, F_WWIND_UWIND, F_WWIND_VWIND,
+    F_BFLX,  F_CFLX,  F_DFLX,  F_EFLX, F_RFLX, F_QFLX, F_SFLX,     F_TFLX,        F_PHI,
+    F_POTT,  F_PVTF,  F_PVTFVB, F_dUFLXdt, F_dVFLXdt};
+static const std::vector<int> NEED_TEMP = {F_POTT,  F_UFLX,     F_VFLX,   F_COLP, F_POTTVB,
+                                                     F_WWIND, F_COLP_NEW, F_dPOTTdt};
+static const std::vector<int> NEED_MOIST = {F_QV,    F_QC,       F_UFLX,  F_VFLX, F_COLP,
+                                                      F_WWIND, F_COLP_NEW, F_dQVdt, F_dQCdt};
+static const std::vector<int> NEED_STEP_DRY = {
+    F_COLP, F_COLP_OLD, F_UWIND_OLD, F_dUFLXdt, F_VWIND_OLD, F_dVFLXdt, F_POTT_OLD,
+    F_dPOTTdt, F_UWIND, F_VWIND, F_POTT};
+static const std::vector<int> NEED_STEP_MOIST = {F_QV_OLD, F_dQVdt, F_QC_OLD, F_dQCdt,
+                                                           F_QV,     F_QC};
+static const std::vector<int> NEED_DIAG = {F_COLP, F_POTT,  F_HSURF, F_PVTF,
+                                                     F_PVTFVB, F_PHI, F_PHIVB, F_POTTVB};
+
+}  // namespace dc
+
+using namespace dc;
+
+extern "C" {
+
+const char *dc_last_error(void) { return g_last_error.c_str(); }
+int dc_is_cuda(void) { return DC_BACKEND_IS_CUDA; }
+
+int dc_num_fields(void) { return F_COUNT; }
+const char *dc_field_name(int id) { return (id >= 0 && id < F_COUNT) ? g_field_info[id].name : 0; }
+int dc_field_id(const char *name)
+{
+    if (!name) return -1;
+    for (int i = 0; i < F_COUNT; i++)
+        if (strcmp(name, g_field_info[i].name) == 0) return i;
+    return -1;
+}
+int dc_field_info(int id, int *stgx, int *stgy, int *nk_kind)
+{
+    if (id < 0 || id >= F_COUNT) return fail(DC_ERR_ARG, "dc_field_info: bad field id %d", id);
+    if (stgx) *stgx = g_field_info[id].stgx;
+    if (stgy) *stgy = g_field_info[id].stgy;
+    if (nk_kind) *nk_kind = g_field_info[id].nk_kind;
+    return DC_OK;
+}
+
+int dc_create(const dc_grid_desc *d, dc_handle **out)
+{
+    if (!d || !out) return fail(DC_ERR_ARG, "dc_create: NULL argument");
+    if (d->nx < 3 || d->ny < 3 || d->nz < 3)
+        return fail(DC_ERR_ARG, "dc_create: need nx, ny, nz >= 3 (got %d %d %d)", d->nx, d->ny,
+                    d->nz);
+    if (d->j0 < 1 || d->j1 > d->ny || d->j0 > d->j1)
+        return fail(DC_ERR_ARG, "dc_create: bad row band [%d, %d] for ny = %d", d->j0, d->j1,
+                    d->ny);
+    const void *ptrs[] = {d->A, d->dxjs, d->dyis, d->corf, d->corf_is, d->lat_rad, d->lat_is_rad,
+                          d->dlon_rad, d->dlat_rad, d->sigma_vb, d->dsigma, d->UVFLX_dif_coef,
+                          d->POTT_dif_coef, d->moist_dif_coef};
+    for (const void *p : ptrs)
+        if (!p) return fail(DC_ERR_ARG, "dc_create: NULL grid field");
+    if (!(d->dt > 0.)) return fail(DC_ERR_ARG, "dc_create: dt must be > 0");
+
+    const int nx = d->nx, ny = d->ny, nz = d->nz;
+    dc_handle *h = new dc_handle();
+    memset(&h->f, 0, sizeof h->f);
+    Geom &g = h->g;
+    g.nx = nx; g.ny = ny; g.nz = nz;
+    g.j0 = d->j0; g.j1 = d->j1;
+    g.i_moist = d->i_moist ? 1 : 0;
+    g.dt = d->dt; g.pair_top = d->pair_top;
+    g.NI = ((nx + 3) + 15) / 16 * 16;
+    g.NJ = (g.j1 - g.j0 + 1) + 2 * HJ + 1;
+    g.jshift = HJ - g.j0;
+    g.plane = (size_t)g.NI * (size_t)g.NJ;
+
+    // constant fields
+    std::vector<double> r;
+    int rc;
+    auto constant = [&](const double *a, int fnx, int fny, int i_lo, int i_hi, int j_lo, int j_hi,
+                        const char *name, double *outv) -> int {
+        const double v = a[(size_t)i_lo * fny + j_lo];
+        for (int i = i_lo; i <= i_hi; i++)
+            for (int j = j_lo; j <= j_hi; j++)
+                if (a[(size_t)i * fny + j] != v)
+                    return fail(DC_ERR_SHAPE, "grid field %s is not constant", name);
+        (void)fnx;
+        *outv = v;
+        return DC_OK;
+    };
+    if ((rc = constant(d->dyis, nx + 3, ny + 2, 1, nx + 1, 1, ny, "dyis", &g.dyis)) ||
+        (rc = constant(d->dlon_rad, nx + 2, ny + 3, 1, nx, 1, ny + 1, "dlon_rad", &g.dlon_rad)) ||
+        (rc = constant(d->dlat_rad, nx + 3, ny + 2, 1, nx + 1, 1, ny, "dlat_rad", &g.dlat_rad))) {
+        delete h;
+        return rc;
+    }
+
+    // per-row arrays (device row = global j + jshift), per-level arrays
+    const int NJ = g.NJ;
+    const size_t n_row = 8, n_lev = 5;
+    std::vector<double> host(n_row * NJ + n_lev * (nz + 1), 0.);
+    double *A = &host[0 * NJ], *dxjs = &host[1 * NJ], *corf = &host[2 * NJ],
+           *corf_is = &host[3 * NJ], *cl = &host[4 * NJ], *sl = &host[5 * NJ],
+           *cl_is = &host[6 * NJ], *sl_is = &host[7 * NJ];
+    struct Src { const double *a; int fnx, fny, i_hi; const char *name; double *dst; int trig; };
+    std::vector<double> lat, lat_is;
+    const Src srcs[] = {
+        {d->A, nx + 2, ny + 2, nx, "A", A, 0},
+        {d->dxjs, nx + 2, ny + 3, nx, "dxjs", dxjs, 0},
+        {d->corf, nx + 2, ny + 2, nx, "corf", corf, 0},
+        {d->corf_is, nx + 3, ny + 2, nx + 1, "corf_is", corf_is, 0},
+        {d->lat_rad, nx + 2, ny + 2, nx, "lat_rad", nullptr, 1},
+        {d->lat_is_rad, nx + 3, ny + 2, nx + 1, "lat_is_rad", nullptr, 2},
+    };
+    for (const Src &s : srcs) {
+        if ((rc = row_values(s.a, s.fnx, s.fny, 1, s.i_hi, s.name, r))) {
+            delete h;
+            return rc;
+        }
+        for (int j = 0; j < s.fny; j++) {
+            const int jd = j + g.jshift;
+            if (jd < 0 || jd >= NJ) continue;
+            if (s.trig == 0) s.dst[jd] = r[j];
+            // host libm cos/sin: what numba's math.cos / math.sin lower to on the CPU path
+            // (dyn_UFLX.py:54-63, dyn_VFLX.py:52-62)
+            if (s.trig == 1) { cl[jd] = cos(r[j]); sl[jd] = sin(r[j]); }
+            if (s.trig == 2) { cl_is[jd] = cos(r[j]); sl_is[jd] = sin(r[j]); }
+        }
+    }
+    double *lev = &host[n_row * NJ];
+    double *sigma_vb = lev, *dsigma = lev + (nz + 1), *ucoef = lev + 2 * (nz + 1),
+           *pcoef = lev + 3 * (nz + 1), *mcoef = lev + 4 * (nz + 1);
+    memcpy(sigma_vb, d->sigma_vb, sizeof(double) * (nz + 1));
+    memcpy(dsigma, d->dsigma, sizeof(double) * nz);
+    memcpy(ucoef, d->UVFLX_dif_coef, sizeof(double) * nz);
+    memcpy(pcoef, d->POTT_dif_coef, sizeof(double) * nz);
+    memcpy(mcoef, d->moist_dif_coef, sizeof(double) * nz);
+
+    void *dev = nullptr;
+    if (dcb_malloc(&dev, host.size() * sizeof(double)) ||
+        dcb_h2d(dev, host.data(), host.size() * sizeof(double))) {
+        int e = dcb_last_error();
+        delete h;
+        return fail(e ? e : DC_ERR_NO_DEVICE, "dc_create: device allocation failed: %s",
+                    dcb_error_string(e));
+    }
+    h->geom_buf = dev;
+    const double *db = static_cast<const double *>(dev);
+    g.A = db + 0 * NJ; g.dxjs = db + 1 * NJ; g.corf = db + 2 * NJ; g.corf_is = db + 3 * NJ;
+    g.cos_lat = db + 4 * NJ; g.sin_lat = db + 5 * NJ; g.cos_lat_is = db + 6 * NJ;
+    g.sin_lat_is = db + 7 * NJ;
+    const double *dl = db + n_row * NJ;
+    g.sigma_vb = dl; g.dsigma = dl + (nz + 1); g.UVFLX_dif_coef = dl + 2 * (nz + 1);
+    g.POTT_dif_coef = dl + 3 * (nz + 1); g.moist_dif_coef = dl + 4 * (nz + 1);
+    h->launches = 0;
+    *out = h;
+    return DC_OK;
+}
+
+int dc_destroy(dc_handle *h)
+{
+    if (!h) return DC_OK;
+    if (h->geom_buf) dcb_free(h->geom_buf);
+    delete h;
+    return DC_OK;
+}
+
+int dc_get_layout(const dc_handle *h, int *NI, int *NJ, int *jshift)
+{
+    if (!h) return fail(DC_ERR_ARG, "dc_get_layout: NULL handle");
+    if (NI) *NI = h->g.NI;
+    if (NJ) *NJ = h->g.NJ;
+    if (jshift) *jshift = h->g.jshift;
+    return DC_OK;
+}
+
+int dc_bind_field(dc_handle *h, int id, void *devptr, size_t nbytes)
+{
+    if (!h) return fail(DC_ERR_ARG, "dc_bind_field: NULL handle");
+    if (id < 0 || id >= F_COUNT) return fail(DC_ERR_ARG, "dc_bind_field: bad field id %d", id);
+    const size_t need_bytes = (size_t)nk_of(h->g, id) * h->g.plane * sizeof(double);
+    if (devptr && nbytes < need_bytes)
+        return fail(DC_ERR_SHAPE, "dc_bind_field: %s needs %zu bytes, got %zu",
+                    g_field_info[id].name, need_bytes, nbytes);
+    *h->slot(id) = static_cast<double *>(devptr);
+    return DC_OK;
+}
+
+long long dc_launch_count(const dc_handle *h) { return h ? h->launches : 0; }
+
+#define DC_ENTRY_CHECK(name)                                                     \
+    if (!h) return fail(DC_ERR_ARG, name ": NULL handle");                       \
+    if (h->g.j0 != 1 || h->g.j1 != h->g.ny)                                      \
+        return fail(DC_ERR_STATE, name ": fine-grained entries need the whole "  \
+                                       "latitude range on one device");
+
+int dc_continuity(dc_handle *h, void *stream)
+{
+    DC_ENTRY_CHECK("dc_continuity");
+    int rc;
+    if ((rc = need(h, "dc_continuity", NEED_CONT)) || (rc = need(h, "dc_continuity", {F_FLXDIV})))
+        return rc;
+    do_continuity(h, true, stream);
+    return backend_status("dc_continuity");
+}
+
+int dc_momentum(dc_handle *h, void *stream)
+{
+    DC_ENTRY_CHECK("dc_momentum");
+    int rc;
+    if ((rc = need(h, "dc_momentum", NEED_MOM))) return rc;
+    do_momentum(h, stream);
+    return backend_status("dc_momentum");
+}
+
+int dc_temperature(dc_handle *h, void *stream)
+{
+    DC_ENTRY_CHECK("dc_temperature");
+    int rc;
+    if ((rc = need(h, "dc_temperature", NEED_TEMP))) return rc;
+    do_temperature(h, stream);
+    return backend_status("dc_temperature");
+}
+
+int dc_moisture(dc_handle *h, void *stream)
+{
+    DC_ENTRY_CHECK("dc_moisture");
+    int rc;
+    if (!h->g.i_moist) return DC_OK;
+    if ((rc = need(h, "dc_moisture", NEED_MOIST))) return rc;
+    do_moisture(h, stream);
+    return backend_status("dc_moisture");
+}
+
+int dc_compute_tendencies(dc_handle *h, void *stream)
+{
+    int rc;
+    if ((rc = dc_continuity(h, stream)) || (rc = dc_momentum(h, stream)) ||
+        (rc = dc_temperature(h, stream)) || (rc = dc_moisture(h, stream)))
+        return rc;
+    return DC_OK;
+}
+
+int dc_euler_forward(dc_handle *h, void *stream)
+{
+    DC_ENTRY_CHECK("dc_euler_forward");
+    int rc;
+    if ((rc = need(h, "dc_euler_forward", NEED_STEP_DRY))) return rc;
+    if (h->g.i_moist && (rc = need(h, "dc_euler_forward", NEED_STEP_MOIST))) return rc;
+    do_euler_forward(h, stream);
+    return backend_status("dc_euler_forward");
+}
+
+int dc_primary_diag(dc_handle *h, void *stream)
+{
+    DC_ENTRY_CHECK("dc_primary_diag");
+    int rc;
+    if ((rc = need(h, "dc_primary_diag", NEED_DIAG))) return rc;
+    do_primary_diag(h, stream);
+    return backend_status("dc_primary_diag");
+}
+
+int dc_secondary_diag(dc_handle *h, void *stream)
+{
+    DC_ENTRY_CHECK("dc_secondary_diag");
+    int rc;
+    if ((rc = need(h, "dc_secondary_diag",
+                   {F_POTTVB, F_PVTFVB, F_POTT, F_PVTF, F_UWIND, F_VWIND, F_TAIRVB, F_PAIRVB,
+                    F_RHOVB, F_TAIR, F_PAIR, F_RHO, F_WINDX, F_WINDY, F_WIND})))
+        return rc;
+    const Fields &f = h->f;
+    SecondaryDiagBody b{h->g,  f.POTTVB, f.PVTFVB, f.POTT, f.PVTF, f.UWIND, f.VWIND, f.TAIRVB,
+                        f.PAIRVB, f.RHOVB, f.TAIR, f.PAIR, f.RHO,  f.WINDX, f.WINDY, f.WIND};
+    launch(h, b, 0, h->g.nx + 1, 0, h->g.ny + 1, stream);
+    return backend_status("dc_secondary_diag");
+}
+
+int dc_exchange_bc(dc_handle *h, int id, void *stream)
+{
+    DC_ENTRY_CHECK("dc_exchange_bc");
+    if (id < 0 || id >= F_COUNT) return fail(DC_ERR_ARG, "dc_exchange_bc: bad field id %d", id);
+    int rc;
+    if ((rc = need(h, "dc_exchange_bc", {id}))) return rc;
+    const FieldInfo &fi = g_field_info[id];
+    if (fi.stgx && fi.stgy)
+        return fail(DC_ERR_STATE, "dc_exchange_bc: %s is staggered in x and y; the reference "
+                                  "never exchanges such a field", fi.name);
+    ExchangeBCBody b{h->g, *h->slot(id), fi.stgx | (fi.stgy << 1), nk_of(h->g, id)};
+    launch(h, b, 1, h->g.nx, 1, h->g.ny + (fi.stgy ? 1 : 0), stream);
+    return backend_status("dc_exchange_bc");
+}
+
+int dc_step_matsuno(dc_handle *h, int nsteps, void *stream)
+{
+    DC_ENTRY_CHECK("dc_step_matsuno");
+    if (nsteps < 0) return fail(DC_ERR_ARG, "dc_step_matsuno: nsteps < 0");
+    int rc;
+    if ((rc = need(h, "dc_step_matsuno", NEED_CONT)) || (rc = need(h, "dc_step_matsuno", NEED_MOM)) ||
+        (rc = need(h, "dc_step_matsuno", NEED_TEMP)) ||
+        (rc = need(h, "dc_step_matsuno", NEED_STEP_DRY)) ||
+        (rc = need(h, "dc_step_matsuno", NEED_DIAG)))
+        return rc;
+    const Geom &g = h->g;
+    if (g.i_moist && ((rc = need(h, "dc_step_matsuno", NEED_MOIST)) ||
+                      (rc = need(h, "dc_step_matsuno", NEED_STEP_MOIST))))
+        return rc;
+    const Fields &f = h->f;
+    const size_t b2 = g.plane * sizeof(double), b3 = b2 * g.nz;
+    for (int s = 0; s < nsteps; s++) {
+        // dyn_matsuno.py:34-49: OLD <- current
+        dcb_d2d_async(f.COLP_OLD, f.COLP, b2, stream);
+        dcb_d2d_async(f.UWIND_OLD, f.UWIND, b3, stream);
+        dcb_d2d_async(f.VWIND_OLD, f.VWIND, b3, stream);
+        dcb_d2d_async(f.POTT_OLD, f.POTT, b3, stream);
+        if (g.i_moist) {
+            dcb_d2d_async(f.QV_OLD, f.QV, b3, stream);
+            dcb_d2d_async(f.QC_OLD, f.QC, b3, stream);
+        }
+        for (int stage = 0; stage < 2; stage++) {  // estimate, final
+            do_continuity(h, false, stream);
+            do_momentum(h, stream);
+            do_temperature(h, stream);
+            do_moisture(h, stream);
+            dcb_d2d_async(f.COLP, f.COLP_NEW, b2, stream);  // dyn_matsuno.py:64-67
+            do_euler_forward(h, stream);
+            do_primary_diag(h, stream);
+        }
+    }
+    return backend_status("dc_step_matsuno");
+}
+
+}  // extern "C"

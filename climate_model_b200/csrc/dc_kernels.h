@@ -1,0 +1,562 @@
+// dc_kernels.h -- per-column kernel bodies of the dynamical core ("v1": one body per
+// reference kernel, boundary exchange fused into the producer as image stores).
+//
+// A body is a functor called once per (i, j) column (global reference indices); it marches
+// the sigma column in registers.  With longitude fastest in memory, consecutive threads
+// (consecutive i) touch consecutive addresses at every level: every load/store coalesces.
+// dyncore.cu wraps each body in a __global__ kernel; tests/emu/ runs the same bodies on
+// the host to check the index arithmetic without a GPU (test infrastructure only).
+#pragma once
+#include "dc_geom.h"
+#include "dc_point.h"
+
+namespace dc {
+
+// ---------------------------------------------------------------------------------------
+// image stores: write v at (i, j, k) and at every halo cell misc_boundaries.py:22-42
+// (exchange_BC_cpu) would copy it to.  Rows are images only on the GLOBAL walls.
+// ---------------------------------------------------------------------------------------
+DC_HD void put_rows(const Geom &g, double *F, int i, int j, int k, double v)
+{
+    F[g.idx(i, j, k)] = v;
+    if (j == 1) F[g.idx(i, 0, k)] = v;            // FIELD[:,0,:] = FIELD[:,1,:]
+    if (j == g.ny) F[g.idx(i, g.ny + 1, k)] = v;  // FIELD[:,ny+1,:] = FIELD[:,ny,:]
+}
+// unstaggered in x, unstaggered in y  (nx+2, ny+2)
+DC_HD void put_mass(const Geom &g, double *F, int i, int j, int k, double v)
+{
+    put_rows(g, F, i, j, k, v);
+    if (i == g.nx) put_rows(g, F, 0, j, k, v);     // FIELD[0] = FIELD[nx]
+    if (i == 1) put_rows(g, F, g.nx + 1, j, k, v);  // FIELD[nx+1] = FIELD[1]
+}
+// staggered in x  (nx+3, ny+2); the body computes i in [1, nx]
+DC_HD void put_xstag(const Geom &g, double *F, int i, int j, int k, double v)
+{
+    put_rows(g, F, i, j, k, v);
+    if (i == g.nx) put_rows(g, F, 0, j, k, v);      // FIELD[0] = FIELD[nxs-1]
+    if (i == 1) put_rows(g, F, g.nx + 1, j, k, v);  // FIELD[nxs] = FIELD[1]
+    if (i == 2) put_rows(g, F, g.nx + 2, j, k, v);  // FIELD[nxs+1] = FIELD[2]
+}
+// staggered in y  (nx+2, ny+3): rows 0, 1, nys, nys+1 are forced to 0.
+// Call for j in [1, nys]; the value is ignored on the wall rows.
+DC_HD void put_ystag(const Geom &g, double *F, int i, int j, int k, double v)
+{
+    const int nys = g.ny + 1;
+    const bool wall = (j == 1) || (j == nys);
+    if (wall) v = 0.;
+    const int jx = (j == 1) ? 0 : nys + 1;  // second zero row beside a wall row
+    F[g.idx(i, j, k)] = v;
+    if (wall) F[g.idx(i, jx, k)] = v;
+    if (i == g.nx) {
+        F[g.idx(0, j, k)] = v;
+        if (wall) F[g.idx(0, jx, k)] = v;
+    }
+    if (i == 1) {
+        F[g.idx(g.nx + 1, j, k)] = v;
+        if (wall) F[g.idx(g.nx + 1, jx, k)] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// generic exchange_BC on one field (misc_boundaries.py:22-42), one thread per (i, j) of the
+// SOURCE cells; used by the dc_exchange_bc entry (initial conditions, external callers).
+// kind: 0 mass, 1 x-staggered, 2 y-staggered, 3 xy-staggered
+// ---------------------------------------------------------------------------------------
+struct ExchangeBCBody {
+    Geom g;
+    double *F;
+    int kind, nk;
+    DC_HD void operator()(int i, int j) const
+    {
+        // threads cover i in [1, nx(+1)], j in [1, ny(+1)]
+        const bool xs = kind & 1, ys = kind & 2;
+        for (int k = 0; k < nk; k++) {
+            double v = F[g.idx(i, j, k)];
+            if (ys) {
+                if (xs) {  // CFLX/QFLX-like: x images of put_xstag, rows of put_ystag
+                    const int nys = g.ny + 1;
+                    const bool wall = (j == 1) || (j == nys);
+                    if (wall) v = 0.;
+                    const int jx = (j == 1) ? 0 : nys + 1;
+                    int ii[2] = {i, -1};
+                    if (i == g.nx) ii[1] = 0;
+                    if (i == 1) ii[1] = g.nx + 1;
+                    if (i == 2) ii[1] = g.nx + 2;
+                    for (int a = 0; a < 2; a++) {
+                        if (ii[a] < 0) continue;
+                        F[g.idx(ii[a], j, k)] = v;
+                        if (wall) F[g.idx(ii[a], jx, k)] = v;
+                    }
+                } else {
+                    put_ystag(g, F, i, j, k, v);
+                }
+            } else if (xs) {
+                put_xstag(g, F, i, j, k, v);
+            } else {
+                put_mass(g, F, i, j, k, v);
+            }
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------
+// continuity: dyn_continuity.py:170-228 + BCs dyn_org_discretizations.py:114-117
+// threads: i in [1, nx], j in [1, ny].  U and V are read ONCE: the running flux-divergence
+// prefix is parked in WWIND[k] during the first sweep and finalised in the second (which
+// re-reads only this thread's own WWIND column).
+// ---------------------------------------------------------------------------------------
+template <bool STORE_FLXDIV>
+struct ContinuityBody {
+    Geom g;
+    const double *UWIND, *VWIND, *COLP, *COLP_OLD;
+    double *UFLX, *VFLX, *FLXDIV, *WWIND, *COLP_NEW, *dCOLPdt;
+    DC_HD void operator()(int i, int j) const
+    {
+        const int nz = g.nz;
+        const double c = COLP[g.idx2(i, j)];
+        const double c_im1 = COLP[g.idx2(i - 1, j)], c_ip1 = COLP[g.idx2(i + 1, j)];
+        const double c_jm1 = COLP[g.idx2(i, j - 1)], c_jp1 = COLP[g.idx2(i, j + 1)];
+        const double dxjs = g.dxjs[g.row(j)], dxjs_jp1 = g.dxjs[g.row(j + 1)];
+        const double A = g.A[g.row(j)];
+        double s = 0.;  // sequential ascending sum (numba's FLXDIV.sum(axis=2))
+        for (int k = 0; k < nz; k++) {
+            const double uf = calc_UFLX(UWIND[g.idx(i, j, k)], c, c_im1, g.dyis);
+            const double uf_ip1 = calc_UFLX(UWIND[g.idx(i + 1, j, k)], c_ip1, c, g.dyis);
+            const double vf = calc_VFLX(VWIND[g.idx(i, j, k)], c, c_jm1, dxjs);
+            const double vf_jp1 = calc_VFLX(VWIND[g.idx(i, j + 1, k)], c_jp1, c, dxjs_jp1);
+            const double fd = calc_FLXDIV(uf, uf_ip1, vf, vf_jp1, g.dsigma[k], A);
+            put_xstag(g, UFLX, i, j, k, uf);
+            put_ystag(g, VFLX, i, j, k, vf);
+            if (j == g.ny) put_ystag(g, VFLX, i, g.ny + 1, k, 0.);
+            if (STORE_FLXDIV) FLXDIV[g.idx(i, j, k)] = fd;
+            s += fd;
+            if (k + 1 < nz) WWIND[g.idx(i, j, k + 1)] = s;  // prefix, finalised below
+        }
+        const double dcdt = -s;
+        const double cnew = COLP_OLD[g.idx2(i, j)] + g.dt * dcdt;
+        dCOLPdt[g.idx2(i, j)] = dcdt;
+        put_mass(g, COLP_NEW, i, j, 0, cnew);
+        for (int k = 1; k < nz; k++) {
+            const double flxdivsum = WWIND[g.idx(i, j, k)];
+            put_mass(g, WWIND, i, j, k, (-flxdivsum / cnew - g.sigma_vb[k] * dcdt / cnew));
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------
+// momentum-flux preparation: dyn_UVFLX_prepare.py:249-439 (turbulence part: zero fields)
+// threads: i in [1, nxs], j in [1, nys]
+// ---------------------------------------------------------------------------------------
+struct PrepBody {
+    Geom g;
+    const double *UWIND, *VWIND, *WWIND, *UFLX, *VFLX, *COLP_NEW;
+    double *WWIND_UWIND, *WWIND_VWIND, *BFLX, *CFLX, *DFLX, *EFLX, *RFLX, *QFLX, *SFLX, *TFLX;
+    DC_HD double P(int i, int j, int k) const
+    {
+        return COLP_NEW[g.idx2(i, j)] * g.A[g.row(j)] * WWIND[g.idx(i, j, k)];
+    }
+    DC_HD void operator()(int i, int j) const
+    {
+        const int nx = g.nx, ny = g.ny, nz = g.nz;
+        const double *u = UFLX, *v = VFLX;
+        if (j <= ny) {  // dyn_UVFLX_prepare.py:262-278
+            const int wall = (j == 1) ? -1 : ((j == ny) ? 1 : 0);
+            WWIND_UWIND[g.idx(i, j, 0)] = 0.;
+            WWIND_UWIND[g.idx(i, j, nz)] = 0.;
+            for (int k = 1; k < nz; k++)
+                WWIND_UWIND[g.idx(i, j, k)] =
+                    colpa_wwind(P(i, j, k), P(i - 1, j, k), P(i, j - 1, k), P(i, j + 1, k),
+                                P(i - 1, j - 1, k), P(i - 1, j + 1, k), wall) *
+                    interp_ks(UWIND[g.idx(i, j, k)], UWIND[g.idx(i, j, k - 1)], g.dsigma[k],
+                              g.dsigma[k - 1]);
+        }
+        if (i <= nx) {  // dyn_UVFLX_prepare.py:280-296
+            WWIND_VWIND[g.idx(i, j, 0)] = 0.;
+            WWIND_VWIND[g.idx(i, j, nz)] = 0.;
+            for (int k = 1; k < nz; k++)
+                WWIND_VWIND[g.idx(i, j, k)] =
+                    colpa_wwind(P(i, j, k), P(i, j - 1, k), P(i - 1, j, k), P(i + 1, j, k),
+                                P(i - 1, j - 1, k), P(i + 1, j - 1, k), 0) *
+                    interp_ks(VWIND[g.idx(i, j, k)], VWIND[g.idx(i, j, k - 1)], g.dsigma[k],
+                              g.dsigma[k - 1]);
+        }
+        for (int k = 0; k < nz; k++) {  // dyn_UVFLX_prepare.py:345-436
+            CFLX[g.idx(i, j, k)] =
+                calc_CFLX(v[g.idx(i - 1, j - 1, k)], v[g.idx(i, j - 1, k)], v[g.idx(i - 1, j, k)],
+                          v[g.idx(i, j, k)], v[g.idx(i - 1, j + 1, k)], v[g.idx(i, j + 1, k)]);
+            QFLX[g.idx(i, j, k)] =
+                calc_QFLX(u[g.idx(i - 1, j - 1, k)], u[g.idx(i - 1, j, k)], u[g.idx(i, j - 1, k)],
+                          u[g.idx(i, j, k)], u[g.idx(i + 1, j - 1, k)], u[g.idx(i + 1, j, k)]);
+            if (i <= nx) {
+                DFLX[g.idx(i, j, k)] = calc_DFLX(
+                    v[g.idx(i, j - 1, k)], v[g.idx(i, j, k)], v[g.idx(i, j + 1, k)],
+                    u[g.idx(i, j - 1, k)], u[g.idx(i, j, k)], u[g.idx(i + 1, j - 1, k)],
+                    u[g.idx(i + 1, j, k)]);
+                EFLX[g.idx(i, j, k)] = calc_EFLX(
+                    v[g.idx(i, j - 1, k)], v[g.idx(i, j, k)], v[g.idx(i, j + 1, k)],
+                    u[g.idx(i, j - 1, k)], u[g.idx(i, j, k)], u[g.idx(i + 1, j - 1, k)],
+                    u[g.idx(i + 1, j, k)]);
+            }
+            if (j <= ny) {
+                SFLX[g.idx(i, j, k)] = calc_SFLX(
+                    v[g.idx(i - 1, j, k)], v[g.idx(i - 1, j + 1, k)], v[g.idx(i, j, k)],
+                    v[g.idx(i, j + 1, k)], u[g.idx(i - 1, j, k)], u[g.idx(i, j, k)],
+                    u[g.idx(i + 1, j, k)]);
+                TFLX[g.idx(i, j, k)] = calc_TFLX(
+                    v[g.idx(i - 1, j, k)], v[g.idx(i - 1, j + 1, k)], v[g.idx(i, j, k)],
+                    v[g.idx(i, j + 1, k)], u[g.idx(i - 1, j, k)], u[g.idx(i, j, k)],
+                    u[g.idx(i + 1, j, k)]);
+            }
+            if (i <= nx && j <= ny) {
+                BFLX[g.idx(i, j, k)] = calc_BFLX(
+                    u[g.idx(i, j - 1, k)], u[g.idx(i + 1, j - 1, k)], u[g.idx(i, j, k)],
+                    u[g.idx(i + 1, j, k)], u[g.idx(i, j + 1, k)], u[g.idx(i + 1, j + 1, k)]);
+                RFLX[g.idx(i, j, k)] = calc_RFLX(
+                    v[g.idx(i - 1, j, k)], v[g.idx(i - 1, j + 1, k)], v[g.idx(i, j, k)],
+                    v[g.idx(i, j + 1, k)], v[g.idx(i + 1, j, k)], v[g.idx(i + 1, j + 1, k)]);
+            }
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------
+// dUFLXdt: dyn_UFLX.py:339-434 + :69-199.  threads: i in [1, nx], j in [1, ny]
+// (column nxs of the reference is garbage that the periodic BC overwrites)
+// ---------------------------------------------------------------------------------------
+struct UFLXTendencyBody {
+    Geom g;
+    const double *UFLX, *UWIND, *VWIND, *BFLX, *CFLX, *DFLX, *EFLX, *PHI, *COLP, *POTT, *PVTF,
+        *PVTFVB, *WWIND_UWIND;
+    double *dUFLXdt;
+    DC_HD void operator()(int i, int j) const
+    {
+        const int nx = g.nx, ny = g.ny, nz = g.nz;
+        const int im1 = (i == 1) ? nx : i - 1;  // BCx, dyn_UFLX.py:367-374
+        const double c = COLP[g.idx2(i, j)], c_im1 = COLP[g.idx2(i - 1, j)];
+        const double corf_is = g.corf_is[g.row(j)];
+        const double cosl = g.cos_lat_is[g.row(j)], sinl = g.sin_lat_is[g.row(j)];
+        const double *U = UWIND, *V = VWIND;
+        for (int k = 0; k < nz; k++) {
+            double bflx = BFLX[g.idx(i, j, k)], cflx = CFLX[g.idx(i, j, k)];
+            double eflx = EFLX[g.idx(i, j, k)], dflx_jp1 = DFLX[g.idx(i, j + 1, k)];
+            double cflx_jp1 = CFLX[g.idx(i, j + 1, k)];
+            double bflx_im1 = BFLX[g.idx(im1, j, k)], dflx_im1 = DFLX[g.idx(im1, j, k)];
+            double eflx_im1_jp1 = EFLX[g.idx(im1, j + 1, k)];
+            if (j == 1) {  // BCy, dyn_UFLX.py:377-384
+                dflx_im1 = 0.;
+                cflx = 0.;
+                eflx = 0.;
+            }
+            if (j == ny) {
+                dflx_jp1 = 0.;
+                cflx_jp1 = 0.;
+                eflx_im1_jp1 = 0.;
+            }
+            const double u = U[g.idx(i, j, k)], u_im1 = U[g.idx(i - 1, j, k)],
+                         u_ip1 = U[g.idx(i + 1, j, k)];
+            double d = 0.;
+            d = d + UVFLX_hor_adv(u, u_im1, u_ip1, U[g.idx(i, j - 1, k)], U[g.idx(i, j + 1, k)],
+                                  U[g.idx(i - 1, j - 1, k)], U[g.idx(i - 1, j + 1, k)],
+                                  U[g.idx(i + 1, j - 1, k)], U[g.idx(i + 1, j + 1, k)], bflx,
+                                  bflx_im1, cflx, cflx_jp1, dflx_im1, dflx_jp1, eflx,
+                                  eflx_im1_jp1, 1.);
+            d = d + ((WWIND_UWIND[g.idx(i, j, k)] - WWIND_UWIND[g.idx(i, j, k + 1)]) /
+                     g.dsigma[k]);
+            d = d + coriolis_UWIND(c, c_im1, V[g.idx(i, j, k)], V[g.idx(i - 1, j, k)],
+                                   V[g.idx(i, j + 1, k)], V[g.idx(i - 1, j + 1, k)], u, u_im1,
+                                   u_ip1, corf_is, cosl, sinl, g.dlon_rad, g.dlat_rad);
+            d = d + pre_grad(PHI[g.idx(i, j, k)], PHI[g.idx(i - 1, j, k)], c, c_im1,
+                             POTT[g.idx(i, j, k)], POTT[g.idx(i - 1, j, k)], PVTF[g.idx(i, j, k)],
+                             PVTF[g.idx(i - 1, j, k)], PVTFVB[g.idx(i, j, k)],
+                             PVTFVB[g.idx(i - 1, j, k)], PVTFVB[g.idx(i - 1, j, k + 1)],
+                             PVTFVB[g.idx(i, j, k + 1)], g.dsigma[k], g.sigma_vb[k],
+                             g.sigma_vb[k + 1], g.dyis);
+            const double coef = g.UVFLX_dif_coef[k];
+            if (coef > 0.)
+                d = d + num_dif(UFLX[g.idx(i, j, k)], UFLX[g.idx(i - 1, j, k)],
+                                UFLX[g.idx(i + 1, j, k)], UFLX[g.idx(i, j - 1, k)],
+                                UFLX[g.idx(i, j + 1, k)], coef);
+            dUFLXdt[g.idx(i, j, k)] = d;
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------
+// dVFLXdt: dyn_VFLX.py:322-408 + :67-198.  threads: i in [1, nx], j in [2, ny]
+// (wall rows 1 and nys are NaN in the reference and zeroed by the BC after the Euler step)
+// ---------------------------------------------------------------------------------------
+struct VFLXTendencyBody {
+    Geom g;
+    const double *VFLX, *UWIND, *VWIND, *RFLX, *SFLX, *TFLX, *QFLX, *PHI, *COLP, *POTT, *PVTF,
+        *PVTFVB, *WWIND_VWIND;
+    double *dVFLXdt;
+    DC_HD void operator()(int i, int j) const
+    {
+        const int nx = g.nx, nz = g.nz;
+        const int ip1 = (i == nx) ? 1 : i + 1;  // BCx, dyn_VFLX.py:349-356
+        const double c = COLP[g.idx2(i, j)], c_jm1 = COLP[g.idx2(i, j - 1)];
+        const double corf = g.corf[g.row(j)], corf_jm1 = g.corf[g.row(j - 1)];
+        const double cosl = g.cos_lat[g.row(j)], sinl = g.sin_lat[g.row(j)];
+        const double cosl_jm1 = g.cos_lat[g.row(j - 1)], sinl_jm1 = g.sin_lat[g.row(j - 1)];
+        const double dxjs = g.dxjs[g.row(j)];
+        const double *U = UWIND, *V = VWIND;
+        for (int k = 0; k < nz; k++) {
+            const double rflx = RFLX[g.idx(i, j, k)], qflx = QFLX[g.idx(i, j, k)];
+            const double tflx = TFLX[g.idx(i, j, k)], rflx_jm1 = RFLX[g.idx(i, j - 1, k)];
+            const double sflx_jm1 = SFLX[g.idx(i, j - 1, k)];
+            const double qflx_ip1 = QFLX[g.idx(ip1, j, k)];
+            const double tflx_ip1_jm1 = TFLX[g.idx(ip1, j - 1, k)];
+            const double sflx_ip1 = SFLX[g.idx(ip1, j, k)];
+            const double v = V[g.idx(i, j, k)];
+            double d = 0.;
+            d = d + UVFLX_hor_adv(v, V[g.idx(i, j - 1, k)], V[g.idx(i, j + 1, k)],
+                                  V[g.idx(i - 1, j, k)], V[g.idx(i + 1, j, k)],
+                                  V[g.idx(i - 1, j - 1, k)], V[g.idx(i + 1, j - 1, k)],
+                                  V[g.idx(i - 1, j + 1, k)], V[g.idx(i + 1, j + 1, k)], rflx,
+                                  rflx_jm1, qflx, qflx_ip1, sflx_jm1, sflx_ip1, tflx,
+                                  tflx_ip1_jm1, -1.);
+            d = d + ((WWIND_VWIND[g.idx(i, j, k)] - WWIND_VWIND[g.idx(i, j, k + 1)]) /
+                     g.dsigma[k]);
+            d = d + coriolis_VWIND(c, c_jm1, U[g.idx(i, j, k)], U[g.idx(i, j - 1, k)],
+                                   U[g.idx(i + 1, j, k)], U[g.idx(i + 1, j - 1, k)], corf,
+                                   corf_jm1, cosl, sinl, cosl_jm1, sinl_jm1, g.dlon_rad,
+                                   g.dlat_rad);
+            d = d + pre_grad(PHI[g.idx(i, j, k)], PHI[g.idx(i, j - 1, k)], c, c_jm1,
+                             POTT[g.idx(i, j, k)], POTT[g.idx(i, j - 1, k)], PVTF[g.idx(i, j, k)],
+                             PVTF[g.idx(i, j - 1, k)], PVTFVB[g.idx(i, j, k)],
+                             PVTFVB[g.idx(i, j - 1, k)], PVTFVB[g.idx(i, j - 1, k + 1)],
+                             PVTFVB[g.idx(i, j, k + 1)], g.dsigma[k], g.sigma_vb[k],
+                             g.sigma_vb[k + 1], dxjs);
+            const double coef = g.UVFLX_dif_coef[k];
+            if (coef > 0.)
+                d = d + num_dif(VFLX[g.idx(i, j, k)], VFLX[g.idx(i - 1, j, k)],
+                                VFLX[g.idx(i + 1, j, k)], VFLX[g.idx(i, j - 1, k)],
+                                VFLX[g.idx(i, j + 1, k)], coef);
+            dVFLXdt[g.idx(i, j, k)] = d;
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------
+// dPOTTdt: dyn_POTT.py:180-216 + :55-110.  threads: i in [1, nx], j in [1, ny]
+// ---------------------------------------------------------------------------------------
+struct POTTTendencyBody {
+    Geom g;
+    const double *POTT, *UFLX, *VFLX, *COLP, *POTTVB, *WWIND, *COLP_NEW;
+    double *dPOTTdt;
+    DC_HD void operator()(int i, int j) const
+    {
+        const int nz = g.nz;
+        const double c = COLP[g.idx2(i, j)];
+        const double c_im1 = COLP[g.idx2(i - 1, j)], c_ip1 = COLP[g.idx2(i + 1, j)];
+        const double c_jm1 = COLP[g.idx2(i, j - 1)], c_jp1 = COLP[g.idx2(i, j + 1)];
+        const double cnew = COLP_NEW[g.idx2(i, j)];
+        const double A = g.A[g.row(j)];
+        for (int k = 0; k < nz; k++) {
+            const double p = POTT[g.idx(i, j, k)];
+            const double p_im1 = POTT[g.idx(i - 1, j, k)], p_ip1 = POTT[g.idx(i + 1, j, k)];
+            const double p_jm1 = POTT[g.idx(i, j - 1, k)], p_jp1 = POTT[g.idx(i, j + 1, k)];
+            double d = 0.;
+            d = d + hor_adv(p, p_im1, p_ip1, p_jm1, p_jp1, UFLX[g.idx(i, j, k)],
+                            UFLX[g.idx(i + 1, j, k)], VFLX[g.idx(i, j, k)],
+                            VFLX[g.idx(i, j + 1, k)], A);
+            d = d + vert_adv(POTTVB[g.idx(i, j, k)], POTTVB[g.idx(i, j, k + 1)],
+                             WWIND[g.idx(i, j, k)], WWIND[g.idx(i, j, k + 1)], cnew, g.dsigma[k],
+                             k);
+            const double coef = g.POTT_dif_coef[k];
+            if (coef > 0.)
+                d = d + num_dif_pw(p, p_im1, p_ip1, p_jm1, p_jp1, c, c_im1, c_ip1, c_jm1, c_jp1,
+                                   coef);
+            dPOTTdt[g.idx(i, j, k)] = d;
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------
+// dQVdt, dQCdt: dyn_moist.py:201-243 + :49-129.  threads: i in [1, nx], j in [1, ny]
+// The reference reads Q[k-1] at k = 0 and Q[k+1] at k = nz-1 out of the column; both only
+// enter products that vert_adv drops (k = 0) or multiplies by WWIND[nz] = 0.
+// ---------------------------------------------------------------------------------------
+struct MoistTendencyBody {
+    Geom g;
+    const double *QV, *QC, *UFLX, *VFLX, *COLP, *WWIND, *COLP_NEW;
+    double *dQVdt, *dQCdt;
+    DC_HD void one(const double *Q, double *dQ, int i, int j) const
+    {
+        const int nz = g.nz;
+        const double c = COLP[g.idx2(i, j)];
+        const double c_im1 = COLP[g.idx2(i - 1, j)], c_ip1 = COLP[g.idx2(i + 1, j)];
+        const double c_jm1 = COLP[g.idx2(i, j - 1)], c_jp1 = COLP[g.idx2(i, j + 1)];
+        const double cnew = COLP_NEW[g.idx2(i, j)];
+        const double A = g.A[g.row(j)];
+        double q = Q[g.idx(i, j, 0)];
+        double qvb = q;  // unused at k = 0
+        for (int k = 0; k < nz; k++) {
+            const double q_kp1 = (k + 1 < nz) ? Q[g.idx(i, j, k + 1)] : q;
+            const double q_im1 = Q[g.idx(i - 1, j, k)], q_ip1 = Q[g.idx(i + 1, j, k)];
+            const double q_jm1 = Q[g.idx(i, j - 1, k)], q_jp1 = Q[g.idx(i, j + 1, k)];
+            double d = 0.;
+            d = d + hor_adv(q, q_im1, q_ip1, q_jm1, q_jp1, UFLX[g.idx(i, j, k)],
+                            UFLX[g.idx(i + 1, j, k)], VFLX[g.idx(i, j, k)],
+                            VFLX[g.idx(i, j + 1, k)], A);
+            const double qvb_kp1 = comp_VARVB_log(q_kp1, q);
+            d = d + vert_adv(qvb, qvb_kp1, WWIND[g.idx(i, j, k)], WWIND[g.idx(i, j, k + 1)], cnew,
+                             g.dsigma[k], k);
+            const double coef = g.moist_dif_coef[k];
+            if (coef > 0.)
+                d = d + num_dif_pw(q, q_im1, q_ip1, q_jm1, q_jp1, c, c_im1, c_ip1, c_jm1, c_jp1,
+                                   coef);
+            dQ[g.idx(i, j, k)] = d;
+            q = q_kp1;
+            qvb = qvb_kp1;  // comp_VARVB_log(Q[k+1], Q[k]) is next level's (VAR, VAR_km1)
+        }
+    }
+    DC_HD void operator()(int i, int j) const
+    {
+        one(QV, dQVdt, i, j);
+        one(QC, dQCdt, i, j);
+    }
+};
+
+// ---------------------------------------------------------------------------------------
+// Euler forward (pressure weighted): dyn_timestep.py:212-296 + BCs
+// dyn_org_discretizations.py:388-393.  threads: i in [1, nx], j in [1, ny]
+// ---------------------------------------------------------------------------------------
+struct TimestepBody {
+    Geom g;
+    const double *COLP, *COLP_OLD, *UWIND_OLD, *dUFLXdt, *VWIND_OLD, *dVFLXdt, *POTT_OLD,
+        *dPOTTdt, *QV_OLD, *dQVdt, *QC_OLD, *dQCdt;
+    double *UWIND, *VWIND, *POTT, *QV, *QC;
+    DC_HD void operator()(int i, int j) const
+    {
+        const int ny = g.ny, nz = g.nz;
+        const double A = g.A[g.row(j)], A_jm1 = g.A[g.row(j - 1)], A_jp1 = g.A[g.row(j + 1)];
+        const double *C = COLP, *CO = COLP_OLD;
+        const double c = C[g.idx2(i, j)], co = CO[g.idx2(i, j)];
+        const double colpa_is = interp_COLPA_is(
+            c, C[g.idx2(i - 1, j)], C[g.idx2(i, j - 1)], C[g.idx2(i, j + 1)],
+            C[g.idx2(i - 1, j + 1)], C[g.idx2(i - 1, j - 1)], A, A_jm1, A_jp1, j, ny);
+        const double colpa_old_is = interp_COLPA_is(
+            co, CO[g.idx2(i - 1, j)], CO[g.idx2(i, j - 1)], CO[g.idx2(i, j + 1)],
+            CO[g.idx2(i - 1, j + 1)], CO[g.idx2(i - 1, j - 1)], A, A_jm1, A_jp1, j, ny);
+        const double colpa_js =
+            interp_COLPA_js(c, C[g.idx2(i, j - 1)], C[g.idx2(i - 1, j)], C[g.idx2(i + 1, j)],
+                            C[g.idx2(i + 1, j - 1)], C[g.idx2(i - 1, j - 1)], A, A_jm1);
+        const double colpa_old_js =
+            interp_COLPA_js(co, CO[g.idx2(i, j - 1)], CO[g.idx2(i - 1, j)], CO[g.idx2(i + 1, j)],
+                            CO[g.idx2(i + 1, j - 1)], CO[g.idx2(i - 1, j - 1)], A, A_jm1);
+        for (int k = 0; k < nz; k++) {
+            put_xstag(g, UWIND, i, j, k,
+                      euler_forward_pw(UWIND_OLD[g.idx(i, j, k)], dUFLXdt[g.idx(i, j, k)],
+                                       colpa_is, colpa_old_is, g.dt));
+            if (j >= 2)
+                put_ystag(g, VWIND, i, j, k,
+                          euler_forward_pw(VWIND_OLD[g.idx(i, j, k)], dVFLXdt[g.idx(i, j, k)],
+                                           colpa_js, colpa_old_js, g.dt));
+            else
+                put_ystag(g, VWIND, i, 1, k, 0.);
+            if (j == ny) put_ystag(g, VWIND, i, ny + 1, k, 0.);
+            put_mass(g, POTT, i, j, k,
+                     euler_forward_pw(POTT_OLD[g.idx(i, j, k)], dPOTTdt[g.idx(i, j, k)], c, co,
+                                      g.dt));
+            if (g.i_moist) {
+                put_mass(g, QV, i, j, k,
+                         euler_forward_pw(QV_OLD[g.idx(i, j, k)], dQVdt[g.idx(i, j, k)], c, co,
+                                          g.dt));
+                put_mass(g, QC, i, j, k,
+                         euler_forward_pw(QC_OLD[g.idx(i, j, k)], dQCdt[g.idx(i, j, k)], c, co,
+                                          g.dt));
+            }
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------
+// primary diagnostics: dyn_diagnostics.py:139-195 (PVTF, PVTFVB; PHI, PHIVB bottom-up;
+// POTTVB).  threads: ALL columns i in [0, nx+1], j in [0, ny+1] (halos are computed, not
+// exchanged).  nz+1 pow per column (the reference evaluates 2 per cell).
+// ---------------------------------------------------------------------------------------
+struct PrimaryDiagBody {
+    Geom g;
+    const double *COLP, *POTT, *HSURF;
+    double *PVTF, *PVTFVB, *PHI, *PHIVB, *POTTVB;
+    DC_HD void operator()(int i, int j) const
+    {
+        const int nz = g.nz;
+        const double colp = COLP[g.idx2(i, j)];
+        double p_km12 = g.pair_top + g.sigma_vb[0] * colp;
+        double pw_km12 = pow(p_km12 / 100000., con_kappa);
+        double pvtf_km1 = 0., pott_km1 = 0.;
+        for (int k = 0; k < nz; k++) {
+            const double p_kp12 = g.pair_top + g.sigma_vb[k + 1] * colp;
+            const double pw_kp12 = pow(p_kp12 / 100000., con_kappa);
+            const double pvtf = 1. / (1. + con_kappa) * (pw_kp12 * p_kp12 - pw_km12 * p_km12) /
+                                (p_kp12 - p_km12);
+            const double pott = POTT[g.idx(i, j, k)];
+            PVTF[g.idx(i, j, k)] = pvtf;
+            PVTFVB[g.idx(i, j, k)] = pw_km12;
+            if (k >= 1)
+                POTTVB[g.idx(i, j, k)] =
+                    (+(pw_km12 - pvtf_km1) * pott_km1 + (pvtf - pw_km12) * pott) /
+                    (pvtf - pvtf_km1);
+            p_km12 = p_kp12;
+            pw_km12 = pw_kp12;
+            pvtf_km1 = pvtf;
+            pott_km1 = pott;
+        }
+        PVTFVB[g.idx(i, j, nz)] = pw_km12;
+        if (nz >= 2) {
+            // extrapolate model top / bottom POTTVB (dyn_diagnostics.py:184-191)
+            const double pott0 = POTT[g.idx(i, j, 0)];
+            POTTVB[g.idx(i, j, 0)] = pott0 - (POTTVB[g.idx(i, j, 1)] - pott0);
+            POTTVB[g.idx(i, j, nz)] = pott_km1 - (POTTVB[g.idx(i, j, nz - 1)] - pott_km1);
+        }
+        // diag_PHI_cpu: bottom-up hydrostatic integral
+        double phivb = HSURF[g.idx2(i, j)] * con_g;
+        PHIVB[g.idx(i, j, nz)] = phivb;
+        for (int k = nz - 1; k >= 0; k--) {
+            const double pott = POTT[g.idx(i, j, k)];
+            const double pvtf = PVTF[g.idx(i, j, k)];
+            const double phi = phivb - con_cp * (pott * (pvtf - PVTFVB[g.idx(i, j, k + 1)]));
+            phivb = phi - con_cp * (pott * (PVTFVB[g.idx(i, j, k)] - pvtf));
+            PHI[g.idx(i, j, k)] = phi;
+            PHIVB[g.idx(i, j, k)] = phivb;
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------
+// secondary diagnostics: dyn_diagnostics.py:199-222.  threads: all columns incl. halos
+// ---------------------------------------------------------------------------------------
+struct SecondaryDiagBody {
+    Geom g;
+    const double *POTTVB, *PVTFVB, *POTT, *PVTF, *UWIND, *VWIND;
+    double *TAIRVB, *PAIRVB, *RHOVB, *TAIR, *PAIR, *RHO, *WINDX, *WINDY, *WIND;
+    DC_HD void operator()(int i, int j) const
+    {
+        const int nz = g.nz;
+        for (int k = 0; k <= nz; k++) {
+            const double pvb = PVTFVB[g.idx(i, j, k)];
+            const double pairvb = 100000. * pow(pvb, 1. / con_kappa);
+            const double tairvb = POTTVB[g.idx(i, j, k)] * pvb;
+            PAIRVB[g.idx(i, j, k)] = pairvb;
+            TAIRVB[g.idx(i, j, k)] = tairvb;
+            RHOVB[g.idx(i, j, k)] = pairvb / (con_Rd * tairvb);
+        }
+        for (int k = 0; k < nz; k++) {
+            const double pv = PVTF[g.idx(i, j, k)];
+            const double tair = POTT[g.idx(i, j, k)] * pv;
+            const double pair = 100000. * pow(pv, 1. / con_kappa);
+            TAIR[g.idx(i, j, k)] = tair;
+            PAIR[g.idx(i, j, k)] = pair;
+            RHO[g.idx(i, j, k)] = pair / (con_Rd * tair);
+            const double wx = (UWIND[g.idx(i, j, k)] + UWIND[g.idx(i + 1, j, k)]) / 2.;
+            const double wy = (VWIND[g.idx(i, j, k)] + VWIND[g.idx(i, j + 1, k)]) / 2.;
+            WINDX[g.idx(i, j, k)] = wx;
+            WINDY[g.idx(i, j, k)] = wy;
+            WIND[g.idx(i, j, k)] = sqrt(wx * wx + wy * wy);
+        }
+    }
+};
+
+}  // namespace dc

@@ -1,0 +1,211 @@
+// dc_point.h -- point functions of the Jacobson-2005 Ch.7 sigma-coordinate scheme.
+// Each keeps the evaluation order of the reference expression it replaces (cited), so a
+// build without FMA contraction (-fmad=false) is bit-identical to the reference's CPU
+// path for everything except pow/log (device libm vs glibc).
+#pragma once
+#include <math.h>
+#include "dc_geom.h"
+
+namespace dc {
+
+// dyn_continuity.py:40-47
+DC_HD double calc_UFLX(double UWIND, double COLP, double COLP_im1, double dyis)
+{
+    return (COLP_im1 + COLP) / 2. * UWIND * dyis;
+}
+DC_HD double calc_VFLX(double VWIND, double COLP, double COLP_jm1, double dxjs)
+{
+    return (COLP_jm1 + COLP) / 2. * VWIND * dxjs;
+}
+DC_HD double calc_FLXDIV(double UFLX, double UFLX_ip1, double VFLX, double VFLX_jp1,
+                         double dsigma, double A)
+{
+    return (+UFLX_ip1 - UFLX + VFLX_jp1 - VFLX) * dsigma / A;
+}
+
+// dyn_functions.py:211-270 (interior interfaces 0 < k < nz).  P_* = COLP_NEW*A*WWIND at
+// the six columns around the velocity point: d = along the wind, p = perpendicular.
+// wall = -1: rigid wall on the pm1 side (p_ind == nb); +1: on the pp1 side (p_ind == np)
+DC_HD double colpa_wwind(double P, double P_dm1, double P_pm1, double P_pp1, double P_pm1_dm1,
+                         double P_pp1_dm1, int wall)
+{
+    // the reference forms the centre-row terms as (2*COLP_NEW)*A*WWIND; scaling by 2 is
+    // exact in binary floating point, so 2*(COLP_NEW*A*WWIND) is the same number
+    if (wall < 0) return 0.25 * (P_pp1_dm1 + P_pp1 + P_dm1 + P);
+    if (wall > 0) return 0.25 * (P_dm1 + P + P_pm1_dm1 + P_pm1);
+    return 0.125 * (P_pp1_dm1 + P_pp1 + 2. * P_dm1 + 2. * P + P_pm1_dm1 + P_pm1);
+}
+DC_HD double interp_ks(double DWIND, double DWIND_km1, double dsigma, double dsigma_km1)
+{
+    return ((dsigma * DWIND_km1 + dsigma_km1 * DWIND) / (dsigma + dsigma_km1));
+}
+
+// dyn_functions.py:429-536 (auxiliary momentum fluxes); u = UFLX, v = VFLX
+DC_HD double calc_CFLX(double v_im1_jm1, double v_jm1, double v_im1, double v, double v_im1_jp1,
+                       double v_jp1)
+{
+    return 1. / 12. * (v_im1_jm1 + v_jm1 + 2. * (v_im1 + v) + v_im1_jp1 + v_jp1);
+}
+DC_HD double calc_QFLX(double u_im1_jm1, double u_im1, double u_jm1, double u, double u_ip1_jm1,
+                       double u_ip1)
+{
+    return 1. / 12. * (u_im1_jm1 + u_im1 + 2. * (u_jm1 + u) + u_ip1_jm1 + u_ip1);
+}
+DC_HD double calc_DFLX(double v_jm1, double v, double v_jp1, double u_jm1, double u,
+                       double u_ip1_jm1, double u_ip1)
+{
+    return 1. / 24. * (v_jm1 + 2. * v + v_jp1 + u_jm1 + u + u_ip1_jm1 + u_ip1);
+}
+DC_HD double calc_EFLX(double v_jm1, double v, double v_jp1, double u_jm1, double u,
+                       double u_ip1_jm1, double u_ip1)
+{
+    return 1. / 24. * (v_jm1 + 2. * v + v_jp1 - u_jm1 - u - u_ip1_jm1 - u_ip1);
+}
+DC_HD double calc_SFLX(double v_im1, double v_im1_jp1, double v, double v_jp1, double u_im1,
+                       double u, double u_ip1)
+{
+    return 1. / 24. * (v_im1 + v_im1_jp1 + v + v_jp1 + u_im1 + 2. * u + u_ip1);
+}
+DC_HD double calc_TFLX(double v_im1, double v_im1_jp1, double v, double v_jp1, double u_im1,
+                       double u, double u_ip1)
+{
+    return 1. / 24. * (v_im1 + v_im1_jp1 + v + v_jp1 - u_im1 - 2. * u - u_ip1);
+}
+DC_HD double calc_BFLX(double u_jm1, double u_ip1_jm1, double u, double u_ip1, double u_jp1,
+                       double u_ip1_jp1)
+{
+    return 1. / 12. * (u_jm1 + u_ip1_jm1 + 2. * (u + u_ip1) + u_jp1 + u_ip1_jp1);
+}
+DC_HD double calc_RFLX(double v_im1, double v_im1_jp1, double v, double v_jp1, double v_ip1,
+                       double v_ip1_jp1)
+{
+    return 1. / 12. * (v_im1 + v_im1_jp1 + 2. * (v + v_jp1) + v_ip1 + v_ip1_jp1);
+}
+
+// dyn_functions.py:541-568
+DC_HD double UVFLX_hor_adv(double DWIND, double DWIND_dm1, double DWIND_dp1, double DWIND_pm1,
+                           double DWIND_pp1, double DWIND_dm1_pm1, double DWIND_dm1_pp1,
+                           double DWIND_dp1_pm1, double DWIND_dp1_pp1, double BRFLX,
+                           double BRFLX_dm1, double CQFLX, double CQFLX_pp1, double DSFLX_dm1,
+                           double DSFLX_pp1, double ETFLX, double ETFLX_dm1_pp1,
+                           double sign_ETFLX_term)
+{
+    return (+BRFLX_dm1 * (DWIND_dm1 + DWIND) / 2. - BRFLX * (DWIND + DWIND_dp1) / 2.
+            + CQFLX * (DWIND_pm1 + DWIND) / 2. - CQFLX_pp1 * (DWIND + DWIND_pp1) / 2.
+            + DSFLX_dm1 * (DWIND_dm1_pm1 + DWIND) / 2. - DSFLX_pp1 * (DWIND + DWIND_dp1_pp1) / 2.
+            + sign_ETFLX_term * (+ETFLX * (DWIND_dp1_pm1 + DWIND) / 2. -
+                                 ETFLX_dm1_pp1 * (DWIND + DWIND_dm1_pp1) / 2.));
+}
+
+// dyn_functions.py:177-207
+DC_HD double pre_grad(double PHI, double PHI_dm1, double COLP, double COLP_dm1, double POTT,
+                      double POTT_dm1, double PVTF, double PVTF_dm1, double PVTFVB,
+                      double PVTFVB_dm1, double PVTFVB_dm1_kp1, double PVTFVB_kp1, double dsigma,
+                      double sigma_vb, double sigma_vb_kp1, double dgrid)
+{
+    return (-dgrid *
+            ((PHI - PHI_dm1) * (COLP + COLP_dm1) / 2. +
+             (COLP - COLP_dm1) * con_cp / 2. *
+                 (+POTT_dm1 / dsigma *
+                      (sigma_vb_kp1 * (PVTFVB_dm1_kp1 - PVTF_dm1) +
+                       sigma_vb * (PVTF_dm1 - PVTFVB_dm1)) +
+                  POTT / dsigma *
+                      (sigma_vb_kp1 * (PVTFVB_kp1 - PVTF) + sigma_vb * (PVTF - PVTFVB)))));
+}
+
+// dyn_functions.py:158-170
+DC_HD double num_dif(double VAR, double VAR_im1, double VAR_ip1, double VAR_jm1, double VAR_jp1,
+                     double VAR_dif_coef)
+{
+    return VAR_dif_coef * (+VAR_im1 + VAR_ip1 + VAR_jm1 + VAR_jp1 - 4. * VAR);
+}
+
+// dyn_UFLX.py:39-66 with cos/sin(lat_is_rad) precomputed per row on the host
+DC_HD double coriolis_UWIND(double COLP, double COLP_im1, double VWIND, double VWIND_im1,
+                            double VWIND_jp1, double VWIND_im1_jp1, double UWIND,
+                            double UWIND_im1, double UWIND_ip1, double corf_is, double cos_lat_is,
+                            double sin_lat_is, double dlon_rad, double dlat_rad)
+{
+    return (con_rE * dlon_rad * dlat_rad / 2. *
+            (COLP_im1 * (VWIND_im1 + VWIND_im1_jp1) / 2. *
+                 (corf_is * con_rE * cos_lat_is + (UWIND_im1 + UWIND) / 2. * sin_lat_is) +
+             COLP * (VWIND + VWIND_jp1) / 2. *
+                 (corf_is * con_rE * cos_lat_is + (UWIND + UWIND_ip1) / 2. * sin_lat_is)));
+}
+
+// dyn_VFLX.py:39-64
+DC_HD double coriolis_VWIND(double COLP, double COLP_jm1, double UWIND, double UWIND_jm1,
+                            double UWIND_ip1, double UWIND_ip1_jm1, double corf, double corf_jm1,
+                            double cos_lat, double sin_lat, double cos_lat_jm1, double sin_lat_jm1,
+                            double dlon_rad, double dlat_rad)
+{
+    return (-con_rE * dlon_rad * dlat_rad / 2. *
+            (COLP_jm1 * (UWIND_jm1 + UWIND_ip1_jm1) / 2. *
+                 (corf_jm1 * con_rE * cos_lat_jm1 +
+                  (UWIND_jm1 + UWIND_ip1_jm1) / 2. * sin_lat_jm1) +
+             COLP * (UWIND + UWIND_ip1) / 2. *
+                 (corf * con_rE * cos_lat + (UWIND + UWIND_ip1) / 2. * sin_lat)));
+}
+
+// dyn_functions.py:105-114
+DC_HD double hor_adv(double VAR, double VAR_im1, double VAR_ip1, double VAR_jm1, double VAR_jp1,
+                     double UFLX, double UFLX_ip1, double VFLX, double VFLX_jp1, double A)
+{
+    return ((+UFLX * (VAR_im1 + VAR) / 2. - UFLX_ip1 * (VAR + VAR_ip1) / 2.
+             + VFLX * (VAR_jm1 + VAR) / 2. - VFLX_jp1 * (VAR + VAR_jp1) / 2.) / A);
+}
+
+// dyn_functions.py:118-136 (k == nz branch unreachable)
+DC_HD double vert_adv(double VARVB, double VARVB_kp1, double WWIND, double WWIND_kp1,
+                      double COLP_NEW, double dsigma, int k)
+{
+    if (k == 0) return COLP_NEW * (-WWIND_kp1 * VARVB_kp1) / dsigma;
+    return COLP_NEW * (+WWIND * VARVB - WWIND_kp1 * VARVB_kp1) / dsigma;
+}
+
+// dyn_functions.py:142-155
+DC_HD double num_dif_pw(double VAR, double VAR_im1, double VAR_ip1, double VAR_jm1,
+                        double VAR_jp1, double COLP, double COLP_im1, double COLP_ip1,
+                        double COLP_jm1, double COLP_jp1, double VAR_dif_coef)
+{
+    return VAR_dif_coef * (+COLP_im1 * VAR_im1 + COLP_ip1 * VAR_ip1 + COLP_jm1 * VAR_jm1 +
+                           COLP_jp1 * VAR_jp1 - 4. * COLP * VAR);
+}
+
+// dyn_functions.py:70-95
+DC_HD double comp_VARVB_log(double VAR, double VAR_km1)
+{
+    const double min_val = 0.0000001;
+    VAR = fmax(VAR, min_val);
+    VAR_km1 = fmax(VAR_km1, min_val);
+    if (VAR_km1 == VAR) return VAR;
+    return ((log(VAR_km1) - log(VAR)) / (1. / VAR - 1. / VAR_km1));
+}
+
+// dyn_timestep.py:34-38
+DC_HD double euler_forward_pw(double VAR, double dVARdt, double COLP, double COLP_OLD, double dt)
+{
+    return VAR * COLP_OLD / COLP + dt * dVARdt / COLP;
+}
+// dyn_timestep.py:40-52
+DC_HD double interp_COLPA_js(double COLP, double COLP_jm1, double COLP_im1, double COLP_ip1,
+                             double COLP_jm1_ip1, double COLP_jm1_im1, double A, double A_jm1)
+{
+    // A depends on the row only: A_im1 = A_ip1 = A, A_jm1_ip1 = A_jm1_im1 = A_jm1
+    return 1. / 8. * (COLP_jm1_ip1 * A_jm1 + COLP_ip1 * A + 2. * COLP_jm1 * A_jm1 +
+                      2. * COLP * A + COLP_jm1_im1 * A_jm1 + COLP_im1 * A);
+}
+// dyn_timestep.py:54-79
+DC_HD double interp_COLPA_is(double COLP, double COLP_im1, double COLP_jm1, double COLP_jp1,
+                             double COLP_im1_jp1, double COLP_im1_jm1, double A, double A_jm1,
+                             double A_jp1, int j, int ny)
+{
+    if (j == 1)
+        return 1. / 4. * (COLP_im1_jp1 * A_jp1 + COLP_jp1 * A_jp1 + COLP_im1 * A + COLP * A);
+    else if (j == ny)
+        return 1. / 4. * (COLP_im1_jm1 * A_jm1 + COLP_jm1 * A_jm1 + COLP_im1 * A + COLP * A);
+    return 1. / 8. * (COLP_im1_jp1 * A_jp1 + COLP_jp1 * A_jp1 + 2. * COLP_im1 * A +
+                      2. * COLP * A + COLP_im1_jm1 * A_jm1 + COLP_jm1 * A_jm1);
+}
+
+}  // namespace dc

@@ -1,0 +1,57 @@
+"""Matsuno predictor/corrector step (reference: dyn_matsuno.py:28-129).
+
+`step_matsuno(GR, F)` advances the device state by one full step with a single C call
+(dc_step_matsuno): OLD <- current, then twice (tendencies -> COLP <- COLP_NEW ->
+pressure-weighted Euler forward -> primary diagnostics), all enqueued on the current torch
+stream with no host round trip.  `step_matsuno_factories` is the same sequence spelled out
+through the factories exactly as the reference's Python does it (kernel-level parity tests).
+"""
+import torch
+
+from . import _lib
+from .dyn_org_discretizations import DiagnosticsFactory, PrognosticsFactory
+from .dyn_tendencies import compute_tendencies
+from .io_read_namelist import B200
+
+Prognostics = PrognosticsFactory(target=B200)
+Diagnostics = DiagnosticsFactory(target=B200)
+
+
+def _bind_all(GR, F):
+    """bind F.device to the handle once per (handle, buffer set)"""
+    key = tuple(t.data_ptr() for t in F.device.values())
+    if F._bound.get('key') != key:
+        L = _lib.lib()
+        h = GR.dyncore()
+        for n, t in F.device.items():
+            _lib.check(L.dc_bind_field(h, F.table[n][0], t.data_ptr(), t.numel() * 8))
+        F._bound['key'] = key
+
+
+def step_matsuno(GR, F, nsteps=1):
+    GR.timer.start('step')
+    _bind_all(GR, F)
+    t = F.device['UWIND']
+    stream = torch.cuda.current_stream(t.device).cuda_stream if t.is_cuda else 0
+    _lib.check(_lib.lib().dc_step_matsuno(GR.dyncore(), int(nsteps), stream))
+    GR.timer.stop('step')
+
+
+def step_matsuno_factories(GR, F):
+    """dyn_matsuno.py:28-129 call for call, on target B200"""
+    d = F.device
+    GR.timer.start('step')
+    for n in ('COLP', 'UWIND', 'VWIND', 'POTT') + (('QV', 'QC') if GR.i_moist_main_switch else ()):
+        d[n + '_OLD'].copy_(d[n])
+    GR.timer.stop('step')
+    for _stage in ('estimate', 'final'):
+        compute_tendencies(GR, F)
+        d['COLP'].copy_(d['COLP_NEW'])
+        GR.timer.start('step')
+        Prognostics.euler_forward(GR, GR.GRF[B200],
+                                  **F.get(Prognostics.fields_prognostic, target=B200))
+        GR.timer.stop('step')
+        GR.timer.start('diag')
+        Diagnostics.primary_diag(GR.GRF[B200],
+                                 **F.get(Diagnostics.fields_primary_diag, target=B200))
+        GR.timer.stop('diag')

@@ -1,0 +1,177 @@
+"""ModelFields (reference: main_fields.py:30-487): registry of model fields, host copies
+in the reference layout (i, j, k) and device buffers in the B200 layout F[k][jd][i]
+(longitude fastest, see csrc/dc_geom.h), with the reference's get/set/copy API.
+
+Device buffers are torch tensors (PyTorch owns the memory); the C library only keeps their
+pointers.  Only the dyn-core fields have device buffers; the physics coupling fields exist
+on the host for API compatibility and must be zero (dry configuration).
+"""
+import weakref
+
+import numpy as np
+import torch
+
+from . import _lib
+from .io_initial_conditions import initialize_fields
+from .io_read_namelist import B200, CPU, GPU, wp
+
+# host-only coupling / physics fields the reference's factories name (stgx, stgy, dimz)
+_HOST_ONLY = {
+    'PSURF': (0, 0, 1), 'KHEAT': (0, 0, 'nzs'), 'KMOM': (0, 0, 'nzs'),
+    'KMOM_dUWINDdz': (1, 0, 'nzs'), 'KMOM_dVWINDdz': (0, 1, 'nzs'),
+    'SMOMXFLX': (0, 0, 1), 'SMOMYFLX': (0, 0, 1), 'SSHFLX': (0, 0, 1), 'SLHFLX': (0, 0, 1),
+    'dPOTTdt_RAD': (0, 0, 'nz'), 'dUFLXdt_TURB': (1, 0, 'nz'), 'dVFLXdt_TURB': (0, 1, 'nz'),
+    'dPOTTdt_TURB': (0, 0, 'nz'), 'dQVdt_TURB': (0, 0, 'nz'),
+}
+# device-buffer address -> Grid that owns the handle the buffer is bound to; lets the
+# factories keep the reference's signatures (which carry no grid object)
+OWNERS = weakref.WeakValueDictionary()
+
+
+def owner_of(fields):
+    for t in fields.values():
+        if isinstance(t, torch.Tensor):
+            GR = OWNERS.get(t.data_ptr())
+            if GR is not None:
+                return GR
+    raise RuntimeError('none of the given tensors was allocated by ModelFields.allocate_device: '
+                       'cannot find the libdyncore handle (target B200 needs F.device tensors)')
+
+
+COUPLING_FIELDS = ['KMOM', 'KHEAT', 'SMOMXFLX', 'SMOMYFLX', 'SSHFLX', 'SLHFLX', 'dPOTTdt_RAD']
+
+
+class ModelFields:
+
+    ALL_FIELDS = 'all_fields'
+    PRINT_DIAG_FIELDS = 'print_diag_fields'
+    NC_OUT_DIAG_FIELDS = 'nc_out_diag_fields'
+    PROGNOSTIC_FIELDS = 'prognostic_fields'
+
+    def __init__(self, GR, gpu_enable=True, device=None, initialize=True, **ic_overrides):
+        self.gpu_enable = gpu_enable
+        self.host, self.fdict = allocate_fields(GR)
+        self.device = {}
+        self.set_field_groups()
+        if device is None:
+            device = 'cuda' if _lib.is_cuda() else 'cpu'
+        self.torch_device = torch.device(device)
+        if _lib.is_cuda() and self.torch_device.type != 'cuda':
+            raise RuntimeError('libdyncore runs on CUDA devices only; there is no CPU fallback')
+        if initialize:
+            initialize_fields(GR, self.host, **ic_overrides)
+            for n in COUPLING_FIELDS:
+                self.host[n][:] = 0.
+        self._bound = {}
+        if gpu_enable:
+            self.allocate_device(GR)
+            self.copy_host_to_device(GR, field_group=self.ALL_FIELDS)
+
+    def set_field_groups(self):
+        self.field_groups = {
+            self.ALL_FIELDS: list(self.host.keys()),
+            self.PRINT_DIAG_FIELDS: ['COLP', 'WIND', 'POTT'],
+            self.NC_OUT_DIAG_FIELDS: ['UWIND', 'VWIND', 'WWIND', 'POTT', 'COLP', 'PVTF',
+                                      'PVTFVB', 'PHI', 'PHIVB', 'RHO', 'QV', 'QC'],
+            self.PROGNOSTIC_FIELDS: ['UWIND', 'VWIND', 'POTT', 'COLP', 'QV', 'QC'],
+        }
+
+    # ------------------------------------------------------------ reference API
+    def get(self, field_names, target=CPU):
+        src = self.host if target == CPU else self.device
+        return {n: src[n] for n in field_names if n in src or target == CPU}
+
+    def set(self, field_dict, target=CPU):
+        dst = self.host if target == CPU else self.device
+        for n, a in field_dict.items():
+            dst[n] = a
+
+    def copy_host_to_device(self, GR, field_group):
+        GR.timer.start('copy')
+        for n in self.field_groups[field_group]:
+            if n in self.device and dict.__contains__(self.host, n):
+                self.to_device(GR, n)
+        GR.timer.stop('copy')
+
+    def copy_device_to_host(self, GR, field_group):
+        GR.timer.start('copy')
+        for n in self.field_groups[field_group]:
+            if n in self.device:
+                self.to_host(GR, n)
+        GR.timer.stop('copy')
+
+    # ------------------------------------------------------------ B200 layout
+    def allocate_device(self, GR):
+        """zero-filled device buffers [nk][NJ][NI] for every field of the library's registry,
+        bound to the handle (dc_bind_field)"""
+        h = GR.dyncore()
+        L = _lib.lib()
+        self.table = _lib.field_table()
+        for n, (fid, sx, sy, nkk) in self.table.items():
+            nk = {_lib.DC_NK_2D: 1, _lib.DC_NK_NZ: int(GR.nz), _lib.DC_NK_NZS: int(GR.nz) + 1}[nkk]
+            t = torch.zeros((nk, GR.NJ, GR.NI), dtype=torch.float64, device=self.torch_device)
+            self.device[n] = t
+            OWNERS[t.data_ptr()] = GR
+            _lib.check(L.dc_bind_field(h, fid, t.data_ptr(), t.numel() * 8))
+
+    def _rows(self, GR, n):
+        """(host j range, device row range) this rank holds of field n: its band plus the
+        halo rows, clipped to the rows the reference array has"""
+        fny = self.host[n].shape[1]
+        j_lo = max(0, GR.j0 - 2)
+        j_hi = min(fny - 1, GR.j1 + 3)
+        j_hi = min(j_hi, GR.NJ - 1 - GR.jshift)
+        return j_lo, j_hi
+
+    def to_device(self, GR, n, staging=None):
+        h = self.host[n]
+        j_lo, j_hi = self._rows(GR, n)
+        src = torch.from_numpy(np.ascontiguousarray(h[:, j_lo:j_hi + 1, :].transpose(2, 1, 0)))
+        if staging is not None:
+            staging[n].copy_(src)
+            src = staging[n]
+        self.device[n][:, j_lo + GR.jshift:j_hi + 1 + GR.jshift, :h.shape[0]].copy_(
+            src, non_blocking=staging is not None)
+
+    def to_host(self, GR, n):
+        h = self.host[n]
+        j_lo, j_hi = self._rows(GR, n)
+        d = self.device[n][:, j_lo + GR.jshift:j_hi + 1 + GR.jshift, :h.shape[0]]
+        h[:, j_lo:j_hi + 1, :] = d.permute(2, 1, 0).cpu().numpy()
+
+
+class _LazyHost(dict):
+    """host field dict that allocates a NaN-filled reference-layout array the first time a
+    name is used (the reference allocates all 93 up front, main_fields.py:477-485; at
+    0.25 deg x 64 levels that would be 0.5 GB per field of host memory never touched)"""
+
+    def __init__(self, shapes):
+        super().__init__()
+        self._shapes = shapes
+
+    def __missing__(self, n):
+        if n not in self._shapes:
+            raise KeyError(n)
+        a = np.full(self._shapes[n], np.nan, dtype=wp)
+        self[n] = a
+        return a
+
+    def __contains__(self, n):
+        return n in self._shapes
+
+    def keys(self):
+        return self._shapes.keys()
+
+
+def allocate_fields(GR):
+    """host arrays in the reference layout, NaN-filled (main_fields.py:218-487)"""
+    fdict, shapes = {}, {}
+    nzmap = {'nz': int(GR.nz), 'nzs': int(GR.nzs), 1: 1}
+    table = {}
+    for n, (fid, sx, sy, nkk) in _lib.field_table().items():
+        table[n] = (sx, sy, {_lib.DC_NK_2D: 1, _lib.DC_NK_NZ: 'nz', _lib.DC_NK_NZS: 'nzs'}[nkk])
+    table.update(_HOST_ONLY)
+    for n, (sx, sy, dz) in table.items():
+        fdict[n] = {'stgx': sx, 'stgy': sy, 'dimz': nzmap[dz], 'dtype': wp}
+        shapes[n] = (int(GR.nx) + 2 + sx, int(GR.ny) + 2 + sy, nzmap[dz])
+    return _LazyHost(shapes), fdict

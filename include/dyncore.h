@@ -1,0 +1,127 @@
+/*
+ * dyncore.h -- C ABI of libdyncore.so, the B200 (sm_100a) dynamical core.
+ *
+ * This is the drop-in boundary for the reference's dynamical-core path: it replaces the
+ * numba kernels behind the `target`-keyed factories of dyn_org_discretizations.py
+ * (TendencyFactory / DiagnosticsFactory / PrognosticsFactory, :75-393) and the Matsuno
+ * stepper dyn_matsuno.py:28-129.  The reference has no C FFI for this path (it is pure
+ * Python + numba); a ctypes binding of these entry points is what a maintainer adds --
+ * see INTEGRATION.md and climate_model_b200/_lib.py.
+ *
+ * Conventions
+ *   - plain C: pointers and sizes only, no torch / C++ types.
+ *   - every call returns 0 on success, a NEGATIVE dc_status on an argument / state error,
+ *     a POSITIVE cudaError_t / ncclResult_t (+1000) on a runtime error; dc_last_error()
+ *     gives the message of the last failure on the calling thread.
+ *   - compute calls enqueue work on the given cudaStream_t (passed as void*, 0 = default
+ *     stream) and return without synchronising; one handle per GPU / rank; a handle is
+ *     not thread-safe.
+ *   - device buffers are OWNED BY THE CALLER (torch tensors on the Python side); the
+ *     library never allocates or frees field memory, it only keeps the bound pointers.
+ *
+ * Device field layout (dc_get_layout): F[k][jd][i], longitude fastest, row pitch NI,
+ * NJ rows per plane, device row jd = global reference row j + jshift; 3-D fields have nz
+ * (or nz+1) planes, 2-D fields one.  The reference layout is (i, j, k) with k fastest
+ * (main_fields.py:477-485); climate_model_b200/main_fields.py converts.
+ */
+#ifndef DYNCORE_H
+#define DYNCORE_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dc_handle dc_handle;
+
+typedef enum {
+    DC_OK = 0,
+    DC_ERR_ARG = -1,       /* NULL / out-of-range argument                     */
+    DC_ERR_SHAPE = -2,     /* buffer too small / grid field not i-invariant    */
+    DC_ERR_UNBOUND = -3,   /* a field the entry needs has not been bound       */
+    DC_ERR_STATE = -4,     /* call not valid in this configuration             */
+    DC_ERR_NO_DEVICE = -5  /* no CUDA device / wrong architecture              */
+} dc_status;
+
+/*
+ * Grid description = what the reference kernels receive as GR.GRF[target] + GR.dt
+ * (main_grid.py:298-315).  All pointers are HOST arrays in the reference layout:
+ * 2-D fields (fnx, fny, 1) C-contiguous, 1-D fields (1, 1, nz[+1]).
+ */
+typedef struct {
+    int nx, ny, nz;          /* main_grid.py:45-52 ; nb == 1                             */
+    int j0, j1;              /* global mass rows owned by this rank, 1 <= j0 <= j1 <= ny;
+                                single GPU: 1, ny                                        */
+    int i_moist;             /* namelist.i_moist_main_switch                             */
+    double dt;               /* GR.dt                                                    */
+    double pair_top;         /* namelist.pair_top                                        */
+    const double *A;         /* (nx+2, ny+2)                                             */
+    const double *dxjs;      /* (nx+2, ny+3)                                             */
+    const double *dyis;      /* (nx+3, ny+2)                                             */
+    const double *corf;      /* (nx+2, ny+2)                                             */
+    const double *corf_is;   /* (nx+3, ny+2)                                             */
+    const double *lat_rad;   /* (nx+2, ny+2)                                             */
+    const double *lat_is_rad;/* (nx+3, ny+2)                                             */
+    const double *dlon_rad;  /* (nx+2, ny+3)                                             */
+    const double *dlat_rad;  /* (nx+3, ny+2)                                             */
+    const double *sigma_vb;  /* (nz+1)                                                   */
+    const double *dsigma;    /* (nz)                                                     */
+    const double *UVFLX_dif_coef, *POTT_dif_coef, *moist_dif_coef; /* (nz)               */
+} dc_grid_desc;
+
+/* kind of vertical extent of a field (dc_field_info) */
+enum { DC_NK_2D = 0, DC_NK_NZ = 1, DC_NK_NZS = 2 };
+
+const char *dc_last_error(void);
+/* 1 when this library runs the kernels on a CUDA device (the product), 0 for the host
+ * emulation harness that the CPU tests build from the same kernel bodies. */
+int dc_is_cuda(void);
+
+/* Grid() + GRF upload (main_grid.py:298-315): builds the per-row / per-level geometry
+ * on the device.  The horizontal grid fields must depend on latitude only. */
+int dc_create(const dc_grid_desc *desc, dc_handle **out);
+int dc_destroy(dc_handle *h);
+
+/* device layout of every field of this handle */
+int dc_get_layout(const dc_handle *h, int *NI, int *NJ, int *jshift);
+
+/* field registry = the dyn-core subset of main_fields.py:233-470 (fdict) */
+int dc_num_fields(void);
+const char *dc_field_name(int field_id);             /* NULL if out of range           */
+int dc_field_id(const char *name);                   /* -1 if unknown                  */
+int dc_field_info(int field_id, int *stgx, int *stgy, int *nk_kind);
+
+/* F.device[name] = buffer (main_fields.py:204-208): nbytes must be >= planes*NJ*NI*8 */
+int dc_bind_field(dc_handle *h, int field_id, void *devptr, size_t nbytes);
+
+/* ---- fine-grained entries: one per factory method of dyn_org_discretizations.py ---- */
+/* TendencyFactory.continuity  (:89-117)  incl. the four exchange_BC calls               */
+int dc_continuity(dc_handle *h, void *stream);
+/* TendencyFactory.momentum    (:121-249) prep + UFLX + VFLX tendencies                  */
+int dc_momentum(dc_handle *h, void *stream);
+/* TendencyFactory.temperature (:253-273)                                                */
+int dc_temperature(dc_handle *h, void *stream);
+/* TendencyFactory.moisture    (:277-294)                                                */
+int dc_moisture(dc_handle *h, void *stream);
+/* dyn_tendencies.compute_tendencies (dyn_tendencies.py:25-72)                           */
+int dc_compute_tendencies(dc_handle *h, void *stream);
+/* PrognosticsFactory.euler_forward (:359-393) incl. the exchange_BC calls               */
+int dc_euler_forward(dc_handle *h, void *stream);
+/* DiagnosticsFactory.primary_diag (:310-326)                                            */
+int dc_primary_diag(dc_handle *h, void *stream);
+/* DiagnosticsFactory.secondary_diag (:329-346)                                          */
+int dc_secondary_diag(dc_handle *h, void *stream);
+/* misc_boundaries.exchange_BC (misc_boundaries.py:22-42) on one bound field             */
+int dc_exchange_bc(dc_handle *h, int field_id, void *stream);
+
+/* ---- coarse entry: dyn_matsuno.step_matsuno (dyn_matsuno.py:28-129), nsteps times ---- */
+int dc_step_matsuno(dc_handle *h, int nsteps, void *stream);
+
+/* number of kernel launches this handle has enqueued so far (bench.py: gpu_launches) */
+long long dc_launch_count(const dc_handle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

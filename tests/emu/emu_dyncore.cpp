@@ -1,0 +1,30 @@
+// emu_dyncore.cpp -- TEST INFRASTRUCTURE ONLY.
+// Host emulation of libdyncore.so: the SAME C ABI implementation (dc_api_impl.h) and the
+// SAME kernel bodies (dc_kernels.h) as the CUDA library, with "device" memory = host
+// memory and a kernel launch = a loop over the thread box.  It lets the CPU test-suite
+// (-m "not gpu") check the index arithmetic, boundary images and host logic of the product
+// without a GPU.  It is never loaded by the product package: climate_model_b200/_lib.py only
+// loads the CUDA library and fails loudly when that is missing.
+#include <stdlib.h>
+#include <string.h>
+
+#define DC_BACKEND_IS_CUDA 0
+
+static int dcb_malloc(void **p, size_t n) { *p = malloc(n); return *p ? 0 : 2; }
+static int dcb_free(void *p) { free(p); return 0; }
+static int dcb_h2d(void *dst, const void *src, size_t n) { memcpy(dst, src, n); return 0; }
+static int dcb_d2d_async(void *dst, const void *src, size_t n, void *) { memcpy(dst, src, n); return 0; }
+static int dcb_last_error() { return 0; }
+static const char *dcb_error_string(int) { return "host emulation"; }
+
+template <class Body>
+static void dcb_launch(const Body &b, int i0, int i1, int j0, int j1, void *)
+{
+    // thread order is irrelevant for a race-free kernel; run rows in DESCENDING order so
+    // that a body that wrongly depended on its neighbours' output would not get the
+    // "natural" sequential answer by accident
+    for (int j = j1; j >= j0; j--)
+        for (int i = i1; i >= i0; i--) b(i, j);
+}
+
+#include "../../climate_model_b200/csrc/dc_api_impl.h"

@@ -1,0 +1,83 @@
+"""Shared test helpers: golden fixtures, the oracle, comparison metrics."""
+import os
+
+import numpy as np
+
+from oracle.oracle import GRID_FIELDS, Oracle
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+STATE = ['UWIND', 'VWIND', 'POTT', 'COLP', 'QV', 'QC']
+
+# parity tolerances, metric max|a-b|/max|b| over the interior (testsuite.py:48-54 of the
+# reference); SURVEY.md section 8(c): >= 20x the measured 1-ulp-perturbation floor
+TOL = {'UWIND': 1e-9, 'VWIND': 1e-9, 'POTT': 1e-12, 'COLP': 1e-12, 'QV': 1e-11, 'QC': 1e-11}
+
+
+def load_golden(name):
+    return np.load(os.path.join(GOLDEN, name))
+
+
+def golden_dims(g):
+    nx, ny, nz, nb, dt = [int(x) for x in g['dims']]
+    assert nb == 1
+    return nx, ny, nz, dt
+
+
+def oracle_from_golden(g, i_moist=True):
+    nx, ny, nz, dt = golden_dims(g)
+    O = Oracle(nx, ny, nz, dt, {n: g['GR_' + n] for n in GRID_FIELDS}, i_moist=i_moist)
+    O.set(**{n: g['IN_' + n] for n in ['HSURF'] + STATE})
+    return O
+
+
+def interior(name, nx, ny):
+    """index box of the cells a field owns (halo cells excluded)"""
+    from oracle.oracle import FIELDS
+    stgx, stgy, _ = FIELDS[name]
+    return (slice(1, nx + 1 + stgx), slice(1, ny + 1 + stgy), slice(None))
+
+
+def rel_err(a, b):
+    """the reference testsuite's metric: max|a-b| / max|b|"""
+    den = np.max(np.abs(b))
+    return float(np.max(np.abs(a - b)) / (den if den > 0 else 1.0))
+
+
+# ---------------------------------------------------------------------------------------
+# product-side helpers (climate_model_b200 on a given libdyncore build)
+# ---------------------------------------------------------------------------------------
+EMU_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'emu')
+
+
+def build_emu():
+    """compile tests/emu/libdyncore_emu.so (host emulation of the kernel bodies)"""
+    import subprocess
+    so = os.path.join(EMU_DIR, 'libdyncore_emu.so')
+    srcs = [os.path.join(EMU_DIR, 'emu_dyncore.cpp')]
+    csrc = os.path.join(os.path.dirname(EMU_DIR), '..', 'climate_model_b200', 'csrc')
+    srcs += [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith('.h')]
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
+        subprocess.check_call(['g++', '-O2', '-std=c++17', '-ffp-contract=off', '-fPIC', '-shared',
+                               '-o', so, srcs[0]])
+    return so
+
+
+def grid_from_golden(g, band=(0, 1), **kw):
+    from climate_model_b200.main_grid import Grid
+    nx, ny, nz, dt = golden_dims(g)
+    arrays = {n: g['GR_' + n] for n in GRID_FIELDS}
+    arrays.update(nx=nx, ny=ny, nz=nz, dt=dt)
+    return Grid(band=band, from_arrays=arrays, **kw)
+
+
+def fields_from_golden(GR, g, prefix='IN_', names=('HSURF',) + tuple(STATE)):
+    """ModelFields whose host state is the golden initial state; coupling fields zero;
+    WWIND / POTTVB zero as io_initial_conditions.py:45-46 leaves them"""
+    from climate_model_b200.main_fields import ModelFields
+    F = ModelFields(GR, gpu_enable=True, initialize=False)
+    for n in names:
+        F.host[n][...] = g[prefix + n]
+    F.host['WWIND'][...] = 0.
+    F.host['POTTVB'][...] = 0.
+    F.copy_host_to_device(GR, F.ALL_FIELDS)
+    return F

@@ -1,0 +1,183 @@
+"""CPU checks of the PRODUCT's host logic and kernel bodies without a GPU.
+
+tests/emu/libdyncore_emu.so is built from the same dc_api_impl.h / dc_kernels.h as the CUDA
+library, with "device" memory = host memory and a launch = a loop over the thread box (in
+descending order).  Loaded through the same ctypes binding and the same Python field /
+factory API, it is compared with the oracle on the reference's golden inputs.  On the
+host the libm is glibc's, and the emulation is compiled without FMA contraction, so the
+comparison is BIT-EXACT -- any index, boundary-image or ordering mistake shows up here.
+(The CUDA build itself is tested by the -m gpu tests.)
+"""
+import numpy as np
+import pytest
+
+from helpers import (STATE, build_emu, fields_from_golden, golden_dims, grid_from_golden,
+                     interior, load_golden, oracle_from_golden)
+
+
+@pytest.fixture(scope='module', autouse=True)
+def emu_library():
+    from climate_model_b200 import _lib
+    prev = _lib.library_path()
+    _lib.use_library(build_emu())
+    assert not _lib.is_cuda()
+    yield
+    if prev:
+        _lib.use_library(prev)
+
+
+@pytest.fixture(scope='module')
+def g10():
+    return load_golden('ref_10deg_rand.npz')
+
+
+def _eq(a, b, what):
+    assert np.array_equal(a, b), '%s: max|diff| = %g' % (what, np.nanmax(np.abs(a - b)))
+
+
+def test_layout_roundtrip(g10):
+    GR = grid_from_golden(g10)
+    F = fields_from_golden(GR, g10)
+    before = {n: F.host[n].copy() for n in ['UWIND', 'VWIND', 'COLP', 'POTT']}
+    for n in before:
+        F.host[n][...] = -1.
+    F.copy_device_to_host(GR, F.ALL_FIELDS)
+    for n, a in before.items():
+        assert np.array_equal(a, F.host[n], equal_nan=True), n
+    # longitude is the fastest axis of the device layout
+    t = F.device['UWIND']
+    assert t.shape == (GR.nz, GR.NJ, GR.NI) and t.stride(2) == 1 and GR.NI % 16 == 0
+
+
+def test_factories_stage1_bit_exact(g10):
+    """every factory (= fine-grained C entry) against the oracle after one compute_tendencies,
+    Euler step and diagnostics"""
+    from climate_model_b200.dyn_matsuno import Diagnostics, Prognostics
+    from climate_model_b200.dyn_tendencies import compute_tendencies
+    from climate_model_b200.io_read_namelist import B200
+    nx, ny, nz, _ = golden_dims(g10)
+    GR = grid_from_golden(g10)
+    F = fields_from_golden(GR, g10)
+    O = oracle_from_golden(g10)
+    O.primary_diag()
+    Diagnostics.primary_diag(GR.GRF[B200], **F.get(Diagnostics.fields_primary_diag, target=B200))
+    F.copy_device_to_host(GR, F.ALL_FIELDS)
+    for n in ['PVTF', 'PVTFVB', 'PHI', 'PHIVB', 'POTTVB']:
+        _eq(F.host[n], O.F[n], n)
+
+    for n in STATE:                          # dyn_matsuno.py:34-49
+        O.F[n + '_OLD'][:] = O.F[n]
+        F.device[n + '_OLD'].copy_(F.device[n])
+    O.compute_tendencies()
+    compute_tendencies(GR, F)
+    F.copy_device_to_host(GR, F.ALL_FIELDS)
+    full = (slice(None),) * 3
+    box = lambda i1, j1: (slice(1, i1 + 1), slice(1, j1 + 1), slice(None))
+    ranges = {
+        'UFLX': full, 'VFLX': full, 'WWIND': full, 'COLP_NEW': full,
+        'FLXDIV': box(nx, ny), 'dCOLPdt': box(nx, ny),
+        'WWIND_UWIND': box(nx + 1, ny), 'WWIND_VWIND': box(nx, ny + 1),
+        'BFLX': box(nx, ny), 'RFLX': box(nx, ny), 'CFLX': box(nx + 1, ny + 1),
+        'QFLX': box(nx + 1, ny + 1), 'DFLX': box(nx, ny + 1), 'EFLX': box(nx, ny + 1),
+        'SFLX': box(nx + 1, ny), 'TFLX': box(nx + 1, ny), 'dUFLXdt': box(nx, ny),
+        'dVFLXdt': (slice(1, nx + 1), slice(2, ny + 1), slice(None)),
+        'dPOTTdt': box(nx, ny), 'dQVdt': box(nx, ny), 'dQCdt': box(nx, ny),
+    }
+    for n, sl in ranges.items():
+        _eq(F.host[n][sl], O.F[n][sl], n)
+
+    O.F['COLP'][:] = O.F['COLP_NEW']
+    F.device['COLP'].copy_(F.device['COLP_NEW'])
+    O.euler_forward()
+    Prognostics.euler_forward(GR, GR.GRF[B200], **F.get(Prognostics.fields_prognostic, target=B200))
+    O.secondary_diag()
+    Diagnostics.secondary_diag(**F.get(Diagnostics.fields_secondary_diag, target=B200))
+    F.copy_device_to_host(GR, F.ALL_FIELDS)
+    for n in STATE:
+        _eq(F.host[n], O.F[n], n)            # whole arrays: the fused BC images too
+    for n in ['TAIR', 'PAIR', 'RHO', 'TAIRVB', 'PAIRVB', 'RHOVB', 'WINDX', 'WINDY', 'WIND']:
+        _eq(F.host[n][interior(n, nx, ny)], O.F[n][interior(n, nx, ny)], n)
+
+
+@pytest.mark.parametrize('fixture,steps', [('ref_10deg_rand.npz', [1, 2, 10]),
+                                           ('ref_5deg.npz', [10])])
+def test_step_matsuno_against_reference_golden(fixture, steps):
+    """the coarse entry (dc_step_matsuno) against the REAL reference's outputs"""
+    from climate_model_b200.dyn_matsuno import Diagnostics, step_matsuno
+    from climate_model_b200.io_read_namelist import B200
+    g = load_golden(fixture)
+    GR = grid_from_golden(g)
+    F = fields_from_golden(GR, g)
+    Diagnostics.primary_diag(GR.GRF[B200], **F.get(Diagnostics.fields_primary_diag, target=B200))
+    done = 0
+    for s in steps:
+        step_matsuno(GR, F, s - done)
+        done = s
+        F.copy_device_to_host(GR, F.PROGNOSTIC_FIELDS)
+        for n in STATE:
+            _eq(F.host[n], g['N%d_%s' % (s, n)], 'N%d %s' % (s, n))
+
+
+def test_factory_path_equals_coarse_entry(g10):
+    from climate_model_b200.dyn_matsuno import (Diagnostics, step_matsuno,
+                                                 step_matsuno_factories)
+    from climate_model_b200.io_read_namelist import B200
+    out = []
+    for stepper in (step_matsuno, step_matsuno_factories):
+        GR = grid_from_golden(g10)
+        F = fields_from_golden(GR, g10)
+        Diagnostics.primary_diag(GR.GRF[B200],
+                                 **F.get(Diagnostics.fields_primary_diag, target=B200))
+        for _ in range(2):
+            stepper(GR, F)
+        F.copy_device_to_host(GR, F.PROGNOSTIC_FIELDS)
+        out.append({n: F.host[n].copy() for n in STATE})
+    for n in STATE:
+        _eq(out[0][n], out[1][n], n)
+
+
+def test_exchange_bc_entry_matches_reference_rule(g10):
+    import ctypes
+    from climate_model_b200 import _lib
+    GR = grid_from_golden(g10)
+    F = fields_from_golden(GR, g10)
+    O = oracle_from_golden(g10)
+    rng = np.random.default_rng(0)
+    L = _lib.lib()
+    for n in ['POTT', 'UWIND', 'VWIND', 'COLP']:
+        a = rng.standard_normal(F.host[n].shape)
+        F.host[n][...] = a
+        F.to_device(GR, n)
+        _lib.check(L.dc_exchange_bc(GR.dyncore(), F.table[n][0], 0))
+        F.to_host(GR, n)
+        ref = a.copy()
+        _lib_o = __import__('oracle.oracle', fromlist=['lib']).lib()
+        _lib_o.orc_exchange_BC.argtypes = [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 3
+        _lib_o.orc_exchange_BC(ctypes.byref(O._g), ref.ctypes.data, *ref.shape)
+        _eq(F.host[n], ref, n)
+
+
+def test_errors_are_loud(g10):
+    from climate_model_b200 import _lib
+    from climate_model_b200.main_grid import Grid
+    GR = grid_from_golden(g10)
+    L = _lib.lib()
+    h = GR.dyncore()
+    with pytest.raises(_lib.DyncoreError, match='not bound'):
+        _lib.check(L.dc_step_matsuno(h, 1, 0))
+    with pytest.raises(_lib.DyncoreError, match='bad field id'):
+        _lib.check(L.dc_bind_field(h, 999, 0, 0))
+    F = fields_from_golden(GR, g10)
+    with pytest.raises(_lib.DyncoreError, match='needs'):
+        _lib.check(L.dc_bind_field(h, F.table['UWIND'][0], F.device['UWIND'].data_ptr(), 8))
+    # a longitude-dependent grid field is rejected
+    arrays = {n: g10['GR_' + n].copy() for n in
+              ['corf', 'corf_is', 'A', 'sigma_vb', 'dsigma', 'dxjs', 'dyis', 'lat_rad',
+               'lat_is_rad', 'dlat_rad', 'dlon_rad', 'POTT_dif_coef', 'UVFLX_dif_coef',
+               'moist_dif_coef']}
+    nx, ny, nz, dt = golden_dims(g10)
+    arrays.update(nx=nx, ny=ny, nz=nz, dt=dt)
+    arrays['A'][3, 4, 0] *= 1.5
+    bad = Grid(from_arrays=arrays)
+    with pytest.raises(_lib.DyncoreError, match='varies with longitude'):
+        bad.dyncore()
