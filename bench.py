@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""bench.py -- dyn-core throughput on B200: cell-updates/s and fraction of the HBM roofline.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg4|cfg2|cfg3|cfg1]
+                  [--moist] [--impl reference]
+
+One "step" = one full Matsuno predictor/corrector step of the dynamical core
+(dyn_matsuno.step_matsuno: OLD copies, 2 x (tendencies, Euler forward, diagnostics, BCs))
+over the whole grid; one cell-update = one mass cell advanced by one such step.
+Default workload = BASELINE.json configs[3]: 0.25 deg x 0.25 deg, 64 sigma levels, synthetic
+initial state (the configuration the north-star target is quoted on; 61.9 M cells, 0.5 GB
+per 3-D field, far larger than L2).  With --gpus N the SAME grid is split into N latitude
+bands (strong scaling), one process per GPU (torchrun), halos exchanged over NCCL.
+
+`--impl reference` times the reference algorithm's CPU implementation (the oracle port,
+oracle/dyncore_oracle.c, OpenMP over all host cores) on a bounded sample of the same
+workload and prints the same JSON line with "impl": "reference".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[0..3]
+    'cfg1': dict(name='5deg x 8 levels (reference testsuite grid), topography',
+                 grid=dict(nz=8, lat0_deg=-80, lat1_deg=80, dlat_deg=5, dlon_deg=5,
+                           i_out_nth_hour=8), ic=dict()),
+    'cfg2': dict(name='1deg x 32 levels, elev.1-deg topography, dry dyn core',
+                 grid=dict(nz=32, lat0_deg=-84, lat1_deg=84, dlat_deg=1.0, dlon_deg=1.0), ic=dict()),
+    'cfg3': dict(name='1deg x 32 levels, elev.1-deg topography, moist tracers (QV, QC)',
+                 grid=dict(nz=32, lat0_deg=-84, lat1_deg=84, dlat_deg=1.0, dlon_deg=1.0), ic=dict(),
+                 moist=True),
+    'cfg4': dict(name='0.25deg x 64 levels, synthetic initial state (no topography), dry dyn core',
+                 grid=dict(nz=64, lat0_deg=-84, lat1_deg=84, dlat_deg=0.25, dlon_deg=0.25,
+                           i_out_nth_hour=1.0), ic=dict(i_use_topo=0)),
+}
+
+# algorithmic bytes per cell-update of the WHOLE step (SURVEY.md 8d counting rule)
+STEP_BYTES = {False: 216, True: 296}
+# algorithmic 3-D field accesses (reads + writes) per cell of each kernel LAUNCH as the step is
+# decomposed today; x 8 B = bytes per cell per launch
+KERNEL_ACCESSES = {
+    'continuity': (5, 5), 'uvflx_prep': (15, 15), 'uflx_tendency': (13, 13),
+    'vflx_tendency': (13, 13), 'pott_tendency': (6, 6), 'moist_tendency': (7, 7),
+    'euler_forward': (9, 15), 'primary_diag': (6, 6), 'copy_old': (6, 10),
+    'stage_fused': (0, 0),
+}
+
+
+def peak_hbm_gbs():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+        except Exception:
+            pass
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region"""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                      '--format=csv,noheader,nounits'], capture_output=True,
+                                     text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(',')])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace('.', '').isdigit())
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
+                                'sw_power_cap'), r[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None,
+                'sm_max_mhz': float(self.rows[0][1]) if self.rows else None,
+                'samples': len(self.rows), 'reasons': sorted(reasons)}
+
+
+def cpu_sample(wl, moist, steps, warmup=1):
+    """the oracle port on a bounded sample of the workload: the SAME grid spacing, levels and
+    initial-state recipe restricted to an equatorial band of <= 84 rows"""
+    import numpy as np
+    from climate_model_b200.main_fields import ModelFields
+    from climate_model_b200.main_grid import Grid
+    from oracle.oracle import GRID_FIELDS, Oracle
+    g = dict(wl['grid'])
+    ny_full = int(round((g['lat1_deg'] - g['lat0_deg']) / g['dlat_deg']))
+    rows = min(ny_full, 84)
+    half = rows * g['dlat_deg'] / 2
+    if rows < ny_full:
+        g['lat0_deg'], g['lat1_deg'] = -half, half
+    GR = Grid(i_moist_main_switch=int(moist), **g)
+    F = ModelFields(GR, gpu_enable=False, device='cpu', **wl['ic'])
+    O = Oracle(GR.nx, GR.ny, GR.nz, GR.dt, {n: GR.GRF['CPU'][n] for n in GRID_FIELDS},
+               i_moist=moist)
+    O.set(**{n: F.host[n] for n in ['HSURF', 'UWIND', 'VWIND', 'POTT', 'COLP', 'QV', 'QC']})
+    O.primary_diag()
+    O.step_matsuno(warmup)
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        O.step_matsuno(1)
+        ts.append(time.perf_counter() - t0)
+    cells = int(GR.nx) * int(GR.ny) * int(GR.nz)
+    assert np.isfinite(O.F['UWIND'][1:-2, 1:-1]).all()
+    sample = '%dx%dx%d band (lat +-%.4g deg) of the workload grid, %d Matsuno steps' % (
+        GR.nx, GR.ny, GR.nz, half if rows < ny_full else g['lat1_deg'], steps)
+    return cells, ts, O.num_threads(), sample
+
+
+def run_reference(args, wl, moist):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cells, ts, threads, sample = cpu_sample(wl, moist, args.steps, max(1, min(args.warmup, 2)))
+    sec = sum(ts) / len(ts)
+    value = cells / sec
+    line = {
+        'impl': 'reference', 'metric': 'dyn-core cell-updates/s', 'value': value,
+        'unit': 'cell-updates/s', 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True,
+        'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': wl['name'], 'moist': moist},
+        'cpu_baseline': {'value': value, 'unit': 'cell-updates/s', 'cores': threads,
+                         'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': 'cell-updates/s', 'h2d_bytes_per_step': 0,
+                'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--workload', default='cfg4', choices=sorted(WORKLOADS))
+    ap.add_argument('--moist', action='store_true')
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--e2e-steps', type=int, default=3)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--emu', action='store_true',
+                    help='debug the bench LOGIC on a box without a GPU against the host emulation '
+                         '(tests/emu); the line is tagged "emu": true and is never a measurement')
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    moist = bool(args.moist or wl.get('moist', False))
+    if args.impl == 'reference':
+        return run_reference(args, wl, moist)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from climate_model_b200 import _lib
+    from climate_model_b200.dyn_matsuno import Diagnostics, step_matsuno
+    from climate_model_b200.io_read_namelist import B200
+    from climate_model_b200.main_fields import ModelFields
+    from climate_model_b200.main_grid import Grid
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.emu:
+        sys.path.insert(0, os.path.join(ROOT, 'tests'))
+        from helpers import build_emu
+        _lib.use_library(build_emu())
+
+        class _Ev:                                       # wall-clock stand-in for CUDA events
+            def __init__(self, enable_timing=True):
+                self.t = 0.
+
+            def record(self):
+                self.t = time.perf_counter()
+
+            def elapsed_time(self, other):
+                return (other.t - self.t) * 1e3
+        torch.cuda.Event = _Ev
+        torch.cuda.synchronize = lambda *a, **k: None
+    else:
+        assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback)'
+        torch.cuda.set_device(local_rank)
+        if world > 1:
+            dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+        _lib.use_library(_lib.DEFAULT_LIBRARY)
+        assert _lib.is_cuda()
+    assert world == args.gpus, '--gpus %d but WORLD_SIZE=%d (launch with torchrun)' % (
+        args.gpus, world)
+
+    GR = Grid(band=(rank, world), i_moist_main_switch=int(moist), **wl['grid'])
+    F = ModelFields(GR, **wl['ic'])
+    if world > 1:
+        from climate_model_b200.parallel_bands import attach_communicator
+        attach_communicator(GR, F)
+    cells = int(GR.nx) * int(GR.ny) * int(GR.nz)
+    Diagnostics.primary_diag(GR.GRF[B200], **F.get(Diagnostics.fields_primary_diag, target=B200))
+    L, h = _lib.lib(), GR.dyncore()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_matsuno(GR, F, 1)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    launches0 = L.dc_launch_count(h)
+    _lib.check(L.dc_profile_enable(h, 1))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step_matsuno(GR, F, 1)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    prof = _lib.profile_read(h)
+    _lib.check(L.dc_profile_enable(h, 0))
+    launches = L.dc_launch_count(h) - launches0
+    clocks = sampler.stop() if sampler else None
+    if world > 1:
+        t = torch.tensor([ms], device=F.torch_device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = cells / (ms_per_step * 1e-3)
+    ok = bool(torch.isfinite(F.device['UWIND']).all().item())
+
+    # ---- end to end through the public field API: host state -> device -> step -> host
+    names = ['UWIND', 'VWIND', 'POTT', 'COLP'] + (['QV', 'QC'] if moist else [])
+    F.copy_device_to_host(GR, F.PROGNOSTIC_FIELDS)
+    h2d = sum(F.host[n].nbytes for n in names)
+    barrier()
+    t_e2e = []
+    for _ in range(args.e2e_steps):
+        barrier()
+        t0 = time.perf_counter()
+        for n in names:
+            F.to_device(GR, n)
+        Diagnostics.primary_diag(GR.GRF[B200],
+                                 **F.get(Diagnostics.fields_primary_diag, target=B200))
+        step_matsuno(GR, F, 1)
+        for n in names:
+            F.to_host(GR, n)
+        barrier()
+        t_e2e.append(time.perf_counter() - t0)
+    e2e_sec = min(t_e2e) if t_e2e else float('nan')
+    if world > 1:
+        t = torch.tensor([e2e_sec], device=F.torch_device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_sec = float(t.item())
+
+    if rank == 0:
+        peak, peak_src = peak_hbm_gbs()
+        # dominant kernel of the step, from the CUDA-event brackets of the timed region
+        kern = {k: v for k, v in prof.items() if v[1] > 0}
+        top = max(kern, key=lambda k: kern[k][0]) if kern else None
+        roof = None
+        if top:
+            acc = KERNEL_ACCESSES.get(top, (0, 0))[1 if moist else 0]
+            k_ms = kern[top][0] / kern[top][1]
+            cells_launch = cells // world
+            bytes_launch = acc * 8 * cells_launch
+            ach = bytes_launch / (k_ms * 1e-3) / 1e9
+            roof = {'bound': 'hbm', 'kernel': top, 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
+                    'frac': ach / peak, 'traffic': None, 'peak_source': peak_src,
+                    'algorithmic_bytes_per_launch': bytes_launch, 'avg_launch_ms': k_ms,
+                    'share_of_step': kern[top][0] / sum(v[0] for v in kern.values())}
+        step_gbs = STEP_BYTES[moist] * value / 1e9
+        line = {
+            **({'emu': True} if args.emu else {}),
+            'metric': 'dyn-core cell-updates/s', 'value': value, 'unit': 'cell-updates/s',
+            'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'strong',
+            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': wl['name'], 'nx': int(GR.nx), 'ny': int(GR.ny),
+                       'nz': int(GR.nz), 'dt_s': int(GR.dt), 'moist': moist,
+                       'parallelism': 'latitude bands x%d' % world,
+                       'l2': 'inputs larger than L2 (%.1f GB state)' % (h2d / 1e9),
+                       'finite': ok},
+            'roofline': roof,
+            'step_roofline': {'bound': 'hbm', 'algorithmic_bytes_per_cell_update': STEP_BYTES[moist],
+                              'achieved': step_gbs / world, 'peak': peak, 'unit': 'GB/s per GPU',
+                              'frac': step_gbs / world / peak},
+            'kernels_ms_per_step': {k: v[0] / args.steps for k, v in sorted(kern.items())},
+            'e2e': {'value': cells / e2e_sec, 'unit': 'cell-updates/s',
+                    'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': h2d,
+                    'ms_per_step': e2e_sec * 1e3,
+                    'what': 'pinned host state -> device (+layout transpose), primary_diag, '
+                            '1 Matsuno step, device -> host state'},
+            'gpu_launches': int(launches),
+            'clocks': clocks,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            c_cells, ts, threads, sample = cpu_sample(wl, moist, steps=3)
+            sec = sum(ts) / len(ts)
+            line['cpu_baseline'] = {'value': c_cells / sec, 'unit': 'cell-updates/s',
+                                    'cores': threads, 'kind': 'port', 'sample': sample}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -58,6 +58,12 @@ def _declare(lib):
         getattr(lib, e).argtypes = [vp, vp]
     lib.dc_exchange_bc.argtypes = [vp, ctypes.c_int, vp]
     lib.dc_step_matsuno.argtypes = [vp, ctypes.c_int, vp]
+    lib.dc_import_field.argtypes = [vp, ctypes.c_int, vp, ctypes.c_size_t, vp]
+    lib.dc_export_field.argtypes = [vp, ctypes.c_int, vp, ctypes.c_size_t, vp]
+    lib.dc_profile_enable.argtypes = [vp, ctypes.c_int]
+    lib.dc_profile_read.argtypes = [vp, ctypes.c_int, ctypes.POINTER(ctypes.c_char_p),
+                                    ctypes.POINTER(ctypes.c_double),
+                                    ctypes.POINTER(ctypes.c_longlong)]
     lib.dc_launch_count.argtypes = [vp]
     lib.dc_launch_count.restype = ctypes.c_longlong
     for opt in ('dc_set_band_comm', 'dc_halo_exchange'):
@@ -108,3 +114,12 @@ def field_table():
         check(L.dc_field_info(i, ctypes.byref(sx), ctypes.byref(sy), ctypes.byref(nk)))
         out[L.dc_field_name(i).decode()] = (i, sx.value, sy.value, nk.value)
     return out
+
+
+def profile_read(handle, max_entries=64):
+    """{kernel name: (total ms, launches)} since the last read (dc_profile_read)"""
+    names = (ctypes.c_char_p * max_entries)()
+    ms = (ctypes.c_double * max_entries)()
+    n = (ctypes.c_longlong * max_entries)()
+    cnt = lib().dc_profile_read(handle, max_entries, names, ms, n)
+    return {names[i].decode(): (ms[i], n[i]) for i in range(cnt)}

@@ -11,6 +11,11 @@
 //   const char *dcb_error_string(int code);
 //   template <class Body> void dcb_launch(const Body &b, int i0, int i1, int j0, int j1,
 //                                         void *stream);   // body(i, j) for the closed box
+//   void dcb_transpose(const dc::Geom &g, double *ref, double *dev, int fnx, int fny,
+//                      int nk, int j_lo, int j_hi, int to_device, void *stream);
+//   void dcb_profile_begin(dc_handle *h, const char *name, void *stream);
+//   void dcb_profile_end(dc_handle *h, void *stream);
+//   int  dcb_profile_read(dc_handle *h, int max, const char **names, double *ms, long long *n);
 #pragma once
 #include <math.h>
 #include <stdarg.h>
@@ -79,6 +84,8 @@ struct dc_handle {
     dc::Fields f;
     void *geom_buf;       // one device allocation holding all per-row / per-level arrays
     long long launches;
+    int profiling;
+    void *profile_state;  // backend-owned
     double **slot(int id) { return reinterpret_cast<double **>(&f) + id; }
     double *const *slot(int id) const { return reinterpret_cast<double *const *>(&f) + id; }
 };
@@ -112,10 +119,13 @@ static int need(const dc_handle *h, const char *entry, const std::vector<int> &i
 }
 
 template <class Body>
-static void launch(dc_handle *h, const Body &b, int i0, int i1, int j0, int j1, void *stream)
+static void launch(dc_handle *h, const char *name, const Body &b, int i0, int i1, int j0, int j1,
+                   void *stream)
 {
     if (i1 < i0 || j1 < j0) return;
+    if (h->profiling) dcb_profile_begin(h, name, stream);
     dcb_launch(b, i0, i1, j0, j1, stream);
+    if (h->profiling) dcb_profile_end(h, stream);
     h->launches++;
 }
 
@@ -144,11 +154,11 @@ static int do_continuity(dc_handle *h, bool store_flxdiv, void *stream)
     if (store_flxdiv) {
         ContinuityBody<true> b{g,      f.UWIND,  f.VWIND, f.COLP,     f.COLP_OLD, f.UFLX,
                                f.VFLX, f.FLXDIV, f.WWIND, f.COLP_NEW, f.dCOLPdt};
-        launch(h, b, 1, g.nx, 1, g.ny, stream);
+        launch(h, "continuity", b, 1, g.nx, 1, g.ny, stream);
     } else {
         ContinuityBody<false> b{g,      f.UWIND,  f.VWIND, f.COLP,     f.COLP_OLD, f.UFLX,
                                 f.VFLX, f.FLXDIV, f.WWIND, f.COLP_NEW, f.dCOLPdt};
-        launch(h, b, 1, g.nx, 1, g.ny, stream);
+        launch(h, "continuity", b, 1, g.nx, 1, g.ny, stream);
     }
     return DC_OK;
 }
@@ -159,13 +169,13 @@ static int do_momentum(dc_handle *h, void *stream)
     const Geom &g = h->g;
     PrepBody p{g,      f.UWIND, f.VWIND, f.WWIND, f.UFLX, f.VFLX, f.COLP_NEW, f.WWIND_UWIND,
                f.WWIND_VWIND, f.BFLX, f.CFLX, f.DFLX, f.EFLX, f.RFLX, f.QFLX, f.SFLX, f.TFLX};
-    launch(h, p, 1, g.nx + 1, 1, g.ny + 1, stream);
+    launch(h, "uvflx_prep", p, 1, g.nx + 1, 1, g.ny + 1, stream);
     UFLXTendencyBody u{g,      f.UFLX, f.UWIND, f.VWIND, f.BFLX,   f.CFLX,        f.DFLX, f.EFLX,
                        f.PHI,  f.COLP, f.POTT,  f.PVTF,  f.PVTFVB, f.WWIND_UWIND, f.dUFLXdt};
-    launch(h, u, 1, g.nx, 1, g.ny, stream);
+    launch(h, "uflx_tendency", u, 1, g.nx, 1, g.ny, stream);
     VFLXTendencyBody v{g,      f.VFLX, f.UWIND, f.VWIND, f.RFLX,   f.SFLX,        f.TFLX, f.QFLX,
                        f.PHI,  f.COLP, f.POTT,  f.PVTF,  f.PVTFVB, f.WWIND_VWIND, f.dVFLXdt};
-    launch(h, v, 1, g.nx, 2, g.ny, stream);
+    launch(h, "vflx_tendency", v, 1, g.nx, 2, g.ny, stream);
     return DC_OK;
 }
 
@@ -175,7 +185,7 @@ static int do_temperature(dc_handle *h, void *stream)
     const Geom &g = h->g;
     POTTTendencyBody b{g, f.POTT, f.UFLX, f.VFLX, f.COLP, f.POTTVB, f.WWIND, f.COLP_NEW,
                        f.dPOTTdt};
-    launch(h, b, 1, g.nx, 1, g.ny, stream);
+    launch(h, "pott_tendency", b, 1, g.nx, 1, g.ny, stream);
     return DC_OK;
 }
 
@@ -186,7 +196,7 @@ static int do_moisture(dc_handle *h, void *stream)
     if (!g.i_moist) return DC_OK;
     MoistTendencyBody b{g, f.QV, f.QC, f.UFLX, f.VFLX, f.COLP, f.WWIND, f.COLP_NEW, f.dQVdt,
                         f.dQCdt};
-    launch(h, b, 1, g.nx, 1, g.ny, stream);
+    launch(h, "moist_tendency", b, 1, g.nx, 1, g.ny, stream);
     return DC_OK;
 }
 
@@ -197,7 +207,7 @@ static int do_euler_forward(dc_handle *h, void *stream)
     TimestepBody b{g,         f.COLP,    f.COLP_OLD, f.UWIND_OLD, f.dUFLXdt, f.VWIND_OLD,
                    f.dVFLXdt, f.POTT_OLD, f.dPOTTdt, f.QV_OLD,    f.dQVdt,   f.QC_OLD,
                    f.dQCdt,   f.UWIND,   f.VWIND,    f.POTT,      f.QV,      f.QC};
-    launch(h, b, 1, g.nx, 1, g.ny, stream);
+    launch(h, "euler_forward", b, 1, g.nx, 1, g.ny, stream);
     return DC_OK;
 }
 
@@ -206,7 +216,7 @@ static int do_primary_diag(dc_handle *h, void *stream)
     const Fields &f = h->f;
     const Geom &g = h->g;
     PrimaryDiagBody b{g, f.COLP, f.POTT, f.HSURF, f.PVTF, f.PVTFVB, f.PHI, f.PHIVB, f.POTTVB};
-    launch(h, b, 0, g.nx + 1, 0, g.ny + 1, stream);
+    launch(h, "primary_diag", b, 0, g.nx + 1, 0, g.ny + 1, stream);
     return DC_OK;
 }
 
@@ -363,6 +373,8 @@ int dc_create(const dc_grid_desc *d, dc_handle **out)
     g.sigma_vb = dl; g.dsigma = dl + (nz + 1); g.UVFLX_dif_coef = dl + 2 * (nz + 1);
     g.POTT_dif_coef = dl + 3 * (nz + 1); g.moist_dif_coef = dl + 4 * (nz + 1);
     h->launches = 0;
+    h->profiling = 0;
+    h->profile_state = nullptr;
     *out = h;
     return DC_OK;
 }
@@ -397,6 +409,64 @@ int dc_bind_field(dc_handle *h, int id, void *devptr, size_t nbytes)
 }
 
 long long dc_launch_count(const dc_handle *h) { return h ? h->launches : 0; }
+
+int dc_profile_enable(dc_handle *h, int on)
+{
+    if (!h) return fail(DC_ERR_ARG, "dc_profile_enable: NULL handle");
+    h->profiling = on ? 1 : 0;
+    return DC_OK;
+}
+
+int dc_profile_read(dc_handle *h, int max_entries, const char **names, double *ms,
+                    long long *launches)
+{
+    if (!h || !names || !ms || !launches || max_entries <= 0) {
+        fail(DC_ERR_ARG, "dc_profile_read: bad argument");
+        return 0;
+    }
+    return dcb_profile_read(h, max_entries, names, ms, launches);
+}
+
+// rows of a reference-layout array (fny rows) that this rank's band holds
+static void held_rows(const Geom &g, int fny, int *j_lo, int *j_hi)
+{
+    *j_lo = g.j0 - HJ < 0 ? 0 : g.j0 - HJ;
+    *j_hi = g.j1 + HJ + 1 > fny - 1 ? fny - 1 : g.j1 + HJ + 1;
+}
+
+static int do_transpose(dc_handle *h, int id, void *ref, size_t nbytes, int to_device,
+                        void *stream, const char *what)
+{
+    if (!h || !ref) return fail(DC_ERR_ARG, "%s: NULL argument", what);
+    if (id < 0 || id >= F_COUNT) return fail(DC_ERR_ARG, "%s: bad field id %d", what, id);
+    int rc;
+    if ((rc = need(h, what, {id}))) return rc;
+    const Geom &g = h->g;
+    const FieldInfo &fi = g_field_info[id];
+    const int fnx = g.nx + 2 + fi.stgx, fny = g.ny + 2 + fi.stgy, nk = nk_of(g, id);
+    const size_t need_bytes = (size_t)fnx * fny * nk * sizeof(double);
+    if (nbytes < need_bytes)
+        return fail(DC_ERR_SHAPE, "%s: %s needs a %zu-byte reference-layout buffer, got %zu",
+                    what, fi.name, need_bytes, nbytes);
+    int j_lo, j_hi;
+    held_rows(g, fny, &j_lo, &j_hi);
+    if (h->profiling) dcb_profile_begin(h, to_device ? "import_field" : "export_field", stream);
+    dcb_transpose(g, static_cast<double *>(ref), *h->slot(id), fnx, fny, nk, j_lo, j_hi,
+                  to_device, stream);
+    if (h->profiling) dcb_profile_end(h, stream);
+    h->launches++;
+    return backend_status(what);
+}
+
+int dc_import_field(dc_handle *h, int id, const void *ref, size_t nbytes, void *stream)
+{
+    return do_transpose(h, id, const_cast<void *>(ref), nbytes, 1, stream, "dc_import_field");
+}
+
+int dc_export_field(dc_handle *h, int id, void *ref, size_t nbytes, void *stream)
+{
+    return do_transpose(h, id, ref, nbytes, 0, stream, "dc_export_field");
+}
 
 #define DC_ENTRY_CHECK(name)                                                     \
     if (!h) return fail(DC_ERR_ARG, name ": NULL handle");                       \
@@ -481,7 +551,7 @@ int dc_secondary_diag(dc_handle *h, void *stream)
     const Fields &f = h->f;
     SecondaryDiagBody b{h->g,  f.POTTVB, f.PVTFVB, f.POTT, f.PVTF, f.UWIND, f.VWIND, f.TAIRVB,
                         f.PAIRVB, f.RHOVB, f.TAIR, f.PAIR, f.RHO,  f.WINDX, f.WINDY, f.WIND};
-    launch(h, b, 0, h->g.nx + 1, 0, h->g.ny + 1, stream);
+    launch(h, "secondary_diag", b, 0, h->g.nx + 1, 0, h->g.ny + 1, stream);
     return backend_status("dc_secondary_diag");
 }
 
@@ -496,7 +566,7 @@ int dc_exchange_bc(dc_handle *h, int id, void *stream)
         return fail(DC_ERR_STATE, "dc_exchange_bc: %s is staggered in x and y; the reference "
                                   "never exchanges such a field", fi.name);
     ExchangeBCBody b{h->g, *h->slot(id), fi.stgx | (fi.stgy << 1), nk_of(h->g, id)};
-    launch(h, b, 1, h->g.nx, 1, h->g.ny + (fi.stgy ? 1 : 0), stream);
+    launch(h, "exchange_bc", b, 1, h->g.nx, 1, h->g.ny + (fi.stgy ? 1 : 0), stream);
     return backend_status("dc_exchange_bc");
 }
 
@@ -518,6 +588,7 @@ int dc_step_matsuno(dc_handle *h, int nsteps, void *stream)
     const size_t b2 = g.plane * sizeof(double), b3 = b2 * g.nz;
     for (int s = 0; s < nsteps; s++) {
         // dyn_matsuno.py:34-49: OLD <- current
+        if (h->profiling) dcb_profile_begin(h, "copy_old", stream);
         dcb_d2d_async(f.COLP_OLD, f.COLP, b2, stream);
         dcb_d2d_async(f.UWIND_OLD, f.UWIND, b3, stream);
         dcb_d2d_async(f.VWIND_OLD, f.VWIND, b3, stream);
@@ -526,6 +597,7 @@ int dc_step_matsuno(dc_handle *h, int nsteps, void *stream)
             dcb_d2d_async(f.QV_OLD, f.QV, b3, stream);
             dcb_d2d_async(f.QC_OLD, f.QC, b3, stream);
         }
+        if (h->profiling) dcb_profile_end(h, stream);
         for (int stage = 0; stage < 2; stage++) {  // estimate, final
             do_continuity(h, false, stream);
             do_momentum(h, stream);

@@ -8,6 +8,8 @@
 // -fmad=false keeps the reference's evaluation order (numba emits no FMA contraction).
 #include <cuda_runtime.h>
 
+#include "dc_geom.h"
+
 #define DC_BACKEND_IS_CUDA 1
 
 static int dcb_malloc(void **p, size_t n) { return (int)cudaMalloc(p, n); }
@@ -43,4 +45,136 @@ static void dcb_launch(const Body &b, int i0, int i1, int j0, int j1, void *stre
     dc::k_columns<Body><<<grid, block, 0, (cudaStream_t)stream>>>(b, i0, i1, j0, j1);
 }
 
+// ---------------------------------------------------------------------------------------
+// layout conversion: reference (i, j, k) k-fastest  <->  device F[k][jd][i] i-fastest.
+// For every row j a tiled (i, k) transpose through shared memory so that both the read
+// and the write side are coalesced.
+// ---------------------------------------------------------------------------------------
+namespace dc {
+constexpr int TT = 32, TR = 8;
+
+template <bool TO_DEVICE>
+__global__ void __launch_bounds__(TT *TR)
+    k_transpose(const Geom g, double *__restrict__ ref, double *__restrict__ dev, int fnx,
+                int fny, int nk, int j_lo)
+{
+    __shared__ double tile[TT][TT + 1];
+    const int j = j_lo + blockIdx.z;
+    const int i0 = blockIdx.x * TT, k0 = blockIdx.y * TT;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    if (TO_DEVICE) {
+        for (int r = ty; r < TT; r += TR) {  // read ref: k along threadIdx.x
+            const int i = i0 + r, k = k0 + tx;
+            if (i < fnx && k < nk) tile[r][tx] = ref[((size_t)i * fny + j) * nk + k];
+        }
+        __syncthreads();
+        for (int r = ty; r < TT; r += TR) {  // write dev: i along threadIdx.x
+            const int i = i0 + tx, k = k0 + r;
+            if (i < fnx && k < nk) dev[g.idx(i, j, k)] = tile[tx][r];
+        }
+    } else {
+        for (int r = ty; r < TT; r += TR) {
+            const int i = i0 + tx, k = k0 + r;
+            if (i < fnx && k < nk) tile[r][tx] = dev[g.idx(i, j, k)];
+        }
+        __syncthreads();
+        for (int r = ty; r < TT; r += TR) {
+            const int i = i0 + r, k = k0 + tx;
+            if (i < fnx && k < nk) ref[((size_t)i * fny + j) * nk + k] = tile[tx][r];
+        }
+    }
+}
+}  // namespace dc
+
+static void dcb_transpose(const dc::Geom &g, double *ref, double *dev, int fnx, int fny, int nk,
+                          int j_lo, int j_hi, int to_device, void *stream)
+{
+    if (j_hi < j_lo) return;
+    dim3 block(dc::TT, dc::TR);
+    dim3 grid((fnx + dc::TT - 1) / dc::TT, (nk + dc::TT - 1) / dc::TT, j_hi - j_lo + 1);
+    if (to_device)
+        dc::k_transpose<true><<<grid, block, 0, (cudaStream_t)stream>>>(g, ref, dev, fnx, fny, nk,
+                                                                        j_lo);
+    else
+        dc::k_transpose<false><<<grid, block, 0, (cudaStream_t)stream>>>(g, ref, dev, fnx, fny,
+                                                                         nk, j_lo);
+}
+
+// ---------------------------------------------------------------------------------------
+// per-kernel timing with CUDA events on the launching stream
+// ---------------------------------------------------------------------------------------
+#include <map>
+#include <string>
+#include <vector>
+struct dc_handle;
+namespace dc {
+struct ProfileRec {
+    const char *name;
+    cudaEvent_t a, b;
+};
+struct ProfileState {
+    std::vector<ProfileRec> recs;
+    std::vector<cudaEvent_t> pool;
+    std::vector<std::string> names;  // storage for dc_profile_read's returned strings
+    cudaEvent_t get()
+    {
+        if (!pool.empty()) {
+            cudaEvent_t e = pool.back();
+            pool.pop_back();
+            return e;
+        }
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        return e;
+    }
+};
+}  // namespace dc
+static void dcb_profile_begin(dc_handle *h, const char *name, void *stream);
+static void dcb_profile_end(dc_handle *h, void *stream);
+static int dcb_profile_read(dc_handle *h, int max, const char **names, double *ms, long long *n);
+
 #include "dc_api_impl.h"
+
+static dc::ProfileState *pstate(dc_handle *h)
+{
+    if (!h->profile_state) h->profile_state = new dc::ProfileState();
+    return static_cast<dc::ProfileState *>(h->profile_state);
+}
+static void dcb_profile_begin(dc_handle *h, const char *name, void *stream)
+{
+    dc::ProfileState *p = pstate(h);
+    dc::ProfileRec r{name, p->get(), p->get()};
+    cudaEventRecord(r.a, (cudaStream_t)stream);
+    p->recs.push_back(r);
+}
+static void dcb_profile_end(dc_handle *h, void *stream)
+{
+    cudaEventRecord(pstate(h)->recs.back().b, (cudaStream_t)stream);
+}
+static int dcb_profile_read(dc_handle *h, int max, const char **names, double *ms, long long *n)
+{
+    dc::ProfileState *p = pstate(h);
+    cudaDeviceSynchronize();
+    std::map<std::string, std::pair<double, long long>> acc;
+    for (const dc::ProfileRec &r : p->recs) {
+        float t = 0.f;
+        cudaEventElapsedTime(&t, r.a, r.b);
+        auto &e = acc[r.name];
+        e.first += t;
+        e.second += 1;
+        p->pool.push_back(r.a);
+        p->pool.push_back(r.b);
+    }
+    p->recs.clear();
+    p->names.clear();
+    for (auto &kv : acc) p->names.push_back(kv.first);
+    int i = 0;
+    for (auto &kv : acc) {
+        if (i >= max) break;
+        names[i] = p->names[i].c_str();
+        ms[i] = kv.second.first;
+        n[i] = kv.second.second;
+        i++;
+    }
+    return i;
+}

@@ -56,7 +56,7 @@ class ModelFields:
         if device is None:
             device = 'cuda' if _lib.is_cuda() else 'cpu'
         self.torch_device = torch.device(device)
-        if _lib.is_cuda() and self.torch_device.type != 'cuda':
+        if gpu_enable and _lib.is_cuda() and self.torch_device.type != 'cuda':
             raise RuntimeError('libdyncore runs on CUDA devices only; there is no CPU fallback')
         if initialize:
             initialize_fields(GR, self.host, **ic_overrides)
@@ -114,30 +114,40 @@ class ModelFields:
             OWNERS[t.data_ptr()] = GR
             _lib.check(L.dc_bind_field(h, fid, t.data_ptr(), t.numel() * 8))
 
-    def _rows(self, GR, n):
-        """(host j range, device row range) this rank holds of field n: its band plus the
-        halo rows, clipped to the rows the reference array has"""
-        fny = self.host[n].shape[1]
-        j_lo = max(0, GR.j0 - 2)
-        j_hi = min(fny - 1, GR.j1 + 3)
-        j_hi = min(j_hi, GR.NJ - 1 - GR.jshift)
-        return j_lo, j_hi
+    def _stage(self, nelem):
+        """device scratch holding one field in the reference layout (raw copy of the host
+        array); dc_import_field / dc_export_field transpose between it and the bound field"""
+        if getattr(self, '_staging', None) is None or self._staging.numel() < nelem:
+            self._staging = torch.empty(nelem, dtype=torch.float64, device=self.torch_device)
+        return self._staging[:nelem]
 
-    def to_device(self, GR, n, staging=None):
+    def _stream(self):
+        if self.torch_device.type == 'cuda':
+            return torch.cuda.current_stream(self.torch_device).cuda_stream
+        return 0
+
+    def to_device(self, GR, n):
+        """host (i, j, k) -> device F[k][jd][i]: one contiguous H2D copy (asynchronous when the
+        host array is pinned) + an on-device tiled transpose (dc_import_field)"""
         h = self.host[n]
-        j_lo, j_hi = self._rows(GR, n)
-        src = torch.from_numpy(np.ascontiguousarray(h[:, j_lo:j_hi + 1, :].transpose(2, 1, 0)))
-        if staging is not None:
-            staging[n].copy_(src)
-            src = staging[n]
-        self.device[n][:, j_lo + GR.jshift:j_hi + 1 + GR.jshift, :h.shape[0]].copy_(
-            src, non_blocking=staging is not None)
+        src = torch.from_numpy(h).view(-1)
+        st = self._stage(src.numel())
+        st.copy_(src, non_blocking=True)
+        _lib.check(_lib.lib().dc_import_field(GR.dyncore(), self.table[n][0], st.data_ptr(),
+                                              st.numel() * 8, self._stream()))
 
     def to_host(self, GR, n):
+        """device -> host, the reverse of to_device; synchronises the stream at the end"""
         h = self.host[n]
-        j_lo, j_hi = self._rows(GR, n)
-        d = self.device[n][:, j_lo + GR.jshift:j_hi + 1 + GR.jshift, :h.shape[0]]
-        h[:, j_lo:j_hi + 1, :] = d.permute(2, 1, 0).cpu().numpy()
+        dst = torch.from_numpy(h).view(-1)
+        st = self._stage(dst.numel())
+        if GR.band[1] > 1:
+            st.copy_(dst, non_blocking=True)      # rows of other ranks keep their host values
+        _lib.check(_lib.lib().dc_export_field(GR.dyncore(), self.table[n][0], st.data_ptr(),
+                                              st.numel() * 8, self._stream()))
+        dst.copy_(st, non_blocking=True)
+        if self.torch_device.type == 'cuda':
+            torch.cuda.current_stream(self.torch_device).synchronize()
 
 
 class _LazyHost(dict):
@@ -145,16 +155,34 @@ class _LazyHost(dict):
     name is used (the reference allocates all 93 up front, main_fields.py:477-485; at
     0.25 deg x 64 levels that would be 0.5 GB per field of host memory never touched)"""
 
-    def __init__(self, shapes):
+    def __init__(self, shapes, pin=False):
         super().__init__()
         self._shapes = shapes
+        self._pin = pin
+        self._pinned = {}
 
     def __missing__(self, n):
         if n not in self._shapes:
             raise KeyError(n)
-        a = np.full(self._shapes[n], np.nan, dtype=wp)
+        if self._pin:
+            # page-locked host memory: H2D / D2H copies run asynchronously at full PCIe rate
+            t = torch.empty(self._shapes[n], dtype=torch.float64, pin_memory=True)
+            t.fill_(float('nan'))
+            self._pinned[n] = t
+            a = t.numpy()
+        else:
+            a = np.full(self._shapes[n], np.nan, dtype=wp)
         self[n] = a
         return a
+
+    def __setitem__(self, n, a):
+        # keep the (possibly pinned) buffer: assignments of a same-shaped array copy into it
+        if dict.__contains__(self, n) and dict.__getitem__(self, n) is not a:
+            cur = dict.__getitem__(self, n)
+            if getattr(a, 'shape', None) == cur.shape:
+                cur[...] = a
+                return
+        super().__setitem__(n, a)
 
     def __contains__(self, n):
         return n in self._shapes
@@ -174,4 +202,4 @@ def allocate_fields(GR):
     for n, (sx, sy, dz) in table.items():
         fdict[n] = {'stgx': sx, 'stgy': sy, 'dimz': nzmap[dz], 'dtype': wp}
         shapes[n] = (int(GR.nx) + 2 + sx, int(GR.ny) + 2 + sy, nzmap[dz])
-    return _LazyHost(shapes), fdict
+    return _LazyHost(shapes, pin=_lib.is_cuda() and torch.cuda.is_available()), fdict

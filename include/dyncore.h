@@ -118,8 +118,24 @@ int dc_exchange_bc(dc_handle *h, int field_id, void *stream);
 /* ---- coarse entry: dyn_matsuno.step_matsuno (dyn_matsuno.py:28-129), nsteps times ---- */
 int dc_step_matsuno(dc_handle *h, int nsteps, void *stream);
 
+/* ---- layout conversion on the device (F.copy_host_to_device / copy_device_to_host,
+ *      main_fields.py:204-215): `ref` is a DEVICE buffer holding the field in the
+ *      reference layout (fnx, fny, nk) with k fastest, i.e. a raw byte copy of the host
+ *      array; import transposes it into the bound field (rows this rank holds), export
+ *      does the reverse.  nbytes = size of `ref`. ---- */
+int dc_import_field(dc_handle *h, int field_id, const void *ref, size_t nbytes, void *stream);
+int dc_export_field(dc_handle *h, int field_id, void *ref, size_t nbytes, void *stream);
+
 /* number of kernel launches this handle has enqueued so far (bench.py: gpu_launches) */
 long long dc_launch_count(const dc_handle *h);
+
+/* ---- per-kernel device timing (bench.py roofline): when enabled, every kernel launch is
+ *      bracketed by CUDA events on its stream.  dc_profile_read synchronises the device,
+ *      adds up the elapsed times per kernel and resets the event list.
+ *      names[i] / ms[i] / launches[i] for i < return value (<= max_entries). ---- */
+int dc_profile_enable(dc_handle *h, int on);
+int dc_profile_read(dc_handle *h, int max_entries, const char **names, double *ms,
+                    long long *launches);
 
 #ifdef __cplusplus
 }

@@ -27,4 +27,21 @@ static void dcb_launch(const Body &b, int i0, int i1, int j0, int j1, void *)
         for (int i = i1; i >= i0; i--) b(i, j);
 }
 
+#include "../../climate_model_b200/csrc/dc_geom.h"
+static void dcb_transpose(const dc::Geom &g, double *ref, double *dev, int fnx, int fny, int nk,
+                          int j_lo, int j_hi, int to_device, void *)
+{
+    for (int i = 0; i < fnx; i++)
+        for (int j = j_lo; j <= j_hi; j++)
+            for (int k = 0; k < nk; k++) {
+                double &r = ref[((size_t)i * fny + j) * nk + k];
+                double &d = dev[g.idx(i, j, k)];
+                if (to_device) d = r; else r = d;
+            }
+}
+struct dc_handle;
+static void dcb_profile_begin(dc_handle *, const char *, void *) {}
+static void dcb_profile_end(dc_handle *, void *) {}
+static int dcb_profile_read(dc_handle *, int, const char **, double *, long long *) { return 0; }
+
 #include "../../climate_model_b200/csrc/dc_api_impl.h"

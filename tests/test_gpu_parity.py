@@ -1,0 +1,215 @@
+"""GPU parity tests: the CUDA library (libdyncore.so, sm_100a) through the C ABI / Python
+factory API against the oracle and the reference's golden vectors.
+
+Tolerances (metric max|a-b|/max|b| over whole arrays, the reference testsuite's metric,
+testsuite.py:48-54): UWIND, VWIND <= 1e-9; POTT, COLP <= 1e-12; QV, QC <= 1e-11
+(>= 20x the oracle's own 1-ulp-perturbation floor).  The kernels are built
+without FMA contraction and keep the reference's evaluation order, so everything that does
+not pass through pow/log is compared BIT-EXACTLY at kernel level.
+"""
+import numpy as np
+import pytest
+
+from helpers import (STATE, TOL, fields_from_golden, golden_dims, grid_from_golden, interior,
+                     load_golden, oracle_from_golden, rel_err)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module', autouse=True)
+def cuda_library():
+    import torch
+    from climate_model_b200 import _lib
+    assert torch.cuda.is_available()
+    _lib.use_library(_lib.DEFAULT_LIBRARY)      # fails loudly if the .so is missing
+    assert _lib.is_cuda(), 'the GPU tests must run the CUDA build, not the host emulation'
+    yield
+
+
+@pytest.fixture(scope='module')
+def g10():
+    return load_golden('ref_10deg_rand.npz')
+
+
+def _eq(a, b, what):
+    assert np.array_equal(a, b), '%s: max|diff| = %g' % (what, np.nanmax(np.abs(a - b)))
+
+
+def _diag(GR, F):
+    from climate_model_b200.dyn_matsuno import Diagnostics
+    from climate_model_b200.io_read_namelist import B200
+    Diagnostics.primary_diag(GR.GRF[B200], **F.get(Diagnostics.fields_primary_diag, target=B200))
+
+
+def test_device_buffers_are_cuda_and_lon_fastest(g10):
+    GR = grid_from_golden(g10)
+    F = fields_from_golden(GR, g10)
+    t = F.device['POTT']
+    assert t.is_cuda and t.stride(2) == 1 and t.shape == (GR.nz, GR.NJ, GR.NI)
+
+
+def test_primary_diag_close_to_oracle(g10):
+    """pow() differs between the device libm and glibc by <= 2 ulp"""
+    GR = grid_from_golden(g10)
+    F = fields_from_golden(GR, g10)
+    O = oracle_from_golden(g10)
+    O.primary_diag()
+    _diag(GR, F)
+    F.copy_device_to_host(GR, F.ALL_FIELDS)
+    for n in ['PVTF', 'PVTFVB']:
+        assert rel_err(F.host[n], O.F[n]) <= 1e-15, n
+    for n in ['PHI', 'PHIVB', 'POTTVB']:
+        assert rel_err(F.host[n], O.F[n]) <= 1e-13, n
+
+
+def test_kernels_bit_exact_given_oracle_diagnostics(g10):
+    """feed the oracle's PVTF/PHI/... to the device: every tendency kernel, the continuity
+    and the Euler step must then reproduce the oracle bit for bit (no pow/log involved,
+    except moisture's log interpolation)"""
+    from climate_model_b200.dyn_matsuno import Prognostics
+    from climate_model_b200.dyn_tendencies import compute_tendencies
+    from climate_model_b200.io_read_namelist import B200
+    nx, ny, nz, _ = golden_dims(g10)
+    GR = grid_from_golden(g10)
+    F = fields_from_golden(GR, g10)
+    O = oracle_from_golden(g10)
+    O.primary_diag()
+    for n in ['PVTF', 'PVTFVB', 'PHI', 'PHIVB', 'POTTVB']:
+        F.host[n][...] = O.F[n]
+        F.to_device(GR, n)
+    for n in STATE:
+        O.F[n + '_OLD'][:] = O.F[n]
+        F.device[n + '_OLD'].copy_(F.device[n])
+    O.compute_tendencies()
+    compute_tendencies(GR, F)
+    F.copy_device_to_host(GR, F.ALL_FIELDS)
+    full = (slice(None),) * 3
+    box = lambda i1, j1: (slice(1, i1 + 1), slice(1, j1 + 1), slice(None))
+    exact = {
+        'UFLX': full, 'VFLX': full, 'WWIND': full, 'COLP_NEW': full,
+        'FLXDIV': box(nx, ny), 'dCOLPdt': box(nx, ny),
+        'WWIND_UWIND': box(nx + 1, ny), 'WWIND_VWIND': box(nx, ny + 1),
+        'BFLX': box(nx, ny), 'RFLX': box(nx, ny), 'CFLX': box(nx + 1, ny + 1),
+        'QFLX': box(nx + 1, ny + 1), 'DFLX': box(nx, ny + 1), 'EFLX': box(nx, ny + 1),
+        'SFLX': box(nx + 1, ny), 'TFLX': box(nx + 1, ny), 'dUFLXdt': box(nx, ny),
+        'dVFLXdt': (slice(1, nx + 1), slice(2, ny + 1), slice(None)),
+        'dPOTTdt': box(nx, ny),
+    }
+    for n, sl in exact.items():
+        _eq(F.host[n][sl], O.F[n][sl], n)
+    for n in ['dQVdt', 'dQCdt']:       # device log() vs glibc log()
+        assert rel_err(F.host[n][box(nx, ny)], O.F[n][box(nx, ny)]) <= 1e-12, n
+    # Euler step from identical tendencies: bit exact incl. the fused BC images
+    for n in ['dQVdt', 'dQCdt']:
+        F.host[n][...] = O.F[n]
+        F.to_device(GR, n)
+    O.F['COLP'][:] = O.F['COLP_NEW']
+    F.device['COLP'].copy_(F.device['COLP_NEW'])
+    O.euler_forward()
+    Prognostics.euler_forward(GR, GR.GRF[B200], **F.get(Prognostics.fields_prognostic, target=B200))
+    F.copy_device_to_host(GR, F.PROGNOSTIC_FIELDS)
+    for n in STATE:
+        _eq(F.host[n], O.F[n], n)
+
+
+@pytest.mark.parametrize('fixture,steps', [('ref_10deg_rand.npz', [1, 2, 10]),
+                                           ('ref_5deg.npz', [10, 50])])
+def test_step_matsuno_against_reference_golden(fixture, steps):
+    """N Matsuno steps against the REAL reference's numba-CPU outputs"""
+    from climate_model_b200.dyn_matsuno import step_matsuno
+    g = load_golden(fixture)
+    GR = grid_from_golden(g)
+    F = fields_from_golden(GR, g)
+    _diag(GR, F)
+    done = 0
+    for s in steps:
+        step_matsuno(GR, F, s - done)
+        done = s
+        F.copy_device_to_host(GR, F.PROGNOSTIC_FIELDS)
+        for n in STATE:
+            e = rel_err(F.host[n], g['N%d_%s' % (s, n)])
+            assert e <= TOL[n], 'N%d %s: %.3e > %.0e' % (s, n, e, TOL[n])
+
+
+def test_factory_path_equals_coarse_entry(g10):
+    from climate_model_b200.dyn_matsuno import step_matsuno, step_matsuno_factories
+    out = []
+    for stepper in (step_matsuno, step_matsuno_factories):
+        GR = grid_from_golden(g10)
+        F = fields_from_golden(GR, g10)
+        _diag(GR, F)
+        for _ in range(2):
+            stepper(GR, F)
+        F.copy_device_to_host(GR, F.PROGNOSTIC_FIELDS)
+        out.append({n: F.host[n].copy() for n in STATE})
+    for n in STATE:
+        _eq(out[0][n], out[1][n], n)
+
+
+def test_config2_1deg_32lev_against_oracle():
+    """BASELINE.json configs[1]/[2]: 1 deg x 32 levels, elev.1-deg topography, moist tracers on;
+    own initial-condition builder feeds both the oracle and the device; 10 steps"""
+    from climate_model_b200.dyn_matsuno import step_matsuno
+    from climate_model_b200.main_fields import ModelFields
+    from climate_model_b200.main_grid import Grid
+    from oracle.oracle import GRID_FIELDS, Oracle
+    GR = Grid(nz=32, lat0_deg=-84, lat1_deg=84, dlat_deg=1.0, dlon_deg=1.0)
+    assert (GR.nx, GR.ny, GR.nz, GR.dt) == (360, 168, 32, 20)
+    F = ModelFields(GR)
+    O = Oracle(GR.nx, GR.ny, GR.nz, GR.dt, {n: GR.GRF['CPU'][n] for n in GRID_FIELDS})
+    O.set(**{n: F.host[n] for n in ['HSURF'] + STATE})
+    O.primary_diag()
+    _diag(GR, F)
+    O.step_matsuno(10)
+    step_matsuno(GR, F, 10)
+    F.copy_device_to_host(GR, F.PROGNOSTIC_FIELDS)
+    for n in STATE:
+        e = rel_err(F.host[n], O.F[n])
+        assert e <= TOL[n], '%s: %.3e > %.0e' % (n, e, TOL[n])
+    assert np.max(np.abs(F.host['UWIND'][interior('UWIND', GR.nx, GR.ny)])) > 5.
+
+
+def test_full_size_properties_quarter_degree_64_levels():
+    """BASELINE.json configs[3] size (1440 x 672 x 64), where the oracle is too slow:
+    size-independent properties of the scheme.
+      - a state shifted by m cells in longitude must give the bitwise shifted result
+        (periodic domain, identical arithmetic per cell);
+      - boundary invariants: periodic duplicates, zero meridional wind on the walls;
+      - the column-pressure update conserves total mass sum(COLP*A) to rounding."""
+    import torch
+    from climate_model_b200.dyn_matsuno import step_matsuno
+    from climate_model_b200.main_fields import ModelFields
+    from climate_model_b200.main_grid import Grid
+    GR = Grid(nz=64, lat0_deg=-84, lat1_deg=84, dlat_deg=0.25, dlon_deg=0.25, i_out_nth_hour=1.0)
+    assert (GR.nx, GR.ny, GR.nz) == (1440, 672, 64)
+    nx, ny = int(GR.nx), int(GR.ny)
+    F = ModelFields(GR, i_use_topo=0)
+    m = 37
+    G = ModelFields(GR, initialize=False)
+    js = GR.jshift
+    for n in ['HSURF'] + STATE:
+        src = F.device[n]
+        dst = G.device[n]
+        sx = F.fdict[n]['stgx']
+        # interior columns 1..nx rolled by m; halos rebuilt by the periodic rule
+        dst[:, :, 1:nx + 1] = torch.roll(src[:, :, 1:nx + 1], shifts=m, dims=2)
+        dst[:, :, 0] = dst[:, :, nx]
+        dst[:, :, nx + 1] = dst[:, :, 1]
+        if sx:
+            dst[:, :, nx + 2] = dst[:, :, 2]
+    a0 = torch.tensor(np.asarray(GR.A[1, :, 0]), device=F.device['COLP'].device)
+    mass0 = (F.device['COLP'][0, js + 1:js + ny + 1, 1:nx + 1] * a0[1:ny + 1, None]).sum().item()
+    for X in (F, G):
+        _diag(GR, X)
+        step_matsuno(GR, X, 2)
+    torch.cuda.synchronize()
+    for n in STATE:
+        a = F.device[n][:, :, 1:nx + 1]
+        b = G.device[n][:, :, 1:nx + 1]
+        assert torch.isfinite(a[:, js + 1:js + ny + 1]).all(), n
+        assert torch.equal(torch.roll(a, shifts=m, dims=2), b), 'shift invariance: ' + n
+    U, V, C = F.device['UWIND'], F.device['VWIND'], F.device['COLP']
+    assert torch.equal(U[:, :, nx + 1], U[:, :, 1]) and torch.equal(U[:, :, 0], U[:, :, nx])
+    assert (V[:, js + 1] == 0).all() and (V[:, js + ny + 1] == 0).all()
+    mass1 = (C[0, js + 1:js + ny + 1, 1:nx + 1] * a0[1:ny + 1, None]).sum().item()
+    assert abs(mass1 - mass0) / mass0 < 1e-13
