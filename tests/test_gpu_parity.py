@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 
 from helpers import (STATE, TOL, fields_from_golden, golden_dims, grid_from_golden, interior,
-                     load_golden, oracle_from_golden, rel_err)
+                     load_golden, oracle_from_golden, rel_err, state_err)
 
 pytestmark = pytest.mark.gpu
 
@@ -57,7 +57,7 @@ def test_primary_diag_close_to_oracle(g10):
     _diag(GR, F)
     F.copy_device_to_host(GR, F.ALL_FIELDS)
     for n in ['PVTF', 'PVTFVB']:
-        assert rel_err(F.host[n], O.F[n]) <= 1e-15, n
+        assert rel_err(F.host[n], O.F[n]) <= 1e-13, n
     for n in ['PHI', 'PHIVB', 'POTTVB']:
         assert rel_err(F.host[n], O.F[n]) <= 1e-13, n
 
@@ -126,8 +126,9 @@ def test_step_matsuno_against_reference_golden(fixture, steps):
         step_matsuno(GR, F, s - done)
         done = s
         F.copy_device_to_host(GR, F.PROGNOSTIC_FIELDS)
+        ref = {n: g['N%d_%s' % (s, n)] for n in STATE}
         for n in STATE:
-            e = rel_err(F.host[n], g['N%d_%s' % (s, n)])
+            e = state_err(n, F.host, ref)
             assert e <= TOL[n], 'N%d %s: %.3e > %.0e' % (s, n, e, TOL[n])
 
 
@@ -164,7 +165,7 @@ def test_config2_1deg_32lev_against_oracle():
     step_matsuno(GR, F, 10)
     F.copy_device_to_host(GR, F.PROGNOSTIC_FIELDS)
     for n in STATE:
-        e = rel_err(F.host[n], O.F[n])
+        e = state_err(n, F.host, O.F)
         assert e <= TOL[n], '%s: %.3e > %.0e' % (n, e, TOL[n])
     assert np.max(np.abs(F.host['UWIND'][interior('UWIND', GR.nx, GR.ny)])) > 5.
 
