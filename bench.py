@@ -47,10 +47,10 @@ STEP_BYTES = {False: 216, True: 296}
 # algorithmic 3-D field accesses (reads + writes) per cell of each kernel LAUNCH as the step is
 # decomposed today; x 8 B = bytes per cell per launch
 KERNEL_ACCESSES = {
-    'continuity': (5, 5), 'uvflx_prep': (15, 15), 'uflx_tendency': (13, 13),
+    'continuity': (5, 5), 'continuity_fused': (3, 5), 'stage_fused': (12.5, 12.5),
+    'moist_euler': (0, 6), 'uvflx_prep': (15, 15), 'uflx_tendency': (13, 13),
     'vflx_tendency': (13, 13), 'pott_tendency': (6, 6), 'moist_tendency': (7, 7),
     'euler_forward': (9, 15), 'primary_diag': (6, 6), 'copy_old': (6, 10),
-    'stage_fused': (0, 0),
 }
 
 
@@ -164,6 +164,8 @@ def main():
     ap.add_argument('--moist', action='store_true')
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--e2e-steps', type=int, default=3)
+    ap.add_argument('--mode', default='fused', choices=['fused', 'kernels'],
+                    help='fused stage kernel (default) or one kernel per reference kernel')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--emu', action='store_true',
                     help='debug the bench LOGIC on a box without a GPU against the host emulation '
@@ -178,7 +180,7 @@ def main():
     import torch
     import torch.distributed as dist
     from climate_model_b200 import _lib
-    from climate_model_b200.dyn_matsuno import Diagnostics, step_matsuno
+    from climate_model_b200.dyn_matsuno import Diagnostics, set_mode, step_matsuno
     from climate_model_b200.io_read_namelist import B200
     from climate_model_b200.main_fields import ModelFields
     from climate_model_b200.main_grid import Grid
@@ -217,6 +219,7 @@ def main():
     if world > 1:
         from climate_model_b200.parallel_bands import attach_communicator
         attach_communicator(GR, F)
+    set_mode(GR, args.mode)
     cells = int(GR.nx) * int(GR.ny) * int(GR.nz)
     Diagnostics.primary_diag(GR.GRF[B200], **F.get(Diagnostics.fields_primary_diag, target=B200))
     L, h = _lib.lib(), GR.dyncore()
@@ -285,7 +288,8 @@ def main():
         top = max(kern, key=lambda k: kern[k][0]) if kern else None
         roof = None
         if top:
-            acc = KERNEL_ACCESSES.get(top, (0, 0))[1 if moist else 0]
+            key = 'continuity_fused' if (top == 'continuity' and args.mode == 'fused') else top
+            acc = KERNEL_ACCESSES.get(key, (0, 0))[1 if moist else 0]
             k_ms = kern[top][0] / kern[top][1]
             cells_launch = cells // world
             bytes_launch = acc * 8 * cells_launch
@@ -303,7 +307,7 @@ def main():
             'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
             'config': {'workload': wl['name'], 'nx': int(GR.nx), 'ny': int(GR.ny),
                        'nz': int(GR.nz), 'dt_s': int(GR.dt), 'moist': moist,
-                       'parallelism': 'latitude bands x%d' % world,
+                       'parallelism': 'latitude bands x%d' % world, 'mode': args.mode,
                        'l2': 'inputs larger than L2 (%.1f GB state)' % (h2d / 1e9),
                        'finite': ok},
             'roofline': roof,

@@ -18,6 +18,7 @@ GRID_FIELDS_2D = ['A', 'dxjs', 'dyis', 'corf', 'corf_is', 'lat_rad', 'lat_is_rad
 GRID_FIELDS_1D = ['sigma_vb', 'dsigma', 'UVFLX_dif_coef', 'POTT_dif_coef', 'moist_dif_coef']
 
 DC_NK_2D, DC_NK_NZ, DC_NK_NZS = 0, 1, 2
+DC_MODE_FUSED, DC_MODE_KERNELS = 0, 1
 
 
 class GridDesc(ctypes.Structure):
@@ -58,6 +59,7 @@ def _declare(lib):
         getattr(lib, e).argtypes = [vp, vp]
     lib.dc_exchange_bc.argtypes = [vp, ctypes.c_int, vp]
     lib.dc_step_matsuno.argtypes = [vp, ctypes.c_int, vp]
+    lib.dc_set_mode.argtypes = [vp, ctypes.c_int]
     lib.dc_import_field.argtypes = [vp, ctypes.c_int, vp, ctypes.c_size_t, vp]
     lib.dc_export_field.argtypes = [vp, ctypes.c_int, vp, ctypes.c_size_t, vp]
     lib.dc_profile_enable.argtypes = [vp, ctypes.c_int]

@@ -11,6 +11,7 @@
 //   const char *dcb_error_string(int code);
 //   template <class Body> void dcb_launch(const Body &b, int i0, int i1, int j0, int j1,
 //                                         void *stream);   // body(i, j) for the closed box
+//   void dcb_launch_stage(const dc::StageBody &b, int nbx, int nby, void *stream);
 //   void dcb_transpose(const dc::Geom &g, double *ref, double *dev, int fnx, int fny,
 //                      int nk, int j_lo, int j_hi, int to_device, void *stream);
 //   void dcb_profile_begin(dc_handle *h, const char *name, void *stream);
@@ -27,6 +28,7 @@
 
 #include "../../include/dyncore.h"
 #include "dc_geom.h"
+#include "dc_fused.h"
 #include "dc_kernels.h"
 
 namespace dc {
@@ -86,6 +88,7 @@ struct dc_handle {
     long long launches;
     int profiling;
     void *profile_state;  // backend-owned
+    int mode;             // DC_MODE_FUSED (default) or DC_MODE_KERNELS
     double **slot(int id) { return reinterpret_cast<double **>(&f) + id; }
     double *const *slot(int id) const { return reinterpret_cast<double *const *>(&f) + id; }
 };
@@ -147,19 +150,32 @@ static int row_values(const double *a, int fnx, int fny, int i_lo, int i_hi, con
     return DC_OK;
 }
 
-static int do_continuity(dc_handle *h, bool store_flxdiv, void *stream)
+// rows [lo, hi] (global) the continuity kernel has to cover so that the stage kernel finds
+// WWIND / COLP_NEW one row beyond the band
+static void continuity_rows(const Geom &g, int *lo, int *hi)
+{
+    *lo = g.j0 - 1 < 1 ? 1 : g.j0 - 1;
+    *hi = g.j1 + 1 > g.ny ? g.ny : g.j1 + 1;
+}
+
+template <int MODE>
+static void launch_continuity(dc_handle *h, const double *U, const double *V, void *stream)
 {
     const Fields &f = h->f;
     const Geom &g = h->g;
-    if (store_flxdiv) {
-        ContinuityBody<true> b{g,      f.UWIND,  f.VWIND, f.COLP,     f.COLP_OLD, f.UFLX,
-                               f.VFLX, f.FLXDIV, f.WWIND, f.COLP_NEW, f.dCOLPdt};
-        launch(h, "continuity", b, 1, g.nx, 1, g.ny, stream);
-    } else {
-        ContinuityBody<false> b{g,      f.UWIND,  f.VWIND, f.COLP,     f.COLP_OLD, f.UFLX,
-                                f.VFLX, f.FLXDIV, f.WWIND, f.COLP_NEW, f.dCOLPdt};
-        launch(h, "continuity", b, 1, g.nx, 1, g.ny, stream);
-    }
+    int lo, hi;
+    continuity_rows(g, &lo, &hi);
+    ContinuityBody<MODE> b{g,      U,        V,       f.COLP,     f.COLP_OLD, f.UFLX,
+                           f.VFLX, f.FLXDIV, f.WWIND, f.COLP_NEW, f.dCOLPdt};
+    launch(h, "continuity", b, 1, g.nx, lo, hi, stream);
+}
+
+static int do_continuity(dc_handle *h, bool store_flxdiv, void *stream)
+{
+    if (store_flxdiv)
+        launch_continuity<3>(h, h->f.UWIND, h->f.VWIND, stream);
+    else
+        launch_continuity<2>(h, h->f.UWIND, h->f.VWIND, stream);
     return DC_OK;
 }
 
@@ -218,6 +234,53 @@ static int do_primary_diag(dc_handle *h, void *stream)
     PrimaryDiagBody b{g, f.COLP, f.POTT, f.HSURF, f.PVTF, f.PVTFVB, f.PHI, f.PHIVB, f.POTTVB};
     launch(h, "primary_diag", b, 0, g.nx + 1, 0, g.ny + 1, stream);
     return DC_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// fused path: one Matsuno stage = continuity + stage kernel (+ moisture) + diagnostics.
+// State buffers: S0 = {UWIND, VWIND, POTT, QV, QC} holds the state at the beginning of the
+// step until stage 2 overwrites it cell by cell; S1 = {UWIND_OLD, ...} receives the estimate
+// of stage 1.  No OLD <- current copies of 3-D fields are needed.
+// ---------------------------------------------------------------------------------------
+static void do_stage_fused(dc_handle *h, int stage, void *stream)
+{
+    const Fields &f = h->f;
+    const Geom &g = h->g;
+    const double *U = stage == 0 ? f.UWIND : f.UWIND_OLD, *V = stage == 0 ? f.VWIND : f.VWIND_OLD,
+                 *T = stage == 0 ? f.POTT : f.POTT_OLD;
+    double *Uo = stage == 0 ? f.UWIND_OLD : f.UWIND, *Vo = stage == 0 ? f.VWIND_OLD : f.VWIND,
+           *To = stage == 0 ? f.POTT_OLD : f.POTT;
+    if (g.i_moist)
+        launch_continuity<2>(h, U, V, stream);   // moisture kernels read UFLX / VFLX
+    else
+        launch_continuity<0>(h, U, V, stream);
+    StageBody sb{g,      U,          V,          T,       f.PHI,   f.PVTF,  f.PVTFVB, f.POTTVB,
+                 f.WWIND, f.COLP,    f.COLP_NEW, f.COLP_OLD, f.UWIND, f.VWIND, f.POTT,
+                 Uo,     Vo,         To,         g.j0,    g.j1};
+    if (h->profiling) dcb_profile_begin(h, "stage_fused", stream);
+    dcb_launch_stage(sb, (g.nx + TX - 1) / TX, (g.j1 - g.j0 + TY) / TY, stream);
+    if (h->profiling) dcb_profile_end(h, stream);
+    h->launches++;
+    if (g.i_moist) {
+        const double *QV = stage == 0 ? f.QV : f.QV_OLD, *QC = stage == 0 ? f.QC : f.QC_OLD;
+        double *QVo = stage == 0 ? f.QV_OLD : f.QV, *QCo = stage == 0 ? f.QC_OLD : f.QC;
+        MoistTendencyBody m{g, QV, QC, f.UFLX, f.VFLX, f.COLP, f.WWIND, f.COLP_NEW, f.dQVdt,
+                            f.dQCdt};
+        launch(h, "moist_tendency", m, 1, g.nx, g.j0, g.j1, stream);
+        MoistEulerBody e{g, f.COLP_NEW, f.COLP_OLD, f.QV, f.dQVdt, f.QC, f.dQCdt, QVo, QCo};
+        launch(h, "moist_euler", e, 1, g.nx, g.j0, g.j1, stream);
+    }
+}
+
+// primary diagnostics of the state a stage produced, on every row this rank holds
+static void do_diag_fused(dc_handle *h, int stage, void *stream)
+{
+    const Fields &f = h->f;
+    const Geom &g = h->g;
+    const int lo = g.j0 - HJ < 0 ? 0 : g.j0 - HJ, hi = g.j1 + HJ > g.ny + 1 ? g.ny + 1 : g.j1 + HJ;
+    PrimaryDiagBody b{g,      f.COLP, stage == 0 ? f.POTT_OLD : f.POTT, f.HSURF, f.PVTF, f.PVTFVB,
+                      f.PHI,  f.PHIVB, f.POTTVB};
+    launch(h, "primary_diag", b, 0, g.nx + 1, lo, hi, stream);
 }
 
 static const std::vector<int> NEED_CONT = {F_UWIND, F_VWIND, F_COLP, F_COLP_OLD, F_UFLX,
@@ -374,6 +437,7 @@ int dc_create(const dc_grid_desc *d, dc_handle **out)
     g.POTT_dif_coef = dl + 3 * (nz + 1); g.moist_dif_coef = dl + 4 * (nz + 1);
     h->launches = 0;
     h->profiling = 0;
+    h->mode = DC_MODE_FUSED;
     h->profile_state = nullptr;
     *out = h;
     return DC_OK;
@@ -570,6 +634,15 @@ int dc_exchange_bc(dc_handle *h, int id, void *stream)
     return backend_status("dc_exchange_bc");
 }
 
+int dc_set_mode(dc_handle *h, int mode)
+{
+    if (!h) return fail(DC_ERR_ARG, "dc_set_mode: NULL handle");
+    if (mode != DC_MODE_FUSED && mode != DC_MODE_KERNELS)
+        return fail(DC_ERR_ARG, "dc_set_mode: unknown mode %d", mode);
+    h->mode = mode;
+    return DC_OK;
+}
+
 int dc_step_matsuno(dc_handle *h, int nsteps, void *stream)
 {
     DC_ENTRY_CHECK("dc_step_matsuno");
@@ -586,6 +659,17 @@ int dc_step_matsuno(dc_handle *h, int nsteps, void *stream)
         return rc;
     const Fields &f = h->f;
     const size_t b2 = g.plane * sizeof(double), b3 = b2 * g.nz;
+    if (h->mode == DC_MODE_FUSED) {
+        for (int s = 0; s < nsteps; s++) {
+            dcb_d2d_async(f.COLP_OLD, f.COLP, b2, stream);      // dyn_matsuno.py:34
+            for (int stage = 0; stage < 2; stage++) {            // estimate, final
+                do_stage_fused(h, stage, stream);
+                dcb_d2d_async(f.COLP, f.COLP_NEW, b2, stream);  // dyn_matsuno.py:64-67
+                do_diag_fused(h, stage, stream);
+            }
+        }
+        return backend_status("dc_step_matsuno");
+    }
     for (int s = 0; s < nsteps; s++) {
         // dyn_matsuno.py:34-49: OLD <- current
         if (h->profiling) dcb_profile_begin(h, "copy_old", stream);

@@ -1,0 +1,367 @@
+// dc_fused.h -- the fused stage kernel of the Matsuno step ("v2").
+//
+// One kernel advances U, V and POTT by one Matsuno stage: it replaces the reference's
+// UVFLX_prep_adv + UFLX_tendency + VFLX_tendency + POTT_tendency + make_timestep launches
+// (dyn_org_discretizations.py:121-273, :359-393) and never materialises UFLX/VFLX, the eight
+// auxiliary momentum fluxes, WWIND_UWIND/WWIND_VWIND or the tendencies in HBM:
+//
+//   thread block = a (TX x TY) tile of (lon, lat) columns, marched through the sigma levels;
+//   per level:  A) U, V of the tile + halo are staged in shared memory together with the
+//                  momentum fluxes UFLX, VFLX computed from them, and COLP_NEW*A*WWIND of
+//                  interface k+1;
+//               B) the eight auxiliary fluxes B..T are formed once per cell in shared memory;
+//               C) every thread adds up dUFLXdt, dVFLXdt, dPOTTdt of its cell (vertical flux
+//                  of interface k carried in registers from the previous level), applies the
+//                  pressure-weighted Euler step and stores the new U, V, POTT with their
+//                  boundary images.
+//
+// Every expression keeps the reference's evaluation order (dc_point.h), so the result is
+// bit-identical to the v1 kernels.  The block body is written against a tiny SPMD macro
+// layer so that tests/emu can execute the very same code on the host (a "phase" is a loop
+// over the block's threads there, thread-private state lives in arrays).
+#pragma once
+#include "dc_geom.h"
+#include "dc_kernels.h"
+#include "dc_point.h"
+
+namespace dc {
+
+constexpr int TX = 32, TY = 8, NT = TX * TY;
+constexpr int SW = TX + 3, SH = TY + 3;  // staged region: ri in [-1, TX+1], rj in [-1, TY+1]
+constexpr int SN = SW * SH;
+constexpr int NQ = (SN + NT - 1) / NT;   // staged cells per thread (2)
+
+struct StageSmem {
+    double U[SN], V[SN], UF[SN], VF[SN], P[SN];
+    double B[SN], C[SN], D[SN], E[SN], R[SN], Q[SN], S[SN], T[SN];
+};
+
+#if defined(__CUDA_ARCH__)
+#define DC_PRIV(type, name) type name
+#define DC_PRIVN(type, name, n) type name[n]
+#define DC_P(name) name
+#define DC_PHASE {                                           \
+        const int tid = threadIdx.y * TX + threadIdx.x;
+#define DC_PHASE_END \
+    }                \
+    __syncthreads();
+#else
+#define DC_PRIV(type, name) type name[NT]
+#define DC_PRIVN(type, name, n) type name[NT][n]
+#define DC_P(name) name[tid]
+#define DC_PHASE for (int tid = 0; tid < NT; tid++) {
+#define DC_PHASE_END }
+#endif
+
+struct StageBody {
+    Geom g;
+    // state the tendencies are evaluated at, and its diagnostics
+    const double *UWIND, *VWIND, *POTT, *PHI, *PVTF, *PVTFVB, *POTTVB, *WWIND;
+    const double *COLP, *COLP_NEW, *COLP_OLD;
+    // state at the beginning of the step (dyn_matsuno.py:34-49)
+    const double *UWIND_OLD, *VWIND_OLD, *POTT_OLD;
+    // result of the stage
+    double *UWIND_out, *VWIND_out, *POTT_out;
+    int j_lo, j_hi;  // global mass rows to advance
+
+    DC_HD int wrap_i(int i) const { return i < 1 ? i + g.nx : (i > g.nx ? i - g.nx : i); }
+    DC_HD static int sidx(int ri, int rj) { return (rj + 1) * SW + (ri + 1); }
+
+    DC_HD void run_block(int bx, int by, StageSmem &s) const
+    {
+        const int nx = g.nx, ny = g.ny, nz = g.nz;
+        const int I0 = 1 + bx * TX, J0 = j_lo + by * TY;
+        const size_t plane = g.plane;
+        // rows this rank holds (global): halo rows included
+        const int j_min = (g.j0 - HJ < 0) ? 0 : g.j0 - HJ;
+        const int j_max_m = (g.j1 + HJ > ny + 1) ? ny + 1 : g.j1 + HJ;      // mass / x-staggered
+        const int j_max_y = (g.j1 + HJ + 1 > ny + 2) ? ny + 2 : g.j1 + HJ + 1;  // y-staggered
+
+        // ---- thread-private state --------------------------------------------------------
+        DC_PRIVN(int, offU, NQ);     // plane offset of the staged U cells of this thread
+        DC_PRIVN(int, offV, NQ);
+        DC_PRIVN(int, offP, NQ);
+        DC_PRIVN(double, cu, NQ);    // (COLP[i-1,j] + COLP[i,j]) / 2
+        DC_PRIVN(double, cv, NQ);    // (COLP[i,j-1] + COLP[i,j]) / 2
+        DC_PRIVN(double, dxv, NQ);   // dxjs[j]
+        DC_PRIVN(double, cp, NQ);    // COLP_NEW[i,j] * A[j]
+        DC_PRIV(int, off0);          // plane offset of the own cell
+        DC_PRIV(int, valid);
+        DC_PRIV(double, c);
+        DC_PRIV(double, c_im1);
+        DC_PRIV(double, c_ip1);
+        DC_PRIV(double, c_jm1);
+        DC_PRIV(double, c_jp1);
+        DC_PRIV(double, cnew);
+        DC_PRIV(double, cold);
+        DC_PRIV(double, colpa_is);
+        DC_PRIV(double, colpa_old_is);
+        DC_PRIV(double, colpa_js);
+        DC_PRIV(double, colpa_old_js);
+        DC_PRIV(double, wwu_k);      // WWIND_UWIND at interface k (carried)
+        DC_PRIV(double, wwv_k);
+        DC_PRIV(double, w_k);        // WWIND[k]
+        DC_PRIV(double, pottvb_k);
+        DC_PRIV(double, pvb);        // PVTFVB[k] at (i,j), (i-1,j), (i,j-1)
+        DC_PRIV(double, pvb_im1);
+        DC_PRIV(double, pvb_jm1);
+
+        // ---- set-up -----------------------------------------------------------------------
+        DC_PHASE
+            for (int q = 0; q < NQ; q++) {
+                const int idx = tid + q * NT;
+                const int ri = idx % SW - 1, rj = idx / SW - 1;
+                int i = I0 + ri, j = J0 + rj;
+                if (i > nx + 2) i = nx + 2;   // columns beyond the domain: masked threads only
+                if (j < j_min) j = j_min;
+                // Columns are wrapped into the interior [1, nx]: the x halo cells of the inputs
+                // hold exactly these periodic images (misc_boundaries.py:26-32), so the staged
+                // values are the ones the reference reads, and never-initialised halo cells
+                // (UWIND[nxs+1] of the python set-up BC, main_grid.py:340-343) are not touched.
+                const int iw = wrap_i(i), iwm = wrap_i(i - 1);
+                {   // U cell (x-staggered, rows 0 .. ny+1): UFLX = (C[i-1] + C[i])/2 * U * dyis
+                    const int jj = j > j_max_m ? j_max_m : j;
+                    DC_P(offU)[q] = (int)g.idx2(iw, jj);
+                    DC_P(cu)[q] = (COLP[g.idx2(iwm, jj)] + COLP[g.idx2(iw, jj)]) / 2.;
+                }
+                {   // V cell (y-staggered, rows 0 .. ny+2): VFLX = (C[j-1] + C[j])/2 * V * dxjs
+                    const int jj = j > j_max_y ? j_max_y : j;
+                    const int jc = jj > j_max_m ? j_max_m : jj;
+                    const int jcm = (jj - 1 < j_min) ? j_min : (jj - 1 > j_max_m ? j_max_m : jj - 1);
+                    DC_P(offV)[q] = (int)g.idx2(iw, jj);
+                    DC_P(cv)[q] = (COLP[g.idx2(iw, jcm)] + COLP[g.idx2(iw, jc)]) / 2.;
+                    DC_P(dxv)[q] = g.dxjs[g.row(jj)];
+                }
+                {   // WWIND cell (mass, rows 0 .. ny+1): COLP_NEW * A * WWIND
+                    const int jj = j > j_max_m ? j_max_m : j;
+                    DC_P(offP)[q] = (int)g.idx2(iw, jj);
+                    DC_P(cp)[q] = COLP_NEW[g.idx2(iw, jj)] * g.A[g.row(jj)];
+                }
+            }
+            {
+                const int tx = tid % TX, ty = tid / TX;
+                const int i = I0 + tx, j = J0 + ty;
+                DC_P(valid) = (i <= nx) && (j <= j_hi);
+                const int ii = i <= nx ? i : nx, jj = j <= j_hi ? j : j_hi;
+                DC_P(off0) = (int)g.idx2(ii, jj);
+                const double *C = COLP, *CN = COLP_NEW, *CO = COLP_OLD;
+                DC_P(c) = C[g.idx2(ii, jj)];
+                DC_P(c_im1) = C[g.idx2(ii - 1, jj)];
+                DC_P(c_ip1) = C[g.idx2(ii + 1, jj)];
+                DC_P(c_jm1) = C[g.idx2(ii, jj - 1)];
+                DC_P(c_jp1) = C[g.idx2(ii, jj + 1)];
+                const double A = g.A[g.row(jj)], A_jm1 = g.A[g.row(jj - 1)],
+                             A_jp1 = g.A[g.row(jj + 1)];
+                // the Euler step runs after COLP <- COLP_NEW (dyn_matsuno.py:64-67)
+                DC_P(cnew) = CN[g.idx2(ii, jj)];
+                DC_P(cold) = CO[g.idx2(ii, jj)];
+                DC_P(colpa_is) = interp_COLPA_is(
+                    CN[g.idx2(ii, jj)], CN[g.idx2(ii - 1, jj)], CN[g.idx2(ii, jj - 1)],
+                    CN[g.idx2(ii, jj + 1)], CN[g.idx2(ii - 1, jj + 1)], CN[g.idx2(ii - 1, jj - 1)],
+                    A, A_jm1, A_jp1, jj, ny);
+                DC_P(colpa_old_is) = interp_COLPA_is(
+                    CO[g.idx2(ii, jj)], CO[g.idx2(ii - 1, jj)], CO[g.idx2(ii, jj - 1)],
+                    CO[g.idx2(ii, jj + 1)], CO[g.idx2(ii - 1, jj + 1)], CO[g.idx2(ii - 1, jj - 1)],
+                    A, A_jm1, A_jp1, jj, ny);
+                DC_P(colpa_js) = interp_COLPA_js(
+                    CN[g.idx2(ii, jj)], CN[g.idx2(ii, jj - 1)], CN[g.idx2(ii - 1, jj)],
+                    CN[g.idx2(ii + 1, jj)], CN[g.idx2(ii + 1, jj - 1)], CN[g.idx2(ii - 1, jj - 1)],
+                    A, A_jm1);
+                DC_P(colpa_old_js) = interp_COLPA_js(
+                    CO[g.idx2(ii, jj)], CO[g.idx2(ii, jj - 1)], CO[g.idx2(ii - 1, jj)],
+                    CO[g.idx2(ii + 1, jj)], CO[g.idx2(ii + 1, jj - 1)], CO[g.idx2(ii - 1, jj - 1)],
+                    A, A_jm1);
+                DC_P(wwu_k) = 0.;  // WWIND_UWIND[0] = 0 (dyn_functions.py:236-237)
+                DC_P(wwv_k) = 0.;
+                DC_P(w_k) = WWIND[DC_P(off0)];
+                DC_P(pottvb_k) = POTTVB[DC_P(off0)];
+                DC_P(pvb) = PVTFVB[DC_P(off0)];
+                DC_P(pvb_im1) = PVTFVB[DC_P(off0) - 1];
+                DC_P(pvb_jm1) = PVTFVB[DC_P(off0) - g.NI];
+            }
+        DC_PHASE_END
+
+        for (int k = 0; k < nz; k++) {
+            const size_t ko = (size_t)k * plane;
+            const double ds = g.dsigma[k];
+            // ---- A: stage U, V, UFLX, VFLX of level k and COLP_NEW*A*WWIND of interface k+1
+            DC_PHASE
+                for (int q = 0; q < NQ; q++) {
+                    const int idx = tid + q * NT;
+                    if (idx < SN) {
+                        const double u = UWIND[ko + DC_P(offU)[q]];
+                        const double v = VWIND[ko + DC_P(offV)[q]];
+                        s.U[idx] = u;
+                        s.V[idx] = v;
+                        s.UF[idx] = DC_P(cu)[q] * u * g.dyis;           // calc_UFLX
+                        s.VF[idx] = DC_P(cv)[q] * v * DC_P(dxv)[q];     // calc_VFLX
+                        if (k + 1 < nz) s.P[idx] = DC_P(cp)[q] * WWIND[ko + plane + DC_P(offP)[q]];
+                    }
+                }
+            DC_PHASE_END
+            // ---- B: auxiliary momentum fluxes (dyn_functions.py:429-536), once per cell
+            DC_PHASE
+                for (int q = 0; q < NQ; q++) {
+                    const int idx = tid + q * NT;
+                    if (idx >= (TX + 2) * (TY + 2)) continue;
+                    const int ri = idx % (TX + 2) - 1, rj = idx / (TX + 2) - 1;
+                    const int c0 = sidx(ri, rj);
+                    const double *u = s.UF, *v = s.VF;
+                    if (ri <= TX - 1 && rj >= 0 && rj <= TY - 1)
+                        s.B[c0] = calc_BFLX(u[c0 - SW], u[c0 - SW + 1], u[c0], u[c0 + 1],
+                                            u[c0 + SW], u[c0 + SW + 1]);
+                    if (ri >= 0 && ri <= TX - 1 && rj >= 0)
+                        s.C[c0] = calc_CFLX(v[c0 - SW - 1], v[c0 - SW], v[c0 - 1], v[c0],
+                                            v[c0 + SW - 1], v[c0 + SW]);
+                    if (ri <= TX - 1 && rj >= 0) {
+                        s.D[c0] = calc_DFLX(v[c0 - SW], v[c0], v[c0 + SW], u[c0 - SW], u[c0],
+                                            u[c0 - SW + 1], u[c0 + 1]);
+                        s.E[c0] = calc_EFLX(v[c0 - SW], v[c0], v[c0 + SW], u[c0 - SW], u[c0],
+                                            u[c0 - SW + 1], u[c0 + 1]);
+                    }
+                    if (ri >= 0 && ri <= TX - 1 && rj <= TY - 1)
+                        s.R[c0] = calc_RFLX(v[c0 - 1], v[c0 + SW - 1], v[c0], v[c0 + SW],
+                                            v[c0 + 1], v[c0 + SW + 1]);
+                    if (ri >= 0 && rj >= 0 && rj <= TY - 1)
+                        s.Q[c0] = calc_QFLX(u[c0 - SW - 1], u[c0 - 1], u[c0 - SW], u[c0],
+                                            u[c0 - SW + 1], u[c0 + 1]);
+                    if (ri >= 0 && rj <= TY - 1) {
+                        s.S[c0] = calc_SFLX(v[c0 - 1], v[c0 + SW - 1], v[c0], v[c0 + SW],
+                                            u[c0 - 1], u[c0], u[c0 + 1]);
+                        s.T[c0] = calc_TFLX(v[c0 - 1], v[c0 + SW - 1], v[c0], v[c0 + SW],
+                                            u[c0 - 1], u[c0], u[c0 + 1]);
+                    }
+                }
+            DC_PHASE_END
+            // ---- C: tendencies of the own cell, Euler step, store with boundary images ----
+            DC_PHASE
+                const int tx = tid % TX, ty = tid / TX;
+                const int i = I0 + tx, j = J0 + ty;
+                const int c0 = sidx(tx, ty);
+                const size_t o = ko + DC_P(off0);
+                const int NI = g.NI;
+                // values of the next level / interface of the own column
+                double u_kp1 = 0., v_kp1 = 0., w_kp1 = 0.;
+                if (k + 1 < nz) {
+                    u_kp1 = UWIND[o + plane];
+                    v_kp1 = VWIND[o + plane];
+                    w_kp1 = WWIND[o + plane];
+                }
+                const double pottvb_kp1 = POTTVB[o + plane];
+                const double pvb_kp1 = PVTFVB[o + plane];
+                const double pvb_im1_kp1 = PVTFVB[o + plane - 1];
+                const double pvb_jm1_kp1 = PVTFVB[o + plane - NI];
+                if (DC_P(valid)) {
+                    const double *U = s.U, *V = s.V;
+                    const double u = U[c0], v = V[c0];
+                    // vertical momentum fluxes through interface k+1
+                    // (dyn_functions.py:211-270; 0 at the model bottom)
+                    double wwu_kp1 = 0., wwv_kp1 = 0.;
+                    if (k + 1 < nz) {
+                        const double *P = s.P;
+                        const int wall = (j == 1) ? -1 : ((j == ny) ? 1 : 0);
+                        wwu_kp1 = colpa_wwind(P[c0], P[c0 - 1], P[c0 - SW], P[c0 + SW],
+                                              P[c0 - SW - 1], P[c0 + SW - 1], wall) *
+                                  interp_ks(u_kp1, u, g.dsigma[k + 1], ds);
+                        wwv_kp1 = colpa_wwind(P[c0], P[c0 - SW], P[c0 - 1], P[c0 + 1],
+                                              P[c0 - SW - 1], P[c0 - SW + 1], 0) *
+                                  interp_ks(v_kp1, v, g.dsigma[k + 1], ds);
+                    }
+                    const double phi = PHI[o], pott = POTT[o], pvtf = PVTF[o];
+                    // ---------------- dUFLXdt (dyn_UFLX.py:69-199) ----------------
+                    {
+                        double bflx = s.B[c0], bflx_im1 = s.B[c0 - 1];
+                        double cflx = s.C[c0], cflx_jp1 = s.C[c0 + SW];
+                        double dflx_im1 = s.D[c0 - 1], dflx_jp1 = s.D[c0 + SW];
+                        double eflx = s.E[c0], eflx_im1_jp1 = s.E[c0 + SW - 1];
+                        if (j == 1) {
+                            dflx_im1 = 0.;
+                            cflx = 0.;
+                            eflx = 0.;
+                        }
+                        if (j == ny) {
+                            dflx_jp1 = 0.;
+                            cflx_jp1 = 0.;
+                            eflx_im1_jp1 = 0.;
+                        }
+                        double d = 0.;
+                        d = d + UVFLX_hor_adv(u, U[c0 - 1], U[c0 + 1], U[c0 - SW], U[c0 + SW],
+                                              U[c0 - SW - 1], U[c0 + SW - 1], U[c0 - SW + 1],
+                                              U[c0 + SW + 1], bflx, bflx_im1, cflx, cflx_jp1,
+                                              dflx_im1, dflx_jp1, eflx, eflx_im1_jp1, 1.);
+                        d = d + ((DC_P(wwu_k) - wwu_kp1) / ds);
+                        d = d + coriolis_UWIND(DC_P(c), DC_P(c_im1), v, V[c0 - 1], V[c0 + SW],
+                                               V[c0 + SW - 1], u, U[c0 - 1], U[c0 + 1],
+                                               g.corf_is[g.row(j)], g.cos_lat_is[g.row(j)],
+                                               g.sin_lat_is[g.row(j)], g.dlon_rad, g.dlat_rad);
+                        d = d + pre_grad(phi, PHI[o - 1], DC_P(c), DC_P(c_im1), pott, POTT[o - 1],
+                                         pvtf, PVTF[o - 1], DC_P(pvb), DC_P(pvb_im1), pvb_im1_kp1,
+                                         pvb_kp1, ds, g.sigma_vb[k], g.sigma_vb[k + 1], g.dyis);
+                        const double coef = g.UVFLX_dif_coef[k];
+                        if (coef > 0.)
+                            d = d + num_dif(s.UF[c0], s.UF[c0 - 1], s.UF[c0 + 1], s.UF[c0 - SW],
+                                            s.UF[c0 + SW], coef);
+                        put_xstag(g, UWIND_out, i, j, k,
+                                  euler_forward_pw(UWIND_OLD[o], d, DC_P(colpa_is),
+                                                   DC_P(colpa_old_is), g.dt));
+                    }
+                    // ---------------- dVFLXdt (dyn_VFLX.py:67-198) ----------------
+                    if (j >= 2) {
+                        double d = 0.;
+                        d = d + UVFLX_hor_adv(v, V[c0 - SW], V[c0 + SW], V[c0 - 1], V[c0 + 1],
+                                              V[c0 - SW - 1], V[c0 - SW + 1], V[c0 + SW - 1],
+                                              V[c0 + SW + 1], s.R[c0], s.R[c0 - SW], s.Q[c0],
+                                              s.Q[c0 + 1], s.S[c0 - SW], s.S[c0 + 1], s.T[c0],
+                                              s.T[c0 - SW + 1], -1.);
+                        d = d + ((DC_P(wwv_k) - wwv_kp1) / ds);
+                        d = d + coriolis_VWIND(DC_P(c), DC_P(c_jm1), u, U[c0 - SW], U[c0 + 1],
+                                               U[c0 - SW + 1], g.corf[g.row(j)],
+                                               g.corf[g.row(j - 1)], g.cos_lat[g.row(j)],
+                                               g.sin_lat[g.row(j)], g.cos_lat[g.row(j - 1)],
+                                               g.sin_lat[g.row(j - 1)], g.dlon_rad, g.dlat_rad);
+                        d = d + pre_grad(phi, PHI[o - NI], DC_P(c), DC_P(c_jm1), pott,
+                                         POTT[o - NI], pvtf, PVTF[o - NI], DC_P(pvb),
+                                         DC_P(pvb_jm1), pvb_jm1_kp1, pvb_kp1, ds, g.sigma_vb[k],
+                                         g.sigma_vb[k + 1], g.dxjs[g.row(j)]);
+                        const double coef = g.UVFLX_dif_coef[k];
+                        if (coef > 0.)
+                            d = d + num_dif(s.VF[c0], s.VF[c0 - 1], s.VF[c0 + 1], s.VF[c0 - SW],
+                                            s.VF[c0 + SW], coef);
+                        put_ystag(g, VWIND_out, i, j, k,
+                                  euler_forward_pw(VWIND_OLD[o], d, DC_P(colpa_js),
+                                                   DC_P(colpa_old_js), g.dt));
+                    } else {
+                        put_ystag(g, VWIND_out, i, 1, k, 0.);
+                    }
+                    if (j == ny) put_ystag(g, VWIND_out, i, ny + 1, k, 0.);
+                    // ---------------- dPOTTdt (dyn_POTT.py:55-110) ----------------
+                    {
+                        const double p_im1 = POTT[o - 1], p_ip1 = POTT[o + 1];
+                        const double p_jm1 = POTT[o - NI], p_jp1 = POTT[o + NI];
+                        double d = 0.;
+                        d = d + hor_adv(pott, p_im1, p_ip1, p_jm1, p_jp1, s.UF[c0], s.UF[c0 + 1],
+                                        s.VF[c0], s.VF[c0 + SW], g.A[g.row(j)]);
+                        d = d + vert_adv(DC_P(pottvb_k), pottvb_kp1, DC_P(w_k), w_kp1,
+                                         DC_P(cnew), ds, k);
+                        const double coef = g.POTT_dif_coef[k];
+                        if (coef > 0.)
+                            d = d + num_dif_pw(pott, p_im1, p_ip1, p_jm1, p_jp1, DC_P(c),
+                                               DC_P(c_im1), DC_P(c_ip1), DC_P(c_jm1), DC_P(c_jp1),
+                                               coef);
+                        put_mass(g, POTT_out, i, j, k,
+                                 euler_forward_pw(POTT_OLD[o], d, DC_P(cnew), DC_P(cold), g.dt));
+                    }
+                    DC_P(wwu_k) = wwu_kp1;
+                    DC_P(wwv_k) = wwv_kp1;
+                }
+                DC_P(w_k) = w_kp1;
+                DC_P(pottvb_k) = pottvb_kp1;
+                DC_P(pvb) = pvb_kp1;
+                DC_P(pvb_im1) = pvb_im1_kp1;
+                DC_P(pvb_jm1) = pvb_jm1_kp1;
+            DC_PHASE_END
+        }
+    }
+};
+
+}  // namespace dc

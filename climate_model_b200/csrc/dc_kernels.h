@@ -105,7 +105,8 @@ struct ExchangeBCBody {
 // prefix is parked in WWIND[k] during the first sweep and finalised in the second (which
 // re-reads only this thread's own WWIND column).
 // ---------------------------------------------------------------------------------------
-template <bool STORE_FLXDIV>
+// MODE bit 0: store FLXDIV; bit 1: store UFLX / VFLX (with their boundary images)
+template <int MODE>
 struct ContinuityBody {
     Geom g;
     const double *UWIND, *VWIND, *COLP, *COLP_OLD;
@@ -125,10 +126,12 @@ struct ContinuityBody {
             const double vf = calc_VFLX(VWIND[g.idx(i, j, k)], c, c_jm1, dxjs);
             const double vf_jp1 = calc_VFLX(VWIND[g.idx(i, j + 1, k)], c_jp1, c, dxjs_jp1);
             const double fd = calc_FLXDIV(uf, uf_ip1, vf, vf_jp1, g.dsigma[k], A);
-            put_xstag(g, UFLX, i, j, k, uf);
-            put_ystag(g, VFLX, i, j, k, vf);
-            if (j == g.ny) put_ystag(g, VFLX, i, g.ny + 1, k, 0.);
-            if (STORE_FLXDIV) FLXDIV[g.idx(i, j, k)] = fd;
+            if (MODE & 2) {
+                put_xstag(g, UFLX, i, j, k, uf);
+                put_ystag(g, VFLX, i, j, k, vf);
+                if (j == g.ny) put_ystag(g, VFLX, i, g.ny + 1, k, 0.);
+            }
+            if (MODE & 1) FLXDIV[g.idx(i, j, k)] = fd;
             s += fd;
             if (k + 1 < nz) WWIND[g.idx(i, j, k + 1)] = s;  // prefix, finalised below
         }
@@ -467,6 +470,26 @@ struct TimestepBody {
                          euler_forward_pw(QC_OLD[g.idx(i, j, k)], dQCdt[g.idx(i, j, k)], c, co,
                                           g.dt));
             }
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------
+// Euler forward of the moisture tracers only (fused path: U, V, POTT are stepped inside the
+// stage kernel).  threads: i in [1, nx], j in the band
+// ---------------------------------------------------------------------------------------
+struct MoistEulerBody {
+    Geom g;
+    const double *COLP_NEW, *COLP_OLD, *QV_OLD, *dQVdt, *QC_OLD, *dQCdt;
+    double *QV, *QC;
+    DC_HD void operator()(int i, int j) const
+    {
+        const double c = COLP_NEW[g.idx2(i, j)], co = COLP_OLD[g.idx2(i, j)];
+        for (int k = 0; k < g.nz; k++) {
+            put_mass(g, QV, i, j, k,
+                     euler_forward_pw(QV_OLD[g.idx(i, j, k)], dQVdt[g.idx(i, j, k)], c, co, g.dt));
+            put_mass(g, QC, i, j, k,
+                     euler_forward_pw(QC_OLD[g.idx(i, j, k)], dQCdt[g.idx(i, j, k)], c, co, g.dt));
         }
     }
 };

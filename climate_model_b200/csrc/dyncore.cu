@@ -45,6 +45,19 @@ static void dcb_launch(const Body &b, int i0, int i1, int j0, int j1, void *stre
     dc::k_columns<Body><<<grid, block, 0, (cudaStream_t)stream>>>(b, i0, i1, j0, j1);
 }
 
+#include "dc_fused.h"
+namespace dc {
+__global__ void __launch_bounds__(NT, 2) k_stage(const StageBody b)
+{
+    __shared__ StageSmem s;
+    b.run_block(blockIdx.x, blockIdx.y, s);
+}
+}  // namespace dc
+static void dcb_launch_stage(const dc::StageBody &b, int nbx, int nby, void *stream)
+{
+    dc::k_stage<<<dim3(nbx, nby), dim3(dc::TX, dc::TY), 0, (cudaStream_t)stream>>>(b);
+}
+
 // ---------------------------------------------------------------------------------------
 // layout conversion: reference (i, j, k) k-fastest  <->  device F[k][jd][i] i-fastest.
 // For every row j a tiled (i, k) transpose through shared memory so that both the read

@@ -28,6 +28,14 @@ def _bind_all(GR, F):
         F._bound['key'] = key
 
 
+def set_mode(GR, mode):
+    """'fused' (default): continuity + one fused stage kernel + diagnostics per stage;
+    'kernels': the reference's kernel decomposition, every intermediate field written
+    (dc_set_mode, include/dyncore.h)"""
+    code = {'fused': _lib.DC_MODE_FUSED, 'kernels': _lib.DC_MODE_KERNELS}[mode]
+    _lib.check(_lib.lib().dc_set_mode(GR.dyncore(), code))
+
+
 def step_matsuno(GR, F, nsteps=1):
     GR.timer.start('step')
     _bind_all(GR, F)

@@ -115,7 +115,16 @@ int dc_secondary_diag(dc_handle *h, void *stream);
 /* misc_boundaries.exchange_BC (misc_boundaries.py:22-42) on one bound field             */
 int dc_exchange_bc(dc_handle *h, int field_id, void *stream);
 
-/* ---- coarse entry: dyn_matsuno.step_matsuno (dyn_matsuno.py:28-129), nsteps times ---- */
+/* ---- coarse entry: dyn_matsuno.step_matsuno (dyn_matsuno.py:28-129), nsteps times ----
+ * DC_MODE_FUSED (default): per stage one continuity kernel, one fused stage kernel
+ *   (momentum-flux preparation + U/V/POTT tendencies + Euler step + boundary images) and
+ *   one diagnostics kernel.  The *_OLD 3-D fields are used as the second state buffer:
+ *   after the call they hold the stage-1 estimate, not the state before the step; the
+ *   intermediate fields (UFLX, BFLX.., dUFLXdt..) are not written.
+ * DC_MODE_KERNELS: the reference's decomposition, one kernel per reference kernel, every
+ *   intermediate field written as the reference does (same result, bit for bit). */
+enum { DC_MODE_FUSED = 0, DC_MODE_KERNELS = 1 };
+int dc_set_mode(dc_handle *h, int mode);
 int dc_step_matsuno(dc_handle *h, int nsteps, void *stream);
 
 /* ---- layout conversion on the device (F.copy_host_to_device / copy_device_to_host,

@@ -27,7 +27,17 @@ static void dcb_launch(const Body &b, int i0, int i1, int j0, int j1, void *)
         for (int i = i1; i >= i0; i--) b(i, j);
 }
 
-#include "../../climate_model_b200/csrc/dc_geom.h"
+#include "../../climate_model_b200/csrc/dc_fused.h"
+static void dcb_launch_stage(const dc::StageBody &b, int nbx, int nby, void *)
+{
+    static dc::StageSmem s;   // one "block" at a time
+    for (int by = nby - 1; by >= 0; by--)
+        for (int bx = nbx - 1; bx >= 0; bx--) {
+            for (size_t n = 0; n < sizeof(s) / sizeof(double); n++)
+                reinterpret_cast<double *>(&s)[n] = 0.0 / 0.0;   // stale smem must not be read
+            b.run_block(bx, by, s);
+        }
+}
 static void dcb_transpose(const dc::Geom &g, double *ref, double *dev, int fnx, int fny, int nk,
                           int j_lo, int j_hi, int to_device, void *)
 {

@@ -118,6 +118,28 @@ def test_step_matsuno_against_reference_golden(fixture, steps):
             _eq(F.host[n], g['N%d_%s' % (s, n)], 'N%d %s' % (s, n))
 
 
+@pytest.mark.parametrize('moist', [1, 0])
+def test_fused_mode_equals_kernel_mode(g10, moist):
+    """dc_step_matsuno: the fused stage kernel (shared-memory tiles, no intermediate fields,
+    *_OLD used as second state buffer) against the one-kernel-per-reference-kernel mode"""
+    from climate_model_b200.dyn_matsuno import Diagnostics, set_mode, step_matsuno
+    from climate_model_b200.io_read_namelist import B200
+    out = {}
+    for mode in ('fused', 'kernels'):
+        GR = grid_from_golden(g10, i_moist_main_switch=moist)
+        F = fields_from_golden(GR, g10)
+        set_mode(GR, mode)
+        Diagnostics.primary_diag(GR.GRF[B200],
+                                 **F.get(Diagnostics.fields_primary_diag, target=B200))
+        step_matsuno(GR, F, 3)
+        F.copy_device_to_host(GR, F.ALL_FIELDS)
+        out[mode] = {n: F.host[n].copy() for n in STATE + ['PHI', 'PVTF', 'WWIND', 'dUFLXdt']}
+    for n in STATE[:4] + (STATE[4:] if moist else []) + ['PHI', 'PVTF', 'WWIND']:
+        _eq(out['fused'][n], out['kernels'][n], n)
+    # the fused path never materialises the tendencies
+    assert np.all(out['fused']['dUFLXdt'] == 0.) and np.any(out['kernels']['dUFLXdt'] != 0.)
+
+
 def test_factory_path_equals_coarse_entry(g10):
     from climate_model_b200.dyn_matsuno import (Diagnostics, step_matsuno,
                                                  step_matsuno_factories)

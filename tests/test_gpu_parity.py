@@ -147,6 +147,28 @@ def test_factory_path_equals_coarse_entry(g10):
         _eq(out[0][n], out[1][n], n)
 
 
+@pytest.mark.parametrize('moist', [1, 0])
+def test_fused_mode_equals_kernel_mode_bitwise(moist):
+    """the fused stage kernel against the one-kernel-per-reference-kernel mode on the device,
+    3 deg x 12 levels with topography (tiles cut by the domain edge in both directions)"""
+    from climate_model_b200.dyn_matsuno import set_mode, step_matsuno
+    from climate_model_b200.main_fields import ModelFields
+    from climate_model_b200.main_grid import Grid
+    out = {}
+    for mode in ('fused', 'kernels'):
+        GR = Grid(nz=12, lat0_deg=-84, lat1_deg=84, dlat_deg=3.0, dlon_deg=3.0,
+                  i_moist_main_switch=moist)
+        F = ModelFields(GR, UWIND_random_pert=2.0, VWIND_random_pert=2.0, POTT_random_pert=1.0,
+                        COLP_random_pert=100.)
+        set_mode(GR, mode)
+        _diag(GR, F)
+        step_matsuno(GR, F, 4)
+        F.copy_device_to_host(GR, F.ALL_FIELDS)
+        out[mode] = {n: F.host[n].copy() for n in STATE + ['PHI', 'WWIND']}
+    for n in STATE[:4] + (STATE[4:] if moist else []) + ['PHI', 'WWIND']:
+        _eq(out['fused'][n], out['kernels'][n], n)
+
+
 def test_config2_1deg_32lev_against_oracle():
     """BASELINE.json configs[1]/[2]: 1 deg x 32 levels, elev.1-deg topography, moist tracers on;
     own initial-condition builder feeds both the oracle and the device; 10 steps"""
