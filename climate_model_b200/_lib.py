@@ -60,6 +60,12 @@ def _declare(lib):
     lib.dc_exchange_bc.argtypes = [vp, ctypes.c_int, vp]
     lib.dc_step_matsuno.argtypes = [vp, ctypes.c_int, vp]
     lib.dc_set_mode.argtypes = [vp, ctypes.c_int]
+    lib.dc_step_begin.argtypes = [vp, vp]
+    lib.dc_stage_compute.argtypes = [vp, ctypes.c_int, vp]
+    lib.dc_stage_diag.argtypes = [vp, ctypes.c_int, vp]
+    lib.dc_halo_bytes.argtypes = [vp, ctypes.POINTER(ctypes.c_size_t)]
+    lib.dc_halo_pack.argtypes = [vp, ctypes.c_int, vp, vp, vp]
+    lib.dc_halo_unpack.argtypes = [vp, ctypes.c_int, vp, vp, vp]
     lib.dc_import_field.argtypes = [vp, ctypes.c_int, vp, ctypes.c_size_t, vp]
     lib.dc_export_field.argtypes = [vp, ctypes.c_int, vp, ctypes.c_size_t, vp]
     lib.dc_profile_enable.argtypes = [vp, ctypes.c_int]
@@ -68,9 +74,6 @@ def _declare(lib):
                                     ctypes.POINTER(ctypes.c_longlong)]
     lib.dc_launch_count.argtypes = [vp]
     lib.dc_launch_count.restype = ctypes.c_longlong
-    for opt in ('dc_set_band_comm', 'dc_halo_exchange'):
-        if hasattr(lib, opt):
-            getattr(lib, opt).restype = ctypes.c_int
     return lib
 
 

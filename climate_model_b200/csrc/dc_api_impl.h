@@ -232,7 +232,8 @@ static int do_primary_diag(dc_handle *h, void *stream)
     const Fields &f = h->f;
     const Geom &g = h->g;
     PrimaryDiagBody b{g, f.COLP, f.POTT, f.HSURF, f.PVTF, f.PVTFVB, f.PHI, f.PHIVB, f.POTTVB};
-    launch(h, "primary_diag", b, 0, g.nx + 1, 0, g.ny + 1, stream);
+    const int lo = g.j0 - HJ < 0 ? 0 : g.j0 - HJ, hi = g.j1 + HJ > g.ny + 1 ? g.ny + 1 : g.j1 + HJ;
+    launch(h, "primary_diag", b, 0, g.nx + 1, lo, hi, stream);   // every row this rank holds
     return DC_OK;
 }
 
@@ -597,7 +598,7 @@ int dc_euler_forward(dc_handle *h, void *stream)
 
 int dc_primary_diag(dc_handle *h, void *stream)
 {
-    DC_ENTRY_CHECK("dc_primary_diag");
+    if (!h) return fail(DC_ERR_ARG, "dc_primary_diag: NULL handle");   // column-local: bands ok
     int rc;
     if ((rc = need(h, "dc_primary_diag", NEED_DIAG))) return rc;
     do_primary_diag(h, stream);
@@ -634,6 +635,115 @@ int dc_exchange_bc(dc_handle *h, int id, void *stream)
     return backend_status("dc_exchange_bc");
 }
 
+static int check_fused_fields(dc_handle *h, const char *what)
+{
+    int rc;
+    if ((rc = need(h, what, NEED_CONT)) || (rc = need(h, what, NEED_TEMP)) ||
+        (rc = need(h, what, NEED_STEP_DRY)) || (rc = need(h, what, NEED_DIAG)))
+        return rc;
+    if (h->g.i_moist && ((rc = need(h, what, NEED_MOIST)) || (rc = need(h, what, NEED_STEP_MOIST))))
+        return rc;
+    return DC_OK;
+}
+
+int dc_step_begin(dc_handle *h, void *stream)
+{
+    if (!h) return fail(DC_ERR_ARG, "dc_step_begin: NULL handle");
+    int rc;
+    if ((rc = check_fused_fields(h, "dc_step_begin"))) return rc;
+    dcb_d2d_async(h->f.COLP_OLD, h->f.COLP, h->g.plane * sizeof(double), stream);
+    return backend_status("dc_step_begin");
+}
+
+int dc_stage_compute(dc_handle *h, int stage, void *stream)
+{
+    if (!h || stage < 0 || stage > 1) return fail(DC_ERR_ARG, "dc_stage_compute: bad argument");
+    int rc;
+    if ((rc = check_fused_fields(h, "dc_stage_compute"))) return rc;
+    if (h->g.j1 - h->g.j0 + 1 < HJ)
+        return fail(DC_ERR_STATE, "dc_stage_compute: a band needs at least %d rows", HJ);
+    do_stage_fused(h, stage, stream);
+    dcb_d2d_async(h->f.COLP, h->f.COLP_NEW, h->g.plane * sizeof(double), stream);
+    return backend_status("dc_stage_compute");
+}
+
+int dc_stage_diag(dc_handle *h, int stage, void *stream)
+{
+    if (!h || stage < 0 || stage > 1) return fail(DC_ERR_ARG, "dc_stage_diag: bad argument");
+    int rc;
+    if ((rc = check_fused_fields(h, "dc_stage_diag"))) return rc;
+    do_diag_fused(h, stage, stream);
+    return backend_status("dc_stage_diag");
+}
+
+// fields whose boundary rows travel after a stage: the stage's output state + COLP
+static int halo_fields(const dc_handle *h, int stage, double **F, int *nk)
+{
+    const Fields &f = h->f;
+    const Geom &g = h->g;
+    int n = 0;
+    F[n] = stage == 0 ? f.UWIND_OLD : f.UWIND; nk[n++] = g.nz;
+    F[n] = stage == 0 ? f.VWIND_OLD : f.VWIND; nk[n++] = g.nz;
+    F[n] = stage == 0 ? f.POTT_OLD : f.POTT; nk[n++] = g.nz;
+    if (g.i_moist) {
+        F[n] = stage == 0 ? f.QV_OLD : f.QV; nk[n++] = g.nz;
+        F[n] = stage == 0 ? f.QC_OLD : f.QC; nk[n++] = g.nz;
+    }
+    F[n] = f.COLP; nk[n++] = 1;
+    return n;
+}
+
+int dc_halo_bytes(const dc_handle *h, size_t *nbytes)
+{
+    if (!h || !nbytes) return fail(DC_ERR_ARG, "dc_halo_bytes: NULL argument");
+    const Geom &g = h->g;
+    const size_t planes = (size_t)(g.i_moist ? 5 : 3) * g.nz + 1;
+    *nbytes = planes * HJ * (size_t)g.NI * sizeof(double);
+    return DC_OK;
+}
+
+static int halo_move(dc_handle *h, int stage, double *south, double *north, int to_buf,
+                     void *stream, const char *what)
+{
+    if (!h || stage < 0 || stage > 1) return fail(DC_ERR_ARG, "%s: bad argument", what);
+    int rc;
+    if ((rc = check_fused_fields(h, what))) return rc;
+    const Geom &g = h->g;
+    double *F[8];
+    int nk[8];
+    const int n = halo_fields(h, stage, F, nk);
+    // pack: the two outermost OWNED rows; unpack: the two halo rows beyond the band
+    const int j_south = to_buf ? g.j0 : g.j0 - HJ;
+    const int j_north = to_buf ? g.j1 - HJ + 1 : g.j1 + 1;
+    size_t off = 0;
+    for (int m = 0; m < n; m++) {
+        if (south) {
+            HaloPackBody b{g, F[m], south + off, j_south, nk[m], to_buf};
+            launch(h, to_buf ? "halo_pack" : "halo_unpack", b, 0, g.NI - 1, 0, HJ - 1, stream);
+        }
+        if (north) {
+            HaloPackBody b{g, F[m], north + off, j_north, nk[m], to_buf};
+            launch(h, to_buf ? "halo_pack" : "halo_unpack", b, 0, g.NI - 1, 0, HJ - 1, stream);
+        }
+        off += (size_t)nk[m] * HJ * g.NI;
+    }
+    return backend_status(what);
+}
+
+int dc_halo_pack(dc_handle *h, int stage, void *send_south, void *send_north, void *stream)
+{
+    return halo_move(h, stage, static_cast<double *>(send_south), static_cast<double *>(send_north),
+                     1, stream, "dc_halo_pack");
+}
+
+int dc_halo_unpack(dc_handle *h, int stage, const void *recv_south, const void *recv_north,
+                   void *stream)
+{
+    return halo_move(h, stage, static_cast<double *>(const_cast<void *>(recv_south)),
+                     static_cast<double *>(const_cast<void *>(recv_north)), 0, stream,
+                     "dc_halo_unpack");
+}
+
 int dc_set_mode(dc_handle *h, int mode)
 {
     if (!h) return fail(DC_ERR_ARG, "dc_set_mode: NULL handle");
@@ -645,7 +755,8 @@ int dc_set_mode(dc_handle *h, int mode)
 
 int dc_step_matsuno(dc_handle *h, int nsteps, void *stream)
 {
-    DC_ENTRY_CHECK("dc_step_matsuno");
+    DC_ENTRY_CHECK("dc_step_matsuno");  // a band needs the halo exchange between stages:
+                                        // dc_step_begin / dc_stage_compute / dc_halo_* / dc_stage_diag
     if (nsteps < 0) return fail(DC_ERR_ARG, "dc_step_matsuno: nsteps < 0");
     int rc;
     if ((rc = need(h, "dc_step_matsuno", NEED_CONT)) || (rc = need(h, "dc_step_matsuno", NEED_MOM)) ||

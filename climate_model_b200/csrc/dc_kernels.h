@@ -100,6 +100,28 @@ struct ExchangeBCBody {
 };
 
 // ---------------------------------------------------------------------------------------
+// latitude-band halo rows <-> contiguous message buffer [k][2][NI].
+// threads: i in [0, NI-1], "j" = r in [0, 1]; copies device rows (global) j_row + r
+// ---------------------------------------------------------------------------------------
+struct HaloPackBody {
+    Geom g;
+    double *F;      // field (nk planes)
+    double *buf;    // message segment of this field
+    int j_row, nk, to_buf;
+    DC_HD void operator()(int i, int r) const
+    {
+        for (int k = 0; k < nk; k++) {
+            const size_t a = g.idx(i, j_row + r, k);
+            const size_t b = ((size_t)k * 2 + r) * (size_t)g.NI + i;
+            if (to_buf)
+                buf[b] = F[a];
+            else
+                F[a] = buf[b];
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------
 // continuity: dyn_continuity.py:170-228 + BCs dyn_org_discretizations.py:114-117
 // threads: i in [1, nx], j in [1, ny].  U and V are read ONCE: the running flux-divergence
 // prefix is parked in WWIND[k] during the first sweep and finalised in the second (which

@@ -41,7 +41,14 @@ def step_matsuno(GR, F, nsteps=1):
     _bind_all(GR, F)
     t = F.device['UWIND']
     stream = torch.cuda.current_stream(t.device).cuda_stream if t.is_cuda else 0
-    _lib.check(_lib.lib().dc_step_matsuno(GR.dyncore(), int(nsteps), stream))
+    if GR.band[1] > 1:
+        from .parallel_bands import step_matsuno_banded
+        if getattr(GR, 'comm', None) is None:
+            raise RuntimeError('latitude-band run: call parallel_bands.attach_communicator(GR, F) '
+                               'after torch.distributed.init_process_group')
+        step_matsuno_banded(GR, F, nsteps, stream)
+    else:
+        _lib.check(_lib.lib().dc_step_matsuno(GR.dyncore(), int(nsteps), stream))
     GR.timer.stop('step')
 
 

@@ -127,6 +127,22 @@ enum { DC_MODE_FUSED = 0, DC_MODE_KERNELS = 1 };
 int dc_set_mode(dc_handle *h, int mode);
 int dc_step_matsuno(dc_handle *h, int nsteps, void *stream);
 
+/* ---- latitude-band decomposition (one handle per rank, dc_grid_desc.j0 / j1) ----------
+ * A Matsuno stage on a band = dc_stage_compute (continuity on rows j0-1..j1+1, fused stage
+ * kernel on rows j0..j1, COLP <- COLP_NEW), then the exchange of the two boundary rows of the
+ * new U, V, POTT (QV, QC) and COLP with the neighbouring ranks (dc_halo_pack -> NCCL
+ * send/recv by the caller -> dc_halo_unpack), then dc_stage_diag on all held rows.
+ * dc_step_begin once per step.  Messages are contiguous buffers of dc_halo_bytes() bytes per
+ * direction; pass NULL for a direction that ends at a domain wall.  The result is bitwise
+ * identical to the single-device run (no cross-rank reductions). */
+int dc_step_begin(dc_handle *h, void *stream);
+int dc_stage_compute(dc_handle *h, int stage, void *stream);
+int dc_stage_diag(dc_handle *h, int stage, void *stream);
+int dc_halo_bytes(const dc_handle *h, size_t *nbytes);
+int dc_halo_pack(dc_handle *h, int stage, void *send_south, void *send_north, void *stream);
+int dc_halo_unpack(dc_handle *h, int stage, const void *recv_south, const void *recv_north,
+                   void *stream);
+
 /* ---- layout conversion on the device (F.copy_host_to_device / copy_device_to_host,
  *      main_fields.py:204-215): `ref` is a DEVICE buffer holding the field in the
  *      reference layout (fnx, fny, nk) with k fastest, i.e. a raw byte copy of the host

@@ -1,0 +1,47 @@
+"""worker of tests/test_bands_gloo.py / test_gpu_bands.py: one process per latitude band
+(BAND_BACKEND=gloo: host emulation on the CPU; nccl: the CUDA library, one GPU per rank)"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    fixture, nsteps, outdir, moist = sys.argv[1], int(sys.argv[2]), sys.argv[3], int(sys.argv[4])
+    import torch.distributed as dist
+    from helpers import STATE, build_emu, fields_from_golden, grid_from_golden, load_golden
+    from climate_model_b200 import _lib
+    from climate_model_b200.dyn_matsuno import Diagnostics, step_matsuno
+    from climate_model_b200.io_read_namelist import B200
+    from climate_model_b200.parallel_bands import attach_communicator
+    backend = os.environ.get('BAND_BACKEND', 'gloo')
+    if backend == 'nccl':
+        import torch
+        torch.cuda.set_device(int(os.environ['LOCAL_RANK']))
+        dist.init_process_group('nccl', device_id=torch.device('cuda', int(os.environ['LOCAL_RANK'])))
+        _lib.use_library(_lib.DEFAULT_LIBRARY)
+        assert _lib.is_cuda()
+    else:
+        dist.init_process_group('gloo')
+        _lib.use_library(build_emu())
+    rank, world = dist.get_rank(), dist.get_world_size()
+    g = load_golden(fixture)
+    GR = grid_from_golden(g, band=(rank, world), i_moist_main_switch=moist)
+    F = fields_from_golden(GR, g)
+    attach_communicator(GR, F)
+    Diagnostics.primary_diag(GR.GRF[B200], **F.get(Diagnostics.fields_primary_diag, target=B200))
+    step_matsuno(GR, F, nsteps)
+    out = {'j0': GR.j0, 'j1': GR.j1}
+    for n in STATE + ['PHI', 'WWIND']:
+        F.to_host(GR, n)
+        out[n] = F.host[n]
+    np.savez(os.path.join(outdir, 'band%d.npz' % rank), **out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()
