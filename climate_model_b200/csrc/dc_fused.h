@@ -1,28 +1,32 @@
-// dc_fused.h -- the fused stage kernel of the Matsuno step ("v2").
+// dc_fused.h -- the fused stage kernel of the Matsuno step.
 //
 // One kernel advances U, V and POTT by one Matsuno stage: it replaces the reference's
 // UVFLX_prep_adv + UFLX_tendency + VFLX_tendency + POTT_tendency + make_timestep launches
 // (dyn_org_discretizations.py:121-273, :359-393) and never materialises UFLX/VFLX, the eight
-// auxiliary momentum fluxes, WWIND_UWIND/WWIND_VWIND or the tendencies in HBM:
+// auxiliary momentum fluxes, WWIND_UWIND/WWIND_VWIND or the tendencies in HBM.
 //
-//   thread block = a (TX x TY) tile of (lon, lat) columns, marched through the sigma levels;
-//   per level:  A) U, V of the tile + halo are staged in shared memory together with the
-//                  momentum fluxes UFLX, VFLX computed from them, and COLP_NEW*A*WWIND of
-//                  interface k+1;
-//               B) the eight auxiliary fluxes B..T are formed once per cell in shared memory;
-//               C) every thread adds up dUFLXdt, dVFLXdt, dPOTTdt of its cell (vertical flux
-//                  of interface k carried in registers from the previous level), applies the
-//                  pressure-weighted Euler step and stores the new U, V, POTT with their
-//                  boundary images.
+//   thread block = a (TX x TY) tile of (lon, lat) columns, marched through the sigma levels.
+//   The (tile + halo) planes of U, V, WWIND, PHI, POTT, PVTF, PVTFVB of level k+1 are copied
+//   global -> shared ASYNCHRONOUSLY (cp.async, double buffered) while level k is computed:
+//     A) UFLX, VFLX and COLP_NEW*A*WWIND(k+1) of the staged region -> shared memory
+//     B) the eight auxiliary fluxes B..T, once per cell, in shared memory
+//     C) every thread adds up dUFLXdt, dVFLXdt, dPOTTdt of its cell (vertical momentum flux
+//        of interface k carried in registers), applies the pressure-weighted Euler step and
+//        stores the new U, V, POTT with their boundary images.
 //
 // Every expression keeps the reference's evaluation order (dc_point.h), so the result is
-// bit-identical to the v1 kernels.  The block body is written against a tiny SPMD macro
-// layer so that tests/emu can execute the very same code on the host (a "phase" is a loop
-// over the block's threads there, thread-private state lives in arrays).
+// bit-identical to the one-kernel-per-reference-kernel mode.  The block body is written
+// against a tiny SPMD macro layer so that tests/emu can execute the very same code on the
+// host (a "phase" is a loop over the block's threads there, thread-private state lives in
+// arrays, an asynchronous copy is a plain copy).
 #pragma once
 #include "dc_geom.h"
 #include "dc_kernels.h"
 #include "dc_point.h"
+
+#if defined(__CUDA_ARCH__)
+#include <cuda_pipeline.h>
+#endif
 
 namespace dc {
 
@@ -32,7 +36,10 @@ constexpr int SN = SW * SH;
 constexpr int NQ = (SN + NT - 1) / NT;   // staged cells per thread (2)
 
 struct StageSmem {
-    double U[SN], V[SN], UF[SN], VF[SN], P[SN];
+    // raw planes, double buffered (filled by cp.async one level ahead)
+    double rU[2][SN], rV[2][SN], rW[2][SN], rPHI[2][SN], rT[2][SN], rPV[2][SN], rPB[2][SN];
+    // derived planes of the current level
+    double UF[SN], VF[SN], P[SN];
     double B[SN], C[SN], D[SN], E[SN], R[SN], Q[SN], S[SN], T[SN];
 };
 
@@ -45,12 +52,22 @@ struct StageSmem {
 #define DC_PHASE_END \
     }                \
     __syncthreads();
+#define DC_PHASE_END_NOSYNC }
+#define DC_ASYNC_COPY8(dst, src) __pipeline_memcpy_async((dst), (src), 8)
+#define DC_ASYNC_COMMIT() __pipeline_commit()
+#define DC_ASYNC_WAIT_AND_SYNC(n) \
+    __pipeline_wait_prior(n);     \
+    __syncthreads();
 #else
 #define DC_PRIV(type, name) type name[NT]
 #define DC_PRIVN(type, name, n) type name[NT][n]
 #define DC_P(name) name[tid]
 #define DC_PHASE for (int tid = 0; tid < NT; tid++) {
 #define DC_PHASE_END }
+#define DC_PHASE_END_NOSYNC }
+#define DC_ASYNC_COPY8(dst, src) (*(dst) = *(src))
+#define DC_ASYNC_COMMIT()
+#define DC_ASYNC_WAIT_AND_SYNC(n)
 #endif
 
 struct StageBody {
@@ -69,24 +86,24 @@ struct StageBody {
 
     DC_HD void run_block(int bx, int by, StageSmem &s) const
     {
-        const int nx = g.nx, ny = g.ny, nz = g.nz;
+        const int nx = g.nx, ny = g.ny, nz = g.nz, NI = g.NI;
         const int I0 = 1 + bx * TX, J0 = j_lo + by * TY;
         const size_t plane = g.plane;
+        const double dyis = g.dyis, dt = g.dt;
         // rows this rank holds (global): halo rows included
         const int j_min = (g.j0 - HJ < 0) ? 0 : g.j0 - HJ;
-        const int j_max_m = (g.j1 + HJ > ny + 1) ? ny + 1 : g.j1 + HJ;      // mass / x-staggered
+        const int j_max_m = (g.j1 + HJ > ny + 1) ? ny + 1 : g.j1 + HJ;          // mass rows
         const int j_max_y = (g.j1 + HJ + 1 > ny + 2) ? ny + 2 : g.j1 + HJ + 1;  // y-staggered
 
         // ---- thread-private state --------------------------------------------------------
-        DC_PRIVN(int, offU, NQ);     // plane offset of the staged U cells of this thread
-        DC_PRIVN(int, offV, NQ);
-        DC_PRIVN(int, offP, NQ);
+        DC_PRIVN(int, offM, NQ);     // plane offsets of this thread's staged cells: mass /
+        DC_PRIVN(int, offV, NQ);     //   x-staggered fields, and y-staggered fields
         DC_PRIVN(double, cu, NQ);    // (COLP[i-1,j] + COLP[i,j]) / 2
         DC_PRIVN(double, cv, NQ);    // (COLP[i,j-1] + COLP[i,j]) / 2
         DC_PRIVN(double, dxv, NQ);   // dxjs[j]
         DC_PRIVN(double, cp, NQ);    // COLP_NEW[i,j] * A[j]
         DC_PRIV(int, off0);          // plane offset of the own cell
-        DC_PRIV(int, valid);
+        DC_PRIV(int, flags);         // bit 0: cell is advanced; bit 1: cell has boundary images
         DC_PRIV(double, c);
         DC_PRIV(double, c_im1);
         DC_PRIV(double, c_ip1);
@@ -105,6 +122,13 @@ struct StageBody {
         DC_PRIV(double, pvb);        // PVTFVB[k] at (i,j), (i-1,j), (i,j-1)
         DC_PRIV(double, pvb_im1);
         DC_PRIV(double, pvb_jm1);
+        // own-column values fetched at the top of a level, used in phase C
+        DC_PRIV(double, u_kp1);
+        DC_PRIV(double, v_kp1);
+        DC_PRIV(double, pottvb_kp1);
+        DC_PRIV(double, u_old);
+        DC_PRIV(double, v_old);
+        DC_PRIV(double, t_old);
 
         // ---- set-up -----------------------------------------------------------------------
         DC_PHASE
@@ -119,30 +143,27 @@ struct StageBody {
                 // values are the ones the reference reads, and never-initialised halo cells
                 // (UWIND[nxs+1] of the python set-up BC, main_grid.py:340-343) are not touched.
                 const int iw = wrap_i(i), iwm = wrap_i(i - 1);
-                {   // U cell (x-staggered, rows 0 .. ny+1): UFLX = (C[i-1] + C[i])/2 * U * dyis
-                    const int jj = j > j_max_m ? j_max_m : j;
-                    DC_P(offU)[q] = (int)g.idx2(iw, jj);
-                    DC_P(cu)[q] = (COLP[g.idx2(iwm, jj)] + COLP[g.idx2(iw, jj)]) / 2.;
-                }
-                {   // V cell (y-staggered, rows 0 .. ny+2): VFLX = (C[j-1] + C[j])/2 * V * dxjs
-                    const int jj = j > j_max_y ? j_max_y : j;
-                    const int jc = jj > j_max_m ? j_max_m : jj;
-                    const int jcm = (jj - 1 < j_min) ? j_min : (jj - 1 > j_max_m ? j_max_m : jj - 1);
-                    DC_P(offV)[q] = (int)g.idx2(iw, jj);
-                    DC_P(cv)[q] = (COLP[g.idx2(iw, jcm)] + COLP[g.idx2(iw, jc)]) / 2.;
-                    DC_P(dxv)[q] = g.dxjs[g.row(jj)];
-                }
-                {   // WWIND cell (mass, rows 0 .. ny+1): COLP_NEW * A * WWIND
-                    const int jj = j > j_max_m ? j_max_m : j;
-                    DC_P(offP)[q] = (int)g.idx2(iw, jj);
-                    DC_P(cp)[q] = COLP_NEW[g.idx2(iw, jj)] * g.A[g.row(jj)];
-                }
+                const int jm = j > j_max_m ? j_max_m : j;   // row in a mass / x-staggered field
+                const int jy = j > j_max_y ? j_max_y : j;   // row in a y-staggered field
+                DC_P(offM)[q] = (int)g.idx2(iw, jm);
+                DC_P(offV)[q] = (int)g.idx2(iw, jy);
+                // UFLX = (C[i-1] + C[i])/2 * U * dyis     (dyn_continuity.py:40-41)
+                DC_P(cu)[q] = (COLP[g.idx2(iwm, jm)] + COLP[g.idx2(iw, jm)]) / 2.;
+                // VFLX = (C[j-1] + C[j])/2 * V * dxjs     (dyn_continuity.py:43-44)
+                const int jc = jy > j_max_m ? j_max_m : jy;
+                const int jcm = (jy - 1 < j_min) ? j_min : (jy - 1 > j_max_m ? j_max_m : jy - 1);
+                DC_P(cv)[q] = (COLP[g.idx2(iw, jcm)] + COLP[g.idx2(iw, jc)]) / 2.;
+                DC_P(dxv)[q] = g.dxjs[g.row(jy)];
+                // COLP_NEW * A * WWIND                    (dyn_functions.py:254-260)
+                DC_P(cp)[q] = COLP_NEW[g.idx2(iw, jm)] * g.A[g.row(jm)];
             }
             {
                 const int tx = tid % TX, ty = tid / TX;
                 const int i = I0 + tx, j = J0 + ty;
-                DC_P(valid) = (i <= nx) && (j <= j_hi);
+                const int valid = (i <= nx) && (j <= j_hi);
                 const int ii = i <= nx ? i : nx, jj = j <= j_hi ? j : j_hi;
+                const int edge = (ii <= 2) || (ii == nx) || (jj == 1) || (jj == ny);
+                DC_P(flags) = valid | (edge << 1);
                 DC_P(off0) = (int)g.idx2(ii, jj);
                 const double *C = COLP, *CN = COLP_NEW, *CO = COLP_OLD;
                 DC_P(c) = C[g.idx2(ii, jj)];
@@ -177,36 +198,114 @@ struct StageBody {
                 DC_P(pottvb_k) = POTTVB[DC_P(off0)];
                 DC_P(pvb) = PVTFVB[DC_P(off0)];
                 DC_P(pvb_im1) = PVTFVB[DC_P(off0) - 1];
-                DC_P(pvb_jm1) = PVTFVB[DC_P(off0) - g.NI];
+                DC_P(pvb_jm1) = PVTFVB[DC_P(off0) - NI];
             }
-        DC_PHASE_END
+            // prologue of the copy pipeline: level 0 -> buffer 0
+            for (int q = 0; q < NQ; q++) {
+                const int idx = tid + q * NT;
+                if (idx < SN) {
+                    const size_t om = DC_P(offM)[q], ov = DC_P(offV)[q];
+                    DC_ASYNC_COPY8(&s.rU[0][idx], UWIND + om);
+                    DC_ASYNC_COPY8(&s.rV[0][idx], VWIND + ov);
+                    DC_ASYNC_COPY8(&s.rW[0][idx], WWIND + plane + om);
+                    DC_ASYNC_COPY8(&s.rPHI[0][idx], PHI + om);
+                    DC_ASYNC_COPY8(&s.rT[0][idx], POTT + om);
+                    DC_ASYNC_COPY8(&s.rPV[0][idx], PVTF + om);
+                    DC_ASYNC_COPY8(&s.rPB[0][idx], PVTFVB + plane + om);
+                }
+            }
+            DC_ASYNC_COMMIT();
+        DC_PHASE_END_NOSYNC
 
         for (int k = 0; k < nz; k++) {
+            const int b = k & 1;
             const size_t ko = (size_t)k * plane;
             const double ds = g.dsigma[k];
-            // ---- A: stage U, V, UFLX, VFLX of level k and COLP_NEW*A*WWIND of interface k+1
+            const bool last = (k + 1 == nz);
+            // ---- prefetch: planes of level k+1 -> buffer 1-b; own-column scalars of level k
+            DC_PHASE
+                if (!last) {
+                    const size_t kn = ko + plane;
+                    for (int q = 0; q < NQ; q++) {
+                        const int idx = tid + q * NT;
+                        if (idx < SN) {
+                            const size_t om = kn + DC_P(offM)[q], ov = kn + DC_P(offV)[q];
+                            DC_ASYNC_COPY8(&s.rU[1 - b][idx], UWIND + om);
+                            DC_ASYNC_COPY8(&s.rV[1 - b][idx], VWIND + ov);
+                            DC_ASYNC_COPY8(&s.rW[1 - b][idx], WWIND + plane + om);
+                            DC_ASYNC_COPY8(&s.rPHI[1 - b][idx], PHI + om);
+                            DC_ASYNC_COPY8(&s.rT[1 - b][idx], POTT + om);
+                            DC_ASYNC_COPY8(&s.rPV[1 - b][idx], PVTF + om);
+                            DC_ASYNC_COPY8(&s.rPB[1 - b][idx], PVTFVB + plane + om);
+                        }
+                    }
+                    DC_ASYNC_COMMIT();
+                }
+                {
+                    const size_t o = ko + DC_P(off0);
+                    DC_P(u_kp1) = last ? 0. : UWIND[o + plane];
+                    DC_P(v_kp1) = last ? 0. : VWIND[o + plane];
+                    DC_P(pottvb_kp1) = POTTVB[o + plane];
+                    DC_P(u_old) = UWIND_OLD[o];
+                    DC_P(v_old) = VWIND_OLD[o];
+                    DC_P(t_old) = POTT_OLD[o];
+                }
+            DC_PHASE_END_NOSYNC
+            if (last) {
+                DC_ASYNC_WAIT_AND_SYNC(0)
+            } else {
+                DC_ASYNC_WAIT_AND_SYNC(1)
+            }
+            // ---- A: UFLX, VFLX of level k and COLP_NEW*A*WWIND of interface k+1 ----------
             DC_PHASE
                 for (int q = 0; q < NQ; q++) {
                     const int idx = tid + q * NT;
                     if (idx < SN) {
-                        const double u = UWIND[ko + DC_P(offU)[q]];
-                        const double v = VWIND[ko + DC_P(offV)[q]];
-                        s.U[idx] = u;
-                        s.V[idx] = v;
-                        s.UF[idx] = DC_P(cu)[q] * u * g.dyis;           // calc_UFLX
-                        s.VF[idx] = DC_P(cv)[q] * v * DC_P(dxv)[q];     // calc_VFLX
-                        if (k + 1 < nz) s.P[idx] = DC_P(cp)[q] * WWIND[ko + plane + DC_P(offP)[q]];
+                        s.UF[idx] = DC_P(cu)[q] * s.rU[b][idx] * dyis;          // calc_UFLX
+                        s.VF[idx] = DC_P(cv)[q] * s.rV[b][idx] * DC_P(dxv)[q];  // calc_VFLX
+                        s.P[idx] = DC_P(cp)[q] * s.rW[b][idx];
                     }
                 }
             DC_PHASE_END
-            // ---- B: auxiliary momentum fluxes (dyn_functions.py:429-536), once per cell
+            // ---- B: auxiliary momentum fluxes (dyn_functions.py:429-536), once per cell --
             DC_PHASE
-                for (int q = 0; q < NQ; q++) {
-                    const int idx = tid + q * NT;
-                    if (idx >= (TX + 2) * (TY + 2)) continue;
-                    const int ri = idx % (TX + 2) - 1, rj = idx / (TX + 2) - 1;
+                const double *u = s.UF, *v = s.VF;
+                {   // own cell: every flux is inside the staged region, no guards
+                    const int c0 = sidx(tid % TX, tid / TX);
+                    s.B[c0] = calc_BFLX(u[c0 - SW], u[c0 - SW + 1], u[c0], u[c0 + 1], u[c0 + SW],
+                                        u[c0 + SW + 1]);
+                    s.C[c0] = calc_CFLX(v[c0 - SW - 1], v[c0 - SW], v[c0 - 1], v[c0],
+                                        v[c0 + SW - 1], v[c0 + SW]);
+                    s.D[c0] = calc_DFLX(v[c0 - SW], v[c0], v[c0 + SW], u[c0 - SW], u[c0],
+                                        u[c0 - SW + 1], u[c0 + 1]);
+                    s.E[c0] = calc_EFLX(v[c0 - SW], v[c0], v[c0 + SW], u[c0 - SW], u[c0],
+                                        u[c0 - SW + 1], u[c0 + 1]);
+                    s.R[c0] = calc_RFLX(v[c0 - 1], v[c0 + SW - 1], v[c0], v[c0 + SW], v[c0 + 1],
+                                        v[c0 + SW + 1]);
+                    s.Q[c0] = calc_QFLX(u[c0 - SW - 1], u[c0 - 1], u[c0 - SW], u[c0],
+                                        u[c0 - SW + 1], u[c0 + 1]);
+                    s.S[c0] = calc_SFLX(v[c0 - 1], v[c0 + SW - 1], v[c0], v[c0 + SW], u[c0 - 1],
+                                        u[c0], u[c0 + 1]);
+                    s.T[c0] = calc_TFLX(v[c0 - 1], v[c0 + SW - 1], v[c0], v[c0 + SW], u[c0 - 1],
+                                        u[c0], u[c0 + 1]);
+                }
+                // frame around the tile: column ri = -1 / TX and row rj = -1 / TY
+                if (tid < 2 * (TX + 2) + 2 * TY) {
+                    int ri, rj;
+                    if (tid < TX + 2) {
+                        ri = tid - 1;
+                        rj = -1;
+                    } else if (tid < 2 * (TX + 2)) {
+                        ri = tid - (TX + 2) - 1;
+                        rj = TY;
+                    } else if (tid < 2 * (TX + 2) + TY) {
+                        ri = -1;
+                        rj = tid - 2 * (TX + 2);
+                    } else {
+                        ri = TX;
+                        rj = tid - 2 * (TX + 2) - TY;
+                    }
                     const int c0 = sidx(ri, rj);
-                    const double *u = s.UF, *v = s.VF;
                     if (ri <= TX - 1 && rj >= 0 && rj <= TY - 1)
                         s.B[c0] = calc_BFLX(u[c0 - SW], u[c0 - SW + 1], u[c0], u[c0 + 1],
                                             u[c0 + SW], u[c0 + SW + 1]);
@@ -239,35 +338,28 @@ struct StageBody {
                 const int i = I0 + tx, j = J0 + ty;
                 const int c0 = sidx(tx, ty);
                 const size_t o = ko + DC_P(off0);
-                const int NI = g.NI;
-                // values of the next level / interface of the own column
-                double u_kp1 = 0., v_kp1 = 0., w_kp1 = 0.;
-                if (k + 1 < nz) {
-                    u_kp1 = UWIND[o + plane];
-                    v_kp1 = VWIND[o + plane];
-                    w_kp1 = WWIND[o + plane];
-                }
-                const double pottvb_kp1 = POTTVB[o + plane];
-                const double pvb_kp1 = PVTFVB[o + plane];
-                const double pvb_im1_kp1 = PVTFVB[o + plane - 1];
-                const double pvb_jm1_kp1 = PVTFVB[o + plane - NI];
-                if (DC_P(valid)) {
-                    const double *U = s.U, *V = s.V;
+                const double w_kp1 = s.rW[b][c0];
+                const double pvb_kp1 = s.rPB[b][c0];
+                const double pvb_im1_kp1 = s.rPB[b][c0 - 1];
+                const double pvb_jm1_kp1 = s.rPB[b][c0 - SW];
+                if (DC_P(flags) & 1) {
+                    const double *U = s.rU[b], *V = s.rV[b], *T = s.rT[b];
                     const double u = U[c0], v = V[c0];
+                    const bool edge = DC_P(flags) & 2;
                     // vertical momentum fluxes through interface k+1
                     // (dyn_functions.py:211-270; 0 at the model bottom)
                     double wwu_kp1 = 0., wwv_kp1 = 0.;
-                    if (k + 1 < nz) {
+                    if (!last) {
                         const double *P = s.P;
                         const int wall = (j == 1) ? -1 : ((j == ny) ? 1 : 0);
                         wwu_kp1 = colpa_wwind(P[c0], P[c0 - 1], P[c0 - SW], P[c0 + SW],
                                               P[c0 - SW - 1], P[c0 + SW - 1], wall) *
-                                  interp_ks(u_kp1, u, g.dsigma[k + 1], ds);
+                                  interp_ks(DC_P(u_kp1), u, g.dsigma[k + 1], ds);
                         wwv_kp1 = colpa_wwind(P[c0], P[c0 - SW], P[c0 - 1], P[c0 + 1],
                                               P[c0 - SW - 1], P[c0 - SW + 1], 0) *
-                                  interp_ks(v_kp1, v, g.dsigma[k + 1], ds);
+                                  interp_ks(DC_P(v_kp1), v, g.dsigma[k + 1], ds);
                     }
-                    const double phi = PHI[o], pott = POTT[o], pvtf = PVTF[o];
+                    const double phi = s.rPHI[b][c0], pott = T[c0], pvtf = s.rPV[b][c0];
                     // ---------------- dUFLXdt (dyn_UFLX.py:69-199) ----------------
                     {
                         double bflx = s.B[c0], bflx_im1 = s.B[c0 - 1];
@@ -294,16 +386,20 @@ struct StageBody {
                                                V[c0 + SW - 1], u, U[c0 - 1], U[c0 + 1],
                                                g.corf_is[g.row(j)], g.cos_lat_is[g.row(j)],
                                                g.sin_lat_is[g.row(j)], g.dlon_rad, g.dlat_rad);
-                        d = d + pre_grad(phi, PHI[o - 1], DC_P(c), DC_P(c_im1), pott, POTT[o - 1],
-                                         pvtf, PVTF[o - 1], DC_P(pvb), DC_P(pvb_im1), pvb_im1_kp1,
-                                         pvb_kp1, ds, g.sigma_vb[k], g.sigma_vb[k + 1], g.dyis);
+                        d = d + pre_grad(phi, s.rPHI[b][c0 - 1], DC_P(c), DC_P(c_im1), pott,
+                                         T[c0 - 1], pvtf, s.rPV[b][c0 - 1], DC_P(pvb),
+                                         DC_P(pvb_im1), pvb_im1_kp1, pvb_kp1, ds, g.sigma_vb[k],
+                                         g.sigma_vb[k + 1], dyis);
                         const double coef = g.UVFLX_dif_coef[k];
                         if (coef > 0.)
                             d = d + num_dif(s.UF[c0], s.UF[c0 - 1], s.UF[c0 + 1], s.UF[c0 - SW],
                                             s.UF[c0 + SW], coef);
-                        put_xstag(g, UWIND_out, i, j, k,
-                                  euler_forward_pw(UWIND_OLD[o], d, DC_P(colpa_is),
-                                                   DC_P(colpa_old_is), g.dt));
+                        const double un = euler_forward_pw(DC_P(u_old), d, DC_P(colpa_is),
+                                                           DC_P(colpa_old_is), dt);
+                        if (edge)
+                            put_xstag(g, UWIND_out, i, j, k, un);
+                        else
+                            UWIND_out[o] = un;
                     }
                     // ---------------- dVFLXdt (dyn_VFLX.py:67-198) ----------------
                     if (j >= 2) {
@@ -319,43 +415,50 @@ struct StageBody {
                                                g.corf[g.row(j - 1)], g.cos_lat[g.row(j)],
                                                g.sin_lat[g.row(j)], g.cos_lat[g.row(j - 1)],
                                                g.sin_lat[g.row(j - 1)], g.dlon_rad, g.dlat_rad);
-                        d = d + pre_grad(phi, PHI[o - NI], DC_P(c), DC_P(c_jm1), pott,
-                                         POTT[o - NI], pvtf, PVTF[o - NI], DC_P(pvb),
+                        d = d + pre_grad(phi, s.rPHI[b][c0 - SW], DC_P(c), DC_P(c_jm1), pott,
+                                         T[c0 - SW], pvtf, s.rPV[b][c0 - SW], DC_P(pvb),
                                          DC_P(pvb_jm1), pvb_jm1_kp1, pvb_kp1, ds, g.sigma_vb[k],
                                          g.sigma_vb[k + 1], g.dxjs[g.row(j)]);
                         const double coef = g.UVFLX_dif_coef[k];
                         if (coef > 0.)
                             d = d + num_dif(s.VF[c0], s.VF[c0 - 1], s.VF[c0 + 1], s.VF[c0 - SW],
                                             s.VF[c0 + SW], coef);
-                        put_ystag(g, VWIND_out, i, j, k,
-                                  euler_forward_pw(VWIND_OLD[o], d, DC_P(colpa_js),
-                                                   DC_P(colpa_old_js), g.dt));
+                        const double vn = euler_forward_pw(DC_P(v_old), d, DC_P(colpa_js),
+                                                           DC_P(colpa_old_js), dt);
+                        if (edge)
+                            put_ystag(g, VWIND_out, i, j, k, vn);
+                        else
+                            VWIND_out[o] = vn;
                     } else {
                         put_ystag(g, VWIND_out, i, 1, k, 0.);
                     }
                     if (j == ny) put_ystag(g, VWIND_out, i, ny + 1, k, 0.);
                     // ---------------- dPOTTdt (dyn_POTT.py:55-110) ----------------
                     {
-                        const double p_im1 = POTT[o - 1], p_ip1 = POTT[o + 1];
-                        const double p_jm1 = POTT[o - NI], p_jp1 = POTT[o + NI];
+                        const double p_im1 = T[c0 - 1], p_ip1 = T[c0 + 1];
+                        const double p_jm1 = T[c0 - SW], p_jp1 = T[c0 + SW];
                         double d = 0.;
                         d = d + hor_adv(pott, p_im1, p_ip1, p_jm1, p_jp1, s.UF[c0], s.UF[c0 + 1],
                                         s.VF[c0], s.VF[c0 + SW], g.A[g.row(j)]);
-                        d = d + vert_adv(DC_P(pottvb_k), pottvb_kp1, DC_P(w_k), w_kp1,
+                        d = d + vert_adv(DC_P(pottvb_k), DC_P(pottvb_kp1), DC_P(w_k), w_kp1,
                                          DC_P(cnew), ds, k);
                         const double coef = g.POTT_dif_coef[k];
                         if (coef > 0.)
                             d = d + num_dif_pw(pott, p_im1, p_ip1, p_jm1, p_jp1, DC_P(c),
                                                DC_P(c_im1), DC_P(c_ip1), DC_P(c_jm1), DC_P(c_jp1),
                                                coef);
-                        put_mass(g, POTT_out, i, j, k,
-                                 euler_forward_pw(POTT_OLD[o], d, DC_P(cnew), DC_P(cold), g.dt));
+                        const double tn = euler_forward_pw(DC_P(t_old), d, DC_P(cnew), DC_P(cold),
+                                                           dt);
+                        if (edge)
+                            put_mass(g, POTT_out, i, j, k, tn);
+                        else
+                            POTT_out[o] = tn;
                     }
                     DC_P(wwu_k) = wwu_kp1;
                     DC_P(wwv_k) = wwv_kp1;
                 }
                 DC_P(w_k) = w_kp1;
-                DC_P(pottvb_k) = pottvb_kp1;
+                DC_P(pottvb_k) = DC_P(pottvb_kp1);
                 DC_P(pvb) = pvb_kp1;
                 DC_P(pvb_im1) = pvb_im1_kp1;
                 DC_P(pvb_jm1) = pvb_jm1_kp1;

@@ -49,13 +49,20 @@ static void dcb_launch(const Body &b, int i0, int i1, int j0, int j1, void *stre
 namespace dc {
 __global__ void __launch_bounds__(NT, 2) k_stage(const StageBody b)
 {
-    __shared__ StageSmem s;
-    b.run_block(blockIdx.x, blockIdx.y, s);
+    extern __shared__ __align__(16) unsigned char stage_smem[];
+    b.run_block(blockIdx.x, blockIdx.y, *reinterpret_cast<StageSmem *>(stage_smem));
 }
 }  // namespace dc
 static void dcb_launch_stage(const dc::StageBody &b, int nbx, int nby, void *stream)
 {
-    dc::k_stage<<<dim3(nbx, nby), dim3(dc::TX, dc::TY), 0, (cudaStream_t)stream>>>(b);
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(dc::k_stage, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(dc::StageSmem));
+        configured = true;
+    }
+    dc::k_stage<<<dim3(nbx, nby), dim3(dc::TX, dc::TY), sizeof(dc::StageSmem),
+                  (cudaStream_t)stream>>>(b);
 }
 
 // ---------------------------------------------------------------------------------------
