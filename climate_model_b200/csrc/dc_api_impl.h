@@ -381,11 +381,11 @@ int dc_create(const dc_grid_desc *d, dc_handle **out)
 
     // per-row arrays (device row = global j + jshift), per-level arrays
     const int NJ = g.NJ;
-    const size_t n_row = 8, n_lev = 5;
+    const size_t n_row = 9, n_lev = 7;
     std::vector<double> host(n_row * NJ + n_lev * (nz + 1), 0.);
     double *A = &host[0 * NJ], *dxjs = &host[1 * NJ], *corf = &host[2 * NJ],
            *corf_is = &host[3 * NJ], *cl = &host[4 * NJ], *sl = &host[5 * NJ],
-           *cl_is = &host[6 * NJ], *sl_is = &host[7 * NJ];
+           *cl_is = &host[6 * NJ], *sl_is = &host[7 * NJ], *rA = &host[8 * NJ];
     struct Src { const double *a; int fnx, fny, i_hi; const char *name; double *dst; int trig; };
     std::vector<double> lat, lat_is;
     const Src srcs[] = {
@@ -411,6 +411,7 @@ int dc_create(const dc_grid_desc *d, dc_handle **out)
             if (s.trig == 2) { cl_is[jd] = cos(r[j]); sl_is[jd] = sin(r[j]); }
         }
     }
+    for (int jd = 0; jd < NJ; jd++) rA[jd] = 1. / A[jd];
     double *lev = &host[n_row * NJ];
     double *sigma_vb = lev, *dsigma = lev + (nz + 1), *ucoef = lev + 2 * (nz + 1),
            *pcoef = lev + 3 * (nz + 1), *mcoef = lev + 4 * (nz + 1);
@@ -419,6 +420,11 @@ int dc_create(const dc_grid_desc *d, dc_handle **out)
     memcpy(ucoef, d->UVFLX_dif_coef, sizeof(double) * nz);
     memcpy(pcoef, d->POTT_dif_coef, sizeof(double) * nz);
     memcpy(mcoef, d->moist_dif_coef, sizeof(double) * nz);
+    double *rds = lev + 5 * (nz + 1), *rdss = lev + 6 * (nz + 1);
+    for (int k = 0; k < nz; k++) {
+        rds[k] = 1. / dsigma[k];
+        rdss[k] = k >= 1 ? 1. / (dsigma[k] + dsigma[k - 1]) : 0.;
+    }
 
     void *dev = nullptr;
     if (dcb_malloc(&dev, host.size() * sizeof(double)) ||
@@ -436,6 +442,7 @@ int dc_create(const dc_grid_desc *d, dc_handle **out)
     const double *dl = db + n_row * NJ;
     g.sigma_vb = dl; g.dsigma = dl + (nz + 1); g.UVFLX_dif_coef = dl + 2 * (nz + 1);
     g.POTT_dif_coef = dl + 3 * (nz + 1); g.moist_dif_coef = dl + 4 * (nz + 1);
+    g.r_A = db + 8 * NJ; g.r_dsigma = dl + 5 * (nz + 1); g.r_dss = dl + 6 * (nz + 1);
     h->launches = 0;
     h->profiling = 0;
     h->mode = DC_MODE_FUSED;

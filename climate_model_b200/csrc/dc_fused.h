@@ -30,17 +30,25 @@
 
 namespace dc {
 
-constexpr int TX = 32, TY = 8, NT = TX * TY;
+#ifndef DC_TY
+#define DC_TY 8
+#endif
+#ifndef DC_MINBLOCKS
+#define DC_MINBLOCKS 2
+#endif
+constexpr int TX = 32, TY = DC_TY, NT = TX * TY;
 constexpr int SW = TX + 3, SH = TY + 3;  // staged region: ri in [-1, TX+1], rj in [-1, TY+1]
-constexpr int SN = SW * SH;
-constexpr int NQ = (SN + NT - 1) / NT;   // staged cells per thread (2)
+constexpr int SN = SW * SH;              // cells of a y-staggered plane (V, VFLX)
+constexpr int SNM = SW * (SH - 1);       // every other plane: rows rj in [-1, TY]
+constexpr int NQ = (SN + NT - 1) / NT;   // staged cells per thread
 
 struct StageSmem {
     // raw planes, double buffered (filled by cp.async one level ahead)
-    double rU[2][SN], rV[2][SN], rW[2][SN], rPHI[2][SN], rT[2][SN], rPV[2][SN], rPB[2][SN];
+    double rU[2][SNM], rV[2][SN], rW[2][SNM], rPHI[2][SNM], rT[2][SNM], rPV[2][SNM],
+        rPB[2][SNM];
     // derived planes of the current level
-    double UF[SN], VF[SN], P[SN];
-    double B[SN], C[SN], D[SN], E[SN], R[SN], Q[SN], S[SN], T[SN];
+    double UF[SNM], VF[SN], P[SNM];
+    double B[SNM], C[SNM], D[SNM], E[SNM], R[SNM], Q[SNM], S[SNM], T[SNM];
 };
 
 #if defined(__CUDA_ARCH__)
@@ -115,6 +123,9 @@ struct StageBody {
         DC_PRIV(double, colpa_old_is);
         DC_PRIV(double, colpa_js);
         DC_PRIV(double, colpa_old_js);
+        DC_PRIV(double, r_colpa_is);  // reciprocals: DC_FAST_MATH only (dead otherwise)
+        DC_PRIV(double, r_colpa_js);
+        DC_PRIV(double, r_cnew);
         DC_PRIV(double, wwu_k);      // WWIND_UWIND at interface k (carried)
         DC_PRIV(double, wwv_k);
         DC_PRIV(double, w_k);        // WWIND[k]
@@ -192,6 +203,9 @@ struct StageBody {
                     CO[g.idx2(ii, jj)], CO[g.idx2(ii, jj - 1)], CO[g.idx2(ii - 1, jj)],
                     CO[g.idx2(ii + 1, jj)], CO[g.idx2(ii + 1, jj - 1)], CO[g.idx2(ii - 1, jj - 1)],
                     A, A_jm1);
+                DC_P(r_colpa_is) = DC_FAST ? 1. / DC_P(colpa_is) : 0.;
+                DC_P(r_colpa_js) = DC_FAST ? 1. / DC_P(colpa_js) : 0.;
+                DC_P(r_cnew) = DC_FAST ? 1. / DC_P(cnew) : 0.;
                 DC_P(wwu_k) = 0.;  // WWIND_UWIND[0] = 0 (dyn_functions.py:236-237)
                 DC_P(wwv_k) = 0.;
                 DC_P(w_k) = WWIND[DC_P(off0)];
@@ -203,10 +217,10 @@ struct StageBody {
             // prologue of the copy pipeline: level 0 -> buffer 0
             for (int q = 0; q < NQ; q++) {
                 const int idx = tid + q * NT;
-                if (idx < SN) {
-                    const size_t om = DC_P(offM)[q], ov = DC_P(offV)[q];
+                if (idx < SN) DC_ASYNC_COPY8(&s.rV[0][idx], VWIND + DC_P(offV)[q]);
+                if (idx < SNM) {
+                    const size_t om = DC_P(offM)[q];
                     DC_ASYNC_COPY8(&s.rU[0][idx], UWIND + om);
-                    DC_ASYNC_COPY8(&s.rV[0][idx], VWIND + ov);
                     DC_ASYNC_COPY8(&s.rW[0][idx], WWIND + plane + om);
                     DC_ASYNC_COPY8(&s.rPHI[0][idx], PHI + om);
                     DC_ASYNC_COPY8(&s.rT[0][idx], POTT + om);
@@ -221,6 +235,7 @@ struct StageBody {
             const int b = k & 1;
             const size_t ko = (size_t)k * plane;
             const double ds = g.dsigma[k];
+            const Div ds_d = mkdiv(ds, g.r_dsigma[k]);
             const bool last = (k + 1 == nz);
             // ---- prefetch: planes of level k+1 -> buffer 1-b; own-column scalars of level k
             DC_PHASE
@@ -228,10 +243,11 @@ struct StageBody {
                     const size_t kn = ko + plane;
                     for (int q = 0; q < NQ; q++) {
                         const int idx = tid + q * NT;
-                        if (idx < SN) {
-                            const size_t om = kn + DC_P(offM)[q], ov = kn + DC_P(offV)[q];
+                        if (idx < SN)
+                            DC_ASYNC_COPY8(&s.rV[1 - b][idx], VWIND + kn + DC_P(offV)[q]);
+                        if (idx < SNM) {
+                            const size_t om = kn + DC_P(offM)[q];
                             DC_ASYNC_COPY8(&s.rU[1 - b][idx], UWIND + om);
-                            DC_ASYNC_COPY8(&s.rV[1 - b][idx], VWIND + ov);
                             DC_ASYNC_COPY8(&s.rW[1 - b][idx], WWIND + plane + om);
                             DC_ASYNC_COPY8(&s.rPHI[1 - b][idx], PHI + om);
                             DC_ASYNC_COPY8(&s.rT[1 - b][idx], POTT + om);
@@ -260,9 +276,10 @@ struct StageBody {
             DC_PHASE
                 for (int q = 0; q < NQ; q++) {
                     const int idx = tid + q * NT;
-                    if (idx < SN) {
-                        s.UF[idx] = DC_P(cu)[q] * s.rU[b][idx] * dyis;          // calc_UFLX
+                    if (idx < SN)
                         s.VF[idx] = DC_P(cv)[q] * s.rV[b][idx] * DC_P(dxv)[q];  // calc_VFLX
+                    if (idx < SNM) {
+                        s.UF[idx] = DC_P(cu)[q] * s.rU[b][idx] * dyis;          // calc_UFLX
                         s.P[idx] = DC_P(cp)[q] * s.rW[b][idx];
                     }
                 }
@@ -351,13 +368,14 @@ struct StageBody {
                     double wwu_kp1 = 0., wwv_kp1 = 0.;
                     if (!last) {
                         const double *P = s.P;
+                        const Div dss_d = mkdiv(g.dsigma[k + 1] + ds, g.r_dss[k + 1]);
                         const int wall = (j == 1) ? -1 : ((j == ny) ? 1 : 0);
                         wwu_kp1 = colpa_wwind(P[c0], P[c0 - 1], P[c0 - SW], P[c0 + SW],
                                               P[c0 - SW - 1], P[c0 + SW - 1], wall) *
-                                  interp_ks(DC_P(u_kp1), u, g.dsigma[k + 1], ds);
+                                  interp_ks(DC_P(u_kp1), u, g.dsigma[k + 1], ds, dss_d);
                         wwv_kp1 = colpa_wwind(P[c0], P[c0 - SW], P[c0 - 1], P[c0 + 1],
                                               P[c0 - SW - 1], P[c0 - SW + 1], 0) *
-                                  interp_ks(DC_P(v_kp1), v, g.dsigma[k + 1], ds);
+                                  interp_ks(DC_P(v_kp1), v, g.dsigma[k + 1], ds, dss_d);
                     }
                     const double phi = s.rPHI[b][c0], pott = T[c0], pvtf = s.rPV[b][c0];
                     // ---------------- dUFLXdt (dyn_UFLX.py:69-199) ----------------
@@ -381,21 +399,22 @@ struct StageBody {
                                               U[c0 - SW - 1], U[c0 + SW - 1], U[c0 - SW + 1],
                                               U[c0 + SW + 1], bflx, bflx_im1, cflx, cflx_jp1,
                                               dflx_im1, dflx_jp1, eflx, eflx_im1_jp1, 1.);
-                        d = d + ((DC_P(wwu_k) - wwu_kp1) / ds);
+                        d = d + ((DC_P(wwu_k) - wwu_kp1) / ds_d);
                         d = d + coriolis_UWIND(DC_P(c), DC_P(c_im1), v, V[c0 - 1], V[c0 + SW],
                                                V[c0 + SW - 1], u, U[c0 - 1], U[c0 + 1],
                                                g.corf_is[g.row(j)], g.cos_lat_is[g.row(j)],
                                                g.sin_lat_is[g.row(j)], g.dlon_rad, g.dlat_rad);
                         d = d + pre_grad(phi, s.rPHI[b][c0 - 1], DC_P(c), DC_P(c_im1), pott,
                                          T[c0 - 1], pvtf, s.rPV[b][c0 - 1], DC_P(pvb),
-                                         DC_P(pvb_im1), pvb_im1_kp1, pvb_kp1, ds, g.sigma_vb[k],
+                                         DC_P(pvb_im1), pvb_im1_kp1, pvb_kp1, ds_d, g.sigma_vb[k],
                                          g.sigma_vb[k + 1], dyis);
                         const double coef = g.UVFLX_dif_coef[k];
                         if (coef > 0.)
                             d = d + num_dif(s.UF[c0], s.UF[c0 - 1], s.UF[c0 + 1], s.UF[c0 - SW],
                                             s.UF[c0 + SW], coef);
-                        const double un = euler_forward_pw(DC_P(u_old), d, DC_P(colpa_is),
-                                                           DC_P(colpa_old_is), dt);
+                        const double un = euler_forward_pw(
+                            DC_P(u_old), d, mkdiv(DC_P(colpa_is), DC_P(r_colpa_is)),
+                            DC_P(colpa_old_is), dt);
                         if (edge)
                             put_xstag(g, UWIND_out, i, j, k, un);
                         else
@@ -409,7 +428,7 @@ struct StageBody {
                                               V[c0 + SW + 1], s.R[c0], s.R[c0 - SW], s.Q[c0],
                                               s.Q[c0 + 1], s.S[c0 - SW], s.S[c0 + 1], s.T[c0],
                                               s.T[c0 - SW + 1], -1.);
-                        d = d + ((DC_P(wwv_k) - wwv_kp1) / ds);
+                        d = d + ((DC_P(wwv_k) - wwv_kp1) / ds_d);
                         d = d + coriolis_VWIND(DC_P(c), DC_P(c_jm1), u, U[c0 - SW], U[c0 + 1],
                                                U[c0 - SW + 1], g.corf[g.row(j)],
                                                g.corf[g.row(j - 1)], g.cos_lat[g.row(j)],
@@ -417,14 +436,15 @@ struct StageBody {
                                                g.sin_lat[g.row(j - 1)], g.dlon_rad, g.dlat_rad);
                         d = d + pre_grad(phi, s.rPHI[b][c0 - SW], DC_P(c), DC_P(c_jm1), pott,
                                          T[c0 - SW], pvtf, s.rPV[b][c0 - SW], DC_P(pvb),
-                                         DC_P(pvb_jm1), pvb_jm1_kp1, pvb_kp1, ds, g.sigma_vb[k],
+                                         DC_P(pvb_jm1), pvb_jm1_kp1, pvb_kp1, ds_d, g.sigma_vb[k],
                                          g.sigma_vb[k + 1], g.dxjs[g.row(j)]);
                         const double coef = g.UVFLX_dif_coef[k];
                         if (coef > 0.)
                             d = d + num_dif(s.VF[c0], s.VF[c0 - 1], s.VF[c0 + 1], s.VF[c0 - SW],
                                             s.VF[c0 + SW], coef);
-                        const double vn = euler_forward_pw(DC_P(v_old), d, DC_P(colpa_js),
-                                                           DC_P(colpa_old_js), dt);
+                        const double vn = euler_forward_pw(
+                            DC_P(v_old), d, mkdiv(DC_P(colpa_js), DC_P(r_colpa_js)),
+                            DC_P(colpa_old_js), dt);
                         if (edge)
                             put_ystag(g, VWIND_out, i, j, k, vn);
                         else
@@ -439,16 +459,17 @@ struct StageBody {
                         const double p_jm1 = T[c0 - SW], p_jp1 = T[c0 + SW];
                         double d = 0.;
                         d = d + hor_adv(pott, p_im1, p_ip1, p_jm1, p_jp1, s.UF[c0], s.UF[c0 + 1],
-                                        s.VF[c0], s.VF[c0 + SW], g.A[g.row(j)]);
+                                        s.VF[c0], s.VF[c0 + SW],
+                                        mkdiv(g.A[g.row(j)], g.r_A[g.row(j)]));
                         d = d + vert_adv(DC_P(pottvb_k), DC_P(pottvb_kp1), DC_P(w_k), w_kp1,
-                                         DC_P(cnew), ds, k);
+                                         DC_P(cnew), ds_d, k);
                         const double coef = g.POTT_dif_coef[k];
                         if (coef > 0.)
                             d = d + num_dif_pw(pott, p_im1, p_ip1, p_jm1, p_jp1, DC_P(c),
                                                DC_P(c_im1), DC_P(c_ip1), DC_P(c_jm1), DC_P(c_jp1),
                                                coef);
-                        const double tn = euler_forward_pw(DC_P(t_old), d, DC_P(cnew), DC_P(cold),
-                                                           dt);
+                        const double tn = euler_forward_pw(
+                            DC_P(t_old), d, mkdiv(DC_P(cnew), DC_P(r_cnew)), DC_P(cold), dt);
                         if (edge)
                             put_mass(g, POTT_out, i, j, k, tn);
                         else

@@ -55,6 +55,10 @@ struct Geom {
     const double *sin_lat_is;  // sin(GRF['lat_is_rad'][.,j])
     // per-level, length nz (+1 for sigma_vb)
     const double *sigma_vb, *dsigma, *UVFLX_dif_coef, *POTT_dif_coef, *moist_dif_coef;
+    // reciprocals used by the DC_FAST_MATH build only (dc_point.h: struct Div)
+    const double *r_A;        // 1 / A[row]
+    const double *r_dsigma;   // 1 / dsigma[k]
+    const double *r_dss;      // 1 / (dsigma[k] + dsigma[k-1]),  k >= 1
 
     DC_HD size_t idx(int i, int j, int k) const
     {

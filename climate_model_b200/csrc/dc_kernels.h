@@ -140,7 +140,7 @@ struct ContinuityBody {
         const double c_im1 = COLP[g.idx2(i - 1, j)], c_ip1 = COLP[g.idx2(i + 1, j)];
         const double c_jm1 = COLP[g.idx2(i, j - 1)], c_jp1 = COLP[g.idx2(i, j + 1)];
         const double dxjs = g.dxjs[g.row(j)], dxjs_jp1 = g.dxjs[g.row(j + 1)];
-        const double A = g.A[g.row(j)];
+        const Div A = mkdiv(g.A[g.row(j)], g.r_A[g.row(j)]);
         double s = 0.;  // sequential ascending sum (numba's FLXDIV.sum(axis=2))
         for (int k = 0; k < nz; k++) {
             const double uf = calc_UFLX(UWIND[g.idx(i, j, k)], c, c_im1, g.dyis);
@@ -161,9 +161,10 @@ struct ContinuityBody {
         const double cnew = COLP_OLD[g.idx2(i, j)] + g.dt * dcdt;
         dCOLPdt[g.idx2(i, j)] = dcdt;
         put_mass(g, COLP_NEW, i, j, 0, cnew);
+        const Div cn = mkdiv(cnew);
         for (int k = 1; k < nz; k++) {
             const double flxdivsum = WWIND[g.idx(i, j, k)];
-            put_mass(g, WWIND, i, j, k, (-flxdivsum / cnew - g.sigma_vb[k] * dcdt / cnew));
+            put_mass(g, WWIND, i, j, k, (-flxdivsum / cn - g.sigma_vb[k] * dcdt / cn));
         }
     }
 };
@@ -193,7 +194,7 @@ struct PrepBody {
                     colpa_wwind(P(i, j, k), P(i - 1, j, k), P(i, j - 1, k), P(i, j + 1, k),
                                 P(i - 1, j - 1, k), P(i - 1, j + 1, k), wall) *
                     interp_ks(UWIND[g.idx(i, j, k)], UWIND[g.idx(i, j, k - 1)], g.dsigma[k],
-                              g.dsigma[k - 1]);
+                              g.dsigma[k - 1], mkdiv(g.dsigma[k] + g.dsigma[k - 1], g.r_dss[k]));
         }
         if (i <= nx) {  // dyn_UVFLX_prepare.py:280-296
             WWIND_VWIND[g.idx(i, j, 0)] = 0.;
@@ -203,7 +204,7 @@ struct PrepBody {
                     colpa_wwind(P(i, j, k), P(i, j - 1, k), P(i - 1, j, k), P(i + 1, j, k),
                                 P(i - 1, j - 1, k), P(i + 1, j - 1, k), 0) *
                     interp_ks(VWIND[g.idx(i, j, k)], VWIND[g.idx(i, j, k - 1)], g.dsigma[k],
-                              g.dsigma[k - 1]);
+                              g.dsigma[k - 1], mkdiv(g.dsigma[k] + g.dsigma[k - 1], g.r_dss[k]));
         }
         for (int k = 0; k < nz; k++) {  // dyn_UVFLX_prepare.py:345-436
             CFLX[g.idx(i, j, k)] =
@@ -285,8 +286,8 @@ struct UFLXTendencyBody {
                                   U[g.idx(i + 1, j - 1, k)], U[g.idx(i + 1, j + 1, k)], bflx,
                                   bflx_im1, cflx, cflx_jp1, dflx_im1, dflx_jp1, eflx,
                                   eflx_im1_jp1, 1.);
-            d = d + ((WWIND_UWIND[g.idx(i, j, k)] - WWIND_UWIND[g.idx(i, j, k + 1)]) /
-                     g.dsigma[k]);
+            const Div ds = mkdiv(g.dsigma[k], g.r_dsigma[k]);
+            d = d + ((WWIND_UWIND[g.idx(i, j, k)] - WWIND_UWIND[g.idx(i, j, k + 1)]) / ds);
             d = d + coriolis_UWIND(c, c_im1, V[g.idx(i, j, k)], V[g.idx(i - 1, j, k)],
                                    V[g.idx(i, j + 1, k)], V[g.idx(i - 1, j + 1, k)], u, u_im1,
                                    u_ip1, corf_is, cosl, sinl, g.dlon_rad, g.dlat_rad);
@@ -294,7 +295,7 @@ struct UFLXTendencyBody {
                              POTT[g.idx(i, j, k)], POTT[g.idx(i - 1, j, k)], PVTF[g.idx(i, j, k)],
                              PVTF[g.idx(i - 1, j, k)], PVTFVB[g.idx(i, j, k)],
                              PVTFVB[g.idx(i - 1, j, k)], PVTFVB[g.idx(i - 1, j, k + 1)],
-                             PVTFVB[g.idx(i, j, k + 1)], g.dsigma[k], g.sigma_vb[k],
+                             PVTFVB[g.idx(i, j, k + 1)], ds, g.sigma_vb[k],
                              g.sigma_vb[k + 1], g.dyis);
             const double coef = g.UVFLX_dif_coef[k];
             if (coef > 0.)
@@ -340,8 +341,8 @@ struct VFLXTendencyBody {
                                   V[g.idx(i - 1, j + 1, k)], V[g.idx(i + 1, j + 1, k)], rflx,
                                   rflx_jm1, qflx, qflx_ip1, sflx_jm1, sflx_ip1, tflx,
                                   tflx_ip1_jm1, -1.);
-            d = d + ((WWIND_VWIND[g.idx(i, j, k)] - WWIND_VWIND[g.idx(i, j, k + 1)]) /
-                     g.dsigma[k]);
+            const Div ds = mkdiv(g.dsigma[k], g.r_dsigma[k]);
+            d = d + ((WWIND_VWIND[g.idx(i, j, k)] - WWIND_VWIND[g.idx(i, j, k + 1)]) / ds);
             d = d + coriolis_VWIND(c, c_jm1, U[g.idx(i, j, k)], U[g.idx(i, j - 1, k)],
                                    U[g.idx(i + 1, j, k)], U[g.idx(i + 1, j - 1, k)], corf,
                                    corf_jm1, cosl, sinl, cosl_jm1, sinl_jm1, g.dlon_rad,
@@ -350,7 +351,7 @@ struct VFLXTendencyBody {
                              POTT[g.idx(i, j, k)], POTT[g.idx(i, j - 1, k)], PVTF[g.idx(i, j, k)],
                              PVTF[g.idx(i, j - 1, k)], PVTFVB[g.idx(i, j, k)],
                              PVTFVB[g.idx(i, j - 1, k)], PVTFVB[g.idx(i, j - 1, k + 1)],
-                             PVTFVB[g.idx(i, j, k + 1)], g.dsigma[k], g.sigma_vb[k],
+                             PVTFVB[g.idx(i, j, k + 1)], ds, g.sigma_vb[k],
                              g.sigma_vb[k + 1], dxjs);
             const double coef = g.UVFLX_dif_coef[k];
             if (coef > 0.)
@@ -376,8 +377,9 @@ struct POTTTendencyBody {
         const double c_im1 = COLP[g.idx2(i - 1, j)], c_ip1 = COLP[g.idx2(i + 1, j)];
         const double c_jm1 = COLP[g.idx2(i, j - 1)], c_jp1 = COLP[g.idx2(i, j + 1)];
         const double cnew = COLP_NEW[g.idx2(i, j)];
-        const double A = g.A[g.row(j)];
+        const Div A = mkdiv(g.A[g.row(j)], g.r_A[g.row(j)]);
         for (int k = 0; k < nz; k++) {
+            const Div ds = mkdiv(g.dsigma[k], g.r_dsigma[k]);
             const double p = POTT[g.idx(i, j, k)];
             const double p_im1 = POTT[g.idx(i - 1, j, k)], p_ip1 = POTT[g.idx(i + 1, j, k)];
             const double p_jm1 = POTT[g.idx(i, j - 1, k)], p_jp1 = POTT[g.idx(i, j + 1, k)];
@@ -386,8 +388,7 @@ struct POTTTendencyBody {
                             UFLX[g.idx(i + 1, j, k)], VFLX[g.idx(i, j, k)],
                             VFLX[g.idx(i, j + 1, k)], A);
             d = d + vert_adv(POTTVB[g.idx(i, j, k)], POTTVB[g.idx(i, j, k + 1)],
-                             WWIND[g.idx(i, j, k)], WWIND[g.idx(i, j, k + 1)], cnew, g.dsigma[k],
-                             k);
+                             WWIND[g.idx(i, j, k)], WWIND[g.idx(i, j, k + 1)], cnew, ds, k);
             const double coef = g.POTT_dif_coef[k];
             if (coef > 0.)
                 d = d + num_dif_pw(p, p_im1, p_ip1, p_jm1, p_jp1, c, c_im1, c_ip1, c_jm1, c_jp1,
@@ -413,7 +414,7 @@ struct MoistTendencyBody {
         const double c_im1 = COLP[g.idx2(i - 1, j)], c_ip1 = COLP[g.idx2(i + 1, j)];
         const double c_jm1 = COLP[g.idx2(i, j - 1)], c_jp1 = COLP[g.idx2(i, j + 1)];
         const double cnew = COLP_NEW[g.idx2(i, j)];
-        const double A = g.A[g.row(j)];
+        const Div A = mkdiv(g.A[g.row(j)], g.r_A[g.row(j)]);
         double q = Q[g.idx(i, j, 0)];
         double qvb = q;  // unused at k = 0
         for (int k = 0; k < nz; k++) {
@@ -426,7 +427,7 @@ struct MoistTendencyBody {
                             VFLX[g.idx(i, j + 1, k)], A);
             const double qvb_kp1 = comp_VARVB_log(q_kp1, q);
             d = d + vert_adv(qvb, qvb_kp1, WWIND[g.idx(i, j, k)], WWIND[g.idx(i, j, k + 1)], cnew,
-                             g.dsigma[k], k);
+                             mkdiv(g.dsigma[k], g.r_dsigma[k]), k);
             const double coef = g.moist_dif_coef[k];
             if (coef > 0.)
                 d = d + num_dif_pw(q, q_im1, q_ip1, q_jm1, q_jp1, c, c_im1, c_ip1, c_jm1, c_jp1,
@@ -470,26 +471,27 @@ struct TimestepBody {
         const double colpa_old_js =
             interp_COLPA_js(co, CO[g.idx2(i, j - 1)], CO[g.idx2(i - 1, j)], CO[g.idx2(i + 1, j)],
                             CO[g.idx2(i + 1, j - 1)], CO[g.idx2(i - 1, j - 1)], A, A_jm1);
+        const Div d_is = mkdiv(colpa_is), d_js = mkdiv(colpa_js), d_c = mkdiv(c);
         for (int k = 0; k < nz; k++) {
             put_xstag(g, UWIND, i, j, k,
                       euler_forward_pw(UWIND_OLD[g.idx(i, j, k)], dUFLXdt[g.idx(i, j, k)],
-                                       colpa_is, colpa_old_is, g.dt));
+                                       d_is, colpa_old_is, g.dt));
             if (j >= 2)
                 put_ystag(g, VWIND, i, j, k,
                           euler_forward_pw(VWIND_OLD[g.idx(i, j, k)], dVFLXdt[g.idx(i, j, k)],
-                                           colpa_js, colpa_old_js, g.dt));
+                                           d_js, colpa_old_js, g.dt));
             else
                 put_ystag(g, VWIND, i, 1, k, 0.);
             if (j == ny) put_ystag(g, VWIND, i, ny + 1, k, 0.);
             put_mass(g, POTT, i, j, k,
-                     euler_forward_pw(POTT_OLD[g.idx(i, j, k)], dPOTTdt[g.idx(i, j, k)], c, co,
+                     euler_forward_pw(POTT_OLD[g.idx(i, j, k)], dPOTTdt[g.idx(i, j, k)], d_c, co,
                                       g.dt));
             if (g.i_moist) {
                 put_mass(g, QV, i, j, k,
-                         euler_forward_pw(QV_OLD[g.idx(i, j, k)], dQVdt[g.idx(i, j, k)], c, co,
+                         euler_forward_pw(QV_OLD[g.idx(i, j, k)], dQVdt[g.idx(i, j, k)], d_c, co,
                                           g.dt));
                 put_mass(g, QC, i, j, k,
-                         euler_forward_pw(QC_OLD[g.idx(i, j, k)], dQCdt[g.idx(i, j, k)], c, co,
+                         euler_forward_pw(QC_OLD[g.idx(i, j, k)], dQCdt[g.idx(i, j, k)], d_c, co,
                                           g.dt));
             }
         }
@@ -506,7 +508,8 @@ struct MoistEulerBody {
     double *QV, *QC;
     DC_HD void operator()(int i, int j) const
     {
-        const double c = COLP_NEW[g.idx2(i, j)], co = COLP_OLD[g.idx2(i, j)];
+        const double co = COLP_OLD[g.idx2(i, j)];
+        const Div c = mkdiv(COLP_NEW[g.idx2(i, j)]);
         for (int k = 0; k < g.nz; k++) {
             put_mass(g, QV, i, j, k,
                      euler_forward_pw(QV_OLD[g.idx(i, j, k)], dQVdt[g.idx(i, j, k)], c, co, g.dt));

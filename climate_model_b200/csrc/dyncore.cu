@@ -47,7 +47,7 @@ static void dcb_launch(const Body &b, int i0, int i1, int j0, int j1, void *stre
 
 #include "dc_fused.h"
 namespace dc {
-__global__ void __launch_bounds__(NT, 2) k_stage(const StageBody b)
+__global__ void __launch_bounds__(NT, DC_MINBLOCKS) k_stage(const StageBody b)
 {
     extern __shared__ __align__(16) unsigned char stage_smem[];
     b.run_block(blockIdx.x, blockIdx.y, *reinterpret_cast<StageSmem *>(stage_smem));

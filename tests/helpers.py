@@ -59,18 +59,25 @@ def state_err(n, got, ref):
 # product-side helpers (climate_model_b200 on a given libdyncore build)
 # ---------------------------------------------------------------------------------------
 EMU_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'emu')
+CUDA_LIB = os.path.join(os.path.dirname(EMU_DIR), '..', 'climate_model_b200', 'libdyncore.so')
+CUDA_LIB_STRICT = os.path.join(os.path.dirname(EMU_DIR), '..', 'climate_model_b200',
+                               'libdyncore_strict.so')
 
 
-def build_emu():
-    """compile tests/emu/libdyncore_emu.so (host emulation of the kernel bodies)"""
+def build_emu(fast=False):
+    """compile tests/emu/libdyncore_emu[_fast].so (host emulation of the kernel bodies);
+    same tiling as the CUDA build; `fast` = the production arithmetic mode (DC_FAST_MATH +
+    FMA contraction), default = strict (IEEE divisions, no FMA)"""
     import subprocess
-    so = os.path.join(EMU_DIR, 'libdyncore_emu.so')
+    so = os.path.join(EMU_DIR, 'libdyncore_emu_fast.so' if fast else 'libdyncore_emu.so')
     srcs = [os.path.join(EMU_DIR, 'emu_dyncore.cpp')]
     csrc = os.path.join(os.path.dirname(EMU_DIR), '..', 'climate_model_b200', 'csrc')
     srcs += [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith('.h')]
     if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
-        subprocess.check_call(['g++', '-O2', '-std=c++17', '-ffp-contract=off', '-fPIC', '-shared',
-                               '-o', so, srcs[0]])
+        mode = (['-DDC_FAST_MATH', '-mfma', '-ffp-contract=fast'] if fast
+                else ['-ffp-contract=off'])
+        subprocess.check_call(['g++', '-O2', '-std=c++17', '-fPIC', '-shared', '-DDC_TY=4'] + mode +
+                              ['-o', so, srcs[0]])
     return so
 
 

@@ -140,6 +140,36 @@ def test_fused_mode_equals_kernel_mode(g10, moist):
     assert np.all(out['fused']['dUFLXdt'] == 0.) and np.any(out['kernels']['dUFLXdt'] != 0.)
 
 
+@pytest.mark.parametrize('fixture,steps', [('ref_10deg_rand.npz', [10]), ('ref_5deg.npz', [10, 50])])
+def test_fast_math_mode_within_tolerance(fixture, steps):
+    """the PRODUCTION arithmetic mode (reciprocal multiplications, FMA contraction; dc_point.h
+    DC_FAST_MATH) against the reference's golden outputs, with the parity tolerances"""
+    from helpers import TOL, state_err
+    from climate_model_b200 import _lib
+    from climate_model_b200.dyn_matsuno import Diagnostics, step_matsuno
+    from climate_model_b200.io_read_namelist import B200
+    strict = _lib.library_path()
+    _lib.use_library(build_emu(fast=True))
+    try:
+        g = load_golden(fixture)
+        GR = grid_from_golden(g)
+        F = fields_from_golden(GR, g)
+        Diagnostics.primary_diag(GR.GRF[B200],
+                                 **F.get(Diagnostics.fields_primary_diag, target=B200))
+        done = 0
+        for s in steps:
+            step_matsuno(GR, F, s - done)
+            done = s
+            F.copy_device_to_host(GR, F.PROGNOSTIC_FIELDS)
+            ref = {n: g['N%d_%s' % (s, n)] for n in STATE}
+            for n in STATE:
+                e = state_err(n, F.host, ref)
+                assert e <= TOL[n], 'N%d %s: %.3e > %.0e' % (s, n, e, TOL[n])
+        GR.close()
+    finally:
+        _lib.use_library(strict)
+
+
 def test_factory_path_equals_coarse_entry(g10):
     from climate_model_b200.dyn_matsuno import (Diagnostics, step_matsuno,
                                                  step_matsuno_factories)

@@ -62,10 +62,21 @@ def test_primary_diag_close_to_oracle(g10):
         assert rel_err(F.host[n], O.F[n]) <= 1e-13, n
 
 
-def test_kernels_bit_exact_given_oracle_diagnostics(g10):
-    """feed the oracle's PVTF/PHI/... to the device: every tendency kernel, the continuity
-    and the Euler step must then reproduce the oracle bit for bit (no pow/log involved,
-    except moisture's log interpolation)"""
+@pytest.fixture()
+def strict_library():
+    """the strict CUDA build (IEEE divisions, -fmad=false) for the bit-exactness tests"""
+    from helpers import CUDA_LIB_STRICT
+    from climate_model_b200 import _lib
+    _lib.use_library(CUDA_LIB_STRICT)
+    assert _lib.is_cuda()
+    yield
+    _lib.use_library(_lib.DEFAULT_LIBRARY)
+
+
+def test_kernels_bit_exact_given_oracle_diagnostics(g10, strict_library):
+    """STRICT build.  Feed the oracle's PVTF/PHI/... to the device: every tendency kernel, the
+    continuity and the Euler step must then reproduce the oracle bit for bit (no pow/log
+    involved, except moisture's log interpolation)"""
     from climate_model_b200.dyn_matsuno import Prognostics
     from climate_model_b200.dyn_tendencies import compute_tendencies
     from climate_model_b200.io_read_namelist import B200
@@ -112,11 +123,15 @@ def test_kernels_bit_exact_given_oracle_diagnostics(g10):
         _eq(F.host[n], O.F[n], n)
 
 
+@pytest.mark.parametrize('build', ['production', 'strict'])
 @pytest.mark.parametrize('fixture,steps', [('ref_10deg_rand.npz', [1, 2, 10]),
                                            ('ref_5deg.npz', [10, 50])])
-def test_step_matsuno_against_reference_golden(fixture, steps):
-    """N Matsuno steps against the REAL reference's numba-CPU outputs"""
+def test_step_matsuno_against_reference_golden(fixture, steps, build, request):
+    """N Matsuno steps against the REAL reference's numba-CPU outputs, for the production
+    build (DC_FAST_MATH) and the strict build"""
     from climate_model_b200.dyn_matsuno import step_matsuno
+    if build == 'strict':
+        request.getfixturevalue('strict_library')
     g = load_golden(fixture)
     GR = grid_from_golden(g)
     F = fields_from_golden(GR, g)
