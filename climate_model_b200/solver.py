@@ -1,0 +1,84 @@
+"""Time loop of the model (reference: solver.py:40-255), dynamical core only.
+
+    python -m climate_model_b200.solver [--days D] [--nsteps N] [name=value ...]
+
+Builds Grid and ModelFields from the namelist (plus `name=value` overrides of grid / initial
+condition parameters), runs one primary_diag, then per time step: print-diagnostics every
+`nth_ts_print_diag` steps (vmax, mean COLP, NaN / over-speed crash check, reference
+io_functions.py:70-114), secondary_diag, step_matsuno -- all on the device.  The physics
+modules, NetCDF output and restart files of the reference are out of scope.
+"""
+import argparse
+import time
+
+import numpy as np
+import torch
+
+from . import namelist as nl
+from .dyn_matsuno import Diagnostics, step_matsuno
+from .io_read_namelist import B200
+from .main_fields import ModelFields
+from .main_grid import Grid
+
+GRID_KEYS = ('nz', 'lat0_deg', 'lat1_deg', 'dlat_deg', 'dlon_deg', 'i_out_nth_hour',
+             'i_sim_n_days', 'CFL', 'pair_top', 'i_moist_main_switch')
+
+
+def print_ts_info(GR, F):
+    """io_functions.py:70-114 on the device: vmax, mean COLP, crash check"""
+    js = GR.jshift
+    U = F.device['UWIND'][:, js + 1:js + int(GR.ny) + 1, 1:int(GR.nx) + 1]
+    V = F.device['VWIND'][:, js + 1:js + int(GR.ny) + 1, 1:int(GR.nx) + 1]
+    C = F.device['COLP'][0, js + 1:js + int(GR.ny) + 1, 1:int(GR.nx) + 1]
+    vmax = float(torch.maximum(U.abs().max(), V.abs().max()).item())
+    print('ts %6d  day %8.3f  vmax %8.3f m/s  mean COLP %12.3f Pa' %
+          (GR.ts, GR.sim_time_sec / 86400., vmax, float(C.mean().item())), flush=True)
+    if not np.isfinite(vmax) or vmax > 500.:
+        raise ValueError('MODEL CRASH')
+
+
+def run(nsteps=None, verbose=True, ic=None, **overrides):
+    """returns (GR, F) after the run; `overrides`: grid parameters, `ic`: initial-condition
+    parameters (initialize_fields)"""
+    GR = Grid(**{k: v for k, v in overrides.items() if k in GRID_KEYS})
+    F = ModelFields(GR, **(ic or {}))
+    Diagnostics.primary_diag(GR.GRF[B200], **F.get(Diagnostics.fields_primary_diag, target=B200))
+    nts = int(GR.nts) if nsteps is None else int(nsteps)
+    t0 = time.time()
+    while GR.ts < nts:
+        GR.timer.start('total')
+        GR.ts += 1
+        GR.sim_time_sec = GR.ts * GR.dt
+        if verbose and (GR.ts % nl.nth_ts_print_diag == 0 or GR.ts == 1):
+            print_ts_info(GR, F)
+        GR.timer.start('diag')
+        Diagnostics.secondary_diag(**F.get(Diagnostics.fields_secondary_diag, target=B200))
+        GR.timer.stop('diag')
+        step_matsuno(GR, F)
+        GR.timer.stop('total')
+    if F.torch_device.type == 'cuda':
+        torch.cuda.synchronize()
+    if verbose:
+        print_ts_info(GR, F)
+        cells = int(GR.nx) * int(GR.ny) * int(GR.nz)
+        dt = time.time() - t0
+        print('%d steps in %.2f s: %.3g cell-updates/s, %.1f x faster than reality' %
+              (nts, dt, cells * nts / dt, nts * GR.dt / dt))
+        GR.timer.print_report()
+    return GR, F
+
+
+def main():
+    ap = argparse.ArgumentParser(description=__doc__)
+    ap.add_argument('--nsteps', type=int, default=None)
+    ap.add_argument('overrides', nargs='*', help='name=value namelist overrides')
+    a = ap.parse_args()
+    ov, ic = {}, {}
+    for s in a.overrides:
+        k, v = s.split('=', 1)
+        (ov if k in GRID_KEYS else ic)[k] = float(v) if '.' in v or 'e' in v.lower() else int(v)
+    run(nsteps=a.nsteps, ic=ic, **ov)
+
+
+if __name__ == '__main__':
+    main()

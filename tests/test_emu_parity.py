@@ -233,3 +233,15 @@ def test_errors_are_loud(g10):
     bad = Grid(from_arrays=arrays)
     with pytest.raises(_lib.DyncoreError, match='varies with longitude'):
         bad.dyncore()
+
+
+def test_solver_entry_point_runs_and_stays_finite(capsys):
+    """solver.run: Grid + ModelFields from namelist-style overrides, primary/secondary diag,
+    step loop, print-diagnostics with the crash check"""
+    from climate_model_b200 import solver
+    GR, F = solver.run(nsteps=3, nz=6, lat0_deg=-80, lat1_deg=80, dlat_deg=10, dlon_deg=10,
+                       i_out_nth_hour=8)
+    assert GR.ts == 3 and GR.sim_time_sec == 3 * GR.dt
+    F.copy_device_to_host(GR, F.PROGNOSTIC_FIELDS)
+    assert np.isfinite(F.host['UWIND'][1:-2, 1:-1]).all()
+    assert 'vmax' in capsys.readouterr().out

@@ -147,7 +147,8 @@ def test_step_matsuno_against_reference_golden(fixture, steps, build, request):
             assert e <= TOL[n], 'N%d %s: %.3e > %.0e' % (s, n, e, TOL[n])
 
 
-def test_factory_path_equals_coarse_entry(g10):
+def test_factory_path_equals_coarse_entry(g10, strict_library):
+    """STRICT build: the factory-by-factory step and the fused coarse entry agree bitwise"""
     from climate_model_b200.dyn_matsuno import step_matsuno, step_matsuno_factories
     out = []
     for stepper in (step_matsuno, step_matsuno_factories):
@@ -163,9 +164,11 @@ def test_factory_path_equals_coarse_entry(g10):
 
 
 @pytest.mark.parametrize('moist', [1, 0])
-def test_fused_mode_equals_kernel_mode_bitwise(moist):
-    """the fused stage kernel against the one-kernel-per-reference-kernel mode on the device,
-    3 deg x 12 levels with topography (tiles cut by the domain edge in both directions)"""
+def test_fused_mode_equals_kernel_mode_bitwise(moist, strict_library):
+    """STRICT build: the fused stage kernel against the one-kernel-per-reference-kernel mode on
+    the device, 3 deg x 12 levels with topography (tiles cut by the domain edge in both
+    directions).  (In the production build FMA contraction differs between the two code paths;
+    there both are checked against the reference with the parity tolerances.)"""
     from climate_model_b200.dyn_matsuno import set_mode, step_matsuno
     from climate_model_b200.main_fields import ModelFields
     from climate_model_b200.main_grid import Grid
@@ -182,6 +185,22 @@ def test_fused_mode_equals_kernel_mode_bitwise(moist):
         out[mode] = {n: F.host[n].copy() for n in STATE + ['PHI', 'WWIND']}
     for n in STATE[:4] + (STATE[4:] if moist else []) + ['PHI', 'WWIND']:
         _eq(out['fused'][n], out['kernels'][n], n)
+
+
+def test_production_kernel_mode_within_tolerance(g10):
+    """PRODUCTION build, one-kernel-per-reference-kernel mode (what the factories run),
+    against the reference's golden outputs"""
+    from climate_model_b200.dyn_matsuno import set_mode, step_matsuno
+    GR = grid_from_golden(g10)
+    F = fields_from_golden(GR, g10)
+    set_mode(GR, 'kernels')
+    _diag(GR, F)
+    step_matsuno(GR, F, 10)
+    F.copy_device_to_host(GR, F.PROGNOSTIC_FIELDS)
+    ref = {n: g10['N10_' + n] for n in STATE}
+    for n in STATE:
+        e = state_err(n, F.host, ref)
+        assert e <= TOL[n], '%s: %.3e > %.0e' % (n, e, TOL[n])
 
 
 def test_config2_1deg_32lev_against_oracle():
