@@ -19,6 +19,7 @@ GRID_FIELDS_1D = ['sigma_vb', 'dsigma', 'UVFLX_dif_coef', 'POTT_dif_coef', 'mois
 
 DC_NK_2D, DC_NK_NZ, DC_NK_NZS = 0, 1, 2
 DC_MODE_FUSED, DC_MODE_KERNELS = 0, 1
+DC_PART_ALL, DC_PART_BOUNDARY, DC_PART_INTERIOR = 0, 1, 2
 
 
 class GridDesc(ctypes.Structure):
@@ -61,7 +62,7 @@ def _declare(lib):
     lib.dc_step_matsuno.argtypes = [vp, ctypes.c_int, vp]
     lib.dc_set_mode.argtypes = [vp, ctypes.c_int]
     lib.dc_step_begin.argtypes = [vp, vp]
-    lib.dc_stage_compute.argtypes = [vp, ctypes.c_int, vp]
+    lib.dc_stage_compute.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp]
     lib.dc_stage_diag.argtypes = [vp, ctypes.c_int, vp]
     lib.dc_halo_bytes.argtypes = [vp, ctypes.POINTER(ctypes.c_size_t)]
     lib.dc_halo_pack.argtypes = [vp, ctypes.c_int, vp, vp, vp]

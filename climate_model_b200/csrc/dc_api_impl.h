@@ -243,7 +243,10 @@ static int do_primary_diag(dc_handle *h, void *stream)
 // step until stage 2 overwrites it cell by cell; S1 = {UWIND_OLD, ...} receives the estimate
 // of stage 1.  No OLD <- current copies of 3-D fields are needed.
 // ---------------------------------------------------------------------------------------
-static void do_stage_fused(dc_handle *h, int stage, void *stream)
+// part: DC_PART_ALL, or DC_PART_BOUNDARY (continuity + the tile rows that hold the two
+// outermost owned rows on each side: what the neighbours wait for) followed by
+// DC_PART_INTERIOR (the remaining tile rows)
+static void do_stage_fused(dc_handle *h, int stage, int part, void *stream)
 {
     const Fields &f = h->f;
     const Geom &g = h->g;
@@ -251,18 +254,36 @@ static void do_stage_fused(dc_handle *h, int stage, void *stream)
                  *T = stage == 0 ? f.POTT : f.POTT_OLD;
     double *Uo = stage == 0 ? f.UWIND_OLD : f.UWIND, *Vo = stage == 0 ? f.VWIND_OLD : f.VWIND,
            *To = stage == 0 ? f.POTT_OLD : f.POTT;
-    if (g.i_moist)
-        launch_continuity<2>(h, U, V, stream);   // moisture kernels read UFLX / VFLX
-    else
-        launch_continuity<0>(h, U, V, stream);
-    StageBody sb{g,      U,          V,          T,       f.PHI,   f.PVTF,  f.PVTFVB, f.POTTVB,
-                 f.WWIND, f.COLP,    f.COLP_NEW, f.COLP_OLD, f.UWIND, f.VWIND, f.POTT,
-                 Uo,     Vo,         To,         g.j0,    g.j1};
-    if (h->profiling) dcb_profile_begin(h, "stage_fused", stream);
-    dcb_launch_stage(sb, (g.nx + TX - 1) / TX, (g.j1 - g.j0 + TY) / TY, stream);
-    if (h->profiling) dcb_profile_end(h, stream);
-    h->launches++;
-    if (g.i_moist) {
+    if (part != DC_PART_INTERIOR) {
+        if (g.i_moist)
+            launch_continuity<2>(h, U, V, stream);   // moisture kernels read UFLX / VFLX
+        else
+            launch_continuity<0>(h, U, V, stream);
+    }
+    // tile rows of the band: [j0, j1] in steps of TY; boundary = first and last tile row
+    const int ntr = (g.j1 - g.j0 + TY) / TY;
+    const int nb = ntr >= 4 ? 1 : 0;          // too few tile rows: no split, all in "boundary"
+    struct Range { int lo, hi; } ranges[2];
+    int nr = 0;
+    if (part == DC_PART_ALL || nb == 0) {
+        if (part != DC_PART_INTERIOR) ranges[nr++] = Range{g.j0, g.j1};
+    } else if (part == DC_PART_BOUNDARY) {
+        ranges[nr++] = Range{g.j0, g.j0 + TY - 1};
+        ranges[nr++] = Range{g.j0 + (ntr - 1) * TY, g.j1};
+    } else {
+        ranges[nr++] = Range{g.j0 + TY, g.j0 + (ntr - 1) * TY - 1};
+    }
+    for (int r = 0; r < nr; r++) {
+        StageBody sb{g,       U,      V,          T,          f.PHI,   f.PVTF,  f.PVTFVB, f.POTTVB,
+                     f.WWIND, f.COLP, f.COLP_NEW, f.COLP_OLD, f.UWIND, f.VWIND, f.POTT,
+                     Uo,      Vo,     To,         ranges[r].lo, ranges[r].hi};
+        if (h->profiling) dcb_profile_begin(h, "stage_fused", stream);
+        dcb_launch_stage(sb, (g.nx + TX - 1) / TX, (ranges[r].hi - ranges[r].lo + TY) / TY, stream);
+        if (h->profiling) dcb_profile_end(h, stream);
+        h->launches++;
+    }
+    if (g.i_moist && part != DC_PART_INTERIOR) {
+        // the moisture tracers still use the kernel-mode tendency kernel: whole band at once
         const double *QV = stage == 0 ? f.QV : f.QV_OLD, *QC = stage == 0 ? f.QC : f.QC_OLD;
         double *QVo = stage == 0 ? f.QV_OLD : f.QV, *QCo = stage == 0 ? f.QC_OLD : f.QC;
         MoistTendencyBody m{g, QV, QC, f.UFLX, f.VFLX, f.COLP, f.WWIND, f.COLP_NEW, f.dQVdt,
@@ -662,15 +683,17 @@ int dc_step_begin(dc_handle *h, void *stream)
     return backend_status("dc_step_begin");
 }
 
-int dc_stage_compute(dc_handle *h, int stage, void *stream)
+int dc_stage_compute(dc_handle *h, int stage, int part, void *stream)
 {
-    if (!h || stage < 0 || stage > 1) return fail(DC_ERR_ARG, "dc_stage_compute: bad argument");
+    if (!h || stage < 0 || stage > 1 || part < DC_PART_ALL || part > DC_PART_INTERIOR)
+        return fail(DC_ERR_ARG, "dc_stage_compute: bad argument");
     int rc;
     if ((rc = check_fused_fields(h, "dc_stage_compute"))) return rc;
     if (h->g.j1 - h->g.j0 + 1 < HJ)
         return fail(DC_ERR_STATE, "dc_stage_compute: a band needs at least %d rows", HJ);
-    do_stage_fused(h, stage, stream);
-    dcb_d2d_async(h->f.COLP, h->f.COLP_NEW, h->g.plane * sizeof(double), stream);
+    do_stage_fused(h, stage, part, stream);
+    if (part != DC_PART_BOUNDARY)   // COLP is read by every stage-kernel launch of the stage
+        dcb_d2d_async(h->f.COLP, h->f.COLP_NEW, h->g.plane * sizeof(double), stream);
     return backend_status("dc_stage_compute");
 }
 
@@ -684,7 +707,7 @@ int dc_stage_diag(dc_handle *h, int stage, void *stream)
 }
 
 // fields whose boundary rows travel after a stage: the stage's output state + COLP
-static int halo_fields(const dc_handle *h, int stage, double **F, int *nk)
+static int halo_fields(const dc_handle *h, int stage, int to_buf, double **F, int *nk)
 {
     const Fields &f = h->f;
     const Geom &g = h->g;
@@ -696,7 +719,9 @@ static int halo_fields(const dc_handle *h, int stage, double **F, int *nk)
         F[n] = stage == 0 ? f.QV_OLD : f.QV; nk[n++] = g.nz;
         F[n] = stage == 0 ? f.QC_OLD : f.QC; nk[n++] = g.nz;
     }
-    F[n] = f.COLP; nk[n++] = 1;
+    // the new column pressure: sent from COLP_NEW (COLP is overwritten only after the last
+    // stage-kernel launch of the stage), received into the halo rows of COLP
+    F[n] = to_buf ? f.COLP_NEW : f.COLP; nk[n++] = 1;
     return n;
 }
 
@@ -718,22 +743,25 @@ static int halo_move(dc_handle *h, int stage, double *south, double *north, int 
     const Geom &g = h->g;
     double *F[8];
     int nk[8];
-    const int n = halo_fields(h, stage, F, nk);
+    const int n = halo_fields(h, stage, to_buf, F, nk);
     // pack: the two outermost OWNED rows; unpack: the two halo rows beyond the band
     const int j_south = to_buf ? g.j0 : g.j0 - HJ;
     const int j_north = to_buf ? g.j1 - HJ + 1 : g.j1 + 1;
-    size_t off = 0;
+    if (!south && !north) return DC_OK;
+    HaloPackBody b;
+    b.g = g;
+    b.nf = n;
     for (int m = 0; m < n; m++) {
-        if (south) {
-            HaloPackBody b{g, F[m], south + off, j_south, nk[m], to_buf};
-            launch(h, to_buf ? "halo_pack" : "halo_unpack", b, 0, g.NI - 1, 0, HJ - 1, stream);
-        }
-        if (north) {
-            HaloPackBody b{g, F[m], north + off, j_north, nk[m], to_buf};
-            launch(h, to_buf ? "halo_pack" : "halo_unpack", b, 0, g.NI - 1, 0, HJ - 1, stream);
-        }
-        off += (size_t)nk[m] * HJ * g.NI;
+        b.F[m] = F[m];
+        b.nk[m] = nk[m];
     }
+    b.south = south;
+    b.north = north;
+    b.j_south = j_south;
+    b.j_north = j_north;
+    b.to_buf = to_buf;
+    // one launch for all fields and both directions
+    launch(h, to_buf ? "halo_pack" : "halo_unpack", b, 0, g.NI - 1, 0, HJ - 1, stream);
     return backend_status(what);
 }
 
@@ -781,7 +809,7 @@ int dc_step_matsuno(dc_handle *h, int nsteps, void *stream)
         for (int s = 0; s < nsteps; s++) {
             dcb_d2d_async(f.COLP_OLD, f.COLP, b2, stream);      // dyn_matsuno.py:34
             for (int stage = 0; stage < 2; stage++) {            // estimate, final
-                do_stage_fused(h, stage, stream);
+                do_stage_fused(h, stage, DC_PART_ALL, stream);
                 dcb_d2d_async(f.COLP, f.COLP_NEW, b2, stream);  // dyn_matsuno.py:64-67
                 do_diag_fused(h, stage, stream);
             }

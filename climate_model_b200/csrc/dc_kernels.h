@@ -104,19 +104,30 @@ struct ExchangeBCBody {
 // threads: i in [0, NI-1], "j" = r in [0, 1]; copies device rows (global) j_row + r
 // ---------------------------------------------------------------------------------------
 struct HaloPackBody {
+    static constexpr int MAXF = 6;
     Geom g;
-    double *F;      // field (nk planes)
-    double *buf;    // message segment of this field
-    int j_row, nk, to_buf;
+    double *F[MAXF];   // fields (nk[m] planes each), message segments in this order
+    int nk[MAXF];
+    int nf;
+    double *south, *north;   // message buffers (NULL: that side is a domain wall)
+    int j_south, j_north;    // first of the two rows on each side
+    int to_buf;
     DC_HD void operator()(int i, int r) const
     {
-        for (int k = 0; k < nk; k++) {
-            const size_t a = g.idx(i, j_row + r, k);
-            const size_t b = ((size_t)k * 2 + r) * (size_t)g.NI + i;
-            if (to_buf)
-                buf[b] = F[a];
-            else
-                F[a] = buf[b];
+        size_t off = 0;
+        for (int m = 0; m < nf; m++) {
+            for (int k = 0; k < nk[m]; k++) {
+                const size_t b = off + ((size_t)k * 2 + r) * (size_t)g.NI + i;
+                if (south) {
+                    const size_t a = g.idx(i, j_south + r, k);
+                    if (to_buf) south[b] = F[m][a]; else F[m][a] = south[b];
+                }
+                if (north) {
+                    const size_t a = g.idx(i, j_north + r, k);
+                    if (to_buf) north[b] = F[m][a]; else F[m][a] = north[b];
+                }
+            }
+            off += (size_t)nk[m] * 2 * g.NI;
         }
     }
 };

@@ -37,13 +37,14 @@ class BandCommunicator:
             return torch.empty(self.nelem, dtype=torch.float64, device=dev) if present else None
         self.send_s, self.recv_s = buf(self.south is not None), buf(self.south is not None)
         self.send_n, self.recv_n = buf(self.north is not None), buf(self.north is not None)
+        self.comm_stream = None
 
     @staticmethod
     def _ptr(t):
         return t.data_ptr() if t is not None else None
 
-    def exchange(self, stage, stream):
-        """pack -> grouped send/recv with both neighbours -> unpack, all stream-ordered"""
+    def _post(self, stage, stream):
+        """pack on `stream`, then post the grouped send/recv with both neighbours"""
         L, h = _lib.lib(), self.GR.dyncore()
         _lib.check(L.dc_halo_pack(h, stage, self._ptr(self.send_s), self._ptr(self.send_n),
                                   stream))
@@ -54,11 +55,39 @@ class BandCommunicator:
         if self.north is not None:
             ops.append(dist.P2POp(dist.isend, self.send_n, self.north, self.group))
             ops.append(dist.P2POp(dist.irecv, self.recv_n, self.north, self.group))
-        if ops:
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
-        _lib.check(L.dc_halo_unpack(h, stage, self._ptr(self.recv_s), self._ptr(self.recv_n),
-                                    stream))
+        return dist.batch_isend_irecv(ops) if ops else []
+
+    def _finish(self, stage, works, stream):
+        for w in works:
+            w.wait()          # NCCL: the current stream waits; gloo: the host waits
+        _lib.check(_lib.lib().dc_halo_unpack(self.GR.dyncore(), stage, self._ptr(self.recv_s),
+                                             self._ptr(self.recv_n), stream))
+
+    def stage(self, stage, stream):
+        """one Matsuno stage on this band.  On CUDA the exchange of the boundary rows runs on
+        a second stream while the interior tile rows are computed."""
+        L, h = _lib.lib(), self.GR.dyncore()
+        dev = self.F.torch_device
+        if dev.type != 'cuda':
+            _lib.check(L.dc_stage_compute(h, stage, _lib.DC_PART_ALL, stream))
+            self._finish(stage, self._post(stage, stream), stream)
+        else:
+            if self.comm_stream is None:
+                self.comm_stream = torch.cuda.Stream(device=dev)
+            main = torch.cuda.current_stream(dev)
+            _lib.check(L.dc_stage_compute(h, stage, _lib.DC_PART_BOUNDARY, stream))
+            ready = torch.cuda.Event()
+            ready.record(main)
+            with torch.cuda.stream(self.comm_stream):
+                self.comm_stream.wait_event(ready)
+                works = self._post(stage, self.comm_stream.cuda_stream)
+            _lib.check(L.dc_stage_compute(h, stage, _lib.DC_PART_INTERIOR, stream))
+            self._finish(stage, works, stream)
+            # the message buffers are reused by the next stage's pack on the comm stream
+            done = torch.cuda.Event()
+            done.record(main)
+            self.comm_stream.wait_event(done)
+        _lib.check(L.dc_stage_diag(h, stage, stream))
 
 
 def attach_communicator(GR, F, group=None):
@@ -72,6 +101,4 @@ def step_matsuno_banded(GR, F, nsteps, stream):
     for _ in range(int(nsteps)):
         _lib.check(L.dc_step_begin(h, stream))
         for stage in (0, 1):
-            _lib.check(L.dc_stage_compute(h, stage, stream))
-            comm.exchange(stage, stream)
-            _lib.check(L.dc_stage_diag(h, stage, stream))
+            comm.stage(stage, stream)

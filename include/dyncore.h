@@ -134,9 +134,14 @@ int dc_step_matsuno(dc_handle *h, int nsteps, void *stream);
  * send/recv by the caller -> dc_halo_unpack), then dc_stage_diag on all held rows.
  * dc_step_begin once per step.  Messages are contiguous buffers of dc_halo_bytes() bytes per
  * direction; pass NULL for a direction that ends at a domain wall.  The result is bitwise
- * identical to the single-device run (no cross-rank reductions). */
+ * identical to the single-device run (no cross-rank reductions).
+ * Overlap: dc_stage_compute(DC_PART_BOUNDARY) computes what the neighbours wait for (continuity
+ * and the outermost tile rows); the caller can then pack + send on a second stream while
+ * dc_stage_compute(DC_PART_INTERIOR) runs; dc_halo_unpack must follow the INTERIOR / ALL call
+ * (it writes the halo rows of COLP, which the stage kernel reads). */
+enum { DC_PART_ALL = 0, DC_PART_BOUNDARY = 1, DC_PART_INTERIOR = 2 };
 int dc_step_begin(dc_handle *h, void *stream);
-int dc_stage_compute(dc_handle *h, int stage, void *stream);
+int dc_stage_compute(dc_handle *h, int stage, int part, void *stream);
 int dc_stage_diag(dc_handle *h, int stage, void *stream);
 int dc_halo_bytes(const dc_handle *h, size_t *nbytes);
 int dc_halo_pack(dc_handle *h, int stage, void *send_south, void *send_north, void *stream);

@@ -245,3 +245,36 @@ def test_solver_entry_point_runs_and_stays_finite(capsys):
     F.copy_device_to_host(GR, F.PROGNOSTIC_FIELDS)
     assert np.isfinite(F.host['UWIND'][1:-2, 1:-1]).all()
     assert 'vmax' in capsys.readouterr().out
+
+
+@pytest.mark.parametrize('fixture', ['ref_10deg_rand.npz', 'ref_5deg.npz'])
+def test_boundary_interior_split_equals_whole_stage(fixture):
+    """the band entries with the stage kernel split into boundary and interior tile rows (what
+    the NCCL run overlaps with the halo exchange) against dc_step_matsuno"""
+    from climate_model_b200 import _lib
+    from climate_model_b200.dyn_matsuno import Diagnostics, _bind_all, step_matsuno
+    from climate_model_b200.io_read_namelist import B200
+    g = load_golden(fixture)
+    out = []
+    for split in (False, True):
+        GR = grid_from_golden(g)
+        F = fields_from_golden(GR, g)
+        Diagnostics.primary_diag(GR.GRF[B200],
+                                 **F.get(Diagnostics.fields_primary_diag, target=B200))
+        if not split:
+            step_matsuno(GR, F, 2)
+        else:
+            L, h = _lib.lib(), GR.dyncore()
+            _bind_all(GR, F)
+            for _ in range(2):
+                _lib.check(L.dc_step_begin(h, 0))
+                for stage in (0, 1):
+                    _lib.check(L.dc_stage_compute(h, stage, _lib.DC_PART_BOUNDARY, 0))
+                    _lib.check(L.dc_halo_pack(h, stage, None, None, 0))
+                    _lib.check(L.dc_stage_compute(h, stage, _lib.DC_PART_INTERIOR, 0))
+                    _lib.check(L.dc_halo_unpack(h, stage, None, None, 0))
+                    _lib.check(L.dc_stage_diag(h, stage, 0))
+        F.copy_device_to_host(GR, F.ALL_FIELDS)
+        out.append({n: F.host[n].copy() for n in STATE + ['PHI', 'WWIND']})
+    for n in STATE + ['PHI', 'WWIND']:
+        _eq(out[0][n], out[1][n], n)
