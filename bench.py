@@ -176,6 +176,7 @@ def main():
     if args.impl == 'reference':
         return run_reference(args, wl, moist)
 
+    os.environ['NCCL_DEBUG'] = os.environ.get('DC_NCCL_DEBUG', 'WARN')   # keep stdout = the JSON line
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -255,7 +256,9 @@ def main():
         ms = float(t.item())
     ms_per_step = ms / args.steps
     value = cells / (ms_per_step * 1e-3)
-    ok = bool(torch.isfinite(F.device['UWIND']).all().item())
+    js = GR.jshift   # owned rows, interior columns (halo cells beyond are never read)
+    ok = bool(torch.isfinite(F.device['UWIND'][:, GR.j0 + js:GR.j1 + js + 1, 1:int(GR.nx) + 1])
+              .all().item())
 
     # ---- end to end through the public field API: host state -> device -> step -> host
     names = ['UWIND', 'VWIND', 'POTT', 'COLP'] + (['QV', 'QC'] if moist else [])

@@ -761,7 +761,7 @@ static int halo_move(dc_handle *h, int stage, double *south, double *north, int 
     b.j_north = j_north;
     b.to_buf = to_buf;
     // one launch for all fields and both directions
-    launch(h, to_buf ? "halo_pack" : "halo_unpack", b, 0, g.NI - 1, 0, HJ - 1, stream);
+    launch(h, to_buf ? "halo_pack" : "halo_unpack", b, 0, g.NI - 1, 0, 2 * (g.nz + 1) - 1, stream);
     return backend_status(what);
 }
 

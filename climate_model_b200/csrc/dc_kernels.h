@@ -100,8 +100,8 @@ struct ExchangeBCBody {
 };
 
 // ---------------------------------------------------------------------------------------
-// latitude-band halo rows <-> contiguous message buffer [k][2][NI].
-// threads: i in [0, NI-1], "j" = r in [0, 1]; copies device rows (global) j_row + r
+// latitude-band halo rows <-> contiguous message buffers [field][k][2][NI], both directions
+// and all fields in one launch
 // ---------------------------------------------------------------------------------------
 struct HaloPackBody {
     static constexpr int MAXF = 6;
@@ -112,11 +112,13 @@ struct HaloPackBody {
     double *south, *north;   // message buffers (NULL: that side is a domain wall)
     int j_south, j_north;    // first of the two rows on each side
     int to_buf;
-    DC_HD void operator()(int i, int r) const
+    // threads: i in [0, NI-1], jj in [0, 2*max(nk)-1] with jj = 2*k + r
+    DC_HD void operator()(int i, int jj) const
     {
+        const int r = jj & 1, k = jj >> 1;
         size_t off = 0;
         for (int m = 0; m < nf; m++) {
-            for (int k = 0; k < nk[m]; k++) {
+            if (k < nk[m]) {
                 const size_t b = off + ((size_t)k * 2 + r) * (size_t)g.NI + i;
                 if (south) {
                     const size_t a = g.idx(i, j_south + r, k);

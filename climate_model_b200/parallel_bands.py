@@ -69,8 +69,11 @@ class BandCommunicator:
         L, h = _lib.lib(), self.GR.dyncore()
         dev = self.F.torch_device
         if dev.type != 'cuda':
-            _lib.check(L.dc_stage_compute(h, stage, _lib.DC_PART_ALL, stream))
-            self._finish(stage, self._post(stage, stream), stream)
+            # host emulation (tests): same call sequence, no streams to overlap
+            _lib.check(L.dc_stage_compute(h, stage, _lib.DC_PART_BOUNDARY, stream))
+            works = self._post(stage, stream)
+            _lib.check(L.dc_stage_compute(h, stage, _lib.DC_PART_INTERIOR, stream))
+            self._finish(stage, works, stream)
         else:
             if self.comm_stream is None:
                 self.comm_stream = torch.cuda.Stream(device=dev)

@@ -35,7 +35,8 @@ def _single(fixture, nsteps, moist):
 
 @pytest.mark.parametrize('world,fixture,moist', [(2, 'ref_10deg_rand.npz', 1),
                                                  (3, 'ref_10deg_rand.npz', 0),
-                                                 (2, 'ref_5deg.npz', 1)])
+                                                 (2, 'ref_5deg.npz', 1),
+                                                 (2, 'ref_5deg.npz', 0)])
 def test_banded_run_equals_single_band_bitwise(tmp_path, world, fixture, moist):
     nsteps = 3
     ref = _single(fixture, nsteps, moist)
