@@ -231,7 +231,7 @@ static int do_primary_diag(dc_handle *h, void *stream)
 {
     const Fields &f = h->f;
     const Geom &g = h->g;
-    PrimaryDiagBody b{g, f.COLP, f.POTT, f.HSURF, f.PVTF, f.PVTFVB, f.PHI, f.PHIVB, f.POTTVB};
+    PrimaryDiagBody<true> b{g, f.COLP, f.POTT, f.HSURF, f.PVTF, f.PVTFVB, f.PHI, f.PHIVB, f.POTTVB};
     const int lo = g.j0 - HJ < 0 ? 0 : g.j0 - HJ, hi = g.j1 + HJ > g.ny + 1 ? g.ny + 1 : g.j1 + HJ;
     launch(h, "primary_diag", b, 0, g.nx + 1, lo, hi, stream);   // every row this rank holds
     return DC_OK;
@@ -300,8 +300,9 @@ static void do_diag_fused(dc_handle *h, int stage, void *stream)
     const Fields &f = h->f;
     const Geom &g = h->g;
     const int lo = g.j0 - HJ < 0 ? 0 : g.j0 - HJ, hi = g.j1 + HJ > g.ny + 1 ? g.ny + 1 : g.j1 + HJ;
-    PrimaryDiagBody b{g,      f.COLP, stage == 0 ? f.POTT_OLD : f.POTT, f.HSURF, f.PVTF, f.PVTFVB,
-                      f.PHI,  f.PHIVB, f.POTTVB};
+    // PHIVB is not an input of the dynamical core (only of the turbulence terms): not stored
+    PrimaryDiagBody<false> b{g,      f.COLP, stage == 0 ? f.POTT_OLD : f.POTT, f.HSURF, f.PVTF,
+                             f.PVTFVB, f.PHI, f.PHIVB, f.POTTVB};
     launch(h, "primary_diag", b, 0, g.nx + 1, lo, hi, stream);
 }
 
@@ -691,6 +692,8 @@ int dc_stage_compute(dc_handle *h, int stage, int part, void *stream)
     if ((rc = check_fused_fields(h, "dc_stage_compute"))) return rc;
     if (h->g.j1 - h->g.j0 + 1 < HJ)
         return fail(DC_ERR_STATE, "dc_stage_compute: a band needs at least %d rows", HJ);
+    if (h->g.nz > NZMAX)
+        return fail(DC_ERR_STATE, "dc_stage_compute: nz <= %d required", NZMAX);
     do_stage_fused(h, stage, part, stream);
     if (part != DC_PART_BOUNDARY)   // COLP is read by every stage-kernel launch of the stage
         dcb_d2d_async(h->f.COLP, h->f.COLP_NEW, h->g.plane * sizeof(double), stream);
@@ -805,6 +808,9 @@ int dc_step_matsuno(dc_handle *h, int nsteps, void *stream)
         return rc;
     const Fields &f = h->f;
     const size_t b2 = g.plane * sizeof(double), b3 = b2 * g.nz;
+    if (h->mode == DC_MODE_FUSED && g.nz > NZMAX)
+        return fail(DC_ERR_STATE, "dc_step_matsuno: the fused mode supports nz <= %d "
+                                  "(use dc_set_mode(h, DC_MODE_KERNELS))", NZMAX);
     if (h->mode == DC_MODE_FUSED) {
         for (int s = 0; s < nsteps; s++) {
             dcb_d2d_async(f.COLP_OLD, f.COLP, b2, stream);      // dyn_matsuno.py:34

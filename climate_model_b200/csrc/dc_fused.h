@@ -41,6 +41,7 @@ constexpr int SW = TX + 3, SH = TY + 3;  // staged region: ri in [-1, TX+1], rj 
 constexpr int SN = SW * SH;              // cells of a y-staggered plane (V, VFLX)
 constexpr int SNM = SW * (SH - 1);       // every other plane: rows rj in [-1, TY]
 constexpr int NQ = (SN + NT - 1) / NT;   // staged cells per thread
+constexpr int NZMAX = 128;               // fused path: nz <= NZMAX (checked by the launcher)
 
 struct StageSmem {
     // raw planes, double buffered (filled by cp.async one level ahead)
@@ -49,6 +50,12 @@ struct StageSmem {
     // derived planes of the current level
     double UF[SNM], VF[SN], P[SNM];
     double B[SNM], C[SNM], D[SNM], E[SNM], R[SNM], Q[SNM], S[SNM], T[SNM];
+    // per-level constants (broadcast reads): dsigma, 1/dsigma, sigma_vb, UVFLX / POTT diffusion
+    // coefficients, 1/(dsigma[k]+dsigma[k-1])
+    double lev[6][NZMAX + 1];
+    // per-row constants of rows J0-1 .. J0+TY-1: cor_fcos(corf_is, cos_is), sin_is,
+    // cor_fcos(corf, cos), sin, dxjs, A, 1/A
+    double row[7][TY + 1];
 };
 
 #if defined(__CUDA_ARCH__)
@@ -92,12 +99,29 @@ struct StageBody {
     DC_HD int wrap_i(int i) const { return i < 1 ? i + g.nx : (i > g.nx ? i - g.nx : i); }
     DC_HD static int sidx(int ri, int rj) { return (rj + 1) * SW + (ri + 1); }
 
+    // Tiles that touch no domain edge (periodic seam columns 1, 2, nx; wall rows 1, ny; rows
+    // beyond the launch range) run a specialisation without the boundary-image, wall and
+    // validity branches.
     DC_HD void run_block(int bx, int by, StageSmem &s) const
+    {
+        const int I0 = 1 + bx * TX, J0 = j_lo + by * TY;
+        const int j_top = (j_hi < g.ny - 1) ? j_hi : g.ny - 1;
+        const bool interior = (I0 >= 3) && (I0 + TX - 1 <= g.nx - 1) && (J0 >= 2) &&
+                              (J0 + TY - 1 <= j_top);
+        if (interior)
+            run<false>(bx, by, s);
+        else
+            run<true>(bx, by, s);
+    }
+
+    template <bool EDGE>
+    DC_HD void run(int bx, int by, StageSmem &s) const
     {
         const int nx = g.nx, ny = g.ny, nz = g.nz, NI = g.NI;
         const int I0 = 1 + bx * TX, J0 = j_lo + by * TY;
         const size_t plane = g.plane;
         const double dyis = g.dyis, dt = g.dt;
+        const double scale = cor_scale(g.dlon_rad, g.dlat_rad);
         // rows this rank holds (global): halo rows included
         const int j_min = (g.j0 - HJ < 0) ? 0 : g.j0 - HJ;
         const int j_max_m = (g.j1 + HJ > ny + 1) ? ny + 1 : g.j1 + HJ;          // mass rows
@@ -214,6 +238,27 @@ struct StageBody {
                 DC_P(pvb_im1) = PVTFVB[DC_P(off0) - 1];
                 DC_P(pvb_jm1) = PVTFVB[DC_P(off0) - NI];
             }
+            // constant tables
+            for (int k = tid; k <= nz; k += NT) {
+                s.lev[0][k] = k < nz ? g.dsigma[k] : 0.;
+                s.lev[1][k] = k < nz ? g.r_dsigma[k] : 0.;
+                s.lev[2][k] = g.sigma_vb[k];
+                s.lev[3][k] = k < nz ? g.UVFLX_dif_coef[k] : 0.;
+                s.lev[4][k] = k < nz ? g.POTT_dif_coef[k] : 0.;
+                s.lev[5][k] = k < nz ? g.r_dss[k] : 0.;
+            }
+            if (tid <= TY) {
+                int j = J0 - 1 + tid;
+                if (j > j_max_m) j = j_max_m;
+                const int r = g.row(j);
+                s.row[0][tid] = cor_fcos(g.corf_is[r], g.cos_lat_is[r]);
+                s.row[1][tid] = g.sin_lat_is[r];
+                s.row[2][tid] = cor_fcos(g.corf[r], g.cos_lat[r]);
+                s.row[3][tid] = g.sin_lat[r];
+                s.row[4][tid] = g.dxjs[r];
+                s.row[5][tid] = g.A[r];
+                s.row[6][tid] = g.r_A[r];
+            }
             // prologue of the copy pipeline: level 0 -> buffer 0
             for (int q = 0; q < NQ; q++) {
                 const int idx = tid + q * NT;
@@ -234,8 +279,6 @@ struct StageBody {
         for (int k = 0; k < nz; k++) {
             const int b = k & 1;
             const size_t ko = (size_t)k * plane;
-            const double ds = g.dsigma[k];
-            const Div ds_d = mkdiv(ds, g.r_dsigma[k]);
             const bool last = (k + 1 == nz);
             // ---- prefetch: planes of level k+1 -> buffer 1-b; own-column scalars of level k
             DC_PHASE
@@ -355,27 +398,31 @@ struct StageBody {
                 const int i = I0 + tx, j = J0 + ty;
                 const int c0 = sidx(tx, ty);
                 const size_t o = ko + DC_P(off0);
+                const double ds = s.lev[0][k];
+                const Div ds_d = mkdiv(ds, s.lev[1][k]);
                 const double w_kp1 = s.rW[b][c0];
                 const double pvb_kp1 = s.rPB[b][c0];
                 const double pvb_im1_kp1 = s.rPB[b][c0 - 1];
                 const double pvb_jm1_kp1 = s.rPB[b][c0 - SW];
-                if (DC_P(flags) & 1) {
+                if (!EDGE || (DC_P(flags) & 1)) {
                     const double *U = s.rU[b], *V = s.rV[b], *T = s.rT[b];
                     const double u = U[c0], v = V[c0];
-                    const bool edge = DC_P(flags) & 2;
+                    const bool edge = EDGE && (DC_P(flags) & 2);
+                    const bool wall_s = EDGE && (j == 1), wall_n = EDGE && (j == ny);
                     // vertical momentum fluxes through interface k+1
                     // (dyn_functions.py:211-270; 0 at the model bottom)
                     double wwu_kp1 = 0., wwv_kp1 = 0.;
                     if (!last) {
                         const double *P = s.P;
-                        const Div dss_d = mkdiv(g.dsigma[k + 1] + ds, g.r_dss[k + 1]);
-                        const int wall = (j == 1) ? -1 : ((j == ny) ? 1 : 0);
+                        const double ds_kp1 = s.lev[0][k + 1];
+                        const Div dss_d = mkdiv(ds_kp1 + ds, s.lev[5][k + 1]);
+                        const int wall = wall_s ? -1 : (wall_n ? 1 : 0);
                         wwu_kp1 = colpa_wwind(P[c0], P[c0 - 1], P[c0 - SW], P[c0 + SW],
                                               P[c0 - SW - 1], P[c0 + SW - 1], wall) *
-                                  interp_ks(DC_P(u_kp1), u, g.dsigma[k + 1], ds, dss_d);
+                                  interp_ks(DC_P(u_kp1), u, ds_kp1, ds, dss_d);
                         wwv_kp1 = colpa_wwind(P[c0], P[c0 - SW], P[c0 - 1], P[c0 + 1],
                                               P[c0 - SW - 1], P[c0 - SW + 1], 0) *
-                                  interp_ks(DC_P(v_kp1), v, g.dsigma[k + 1], ds, dss_d);
+                                  interp_ks(DC_P(v_kp1), v, ds_kp1, ds, dss_d);
                     }
                     const double phi = s.rPHI[b][c0], pott = T[c0], pvtf = s.rPV[b][c0];
                     // ---------------- dUFLXdt (dyn_UFLX.py:69-199) ----------------
@@ -384,12 +431,12 @@ struct StageBody {
                         double cflx = s.C[c0], cflx_jp1 = s.C[c0 + SW];
                         double dflx_im1 = s.D[c0 - 1], dflx_jp1 = s.D[c0 + SW];
                         double eflx = s.E[c0], eflx_im1_jp1 = s.E[c0 + SW - 1];
-                        if (j == 1) {
+                        if (wall_s) {
                             dflx_im1 = 0.;
                             cflx = 0.;
                             eflx = 0.;
                         }
-                        if (j == ny) {
+                        if (wall_n) {
                             dflx_jp1 = 0.;
                             cflx_jp1 = 0.;
                             eflx_im1_jp1 = 0.;
@@ -402,13 +449,12 @@ struct StageBody {
                         d = d + ((DC_P(wwu_k) - wwu_kp1) / ds_d);
                         d = d + coriolis_UWIND(DC_P(c), DC_P(c_im1), v, V[c0 - 1], V[c0 + SW],
                                                V[c0 + SW - 1], u, U[c0 - 1], U[c0 + 1],
-                                               g.corf_is[g.row(j)], g.cos_lat_is[g.row(j)],
-                                               g.sin_lat_is[g.row(j)], g.dlon_rad, g.dlat_rad);
+                                               s.row[0][ty + 1], s.row[1][ty + 1], scale);
                         d = d + pre_grad(phi, s.rPHI[b][c0 - 1], DC_P(c), DC_P(c_im1), pott,
                                          T[c0 - 1], pvtf, s.rPV[b][c0 - 1], DC_P(pvb),
-                                         DC_P(pvb_im1), pvb_im1_kp1, pvb_kp1, ds_d, g.sigma_vb[k],
-                                         g.sigma_vb[k + 1], dyis);
-                        const double coef = g.UVFLX_dif_coef[k];
+                                         DC_P(pvb_im1), pvb_im1_kp1, pvb_kp1, ds_d, s.lev[2][k],
+                                         s.lev[2][k + 1], dyis);
+                        const double coef = s.lev[3][k];
                         if (coef > 0.)
                             d = d + num_dif(s.UF[c0], s.UF[c0 - 1], s.UF[c0 + 1], s.UF[c0 - SW],
                                             s.UF[c0 + SW], coef);
@@ -421,7 +467,7 @@ struct StageBody {
                             UWIND_out[o] = un;
                     }
                     // ---------------- dVFLXdt (dyn_VFLX.py:67-198) ----------------
-                    if (j >= 2) {
+                    if (!EDGE || j >= 2) {
                         double d = 0.;
                         d = d + UVFLX_hor_adv(v, V[c0 - SW], V[c0 + SW], V[c0 - 1], V[c0 + 1],
                                               V[c0 - SW - 1], V[c0 - SW + 1], V[c0 + SW - 1],
@@ -430,15 +476,13 @@ struct StageBody {
                                               s.T[c0 - SW + 1], -1.);
                         d = d + ((DC_P(wwv_k) - wwv_kp1) / ds_d);
                         d = d + coriolis_VWIND(DC_P(c), DC_P(c_jm1), u, U[c0 - SW], U[c0 + 1],
-                                               U[c0 - SW + 1], g.corf[g.row(j)],
-                                               g.corf[g.row(j - 1)], g.cos_lat[g.row(j)],
-                                               g.sin_lat[g.row(j)], g.cos_lat[g.row(j - 1)],
-                                               g.sin_lat[g.row(j - 1)], g.dlon_rad, g.dlat_rad);
+                                               U[c0 - SW + 1], s.row[2][ty + 1], s.row[3][ty + 1],
+                                               s.row[2][ty], s.row[3][ty], scale);
                         d = d + pre_grad(phi, s.rPHI[b][c0 - SW], DC_P(c), DC_P(c_jm1), pott,
                                          T[c0 - SW], pvtf, s.rPV[b][c0 - SW], DC_P(pvb),
-                                         DC_P(pvb_jm1), pvb_jm1_kp1, pvb_kp1, ds_d, g.sigma_vb[k],
-                                         g.sigma_vb[k + 1], g.dxjs[g.row(j)]);
-                        const double coef = g.UVFLX_dif_coef[k];
+                                         DC_P(pvb_jm1), pvb_jm1_kp1, pvb_kp1, ds_d, s.lev[2][k],
+                                         s.lev[2][k + 1], s.row[4][ty + 1]);
+                        const double coef = s.lev[3][k];
                         if (coef > 0.)
                             d = d + num_dif(s.VF[c0], s.VF[c0 - 1], s.VF[c0 + 1], s.VF[c0 - SW],
                                             s.VF[c0 + SW], coef);
@@ -452,7 +496,7 @@ struct StageBody {
                     } else {
                         put_ystag(g, VWIND_out, i, 1, k, 0.);
                     }
-                    if (j == ny) put_ystag(g, VWIND_out, i, ny + 1, k, 0.);
+                    if (wall_n) put_ystag(g, VWIND_out, i, ny + 1, k, 0.);
                     // ---------------- dPOTTdt (dyn_POTT.py:55-110) ----------------
                     {
                         const double p_im1 = T[c0 - 1], p_ip1 = T[c0 + 1];
@@ -460,10 +504,10 @@ struct StageBody {
                         double d = 0.;
                         d = d + hor_adv(pott, p_im1, p_ip1, p_jm1, p_jp1, s.UF[c0], s.UF[c0 + 1],
                                         s.VF[c0], s.VF[c0 + SW],
-                                        mkdiv(g.A[g.row(j)], g.r_A[g.row(j)]));
+                                        mkdiv(s.row[5][ty + 1], s.row[6][ty + 1]));
                         d = d + vert_adv(DC_P(pottvb_k), DC_P(pottvb_kp1), DC_P(w_k), w_kp1,
                                          DC_P(cnew), ds_d, k);
-                        const double coef = g.POTT_dif_coef[k];
+                        const double coef = s.lev[4][k];
                         if (coef > 0.)
                             d = d + num_dif_pw(pott, p_im1, p_ip1, p_jm1, p_jp1, DC_P(c),
                                                DC_P(c_im1), DC_P(c_ip1), DC_P(c_jm1), DC_P(c_jp1),

@@ -272,8 +272,9 @@ struct UFLXTendencyBody {
         const int nx = g.nx, ny = g.ny, nz = g.nz;
         const int im1 = (i == 1) ? nx : i - 1;  // BCx, dyn_UFLX.py:367-374
         const double c = COLP[g.idx2(i, j)], c_im1 = COLP[g.idx2(i - 1, j)];
-        const double corf_is = g.corf_is[g.row(j)];
-        const double cosl = g.cos_lat_is[g.row(j)], sinl = g.sin_lat_is[g.row(j)];
+        const double fcos_is = cor_fcos(g.corf_is[g.row(j)], g.cos_lat_is[g.row(j)]);
+        const double sinl = g.sin_lat_is[g.row(j)];
+        const double scale = cor_scale(g.dlon_rad, g.dlat_rad);
         const double *U = UWIND, *V = VWIND;
         for (int k = 0; k < nz; k++) {
             double bflx = BFLX[g.idx(i, j, k)], cflx = CFLX[g.idx(i, j, k)];
@@ -303,7 +304,7 @@ struct UFLXTendencyBody {
             d = d + ((WWIND_UWIND[g.idx(i, j, k)] - WWIND_UWIND[g.idx(i, j, k + 1)]) / ds);
             d = d + coriolis_UWIND(c, c_im1, V[g.idx(i, j, k)], V[g.idx(i - 1, j, k)],
                                    V[g.idx(i, j + 1, k)], V[g.idx(i - 1, j + 1, k)], u, u_im1,
-                                   u_ip1, corf_is, cosl, sinl, g.dlon_rad, g.dlat_rad);
+                                   u_ip1, fcos_is, sinl, scale);
             d = d + pre_grad(PHI[g.idx(i, j, k)], PHI[g.idx(i - 1, j, k)], c, c_im1,
                              POTT[g.idx(i, j, k)], POTT[g.idx(i - 1, j, k)], PVTF[g.idx(i, j, k)],
                              PVTF[g.idx(i - 1, j, k)], PVTFVB[g.idx(i, j, k)],
@@ -334,9 +335,10 @@ struct VFLXTendencyBody {
         const int nx = g.nx, nz = g.nz;
         const int ip1 = (i == nx) ? 1 : i + 1;  // BCx, dyn_VFLX.py:349-356
         const double c = COLP[g.idx2(i, j)], c_jm1 = COLP[g.idx2(i, j - 1)];
-        const double corf = g.corf[g.row(j)], corf_jm1 = g.corf[g.row(j - 1)];
-        const double cosl = g.cos_lat[g.row(j)], sinl = g.sin_lat[g.row(j)];
-        const double cosl_jm1 = g.cos_lat[g.row(j - 1)], sinl_jm1 = g.sin_lat[g.row(j - 1)];
+        const double fcos = cor_fcos(g.corf[g.row(j)], g.cos_lat[g.row(j)]);
+        const double fcos_jm1 = cor_fcos(g.corf[g.row(j - 1)], g.cos_lat[g.row(j - 1)]);
+        const double sinl = g.sin_lat[g.row(j)], sinl_jm1 = g.sin_lat[g.row(j - 1)];
+        const double scale = cor_scale(g.dlon_rad, g.dlat_rad);
         const double dxjs = g.dxjs[g.row(j)];
         const double *U = UWIND, *V = VWIND;
         for (int k = 0; k < nz; k++) {
@@ -357,9 +359,8 @@ struct VFLXTendencyBody {
             const Div ds = mkdiv(g.dsigma[k], g.r_dsigma[k]);
             d = d + ((WWIND_VWIND[g.idx(i, j, k)] - WWIND_VWIND[g.idx(i, j, k + 1)]) / ds);
             d = d + coriolis_VWIND(c, c_jm1, U[g.idx(i, j, k)], U[g.idx(i, j - 1, k)],
-                                   U[g.idx(i + 1, j, k)], U[g.idx(i + 1, j - 1, k)], corf,
-                                   corf_jm1, cosl, sinl, cosl_jm1, sinl_jm1, g.dlon_rad,
-                                   g.dlat_rad);
+                                   U[g.idx(i + 1, j, k)], U[g.idx(i + 1, j - 1, k)], fcos, sinl,
+                                   fcos_jm1, sinl_jm1, scale);
             d = d + pre_grad(PHI[g.idx(i, j, k)], PHI[g.idx(i, j - 1, k)], c, c_jm1,
                              POTT[g.idx(i, j, k)], POTT[g.idx(i, j - 1, k)], PVTF[g.idx(i, j, k)],
                              PVTF[g.idx(i, j - 1, k)], PVTFVB[g.idx(i, j, k)],
@@ -537,51 +538,57 @@ struct MoistEulerBody {
 // POTTVB).  threads: ALL columns i in [0, nx+1], j in [0, ny+1] (halos are computed, not
 // exchanged).  nz+1 pow per column (the reference evaluates 2 per cell).
 // ---------------------------------------------------------------------------------------
+template <bool STORE_PHIVB>
 struct PrimaryDiagBody {
     Geom g;
     const double *COLP, *POTT, *HSURF;
     double *PVTF, *PVTFVB, *PHI, *PHIVB, *POTTVB;
+    DC_HD static double exner(double p)
+    {
+        return pow(DC_FAST ? p * 1e-5 : p / 100000., con_kappa);
+    }
+    // One BOTTOM-UP sweep: the hydrostatic integral needs that direction, everything else is
+    // level-local or couples two neighbouring levels, so POTT is read once and nothing the
+    // thread wrote is read back.  Same operands and operations as the reference's three
+    // kernels (diag_PVTF / diag_PHI / diag_POTTVB).
     DC_HD void operator()(int i, int j) const
     {
         const int nz = g.nz;
         const double colp = COLP[g.idx2(i, j)];
-        double p_km12 = g.pair_top + g.sigma_vb[0] * colp;
-        double pw_km12 = pow(p_km12 / 100000., con_kappa);
-        double pvtf_km1 = 0., pott_km1 = 0.;
-        for (int k = 0; k < nz; k++) {
-            const double p_kp12 = g.pair_top + g.sigma_vb[k + 1] * colp;
-            const double pw_kp12 = pow(p_kp12 / 100000., con_kappa);
+        double p_kp12 = g.pair_top + g.sigma_vb[nz] * colp;
+        double pw_kp12 = exner(p_kp12);
+        PVTFVB[g.idx(i, j, nz)] = pw_kp12;
+        double phivb = HSURF[g.idx2(i, j)] * con_g;
+        if (STORE_PHIVB) PHIVB[g.idx(i, j, nz)] = phivb;
+        double pvtf_kp1 = 0., pott_kp1 = 0.;
+        for (int k = nz - 1; k >= 0; k--) {
+            const double p_km12 = g.pair_top + g.sigma_vb[k] * colp;
+            const double pw_km12 = exner(p_km12);
             const double pvtf = 1. / (1. + con_kappa) * (pw_kp12 * p_kp12 - pw_km12 * p_km12) /
                                 (p_kp12 - p_km12);
             const double pott = POTT[g.idx(i, j, k)];
             PVTF[g.idx(i, j, k)] = pvtf;
             PVTFVB[g.idx(i, j, k)] = pw_km12;
-            if (k >= 1)
-                POTTVB[g.idx(i, j, k)] =
-                    (+(pw_km12 - pvtf_km1) * pott_km1 + (pvtf - pw_km12) * pott) /
-                    (pvtf - pvtf_km1);
-            p_km12 = p_kp12;
-            pw_km12 = pw_kp12;
-            pvtf_km1 = pvtf;
-            pott_km1 = pott;
-        }
-        PVTFVB[g.idx(i, j, nz)] = pw_km12;
-        if (nz >= 2) {
-            // extrapolate model top / bottom POTTVB (dyn_diagnostics.py:184-191)
-            const double pott0 = POTT[g.idx(i, j, 0)];
-            POTTVB[g.idx(i, j, 0)] = pott0 - (POTTVB[g.idx(i, j, 1)] - pott0);
-            POTTVB[g.idx(i, j, nz)] = pott_km1 - (POTTVB[g.idx(i, j, nz - 1)] - pott_km1);
-        }
-        // diag_PHI_cpu: bottom-up hydrostatic integral
-        double phivb = HSURF[g.idx2(i, j)] * con_g;
-        PHIVB[g.idx(i, j, nz)] = phivb;
-        for (int k = nz - 1; k >= 0; k--) {
-            const double pott = POTT[g.idx(i, j, k)];
-            const double pvtf = PVTF[g.idx(i, j, k)];
-            const double phi = phivb - con_cp * (pott * (pvtf - PVTFVB[g.idx(i, j, k + 1)]));
-            phivb = phi - con_cp * (pott * (PVTFVB[g.idx(i, j, k)] - pvtf));
+            // diag_PHI_cpu
+            const double phi = phivb - con_cp * (pott * (pvtf - pw_kp12));
+            phivb = phi - con_cp * (pott * (pw_km12 - pvtf));
             PHI[g.idx(i, j, k)] = phi;
-            PHIVB[g.idx(i, j, k)] = phivb;
+            if (STORE_PHIVB) PHIVB[g.idx(i, j, k)] = phivb;
+            // diag_POTTVB_cpu: interface k+1 between level k (above) and level k+1 (below)
+            if (k + 1 <= nz - 1) {
+                const double pottvb =
+                    (+(pw_kp12 - pvtf) * pott + (pvtf_kp1 - pw_kp12) * pott_kp1) /
+                    (pvtf_kp1 - pvtf);
+                POTTVB[g.idx(i, j, k + 1)] = pottvb;
+                if (k + 1 == nz - 1)  // extrapolate model bottom (dyn_diagnostics.py:188-191)
+                    POTTVB[g.idx(i, j, nz)] = pott_kp1 - (pottvb - pott_kp1);
+                if (k == 0)           // extrapolate model top (dyn_diagnostics.py:184-187)
+                    POTTVB[g.idx(i, j, 0)] = pott - (pottvb - pott);
+            }
+            p_kp12 = p_km12;
+            pw_kp12 = pw_km12;
+            pvtf_kp1 = pvtf;
+            pott_kp1 = pott;
         }
     }
 };

@@ -143,31 +143,34 @@ DC_HD double num_dif(double VAR, double VAR_im1, double VAR_ip1, double VAR_jm1,
     return VAR_dif_coef * (+VAR_im1 + VAR_ip1 + VAR_jm1 + VAR_jp1 - 4. * VAR);
 }
 
-// dyn_UFLX.py:39-66 with cos/sin(lat_is_rad) precomputed per row on the host
+// Coriolis + spherical-metric terms.  The latitude-only factors of the reference expressions
+// are formed once per row, with the reference's own operation order, by these two helpers:
+//   cor_fcos  = corf * con_rE * cos(lat)          (dyn_UFLX.py:56-57, dyn_VFLX.py:53-54)
+//   cor_scale = con_rE * dlon_rad * dlat_rad / 2  (dyn_UFLX.py:52, dyn_VFLX.py:50)
+DC_HD double cor_fcos(double corf, double cos_lat) { return corf * con_rE * cos_lat; }
+DC_HD double cor_scale(double dlon_rad, double dlat_rad) { return con_rE * dlon_rad * dlat_rad / 2.; }
+
+// dyn_UFLX.py:39-66
 DC_HD double coriolis_UWIND(double COLP, double COLP_im1, double VWIND, double VWIND_im1,
                             double VWIND_jp1, double VWIND_im1_jp1, double UWIND,
-                            double UWIND_im1, double UWIND_ip1, double corf_is, double cos_lat_is,
-                            double sin_lat_is, double dlon_rad, double dlat_rad)
+                            double UWIND_im1, double UWIND_ip1, double fcos_is, double sin_lat_is,
+                            double scale)
 {
-    return (con_rE * dlon_rad * dlat_rad / 2. *
+    return (scale *
             (COLP_im1 * (VWIND_im1 + VWIND_im1_jp1) / 2. *
-                 (corf_is * con_rE * cos_lat_is + (UWIND_im1 + UWIND) / 2. * sin_lat_is) +
-             COLP * (VWIND + VWIND_jp1) / 2. *
-                 (corf_is * con_rE * cos_lat_is + (UWIND + UWIND_ip1) / 2. * sin_lat_is)));
+                 (fcos_is + (UWIND_im1 + UWIND) / 2. * sin_lat_is) +
+             COLP * (VWIND + VWIND_jp1) / 2. * (fcos_is + (UWIND + UWIND_ip1) / 2. * sin_lat_is)));
 }
 
 // dyn_VFLX.py:39-64
 DC_HD double coriolis_VWIND(double COLP, double COLP_jm1, double UWIND, double UWIND_jm1,
-                            double UWIND_ip1, double UWIND_ip1_jm1, double corf, double corf_jm1,
-                            double cos_lat, double sin_lat, double cos_lat_jm1, double sin_lat_jm1,
-                            double dlon_rad, double dlat_rad)
+                            double UWIND_ip1, double UWIND_ip1_jm1, double fcos, double sin_lat,
+                            double fcos_jm1, double sin_lat_jm1, double scale)
 {
-    return (-con_rE * dlon_rad * dlat_rad / 2. *
+    return (-scale *
             (COLP_jm1 * (UWIND_jm1 + UWIND_ip1_jm1) / 2. *
-                 (corf_jm1 * con_rE * cos_lat_jm1 +
-                  (UWIND_jm1 + UWIND_ip1_jm1) / 2. * sin_lat_jm1) +
-             COLP * (UWIND + UWIND_ip1) / 2. *
-                 (corf * con_rE * cos_lat + (UWIND + UWIND_ip1) / 2. * sin_lat)));
+                 (fcos_jm1 + (UWIND_jm1 + UWIND_ip1_jm1) / 2. * sin_lat_jm1) +
+             COLP * (UWIND + UWIND_ip1) / 2. * (fcos + (UWIND + UWIND_ip1) / 2. * sin_lat)));
 }
 
 // dyn_functions.py:105-114
