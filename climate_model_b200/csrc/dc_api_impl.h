@@ -286,11 +286,9 @@ static void do_stage_fused(dc_handle *h, int stage, int part, void *stream)
         // the moisture tracers still use the kernel-mode tendency kernel: whole band at once
         const double *QV = stage == 0 ? f.QV : f.QV_OLD, *QC = stage == 0 ? f.QC : f.QC_OLD;
         double *QVo = stage == 0 ? f.QV_OLD : f.QV, *QCo = stage == 0 ? f.QC_OLD : f.QC;
-        MoistTendencyBody m{g, QV, QC, f.UFLX, f.VFLX, f.COLP, f.WWIND, f.COLP_NEW, f.dQVdt,
-                            f.dQCdt};
-        launch(h, "moist_tendency", m, 1, g.nx, g.j0, g.j1, stream);
-        MoistEulerBody e{g, f.COLP_NEW, f.COLP_OLD, f.QV, f.dQVdt, f.QC, f.dQCdt, QVo, QCo};
-        launch(h, "moist_euler", e, 1, g.nx, g.j0, g.j1, stream);
+        MoistStageBody m{g,      QV,         QC,         f.UFLX, f.VFLX, f.COLP,
+                         f.WWIND, f.COLP_NEW, f.COLP_OLD, f.QV,   f.QC,   QVo,    QCo};
+        launch(h, "moist_stage", m, 1, g.nx, g.j0, g.j1, stream);
     }
 }
 

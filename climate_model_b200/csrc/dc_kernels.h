@@ -513,6 +513,70 @@ struct TimestepBody {
 };
 
 // ---------------------------------------------------------------------------------------
+// fused moisture stage: dQVdt / dQCdt (dyn_moist.py:49-129) followed immediately by the
+// pressure-weighted Euler step (dyn_timestep.py:292-296) and the boundary images; the
+// tendencies are not materialised.  threads: i in [1, nx], j in the band.
+// Q_OLD may alias Q_out (stage 2 overwrites the step-start state cell by cell).
+// ---------------------------------------------------------------------------------------
+struct MoistStageBody {
+    Geom g;
+    const double *QV, *QC, *UFLX, *VFLX, *COLP, *WWIND, *COLP_NEW, *COLP_OLD, *QV_OLD, *QC_OLD;
+    double *QV_out, *QC_out;
+    DC_HD void one(const double *Q, const double *Q_OLD, double *Q_out, int i, int j) const
+    {
+        const int nz = g.nz;
+        const double c = COLP[g.idx2(i, j)];
+        const double c_im1 = COLP[g.idx2(i - 1, j)], c_ip1 = COLP[g.idx2(i + 1, j)];
+        const double c_jm1 = COLP[g.idx2(i, j - 1)], c_jp1 = COLP[g.idx2(i, j + 1)];
+        const double cnew = COLP_NEW[g.idx2(i, j)], cold = COLP_OLD[g.idx2(i, j)];
+        const Div cn = mkdiv(cnew);
+        const Div A = mkdiv(g.A[g.row(j)], g.r_A[g.row(j)]);
+        // comp_VARVB_log (dyn_functions.py:70-95) needs log and reciprocal of the clamped value
+        // of both levels around an interface: computed once per level and carried (the
+        // reference evaluates them twice per cell), same values, same result
+        const double min_val = 0.0000001;
+        double q = Q[g.idx(i, j, 0)];
+        double qc = fmax(q, min_val), lq = log(qc), rq = 1. / qc;
+        double qvb = q;  // unused at k = 0
+        for (int k = 0; k < nz; k++) {
+            const double q_kp1 = (k + 1 < nz) ? Q[g.idx(i, j, k + 1)] : q;
+            const double q_im1 = Q[g.idx(i - 1, j, k)], q_ip1 = Q[g.idx(i + 1, j, k)];
+            const double q_jm1 = Q[g.idx(i, j - 1, k)], q_jp1 = Q[g.idx(i, j + 1, k)];
+            double d = 0.;
+            d = d + hor_adv(q, q_im1, q_ip1, q_jm1, q_jp1, UFLX[g.idx(i, j, k)],
+                            UFLX[g.idx(i + 1, j, k)], VFLX[g.idx(i, j, k)],
+                            VFLX[g.idx(i, j + 1, k)], A);
+            // QVVB_kp1 = comp_VARVB_log(VAR = Q[k+1], VAR_km1 = Q[k])
+            const double qc_kp1 = fmax(q_kp1, min_val);
+            double lq_kp1 = lq, rq_kp1 = rq, qvb_kp1 = qc_kp1;
+            if (qc_kp1 != qc) {
+                lq_kp1 = log(qc_kp1);
+                rq_kp1 = 1. / qc_kp1;
+                qvb_kp1 = ((lq - lq_kp1) / (rq_kp1 - rq));
+            }
+            d = d + vert_adv(qvb, qvb_kp1, WWIND[g.idx(i, j, k)], WWIND[g.idx(i, j, k + 1)], cnew,
+                             mkdiv(g.dsigma[k], g.r_dsigma[k]), k);
+            const double coef = g.moist_dif_coef[k];
+            if (coef > 0.)
+                d = d + num_dif_pw(q, q_im1, q_ip1, q_jm1, q_jp1, c, c_im1, c_ip1, c_jm1, c_jp1,
+                                   coef);
+            put_mass(g, Q_out, i, j, k,
+                     euler_forward_pw(Q_OLD[g.idx(i, j, k)], d, cn, cold, g.dt));
+            q = q_kp1;
+            qc = qc_kp1;
+            lq = lq_kp1;
+            rq = rq_kp1;
+            qvb = qvb_kp1;
+        }
+    }
+    DC_HD void operator()(int i, int j) const
+    {
+        one(QV, QV_OLD, QV_out, i, j);
+        one(QC, QC_OLD, QC_out, i, j);
+    }
+};
+
+// ---------------------------------------------------------------------------------------
 // Euler forward of the moisture tracers only (fused path: U, V, POTT are stepped inside the
 // stage kernel).  threads: i in [1, nx], j in the band
 // ---------------------------------------------------------------------------------------
