@@ -19,7 +19,7 @@ GRID_FIELDS_1D = ['sigma_vb', 'dsigma', 'UVFLX_dif_coef', 'POTT_dif_coef', 'mois
 
 DC_NK_2D, DC_NK_NZ, DC_NK_NZS = 0, 1, 2
 DC_MODE_FUSED, DC_MODE_KERNELS = 0, 1
-DC_PART_ALL, DC_PART_BOUNDARY, DC_PART_INTERIOR = 0, 1, 2
+DC_PART_ALL, DC_PART_CONT, DC_PART_BOUNDARY, DC_PART_INTERIOR, DC_PART_COLP = 0, 1, 2, 3, 4
 
 
 class GridDesc(ctypes.Structure):

@@ -243,9 +243,13 @@ static int do_primary_diag(dc_handle *h, void *stream)
 // step until stage 2 overwrites it cell by cell; S1 = {UWIND_OLD, ...} receives the estimate
 // of stage 1.  No OLD <- current copies of 3-D fields are needed.
 // ---------------------------------------------------------------------------------------
-// part: DC_PART_ALL, or DC_PART_BOUNDARY (continuity + the tile rows that hold the two
-// outermost owned rows on each side: what the neighbours wait for) followed by
-// DC_PART_INTERIOR (the remaining tile rows)
+// The pieces of a stage (include/dyncore.h): DC_PART_ALL = all of them in order, or
+//   DC_PART_CONT      continuity (+ the moisture stage kernel, which only needs its outputs)
+//   DC_PART_BOUNDARY  stage kernel on the first and last tile row of the band (what the
+//                     neighbours wait for)
+//   DC_PART_INTERIOR  stage kernel on the remaining tile rows
+//   DC_PART_COLP      COLP <- COLP_NEW (after every stage-kernel launch of the stage)
+// BOUNDARY and INTERIOR are independent of each other and may run on different streams.
 static void do_stage_fused(dc_handle *h, int stage, int part, void *stream)
 {
     const Fields &f = h->f;
@@ -254,23 +258,30 @@ static void do_stage_fused(dc_handle *h, int stage, int part, void *stream)
                  *T = stage == 0 ? f.POTT : f.POTT_OLD;
     double *Uo = stage == 0 ? f.UWIND_OLD : f.UWIND, *Vo = stage == 0 ? f.VWIND_OLD : f.VWIND,
            *To = stage == 0 ? f.POTT_OLD : f.POTT;
-    if (part != DC_PART_INTERIOR) {
+    if (part == DC_PART_ALL || part == DC_PART_CONT) {
         if (g.i_moist)
-            launch_continuity<2>(h, U, V, stream);   // moisture kernels read UFLX / VFLX
+            launch_continuity<2>(h, U, V, stream);   // the moisture kernel reads UFLX / VFLX
         else
             launch_continuity<0>(h, U, V, stream);
+        if (g.i_moist) {
+            const double *QV = stage == 0 ? f.QV : f.QV_OLD, *QC = stage == 0 ? f.QC : f.QC_OLD;
+            double *QVo = stage == 0 ? f.QV_OLD : f.QV, *QCo = stage == 0 ? f.QC_OLD : f.QC;
+            MoistStageBody m{g,      QV,         QC,         f.UFLX, f.VFLX, f.COLP,
+                             f.WWIND, f.COLP_NEW, f.COLP_OLD, f.QV,   f.QC,   QVo,    QCo};
+            launch(h, "moist_stage", m, 1, g.nx, g.j0, g.j1, stream);
+        }
     }
     // tile rows of the band: [j0, j1] in steps of TY; boundary = first and last tile row
     const int ntr = (g.j1 - g.j0 + TY) / TY;
-    const int nb = ntr >= 4 ? 1 : 0;          // too few tile rows: no split, all in "boundary"
+    const bool can_split = ntr >= 4;
     struct Range { int lo, hi; } ranges[2];
     int nr = 0;
-    if (part == DC_PART_ALL || nb == 0) {
-        if (part != DC_PART_INTERIOR) ranges[nr++] = Range{g.j0, g.j1};
+    if (part == DC_PART_ALL || (part == DC_PART_BOUNDARY && !can_split)) {
+        ranges[nr++] = Range{g.j0, g.j1};
     } else if (part == DC_PART_BOUNDARY) {
         ranges[nr++] = Range{g.j0, g.j0 + TY - 1};
         ranges[nr++] = Range{g.j0 + (ntr - 1) * TY, g.j1};
-    } else {
+    } else if (part == DC_PART_INTERIOR && can_split) {
         ranges[nr++] = Range{g.j0 + TY, g.j0 + (ntr - 1) * TY - 1};
     }
     for (int r = 0; r < nr; r++) {
@@ -282,14 +293,8 @@ static void do_stage_fused(dc_handle *h, int stage, int part, void *stream)
         if (h->profiling) dcb_profile_end(h, stream);
         h->launches++;
     }
-    if (g.i_moist && part != DC_PART_INTERIOR) {
-        // the moisture tracers still use the kernel-mode tendency kernel: whole band at once
-        const double *QV = stage == 0 ? f.QV : f.QV_OLD, *QC = stage == 0 ? f.QC : f.QC_OLD;
-        double *QVo = stage == 0 ? f.QV_OLD : f.QV, *QCo = stage == 0 ? f.QC_OLD : f.QC;
-        MoistStageBody m{g,      QV,         QC,         f.UFLX, f.VFLX, f.COLP,
-                         f.WWIND, f.COLP_NEW, f.COLP_OLD, f.QV,   f.QC,   QVo,    QCo};
-        launch(h, "moist_stage", m, 1, g.nx, g.j0, g.j1, stream);
-    }
+    if (part == DC_PART_ALL || part == DC_PART_COLP)
+        dcb_d2d_async(f.COLP, f.COLP_NEW, g.plane * sizeof(double), stream);  // dyn_matsuno.py:64-67
 }
 
 // primary diagnostics of the state a stage produced, on every row this rank holds
@@ -684,7 +689,7 @@ int dc_step_begin(dc_handle *h, void *stream)
 
 int dc_stage_compute(dc_handle *h, int stage, int part, void *stream)
 {
-    if (!h || stage < 0 || stage > 1 || part < DC_PART_ALL || part > DC_PART_INTERIOR)
+    if (!h || stage < 0 || stage > 1 || part < DC_PART_ALL || part > DC_PART_COLP)
         return fail(DC_ERR_ARG, "dc_stage_compute: bad argument");
     int rc;
     if ((rc = check_fused_fields(h, "dc_stage_compute"))) return rc;
@@ -693,8 +698,6 @@ int dc_stage_compute(dc_handle *h, int stage, int part, void *stream)
     if (h->g.nz > NZMAX)
         return fail(DC_ERR_STATE, "dc_stage_compute: nz <= %d required", NZMAX);
     do_stage_fused(h, stage, part, stream);
-    if (part != DC_PART_BOUNDARY)   // COLP is read by every stage-kernel launch of the stage
-        dcb_d2d_async(h->f.COLP, h->f.COLP_NEW, h->g.plane * sizeof(double), stream);
     return backend_status("dc_stage_compute");
 }
 
@@ -814,7 +817,6 @@ int dc_step_matsuno(dc_handle *h, int nsteps, void *stream)
             dcb_d2d_async(f.COLP_OLD, f.COLP, b2, stream);      // dyn_matsuno.py:34
             for (int stage = 0; stage < 2; stage++) {            // estimate, final
                 do_stage_fused(h, stage, DC_PART_ALL, stream);
-                dcb_d2d_async(f.COLP, f.COLP_NEW, b2, stream);  // dyn_matsuno.py:64-67
                 do_diag_fused(h, stage, stream);
             }
         }

@@ -64,32 +64,37 @@ class BandCommunicator:
                                              self._ptr(self.recv_n), stream))
 
     def stage(self, stage, stream):
-        """one Matsuno stage on this band.  On CUDA the exchange of the boundary rows runs on
-        a second stream while the interior tile rows are computed."""
+        """one Matsuno stage on this band.  On CUDA the boundary tile rows, the packing and
+        the NCCL exchange run on a second, high-priority stream concurrently with the
+        interior tile rows on the main stream."""
         L, h = _lib.lib(), self.GR.dyncore()
         dev = self.F.torch_device
+        P = _lib
         if dev.type != 'cuda':
             # host emulation (tests): same call sequence, no streams to overlap
-            _lib.check(L.dc_stage_compute(h, stage, _lib.DC_PART_BOUNDARY, stream))
+            for part in (P.DC_PART_CONT, P.DC_PART_BOUNDARY):
+                _lib.check(L.dc_stage_compute(h, stage, part, stream))
             works = self._post(stage, stream)
-            _lib.check(L.dc_stage_compute(h, stage, _lib.DC_PART_INTERIOR, stream))
+            for part in (P.DC_PART_INTERIOR, P.DC_PART_COLP):
+                _lib.check(L.dc_stage_compute(h, stage, part, stream))
             self._finish(stage, works, stream)
         else:
             if self.comm_stream is None:
-                self.comm_stream = torch.cuda.Stream(device=dev)
-            main = torch.cuda.current_stream(dev)
-            _lib.check(L.dc_stage_compute(h, stage, _lib.DC_PART_BOUNDARY, stream))
+                self.comm_stream = torch.cuda.Stream(device=dev, priority=-1)
+            main, side = torch.cuda.current_stream(dev), self.comm_stream
+            _lib.check(L.dc_stage_compute(h, stage, P.DC_PART_CONT, stream))
             ready = torch.cuda.Event()
             ready.record(main)
-            with torch.cuda.stream(self.comm_stream):
-                self.comm_stream.wait_event(ready)
-                works = self._post(stage, self.comm_stream.cuda_stream)
-            _lib.check(L.dc_stage_compute(h, stage, _lib.DC_PART_INTERIOR, stream))
+            with torch.cuda.stream(side):
+                side.wait_event(ready)    # also orders after the previous stage's unpack
+                _lib.check(L.dc_stage_compute(h, stage, P.DC_PART_BOUNDARY, side.cuda_stream))
+                boundary_done = torch.cuda.Event()
+                boundary_done.record(side)
+                works = self._post(stage, side.cuda_stream)
+            _lib.check(L.dc_stage_compute(h, stage, P.DC_PART_INTERIOR, stream))
+            main.wait_event(boundary_done)       # both stage-kernel parts have read COLP
+            _lib.check(L.dc_stage_compute(h, stage, P.DC_PART_COLP, stream))
             self._finish(stage, works, stream)
-            # the message buffers are reused by the next stage's pack on the comm stream
-            done = torch.cuda.Event()
-            done.record(main)
-            self.comm_stream.wait_event(done)
         _lib.check(L.dc_stage_diag(h, stage, stream))
 
 

@@ -135,11 +135,14 @@ int dc_step_matsuno(dc_handle *h, int nsteps, void *stream);
  * dc_step_begin once per step.  Messages are contiguous buffers of dc_halo_bytes() bytes per
  * direction; pass NULL for a direction that ends at a domain wall.  The result is bitwise
  * identical to the single-device run (no cross-rank reductions).
- * Overlap: dc_stage_compute(DC_PART_BOUNDARY) computes what the neighbours wait for (continuity
- * and the outermost tile rows); the caller can then pack + send on a second stream while
- * dc_stage_compute(DC_PART_INTERIOR) runs; dc_halo_unpack must follow the INTERIOR / ALL call
- * (it writes the halo rows of COLP, which the stage kernel reads). */
-enum { DC_PART_ALL = 0, DC_PART_BOUNDARY = 1, DC_PART_INTERIOR = 2 };
+ * Overlap: a stage can be issued in pieces -- DC_PART_CONT (continuity + moisture stage),
+ * DC_PART_BOUNDARY (stage kernel on the first / last tile row: what the neighbours wait for),
+ * DC_PART_INTERIOR (the other tile rows), DC_PART_COLP (COLP <- COLP_NEW).  BOUNDARY and
+ * INTERIOR only depend on CONT and may run concurrently on two streams; the caller packs and
+ * sends after BOUNDARY while INTERIOR runs.  COLP must follow both (they read COLP), and
+ * dc_halo_unpack must follow COLP (it writes the halo rows of COLP). */
+enum { DC_PART_ALL = 0, DC_PART_CONT = 1, DC_PART_BOUNDARY = 2, DC_PART_INTERIOR = 3,
+       DC_PART_COLP = 4 };
 int dc_step_begin(dc_handle *h, void *stream);
 int dc_stage_compute(dc_handle *h, int stage, int part, void *stream);
 int dc_stage_diag(dc_handle *h, int stage, void *stream);

@@ -269,9 +269,12 @@ def test_boundary_interior_split_equals_whole_stage(fixture):
             for _ in range(2):
                 _lib.check(L.dc_step_begin(h, 0))
                 for stage in (0, 1):
+                    _lib.check(L.dc_stage_compute(h, stage, _lib.DC_PART_CONT, 0))
+                    # INTERIOR before BOUNDARY: the two are independent
+                    _lib.check(L.dc_stage_compute(h, stage, _lib.DC_PART_INTERIOR, 0))
                     _lib.check(L.dc_stage_compute(h, stage, _lib.DC_PART_BOUNDARY, 0))
                     _lib.check(L.dc_halo_pack(h, stage, None, None, 0))
-                    _lib.check(L.dc_stage_compute(h, stage, _lib.DC_PART_INTERIOR, 0))
+                    _lib.check(L.dc_stage_compute(h, stage, _lib.DC_PART_COLP, 0))
                     _lib.check(L.dc_halo_unpack(h, stage, None, None, 0))
                     _lib.check(L.dc_stage_diag(h, stage, 0))
         F.copy_device_to_host(GR, F.ALL_FIELDS)
