@@ -48,6 +48,7 @@ STEP_BYTES = {False: 216, True: 296}
 # decomposed today; x 8 B = bytes per cell per launch
 KERNEL_ACCESSES = {
     'continuity': (5, 5), 'continuity_fused': (3, 5), 'stage_fused': (12.5, 12.5),
+    'primary_diag_fused': (5, 5),
     'moist_euler': (0, 6), 'moist_stage': (0, 9), 'uvflx_prep': (15, 15), 'uflx_tendency': (13, 13),
     'vflx_tendency': (13, 13), 'pott_tendency': (6, 6), 'moist_tendency': (7, 7),
     'euler_forward': (9, 15), 'primary_diag': (6, 6), 'copy_old': (6, 10),
@@ -291,7 +292,8 @@ def main():
         top = max(kern, key=lambda k: kern[k][0]) if kern else None
         roof = None
         if top:
-            key = 'continuity_fused' if (top == 'continuity' and args.mode == 'fused') else top
+            key = top + '_fused' if (top in ('continuity', 'primary_diag') and
+                                     args.mode == 'fused') else top
             acc = KERNEL_ACCESSES.get(key, (0, 0))[1 if moist else 0]
             k_ms = kern[top][0] / kern[top][1]
             cells_launch = cells // world
