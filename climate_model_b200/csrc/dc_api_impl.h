@@ -12,6 +12,8 @@
 //   template <class Body> void dcb_launch(const Body &b, int i0, int i1, int j0, int j1,
 //                                         void *stream);   // body(i, j) for the closed box
 //   void dcb_launch_stage(const dc::StageBody &b, int nbx, int nby, void *stream);
+//   void dcb_launch_stage3(dc_handle *h, dc::Stage3Body &b, const dc::Stage3Ptrs &p, int nbx,
+//                          int nby, void *stream);   // fills b's TMA descriptors from p
 //   void dcb_transpose(const dc::Geom &g, double *ref, double *dev, int fnx, int fny,
 //                      int nk, int j_lo, int j_hi, int to_device, void *stream);
 //   void dcb_profile_begin(dc_handle *h, const char *name, void *stream);
@@ -21,6 +23,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -30,8 +33,15 @@
 #include "dc_geom.h"
 #include "dc_fused.h"
 #include "dc_kernels.h"
+#include "dc_stage3.h"
 
 namespace dc {
+
+// fields the third-generation stage kernel stages by TMA (a descriptor each)
+struct Stage3Ptrs {
+    const double *U, *V, *W, *PHI, *T, *PV, *PB;   // staged boxes; W, PB: nz+1 interfaces
+    const double *TB, *Uo, *Vo, *To;               // own-column boxes; TB: nz+1 interfaces
+};
 
 static thread_local std::string g_last_error;
 
@@ -89,6 +99,8 @@ struct dc_handle {
     int profiling;
     void *profile_state;  // backend-owned
     int mode;             // DC_MODE_FUSED (default) or DC_MODE_KERNELS
+    int stage_impl;       // fused mode: 3 = dc_stage3.h (default), 2 = dc_fused.h (DC_STAGE_IMPL=2)
+    void *tma_state;      // backend-owned descriptor cache
     double **slot(int id) { return reinterpret_cast<double **>(&f) + id; }
     double *const *slot(int id) const { return reinterpret_cast<double *const *>(&f) + id; }
 };
@@ -272,6 +284,7 @@ static void do_stage_fused(dc_handle *h, int stage, int part, void *stream)
         }
     }
     // tile rows of the band: [j0, j1] in steps of TY; boundary = first and last tile row
+    const int TY = h->stage_impl == 3 ? S3_TY : dc::TY;
     const int ntr = (g.j1 - g.j0 + TY) / TY;
     const bool can_split = ntr >= 4;
     struct Range { int lo, hi; } ranges[2];
@@ -284,17 +297,44 @@ static void do_stage_fused(dc_handle *h, int stage, int part, void *stream)
     } else if (part == DC_PART_INTERIOR && can_split) {
         ranges[nr++] = Range{g.j0 + TY, g.j0 + (ntr - 1) * TY - 1};
     }
-    for (int r = 0; r < nr; r++) {
+    for (int r = 0; r < nr && h->stage_impl == 3; r++) {
+        Stage3Body sb;
+        sb.g = g;
+        sb.COLP = f.COLP; sb.COLP_NEW = f.COLP_NEW; sb.COLP_OLD = f.COLP_OLD;
+        sb.WWIND = f.WWIND; sb.POTTVB = f.POTTVB; sb.PVTFVB = f.PVTFVB;
+        sb.UWIND_out = Uo; sb.VWIND_out = Vo; sb.POTT_out = To;
+        sb.j_lo = ranges[r].lo; sb.j_hi = ranges[r].hi;
+        sb.have_old = stage == 0 ? 0 : 1;   // stage 1 evaluates the step-start state itself
+        const Stage3Ptrs sp{U, V, f.WWIND, f.PHI, T, f.PVTF, f.PVTFVB, f.POTTVB,
+                            f.UWIND, f.VWIND, f.POTT};
+        if (h->profiling) dcb_profile_begin(h, "stage_fused", stream);
+        dcb_launch_stage3(h, sb, sp, (g.nx + S3_TX - 1) / S3_TX,
+                          (ranges[r].hi - ranges[r].lo + S3_TY) / S3_TY, stream);
+        if (h->profiling) dcb_profile_end(h, stream);
+        h->launches++;
+    }
+    for (int r = 0; r < nr && h->stage_impl != 3; r++) {
         StageBody sb{g,       U,      V,          T,          f.PHI,   f.PVTF,  f.PVTFVB, f.POTTVB,
                      f.WWIND, f.COLP, f.COLP_NEW, f.COLP_OLD, f.UWIND, f.VWIND, f.POTT,
                      Uo,      Vo,     To,         ranges[r].lo, ranges[r].hi};
         if (h->profiling) dcb_profile_begin(h, "stage_fused", stream);
-        dcb_launch_stage(sb, (g.nx + TX - 1) / TX, (ranges[r].hi - ranges[r].lo + TY) / TY, stream);
+        dcb_launch_stage(sb, (g.nx + TX - 1) / TX, (ranges[r].hi - ranges[r].lo + dc::TY) / dc::TY,
+                         stream);
         if (h->profiling) dcb_profile_end(h, stream);
         h->launches++;
     }
     if (part == DC_PART_ALL || part == DC_PART_COLP)
         dcb_d2d_async(f.COLP, f.COLP_NEW, g.plane * sizeof(double), stream);  // dyn_matsuno.py:64-67
+}
+
+// the TMA-staged stage kernel reads the periodic image UWIND[nx+2] = UWIND[2], which an
+// imported initial state does not carry (dc_stage3.h: XHaloFixBody)
+static void do_xhalo_fix(dc_handle *h, void *stream)
+{
+    if (h->stage_impl != 3) return;
+    const Geom &g = h->g;
+    const int lo = g.j0 - HJ < 0 ? 0 : g.j0 - HJ, hi = g.j1 + HJ > g.ny + 1 ? g.ny + 1 : g.j1 + HJ;
+    launch(h, "xhalo_fix", XHaloFixBody{g, h->f.UWIND}, 0, g.nz - 1, lo, hi, stream);
 }
 
 // primary diagnostics of the state a stage produced, on every row this rank holds
@@ -472,6 +512,9 @@ int dc_create(const dc_grid_desc *d, dc_handle **out)
     h->profiling = 0;
     h->mode = DC_MODE_FUSED;
     h->profile_state = nullptr;
+    h->tma_state = nullptr;
+    const char *impl = getenv("DC_STAGE_IMPL");
+    h->stage_impl = (impl && impl[0] == '2') ? 2 : 3;
     *out = h;
     return DC_OK;
 }
@@ -480,6 +523,7 @@ int dc_destroy(dc_handle *h)
 {
     if (!h) return DC_OK;
     if (h->geom_buf) dcb_free(h->geom_buf);
+    dcb_tma_release(h);
     delete h;
     return DC_OK;
 }
@@ -684,6 +728,7 @@ int dc_step_begin(dc_handle *h, void *stream)
     int rc;
     if ((rc = check_fused_fields(h, "dc_step_begin"))) return rc;
     dcb_d2d_async(h->f.COLP_OLD, h->f.COLP, h->g.plane * sizeof(double), stream);
+    do_xhalo_fix(h, stream);
     return backend_status("dc_step_begin");
 }
 
@@ -813,6 +858,7 @@ int dc_step_matsuno(dc_handle *h, int nsteps, void *stream)
         return fail(DC_ERR_STATE, "dc_step_matsuno: the fused mode supports nz <= %d "
                                   "(use dc_set_mode(h, DC_MODE_KERNELS))", NZMAX);
     if (h->mode == DC_MODE_FUSED) {
+        do_xhalo_fix(h, stream);
         for (int s = 0; s < nsteps; s++) {
             dcb_d2d_async(f.COLP_OLD, f.COLP, b2, stream);      // dyn_matsuno.py:34
             for (int stage = 0; stage < 2; stage++) {            // estimate, final

@@ -1,0 +1,724 @@
+// dc_stage3.h -- the fused stage kernel of the Matsuno step, third generation.
+//
+// Same job as dc_fused.h (one launch advances U, V and POTT by one Matsuno stage: momentum-flux
+// preparation dyn_UVFLX_prepare.py:249-439, dUFLXdt dyn_UFLX.py:69-199, dVFLXdt
+// dyn_VFLX.py:67-198, dPOTTdt dyn_POTT.py:55-110, pressure-weighted Euler step
+// dyn_timestep.py:212-296, boundary images misc_boundaries.py:22-42), re-designed around the
+// resource ncu showed to bound the second generation: SHARED-MEMORY BANDWIDTH (128 B/clk/SM;
+// 80 % busy, profiles/r1_variants.md).
+//
+//   * a thread owns TWO longitude-adjacent columns and reads every stencil row with 16-byte
+//     shared loads: a 3-wide stencil row of two cells is 4 words instead of 6;
+//   * the (tile + halo) planes of U, V, WWIND, PHI, POTT, PVTF, PVTFVB arrive by TMA
+//     (cp.async.bulk.tensor, one elected thread, mbarrier completion, 3-deep ring): no
+//     per-thread copy instructions, no address registers, no LSU wavefronts for the fill;
+//   * the eight auxiliary momentum fluxes (B..T) are NOT exchanged through shared memory: each
+//     thread evaluates the 30 flux values its two cells need from the UFLX / VFLX planes
+//     (15 per cell instead of 8 + frame, but the FP64 pipe has room and the kernel loses
+//     eight planes, one phase and one block barrier per level);
+//   * the pressure-gradient term reads ONE precomputed plane
+//       G = POTT/dsigma * (sigma_vb[k+1]*(PVTFVB[k+1]-PVTF) + sigma_vb[k]*(PVTF-PVTFVB[k]))
+//     (the reference's per-column sub-expression, dyn_functions.py:177-207) instead of POTT,
+//     PVTF and two PVTFVB planes.
+//
+// Per level: TMA wait -> phase A (UFLX, VFLX, COLP_NEW*A*WWIND, G of the staged region) ->
+// barrier -> phase C (everything else, in registers) -> barrier.  Every expression keeps the
+// reference's evaluation order, so the strict build stays bit-identical to the
+// one-kernel-per-reference-kernel mode.  The periodic longitude images are read from the x
+// halo cells of the inputs (valid by construction: every producer stores its boundary
+// images; the x-staggered cell nx+2 of the initial UWIND is refreshed by k_xhalo_fix).
+//
+// Written against the SPMD macro layer so that tests/emu runs the same body on the host
+// (TMA = a box copy with zero fill, mbarrier = no-op).
+#pragma once
+#include <stdlib.h>
+
+#include "dc_fused.h"
+#include "dc_geom.h"
+#include "dc_kernels.h"
+#include "dc_point.h"
+
+namespace dc {
+
+#ifndef DC_S3_TY
+#define DC_S3_TY 8
+#endif
+constexpr int S3_TX = 32, S3_TY = DC_S3_TY;          // tile: 32 x TY columns
+constexpr int S3_NTX = S3_TX / 2;                    // threads along longitude (2 cells each)
+constexpr int S3_NT = S3_NTX * S3_TY;                // threads per block
+constexpr int S3_SW = S3_TX + 4;                     // staged columns ri in [-1, TX+2]
+constexpr int S3_SH = S3_TY + 3;                     // staged rows    rj in [-1, TY+1]
+constexpr int S3_SN = S3_SW * S3_SH;
+constexpr int S3_PL = (S3_SN + 15) / 16 * 16;        // plane pitch: a multiple of 128 B
+constexpr int S3_NP = S3_SN / 2;                     // staged pairs (SW is even)
+constexpr int S3_NQ = (S3_NP + S3_NT - 1) / S3_NT;   // staged pairs per thread
+// own-column boxes start one column left of the tile: the innermost TMA coordinate must be
+// 16-byte aligned (an odd fp64 column raises "illegal instruction"), and I0 - 1 is even
+constexpr int S3_OW = S3_TX + 2;
+constexpr int S3_OWN = S3_OW * S3_TY;
+constexpr int S3_NBUF = 3;                           // level k computes, k+1 has landed (its
+                                                     // own U, V are read), k+2 is in flight
+
+// ---- TMA descriptor -------------------------------------------------------------------
+#if defined(__CUDACC__)
+typedef CUtensorMap TmaMap;
+#else
+struct alignas(64) TmaMap {   // host emulation: what cuTensorMapEncodeTiled would encode
+    const double *base;
+    int dim[3];               // NI, NJ, nk (contiguous)
+    int box[3];
+    char pad[128 - sizeof(const double *) - 6 * sizeof(int)];
+};
+#endif
+
+struct alignas(16) D2 {
+    double x, y;
+};
+DC_HD D2 ld2(const double *p) { return *reinterpret_cast<const D2 *>(p); }
+DC_HD void st2(double *p, double x, double y) { *reinterpret_cast<D2 *>(p) = D2{x, y}; }
+// stencil rows of a pair: columns i_a-1, i_a, i_b, i_b+1 (, i_b+2, i_b+3)
+struct R4 {
+    double m1, a, b, p1;
+};
+struct R6 {
+    double m1, a, b, p1, p2, p3;
+};
+DC_HD R4 ld4(const double *p)
+{
+    const D2 x = ld2(p), y = ld2(p + 2);
+    return R4{x.x, x.y, y.x, y.y};
+}
+DC_HD R6 ld6(const double *p)
+{
+    const D2 x = ld2(p), y = ld2(p + 2), z = ld2(p + 4);
+    return R6{x.x, x.y, y.x, y.y, z.x, z.y};
+}
+
+struct alignas(128) Stage3Smem {
+    // TMA destinations (128-byte aligned): raw planes of a level, 3-deep ring
+    double rU[S3_NBUF][S3_PL], rV[S3_NBUF][S3_PL], rW[S3_NBUF][S3_PL], rPHI[S3_NBUF][S3_PL],
+        rT[S3_NBUF][S3_PL], rPV[S3_NBUF][S3_PL], rPB[S3_NBUF][S3_PL];
+    // own-column boxes: POTTVB[k+1] and the step-start U, V, POTT of level k
+    double oTB[S3_NBUF][S3_OWN], oUo[S3_NBUF][S3_OWN], oVo[S3_NBUF][S3_OWN], oTo[S3_NBUF][S3_OWN];
+    // derived planes of the current level
+    double UF[S3_PL], VF[S3_PL], P[S3_PL], G[S3_PL];
+    double lev[6][NZMAX + 1];   // as StageSmem::lev
+    double row[7][S3_TY + 1];   // as StageSmem::row
+    unsigned long long full[S3_NBUF];   // mbarriers: "level has landed"
+};
+
+// ---- SPMD layer for this kernel (1-D block of S3_NT threads) ----------------------------
+#if defined(__CUDA_ARCH__)
+#define S3_PRIV(type, name) type name
+#define S3_PRIVN(type, name, n) type name[n]
+#define S3_PRIVNN(type, name, n, m) type name[n][m]
+#define S3_P(name) name
+#define S3_PHASE {                       \
+        const int tid = threadIdx.x;
+#define S3_PHASE_END \
+    }                \
+    __syncthreads();
+#define S3_PHASE_END_NOSYNC }
+#else
+#define S3_PRIV(type, name) type name[S3_NT]
+#define S3_PRIVN(type, name, n) type name[S3_NT][n]
+#define S3_PRIVNN(type, name, n, m) type name[S3_NT][n][m]
+#define S3_P(name) name[tid]
+#define S3_PHASE for (int tid = 0; tid < S3_NT; tid++) {
+#define S3_PHASE_END }
+#define S3_PHASE_END_NOSYNC }
+#endif
+
+#if defined(__CUDACC__)
+// nvcc: device code issues the PTX; the host pass only needs the symbols
+DC_HD unsigned s3_smem_u32(const void *p)
+{
+#if defined(__CUDA_ARCH__)
+    return (unsigned)__cvta_generic_to_shared(p);
+#else
+    (void)p;
+    return 0;
+#endif
+}
+DC_HD void s3_mbar_init(unsigned long long *bar, int count)
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s3_smem_u32(bar)), "r"(count)
+                 : "memory");
+#else
+    (void)bar; (void)count;
+#endif
+}
+DC_HD void s3_mbar_init_fence()
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
+}
+DC_HD void s3_mbar_expect(unsigned long long *bar, unsigned bytes)
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s3_smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+#else
+    (void)bar; (void)bytes;
+#endif
+}
+DC_HD void s3_mbar_wait(unsigned long long *bar, unsigned parity)
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "S3_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra S3_DONE;\n\t"
+        "bra S3_WAIT;\n\t"
+        "S3_DONE:\n\t"
+        "}" ::"r"(s3_smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+#else
+    (void)bar; (void)parity;
+#endif
+}
+DC_HD void s3_tma_load(void *dst, const TmaMap *map, int x, int y, int z, unsigned long long *bar)
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(s3_smem_u32(dst)),
+        "l"(reinterpret_cast<unsigned long long>(map)), "r"(s3_smem_u32(bar)), "r"(x), "r"(y),
+        "r"(z)
+        : "memory");
+#else
+    (void)dst; (void)map; (void)x; (void)y; (void)z; (void)bar;
+#endif
+}
+#else
+inline void s3_mbar_init(unsigned long long *, int) {}
+inline void s3_mbar_init_fence() {}
+inline void s3_mbar_expect(unsigned long long *, unsigned) {}
+inline void s3_mbar_wait(unsigned long long *, unsigned) {}
+inline void s3_tma_load(void *dst, const TmaMap *m, int x, int y, int z, unsigned long long *)
+{
+    double *d = static_cast<double *>(dst);
+    // hardware rule (measured on B200): the innermost box coordinate must be 16-byte aligned
+    if ((x & 1) || (reinterpret_cast<size_t>(dst) & 127)) abort();
+    for (int b = 0; b < m->box[1]; b++)
+        for (int a = 0; a < m->box[0]; a++) {
+            const int i = x + a, j = y + b;
+            const bool in = i >= 0 && i < m->dim[0] && j >= 0 && j < m->dim[1] && z >= 0 &&
+                            z < m->dim[2];
+            d[b * m->box[0] + a] =
+                in ? m->base[((size_t)z * m->dim[1] + j) * (size_t)m->dim[0] + i] : 0.;
+        }
+}
+#endif
+
+// pressure-gradient term with the per-column part G precomputed (dyn_functions.py:177-207):
+// csum = COLP + COLP_dm1, cdif = (COLP - COLP_dm1) * con_cp / 2.
+DC_HD double pre_grad_g(double PHI, double PHI_dm1, double csum, double cdif, double G,
+                        double G_dm1, double dgrid)
+{
+    return (-dgrid * ((PHI - PHI_dm1) * csum / 2. + cdif * (+G_dm1 + G)));
+}
+
+struct Stage3Body {
+    Geom g;
+    TmaMap mU, mV, mW, mPHI, mT, mPV, mPB;   // boxes S3_SW x S3_SH x 1
+    TmaMap mTB, mUo, mVo, mTo;               // boxes S3_OW x S3_TY x 1
+    const double *COLP, *COLP_NEW, *COLP_OLD;
+    const double *WWIND, *POTTVB, *PVTFVB;   // set-up reads of interface 0
+    double *UWIND_out, *VWIND_out, *POTT_out;
+    int j_lo, j_hi;   // global mass rows to advance
+    int have_old;     // 0: the step-start state is the state the tendencies are evaluated at
+
+    DC_HD int wrap_i(int i) const { return i < 1 ? i + g.nx : (i > g.nx ? i - g.nx : i); }
+
+    DC_HD void run_block(int bx, int by, Stage3Smem &s) const
+    {
+        const int I0 = 1 + bx * S3_TX, J0 = j_lo + by * S3_TY;
+        const int j_top = (j_hi < g.ny - 1) ? j_hi : g.ny - 1;
+        const bool interior = (I0 >= 3) && (I0 + S3_TX - 1 <= g.nx - 1) && (J0 >= 2) &&
+                              (J0 + S3_TY - 1 <= j_top);
+        if (interior)
+            run<false>(bx, by, s);
+        else
+            run<true>(bx, by, s);
+    }
+
+    // issue the TMA copies of level kp into ring slot kp % NBUF (one thread)
+    DC_HD void issue(Stage3Smem &s, int kp, int x0, int y0) const
+    {
+        const int bp = kp % S3_NBUF;
+        unsigned long long *bar = &s.full[bp];
+        const unsigned bytes =
+            7u * S3_SN * 8u + (have_old ? 4u : 1u) * (unsigned)S3_OWN * 8u;
+        s3_mbar_expect(bar, bytes);
+        s3_tma_load(s.rU[bp], &mU, x0, y0, kp, bar);
+        s3_tma_load(s.rV[bp], &mV, x0, y0, kp, bar);
+        s3_tma_load(s.rW[bp], &mW, x0, y0, kp + 1, bar);
+        s3_tma_load(s.rPHI[bp], &mPHI, x0, y0, kp, bar);
+        s3_tma_load(s.rT[bp], &mT, x0, y0, kp, bar);
+        s3_tma_load(s.rPV[bp], &mPV, x0, y0, kp, bar);
+        s3_tma_load(s.rPB[bp], &mPB, x0, y0, kp + 1, bar);
+        s3_tma_load(s.oTB[bp], &mTB, x0, y0 + 1, kp + 1, bar);
+        if (have_old) {
+            s3_tma_load(s.oUo[bp], &mUo, x0, y0 + 1, kp, bar);
+            s3_tma_load(s.oVo[bp], &mVo, x0, y0 + 1, kp, bar);
+            s3_tma_load(s.oTo[bp], &mTo, x0, y0 + 1, kp, bar);
+        }
+    }
+
+    template <bool EDGE>
+    DC_HD void run(int bx, int by, Stage3Smem &s) const
+    {
+        const int nx = g.nx, ny = g.ny, nz = g.nz;
+        const int I0 = 1 + bx * S3_TX, J0 = j_lo + by * S3_TY;
+        const size_t plane = g.plane;
+        const double dyis = g.dyis, dt = g.dt;
+        const double scale = cor_scale(g.dlon_rad, g.dlat_rad);
+        const int x0 = I0 - 1, y0 = g.row(J0 - 1);   // TMA box origin (columns, device rows)
+        // rows this rank holds (global): halo rows included
+        const int j_min = (g.j0 - HJ < 0) ? 0 : g.j0 - HJ;
+        const int j_max_m = (g.j1 + HJ > ny + 1) ? ny + 1 : g.j1 + HJ;          // mass rows
+        const int j_max_y = (g.j1 + HJ + 1 > ny + 2) ? ny + 2 : g.j1 + HJ + 1;  // y-staggered
+
+        // ---- thread-private state --------------------------------------------------------
+        // phase A: coefficients of this thread's staged pairs
+        S3_PRIVNN(double, cu, S3_NQ, 2);    // (COLP[i-1,j] + COLP[i,j]) / 2
+        S3_PRIVNN(double, cv, S3_NQ, 2);    // (COLP[i,j-1] + COLP[i,j]) / 2
+        S3_PRIVNN(double, cp, S3_NQ, 2);    // COLP_NEW[i,j] * A[j]
+        S3_PRIVNN(double, pbp, S3_NQ, 2);   // PVTFVB of interface k (carried)
+        S3_PRIVN(double, dxv, S3_NQ);       // dxjs[j]
+        // phase C: the two own columns a = (ia, j), b = (ia + 1, j)
+        S3_PRIV(int, off0);                 // plane offset of cell a
+        S3_PRIV(int, flags);                // bit 0/1: a/b is advanced; bit 2/3: a/b has images
+        S3_PRIV(double, c_m1);              // COLP at ia-1, ia, ia+1, ia+2 of row j
+        S3_PRIV(double, c_a);
+        S3_PRIV(double, c_b);
+        S3_PRIV(double, c_p1);
+        S3_PRIVN(double, c_jm1, 2);
+        S3_PRIVN(double, c_jp1, 2);
+        S3_PRIVN(double, csx, 2);           // COLP + COLP_im1
+        S3_PRIVN(double, cdx, 2);           // (COLP - COLP_im1) * con_cp / 2
+        S3_PRIVN(double, csy, 2);
+        S3_PRIVN(double, cdy, 2);
+        S3_PRIVN(double, cnew, 2);
+        S3_PRIVN(double, cold, 2);
+        S3_PRIVN(double, colpa_is, 2);
+        S3_PRIVN(double, colpa_old_is, 2);
+        S3_PRIVN(double, colpa_js, 2);
+        S3_PRIVN(double, colpa_old_js, 2);
+        S3_PRIVN(double, r_colpa_is, 2);    // reciprocals: DC_FAST_MATH only (dead otherwise)
+        S3_PRIVN(double, r_colpa_js, 2);
+        S3_PRIVN(double, r_cnew, 2);
+        S3_PRIVN(double, wwu_k, 2);         // WWIND_UWIND at interface k (carried)
+        S3_PRIVN(double, wwv_k, 2);
+        S3_PRIVN(double, w_k, 2);           // WWIND[k]
+        S3_PRIVN(double, pottvb_k, 2);
+
+        // ---- set-up -----------------------------------------------------------------------
+        S3_PHASE
+            if (tid == 0) {
+                for (int n = 0; n < S3_NBUF; n++) s3_mbar_init(&s.full[n], 1);
+                s3_mbar_init_fence();
+            }
+        S3_PHASE_END
+        S3_PHASE
+            if (tid == 0) {   // levels 0 and 1 fly while the column constants are gathered
+                issue(s, 0, x0, y0);
+                if (nz > 1) issue(s, 1, x0, y0);
+            }
+            // 1) coefficients of the staged pairs: pair p holds staged words 2p, 2p+1
+            for (int q = 0; q < S3_NQ; q++) {
+                const int p = tid + q * S3_NT;
+                const int r = (2 * p) / S3_SW, cw = (2 * p) % S3_SW;
+                int j = J0 + r - 1;
+                if (j < j_min) j = j_min;
+                const int jm = j > j_max_m ? j_max_m : j;   // row in a mass / x-staggered field
+                const int jy = j > j_max_y ? j_max_y : j;   // row in a y-staggered field
+                const int jc = jy > j_max_m ? j_max_m : jy;
+                const int jcm = (jy - 1 < j_min) ? j_min : (jy - 1 > j_max_m ? j_max_m : jy - 1);
+                for (int e = 0; e < 2; e++) {
+                    int i = I0 + cw - 1 + e;
+                    if (i > nx + 2) i = nx + 2;   // columns beyond the domain: masked cells only
+                    // the periodic images are formed from the interior columns [1, nx], as
+                    // exchange_BC does (misc_boundaries.py:26-32)
+                    const int iw = wrap_i(i), iwm = wrap_i(i - 1);
+                    // UFLX = (C[i-1] + C[i])/2 * U * dyis     (dyn_continuity.py:40-41)
+                    S3_P(cu)[q][e] = (COLP[g.idx2(iwm, jm)] + COLP[g.idx2(iw, jm)]) / 2.;
+                    // VFLX = (C[j-1] + C[j])/2 * V * dxjs     (dyn_continuity.py:43-44)
+                    S3_P(cv)[q][e] = (COLP[g.idx2(iw, jcm)] + COLP[g.idx2(iw, jc)]) / 2.;
+                    // COLP_NEW * A * WWIND                    (dyn_functions.py:254-260)
+                    S3_P(cp)[q][e] = COLP_NEW[g.idx2(iw, jm)] * g.A[g.row(jm)];
+                    S3_P(pbp)[q][e] = PVTFVB[g.idx2(iw, jm)];
+                }
+                S3_P(dxv)[q] = g.dxjs[g.row(jy)];
+            }
+            // 2) constants of the two own columns
+            {
+                const int tx = tid % S3_NTX, ty = tid / S3_NTX;
+                const int ia = I0 + 2 * tx, j = J0 + ty;
+                const int va = (ia <= nx) && (j <= j_hi), vb = (ia + 1 <= nx) && (j <= j_hi);
+                // masked pairs read a safe in-domain neighbourhood
+                const int ii = ia > nx ? nx - 1 : ia, jj = j <= j_hi ? j : j_hi;
+                const int ea = (ia <= 2) || (ia == nx) || (jj == 1) || (jj == ny);
+                const int eb = (ia + 1 <= 2) || (ia + 1 == nx) || (jj == 1) || (jj == ny);
+                S3_P(flags) = va | (vb << 1) | (ea << 2) | (eb << 3);
+                S3_P(off0) = (int)g.idx2(ii, jj);
+                const double *C = COLP, *CN = COLP_NEW, *CO = COLP_OLD;
+                S3_P(c_m1) = C[g.idx2(ii - 1, jj)];
+                S3_P(c_a) = C[g.idx2(ii, jj)];
+                S3_P(c_b) = C[g.idx2(ii + 1, jj)];
+                S3_P(c_p1) = C[g.idx2(ii + 2, jj)];
+                const double A = g.A[g.row(jj)], A_jm1 = g.A[g.row(jj - 1)],
+                             A_jp1 = g.A[g.row(jj + 1)];
+                for (int e = 0; e < 2; e++) {
+                    const int ie = ii + e;
+                    const double c = C[g.idx2(ie, jj)], cm = C[g.idx2(ie - 1, jj)];
+                    S3_P(c_jm1)[e] = C[g.idx2(ie, jj - 1)];
+                    S3_P(c_jp1)[e] = C[g.idx2(ie, jj + 1)];
+                    S3_P(csx)[e] = c + cm;
+                    S3_P(cdx)[e] = (c - cm) * con_cp / 2.;
+                    S3_P(csy)[e] = c + S3_P(c_jm1)[e];
+                    S3_P(cdy)[e] = (c - S3_P(c_jm1)[e]) * con_cp / 2.;
+                    // the Euler step runs after COLP <- COLP_NEW (dyn_matsuno.py:64-67)
+                    S3_P(cnew)[e] = CN[g.idx2(ie, jj)];
+                    S3_P(cold)[e] = CO[g.idx2(ie, jj)];
+                    S3_P(colpa_is)[e] = interp_COLPA_is(
+                        CN[g.idx2(ie, jj)], CN[g.idx2(ie - 1, jj)], CN[g.idx2(ie, jj - 1)],
+                        CN[g.idx2(ie, jj + 1)], CN[g.idx2(ie - 1, jj + 1)],
+                        CN[g.idx2(ie - 1, jj - 1)], A, A_jm1, A_jp1, jj, ny);
+                    S3_P(colpa_old_is)[e] = interp_COLPA_is(
+                        CO[g.idx2(ie, jj)], CO[g.idx2(ie - 1, jj)], CO[g.idx2(ie, jj - 1)],
+                        CO[g.idx2(ie, jj + 1)], CO[g.idx2(ie - 1, jj + 1)],
+                        CO[g.idx2(ie - 1, jj - 1)], A, A_jm1, A_jp1, jj, ny);
+                    S3_P(colpa_js)[e] = interp_COLPA_js(
+                        CN[g.idx2(ie, jj)], CN[g.idx2(ie, jj - 1)], CN[g.idx2(ie - 1, jj)],
+                        CN[g.idx2(ie + 1, jj)], CN[g.idx2(ie + 1, jj - 1)],
+                        CN[g.idx2(ie - 1, jj - 1)], A, A_jm1);
+                    S3_P(colpa_old_js)[e] = interp_COLPA_js(
+                        CO[g.idx2(ie, jj)], CO[g.idx2(ie, jj - 1)], CO[g.idx2(ie - 1, jj)],
+                        CO[g.idx2(ie + 1, jj)], CO[g.idx2(ie + 1, jj - 1)],
+                        CO[g.idx2(ie - 1, jj - 1)], A, A_jm1);
+                    S3_P(r_colpa_is)[e] = DC_FAST ? 1. / S3_P(colpa_is)[e] : 0.;
+                    S3_P(r_colpa_js)[e] = DC_FAST ? 1. / S3_P(colpa_js)[e] : 0.;
+                    S3_P(r_cnew)[e] = DC_FAST ? 1. / S3_P(cnew)[e] : 0.;
+                    S3_P(wwu_k)[e] = 0.;   // WWIND_UWIND[0] = 0 (dyn_functions.py:236-237)
+                    S3_P(wwv_k)[e] = 0.;
+                    S3_P(w_k)[e] = WWIND[S3_P(off0) + e];
+                    S3_P(pottvb_k)[e] = POTTVB[S3_P(off0) + e];
+                }
+            }
+            // constant tables
+            for (int k = tid; k <= nz; k += S3_NT) {
+                s.lev[0][k] = k < nz ? g.dsigma[k] : 0.;
+                s.lev[1][k] = k < nz ? g.r_dsigma[k] : 0.;
+                s.lev[2][k] = g.sigma_vb[k];
+                s.lev[3][k] = k < nz ? g.UVFLX_dif_coef[k] : 0.;
+                s.lev[4][k] = k < nz ? g.POTT_dif_coef[k] : 0.;
+                s.lev[5][k] = k < nz ? g.r_dss[k] : 0.;
+            }
+            if (tid <= S3_TY) {
+                int j = J0 - 1 + tid;
+                if (j > j_max_m) j = j_max_m;
+                const int r = g.row(j);
+                s.row[0][tid] = cor_fcos(g.corf_is[r], g.cos_lat_is[r]);
+                s.row[1][tid] = g.sin_lat_is[r];
+                s.row[2][tid] = cor_fcos(g.corf[r], g.cos_lat[r]);
+                s.row[3][tid] = g.sin_lat[r];
+                s.row[4][tid] = g.dxjs[r];
+                s.row[5][tid] = g.A[r];
+                s.row[6][tid] = g.r_A[r];
+            }
+            s3_mbar_wait(&s.full[0], 0);   // level 0 has landed
+        S3_PHASE_END
+
+        for (int k = 0; k < nz; k++) {
+            const int b = k % S3_NBUF, b1 = (k + 1) % S3_NBUF;
+            const size_t ko = (size_t)k * plane;
+            const bool last = (k + 1 == nz);
+            // ---- A: UFLX, VFLX, COLP_NEW*A*WWIND(k+1) and G of the staged region ------------
+            S3_PHASE
+                // level k+2 -> the slot level k-1 has released (trailing barrier of level k-1)
+                if (tid == 0 && k + 2 < nz) issue(s, k + 2, x0, y0);
+                const double ds = s.lev[0][k];
+                const Div ds_d = mkdiv(ds, s.lev[1][k]);
+                const double svb = s.lev[2][k], svb1 = s.lev[2][k + 1];
+                for (int q = 0; q < S3_NQ; q++) {
+                    const int p = tid + q * S3_NT;
+                    if (p < S3_NP) {
+                        const int idx = 2 * p;
+                        const D2 U = ld2(&s.rU[b][idx]), V = ld2(&s.rV[b][idx]),
+                                 W = ld2(&s.rW[b][idx]), T = ld2(&s.rT[b][idx]),
+                                 PV = ld2(&s.rPV[b][idx]), PB = ld2(&s.rPB[b][idx]);
+                        st2(&s.UF[idx], S3_P(cu)[q][0] * U.x * dyis,               // calc_UFLX
+                            S3_P(cu)[q][1] * U.y * dyis);
+                        st2(&s.VF[idx], S3_P(cv)[q][0] * V.x * S3_P(dxv)[q],       // calc_VFLX
+                            S3_P(cv)[q][1] * V.y * S3_P(dxv)[q]);
+                        st2(&s.P[idx], S3_P(cp)[q][0] * W.x, S3_P(cp)[q][1] * W.y);
+                        st2(&s.G[idx],
+                            T.x / ds_d * (svb1 * (PB.x - PV.x) + svb * (PV.x - S3_P(pbp)[q][0])),
+                            T.y / ds_d * (svb1 * (PB.y - PV.y) + svb * (PV.y - S3_P(pbp)[q][1])));
+                        S3_P(pbp)[q][0] = PB.x;
+                        S3_P(pbp)[q][1] = PB.y;
+                    }
+                }
+                // phase C reads the own U, V of level k+1 from the next ring slot
+                if (!last) s3_mbar_wait(&s.full[b1], ((k + 1) / S3_NBUF) & 1);
+            S3_PHASE_END
+            // ---- C: fluxes, tendencies, Euler step, stores ------------------------------
+            S3_PHASE
+                const int tx = tid % S3_NTX, ty = tid / S3_NTX;
+                const int ia = I0 + 2 * tx, j = J0 + ty;
+                const int b0 = (ty + 1) * S3_SW + 2 * tx;   // staged word of (ia - 1, j)
+                const int o0 = ty * S3_OW + 2 * tx + 1;     // own-box word of cell a
+                const double ds = s.lev[0][k];
+                const Div ds_d = mkdiv(ds, s.lev[1][k]);
+                const double w_kp1[2] = {s.rW[b][b0 + 1], s.rW[b][b0 + 2]};
+                const double pottvb_kp1[2] = {s.oTB[b][o0], s.oTB[b][o0 + 1]};
+                const int fl = S3_P(flags);
+                if (!EDGE || (fl & 3)) {
+                    const bool wall_s = EDGE && (j == 1), wall_n = EDGE && (j == ny);
+                    // UFLX / VFLX neighbourhoods of the pair
+                    const R6 u_m = ld6(&s.UF[b0 - S3_SW]), u_0 = ld6(&s.UF[b0]);
+                    const R4 u_p = ld4(&s.UF[b0 + S3_SW]);
+                    const R4 v_m = ld4(&s.VF[b0 - S3_SW]), v_0 = ld4(&s.VF[b0]),
+                             v_p = ld4(&s.VF[b0 + S3_SW]), v_pp = ld4(&s.VF[b0 + 2 * S3_SW]);
+                    const R4 U_m = ld4(&s.rU[b][b0 - S3_SW]), U_0 = ld4(&s.rU[b][b0]),
+                             U_p = ld4(&s.rU[b][b0 + S3_SW]);
+                    const R4 V_m = ld4(&s.rV[b][b0 - S3_SW]), V_0 = ld4(&s.rV[b][b0]),
+                             V_p = ld4(&s.rV[b][b0 + S3_SW]);
+                    const double u[2] = {U_0.a, U_0.b}, v[2] = {V_0.a, V_0.b};
+                    // vertical momentum fluxes through interface k+1
+                    // (dyn_functions.py:211-270; 0 at the model bottom)
+                    double wwu_kp1[2] = {0., 0.}, wwv_kp1[2] = {0., 0.};
+                    if (!last) {
+                        const R4 P_m = ld4(&s.P[b0 - S3_SW]), P_0 = ld4(&s.P[b0]),
+                                 P_p = ld4(&s.P[b0 + S3_SW]);
+                        const double ds_kp1 = s.lev[0][k + 1];
+                        const Div dss_d = mkdiv(ds_kp1 + ds, s.lev[5][k + 1]);
+                        const int wall = wall_s ? -1 : (wall_n ? 1 : 0);
+                        const double u1[2] = {s.rU[b1][b0 + 1], s.rU[b1][b0 + 2]};
+                        const double v1[2] = {s.rV[b1][b0 + 1], s.rV[b1][b0 + 2]};
+                        wwu_kp1[0] = colpa_wwind(P_0.a, P_0.m1, P_m.a, P_p.a, P_m.m1, P_p.m1, wall) *
+                                     interp_ks(u1[0], u[0], ds_kp1, ds, dss_d);
+                        wwu_kp1[1] = colpa_wwind(P_0.b, P_0.a, P_m.b, P_p.b, P_m.a, P_p.a, wall) *
+                                     interp_ks(u1[1], u[1], ds_kp1, ds, dss_d);
+                        wwv_kp1[0] = colpa_wwind(P_0.a, P_m.a, P_0.m1, P_0.b, P_m.m1, P_m.b, 0) *
+                                     interp_ks(v1[0], v[0], ds_kp1, ds, dss_d);
+                        wwv_kp1[1] = colpa_wwind(P_0.b, P_m.b, P_0.a, P_0.p1, P_m.a, P_m.p1, 0) *
+                                     interp_ks(v1[1], v[1], ds_kp1, ds, dss_d);
+                    }
+                    const R4 PHI_0 = ld4(&s.rPHI[b][b0]), G_0 = ld4(&s.G[b0]);
+                    const double coef_uv = s.lev[3][k];
+                    // step-start values of the own cells
+                    double uo[2] = {u[0], u[1]}, vo[2] = {v[0], v[1]};
+                    if (have_old) {
+                        uo[0] = s.oUo[b][o0]; uo[1] = s.oUo[b][o0 + 1];
+                        vo[0] = s.oVo[b][o0]; vo[1] = s.oVo[b][o0 + 1];
+                    }
+                    // ---------------- dUFLXdt (dyn_UFLX.py:69-199) ----------------
+                    {
+                        // auxiliary fluxes (dyn_functions.py:429-536) around the pair
+                        const double B_m1 = calc_BFLX(u_m.m1, u_m.a, u_0.m1, u_0.a, u_p.m1, u_p.a);
+                        const double B_a = calc_BFLX(u_m.a, u_m.b, u_0.a, u_0.b, u_p.a, u_p.b);
+                        const double B_b = calc_BFLX(u_m.b, u_m.p1, u_0.b, u_0.p1, u_p.b, u_p.p1);
+                        double C_a = calc_CFLX(v_m.m1, v_m.a, v_0.m1, v_0.a, v_p.m1, v_p.a);
+                        double C_b = calc_CFLX(v_m.a, v_m.b, v_0.a, v_0.b, v_p.a, v_p.b);
+                        double C_a_jp1 = calc_CFLX(v_0.m1, v_0.a, v_p.m1, v_p.a, v_pp.m1, v_pp.a);
+                        double C_b_jp1 = calc_CFLX(v_0.a, v_0.b, v_p.a, v_p.b, v_pp.a, v_pp.b);
+                        double D_m1 = calc_DFLX(v_m.m1, v_0.m1, v_p.m1, u_m.m1, u_0.m1, u_m.a, u_0.a);
+                        double D_a = calc_DFLX(v_m.a, v_0.a, v_p.a, u_m.a, u_0.a, u_m.b, u_0.b);
+                        double D_a_jp1 = calc_DFLX(v_0.a, v_p.a, v_pp.a, u_0.a, u_p.a, u_0.b, u_p.b);
+                        double D_b_jp1 = calc_DFLX(v_0.b, v_p.b, v_pp.b, u_0.b, u_p.b, u_0.p1, u_p.p1);
+                        double E_a = calc_EFLX(v_m.a, v_0.a, v_p.a, u_m.a, u_0.a, u_m.b, u_0.b);
+                        double E_b = calc_EFLX(v_m.b, v_0.b, v_p.b, u_m.b, u_0.b, u_m.p1, u_0.p1);
+                        double E_m1_jp1 =
+                            calc_EFLX(v_0.m1, v_p.m1, v_pp.m1, u_0.m1, u_p.m1, u_0.a, u_p.a);
+                        double E_a_jp1 = calc_EFLX(v_0.a, v_p.a, v_pp.a, u_0.a, u_p.a, u_0.b, u_p.b);
+                        if (wall_s) {   // BCy, dyn_UFLX.py:377-384
+                            D_m1 = 0.; D_a = 0.; C_a = 0.; C_b = 0.; E_a = 0.; E_b = 0.;
+                        }
+                        if (wall_n) {
+                            D_a_jp1 = 0.; D_b_jp1 = 0.; C_a_jp1 = 0.; C_b_jp1 = 0.;
+                            E_m1_jp1 = 0.; E_a_jp1 = 0.;
+                        }
+                        double d[2] = {0., 0.};
+                        d[0] = d[0] + UVFLX_hor_adv(U_0.a, U_0.m1, U_0.b, U_m.a, U_p.a, U_m.m1, U_p.m1,
+                                                    U_m.b, U_p.b, B_a, B_m1, C_a, C_a_jp1, D_m1,
+                                                    D_a_jp1, E_a, E_m1_jp1, 1.);
+                        d[1] = d[1] + UVFLX_hor_adv(U_0.b, U_0.a, U_0.p1, U_m.b, U_p.b, U_m.a, U_p.a,
+                                                    U_m.p1, U_p.p1, B_b, B_a, C_b, C_b_jp1, D_a,
+                                                    D_b_jp1, E_b, E_a_jp1, 1.);
+                        d[0] = d[0] + ((S3_P(wwu_k)[0] - wwu_kp1[0]) / ds_d);
+                        d[1] = d[1] + ((S3_P(wwu_k)[1] - wwu_kp1[1]) / ds_d);
+                        const double fcos_is = s.row[0][ty + 1], sin_is = s.row[1][ty + 1];
+                        d[0] = d[0] + coriolis_UWIND(S3_P(c_a), S3_P(c_m1), V_0.a, V_0.m1, V_p.a,
+                                                     V_p.m1, U_0.a, U_0.m1, U_0.b, fcos_is, sin_is,
+                                                     scale);
+                        d[1] = d[1] + coriolis_UWIND(S3_P(c_b), S3_P(c_a), V_0.b, V_0.a, V_p.b, V_p.a,
+                                                     U_0.b, U_0.a, U_0.p1, fcos_is, sin_is, scale);
+                        d[0] = d[0] + pre_grad_g(PHI_0.a, PHI_0.m1, S3_P(csx)[0], S3_P(cdx)[0], G_0.a,
+                                                 G_0.m1, dyis);
+                        d[1] = d[1] + pre_grad_g(PHI_0.b, PHI_0.a, S3_P(csx)[1], S3_P(cdx)[1], G_0.b,
+                                                 G_0.a, dyis);
+                        if (coef_uv > 0.) {
+                            d[0] = d[0] + num_dif(u_0.a, u_0.m1, u_0.b, u_m.a, u_p.a, coef_uv);
+                            d[1] = d[1] + num_dif(u_0.b, u_0.a, u_0.p1, u_m.b, u_p.b, coef_uv);
+                        }
+                        for (int e = 0; e < 2; e++) {
+                            const double un = euler_forward_pw(
+                                uo[e], d[e], mkdiv(S3_P(colpa_is)[e], S3_P(r_colpa_is)[e]),
+                                S3_P(colpa_old_is)[e], dt);
+                            if (EDGE) {
+                                if (fl & (1 << e)) {
+                                    if (fl & (4 << e))
+                                        put_xstag(g, UWIND_out, ia + e, j, k, un);
+                                    else
+                                        UWIND_out[ko + S3_P(off0) + e] = un;
+                                }
+                            } else {
+                                UWIND_out[ko + S3_P(off0) + e] = un;
+                            }
+                        }
+                    }
+                    // ---------------- dVFLXdt (dyn_VFLX.py:67-198) ----------------
+                    if (!EDGE || j >= 2) {
+                        const double R_a = calc_RFLX(v_0.m1, v_p.m1, v_0.a, v_p.a, v_0.b, v_p.b);
+                        const double R_b = calc_RFLX(v_0.a, v_p.a, v_0.b, v_p.b, v_0.p1, v_p.p1);
+                        const double R_a_jm1 = calc_RFLX(v_m.m1, v_0.m1, v_m.a, v_0.a, v_m.b, v_0.b);
+                        const double R_b_jm1 = calc_RFLX(v_m.a, v_0.a, v_m.b, v_0.b, v_m.p1, v_0.p1);
+                        const double Q_a = calc_QFLX(u_m.m1, u_0.m1, u_m.a, u_0.a, u_m.b, u_0.b);
+                        const double Q_b = calc_QFLX(u_m.a, u_0.a, u_m.b, u_0.b, u_m.p1, u_0.p1);
+                        const double Q_p1 = calc_QFLX(u_m.b, u_0.b, u_m.p1, u_0.p1, u_m.p2, u_0.p2);
+                        const double S_a_jm1 =
+                            calc_SFLX(v_m.m1, v_0.m1, v_m.a, v_0.a, u_m.m1, u_m.a, u_m.b);
+                        const double S_b_jm1 =
+                            calc_SFLX(v_m.a, v_0.a, v_m.b, v_0.b, u_m.a, u_m.b, u_m.p1);
+                        const double S_b = calc_SFLX(v_0.a, v_p.a, v_0.b, v_p.b, u_0.a, u_0.b, u_0.p1);
+                        const double S_p1 =
+                            calc_SFLX(v_0.b, v_p.b, v_0.p1, v_p.p1, u_0.b, u_0.p1, u_0.p2);
+                        const double T_a = calc_TFLX(v_0.m1, v_p.m1, v_0.a, v_p.a, u_0.m1, u_0.a, u_0.b);
+                        const double T_b = calc_TFLX(v_0.a, v_p.a, v_0.b, v_p.b, u_0.a, u_0.b, u_0.p1);
+                        const double T_b_jm1 =
+                            calc_TFLX(v_m.a, v_0.a, v_m.b, v_0.b, u_m.a, u_m.b, u_m.p1);
+                        const double T_p1_jm1 =
+                            calc_TFLX(v_m.b, v_0.b, v_m.p1, v_0.p1, u_m.b, u_m.p1, u_m.p2);
+                        double d[2] = {0., 0.};
+                        d[0] = d[0] + UVFLX_hor_adv(V_0.a, V_m.a, V_p.a, V_0.m1, V_0.b, V_m.m1, V_m.b,
+                                                    V_p.m1, V_p.b, R_a, R_a_jm1, Q_a, Q_b, S_a_jm1,
+                                                    S_b, T_a, T_b_jm1, -1.);
+                        d[1] = d[1] + UVFLX_hor_adv(V_0.b, V_m.b, V_p.b, V_0.a, V_0.p1, V_m.a, V_m.p1,
+                                                    V_p.a, V_p.p1, R_b, R_b_jm1, Q_b, Q_p1, S_b_jm1,
+                                                    S_p1, T_b, T_p1_jm1, -1.);
+                        d[0] = d[0] + ((S3_P(wwv_k)[0] - wwv_kp1[0]) / ds_d);
+                        d[1] = d[1] + ((S3_P(wwv_k)[1] - wwv_kp1[1]) / ds_d);
+                        const double fcos = s.row[2][ty + 1], sinl = s.row[3][ty + 1],
+                                     fcos_jm1 = s.row[2][ty], sinl_jm1 = s.row[3][ty];
+                        d[0] = d[0] + coriolis_VWIND(S3_P(c_a), S3_P(c_jm1)[0], U_0.a, U_m.a, U_0.b,
+                                                     U_m.b, fcos, sinl, fcos_jm1, sinl_jm1, scale);
+                        d[1] = d[1] + coriolis_VWIND(S3_P(c_b), S3_P(c_jm1)[1], U_0.b, U_m.b, U_0.p1,
+                                                     U_m.p1, fcos, sinl, fcos_jm1, sinl_jm1, scale);
+                        const double dxjs = s.row[4][ty + 1];
+                        d[0] = d[0] + pre_grad_g(PHI_0.a, s.rPHI[b][b0 - S3_SW + 1], S3_P(csy)[0],
+                                                 S3_P(cdy)[0], G_0.a, s.G[b0 - S3_SW + 1], dxjs);
+                        d[1] = d[1] + pre_grad_g(PHI_0.b, s.rPHI[b][b0 - S3_SW + 2], S3_P(csy)[1],
+                                                 S3_P(cdy)[1], G_0.b, s.G[b0 - S3_SW + 2], dxjs);
+                        if (coef_uv > 0.) {
+                            d[0] = d[0] + num_dif(v_0.a, v_0.m1, v_0.b, v_m.a, v_p.a, coef_uv);
+                            d[1] = d[1] + num_dif(v_0.b, v_0.a, v_0.p1, v_m.b, v_p.b, coef_uv);
+                        }
+                        for (int e = 0; e < 2; e++) {
+                            const double vn = euler_forward_pw(
+                                vo[e], d[e], mkdiv(S3_P(colpa_js)[e], S3_P(r_colpa_js)[e]),
+                                S3_P(colpa_old_js)[e], dt);
+                            if (EDGE) {
+                                if (fl & (1 << e)) {
+                                    if (fl & (4 << e))
+                                        put_ystag(g, VWIND_out, ia + e, j, k, vn);
+                                    else
+                                        VWIND_out[ko + S3_P(off0) + e] = vn;
+                                }
+                            } else {
+                                VWIND_out[ko + S3_P(off0) + e] = vn;
+                            }
+                        }
+                    } else {
+                        for (int e = 0; e < 2; e++)
+                            if (fl & (1 << e)) put_ystag(g, VWIND_out, ia + e, 1, k, 0.);
+                    }
+                    if (wall_n)
+                        for (int e = 0; e < 2; e++)
+                            if (fl & (1 << e)) put_ystag(g, VWIND_out, ia + e, ny + 1, k, 0.);
+                    // ---------------- dPOTTdt (dyn_POTT.py:55-110) ----------------
+                    {
+                        const R4 T_0 = ld4(&s.rT[b][b0]);
+                        const double p_jm1[2] = {s.rT[b][b0 - S3_SW + 1], s.rT[b][b0 - S3_SW + 2]};
+                        const double p_jp1[2] = {s.rT[b][b0 + S3_SW + 1], s.rT[b][b0 + S3_SW + 2]};
+                        const Div A_d = mkdiv(s.row[5][ty + 1], s.row[6][ty + 1]);
+                        const double coef = s.lev[4][k];
+                        double to[2] = {T_0.a, T_0.b};
+                        if (have_old) {
+                            to[0] = s.oTo[b][o0]; to[1] = s.oTo[b][o0 + 1];
+                        }
+                        double d[2] = {0., 0.};
+                        d[0] = d[0] + hor_adv(T_0.a, T_0.m1, T_0.b, p_jm1[0], p_jp1[0], u_0.a, u_0.b,
+                                              v_0.a, v_p.a, A_d);
+                        d[1] = d[1] + hor_adv(T_0.b, T_0.a, T_0.p1, p_jm1[1], p_jp1[1], u_0.b, u_0.p1,
+                                              v_0.b, v_p.b, A_d);
+                        for (int e = 0; e < 2; e++)
+                            d[e] = d[e] + vert_adv(S3_P(pottvb_k)[e], pottvb_kp1[e], S3_P(w_k)[e],
+                                                   w_kp1[e], S3_P(cnew)[e], ds_d, k);
+                        if (coef > 0.) {
+                            d[0] = d[0] + num_dif_pw(T_0.a, T_0.m1, T_0.b, p_jm1[0], p_jp1[0],
+                                                     S3_P(c_a), S3_P(c_m1), S3_P(c_b),
+                                                     S3_P(c_jm1)[0], S3_P(c_jp1)[0], coef);
+                            d[1] = d[1] + num_dif_pw(T_0.b, T_0.a, T_0.p1, p_jm1[1], p_jp1[1],
+                                                     S3_P(c_b), S3_P(c_a), S3_P(c_p1),
+                                                     S3_P(c_jm1)[1], S3_P(c_jp1)[1], coef);
+                        }
+                        for (int e = 0; e < 2; e++) {
+                            const double tn = euler_forward_pw(
+                                to[e], d[e], mkdiv(S3_P(cnew)[e], S3_P(r_cnew)[e]), S3_P(cold)[e],
+                                dt);
+                            if (EDGE) {
+                                if (fl & (1 << e)) {
+                                    if (fl & (4 << e))
+                                        put_mass(g, POTT_out, ia + e, j, k, tn);
+                                    else
+                                        POTT_out[ko + S3_P(off0) + e] = tn;
+                                }
+                            } else {
+                                POTT_out[ko + S3_P(off0) + e] = tn;
+                            }
+                        }
+                    }
+                    for (int e = 0; e < 2; e++) {
+                        S3_P(wwu_k)[e] = wwu_kp1[e];
+                        S3_P(wwv_k)[e] = wwv_kp1[e];
+                    }
+                }
+                for (int e = 0; e < 2; e++) {
+                    S3_P(w_k)[e] = w_kp1[e];
+                    S3_P(pottvb_k)[e] = pottvb_kp1[e];
+                }
+            S3_PHASE_END
+        }
+    }
+};
+
+// the x-staggered halo column nx+2 of an imported UWIND is never initialised by the
+// reference's set-up boundary condition (main_grid.py:340-343); the TMA-staged kernel reads
+// the periodic image there.  threads: i = level, j = held rows
+struct XHaloFixBody {
+    Geom g;
+    double *U;
+    DC_HD void operator()(int k, int j) const { U[g.idx(g.nx + 2, j, k)] = U[g.idx(2, j, k)]; }
+};
+
+}  // namespace dc

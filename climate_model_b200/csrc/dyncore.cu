@@ -6,6 +6,7 @@
 // Build (see __graft_entry__.build):
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -shared ...
 // -fmad=false keeps the reference's evaluation order (numba emits no FMA contraction).
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include "dc_geom.h"
@@ -22,7 +23,16 @@ static int dcb_d2d_async(void *dst, const void *src, size_t n, void *stream)
 {
     return (int)cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
 }
-static int dcb_last_error() { return (int)cudaGetLastError(); }
+static int g_stage3_error = 0;   // descriptor failures of the stage-3 launcher (sticky)
+static int dcb_last_error()
+{
+    if (g_stage3_error) {
+        const int e = g_stage3_error;
+        g_stage3_error = 0;
+        return e;
+    }
+    return (int)cudaGetLastError();
+}
 static const char *dcb_error_string(int code) { return cudaGetErrorString((cudaError_t)code); }
 
 namespace dc {
@@ -64,6 +74,47 @@ static void dcb_launch_stage(const dc::StageBody &b, int nbx, int nby, void *str
     dc::k_stage<<<dim3(nbx, nby), dim3(dc::TX, dc::TY), sizeof(dc::StageSmem),
                   (cudaStream_t)stream>>>(b);
 }
+
+// ---------------------------------------------------------------------------------------
+// third-generation stage kernel (dc_stage3.h): TMA descriptors + launch
+// ---------------------------------------------------------------------------------------
+#include <map>
+#include <utility>
+#include "dc_stage3.h"
+struct dc_handle;
+namespace dc {
+struct Stage3Ptrs;
+__global__ void __launch_bounds__(S3_NT, 2) k_stage3(const __grid_constant__ Stage3Body b)
+{
+    extern __shared__ unsigned char stage3_smem[];
+    // the TMA destinations need 128-byte alignment
+    const unsigned a = (unsigned)__cvta_generic_to_shared(stage3_smem);
+    Stage3Smem &s = *reinterpret_cast<Stage3Smem *>(stage3_smem + ((128u - (a & 127u)) & 127u));
+    b.run_block(blockIdx.x, blockIdx.y, s);
+}
+struct TmaState {
+    std::map<std::pair<const void *, int>, CUtensorMap> maps;   // (field base, own box?)
+};
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                  const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) ==
+                cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+}  // namespace dc
+static void dcb_launch_stage3(dc_handle *h, dc::Stage3Body &b, const dc::Stage3Ptrs &p, int nbx,
+                              int nby, void *stream);
+static void dcb_tma_release(dc_handle *h);
 
 // ---------------------------------------------------------------------------------------
 // layout conversion: reference (i, j, k) k-fastest  <->  device F[k][jd][i] i-fastest.
@@ -197,4 +248,62 @@ static int dcb_profile_read(dc_handle *h, int max, const char **names, double *m
         i++;
     }
     return i;
+}
+
+// ---------------------------------------------------------------------------------------
+// third-generation stage kernel: descriptor cache and launch
+// ---------------------------------------------------------------------------------------
+static const CUtensorMap *stage3_map(dc_handle *h, const double *base, int nk, bool own)
+{
+    using namespace dc;
+    if (!h->tma_state) h->tma_state = new TmaState();
+    TmaState *st = static_cast<TmaState *>(h->tma_state);
+    const auto key = std::make_pair(static_cast<const void *>(base), (own ? 1 : 0) | (nk << 1));
+    auto it = st->maps.find(key);
+    if (it != st->maps.end()) return &it->second;
+    EncodeTiledFn enc = encode_tiled();
+    const Geom &g = h->g;
+    CUtensorMap m;
+    const cuuint64_t dims[3] = {(cuuint64_t)g.NI, (cuuint64_t)g.NJ, (cuuint64_t)nk};
+    const cuuint64_t strides[2] = {(cuuint64_t)g.NI * 8, (cuuint64_t)g.plane * 8};
+    const cuuint32_t box[3] = {(cuuint32_t)(own ? S3_OW : S3_SW), (cuuint32_t)(own ? S3_TY : S3_SH),
+                               1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    if (!enc || enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double *>(base), dims,
+                    strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+        g_stage3_error = (int)cudaErrorInvalidValue;
+        return nullptr;
+    }
+    return &(st->maps[key] = m);
+}
+static void dcb_tma_release(dc_handle *h)
+{
+    delete static_cast<dc::TmaState *>(h->tma_state);
+    h->tma_state = nullptr;
+}
+static void dcb_launch_stage3(dc_handle *h, dc::Stage3Body &b, const dc::Stage3Ptrs &p, int nbx,
+                              int nby, void *stream)
+{
+    using namespace dc;
+    static bool configured = false;
+    const int smem = (int)sizeof(Stage3Smem) + 128;
+    if (!configured) {
+        cudaFuncSetAttribute(k_stage3, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(k_stage3, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        configured = true;
+    }
+    const int nz = h->g.nz;
+    struct { CUtensorMap *dst; const double *base; int nk; bool own; } want[] = {
+        {&b.mU, p.U, nz, false},     {&b.mV, p.V, nz, false},   {&b.mW, p.W, nz + 1, false},
+        {&b.mPHI, p.PHI, nz, false}, {&b.mT, p.T, nz, false},   {&b.mPV, p.PV, nz, false},
+        {&b.mPB, p.PB, nz + 1, false}, {&b.mTB, p.TB, nz + 1, true}, {&b.mUo, p.Uo, nz, true},
+        {&b.mVo, p.Vo, nz, true},    {&b.mTo, p.To, nz, true}};
+    for (auto &w : want) {
+        const CUtensorMap *m = stage3_map(h, w.base, w.nk, w.own);
+        if (!m) return;
+        *w.dst = *m;
+    }
+    k_stage3<<<dim3(nbx, nby), dim3(S3_NT), smem, (cudaStream_t)stream>>>(b);
 }

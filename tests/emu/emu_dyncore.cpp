@@ -38,6 +38,12 @@ static void dcb_launch_stage(const dc::StageBody &b, int nbx, int nby, void *)
             b.run_block(bx, by, s);
         }
 }
+#include "../../climate_model_b200/csrc/dc_stage3.h"
+struct dc_handle;
+namespace dc { struct Stage3Ptrs; }
+static void dcb_launch_stage3(dc_handle *h, dc::Stage3Body &b, const dc::Stage3Ptrs &p, int nbx,
+                              int nby, void *);
+static void dcb_tma_release(dc_handle *) {}
 static void dcb_transpose(const dc::Geom &g, double *ref, double *dev, int fnx, int fny, int nk,
                           int j_lo, int j_hi, int to_device, void *)
 {
@@ -55,3 +61,28 @@ static void dcb_profile_end(dc_handle *, void *) {}
 static int dcb_profile_read(dc_handle *, int, const char **, double *, long long *) { return 0; }
 
 #include "../../climate_model_b200/csrc/dc_api_impl.h"
+
+// third-generation stage kernel: a TMA descriptor = (base, dims, box); a block = one call
+static void dcb_launch_stage3(dc_handle *, dc::Stage3Body &b, const dc::Stage3Ptrs &p, int nbx,
+                              int nby, void *)
+{
+    using namespace dc;
+    const Geom &g = b.g;
+    auto mk = [&](TmaMap &m, const double *base, int nk, bool own) {
+        m.base = base;
+        m.dim[0] = g.NI; m.dim[1] = g.NJ; m.dim[2] = nk;
+        m.box[0] = own ? S3_OW : S3_SW; m.box[1] = own ? S3_TY : S3_SH; m.box[2] = 1;
+    };
+    mk(b.mU, p.U, g.nz, false); mk(b.mV, p.V, g.nz, false); mk(b.mW, p.W, g.nz + 1, false);
+    mk(b.mPHI, p.PHI, g.nz, false); mk(b.mT, p.T, g.nz, false); mk(b.mPV, p.PV, g.nz, false);
+    mk(b.mPB, p.PB, g.nz + 1, false);
+    mk(b.mTB, p.TB, g.nz + 1, true); mk(b.mUo, p.Uo, g.nz, true); mk(b.mVo, p.Vo, g.nz, true);
+    mk(b.mTo, p.To, g.nz, true);
+    static Stage3Smem s;   // one "block" at a time
+    for (int by = nby - 1; by >= 0; by--)
+        for (int bx = nbx - 1; bx >= 0; bx--) {
+            for (size_t n = 0; n < sizeof(s) / sizeof(double); n++)
+                reinterpret_cast<double *>(&s)[n] = 0.0 / 0.0;   // stale smem must not be read
+            b.run_block(bx, by, s);
+        }
+}

@@ -226,17 +226,23 @@ def test_config2_1deg_32lev_against_oracle():
     assert np.max(np.abs(F.host['UWIND'][interior('UWIND', GR.nx, GR.ny)])) > 5.
 
 
-def test_full_size_properties_quarter_degree_64_levels():
+@pytest.mark.parametrize('build', ['strict', 'production'])
+def test_full_size_properties_quarter_degree_64_levels(build, request):
     """BASELINE.json configs[3] size (1440 x 672 x 64), where the oracle is too slow:
     size-independent properties of the scheme.
-      - a state shifted by m cells in longitude must give the bitwise shifted result
-        (periodic domain, identical arithmetic per cell);
+      - a state shifted by m cells in longitude must give the shifted result (periodic
+        domain): BITWISE in the strict build (identical arithmetic per cell; m is odd, so
+        the two columns a thread of the stage kernel owns swap roles), to rounding in the
+        production build (FMA contraction may differ between the two columns of a pair and
+        between edge and interior tiles);
       - boundary invariants: periodic duplicates, zero meridional wind on the walls;
       - the column-pressure update conserves total mass sum(COLP*A) to rounding."""
     import torch
     from climate_model_b200.dyn_matsuno import step_matsuno
     from climate_model_b200.main_fields import ModelFields
     from climate_model_b200.main_grid import Grid
+    if build == 'strict':
+        request.getfixturevalue('strict_library')
     GR = Grid(nz=64, lat0_deg=-84, lat1_deg=84, dlat_deg=0.25, dlon_deg=0.25, i_out_nth_hour=1.0)
     assert (GR.nx, GR.ny, GR.nz) == (1440, 672, 64)
     nx, ny = int(GR.nx), int(GR.ny)
@@ -264,7 +270,12 @@ def test_full_size_properties_quarter_degree_64_levels():
         a = F.device[n][:, :, 1:nx + 1]
         b = G.device[n][:, :, 1:nx + 1]
         assert torch.isfinite(a[:, js + 1:js + ny + 1]).all(), n
-        assert torch.equal(torch.roll(a, shifts=m, dims=2), b), 'shift invariance: ' + n
+        r = torch.roll(a, shifts=m, dims=2)
+        if build == 'strict':
+            assert torch.equal(r, b), 'shift invariance: ' + n
+        else:
+            e = ((r - b).abs().max() / b.abs().max().clamp_min(1e-300)).item()
+            assert e <= 0.1 * TOL[n], 'shift invariance (rounding): %s %.3e' % (n, e)
     U, V, C = F.device['UWIND'], F.device['VWIND'], F.device['COLP']
     assert torch.equal(U[:, :, nx + 1], U[:, :, 1]) and torch.equal(U[:, :, 0], U[:, :, nx])
     assert (V[:, js + 1] == 0).all() and (V[:, js + ny + 1] == 0).all()
