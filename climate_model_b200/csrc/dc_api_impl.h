@@ -11,6 +11,8 @@
 //   const char *dcb_error_string(int code);
 //   template <class Body> void dcb_launch(const Body &b, int i0, int i1, int j0, int j1,
 //                                         void *stream);   // body(i, j) for the closed box
+//   template <class Body, class Smem> void dcb_launch_blocks(const Body &b, int nbx, int nby,
+//                                         int nthreads, void *stream);  // b.run_block(bx, by, smem)
 //   void dcb_launch_stage(const dc::StageBody &b, int nbx, int nby, void *stream);
 //   void dcb_launch_stage3(dc_handle *h, dc::Stage3Body &b, const dc::Stage3Ptrs &p, int nbx,
 //                          int nby, void *stream);   // fills b's TMA descriptors from p
@@ -99,6 +101,7 @@ struct dc_handle {
     int profiling;
     void *profile_state;  // backend-owned
     int mode;             // DC_MODE_FUSED (default) or DC_MODE_KERNELS
+    int cont_impl;        // 2 = single-pass tile kernel (default), 1 = two-sweep column kernel
     int stage_impl;       // fused mode: 3 = dc_stage3.h (default), 2 = dc_fused.h (DC_STAGE_IMPL=2)
     void *tma_state;      // backend-owned descriptor cache
     double **slot(int id) { return reinterpret_cast<double **>(&f) + id; }
@@ -177,9 +180,20 @@ static void launch_continuity(dc_handle *h, const double *U, const double *V, vo
     const Geom &g = h->g;
     int lo, hi;
     continuity_rows(g, &lo, &hi);
-    ContinuityBody<MODE> b{g,      U,        V,       f.COLP,     f.COLP_OLD, f.UFLX,
-                           f.VFLX, f.FLXDIV, f.WWIND, f.COLP_NEW, f.dCOLPdt};
-    launch(h, "continuity", b, 1, g.nx, lo, hi, stream);
+    if (h->cont_impl == 1) {   // two-sweep column kernel (DC_CONT_IMPL=1)
+        ContinuityBody<MODE> b{g,      U,        V,       f.COLP,     f.COLP_OLD, f.UFLX,
+                               f.VFLX, f.FLXDIV, f.WWIND, f.COLP_NEW, f.dCOLPdt};
+        launch(h, "continuity", b, 1, g.nx, lo, hi, stream);
+        return;
+    }
+    if (hi < lo) return;
+    ContinuityTileBody<MODE> b{g,      U,        V,       f.COLP,     f.COLP_OLD, f.UFLX,
+                               f.VFLX, f.FLXDIV, f.WWIND, f.COLP_NEW, f.dCOLPdt, lo};
+    if (h->profiling) dcb_profile_begin(h, "continuity", stream);
+    dcb_launch_blocks<ContinuityTileBody<MODE>, ContinuitySmem>(
+        b, (g.nx + CT_TX - 1) / CT_TX, hi - lo + 1, (g.nz + CT_L - 1) / CT_L * CT_TX, stream);
+    if (h->profiling) dcb_profile_end(h, stream);
+    h->launches++;
 }
 
 static int do_continuity(dc_handle *h, bool store_flxdiv, void *stream)
@@ -397,6 +411,8 @@ int dc_field_info(int id, int *stgx, int *stgy, int *nk_kind)
 int dc_create(const dc_grid_desc *d, dc_handle **out)
 {
     if (!d || !out) return fail(DC_ERR_ARG, "dc_create: NULL argument");
+    if (d->nz > CT_L * CT_MAXW)
+        return fail(DC_ERR_ARG, "dc_create: nz <= %d required (got %d)", CT_L * CT_MAXW, d->nz);
     if (d->nx < 3 || d->ny < 3 || d->nz < 3)
         return fail(DC_ERR_ARG, "dc_create: need nx, ny, nz >= 3 (got %d %d %d)", d->nx, d->ny,
                     d->nz);
@@ -515,6 +531,8 @@ int dc_create(const dc_grid_desc *d, dc_handle **out)
     h->tma_state = nullptr;
     const char *impl = getenv("DC_STAGE_IMPL");
     h->stage_impl = (impl && impl[0] == '2') ? 2 : 3;
+    const char *cimpl = getenv("DC_CONT_IMPL");
+    h->cont_impl = (cimpl && cimpl[0] == '1') ? 1 : 2;
     *out = h;
     return DC_OK;
 }

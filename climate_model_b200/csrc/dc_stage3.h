@@ -226,6 +226,25 @@ DC_HD double pre_grad_g(double PHI, double PHI_dm1, double csum, double cdif, do
     return (-dgrid * ((PHI - PHI_dm1) * csum / 2. + cdif * (+G_dm1 + G)));
 }
 
+// momentum advection (dyn_functions.py:541-568).  Production build: the auxiliary fluxes arrive
+// pre-multiplied by 1/2 (folded into their 1/12, 1/24 factors), one multiplication less per term
+DC_HD double hor_adv_uv(double DWIND, double DWIND_dm1, double DWIND_dp1, double DWIND_pm1,
+                        double DWIND_pp1, double DWIND_dm1_pm1, double DWIND_dm1_pp1,
+                        double DWIND_dp1_pm1, double DWIND_dp1_pp1, double BRFLX, double BRFLX_dm1,
+                        double CQFLX, double CQFLX_pp1, double DSFLX_dm1, double DSFLX_pp1,
+                        double ETFLX, double ETFLX_dm1_pp1, double sign_ETFLX_term)
+{
+    if (DC_FAST)
+        return (+BRFLX_dm1 * (DWIND_dm1 + DWIND) - BRFLX * (DWIND + DWIND_dp1)
+                + CQFLX * (DWIND_pm1 + DWIND) - CQFLX_pp1 * (DWIND + DWIND_pp1)
+                + DSFLX_dm1 * (DWIND_dm1_pm1 + DWIND) - DSFLX_pp1 * (DWIND + DWIND_dp1_pp1)
+                + sign_ETFLX_term * (+ETFLX * (DWIND_dp1_pm1 + DWIND) -
+                                     ETFLX_dm1_pp1 * (DWIND + DWIND_dm1_pp1)));
+    return UVFLX_hor_adv(DWIND, DWIND_dm1, DWIND_dp1, DWIND_pm1, DWIND_pp1, DWIND_dm1_pm1,
+                         DWIND_dm1_pp1, DWIND_dp1_pm1, DWIND_dp1_pp1, BRFLX, BRFLX_dm1, CQFLX,
+                         CQFLX_pp1, DSFLX_dm1, DSFLX_pp1, ETFLX, ETFLX_dm1_pp1, sign_ETFLX_term);
+}
+
 struct Stage3Body {
     Geom g;
     TmaMap mU, mV, mW, mPHI, mT, mPV, mPB;   // boxes S3_SW x S3_SH x 1
@@ -525,22 +544,60 @@ struct Stage3Body {
                     // ---------------- dUFLXdt (dyn_UFLX.py:69-199) ----------------
                     {
                         // auxiliary fluxes (dyn_functions.py:429-536) around the pair
-                        const double B_m1 = calc_BFLX(u_m.m1, u_m.a, u_0.m1, u_0.a, u_p.m1, u_p.a);
-                        const double B_a = calc_BFLX(u_m.a, u_m.b, u_0.a, u_0.b, u_p.a, u_p.b);
-                        const double B_b = calc_BFLX(u_m.b, u_m.p1, u_0.b, u_0.p1, u_p.b, u_p.p1);
-                        double C_a = calc_CFLX(v_m.m1, v_m.a, v_0.m1, v_0.a, v_p.m1, v_p.a);
-                        double C_b = calc_CFLX(v_m.a, v_m.b, v_0.a, v_0.b, v_p.a, v_p.b);
-                        double C_a_jp1 = calc_CFLX(v_0.m1, v_0.a, v_p.m1, v_p.a, v_pp.m1, v_pp.a);
-                        double C_b_jp1 = calc_CFLX(v_0.a, v_0.b, v_p.a, v_p.b, v_pp.a, v_pp.b);
-                        double D_m1 = calc_DFLX(v_m.m1, v_0.m1, v_p.m1, u_m.m1, u_0.m1, u_m.a, u_0.a);
-                        double D_a = calc_DFLX(v_m.a, v_0.a, v_p.a, u_m.a, u_0.a, u_m.b, u_0.b);
-                        double D_a_jp1 = calc_DFLX(v_0.a, v_p.a, v_pp.a, u_0.a, u_p.a, u_0.b, u_p.b);
-                        double D_b_jp1 = calc_DFLX(v_0.b, v_p.b, v_pp.b, u_0.b, u_p.b, u_0.p1, u_p.p1);
-                        double E_a = calc_EFLX(v_m.a, v_0.a, v_p.a, u_m.a, u_0.a, u_m.b, u_0.b);
-                        double E_b = calc_EFLX(v_m.b, v_0.b, v_p.b, u_m.b, u_0.b, u_m.p1, u_0.p1);
-                        double E_m1_jp1 =
-                            calc_EFLX(v_0.m1, v_p.m1, v_pp.m1, u_0.m1, u_p.m1, u_0.a, u_p.a);
-                        double E_a_jp1 = calc_EFLX(v_0.a, v_p.a, v_pp.a, u_0.a, u_p.a, u_0.b, u_p.b);
+                        double B_m1, B_a, B_b, C_a, C_b, C_a_jp1, C_b_jp1, D_m1, D_a, D_a_jp1,
+                            D_b_jp1, E_a, E_b, E_m1_jp1, E_a_jp1;
+                        if (DC_FAST) {
+                            // shared partial sums; every flux carries the 1/2 of its advection term
+                            const double h12 = 1. / 24., h24 = 1. / 48.;
+                            const double uhm_m1 = u_m.m1 + u_m.a, uhm_a = u_m.a + u_m.b,
+                                         uhm_b = u_m.b + u_m.p1;
+                            const double uh0_m1 = u_0.m1 + u_0.a, uh0_a = u_0.a + u_0.b,
+                                         uh0_b = u_0.b + u_0.p1;
+                            const double uhp_m1 = u_p.m1 + u_p.a, uhp_a = u_p.a + u_p.b,
+                                         uhp_b = u_p.b + u_p.p1;
+                            B_m1 = h12 * (uhm_m1 + 2. * uh0_m1 + uhp_m1);
+                            B_a = h12 * (uhm_a + 2. * uh0_a + uhp_a);
+                            B_b = h12 * (uhm_b + 2. * uh0_b + uhp_b);
+                            const double vs0_m1 = v_m.m1 + 2. * v_0.m1 + v_p.m1,
+                                         vs0_a = v_m.a + 2. * v_0.a + v_p.a,
+                                         vs0_b = v_m.b + 2. * v_0.b + v_p.b;
+                            const double vs1_m1 = v_0.m1 + 2. * v_p.m1 + v_pp.m1,
+                                         vs1_a = v_0.a + 2. * v_p.a + v_pp.a,
+                                         vs1_b = v_0.b + 2. * v_p.b + v_pp.b;
+                            C_a = h12 * (vs0_m1 + vs0_a);
+                            C_b = h12 * (vs0_a + vs0_b);
+                            C_a_jp1 = h12 * (vs1_m1 + vs1_a);
+                            C_b_jp1 = h12 * (vs1_a + vs1_b);
+                            const double us0_m1 = uhm_m1 + uh0_m1, us0_a = uhm_a + uh0_a,
+                                         us0_b = uhm_b + uh0_b;
+                            const double us1_m1 = uh0_m1 + uhp_m1, us1_a = uh0_a + uhp_a,
+                                         us1_b = uh0_b + uhp_b;
+                            D_m1 = h24 * (vs0_m1 + us0_m1);
+                            D_a = h24 * (vs0_a + us0_a);
+                            D_a_jp1 = h24 * (vs1_a + us1_a);
+                            D_b_jp1 = h24 * (vs1_b + us1_b);
+                            E_a = h24 * (vs0_a - us0_a);
+                            E_b = h24 * (vs0_b - us0_b);
+                            E_m1_jp1 = h24 * (vs1_m1 - us1_m1);
+                            E_a_jp1 = h24 * (vs1_a - us1_a);
+                        } else {
+                            B_m1 = calc_BFLX(u_m.m1, u_m.a, u_0.m1, u_0.a, u_p.m1, u_p.a);
+                            B_a = calc_BFLX(u_m.a, u_m.b, u_0.a, u_0.b, u_p.a, u_p.b);
+                            B_b = calc_BFLX(u_m.b, u_m.p1, u_0.b, u_0.p1, u_p.b, u_p.p1);
+                            C_a = calc_CFLX(v_m.m1, v_m.a, v_0.m1, v_0.a, v_p.m1, v_p.a);
+                            C_b = calc_CFLX(v_m.a, v_m.b, v_0.a, v_0.b, v_p.a, v_p.b);
+                            C_a_jp1 = calc_CFLX(v_0.m1, v_0.a, v_p.m1, v_p.a, v_pp.m1, v_pp.a);
+                            C_b_jp1 = calc_CFLX(v_0.a, v_0.b, v_p.a, v_p.b, v_pp.a, v_pp.b);
+                            D_m1 = calc_DFLX(v_m.m1, v_0.m1, v_p.m1, u_m.m1, u_0.m1, u_m.a, u_0.a);
+                            D_a = calc_DFLX(v_m.a, v_0.a, v_p.a, u_m.a, u_0.a, u_m.b, u_0.b);
+                            D_a_jp1 = calc_DFLX(v_0.a, v_p.a, v_pp.a, u_0.a, u_p.a, u_0.b, u_p.b);
+                            D_b_jp1 = calc_DFLX(v_0.b, v_p.b, v_pp.b, u_0.b, u_p.b, u_0.p1, u_p.p1);
+                            E_a = calc_EFLX(v_m.a, v_0.a, v_p.a, u_m.a, u_0.a, u_m.b, u_0.b);
+                            E_b = calc_EFLX(v_m.b, v_0.b, v_p.b, u_m.b, u_0.b, u_m.p1, u_0.p1);
+                            E_m1_jp1 =
+                                calc_EFLX(v_0.m1, v_p.m1, v_pp.m1, u_0.m1, u_p.m1, u_0.a, u_p.a);
+                            E_a_jp1 = calc_EFLX(v_0.a, v_p.a, v_pp.a, u_0.a, u_p.a, u_0.b, u_p.b);
+                        }
                         if (wall_s) {   // BCy, dyn_UFLX.py:377-384
                             D_m1 = 0.; D_a = 0.; C_a = 0.; C_b = 0.; E_a = 0.; E_b = 0.;
                         }
@@ -549,10 +606,10 @@ struct Stage3Body {
                             E_m1_jp1 = 0.; E_a_jp1 = 0.;
                         }
                         double d[2] = {0., 0.};
-                        d[0] = d[0] + UVFLX_hor_adv(U_0.a, U_0.m1, U_0.b, U_m.a, U_p.a, U_m.m1, U_p.m1,
+                        d[0] = d[0] + hor_adv_uv(U_0.a, U_0.m1, U_0.b, U_m.a, U_p.a, U_m.m1, U_p.m1,
                                                     U_m.b, U_p.b, B_a, B_m1, C_a, C_a_jp1, D_m1,
                                                     D_a_jp1, E_a, E_m1_jp1, 1.);
-                        d[1] = d[1] + UVFLX_hor_adv(U_0.b, U_0.a, U_0.p1, U_m.b, U_p.b, U_m.a, U_p.a,
+                        d[1] = d[1] + hor_adv_uv(U_0.b, U_0.a, U_0.p1, U_m.b, U_p.b, U_m.a, U_p.a,
                                                     U_m.p1, U_p.p1, B_b, B_a, C_b, C_b_jp1, D_a,
                                                     D_b_jp1, E_b, E_a_jp1, 1.);
                         d[0] = d[0] + ((S3_P(wwu_k)[0] - wwu_kp1[0]) / ds_d);
@@ -589,31 +646,65 @@ struct Stage3Body {
                     }
                     // ---------------- dVFLXdt (dyn_VFLX.py:67-198) ----------------
                     if (!EDGE || j >= 2) {
-                        const double R_a = calc_RFLX(v_0.m1, v_p.m1, v_0.a, v_p.a, v_0.b, v_p.b);
-                        const double R_b = calc_RFLX(v_0.a, v_p.a, v_0.b, v_p.b, v_0.p1, v_p.p1);
-                        const double R_a_jm1 = calc_RFLX(v_m.m1, v_0.m1, v_m.a, v_0.a, v_m.b, v_0.b);
-                        const double R_b_jm1 = calc_RFLX(v_m.a, v_0.a, v_m.b, v_0.b, v_m.p1, v_0.p1);
-                        const double Q_a = calc_QFLX(u_m.m1, u_0.m1, u_m.a, u_0.a, u_m.b, u_0.b);
-                        const double Q_b = calc_QFLX(u_m.a, u_0.a, u_m.b, u_0.b, u_m.p1, u_0.p1);
-                        const double Q_p1 = calc_QFLX(u_m.b, u_0.b, u_m.p1, u_0.p1, u_m.p2, u_0.p2);
-                        const double S_a_jm1 =
-                            calc_SFLX(v_m.m1, v_0.m1, v_m.a, v_0.a, u_m.m1, u_m.a, u_m.b);
-                        const double S_b_jm1 =
-                            calc_SFLX(v_m.a, v_0.a, v_m.b, v_0.b, u_m.a, u_m.b, u_m.p1);
-                        const double S_b = calc_SFLX(v_0.a, v_p.a, v_0.b, v_p.b, u_0.a, u_0.b, u_0.p1);
-                        const double S_p1 =
-                            calc_SFLX(v_0.b, v_p.b, v_0.p1, v_p.p1, u_0.b, u_0.p1, u_0.p2);
-                        const double T_a = calc_TFLX(v_0.m1, v_p.m1, v_0.a, v_p.a, u_0.m1, u_0.a, u_0.b);
-                        const double T_b = calc_TFLX(v_0.a, v_p.a, v_0.b, v_p.b, u_0.a, u_0.b, u_0.p1);
-                        const double T_b_jm1 =
-                            calc_TFLX(v_m.a, v_0.a, v_m.b, v_0.b, u_m.a, u_m.b, u_m.p1);
-                        const double T_p1_jm1 =
-                            calc_TFLX(v_m.b, v_0.b, v_m.p1, v_0.p1, u_m.b, u_m.p1, u_m.p2);
+                        double R_a, R_b, R_a_jm1, R_b_jm1, Q_a, Q_b, Q_p1, S_a_jm1, S_b_jm1, S_b,
+                            S_p1, T_a, T_b, T_b_jm1, T_p1_jm1;
+                        if (DC_FAST) {
+                            const double h12 = 1. / 24., h24 = 1. / 48.;
+                            const double vvm_m1 = v_m.m1 + v_0.m1, vvm_a = v_m.a + v_0.a,
+                                         vvm_b = v_m.b + v_0.b, vvm_p1 = v_m.p1 + v_0.p1;
+                            const double vv0_m1 = v_0.m1 + v_p.m1, vv0_a = v_0.a + v_p.a,
+                                         vv0_b = v_0.b + v_p.b, vv0_p1 = v_0.p1 + v_p.p1;
+                            R_a = h12 * (vv0_m1 + 2. * vv0_a + vv0_b);
+                            R_b = h12 * (vv0_a + 2. * vv0_b + vv0_p1);
+                            R_a_jm1 = h12 * (vvm_m1 + 2. * vvm_a + vvm_b);
+                            R_b_jm1 = h12 * (vvm_a + 2. * vvm_b + vvm_p1);
+                            const double uv_m1 = u_m.m1 + u_0.m1, uv_a = u_m.a + u_0.a,
+                                         uv_b = u_m.b + u_0.b, uv_p1 = u_m.p1 + u_0.p1,
+                                         uv_p2 = u_m.p2 + u_0.p2;
+                            Q_a = h12 * (uv_m1 + 2. * uv_a + uv_b);
+                            Q_b = h12 * (uv_a + 2. * uv_b + uv_p1);
+                            Q_p1 = h12 * (uv_b + 2. * uv_p1 + uv_p2);
+                            const double uu0_a = u_0.m1 + 2. * u_0.a + u_0.b,
+                                         uu0_b = u_0.a + 2. * u_0.b + u_0.p1,
+                                         uu0_p1 = u_0.b + 2. * u_0.p1 + u_0.p2;
+                            const double uum_a = u_m.m1 + 2. * u_m.a + u_m.b,
+                                         uum_b = u_m.a + 2. * u_m.b + u_m.p1,
+                                         uum_p1 = u_m.b + 2. * u_m.p1 + u_m.p2;
+                            const double wm_a = vvm_m1 + vvm_a, wm_b = vvm_a + vvm_b,
+                                         wm_p1 = vvm_b + vvm_p1;
+                            const double w0_a = vv0_m1 + vv0_a, w0_b = vv0_a + vv0_b,
+                                         w0_p1 = vv0_b + vv0_p1;
+                            S_a_jm1 = h24 * (wm_a + uum_a);
+                            S_b_jm1 = h24 * (wm_b + uum_b);
+                            S_b = h24 * (w0_b + uu0_b);
+                            S_p1 = h24 * (w0_p1 + uu0_p1);
+                            T_a = h24 * (w0_a - uu0_a);
+                            T_b = h24 * (w0_b - uu0_b);
+                            T_b_jm1 = h24 * (wm_b - uum_b);
+                            T_p1_jm1 = h24 * (wm_p1 - uum_p1);
+                        } else {
+                            R_a = calc_RFLX(v_0.m1, v_p.m1, v_0.a, v_p.a, v_0.b, v_p.b);
+                            R_b = calc_RFLX(v_0.a, v_p.a, v_0.b, v_p.b, v_0.p1, v_p.p1);
+                            R_a_jm1 = calc_RFLX(v_m.m1, v_0.m1, v_m.a, v_0.a, v_m.b, v_0.b);
+                            R_b_jm1 = calc_RFLX(v_m.a, v_0.a, v_m.b, v_0.b, v_m.p1, v_0.p1);
+                            Q_a = calc_QFLX(u_m.m1, u_0.m1, u_m.a, u_0.a, u_m.b, u_0.b);
+                            Q_b = calc_QFLX(u_m.a, u_0.a, u_m.b, u_0.b, u_m.p1, u_0.p1);
+                            Q_p1 = calc_QFLX(u_m.b, u_0.b, u_m.p1, u_0.p1, u_m.p2, u_0.p2);
+                            S_a_jm1 = calc_SFLX(v_m.m1, v_0.m1, v_m.a, v_0.a, u_m.m1, u_m.a, u_m.b);
+                            S_b_jm1 = calc_SFLX(v_m.a, v_0.a, v_m.b, v_0.b, u_m.a, u_m.b, u_m.p1);
+                            S_b = calc_SFLX(v_0.a, v_p.a, v_0.b, v_p.b, u_0.a, u_0.b, u_0.p1);
+                            S_p1 = calc_SFLX(v_0.b, v_p.b, v_0.p1, v_p.p1, u_0.b, u_0.p1, u_0.p2);
+                            T_a = calc_TFLX(v_0.m1, v_p.m1, v_0.a, v_p.a, u_0.m1, u_0.a, u_0.b);
+                            T_b = calc_TFLX(v_0.a, v_p.a, v_0.b, v_p.b, u_0.a, u_0.b, u_0.p1);
+                            T_b_jm1 = calc_TFLX(v_m.a, v_0.a, v_m.b, v_0.b, u_m.a, u_m.b, u_m.p1);
+                            T_p1_jm1 =
+                                calc_TFLX(v_m.b, v_0.b, v_m.p1, v_0.p1, u_m.b, u_m.p1, u_m.p2);
+                        }
                         double d[2] = {0., 0.};
-                        d[0] = d[0] + UVFLX_hor_adv(V_0.a, V_m.a, V_p.a, V_0.m1, V_0.b, V_m.m1, V_m.b,
+                        d[0] = d[0] + hor_adv_uv(V_0.a, V_m.a, V_p.a, V_0.m1, V_0.b, V_m.m1, V_m.b,
                                                     V_p.m1, V_p.b, R_a, R_a_jm1, Q_a, Q_b, S_a_jm1,
                                                     S_b, T_a, T_b_jm1, -1.);
-                        d[1] = d[1] + UVFLX_hor_adv(V_0.b, V_m.b, V_p.b, V_0.a, V_0.p1, V_m.a, V_m.p1,
+                        d[1] = d[1] + hor_adv_uv(V_0.b, V_m.b, V_p.b, V_0.a, V_0.p1, V_m.a, V_m.p1,
                                                     V_p.a, V_p.p1, R_b, R_b_jm1, Q_b, Q_p1, S_b_jm1,
                                                     S_p1, T_b, T_p1_jm1, -1.);
                         d[0] = d[0] + ((S3_P(wwv_k)[0] - wwv_kp1[0]) / ds_d);

@@ -55,6 +55,20 @@ static void dcb_launch(const Body &b, int i0, int i1, int j0, int j1, void *stre
     dc::k_columns<Body><<<grid, block, 0, (cudaStream_t)stream>>>(b, i0, i1, j0, j1);
 }
 
+namespace dc {
+template <class Body, class Smem>
+__global__ void k_blocks(const Body b)
+{
+    __shared__ Smem s;
+    b.run_block(blockIdx.x, blockIdx.y, s);
+}
+}  // namespace dc
+template <class Body, class Smem>
+static void dcb_launch_blocks(const Body &b, int nbx, int nby, int nthreads, void *stream)
+{
+    dc::k_blocks<Body, Smem><<<dim3(nbx, nby), dim3(nthreads), 0, (cudaStream_t)stream>>>(b);
+}
+
 #include "dc_fused.h"
 namespace dc {
 __global__ void __launch_bounds__(NT, DC_MINBLOCKS) k_stage(const StageBody b)

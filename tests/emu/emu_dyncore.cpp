@@ -27,6 +27,18 @@ static void dcb_launch(const Body &b, int i0, int i1, int j0, int j1, void *)
         for (int i = i1; i >= i0; i--) b(i, j);
 }
 
+template <class Body, class Smem>
+static void dcb_launch_blocks(const Body &b, int nbx, int nby, int, void *)
+{
+    static Smem s;
+    for (int by = nby - 1; by >= 0; by--)
+        for (int bx = nbx - 1; bx >= 0; bx--) {
+            for (size_t n = 0; n < sizeof(s) / sizeof(double); n++)
+                reinterpret_cast<double *>(&s)[n] = 0.0 / 0.0;   // stale smem must not be read
+            b.run_block(bx, by, s);
+        }
+}
+
 #include "../../climate_model_b200/csrc/dc_fused.h"
 static void dcb_launch_stage(const dc::StageBody &b, int nbx, int nby, void *)
 {
