@@ -41,7 +41,7 @@ namespace dc {
 
 // fields the third-generation stage kernel stages by TMA (a descriptor each)
 struct Stage3Ptrs {
-    const double *U, *V, *W, *PHI, *T, *PV, *PB;   // staged boxes; W, PB: nz+1 interfaces
+    const double *U, *V, *W, *PHI, *T, *G;         // staged boxes; W: nz+1 interfaces
     const double *TB, *Uo, *Vo, *To;               // own-column boxes; TB: nz+1 interfaces
 };
 
@@ -89,6 +89,9 @@ static const FieldInfo g_field_info[F_COUNT] = {
     {"PAIRVB", 0, 0, DC_NK_NZS},    {"RHO", 0, 0, DC_NK_NZ},
     {"RHOVB", 0, 0, DC_NK_NZS},     {"WINDX", 0, 0, DC_NK_NZ},
     {"WINDY", 0, 0, DC_NK_NZ},      {"WIND", 0, 0, DC_NK_NZ},
+    // work field of this library (not a reference field): the per-column part of the
+    // pressure-gradient term, written by the primary diagnostics (dc_kernels.h)
+    {"PGCOL", 0, 0, DC_NK_NZ},
 };
 
 }  // namespace dc
@@ -101,6 +104,7 @@ struct dc_handle {
     int profiling;
     void *profile_state;  // backend-owned
     int mode;             // DC_MODE_FUSED (default) or DC_MODE_KERNELS
+    int diag_partial;     // 1: the last diagnostics pass skipped PVTF / PVTFVB / PHIVB
     int cont_impl;        // 2 = single-pass tile kernel (default), 1 = two-sweep column kernel
     int stage_impl;       // fused mode: 3 = dc_stage3.h (default), 2 = dc_fused.h (DC_STAGE_IMPL=2)
     void *tma_state;      // backend-owned descriptor cache
@@ -257,7 +261,9 @@ static int do_primary_diag(dc_handle *h, void *stream)
 {
     const Fields &f = h->f;
     const Geom &g = h->g;
-    PrimaryDiagBody<true> b{g, f.COLP, f.POTT, f.HSURF, f.PVTF, f.PVTFVB, f.PHI, f.PHIVB, f.POTTVB};
+    PrimaryDiagBody<0> b{g,        f.COLP, f.POTT,  f.HSURF,  f.PVTF,
+                         f.PVTFVB, f.PHI,  f.PHIVB, f.POTTVB, f.PGCOL};
+    h->diag_partial = 0;
     const int lo = g.j0 - HJ < 0 ? 0 : g.j0 - HJ, hi = g.j1 + HJ > g.ny + 1 ? g.ny + 1 : g.j1 + HJ;
     launch(h, "primary_diag", b, 0, g.nx + 1, lo, hi, stream);   // every row this rank holds
     return DC_OK;
@@ -315,12 +321,11 @@ static void do_stage_fused(dc_handle *h, int stage, int part, void *stream)
         Stage3Body sb;
         sb.g = g;
         sb.COLP = f.COLP; sb.COLP_NEW = f.COLP_NEW; sb.COLP_OLD = f.COLP_OLD;
-        sb.WWIND = f.WWIND; sb.POTTVB = f.POTTVB; sb.PVTFVB = f.PVTFVB;
+        sb.WWIND = f.WWIND; sb.POTTVB = f.POTTVB;
         sb.UWIND_out = Uo; sb.VWIND_out = Vo; sb.POTT_out = To;
         sb.j_lo = ranges[r].lo; sb.j_hi = ranges[r].hi;
         sb.have_old = stage == 0 ? 0 : 1;   // stage 1 evaluates the step-start state itself
-        const Stage3Ptrs sp{U, V, f.WWIND, f.PHI, T, f.PVTF, f.PVTFVB, f.POTTVB,
-                            f.UWIND, f.VWIND, f.POTT};
+        const Stage3Ptrs sp{U, V, f.WWIND, f.PHI, T, f.PGCOL, f.POTTVB, f.UWIND, f.VWIND, f.POTT};
         if (h->profiling) dcb_profile_begin(h, "stage_fused", stream);
         dcb_launch_stage3(h, sb, sp, (g.nx + S3_TX - 1) / S3_TX,
                           (ranges[r].hi - ranges[r].lo + S3_TY) / S3_TY, stream);
@@ -357,10 +362,19 @@ static void do_diag_fused(dc_handle *h, int stage, void *stream)
     const Fields &f = h->f;
     const Geom &g = h->g;
     const int lo = g.j0 - HJ < 0 ? 0 : g.j0 - HJ, hi = g.j1 + HJ > g.ny + 1 ? g.ny + 1 : g.j1 + HJ;
-    // PHIVB is not an input of the dynamical core (only of the turbulence terms): not stored
-    PrimaryDiagBody<false> b{g,      f.COLP, stage == 0 ? f.POTT_OLD : f.POTT, f.HSURF, f.PVTF,
-                             f.PVTFVB, f.PHI, f.PHIVB, f.POTTVB};
-    launch(h, "primary_diag", b, 0, g.nx + 1, lo, hi, stream);
+    // the stage kernel reads PHI, POTTVB and PGCOL only: PVTF, PVTFVB and PHIVB are not
+    // stored between stages (dc_primary_diag refreshes them on demand)
+    const double *T = stage == 0 ? f.POTT_OLD : f.POTT;
+    if (h->stage_impl == 3) {
+        PrimaryDiagBody<1> b{g,        f.COLP, T,       f.HSURF,  f.PVTF,
+                             f.PVTFVB, f.PHI,  f.PHIVB, f.POTTVB, f.PGCOL};
+        launch(h, "primary_diag", b, 0, g.nx + 1, lo, hi, stream);
+        h->diag_partial = 1;
+    } else {
+        PrimaryDiagBody<2> b{g,        f.COLP, T,       f.HSURF,  f.PVTF,
+                             f.PVTFVB, f.PHI,  f.PHIVB, f.POTTVB, f.PGCOL};
+        launch(h, "primary_diag", b, 0, g.nx + 1, lo, hi, stream);
+    }
 }
 
 static const std::vector<int> NEED_CONT = {F_UWIND, F_VWIND, F_COLP, F_COLP_OLD, F_UFLX,
@@ -378,8 +392,8 @@ static const std::vector<int> NEED_STEP_DRY = {
     F_dPOTTdt, F_UWIND, F_VWIND, F_POTT};
 static const std::vector<int> NEED_STEP_MOIST = {F_QV_OLD, F_dQVdt, F_QC_OLD, F_dQCdt,
                                                            F_QV,     F_QC};
-static const std::vector<int> NEED_DIAG = {F_COLP, F_POTT,  F_HSURF, F_PVTF,
-                                                     F_PVTFVB, F_PHI, F_PHIVB, F_POTTVB};
+static const std::vector<int> NEED_DIAG = {F_COLP, F_POTT,  F_HSURF, F_PVTF, F_PVTFVB,
+                                                     F_PHI,  F_PHIVB, F_POTTVB, F_PGCOL};
 
 }  // namespace dc
 
@@ -529,6 +543,7 @@ int dc_create(const dc_grid_desc *d, dc_handle **out)
     h->mode = DC_MODE_FUSED;
     h->profile_state = nullptr;
     h->tma_state = nullptr;
+    h->diag_partial = 0;
     const char *impl = getenv("DC_STAGE_IMPL");
     h->stage_impl = (impl && impl[0] == '2') ? 2 : 3;
     const char *cimpl = getenv("DC_CONT_IMPL");
@@ -643,11 +658,22 @@ int dc_continuity(dc_handle *h, void *stream)
     return backend_status("dc_continuity");
 }
 
+// PVTF / PVTFVB / PHIVB after fused stages: recomputed before the first entry that reads them
+static int refresh_diag(dc_handle *h, const char *what, void *stream)
+{
+    if (!h->diag_partial) return DC_OK;
+    int rc;
+    if ((rc = need(h, what, NEED_DIAG))) return rc;
+    do_primary_diag(h, stream);
+    return DC_OK;
+}
+
 int dc_momentum(dc_handle *h, void *stream)
 {
     DC_ENTRY_CHECK("dc_momentum");
     int rc;
-    if ((rc = need(h, "dc_momentum", NEED_MOM))) return rc;
+    if ((rc = need(h, "dc_momentum", NEED_MOM)) || (rc = refresh_diag(h, "dc_momentum", stream)))
+        return rc;
     do_momentum(h, stream);
     return backend_status("dc_momentum");
 }
@@ -707,6 +733,7 @@ int dc_secondary_diag(dc_handle *h, void *stream)
                    {F_POTTVB, F_PVTFVB, F_POTT, F_PVTF, F_UWIND, F_VWIND, F_TAIRVB, F_PAIRVB,
                     F_RHOVB, F_TAIR, F_PAIR, F_RHO, F_WINDX, F_WINDY, F_WIND})))
         return rc;
+    if ((rc = refresh_diag(h, "dc_secondary_diag", stream))) return rc;
     const Fields &f = h->f;
     SecondaryDiagBody b{h->g,  f.POTTVB, f.PVTFVB, f.POTT, f.PVTF, f.UWIND, f.VWIND, f.TAIRVB,
                         f.PAIRVB, f.RHOVB, f.TAIR, f.PAIR, f.RHO,  f.WINDX, f.WINDY, f.WIND};
@@ -886,6 +913,7 @@ int dc_step_matsuno(dc_handle *h, int nsteps, void *stream)
         }
         return backend_status("dc_step_matsuno");
     }
+    if ((rc = refresh_diag(h, "dc_step_matsuno", stream))) return rc;
     for (int s = 0; s < nsteps; s++) {
         // dyn_matsuno.py:34-49: OLD <- current
         if (h->profiling) dcb_profile_begin(h, "copy_old", stream);

@@ -79,7 +79,8 @@ struct Geom {
     X(WWIND_UWIND) X(WWIND_VWIND)                                                            \
     X(dUFLXdt) X(dVFLXdt) X(dPOTTdt) X(dQVdt) X(dQCdt)                                       \
     X(PHI) X(PHIVB) X(PVTF) X(PVTFVB) X(POTTVB)                                              \
-    X(TAIR) X(TAIRVB) X(PAIR) X(PAIRVB) X(RHO) X(RHOVB) X(WINDX) X(WINDY) X(WIND)
+    X(TAIR) X(TAIRVB) X(PAIR) X(PAIRVB) X(RHO) X(RHOVB) X(WINDX) X(WINDY) X(WIND)         \
+    X(PGCOL)
 
 struct Fields {
 #define X(n) double *n;

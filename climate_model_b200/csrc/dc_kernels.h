@@ -602,11 +602,13 @@ struct MoistEulerBody {
 // POTTVB).  threads: ALL columns i in [0, nx+1], j in [0, ny+1] (halos are computed, not
 // exchanged).  nz+1 pow per column (the reference evaluates 2 per cell).
 // ---------------------------------------------------------------------------------------
-template <bool STORE_PHIVB>
+// MODE 0: every output (the factory entry); 1: what the third-generation stage kernel reads
+// (PHI, POTTVB, PGCOL); 2: what the second-generation stage kernel reads (no PHIVB, no PGCOL)
+template <int MODE>
 struct PrimaryDiagBody {
     Geom g;
     const double *COLP, *POTT, *HSURF;
-    double *PVTF, *PVTFVB, *PHI, *PHIVB, *POTTVB;
+    double *PVTF, *PVTFVB, *PHI, *PHIVB, *POTTVB, *PGCOL;
     // production build: exp(kappa*log(x)) instead of pow(x, kappa).  pow carries its logarithm
     // in extended precision to stay below 1 ulp; here 0 < x < 1.3 and |kappa*log(x)| < 2.5, so
     // the plain composition is within ~5 ulp (5e-16) at a third of the instructions
@@ -618,29 +620,40 @@ struct PrimaryDiagBody {
     // level-local or couples two neighbouring levels, so POTT is read once and nothing the
     // thread wrote is read back.  Same operands and operations as the reference's three
     // kernels (diag_PVTF / diag_PHI / diag_POTTVB).
+    // PGCOL[k] = POTT/dsigma * (sigma_vb[k+1]*(PVTFVB[k+1]-PVTF) + sigma_vb[k]*(PVTF-PVTFVB[k]))
+    // is the per-column sub-expression of the pressure-gradient term (dyn_functions.py:177-207),
+    // formed here once per cell instead of four times per cell in the momentum kernels.
     DC_HD void operator()(int i, int j) const
     {
+        constexpr bool PV = MODE != 1, PHB = MODE == 0, PG = MODE != 2;
         const int nz = g.nz;
         const double colp = COLP[g.idx2(i, j)];
         double p_kp12 = g.pair_top + g.sigma_vb[nz] * colp;
         double pw_kp12 = exner(p_kp12);
-        PVTFVB[g.idx(i, j, nz)] = pw_kp12;
+        if (PV) PVTFVB[g.idx(i, j, nz)] = pw_kp12;
         double phivb = HSURF[g.idx2(i, j)] * con_g;
-        if (STORE_PHIVB) PHIVB[g.idx(i, j, nz)] = phivb;
+        if (PHB) PHIVB[g.idx(i, j, nz)] = phivb;
         double pvtf_kp1 = 0., pott_kp1 = 0.;
         for (int k = nz - 1; k >= 0; k--) {
-            const double p_km12 = g.pair_top + g.sigma_vb[k] * colp;
+            const double svb = g.sigma_vb[k];
+            const double p_km12 = g.pair_top + svb * colp;
             const double pw_km12 = exner(p_km12);
             const double pvtf = 1. / (1. + con_kappa) * (pw_kp12 * p_kp12 - pw_km12 * p_km12) /
                                 (p_kp12 - p_km12);
             const double pott = POTT[g.idx(i, j, k)];
-            PVTF[g.idx(i, j, k)] = pvtf;
-            PVTFVB[g.idx(i, j, k)] = pw_km12;
+            if (PV) {
+                PVTF[g.idx(i, j, k)] = pvtf;
+                PVTFVB[g.idx(i, j, k)] = pw_km12;
+            }
+            if (PG)
+                PGCOL[g.idx(i, j, k)] =
+                    pott / mkdiv(g.dsigma[k], g.r_dsigma[k]) *
+                    (g.sigma_vb[k + 1] * (pw_kp12 - pvtf) + svb * (pvtf - pw_km12));
             // diag_PHI_cpu
             const double phi = phivb - con_cp * (pott * (pvtf - pw_kp12));
             phivb = phi - con_cp * (pott * (pw_km12 - pvtf));
             PHI[g.idx(i, j, k)] = phi;
-            if (STORE_PHIVB) PHIVB[g.idx(i, j, k)] = phivb;
+            if (PHB) PHIVB[g.idx(i, j, k)] = phivb;
             // diag_POTTVB_cpu: interface k+1 between level k (above) and level k+1 (below)
             if (k + 1 <= nz - 1) {
                 const double pottvb =

@@ -16,13 +16,15 @@
 //     thread evaluates the 30 flux values its two cells need from the UFLX / VFLX planes
 //     (15 per cell instead of 8 + frame, but the FP64 pipe has room and the kernel loses
 //     eight planes, one phase and one block barrier per level);
-//   * the pressure-gradient term reads ONE precomputed plane
-//       G = POTT/dsigma * (sigma_vb[k+1]*(PVTFVB[k+1]-PVTF) + sigma_vb[k]*(PVTF-PVTFVB[k]))
-//     (the reference's per-column sub-expression, dyn_functions.py:177-207) instead of POTT,
-//     PVTF and two PVTFVB planes.
+//   * the pressure-gradient term reads ONE plane, PGCOL
+//       = POTT/dsigma * (sigma_vb[k+1]*(PVTFVB[k+1]-PVTF) + sigma_vb[k]*(PVTF-PVTFVB[k]))
+//     (the reference's per-column sub-expression, dyn_functions.py:177-207), which the
+//     diagnostics kernel writes instead of PVTF and PVTFVB;
+//   * UFLX, VFLX and COLP_NEW*A*WWIND are formed in registers from the raw planes and three
+//     coefficient planes built once per block: no derived planes, no second phase, ONE block
+//     barrier per level (the ring-slot release).
 //
-// Per level: TMA wait -> phase A (UFLX, VFLX, COLP_NEW*A*WWIND, G of the staged region) ->
-// barrier -> phase C (everything else, in registers) -> barrier.  Every expression keeps the
+// Per level: TMA wait -> everything in registers -> barrier.  Every expression keeps the
 // reference's evaluation order, so the strict build stays bit-identical to the
 // one-kernel-per-reference-kernel mode.  The periodic longitude images are read from the x
 // halo cells of the inputs (valid by construction: every producer stores its boundary
@@ -97,13 +99,15 @@ DC_HD R6 ld6(const double *p)
 struct alignas(128) Stage3Smem {
     // TMA destinations (128-byte aligned): raw planes of a level, 3-deep ring
     double rU[S3_NBUF][S3_PL], rV[S3_NBUF][S3_PL], rW[S3_NBUF][S3_PL], rPHI[S3_NBUF][S3_PL],
-        rT[S3_NBUF][S3_PL], rPV[S3_NBUF][S3_PL], rPB[S3_NBUF][S3_PL];
+        rT[S3_NBUF][S3_PL], rG[S3_NBUF][S3_PL];
     // own-column boxes: POTTVB[k+1] and the step-start U, V, POTT of level k
     double oTB[S3_NBUF][S3_OWN], oUo[S3_NBUF][S3_OWN], oVo[S3_NBUF][S3_OWN], oTo[S3_NBUF][S3_OWN];
-    // derived planes of the current level
-    double UF[S3_PL], VF[S3_PL], P[S3_PL], G[S3_PL];
+    // flux coefficients of the staged cells (level independent):
+    //   CU = (COLP[i-1,j] + COLP[i,j]) / 2, CV = (COLP[i,j-1] + COLP[i,j]) / 2, CP = COLP_NEW*A
+    double CU[S3_PL], CV[S3_PL], CP[S3_PL];
     double lev[6][NZMAX + 1];   // as StageSmem::lev
     double row[7][S3_TY + 1];   // as StageSmem::row
+    double dxr[S3_SH + 1];      // dxjs of the staged rows rj = -1 .. TY+1
     unsigned long long full[S3_NBUF];   // mbarriers: "level has landed"
 };
 
@@ -247,10 +251,10 @@ DC_HD double hor_adv_uv(double DWIND, double DWIND_dm1, double DWIND_dp1, double
 
 struct Stage3Body {
     Geom g;
-    TmaMap mU, mV, mW, mPHI, mT, mPV, mPB;   // boxes S3_SW x S3_SH x 1
+    TmaMap mU, mV, mW, mPHI, mT, mG;         // boxes S3_SW x S3_SH x 1
     TmaMap mTB, mUo, mVo, mTo;               // boxes S3_OW x S3_TY x 1
     const double *COLP, *COLP_NEW, *COLP_OLD;
-    const double *WWIND, *POTTVB, *PVTFVB;   // set-up reads of interface 0
+    const double *WWIND, *POTTVB;            // set-up reads of interface 0
     double *UWIND_out, *VWIND_out, *POTT_out;
     int j_lo, j_hi;   // global mass rows to advance
     int have_old;     // 0: the step-start state is the state the tendencies are evaluated at
@@ -275,15 +279,14 @@ struct Stage3Body {
         const int bp = kp % S3_NBUF;
         unsigned long long *bar = &s.full[bp];
         const unsigned bytes =
-            7u * S3_SN * 8u + (have_old ? 4u : 1u) * (unsigned)S3_OWN * 8u;
+            6u * S3_SN * 8u + (have_old ? 4u : 1u) * (unsigned)S3_OWN * 8u;
         s3_mbar_expect(bar, bytes);
         s3_tma_load(s.rU[bp], &mU, x0, y0, kp, bar);
         s3_tma_load(s.rV[bp], &mV, x0, y0, kp, bar);
         s3_tma_load(s.rW[bp], &mW, x0, y0, kp + 1, bar);
         s3_tma_load(s.rPHI[bp], &mPHI, x0, y0, kp, bar);
         s3_tma_load(s.rT[bp], &mT, x0, y0, kp, bar);
-        s3_tma_load(s.rPV[bp], &mPV, x0, y0, kp, bar);
-        s3_tma_load(s.rPB[bp], &mPB, x0, y0, kp + 1, bar);
+        s3_tma_load(s.rG[bp], &mG, x0, y0, kp, bar);
         s3_tma_load(s.oTB[bp], &mTB, x0, y0 + 1, kp + 1, bar);
         if (have_old) {
             s3_tma_load(s.oUo[bp], &mUo, x0, y0 + 1, kp, bar);
@@ -307,13 +310,7 @@ struct Stage3Body {
         const int j_max_y = (g.j1 + HJ + 1 > ny + 2) ? ny + 2 : g.j1 + HJ + 1;  // y-staggered
 
         // ---- thread-private state --------------------------------------------------------
-        // phase A: coefficients of this thread's staged pairs
-        S3_PRIVNN(double, cu, S3_NQ, 2);    // (COLP[i-1,j] + COLP[i,j]) / 2
-        S3_PRIVNN(double, cv, S3_NQ, 2);    // (COLP[i,j-1] + COLP[i,j]) / 2
-        S3_PRIVNN(double, cp, S3_NQ, 2);    // COLP_NEW[i,j] * A[j]
-        S3_PRIVNN(double, pbp, S3_NQ, 2);   // PVTFVB of interface k (carried)
-        S3_PRIVN(double, dxv, S3_NQ);       // dxjs[j]
-        // phase C: the two own columns a = (ia, j), b = (ia + 1, j)
+        // the two own columns a = (ia, j), b = (ia + 1, j)
         S3_PRIV(int, off0);                 // plane offset of cell a
         S3_PRIV(int, flags);                // bit 0/1: a/b is advanced; bit 2/3: a/b has images
         S3_PRIV(double, c_m1);              // COLP at ia-1, ia, ia+1, ia+2 of row j
@@ -352,31 +349,31 @@ struct Stage3Body {
                 issue(s, 0, x0, y0);
                 if (nz > 1) issue(s, 1, x0, y0);
             }
-            // 1) coefficients of the staged pairs: pair p holds staged words 2p, 2p+1
-            for (int q = 0; q < S3_NQ; q++) {
-                const int p = tid + q * S3_NT;
-                const int r = (2 * p) / S3_SW, cw = (2 * p) % S3_SW;
-                int j = J0 + r - 1;
+            // 1) coefficient planes of the staged region
+            for (int n = tid; n < S3_PL; n += S3_NT) {
+                const int r = n / S3_SW, cw = n % S3_SW;
+                int i = I0 + cw - 1, j = J0 + r - 1;
+                if (i > nx + 2) i = nx + 2;   // columns beyond the domain: masked cells only
                 if (j < j_min) j = j_min;
                 const int jm = j > j_max_m ? j_max_m : j;   // row in a mass / x-staggered field
                 const int jy = j > j_max_y ? j_max_y : j;   // row in a y-staggered field
                 const int jc = jy > j_max_m ? j_max_m : jy;
                 const int jcm = (jy - 1 < j_min) ? j_min : (jy - 1 > j_max_m ? j_max_m : jy - 1);
-                for (int e = 0; e < 2; e++) {
-                    int i = I0 + cw - 1 + e;
-                    if (i > nx + 2) i = nx + 2;   // columns beyond the domain: masked cells only
-                    // the periodic images are formed from the interior columns [1, nx], as
-                    // exchange_BC does (misc_boundaries.py:26-32)
-                    const int iw = wrap_i(i), iwm = wrap_i(i - 1);
-                    // UFLX = (C[i-1] + C[i])/2 * U * dyis     (dyn_continuity.py:40-41)
-                    S3_P(cu)[q][e] = (COLP[g.idx2(iwm, jm)] + COLP[g.idx2(iw, jm)]) / 2.;
-                    // VFLX = (C[j-1] + C[j])/2 * V * dxjs     (dyn_continuity.py:43-44)
-                    S3_P(cv)[q][e] = (COLP[g.idx2(iw, jcm)] + COLP[g.idx2(iw, jc)]) / 2.;
-                    // COLP_NEW * A * WWIND                    (dyn_functions.py:254-260)
-                    S3_P(cp)[q][e] = COLP_NEW[g.idx2(iw, jm)] * g.A[g.row(jm)];
-                    S3_P(pbp)[q][e] = PVTFVB[g.idx2(iw, jm)];
-                }
-                S3_P(dxv)[q] = g.dxjs[g.row(jy)];
+                // the periodic images are formed from the interior columns [1, nx], as
+                // exchange_BC does (misc_boundaries.py:26-32)
+                const int iw = wrap_i(i), iwm = wrap_i(i - 1);
+                // UFLX = (C[i-1] + C[i])/2 * U * dyis     (dyn_continuity.py:40-41)
+                s.CU[n] = (COLP[g.idx2(iwm, jm)] + COLP[g.idx2(iw, jm)]) / 2.;
+                // VFLX = (C[j-1] + C[j])/2 * V * dxjs     (dyn_continuity.py:43-44)
+                s.CV[n] = (COLP[g.idx2(iw, jcm)] + COLP[g.idx2(iw, jc)]) / 2.;
+                // COLP_NEW * A * WWIND                    (dyn_functions.py:254-260)
+                s.CP[n] = COLP_NEW[g.idx2(iw, jm)] * g.A[g.row(jm)];
+            }
+            if (tid <= S3_SH) {
+                int j = J0 - 1 + tid;
+                if (j < j_min) j = j_min;
+                if (j > j_max_y) j = j_max_y;
+                s.dxr[tid] = g.dxjs[g.row(j)];
             }
             // 2) constants of the two own columns
             {
@@ -461,35 +458,13 @@ struct Stage3Body {
             const int b = k % S3_NBUF, b1 = (k + 1) % S3_NBUF;
             const size_t ko = (size_t)k * plane;
             const bool last = (k + 1 == nz);
-            // ---- A: UFLX, VFLX, COLP_NEW*A*WWIND(k+1) and G of the staged region ------------
+            // ---- ring: issue level k+2, make sure level k+1 (own U, V of the interface
+            //      interpolation) has landed; level k was awaited one iteration ago ---------
             S3_PHASE
                 // level k+2 -> the slot level k-1 has released (trailing barrier of level k-1)
                 if (tid == 0 && k + 2 < nz) issue(s, k + 2, x0, y0);
-                const double ds = s.lev[0][k];
-                const Div ds_d = mkdiv(ds, s.lev[1][k]);
-                const double svb = s.lev[2][k], svb1 = s.lev[2][k + 1];
-                for (int q = 0; q < S3_NQ; q++) {
-                    const int p = tid + q * S3_NT;
-                    if (p < S3_NP) {
-                        const int idx = 2 * p;
-                        const D2 U = ld2(&s.rU[b][idx]), V = ld2(&s.rV[b][idx]),
-                                 W = ld2(&s.rW[b][idx]), T = ld2(&s.rT[b][idx]),
-                                 PV = ld2(&s.rPV[b][idx]), PB = ld2(&s.rPB[b][idx]);
-                        st2(&s.UF[idx], S3_P(cu)[q][0] * U.x * dyis,               // calc_UFLX
-                            S3_P(cu)[q][1] * U.y * dyis);
-                        st2(&s.VF[idx], S3_P(cv)[q][0] * V.x * S3_P(dxv)[q],       // calc_VFLX
-                            S3_P(cv)[q][1] * V.y * S3_P(dxv)[q]);
-                        st2(&s.P[idx], S3_P(cp)[q][0] * W.x, S3_P(cp)[q][1] * W.y);
-                        st2(&s.G[idx],
-                            T.x / ds_d * (svb1 * (PB.x - PV.x) + svb * (PV.x - S3_P(pbp)[q][0])),
-                            T.y / ds_d * (svb1 * (PB.y - PV.y) + svb * (PV.y - S3_P(pbp)[q][1])));
-                        S3_P(pbp)[q][0] = PB.x;
-                        S3_P(pbp)[q][1] = PB.y;
-                    }
-                }
-                // phase C reads the own U, V of level k+1 from the next ring slot
                 if (!last) s3_mbar_wait(&s.full[b1], ((k + 1) / S3_NBUF) & 1);
-            S3_PHASE_END
+            S3_PHASE_END_NOSYNC
             // ---- C: fluxes, tendencies, Euler step, stores ------------------------------
             S3_PHASE
                 const int tx = tid % S3_NTX, ty = tid / S3_NTX;
@@ -498,27 +473,59 @@ struct Stage3Body {
                 const int o0 = ty * S3_OW + 2 * tx + 1;     // own-box word of cell a
                 const double ds = s.lev[0][k];
                 const Div ds_d = mkdiv(ds, s.lev[1][k]);
-                const double w_kp1[2] = {s.rW[b][b0 + 1], s.rW[b][b0 + 2]};
                 const double pottvb_kp1[2] = {s.oTB[b][o0], s.oTB[b][o0 + 1]};
+                const R4 W_0 = ld4(&s.rW[b][b0]);
+                const double w_kp1[2] = {W_0.a, W_0.b};
                 const int fl = S3_P(flags);
                 if (!EDGE || (fl & 3)) {
                     const bool wall_s = EDGE && (j == 1), wall_n = EDGE && (j == ny);
-                    // UFLX / VFLX neighbourhoods of the pair
-                    const R6 u_m = ld6(&s.UF[b0 - S3_SW]), u_0 = ld6(&s.UF[b0]);
-                    const R4 u_p = ld4(&s.UF[b0 + S3_SW]);
-                    const R4 v_m = ld4(&s.VF[b0 - S3_SW]), v_0 = ld4(&s.VF[b0]),
-                             v_p = ld4(&s.VF[b0 + S3_SW]), v_pp = ld4(&s.VF[b0 + 2 * S3_SW]);
-                    const R4 U_m = ld4(&s.rU[b][b0 - S3_SW]), U_0 = ld4(&s.rU[b][b0]),
-                             U_p = ld4(&s.rU[b][b0 + S3_SW]);
+                    // raw winds around the pair and, from them, UFLX / VFLX
+                    // (calc_UFLX, calc_VFLX: dyn_continuity.py:40-47)
+                    const R6 U_m = ld6(&s.rU[b][b0 - S3_SW]), U_0 = ld6(&s.rU[b][b0]);
+                    const R4 U_p = ld4(&s.rU[b][b0 + S3_SW]);
                     const R4 V_m = ld4(&s.rV[b][b0 - S3_SW]), V_0 = ld4(&s.rV[b][b0]),
-                             V_p = ld4(&s.rV[b][b0 + S3_SW]);
+                             V_p = ld4(&s.rV[b][b0 + S3_SW]), V_pp = ld4(&s.rV[b][b0 + 2 * S3_SW]);
+                    R6 u_m, u_0;
+                    R4 u_p, v_m, v_0, v_p, v_pp;
+                    {
+                        const R6 c_m = ld6(&s.CU[b0 - S3_SW]), c_0 = ld6(&s.CU[b0]);
+                        const R4 c_p = ld4(&s.CU[b0 + S3_SW]);
+                        u_m = R6{c_m.m1 * U_m.m1 * dyis, c_m.a * U_m.a * dyis, c_m.b * U_m.b * dyis,
+                                 c_m.p1 * U_m.p1 * dyis, c_m.p2 * U_m.p2 * dyis, 0.};
+                        u_0 = R6{c_0.m1 * U_0.m1 * dyis, c_0.a * U_0.a * dyis, c_0.b * U_0.b * dyis,
+                                 c_0.p1 * U_0.p1 * dyis, c_0.p2 * U_0.p2 * dyis, 0.};
+                        u_p = R4{c_p.m1 * U_p.m1 * dyis, c_p.a * U_p.a * dyis, c_p.b * U_p.b * dyis,
+                                 c_p.p1 * U_p.p1 * dyis};
+                    }
+                    {
+                        const R4 c_m = ld4(&s.CV[b0 - S3_SW]), c_0 = ld4(&s.CV[b0]),
+                                 c_p = ld4(&s.CV[b0 + S3_SW]), c_pp = ld4(&s.CV[b0 + 2 * S3_SW]);
+                        const double dx_m = s.dxr[ty], dx_0 = s.dxr[ty + 1], dx_p = s.dxr[ty + 2],
+                                     dx_pp = s.dxr[ty + 3];
+                        v_m = R4{c_m.m1 * V_m.m1 * dx_m, c_m.a * V_m.a * dx_m, c_m.b * V_m.b * dx_m,
+                                 c_m.p1 * V_m.p1 * dx_m};
+                        v_0 = R4{c_0.m1 * V_0.m1 * dx_0, c_0.a * V_0.a * dx_0, c_0.b * V_0.b * dx_0,
+                                 c_0.p1 * V_0.p1 * dx_0};
+                        v_p = R4{c_p.m1 * V_p.m1 * dx_p, c_p.a * V_p.a * dx_p, c_p.b * V_p.b * dx_p,
+                                 c_p.p1 * V_p.p1 * dx_p};
+                        v_pp = R4{c_pp.m1 * V_pp.m1 * dx_pp, c_pp.a * V_pp.a * dx_pp,
+                                  c_pp.b * V_pp.b * dx_pp, 0.};
+                    }
                     const double u[2] = {U_0.a, U_0.b}, v[2] = {V_0.a, V_0.b};
                     // vertical momentum fluxes through interface k+1
                     // (dyn_functions.py:211-270; 0 at the model bottom)
                     double wwu_kp1[2] = {0., 0.}, wwv_kp1[2] = {0., 0.};
                     if (!last) {
-                        const R4 P_m = ld4(&s.P[b0 - S3_SW]), P_0 = ld4(&s.P[b0]),
-                                 P_p = ld4(&s.P[b0 + S3_SW]);
+                        // COLP_NEW * A * WWIND(k+1) around the pair
+                        R4 P_m, P_0, P_p;
+                        {
+                            const R4 W_m = ld4(&s.rW[b][b0 - S3_SW]), W_p = ld4(&s.rW[b][b0 + S3_SW]);
+                            const R4 c_m = ld4(&s.CP[b0 - S3_SW]), c_0 = ld4(&s.CP[b0]),
+                                     c_p = ld4(&s.CP[b0 + S3_SW]);
+                            P_m = R4{c_m.m1 * W_m.m1, c_m.a * W_m.a, c_m.b * W_m.b, c_m.p1 * W_m.p1};
+                            P_0 = R4{c_0.m1 * W_0.m1, c_0.a * W_0.a, c_0.b * W_0.b, c_0.p1 * W_0.p1};
+                            P_p = R4{c_p.m1 * W_p.m1, c_p.a * W_p.a, c_p.b * W_p.b, 0.};
+                        }
                         const double ds_kp1 = s.lev[0][k + 1];
                         const Div dss_d = mkdiv(ds_kp1 + ds, s.lev[5][k + 1]);
                         const int wall = wall_s ? -1 : (wall_n ? 1 : 0);
@@ -533,7 +540,7 @@ struct Stage3Body {
                         wwv_kp1[1] = colpa_wwind(P_0.b, P_m.b, P_0.a, P_0.p1, P_m.a, P_m.p1, 0) *
                                      interp_ks(v1[1], v[1], ds_kp1, ds, dss_d);
                     }
-                    const R4 PHI_0 = ld4(&s.rPHI[b][b0]), G_0 = ld4(&s.G[b0]);
+                    const R4 PHI_0 = ld4(&s.rPHI[b][b0]), G_0 = ld4(&s.rG[b][b0]);
                     const double coef_uv = s.lev[3][k];
                     // step-start values of the own cells
                     double uo[2] = {u[0], u[1]}, vo[2] = {v[0], v[1]};
@@ -717,9 +724,9 @@ struct Stage3Body {
                                                      U_m.p1, fcos, sinl, fcos_jm1, sinl_jm1, scale);
                         const double dxjs = s.row[4][ty + 1];
                         d[0] = d[0] + pre_grad_g(PHI_0.a, s.rPHI[b][b0 - S3_SW + 1], S3_P(csy)[0],
-                                                 S3_P(cdy)[0], G_0.a, s.G[b0 - S3_SW + 1], dxjs);
+                                                 S3_P(cdy)[0], G_0.a, s.rG[b][b0 - S3_SW + 1], dxjs);
                         d[1] = d[1] + pre_grad_g(PHI_0.b, s.rPHI[b][b0 - S3_SW + 2], S3_P(csy)[1],
-                                                 S3_P(cdy)[1], G_0.b, s.G[b0 - S3_SW + 2], dxjs);
+                                                 S3_P(cdy)[1], G_0.b, s.rG[b][b0 - S3_SW + 2], dxjs);
                         if (coef_uv > 0.) {
                             d[0] = d[0] + num_dif(v_0.a, v_0.m1, v_0.b, v_m.a, v_p.a, coef_uv);
                             d[1] = d[1] + num_dif(v_0.b, v_0.a, v_0.p1, v_m.b, v_p.b, coef_uv);

@@ -311,8 +311,8 @@ static void dcb_launch_stage3(dc_handle *h, dc::Stage3Body &b, const dc::Stage3P
     const int nz = h->g.nz;
     struct { CUtensorMap *dst; const double *base; int nk; bool own; } want[] = {
         {&b.mU, p.U, nz, false},     {&b.mV, p.V, nz, false},   {&b.mW, p.W, nz + 1, false},
-        {&b.mPHI, p.PHI, nz, false}, {&b.mT, p.T, nz, false},   {&b.mPV, p.PV, nz, false},
-        {&b.mPB, p.PB, nz + 1, false}, {&b.mTB, p.TB, nz + 1, true}, {&b.mUo, p.Uo, nz, true},
+        {&b.mPHI, p.PHI, nz, false}, {&b.mT, p.T, nz, false},   {&b.mG, p.G, nz, false},
+        {&b.mTB, p.TB, nz + 1, true}, {&b.mUo, p.Uo, nz, true},
         {&b.mVo, p.Vo, nz, true},    {&b.mTo, p.To, nz, true}};
     for (auto &w : want) {
         const CUtensorMap *m = stage3_map(h, w.base, w.nk, w.own);

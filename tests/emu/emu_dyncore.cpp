@@ -86,8 +86,7 @@ static void dcb_launch_stage3(dc_handle *, dc::Stage3Body &b, const dc::Stage3Pt
         m.box[0] = own ? S3_OW : S3_SW; m.box[1] = own ? S3_TY : S3_SH; m.box[2] = 1;
     };
     mk(b.mU, p.U, g.nz, false); mk(b.mV, p.V, g.nz, false); mk(b.mW, p.W, g.nz + 1, false);
-    mk(b.mPHI, p.PHI, g.nz, false); mk(b.mT, p.T, g.nz, false); mk(b.mPV, p.PV, g.nz, false);
-    mk(b.mPB, p.PB, g.nz + 1, false);
+    mk(b.mPHI, p.PHI, g.nz, false); mk(b.mT, p.T, g.nz, false); mk(b.mG, p.G, g.nz, false);
     mk(b.mTB, p.TB, g.nz + 1, true); mk(b.mUo, p.Uo, g.nz, true); mk(b.mVo, p.Vo, g.nz, true);
     mk(b.mTo, p.To, g.nz, true);
     static Stage3Smem s;   // one "block" at a time

@@ -133,8 +133,16 @@ def test_fused_mode_equals_kernel_mode(g10, moist):
                                  **F.get(Diagnostics.fields_primary_diag, target=B200))
         step_matsuno(GR, F, 3)
         F.copy_device_to_host(GR, F.ALL_FIELDS)
-        out[mode] = {n: F.host[n].copy() for n in STATE + ['PHI', 'PVTF', 'WWIND', 'dUFLXdt']}
-    for n in STATE[:4] + (STATE[4:] if moist else []) + ['PHI', 'PVTF', 'WWIND']:
+        out[mode] = {n: F.host[n].copy() for n in STATE + ['PHI', 'POTTVB', 'PGCOL', 'WWIND',
+                                                           'dUFLXdt'] if n in F.host}
+        # the fused stages keep PHI / POTTVB / PGCOL only; the factory entry brings PVTF,
+        # PVTFVB and PHIVB up to date on demand
+        Diagnostics.primary_diag(GR.GRF[B200],
+                                 **F.get(Diagnostics.fields_primary_diag, target=B200))
+        F.copy_device_to_host(GR, F.ALL_FIELDS)
+        out[mode].update({n: F.host[n].copy() for n in ('PVTF', 'PVTFVB', 'PHIVB')})
+    for n in STATE[:4] + (STATE[4:] if moist else []) + ['PHI', 'POTTVB', 'WWIND', 'PVTF',
+                                                         'PVTFVB', 'PHIVB']:
         _eq(out['fused'][n], out['kernels'][n], n)
     # the fused path never materialises the tendencies
     assert np.all(out['fused']['dUFLXdt'] == 0.) and np.any(out['kernels']['dUFLXdt'] != 0.)
