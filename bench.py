@@ -47,8 +47,8 @@ STEP_BYTES = {False: 216, True: 296}
 # algorithmic 3-D field accesses (reads + writes) per cell of each kernel LAUNCH as the step is
 # decomposed today; x 8 B = bytes per cell per launch
 KERNEL_ACCESSES = {
-    'continuity': (5, 5), 'continuity_fused': (3, 5), 'stage_fused': (12.5, 12.5),
-    'primary_diag_fused': (5, 5),
+    'continuity': (3, 5), 'continuity_fused': (3, 5), 'stage_fused': (11.5, 11.5),
+    'primary_diag_fused': (4, 4),
     'moist_euler': (0, 6), 'moist_stage': (0, 9), 'uvflx_prep': (15, 15), 'uflx_tendency': (13, 13),
     'vflx_tendency': (13, 13), 'pott_tendency': (6, 6), 'moist_tendency': (7, 7),
     'euler_forward': (9, 15), 'primary_diag': (6, 6), 'copy_old': (6, 10),

@@ -623,52 +623,83 @@ struct PrimaryDiagBody {
     // PGCOL[k] = POTT/dsigma * (sigma_vb[k+1]*(PVTFVB[k+1]-PVTF) + sigma_vb[k]*(PVTF-PVTFVB[k]))
     // is the per-column sub-expression of the pressure-gradient term (dyn_functions.py:177-207),
     // formed here once per cell instead of four times per cell in the momentum kernels.
-    DC_HD void operator()(int i, int j) const
+    // A thread marches NC columns, (i, j_lo + NC*jj + c), in lockstep.  Measured on B200
+    // (0.25 deg x 64 levels): NC = 2 halves the resident warps (86 registers) and is 40 %
+    // SLOWER than NC = 1 -- the sweep is bound by the latency of its exp/log/division chains,
+    // not by instruction issue -- so NC stays 1.
+    static constexpr int NC = 1;
+    int j_lo, j_hi;
+    DC_HD void operator()(int i, int jj) const
     {
         constexpr bool PV = MODE != 1, PHB = MODE == 0, PG = MODE != 2;
         const int nz = g.nz;
-        const double colp = COLP[g.idx2(i, j)];
-        double p_kp12 = g.pair_top + g.sigma_vb[nz] * colp;
-        double pw_kp12 = exner(p_kp12);
-        if (PV) PVTFVB[g.idx(i, j, nz)] = pw_kp12;
-        double phivb = HSURF[g.idx2(i, j)] * con_g;
-        if (PHB) PHIVB[g.idx(i, j, nz)] = phivb;
-        double pvtf_kp1 = 0., pott_kp1 = 0.;
+        const size_t plane = g.plane;
+        const int j0 = j_lo + NC * jj;
+        const int nc = (j0 + NC - 1 <= j_hi) ? NC : j_hi - j0 + 1;   // ragged last thread row
+        double colp[NC], p_kp12[NC], pw_kp12[NC], phivb[NC], pvtf_kp1[NC], pott_kp1[NC];
+        size_t o[NC];   // one running offset per column serves every field
+        for (int c = 0; c < NC; c++) {
+            const int j = c < nc ? j0 + c : j0;   // a masked second column shadows the first
+            colp[c] = COLP[g.idx2(i, j)];
+            p_kp12[c] = g.pair_top + g.sigma_vb[nz] * colp[c];
+            pw_kp12[c] = exner(p_kp12[c]);
+            o[c] = g.idx(i, j, nz);
+            phivb[c] = HSURF[g.idx2(i, j)] * con_g;
+            pvtf_kp1[c] = 0.;
+            pott_kp1[c] = 0.;
+            if (c < nc) {
+                if (PV) PVTFVB[o[c]] = pw_kp12[c];
+                if (PHB) PHIVB[o[c]] = phivb[c];
+            }
+        }
+        double svb_kp1 = g.sigma_vb[nz];
+        // POTT of the next level is requested one iteration ahead: its latency hides behind the
+        // exp / log / division chain of the current level (ncu: 60 % of the stalls were this load)
+        double pott_next[NC];
+        for (int c = 0; c < NC; c++) pott_next[c] = POTT[o[c] - plane];
         for (int k = nz - 1; k >= 0; k--) {
             const double svb = g.sigma_vb[k];
-            const double p_km12 = g.pair_top + svb * colp;
-            const double pw_km12 = exner(p_km12);
-            const double pvtf = 1. / (1. + con_kappa) * (pw_kp12 * p_kp12 - pw_km12 * p_km12) /
-                                (p_kp12 - p_km12);
-            const double pott = POTT[g.idx(i, j, k)];
-            if (PV) {
-                PVTF[g.idx(i, j, k)] = pvtf;
-                PVTFVB[g.idx(i, j, k)] = pw_km12;
+            const Div ds = mkdiv(g.dsigma[k], g.r_dsigma[k]);
+            for (int c = 0; c < NC; c++) {
+                o[c] -= plane;
+                const double pott = pott_next[c];
+                if (k > 0) pott_next[c] = POTT[o[c] - plane];
+                const double p_km12 = g.pair_top + svb * colp[c];
+                const double pw_km12 = exner(p_km12);
+                const double pvtf = 1. / (1. + con_kappa) *
+                                    (pw_kp12[c] * p_kp12[c] - pw_km12 * p_km12) /
+                                    (p_kp12[c] - p_km12);
+                // diag_PHI_cpu
+                const double phi = phivb[c] - con_cp * (pott * (pvtf - pw_kp12[c]));
+                phivb[c] = phi - con_cp * (pott * (pw_km12 - pvtf));
+                // diag_POTTVB_cpu: interface k+1 between level k (above) and k+1 (below)
+                double pottvb = 0.;
+                if (k + 1 <= nz - 1)
+                    pottvb = (+(pw_kp12[c] - pvtf) * pott + (pvtf_kp1[c] - pw_kp12[c]) * pott_kp1[c]) /
+                             (pvtf_kp1[c] - pvtf);
+                if (c < nc) {
+                    if (PV) {
+                        PVTF[o[c]] = pvtf;
+                        PVTFVB[o[c]] = pw_km12;
+                    }
+                    if (PG)
+                        PGCOL[o[c]] = pott / ds * (svb_kp1 * (pw_kp12[c] - pvtf) + svb * (pvtf - pw_km12));
+                    PHI[o[c]] = phi;
+                    if (PHB) PHIVB[o[c]] = phivb[c];
+                    if (k + 1 <= nz - 1) {
+                        POTTVB[o[c] + plane] = pottvb;
+                        if (k + 1 == nz - 1)  // extrapolate model bottom (dyn_diagnostics.py:188-191)
+                            POTTVB[o[c] + 2 * plane] = pott_kp1[c] - (pottvb - pott_kp1[c]);
+                        if (k == 0)           // extrapolate model top (dyn_diagnostics.py:184-187)
+                            POTTVB[o[c]] = pott - (pottvb - pott);
+                    }
+                }
+                p_kp12[c] = p_km12;
+                pw_kp12[c] = pw_km12;
+                pvtf_kp1[c] = pvtf;
+                pott_kp1[c] = pott;
             }
-            if (PG)
-                PGCOL[g.idx(i, j, k)] =
-                    pott / mkdiv(g.dsigma[k], g.r_dsigma[k]) *
-                    (g.sigma_vb[k + 1] * (pw_kp12 - pvtf) + svb * (pvtf - pw_km12));
-            // diag_PHI_cpu
-            const double phi = phivb - con_cp * (pott * (pvtf - pw_kp12));
-            phivb = phi - con_cp * (pott * (pw_km12 - pvtf));
-            PHI[g.idx(i, j, k)] = phi;
-            if (PHB) PHIVB[g.idx(i, j, k)] = phivb;
-            // diag_POTTVB_cpu: interface k+1 between level k (above) and level k+1 (below)
-            if (k + 1 <= nz - 1) {
-                const double pottvb =
-                    (+(pw_kp12 - pvtf) * pott + (pvtf_kp1 - pw_kp12) * pott_kp1) /
-                    (pvtf_kp1 - pvtf);
-                POTTVB[g.idx(i, j, k + 1)] = pottvb;
-                if (k + 1 == nz - 1)  // extrapolate model bottom (dyn_diagnostics.py:188-191)
-                    POTTVB[g.idx(i, j, nz)] = pott_kp1 - (pottvb - pott_kp1);
-                if (k == 0)           // extrapolate model top (dyn_diagnostics.py:184-187)
-                    POTTVB[g.idx(i, j, 0)] = pott - (pottvb - pott);
-            }
-            p_kp12 = p_km12;
-            pw_kp12 = pw_km12;
-            pvtf_kp1 = pvtf;
-            pott_kp1 = pott;
+            svb_kp1 = svb;
         }
     }
 };
@@ -719,9 +750,15 @@ struct SecondaryDiagBody {
 // from registers.  U and V are read once, WWIND is written once: 3 accesses per cell.
 // Written against a small SPMD layer (CT_*) so that tests/emu runs the same body.
 // ---------------------------------------------------------------------------------------
-constexpr int CT_TX = 32;   // longitudes per block
-constexpr int CT_L = 16;    // levels per warp
-constexpr int CT_MAXW = 32; // nz <= CT_L * CT_MAXW
+#ifndef DC_CT_TX
+#define DC_CT_TX 32
+#endif
+constexpr int CT_TX = DC_CT_TX;   // longitudes per block
+#ifndef DC_CT_L
+#define DC_CT_L 16
+#endif
+constexpr int CT_L = DC_CT_L;     // levels per thread
+constexpr int CT_MAXW = 128 / CT_L;   // nz <= 128
 
 #if defined(__CUDA_ARCH__)
 #define CT_PRIV(type, name) type name
