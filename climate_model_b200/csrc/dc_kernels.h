@@ -804,17 +804,29 @@ struct ContinuityTileBody {
                 const double c_jm1 = COLP[g.idx2(i, j - 1)], c_jp1 = COLP[g.idx2(i, j + 1)];
                 const double dxjs = g.dxjs[g.row(j)], dxjs_jp1 = g.dxjs[g.row(j + 1)];
                 const Div A = mkdiv(g.A[g.row(j)], g.r_A[g.row(j)]);
-                // straight-line code over the CT_L levels (levels beyond nz re-read level nz-1
-                // and are never used): the loads of all levels can be in flight together
+                // All 4*CT_L loads of the thread are issued before the first use (levels beyond
+                // nz re-read level nz-1 and are never used): the kernel is bound by memory
+                // latency, so the bytes in flight per warp are what counts
                 const size_t o_u = g.idx(i, j, 0), o_v1 = g.idx(i, j + 1, 0);
+                double ru[CT_L], ru1[CT_L], rv[CT_L], rv1[CT_L];
 #pragma unroll
                 for (int l = 0; l < CT_L; l++) {
                     const int k = w * CT_L + l;
                     const size_t ko = (size_t)(k < nz ? k : nz - 1) * g.plane;
-                    const double uf = calc_UFLX(UWIND[o_u + ko], c, c_im1, g.dyis);
-                    const double uf_ip1 = calc_UFLX(UWIND[o_u + ko + 1], c_ip1, c, g.dyis);
-                    const double vf = calc_VFLX(VWIND[o_u + ko], c, c_jm1, dxjs);
-                    const double vf_jp1 = calc_VFLX(VWIND[o_v1 + ko], c_jp1, c, dxjs_jp1);
+                    ru[l] = UWIND[o_u + ko];
+                    ru1[l] = UWIND[o_u + ko + 1];
+                    rv[l] = VWIND[o_u + ko];
+                    rv1[l] = VWIND[o_v1 + ko];
+                }
+                // keep the compiler from sinking the loads back into the arithmetic below
+                asm volatile("" ::: "memory");
+#pragma unroll
+                for (int l = 0; l < CT_L; l++) {
+                    const int k = w * CT_L + l;
+                    const double uf = calc_UFLX(ru[l], c, c_im1, g.dyis);
+                    const double uf_ip1 = calc_UFLX(ru1[l], c_ip1, c, g.dyis);
+                    const double vf = calc_VFLX(rv[l], c, c_jm1, dxjs);
+                    const double vf_jp1 = calc_VFLX(rv1[l], c_jp1, c, dxjs_jp1);
                     const double f =
                         calc_FLXDIV(uf, uf_ip1, vf, vf_jp1, g.dsigma[k < nz ? k : nz - 1], A);
                     if ((MODE & 2) && k < nz) {

@@ -363,9 +363,12 @@ struct Stage3Body {
                 // exchange_BC does (misc_boundaries.py:26-32)
                 const int iw = wrap_i(i), iwm = wrap_i(i - 1);
                 // UFLX = (C[i-1] + C[i])/2 * U * dyis     (dyn_continuity.py:40-41)
-                s.CU[n] = (COLP[g.idx2(iwm, jm)] + COLP[g.idx2(iw, jm)]) / 2.;
+                // (production build: dyis / dxjs are folded into the planes, one multiplication
+                // less per flux value in the level loop)
+                s.CU[n] = (COLP[g.idx2(iwm, jm)] + COLP[g.idx2(iw, jm)]) / 2. * (DC_FAST ? dyis : 1.);
                 // VFLX = (C[j-1] + C[j])/2 * V * dxjs     (dyn_continuity.py:43-44)
-                s.CV[n] = (COLP[g.idx2(iw, jcm)] + COLP[g.idx2(iw, jc)]) / 2.;
+                s.CV[n] = (COLP[g.idx2(iw, jcm)] + COLP[g.idx2(iw, jc)]) / 2. *
+                          (DC_FAST ? g.dxjs[g.row(jy)] : 1.);
                 // COLP_NEW * A * WWIND                    (dyn_functions.py:254-260)
                 s.CP[n] = COLP_NEW[g.idx2(iw, jm)] * g.A[g.row(jm)];
             }
@@ -490,26 +493,43 @@ struct Stage3Body {
                     {
                         const R6 c_m = ld6(&s.CU[b0 - S3_SW]), c_0 = ld6(&s.CU[b0]);
                         const R4 c_p = ld4(&s.CU[b0 + S3_SW]);
-                        u_m = R6{c_m.m1 * U_m.m1 * dyis, c_m.a * U_m.a * dyis, c_m.b * U_m.b * dyis,
-                                 c_m.p1 * U_m.p1 * dyis, c_m.p2 * U_m.p2 * dyis, 0.};
-                        u_0 = R6{c_0.m1 * U_0.m1 * dyis, c_0.a * U_0.a * dyis, c_0.b * U_0.b * dyis,
-                                 c_0.p1 * U_0.p1 * dyis, c_0.p2 * U_0.p2 * dyis, 0.};
-                        u_p = R4{c_p.m1 * U_p.m1 * dyis, c_p.a * U_p.a * dyis, c_p.b * U_p.b * dyis,
-                                 c_p.p1 * U_p.p1 * dyis};
+                        if (DC_FAST) {
+                            u_m = R6{c_m.m1 * U_m.m1, c_m.a * U_m.a, c_m.b * U_m.b, c_m.p1 * U_m.p1,
+                                     c_m.p2 * U_m.p2, 0.};
+                            u_0 = R6{c_0.m1 * U_0.m1, c_0.a * U_0.a, c_0.b * U_0.b, c_0.p1 * U_0.p1,
+                                     c_0.p2 * U_0.p2, 0.};
+                            u_p = R4{c_p.m1 * U_p.m1, c_p.a * U_p.a, c_p.b * U_p.b, c_p.p1 * U_p.p1};
+                        } else {
+                            u_m = R6{c_m.m1 * U_m.m1 * dyis, c_m.a * U_m.a * dyis,
+                                     c_m.b * U_m.b * dyis,   c_m.p1 * U_m.p1 * dyis,
+                                     c_m.p2 * U_m.p2 * dyis, 0.};
+                            u_0 = R6{c_0.m1 * U_0.m1 * dyis, c_0.a * U_0.a * dyis,
+                                     c_0.b * U_0.b * dyis,   c_0.p1 * U_0.p1 * dyis,
+                                     c_0.p2 * U_0.p2 * dyis, 0.};
+                            u_p = R4{c_p.m1 * U_p.m1 * dyis, c_p.a * U_p.a * dyis,
+                                     c_p.b * U_p.b * dyis, c_p.p1 * U_p.p1 * dyis};
+                        }
                     }
                     {
                         const R4 c_m = ld4(&s.CV[b0 - S3_SW]), c_0 = ld4(&s.CV[b0]),
                                  c_p = ld4(&s.CV[b0 + S3_SW]), c_pp = ld4(&s.CV[b0 + 2 * S3_SW]);
-                        const double dx_m = s.dxr[ty], dx_0 = s.dxr[ty + 1], dx_p = s.dxr[ty + 2],
-                                     dx_pp = s.dxr[ty + 3];
-                        v_m = R4{c_m.m1 * V_m.m1 * dx_m, c_m.a * V_m.a * dx_m, c_m.b * V_m.b * dx_m,
-                                 c_m.p1 * V_m.p1 * dx_m};
-                        v_0 = R4{c_0.m1 * V_0.m1 * dx_0, c_0.a * V_0.a * dx_0, c_0.b * V_0.b * dx_0,
-                                 c_0.p1 * V_0.p1 * dx_0};
-                        v_p = R4{c_p.m1 * V_p.m1 * dx_p, c_p.a * V_p.a * dx_p, c_p.b * V_p.b * dx_p,
-                                 c_p.p1 * V_p.p1 * dx_p};
-                        v_pp = R4{c_pp.m1 * V_pp.m1 * dx_pp, c_pp.a * V_pp.a * dx_pp,
-                                  c_pp.b * V_pp.b * dx_pp, 0.};
+                        if (DC_FAST) {
+                            v_m = R4{c_m.m1 * V_m.m1, c_m.a * V_m.a, c_m.b * V_m.b, c_m.p1 * V_m.p1};
+                            v_0 = R4{c_0.m1 * V_0.m1, c_0.a * V_0.a, c_0.b * V_0.b, c_0.p1 * V_0.p1};
+                            v_p = R4{c_p.m1 * V_p.m1, c_p.a * V_p.a, c_p.b * V_p.b, c_p.p1 * V_p.p1};
+                            v_pp = R4{c_pp.m1 * V_pp.m1, c_pp.a * V_pp.a, c_pp.b * V_pp.b, 0.};
+                        } else {
+                            const double dx_m = s.dxr[ty], dx_0 = s.dxr[ty + 1],
+                                         dx_p = s.dxr[ty + 2], dx_pp = s.dxr[ty + 3];
+                            v_m = R4{c_m.m1 * V_m.m1 * dx_m, c_m.a * V_m.a * dx_m,
+                                     c_m.b * V_m.b * dx_m, c_m.p1 * V_m.p1 * dx_m};
+                            v_0 = R4{c_0.m1 * V_0.m1 * dx_0, c_0.a * V_0.a * dx_0,
+                                     c_0.b * V_0.b * dx_0, c_0.p1 * V_0.p1 * dx_0};
+                            v_p = R4{c_p.m1 * V_p.m1 * dx_p, c_p.a * V_p.a * dx_p,
+                                     c_p.b * V_p.b * dx_p, c_p.p1 * V_p.p1 * dx_p};
+                            v_pp = R4{c_pp.m1 * V_pp.m1 * dx_pp, c_pp.a * V_pp.a * dx_pp,
+                                      c_pp.b * V_pp.b * dx_pp, 0.};
+                        }
                     }
                     const double u[2] = {U_0.a, U_0.b}, v[2] = {V_0.a, V_0.b};
                     // vertical momentum fluxes through interface k+1

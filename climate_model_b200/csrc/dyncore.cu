@@ -57,7 +57,7 @@ static void dcb_launch(const Body &b, int i0, int i1, int j0, int j1, void *stre
 
 namespace dc {
 template <class Body, class Smem>
-__global__ void k_blocks(const Body b)
+__global__ void __launch_bounds__(256, 2) k_blocks(const Body b)
 {
     __shared__ Smem s;
     b.run_block(blockIdx.x, blockIdx.y, s);
