@@ -263,7 +263,8 @@ static int do_primary_diag(dc_handle *h, void *stream)
     const Geom &g = h->g;
     const int lo = g.j0 - HJ < 0 ? 0 : g.j0 - HJ, hi = g.j1 + HJ > g.ny + 1 ? g.ny + 1 : g.j1 + HJ;
     PrimaryDiagBody<0> b{g,        f.COLP, f.POTT,  f.HSURF,  f.PVTF,  f.PVTFVB,
-                         f.PHI,    f.PHIVB, f.POTTVB, f.PGCOL, lo,      hi};
+                         f.PHI,    f.PHIVB, f.POTTVB, f.PGCOL, lo,      hi,
+                         make_pow_coef(con_kappa)};
     h->diag_partial = 0;
     launch(h, "primary_diag", b, 0, g.nx + 1, 0, (hi - lo) / b.NC, stream);   // every held row
     return DC_OK;
@@ -367,12 +368,14 @@ static void do_diag_fused(dc_handle *h, int stage, void *stream)
     const double *T = stage == 0 ? f.POTT_OLD : f.POTT;
     if (h->stage_impl == 3) {
         PrimaryDiagBody<1> b{g,     f.COLP,  T,        f.HSURF, f.PVTF, f.PVTFVB,
-                             f.PHI, f.PHIVB, f.POTTVB, f.PGCOL, lo,     hi};
+                             f.PHI, f.PHIVB, f.POTTVB, f.PGCOL, lo,     hi,
+                             make_pow_coef(con_kappa)};
         launch(h, "primary_diag", b, 0, g.nx + 1, 0, (hi - lo) / b.NC, stream);
         h->diag_partial = 1;
     } else {
         PrimaryDiagBody<2> b{g,     f.COLP,  T,        f.HSURF, f.PVTF, f.PVTFVB,
-                             f.PHI, f.PHIVB, f.POTTVB, f.PGCOL, lo,     hi};
+                             f.PHI, f.PHIVB, f.POTTVB, f.PGCOL, lo,     hi,
+                             make_pow_coef(con_kappa)};
         launch(h, "primary_diag", b, 0, g.nx + 1, 0, (hi - lo) / b.NC, stream);
     }
 }

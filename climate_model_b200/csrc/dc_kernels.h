@@ -609,12 +609,12 @@ struct PrimaryDiagBody {
     Geom g;
     const double *COLP, *POTT, *HSURF;
     double *PVTF, *PVTFVB, *PHI, *PHIVB, *POTTVB, *PGCOL;
-    // production build: exp(kappa*log(x)) instead of pow(x, kappa).  pow carries its logarithm
-    // in extended precision to stay below 1 ulp; here 0 < x < 1.3 and |kappa*log(x)| < 2.5, so
-    // the plain composition is within ~5 ulp (5e-16) at a third of the instructions
-    DC_HD static double exner(double p)
+    // production build: a / b as a * (correctly rounded reciprocal of b), <= 1 ulp off
+    DC_HD static double fdiv(double a, double b) { return DC_FAST ? a * dc_rcp(b) : a / b; }
+    // production build: pow_kappa (dc_point.h) instead of pow(x, kappa)
+    DC_HD double exner(double p) const
     {
-        return DC_FAST ? exp(con_kappa * log(p * 1e-5)) : pow(p / 100000., con_kappa);
+        return DC_FAST ? pow_kappa(p * 1e-5, pc) : pow(p / 100000., con_kappa);
     }
     // One BOTTOM-UP sweep: the hydrostatic integral needs that direction, everything else is
     // level-local or couples two neighbouring levels, so POTT is read once and nothing the
@@ -629,6 +629,7 @@ struct PrimaryDiagBody {
     // not by instruction issue -- so NC stays 1.
     static constexpr int NC = 1;
     int j_lo, j_hi;
+    PowCoef pc;
     DC_HD void operator()(int i, int jj) const
     {
         constexpr bool PV = MODE != 1, PHB = MODE == 0, PG = MODE != 2;
@@ -666,17 +667,17 @@ struct PrimaryDiagBody {
                 if (k > 0) pott_next[c] = POTT[o[c] - plane];
                 const double p_km12 = g.pair_top + svb * colp[c];
                 const double pw_km12 = exner(p_km12);
-                const double pvtf = 1. / (1. + con_kappa) *
-                                    (pw_kp12[c] * p_kp12[c] - pw_km12 * p_km12) /
-                                    (p_kp12[c] - p_km12);
+                const double pvtf = fdiv(1. / (1. + con_kappa) *
+                                             (pw_kp12[c] * p_kp12[c] - pw_km12 * p_km12),
+                                         p_kp12[c] - p_km12);
                 // diag_PHI_cpu
                 const double phi = phivb[c] - con_cp * (pott * (pvtf - pw_kp12[c]));
                 phivb[c] = phi - con_cp * (pott * (pw_km12 - pvtf));
                 // diag_POTTVB_cpu: interface k+1 between level k (above) and k+1 (below)
                 double pottvb = 0.;
                 if (k + 1 <= nz - 1)
-                    pottvb = (+(pw_kp12[c] - pvtf) * pott + (pvtf_kp1[c] - pw_kp12[c]) * pott_kp1[c]) /
-                             (pvtf_kp1[c] - pvtf);
+                    pottvb = fdiv(+(pw_kp12[c] - pvtf) * pott + (pvtf_kp1[c] - pw_kp12[c]) * pott_kp1[c],
+                                  pvtf_kp1[c] - pvtf);
                 if (c < nc) {
                     if (PV) {
                         PVTF[o[c]] = pvtf;
