@@ -120,7 +120,10 @@ int dc_exchange_bc(dc_handle *h, int field_id, void *stream);
  *   (momentum-flux preparation + U/V/POTT tendencies + Euler step + boundary images) and
  *   one diagnostics kernel.  The *_OLD 3-D fields are used as the second state buffer:
  *   after the call they hold the stage-1 estimate, not the state before the step; the
- *   intermediate fields (UFLX, BFLX.., dUFLXdt..) and PHIVB are not written.
+ *   intermediate fields (UFLX, BFLX.., dUFLXdt..) are not written, and of the diagnostics
+ *   only PHI, POTTVB and the work field PGCOL are kept current between stages: PVTF,
+ *   PVTFVB and PHIVB are refreshed by dc_primary_diag (and implicitly by dc_momentum,
+ *   dc_secondary_diag and kernel-mode stepping) before they are read.
  * DC_MODE_KERNELS: the reference's decomposition, one kernel per reference kernel, every
  *   intermediate field written as the reference does (same result, bit for bit). */
 enum { DC_MODE_FUSED = 0, DC_MODE_KERNELS = 1 };
