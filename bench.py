@@ -40,6 +40,11 @@ WORKLOADS = {
     'cfg4': dict(name='0.25deg x 64 levels, synthetic initial state (no topography), dry dyn core',
                  grid=dict(nz=64, lat0_deg=-84, lat1_deg=84, dlat_deg=0.25, dlon_deg=0.25,
                            i_out_nth_hour=1.0), ic=dict(i_use_topo=0)),
+    # development proxy (not a BASELINE config): two ranks of this grid each hold the 84 rows a
+    # rank of cfg4 holds at N = 8
+    'cfg4_band8x2': dict(name='0.25deg x 64 levels, +-21 deg (2 x 84 rows: per-rank size of cfg4 at N = 8)',
+                         grid=dict(nz=64, lat0_deg=-21, lat1_deg=21, dlat_deg=0.25, dlon_deg=0.25,
+                                   i_out_nth_hour=1.0), ic=dict(i_use_topo=0)),
 }
 
 # algorithmic bytes per cell-update of the WHOLE step (SURVEY.md 8d counting rule)
@@ -52,6 +57,14 @@ KERNEL_ACCESSES = {
     'moist_euler': (0, 6), 'moist_stage': (0, 9), 'uvflx_prep': (15, 15), 'uflx_tendency': (13, 13),
     'vflx_tendency': (13, 13), 'pott_tendency': (6, 6), 'moist_tendency': (7, 7),
     'euler_forward': (9, 15), 'primary_diag': (6, 6), 'copy_old': (6, 10),
+}
+
+
+# DRAM bytes per launch of the dominant kernel (dram__bytes_read.sum + dram__bytes_write.sum of one
+# `ncu --set full` capture, profiles/r1_final_ncu_full_summary.csv): valid for that workload on one
+# GPU only; anything else reports null
+NCU_TRAFFIC = {
+    ('cfg4', 1, False, 'stage_fused'): 0.5 * ((4.050476 + 1.484360) + (5.584172 + 1.481632)) * 1e9,
 }
 
 
@@ -300,7 +313,12 @@ def main():
             bytes_launch = acc * 8 * cells_launch
             ach = bytes_launch / (k_ms * 1e-3) / 1e9
             roof = {'bound': 'hbm', 'kernel': top, 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
-                    'frac': ach / peak, 'traffic': None, 'peak_source': peak_src,
+                    'frac': ach / peak,
+                    'traffic': NCU_TRAFFIC.get((args.workload, world, moist, top))
+                    if args.mode == 'fused' else None,
+                    'traffic_source': 'ncu --set full, profiles/r1_final_ncu_full_summary.csv '
+                                      '(mean of the stage-1 and stage-2 launch)',
+                    'peak_source': peak_src,
                     'algorithmic_bytes_per_launch': bytes_launch, 'avg_launch_ms': k_ms,
                     'share_of_step': kern[top][0] / sum(v[0] for v in kern.values())}
         step_gbs = STEP_BYTES[moist] * value / 1e9

@@ -105,6 +105,7 @@ struct dc_handle {
     void *profile_state;  // backend-owned
     int mode;             // DC_MODE_FUSED (default) or DC_MODE_KERNELS
     int diag_partial;     // 1: the last diagnostics pass skipped PVTF / PVTFVB / PHIVB
+    int stage_kchunks;    // sigma-column chunks of the stage kernel (0 = by launch size)
     int cont_impl;        // 2 = single-pass tile kernel (default), 1 = two-sweep column kernel
     int stage_impl;       // fused mode: 3 = dc_stage3.h (default), 2 = dc_fused.h (DC_STAGE_IMPL=2)
     void *tma_state;      // backend-owned descriptor cache
@@ -318,18 +319,31 @@ static void do_stage_fused(dc_handle *h, int stage, int part, void *stream)
     } else if (part == DC_PART_INTERIOR && can_split) {
         ranges[nr++] = Range{g.j0 + TY, g.j0 + (ntr - 1) * TY - 1};
     }
-    for (int r = 0; r < nr && h->stage_impl == 3; r++) {
+    if (nr && h->stage_impl == 3) {   // both row ranges (if two) in ONE launch
         Stage3Body sb;
         sb.g = g;
         sb.COLP = f.COLP; sb.COLP_NEW = f.COLP_NEW; sb.COLP_OLD = f.COLP_OLD;
         sb.WWIND = f.WWIND; sb.POTTVB = f.POTTVB;
         sb.UWIND_out = Uo; sb.VWIND_out = Vo; sb.POTT_out = To;
-        sb.j_lo = ranges[r].lo; sb.j_hi = ranges[r].hi;
+        sb.j_lo = ranges[0].lo; sb.j_hi = ranges[0].hi;
+        sb.nby0 = (ranges[0].hi - ranges[0].lo + S3_TY) / S3_TY;
+        sb.j_lo2 = nr > 1 ? ranges[1].lo : 0; sb.j_hi2 = nr > 1 ? ranges[1].hi : -1;
+        const int nby1 = nr > 1 ? (ranges[1].hi - ranges[1].lo + S3_TY) / S3_TY : 0;
         sb.have_old = stage == 0 ? 0 : 1;   // stage 1 evaluates the step-start state itself
+        // sigma-column chunks: only when the launch has too few blocks to keep the 2 x 148
+        // block slots of a B200 busy (a latitude band at N = 8); DC_STAGE_KCHUNKS overrides
+        const int nbx3 = (g.nx + S3_TX - 1) / S3_TX, nblocks = nbx3 * (sb.nby0 + nby1);
+        int nkc = h->stage_kchunks;
+        if (nkc <= 0) {
+            nkc = nblocks >= 4 * 296 ? 1 : (nblocks >= 296 ? 2 : 4);
+            while (nkc > 1 && (g.nz + nkc - 1) / nkc < 8) nkc--;   // a warm-up level per chunk
+        }
+        if (nkc > g.nz) nkc = g.nz;
+        while ((nkc - 1) * ((g.nz + nkc - 1) / nkc) >= g.nz) nkc--;   // no empty chunk
+        sb.nkc = nkc;
         const Stage3Ptrs sp{U, V, f.WWIND, f.PHI, T, f.PGCOL, f.POTTVB, f.UWIND, f.VWIND, f.POTT};
         if (h->profiling) dcb_profile_begin(h, "stage_fused", stream);
-        dcb_launch_stage3(h, sb, sp, (g.nx + S3_TX - 1) / S3_TX,
-                          (ranges[r].hi - ranges[r].lo + S3_TY) / S3_TY, stream);
+        dcb_launch_stage3(h, sb, sp, nbx3, sb.nby0 + nby1, stream);
         if (h->profiling) dcb_profile_end(h, stream);
         h->launches++;
     }
@@ -549,6 +563,8 @@ int dc_create(const dc_grid_desc *d, dc_handle **out)
     h->diag_partial = 0;
     const char *impl = getenv("DC_STAGE_IMPL");
     h->stage_impl = (impl && impl[0] == '2') ? 2 : 3;
+    const char *kch = getenv("DC_STAGE_KCHUNKS");
+    h->stage_kchunks = kch ? atoi(kch) : 0;
     const char *cimpl = getenv("DC_CONT_IMPL");
     h->cont_impl = (cimpl && cimpl[0] == '1') ? 1 : 2;
     *out = h;

@@ -256,27 +256,38 @@ struct Stage3Body {
     const double *COLP, *COLP_NEW, *COLP_OLD;
     const double *WWIND, *POTTVB;            // set-up reads of interface 0
     double *UWIND_out, *VWIND_out, *POTT_out;
-    int j_lo, j_hi;   // global mass rows to advance
+    // global mass rows to advance: tile rows [0, nby0) cover j_lo .. j_hi, tile rows from nby0
+    // on cover j_lo2 .. j_hi2 (the two boundary tile rows of a band in ONE launch)
+    int j_lo, j_hi, nby0, j_lo2, j_hi2;
     int have_old;     // 0: the step-start state is the state the tendencies are evaluated at
+    // Small grids (a latitude band at N = 8) do not fill the 2 x 148 block slots for long: the
+    // sigma column is then cut into nkc chunks, one block each (blockIdx.z).  A chunk that does
+    // not start at the model top first runs the level above it with the stores suppressed --
+    // that recreates the vertical momentum flux through its top interface, the only state the
+    // march carries -- so the result is bit-identical to the unchunked march.
+    int nkc;
 
     DC_HD int wrap_i(int i) const { return i < 1 ? i + g.nx : (i > g.nx ? i - g.nx : i); }
 
-    DC_HD void run_block(int bx, int by, Stage3Smem &s) const
+    DC_HD void run_block(int bx, int by, int bz, Stage3Smem &s) const
     {
-        const int I0 = 1 + bx * S3_TX, J0 = j_lo + by * S3_TY;
-        const int j_top = (j_hi < g.ny - 1) ? j_hi : g.ny - 1;
+        const bool second = by >= nby0;
+        const int jl = second ? j_lo2 : j_lo, jh = second ? j_hi2 : j_hi;
+        if (second) by -= nby0;
+        const int I0 = 1 + bx * S3_TX, J0 = jl + by * S3_TY;
+        const int j_top = (jh < g.ny - 1) ? jh : g.ny - 1;
         const bool interior = (I0 >= 3) && (I0 + S3_TX - 1 <= g.nx - 1) && (J0 >= 2) &&
                               (J0 + S3_TY - 1 <= j_top);
         if (interior)
-            run<false>(bx, by, s);
+            run<false>(bx, by, bz, jl, jh, s);
         else
-            run<true>(bx, by, s);
+            run<true>(bx, by, bz, jl, jh, s);
     }
 
-    // issue the TMA copies of level kp into ring slot kp % NBUF (one thread)
-    DC_HD void issue(Stage3Smem &s, int kp, int x0, int y0) const
+    // issue the TMA copies of level kp into ring slot (kp - ks) % NBUF (one thread)
+    DC_HD void issue(Stage3Smem &s, int kp, int ks, int x0, int y0) const
     {
-        const int bp = kp % S3_NBUF;
+        const int bp = (kp - ks) % S3_NBUF;
         unsigned long long *bar = &s.full[bp];
         const unsigned bytes =
             6u * S3_SN * 8u + (have_old ? 4u : 1u) * (unsigned)S3_OWN * 8u;
@@ -296,9 +307,15 @@ struct Stage3Body {
     }
 
     template <bool EDGE>
-    DC_HD void run(int bx, int by, Stage3Smem &s) const
+    DC_HD void run(int bx, int by, int bz, int j_lo, int j_hi, Stage3Smem &s) const
     {
+        (void)j_lo;
         const int nx = g.nx, ny = g.ny, nz = g.nz;
+        // levels of this block: k0 .. k1-1, marched from ks (= k0 - 1 for a warm-up level);
+        // planes are needed up to level ke (the own U, V of level k1 close the last interface)
+        const int kcl = (nz + nkc - 1) / nkc;
+        const int k0 = bz * kcl, k1 = (k0 + kcl < nz) ? k0 + kcl : nz;
+        const int ks = k0 > 0 ? k0 - 1 : 0, ke = k1 < nz ? k1 : nz - 1;
         const int I0 = 1 + bx * S3_TX, J0 = j_lo + by * S3_TY;
         const size_t plane = g.plane;
         const double dyis = g.dyis, dt = g.dt;
@@ -346,8 +363,8 @@ struct Stage3Body {
         S3_PHASE_END
         S3_PHASE
             if (tid == 0) {   // levels 0 and 1 fly while the column constants are gathered
-                issue(s, 0, x0, y0);
-                if (nz > 1) issue(s, 1, x0, y0);
+                issue(s, ks, ks, x0, y0);
+                if (ks + 1 <= ke) issue(s, ks + 1, ks, x0, y0);
             }
             // 1) coefficient planes of the staged region
             for (int n = tid; n < S3_PL; n += S3_NT) {
@@ -429,8 +446,8 @@ struct Stage3Body {
                     S3_P(r_cnew)[e] = DC_FAST ? 1. / S3_P(cnew)[e] : 0.;
                     S3_P(wwu_k)[e] = 0.;   // WWIND_UWIND[0] = 0 (dyn_functions.py:236-237)
                     S3_P(wwv_k)[e] = 0.;
-                    S3_P(w_k)[e] = WWIND[S3_P(off0) + e];
-                    S3_P(pottvb_k)[e] = POTTVB[S3_P(off0) + e];
+                    S3_P(w_k)[e] = WWIND[(size_t)ks * plane + S3_P(off0) + e];
+                    S3_P(pottvb_k)[e] = POTTVB[(size_t)ks * plane + S3_P(off0) + e];
                 }
             }
             // constant tables
@@ -454,19 +471,20 @@ struct Stage3Body {
                 s.row[5][tid] = g.A[r];
                 s.row[6][tid] = g.r_A[r];
             }
-            s3_mbar_wait(&s.full[0], 0);   // level 0 has landed
+            s3_mbar_wait(&s.full[0], 0);   // the first level has landed
         S3_PHASE_END
 
-        for (int k = 0; k < nz; k++) {
-            const int b = k % S3_NBUF, b1 = (k + 1) % S3_NBUF;
+        for (int k = ks; k < k1; k++) {
+            const int b = (k - ks) % S3_NBUF, b1 = (k + 1 - ks) % S3_NBUF;
+            const bool warm = k < k0;   // warm-up level of a chunk: nothing is stored
             const size_t ko = (size_t)k * plane;
             const bool last = (k + 1 == nz);
             // ---- ring: issue level k+2, make sure level k+1 (own U, V of the interface
             //      interpolation) has landed; level k was awaited one iteration ago ---------
             S3_PHASE
                 // level k+2 -> the slot level k-1 has released (trailing barrier of level k-1)
-                if (tid == 0 && k + 2 < nz) issue(s, k + 2, x0, y0);
-                if (!last) s3_mbar_wait(&s.full[b1], ((k + 1) / S3_NBUF) & 1);
+                if (tid == 0 && k + 2 <= ke) issue(s, k + 2, ks, x0, y0);
+                if (!last) s3_mbar_wait(&s.full[b1], ((k + 1 - ks) / S3_NBUF) & 1);
             S3_PHASE_END_NOSYNC
             // ---- C: fluxes, tendencies, Euler step, stores ------------------------------
             S3_PHASE
@@ -659,6 +677,7 @@ struct Stage3Body {
                             const double un = euler_forward_pw(
                                 uo[e], d[e], mkdiv(S3_P(colpa_is)[e], S3_P(r_colpa_is)[e]),
                                 S3_P(colpa_old_is)[e], dt);
+                            if (warm) continue;
                             if (EDGE) {
                                 if (fl & (1 << e)) {
                                     if (fl & (4 << e))
@@ -755,6 +774,7 @@ struct Stage3Body {
                             const double vn = euler_forward_pw(
                                 vo[e], d[e], mkdiv(S3_P(colpa_js)[e], S3_P(r_colpa_js)[e]),
                                 S3_P(colpa_old_js)[e], dt);
+                            if (warm) continue;
                             if (EDGE) {
                                 if (fl & (1 << e)) {
                                     if (fl & (4 << e))
@@ -768,11 +788,12 @@ struct Stage3Body {
                         }
                     } else {
                         for (int e = 0; e < 2; e++)
-                            if (fl & (1 << e)) put_ystag(g, VWIND_out, ia + e, 1, k, 0.);
+                            if (!warm && (fl & (1 << e))) put_ystag(g, VWIND_out, ia + e, 1, k, 0.);
                     }
                     if (wall_n)
                         for (int e = 0; e < 2; e++)
-                            if (fl & (1 << e)) put_ystag(g, VWIND_out, ia + e, ny + 1, k, 0.);
+                            if (!warm && (fl & (1 << e)))
+                                put_ystag(g, VWIND_out, ia + e, ny + 1, k, 0.);
                     // ---------------- dPOTTdt (dyn_POTT.py:55-110) ----------------
                     {
                         const R4 T_0 = ld4(&s.rT[b][b0]);
@@ -804,6 +825,7 @@ struct Stage3Body {
                             const double tn = euler_forward_pw(
                                 to[e], d[e], mkdiv(S3_P(cnew)[e], S3_P(r_cnew)[e]), S3_P(cold)[e],
                                 dt);
+                            if (warm) continue;
                             if (EDGE) {
                                 if (fl & (1 << e)) {
                                     if (fl & (4 << e))

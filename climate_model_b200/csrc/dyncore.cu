@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(S3_NT, 2) k_stage3(const __grid_constant__ Sta
     // the TMA destinations need 128-byte alignment
     const unsigned a = (unsigned)__cvta_generic_to_shared(stage3_smem);
     Stage3Smem &s = *reinterpret_cast<Stage3Smem *>(stage3_smem + ((128u - (a & 127u)) & 127u));
-    b.run_block(blockIdx.x, blockIdx.y, s);
+    b.run_block(blockIdx.x, blockIdx.y, blockIdx.z, s);
 }
 struct TmaState {
     std::map<std::pair<const void *, int>, CUtensorMap> maps;   // (field base, own box?)
@@ -319,5 +319,5 @@ static void dcb_launch_stage3(dc_handle *h, dc::Stage3Body &b, const dc::Stage3P
         if (!m) return;
         *w.dst = *m;
     }
-    k_stage3<<<dim3(nbx, nby), dim3(S3_NT), smem, (cudaStream_t)stream>>>(b);
+    k_stage3<<<dim3(nbx, nby, b.nkc), dim3(S3_NT), smem, (cudaStream_t)stream>>>(b);
 }

@@ -90,10 +90,11 @@ static void dcb_launch_stage3(dc_handle *, dc::Stage3Body &b, const dc::Stage3Pt
     mk(b.mTB, p.TB, g.nz + 1, true); mk(b.mUo, p.Uo, g.nz, true); mk(b.mVo, p.Vo, g.nz, true);
     mk(b.mTo, p.To, g.nz, true);
     static Stage3Smem s;   // one "block" at a time
-    for (int by = nby - 1; by >= 0; by--)
-        for (int bx = nbx - 1; bx >= 0; bx--) {
-            for (size_t n = 0; n < sizeof(s) / sizeof(double); n++)
-                reinterpret_cast<double *>(&s)[n] = 0.0 / 0.0;   // stale smem must not be read
-            b.run_block(bx, by, s);
-        }
+    for (int bz = 0; bz < b.nkc; bz++)
+        for (int by = nby - 1; by >= 0; by--)
+            for (int bx = nbx - 1; bx >= 0; bx--) {
+                for (size_t n = 0; n < sizeof(s) / sizeof(double); n++)
+                    reinterpret_cast<double *>(&s)[n] = 0.0 / 0.0;   // stale smem must not be read
+                b.run_block(bx, by, bz, s);
+            }
 }

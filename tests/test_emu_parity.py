@@ -148,6 +148,26 @@ def test_fused_mode_equals_kernel_mode(g10, moist):
     assert np.all(out['fused']['dUFLXdt'] == 0.) and np.any(out['kernels']['dUFLXdt'] != 0.)
 
 
+@pytest.mark.parametrize('kchunks', [2, 3])
+def test_sigma_column_chunks_are_bit_identical(g10, kchunks, monkeypatch):
+    """the stage kernel with the sigma column cut into chunks (one block each, a warm-up level
+    per chunk; used for small latitude bands) against the unchunked march"""
+    from climate_model_b200.dyn_matsuno import Diagnostics, step_matsuno
+    from climate_model_b200.io_read_namelist import B200
+    out = {}
+    for n in (1, kchunks):
+        monkeypatch.setenv('DC_STAGE_KCHUNKS', str(n))     # read by dc_create
+        GR = grid_from_golden(g10)
+        F = fields_from_golden(GR, g10)
+        Diagnostics.primary_diag(GR.GRF[B200],
+                                 **F.get(Diagnostics.fields_primary_diag, target=B200))
+        step_matsuno(GR, F, 3)
+        F.copy_device_to_host(GR, F.PROGNOSTIC_FIELDS)
+        out[n] = {m: F.host[m].copy() for m in STATE}
+    for m in STATE:
+        assert np.array_equal(out[1][m], out[kchunks][m], equal_nan=True), m
+
+
 @pytest.mark.parametrize('fixture,steps', [('ref_10deg_rand.npz', [10]), ('ref_5deg.npz', [10, 50])])
 def test_fast_math_mode_within_tolerance(fixture, steps):
     """the PRODUCTION arithmetic mode (reciprocal multiplications, FMA contraction; dc_point.h

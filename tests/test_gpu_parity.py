@@ -187,6 +187,31 @@ def test_fused_mode_equals_kernel_mode_bitwise(moist, strict_library):
         _eq(out['fused'][n], out['kernels'][n], n)
 
 
+@pytest.mark.parametrize('build', ['strict', 'production'])
+def test_sigma_column_chunks_are_bit_identical(build, request, monkeypatch):
+    """the stage kernel with the sigma column cut into 2 / 4 chunks (what a small latitude band
+    runs) against the unchunked march: same arithmetic per cell, bitwise equal in both builds"""
+    import torch
+    from climate_model_b200.dyn_matsuno import step_matsuno
+    from climate_model_b200.main_fields import ModelFields
+    from climate_model_b200.main_grid import Grid
+    if build == 'strict':
+        request.getfixturevalue('strict_library')
+    out = {}
+    for n in (1, 2, 4):
+        monkeypatch.setenv('DC_STAGE_KCHUNKS', str(n))     # read by dc_create
+        GR = Grid(nz=32, lat0_deg=-60, lat1_deg=60, dlat_deg=1.0, dlon_deg=1.0)
+        F = ModelFields(GR, UWIND_random_pert=2.0, VWIND_random_pert=2.0, POTT_random_pert=1.0,
+                        COLP_random_pert=100.)
+        _diag(GR, F)
+        step_matsuno(GR, F, 3)
+        torch.cuda.synchronize()
+        out[n] = {m: F.device[m].clone() for m in STATE[:4]}
+    for n in (2, 4):
+        for m in STATE[:4]:
+            assert torch.equal(out[1][m], out[n][m]), (n, m)
+
+
 def test_production_kernel_mode_within_tolerance(g10):
     """PRODUCTION build, one-kernel-per-reference-kernel mode (what the factories run),
     against the reference's golden outputs"""
