@@ -293,15 +293,12 @@ static void do_stage_fused(dc_handle *h, int stage, int part, void *stream)
     double *Uo = stage == 0 ? f.UWIND_OLD : f.UWIND, *Vo = stage == 0 ? f.VWIND_OLD : f.VWIND,
            *To = stage == 0 ? f.POTT_OLD : f.POTT;
     if (part == DC_PART_ALL || part == DC_PART_CONT) {
-        if (g.i_moist)
-            launch_continuity<2>(h, U, V, stream);   // the moisture kernel reads UFLX / VFLX
-        else
-            launch_continuity<0>(h, U, V, stream);
+        launch_continuity<0>(h, U, V, stream);
         if (g.i_moist) {
             const double *QV = stage == 0 ? f.QV : f.QV_OLD, *QC = stage == 0 ? f.QC : f.QC_OLD;
             double *QVo = stage == 0 ? f.QV_OLD : f.QV, *QCo = stage == 0 ? f.QC_OLD : f.QC;
-            MoistStageBody m{g,      QV,         QC,         f.UFLX, f.VFLX, f.COLP,
-                             f.WWIND, f.COLP_NEW, f.COLP_OLD, f.QV,   f.QC,   QVo,    QCo};
+            MoistStageBody m{g,       QV,         QC,         U,    V,    f.COLP,
+                             f.WWIND, f.COLP_NEW, f.COLP_OLD, f.QV, f.QC, QVo,    QCo};
             launch(h, "moist_stage", m, 1, g.nx, g.j0, g.j1, stream);
         }
     }

@@ -520,32 +520,45 @@ struct TimestepBody {
 // ---------------------------------------------------------------------------------------
 struct MoistStageBody {
     Geom g;
-    const double *QV, *QC, *UFLX, *VFLX, *COLP, *WWIND, *COLP_NEW, *COLP_OLD, *QV_OLD, *QC_OLD;
+    // UFLX / VFLX are formed on the fly from the winds and COLP (calc_UFLX / calc_VFLX, the very
+    // expressions of the continuity kernel: same values as the stored fields, which the fused
+    // path therefore does not write).  One tracer at a time: marching both in one loop needs
+    // 153 registers and was twice as slow (one resident block per SM).
+    const double *QV, *QC, *UWIND, *VWIND, *COLP, *WWIND, *COLP_NEW, *COLP_OLD, *QV_OLD, *QC_OLD;
     double *QV_out, *QC_out;
     DC_HD void one(const double *Q, const double *Q_OLD, double *Q_out, int i, int j) const
     {
         const int nz = g.nz;
+        const size_t plane = g.plane;
         const double c = COLP[g.idx2(i, j)];
         const double c_im1 = COLP[g.idx2(i - 1, j)], c_ip1 = COLP[g.idx2(i + 1, j)];
         const double c_jm1 = COLP[g.idx2(i, j - 1)], c_jp1 = COLP[g.idx2(i, j + 1)];
         const double cnew = COLP_NEW[g.idx2(i, j)], cold = COLP_OLD[g.idx2(i, j)];
+        const double dxjs = g.dxjs[g.row(j)], dxjs_jp1 = g.dxjs[g.row(j + 1)];
         const Div cn = mkdiv(cnew);
         const Div A = mkdiv(g.A[g.row(j)], g.r_A[g.row(j)]);
+        const bool edge = (i == 1) || (i == g.nx) || (j == 1) || (j == g.ny);
         // comp_VARVB_log (dyn_functions.py:70-95) needs log and reciprocal of the clamped value
         // of both levels around an interface: computed once per level and carried (the
         // reference evaluates them twice per cell), same values, same result
         const double min_val = 0.0000001;
-        double q = Q[g.idx(i, j, 0)];
+        const size_t o0 = g.idx(i, j, 0), o_jp1 = g.idx(i, j + 1, 0), o_jm1 = g.idx(i, j - 1, 0);
+        double q = Q[o0];
         double qc = fmax(q, min_val), lq = log(qc), rq = 1. / qc;
         double qvb = q;  // unused at k = 0
+        double w_k = WWIND[o0];
         for (int k = 0; k < nz; k++) {
-            const double q_kp1 = (k + 1 < nz) ? Q[g.idx(i, j, k + 1)] : q;
-            const double q_im1 = Q[g.idx(i - 1, j, k)], q_ip1 = Q[g.idx(i + 1, j, k)];
-            const double q_jm1 = Q[g.idx(i, j - 1, k)], q_jp1 = Q[g.idx(i, j + 1, k)];
+            const size_t ko = (size_t)k * plane;
+            const double uf = calc_UFLX(UWIND[o0 + ko], c, c_im1, g.dyis);
+            const double uf_ip1 = calc_UFLX(UWIND[o0 + ko + 1], c_ip1, c, g.dyis);
+            const double vf = calc_VFLX(VWIND[o0 + ko], c, c_jm1, dxjs);
+            const double vf_jp1 = calc_VFLX(VWIND[o_jp1 + ko], c_jp1, c, dxjs_jp1);
+            const double w_kp1 = WWIND[o0 + ko + plane];
+            const double q_kp1 = (k + 1 < nz) ? Q[o0 + ko + plane] : q;
+            const double q_im1 = Q[o0 + ko - 1], q_ip1 = Q[o0 + ko + 1];
+            const double q_jm1 = Q[o_jm1 + ko], q_jp1 = Q[o_jp1 + ko];
             double d = 0.;
-            d = d + hor_adv(q, q_im1, q_ip1, q_jm1, q_jp1, UFLX[g.idx(i, j, k)],
-                            UFLX[g.idx(i + 1, j, k)], VFLX[g.idx(i, j, k)],
-                            VFLX[g.idx(i, j + 1, k)], A);
+            d = d + hor_adv(q, q_im1, q_ip1, q_jm1, q_jp1, uf, uf_ip1, vf, vf_jp1, A);
             // QVVB_kp1 = comp_VARVB_log(VAR = Q[k+1], VAR_km1 = Q[k])
             const double qc_kp1 = fmax(q_kp1, min_val);
             double lq_kp1 = lq, rq_kp1 = rq, qvb_kp1 = qc_kp1;
@@ -554,19 +567,22 @@ struct MoistStageBody {
                 rq_kp1 = 1. / qc_kp1;
                 qvb_kp1 = ((lq - lq_kp1) / (rq_kp1 - rq));
             }
-            d = d + vert_adv(qvb, qvb_kp1, WWIND[g.idx(i, j, k)], WWIND[g.idx(i, j, k + 1)], cnew,
-                             mkdiv(g.dsigma[k], g.r_dsigma[k]), k);
+            d = d + vert_adv(qvb, qvb_kp1, w_k, w_kp1, cnew, mkdiv(g.dsigma[k], g.r_dsigma[k]), k);
             const double coef = g.moist_dif_coef[k];
             if (coef > 0.)
                 d = d + num_dif_pw(q, q_im1, q_ip1, q_jm1, q_jp1, c, c_im1, c_ip1, c_jm1, c_jp1,
                                    coef);
-            put_mass(g, Q_out, i, j, k,
-                     euler_forward_pw(Q_OLD[g.idx(i, j, k)], d, cn, cold, g.dt));
+            const double qn = euler_forward_pw(Q_OLD[o0 + ko], d, cn, cold, g.dt);
+            if (edge)
+                put_mass(g, Q_out, i, j, k, qn);
+            else
+                Q_out[o0 + ko] = qn;
             q = q_kp1;
             qc = qc_kp1;
             lq = lq_kp1;
             rq = rq_kp1;
-            qvb = qvb_kp1;
+            qvb = qvb_kp1;  // comp_VARVB_log(Q[k+1], Q[k]) is next level's (VAR, VAR_km1)
+            w_k = w_kp1;
         }
     }
     DC_HD void operator()(int i, int j) const
