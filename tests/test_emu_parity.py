@@ -309,3 +309,27 @@ def test_boundary_interior_split_equals_whole_stage(fixture):
         out.append({n: F.host[n].copy() for n in STATE + ['PHI', 'WWIND']})
     for n in STATE + ['PHI', 'WWIND']:
         _eq(out[0][n], out[1][n], n)
+
+
+@pytest.mark.parametrize('dlon,dlat,nz', [(8.0, 7.0, 5), (2.4, 5.0, 9), (1.25, 3.0, 7)])
+def test_ragged_grids_fused_equals_kernel_mode(dlon, dlat, nz):
+    """odd nx (the second column of the last thread pair is masked), tile rows and columns that
+    do not divide the grid, odd ny: fused path against the one-kernel-per-reference-kernel mode"""
+    from climate_model_b200.dyn_matsuno import Diagnostics, set_mode, step_matsuno
+    from climate_model_b200.io_read_namelist import B200
+    from climate_model_b200.main_fields import ModelFields
+    from climate_model_b200.main_grid import Grid
+    out = {}
+    for mode in ('fused', 'kernels'):
+        GR = Grid(nz=nz, lat0_deg=-77, lat1_deg=77, dlat_deg=dlat, dlon_deg=dlon,
+                  i_moist_main_switch=1)
+        F = ModelFields(GR, UWIND_random_pert=2.0, VWIND_random_pert=2.0, POTT_random_pert=1.0,
+                        COLP_random_pert=100.)
+        set_mode(GR, mode)
+        Diagnostics.primary_diag(GR.GRF[B200],
+                                 **F.get(Diagnostics.fields_primary_diag, target=B200))
+        step_matsuno(GR, F, 3)
+        F.copy_device_to_host(GR, F.PROGNOSTIC_FIELDS)
+        out[mode] = {n: F.host[n][interior(n, int(GR.nx), int(GR.ny))].copy() for n in STATE}
+    for n in STATE:
+        _eq(out['fused'][n], out['kernels'][n], n)
