@@ -181,6 +181,9 @@ def main():
     ap.add_argument('--mode', default='fused', choices=['fused', 'kernels'],
                     help='fused stage kernel (default) or one kernel per reference kernel')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-kernel-events', action='store_true',
+                    help='do not bracket the kernels with CUDA events in the timed region (no '
+                         'roofline object); checks that the brackets do not perturb the step')
     ap.add_argument('--emu', action='store_true',
                     help='debug the bench LOGIC on a box without a GPU against the host emulation '
                          '(tests/emu); the line is tagged "emu": true and is never a measurement')
@@ -251,7 +254,7 @@ def main():
     if sampler:
         sampler.start()
     launches0 = L.dc_launch_count(h)
-    _lib.check(L.dc_profile_enable(h, 1))
+    _lib.check(L.dc_profile_enable(h, 0 if args.no_kernel_events else 1))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
