@@ -67,6 +67,8 @@ def _declare(lib):
     lib.dc_halo_bytes.argtypes = [vp, ctypes.POINTER(ctypes.c_size_t)]
     lib.dc_halo_pack.argtypes = [vp, ctypes.c_int, vp, vp, vp]
     lib.dc_halo_unpack.argtypes = [vp, ctypes.c_int, vp, vp, vp]
+    lib.dc_run_diag_bytes.argtypes = [vp, ctypes.POINTER(ctypes.c_size_t)]
+    lib.dc_run_diag.argtypes = [vp, vp, ctypes.c_size_t, vp]
     lib.dc_import_field.argtypes = [vp, ctypes.c_int, vp, ctypes.c_size_t, vp]
     lib.dc_export_field.argtypes = [vp, ctypes.c_int, vp, ctypes.c_size_t, vp]
     lib.dc_profile_enable.argtypes = [vp, ctypes.c_int]

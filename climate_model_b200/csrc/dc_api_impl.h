@@ -757,6 +757,31 @@ int dc_secondary_diag(dc_handle *h, void *stream)
     return backend_status("dc_secondary_diag");
 }
 
+int dc_run_diag_bytes(const dc_handle *h, size_t *nbytes)
+{
+    if (!h || !nbytes) return fail(DC_ERR_ARG, "dc_run_diag_bytes: NULL argument");
+    *nbytes = (5 * h->g.plane + 7 * (size_t)h->g.NJ) * sizeof(double);
+    return DC_OK;
+}
+
+int dc_run_diag(dc_handle *h, void *scratch, size_t nbytes, void *stream)
+{
+    if (!h || !scratch) return fail(DC_ERR_ARG, "dc_run_diag: NULL argument");
+    int rc;
+    if ((rc = need(h, "dc_run_diag", {F_UWIND, F_VWIND, F_POTT, F_COLP}))) return rc;
+    const Geom &g = h->g;
+    size_t want;
+    dc_run_diag_bytes(h, &want);
+    if (nbytes < want)
+        return fail(DC_ERR_SHAPE, "dc_run_diag: scratch needs %zu bytes, got %zu", want, nbytes);
+    double *col = static_cast<double *>(scratch), *rows = col + 5 * g.plane;
+    RunDiagColumnBody c{g, h->f.UWIND, h->f.VWIND, h->f.POTT, col};
+    launch(h, "run_diag", c, 1, g.nx + 1, g.j0, g.j1, stream);
+    RunDiagRowBody r{g, col, h->f.COLP, rows};
+    launch(h, "run_diag", r, 0, 0, g.j0, g.j1, stream);
+    return backend_status("dc_run_diag");
+}
+
 int dc_exchange_bc(dc_handle *h, int id, void *stream)
 {
     DC_ENTRY_CHECK("dc_exchange_bc");

@@ -756,6 +756,79 @@ struct SecondaryDiagBody {
 };
 
 // ---------------------------------------------------------------------------------------
+// run-time diagnostics on the device (io_functions.py:70-114: diagnose_print_diag_fields and
+// the crash check of print_ts_info): vmax, mass-weighted mean wind and potential temperature,
+// area-weighted mean column pressure, NaN / over-speed check of UWIND.  The reference copies
+// WIND, COLP and POTT (three full fields) to the host every nth_ts_print_diag steps; here
+// the fields are reduced where they are and 7 numbers per row travel.  Two deterministic
+// passes, no atomics: per-column partials (threads: i in [1, nx+1], j in the band), then one
+// thread per row adds its columns in ascending i; the host adds the rows.
+//   col planes [NJ][NI]: 0 sum_k WIND, 1 sum_k POTT, 2 max_k WIND, 3 max_k UWIND, 4 #NaN(UWIND)
+//   row vectors [NJ]:    0 sum WIND*COLP*A, 1 sum POTT*COLP*A, 2 sum COLP*A, 3 sum A,
+//                        4 max WIND, 5 max UWIND, 6 #NaN(UWIND)
+// WIND = sqrt(WINDX^2 + WINDY^2) as in diag_secondary (dyn_diagnostics.py:199-222).
+// ---------------------------------------------------------------------------------------
+struct RunDiagColumnBody {
+    Geom g;
+    const double *UWIND, *VWIND, *POTT;
+    double *col;
+    DC_HD void operator()(int i, int j) const
+    {
+        const size_t o2 = g.idx2(i, j);
+        double sw = 0., sp = 0., mw = 0., mu = -1e300, nan = 0.;
+        for (int k = 0; k < g.nz; k++) {
+            const double u = UWIND[g.idx(i, j, k)];
+            if (u != u) nan += 1.;
+            mu = fmax(mu, u);
+            if (i <= g.nx) {
+                const double wx = (u + UWIND[g.idx(i + 1, j, k)]) / 2.;
+                const double wy = (VWIND[g.idx(i, j, k)] + VWIND[g.idx(i, j + 1, k)]) / 2.;
+                const double w = sqrt(wx * wx + wy * wy);
+                sw += w;
+                mw = fmax(mw, w);
+                sp += POTT[g.idx(i, j, k)];
+            }
+        }
+        col[0 * g.plane + o2] = sw;
+        col[1 * g.plane + o2] = sp;
+        col[2 * g.plane + o2] = mw;
+        col[3 * g.plane + o2] = mu;
+        col[4 * g.plane + o2] = nan;
+    }
+};
+struct RunDiagRowBody {
+    Geom g;
+    const double *col, *COLP;
+    double *rows;
+    DC_HD void operator()(int, int j) const
+    {
+        const double A = g.A[g.row(j)];
+        double s_w = 0., s_p = 0., s_ca = 0., s_a = 0., m_w = 0., m_u = -1e300, nan = 0.;
+        for (int i = 1; i <= g.nx + 1; i++) {
+            const size_t o2 = g.idx2(i, j);
+            m_u = fmax(m_u, col[3 * g.plane + o2]);
+            nan += col[4 * g.plane + o2];
+            if (i <= g.nx) {
+                const double ca = COLP[o2] * A;
+                s_w += col[0 * g.plane + o2] * ca;
+                s_p += col[1 * g.plane + o2] * ca;
+                s_ca += ca;
+                s_a += A;
+                m_w = fmax(m_w, col[2 * g.plane + o2]);
+            }
+        }
+        const int jd = g.row(j);
+        rows[0 * g.NJ + jd] = s_w;
+        rows[1 * g.NJ + jd] = s_p;
+        rows[2 * g.NJ + jd] = s_ca;
+        rows[3 * g.NJ + jd] = s_a;
+        rows[4 * g.NJ + jd] = m_w;
+        rows[5 * g.NJ + jd] = m_u;
+        rows[6 * g.NJ + jd] = nan;
+    }
+};
+
+// ---------------------------------------------------------------------------------------
 // continuity, single pass (dyn_continuity.py:170-228 + BCs dyn_org_discretizations.py:114-117)
 //
 // ContinuityBody above parks the running flux-divergence prefix in WWIND and re-reads it

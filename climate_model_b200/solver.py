@@ -4,8 +4,9 @@
 
 Builds Grid and ModelFields from the namelist (plus `name=value` overrides of grid / initial
 condition parameters), runs one primary_diag, then per time step: print-diagnostics every
-`nth_ts_print_diag` steps (vmax, mean COLP, NaN / over-speed crash check, reference
-io_functions.py:70-114), secondary_diag, step_matsuno -- all on the device.  The physics
+`nth_ts_print_diag` steps (vmax, mean wind / temperature / COLP, NaN / over-speed crash check,
+reference io_functions.py:70-114, reduced on the device: io_functions.py), secondary_diag,
+step_matsuno -- all on the device.  The physics
 modules, NetCDF output and restart files of the reference are out of scope.
 """
 import argparse
@@ -16,25 +17,13 @@ import torch
 
 from . import namelist as nl
 from .dyn_matsuno import Diagnostics, step_matsuno
+from .io_functions import print_ts_info
 from .io_read_namelist import B200
 from .main_fields import ModelFields
 from .main_grid import Grid
 
 GRID_KEYS = ('nz', 'lat0_deg', 'lat1_deg', 'dlat_deg', 'dlon_deg', 'i_out_nth_hour',
              'i_sim_n_days', 'CFL', 'pair_top', 'i_moist_main_switch')
-
-
-def print_ts_info(GR, F):
-    """io_functions.py:70-114 on the device: vmax, mean COLP, crash check"""
-    js = GR.jshift
-    U = F.device['UWIND'][:, js + 1:js + int(GR.ny) + 1, 1:int(GR.nx) + 1]
-    V = F.device['VWIND'][:, js + 1:js + int(GR.ny) + 1, 1:int(GR.nx) + 1]
-    C = F.device['COLP'][0, js + 1:js + int(GR.ny) + 1, 1:int(GR.nx) + 1]
-    vmax = float(torch.maximum(U.abs().max(), V.abs().max()).item())
-    print('ts %6d  day %8.3f  vmax %8.3f m/s  mean COLP %12.3f Pa' %
-          (GR.ts, GR.sim_time_sec / 86400., vmax, float(C.mean().item())), flush=True)
-    if not np.isfinite(vmax) or vmax > 500.:
-        raise ValueError('MODEL CRASH')
 
 
 def run(nsteps=None, verbose=True, ic=None, **overrides):
@@ -49,8 +38,8 @@ def run(nsteps=None, verbose=True, ic=None, **overrides):
         GR.timer.start('total')
         GR.ts += 1
         GR.sim_time_sec = GR.ts * GR.dt
-        if verbose and (GR.ts % nl.nth_ts_print_diag == 0 or GR.ts == 1):
-            print_ts_info(GR, F)
+        if verbose:
+            print_ts_info(GR, F, force=(GR.ts == 1))
         GR.timer.start('diag')
         Diagnostics.secondary_diag(**F.get(Diagnostics.fields_secondary_diag, target=B200))
         GR.timer.stop('diag')
@@ -59,7 +48,7 @@ def run(nsteps=None, verbose=True, ic=None, **overrides):
     if F.torch_device.type == 'cuda':
         torch.cuda.synchronize()
     if verbose:
-        print_ts_info(GR, F)
+        print_ts_info(GR, F, force=True)
         cells = int(GR.nx) * int(GR.ny) * int(GR.nz)
         dt = time.time() - t0
         print('%d steps in %.2f s: %.3g cell-updates/s, %.1f x faster than reality' %

@@ -115,6 +115,17 @@ int dc_secondary_diag(dc_handle *h, void *stream);
 /* misc_boundaries.exchange_BC (misc_boundaries.py:22-42) on one bound field             */
 int dc_exchange_bc(dc_handle *h, int field_id, void *stream);
 
+/* ---- run-time diagnostics on the device (io_functions.py:70-114, diagnose_print_diag_fields
+ *      + the crash check of print_ts_info).  `scratch` is a caller-owned device buffer of
+ *      dc_run_diag_bytes() bytes; on return (stream order) its LAST 7*NJ doubles hold, per
+ *      device row jd of this rank's band (other rows untouched), the row sums
+ *        [0] sum WIND*COLP*A  [1] sum POTT*COLP*A  [2] sum COLP*A  [3] sum A
+ *        [4] max WIND         [5] max UWIND        [6] number of NaNs in UWIND
+ *      over the interior longitudes and all levels (WIND as in diag_secondary); the caller
+ *      adds the rows (and the ranks).  64 bytes per row instead of three full fields. ---- */
+int dc_run_diag_bytes(const dc_handle *h, size_t *nbytes);
+int dc_run_diag(dc_handle *h, void *scratch, size_t nbytes, void *stream);
+
 /* ---- coarse entry: dyn_matsuno.step_matsuno (dyn_matsuno.py:28-129), nsteps times ----
  * DC_MODE_FUSED (default): per stage one continuity kernel, one fused stage kernel
  *   (momentum-flux preparation + U/V/POTT tendencies + Euler step + boundary images) and

@@ -34,7 +34,9 @@ def main():
     attach_communicator(GR, F)
     Diagnostics.primary_diag(GR.GRF[B200], **F.get(Diagnostics.fields_primary_diag, target=B200))
     step_matsuno(GR, F, nsteps)
-    out = {'j0': GR.j0, 'j1': GR.j1}
+    from climate_model_b200.io_functions import diagnose_print_diag_fields
+    out = {'j0': GR.j0, 'j1': GR.j1,
+           'run_diag': np.array(diagnose_print_diag_fields(GR, F))}   # all-reduced over the bands
     for n in STATE + ['PHI', 'WWIND']:
         F.to_host(GR, n)
         out[n] = F.host[n]

@@ -26,8 +26,10 @@ def _single(fixture, nsteps, moist):
     F = fields_from_golden(GR, g)
     Diagnostics.primary_diag(GR.GRF[B200], **F.get(Diagnostics.fields_primary_diag, target=B200))
     step_matsuno(GR, F, nsteps)
+    from climate_model_b200.io_functions import diagnose_print_diag_fields
     F.copy_device_to_host(GR, F.ALL_FIELDS)
     out = {n: F.host[n].copy() for n in STATE + ['PHI', 'WWIND']}
+    out['run_diag'] = np.array(diagnose_print_diag_fields(GR, F))
     if prev:
         _lib.use_library(prev)
     return out
@@ -57,6 +59,10 @@ def test_banded_run_equals_single_band_bitwise(tmp_path, world, fixture, moist):
             a, e = b[n][:, j0:j1 + 1], ref[n][:, j0:j1 + 1]
             assert np.array_equal(a, e), 'rank %d %s: max|diff| %g' % (
                 rank, n, np.nanmax(np.abs(a - e)))
+        # device-side run diagnostics: maxima exact, the sums to rounding (other row grouping)
+        d, e = b['run_diag'], ref['run_diag']
+        assert d[0] == e[0] and d[4] == e[4] and d[5] == e[5] == 0.
+        assert np.all(np.abs(d[1:4] - e[1:4]) <= 1e-13 * np.abs(e[1:4])), (d, e)
     assert covered == ref['POTT'].shape[1] - 2
 
 

@@ -333,3 +333,36 @@ def test_ragged_grids_fused_equals_kernel_mode(dlon, dlat, nz):
         out[mode] = {n: F.host[n][interior(n, int(GR.nx), int(GR.ny))].copy() for n in STATE}
     for n in STATE:
         _eq(out['fused'][n], out['kernels'][n], n)
+
+
+def test_run_diagnostics_on_device_match_reference_formulas(g10):
+    """dc_run_diag (two deterministic reduction passes on the device) against the reference's
+    diagnose_print_diag_fields (io_functions.py:70-93) restated with numpy on the host state"""
+    from climate_model_b200.dyn_matsuno import Diagnostics, step_matsuno
+    from climate_model_b200.io_functions import diagnose_print_diag_fields, print_ts_info
+    from climate_model_b200.io_read_namelist import B200
+    nx, ny, nz, _ = golden_dims(g10)
+    GR = grid_from_golden(g10)
+    F = fields_from_golden(GR, g10)
+    Diagnostics.primary_diag(GR.GRF[B200], **F.get(Diagnostics.fields_primary_diag, target=B200))
+    step_matsuno(GR, F, 2)
+    got = diagnose_print_diag_fields(GR, F)
+    F.copy_device_to_host(GR, F.PROGNOSTIC_FIELDS)
+    U, V, T, C = (F.host[n] for n in ('UWIND', 'VWIND', 'POTT', 'COLP'))
+    ii, jj = slice(1, nx + 1), slice(1, ny + 1)
+    wx = (U[1:nx + 1, jj] + U[2:nx + 2, jj]) / 2.
+    wy = (V[ii, 1:ny + 1] + V[ii, 2:ny + 2]) / 2.
+    WIND = np.sqrt(wx * wx + wy * wy)
+    A = np.asarray(GR.A)[ii, jj, 0]
+    ca = C[ii, jj, 0] * A
+    mean_wind = sum(np.sum(WIND[:, :, k] * ca) / np.sum(ca) for k in range(nz)) / nz
+    mean_temp = sum(np.sum(T[ii, jj, k] * ca) / np.sum(ca) for k in range(nz)) / nz
+    want = (np.max(WIND), mean_wind, mean_temp, np.sum(ca) / np.sum(A),
+            np.max(U[1:nx + 2, jj]), 0.)
+    assert got[0] == want[0] and got[4] == want[4] and got[5] == 0.
+    for g_, w_ in zip(got[1:4], want[1:4]):
+        assert abs(g_ - w_) <= 1e-13 * abs(w_), (g_, w_)
+    # the crash check fires on a NaN in UWIND
+    F.device['UWIND'][1, GR.jshift + 3, 5] = float('nan')
+    with pytest.raises(ValueError, match='MODEL CRASH'):
+        print_ts_info(GR, F, force=True)

@@ -308,3 +308,35 @@ def test_full_size_properties_quarter_degree_64_levels(build, request):
     assert (V[:, js + 1] == 0).all() and (V[:, js + ny + 1] == 0).all()
     mass1 = (C[0, js + 1:js + ny + 1, 1:nx + 1] * a0[1:ny + 1, None]).sum().item()
     assert abs(mass1 - mass0) / mass0 < 1e-13
+
+
+def test_run_diagnostics_on_device(g10):
+    """dc_run_diag on the GPU against torch reductions of the same device arrays
+    (io_functions.py:70-114: vmax, mass-weighted means, area-weighted COLP, crash check)"""
+    import torch
+    from climate_model_b200.dyn_matsuno import step_matsuno
+    from climate_model_b200.io_functions import diagnose_print_diag_fields, print_ts_info
+    from climate_model_b200.main_fields import ModelFields
+    from climate_model_b200.main_grid import Grid
+    GR = Grid(nz=32, lat0_deg=-84, lat1_deg=84, dlat_deg=1.0, dlon_deg=1.0)
+    F = ModelFields(GR)
+    _diag(GR, F)
+    step_matsuno(GR, F, 2)
+    got = diagnose_print_diag_fields(GR, F)
+    nx, ny, nz, js = int(GR.nx), int(GR.ny), int(GR.nz), int(GR.jshift)
+    U, V, T, C = (F.device[n] for n in ('UWIND', 'VWIND', 'POTT', 'COLP'))
+    rows = slice(js + 1, js + ny + 1)
+    wx = (U[:, rows, 1:nx + 1] + U[:, rows, 2:nx + 2]) / 2.
+    wy = (V[:, rows, 1:nx + 1] + V[:, js + 2:js + ny + 2, 1:nx + 1]) / 2.
+    W = torch.sqrt(wx * wx + wy * wy)
+    A = torch.tensor(np.asarray(GR.A[1, 1:ny + 1, 0]), device=U.device)[:, None]
+    ca = C[0, rows, 1:nx + 1] * A
+    want = (W.max().item(), ((W * ca).sum() / ca.sum() / nz).item(),
+            ((T[:, rows, 1:nx + 1] * ca).sum() / ca.sum() / nz).item(),
+            (ca.sum() / (A.sum() * nx)).item(), U[:, rows, 1:nx + 2].max().item(), 0.)
+    assert got[0] == want[0] and got[4] == want[4] and got[5] == 0.
+    for g_, w_ in zip(got[1:4], want[1:4]):
+        assert abs(g_ - w_) <= 1e-12 * abs(w_), (g_, w_)
+    F.device['UWIND'][3, js + 7, 11] = float('nan')
+    with pytest.raises(ValueError, match='MODEL CRASH'):
+        print_ts_info(GR, F, force=True)
