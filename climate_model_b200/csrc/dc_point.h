@@ -268,10 +268,18 @@ DC_HD double dc_fma(double a, double b, double c)
     return fma(a, b, c);
 #endif
 }
+// 1 / x for finite x of ordinary magnitude (pressures, Exner differences): the hardware seed
+// (rcp.approx.ftz.f64, ~20 bits) and two Newton steps, no special-case branches -- 5 instructions
+// against ~15 of __drcp_rn with its slow-path call; <= 1 ulp
 DC_HD double dc_rcp(double x)
 {
 #if defined(__CUDA_ARCH__)
-    return __drcp_rn(x);
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = __fma_rn(-x, r, 1.);
+    r = __fma_rn(r, e, r);
+    e = __fma_rn(-x, r, 1.);
+    return __fma_rn(r, e, r);
 #else
     return 1. / x;
 #endif
