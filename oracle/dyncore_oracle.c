@@ -20,6 +20,7 @@ static const double con_g = 9.81;
 static const double con_rE = 6371000.;
 static const double con_Rd = 287.058;
 static const double con_cp = 1005.;
+static const double con_Lh = 2264E3; /* io_constants.py:25 */
 #define CON_KAPPA (con_Rd / con_cp)
 
 #define I3(i, j, k, FNY, FNZ) \
@@ -175,7 +176,81 @@ static inline double interp_WWIND_UVWIND(
     return COLPAWWIND_ds_ks * DWIND_ks;
 }
 
-/* dyn_UVFLX_prepare.py:249-439 (launch_numba_cpu_prep_adv), turbulence part omitted */
+/* dyn_functions.py:276-377 (interp_KMOM_dUVWINDdz_py), interior interfaces only.
+ * K = KMOM, R = RHOVB, P = PHI[k], Q = PHI[k-1], C = the COLP argument, A = cell area;
+ * suffixes as in the reference: d = along the wind, p = perpendicular. */
+static inline double interp_KMOM_dUVWINDdz(
+    double DWIND, double DWIND_km1, double K, double K_dm1, double K_pm1, double K_pp1,
+    double K_pm1_dm1, double K_pp1_dm1, double R, double R_dm1, double R_pm1, double R_pp1,
+    double R_pm1_dm1, double R_pp1_dm1, double P, double P_dm1, double P_pm1, double P_pp1,
+    double P_pm1_dm1, double P_pp1_dm1, double Q, double Q_dm1, double Q_pm1, double Q_pp1,
+    double Q_pm1_dm1, double Q_pp1_dm1, double C, double C_dm1, double C_pm1, double C_pp1,
+    double C_pm1_dm1, double C_pp1_dm1, double A, double A_dm1, double A_pm1, double A_pp1,
+    double A_pm1_dm1, double A_pp1_dm1, int rigid_wall, int p_ind, int np)
+{
+    double COLPAKMOM_ds_ks, ALT_ds_km1, ALT_ds;
+    if (rigid_wall && p_ind == 1) {
+        COLPAKMOM_ds_ks = 0.25 * (R_pp1_dm1 * C_pp1_dm1 * A_pp1_dm1 * K_pp1_dm1 +
+                                  R_pp1 * C_pp1 * A_pp1 * K_pp1 + R_dm1 * C_dm1 * A_dm1 * K_dm1 +
+                                  R * C * A * K);
+        ALT_ds_km1 = 0.25 * (Q_pp1_dm1 + Q_pp1 + Q_dm1 + Q) / con_g;
+        ALT_ds = 0.25 * (P_pp1_dm1 + P_pp1 + P_dm1 + P) / con_g;
+    } else if (rigid_wall && p_ind == np) {
+        COLPAKMOM_ds_ks = 0.25 * (R_dm1 * C_dm1 * A_dm1 * K_dm1 + R * C * A * K +
+                                  R_pm1_dm1 * C_pm1_dm1 * A_pm1_dm1 * K_pm1_dm1 +
+                                  R_pm1 * C_pm1 * A_pm1 * K_pm1);
+        ALT_ds_km1 = 0.25 * (Q_dm1 + Q + Q_pm1_dm1 + Q_pm1) / con_g;
+        ALT_ds = 0.25 * (P_dm1 + P + P_pm1_dm1 + P_pm1) / con_g;
+    } else {
+        COLPAKMOM_ds_ks =
+            0.125 * (R_pp1_dm1 * C_pp1_dm1 * A_pp1_dm1 * K_pp1_dm1 + R_pp1 * C_pp1 * A_pp1 * K_pp1 +
+                     2. * R_dm1 * C_dm1 * A_dm1 * K_dm1 + 2. * R * C * A * K +
+                     R_pm1_dm1 * C_pm1_dm1 * A_pm1_dm1 * K_pm1_dm1 + R_pm1 * C_pm1 * A_pm1 * K_pm1);
+        ALT_ds_km1 =
+            0.125 * (Q_pp1_dm1 + Q_pp1 + 2. * Q_dm1 + 2. * Q + Q_pm1_dm1 + Q_pm1) / con_g;
+        ALT_ds = 0.125 * (P_pp1_dm1 + P_pp1 + 2. * P_dm1 + 2. * P + P_pm1_dm1 + P_pm1) / con_g;
+    }
+    const double dDWINDdz_ks = ((DWIND_km1 - DWIND) / (ALT_ds_km1 - ALT_ds));
+    return COLPAKMOM_ds_ks * dDWINDdz_ks;
+}
+
+/* dyn_functions.py:383-422 (interp_VAR_ds_py).  The division by con_g is part of the
+ * reference function whatever VAR is (it is also applied to RHO and the surface momentum
+ * fluxes, and a second time to PHIVB by the callers): reproduced as is. */
+static inline double interp_VAR_ds(double VAR, double VAR_dm1, double VAR_pm1, double VAR_pp1,
+                                   double VAR_pm1_dm1, double VAR_pp1_dm1, int rigid_wall,
+                                   int p_ind, int np)
+{
+    if (rigid_wall && p_ind == 1)
+        return 0.25 * (VAR_pp1_dm1 + VAR_pp1 + VAR_dm1 + VAR) / con_g;
+    if (rigid_wall && p_ind == np)
+        return 0.25 * (VAR_dm1 + VAR + VAR_pm1_dm1 + VAR_pm1) / con_g;
+    return 0.125 * (VAR_pp1_dm1 + VAR_pp1 + 2. * VAR_dm1 + 2. * VAR + VAR_pm1_dm1 + VAR_pm1) /
+           con_g;
+}
+
+/* dyn_functions.py:26-67 (turb_flux_tendency_py).  The neighbour levels that a branch does
+ * not use are never dereferenced here (the reference reads one past the column at k = nz-1) */
+static inline double turb_flux_tendency(double PHI, double PHI_kp1, double PHI_km1, double PHIVB,
+                                        double PHIVB_kp1, double VAR, double VAR_kp1,
+                                        double VAR_km1, double KVAR, double KVAR_kp1, double RHO,
+                                        double RHOVB, double RHOVB_kp1, double COLP,
+                                        double surf_flux_VAR, int k, int nz)
+{
+    const double ALT = PHI / con_g, ALT_kp1 = PHI_kp1 / con_g, ALT_km1 = PHI_km1 / con_g;
+    const double ALTVB = PHIVB / con_g, ALTVB_kp1 = PHIVB_kp1 / con_g;
+    if (k == 0)
+        return COLP * ((+0. - ((VAR - VAR_kp1) / (ALT - ALT_kp1) * RHOVB_kp1 * KVAR_kp1)) /
+                       ((ALTVB - ALTVB_kp1) * RHO));
+    if (k == nz - 1)
+        return COLP * ((+((VAR_km1 - VAR) / (ALT_km1 - ALT) * RHOVB * KVAR) + surf_flux_VAR) /
+                       ((ALTVB - ALTVB_kp1) * RHO));
+    return COLP * ((+((VAR_km1 - VAR) / (ALT_km1 - ALT) * RHOVB * KVAR) -
+                    ((VAR - VAR_kp1) / (ALT - ALT_kp1) * RHOVB_kp1 * KVAR_kp1)) /
+                   ((ALTVB - ALTVB_kp1) * RHO));
+}
+
+/* dyn_UVFLX_prepare.py:249-439 (launch_numba_cpu_prep_adv) */
 static void orc_UVFLX_prep_adv(const orc_grid *g, orc_fields *f)
 {
     const int nx = g->nx, ny = g->ny, nz = g->nz, nxs = nx + 1, nys = ny + 1;
@@ -212,6 +287,51 @@ static void orc_UVFLX_prep_adv(const orc_grid *g, orc_fields *f)
                     A[M2(i, j - 1)], A[M2(i - 1, j)], A[M2(i + 1, j)], A[M2(i - 1, j - 1)],
                     A[M2(i + 1, j - 1)], ds[k], ds[k - 1], 0, i, nx);
         }
+
+    /* dyn_UVFLX_prepare.py:298-343: K * d(wind)/dz on the interfaces (0 at k = 0 and nz) */
+    if (g->i_coupling) {
+        const double *K = f->KMOM, *R = f->RHOVB, *P = f->PHI, *C = f->COLP;
+#pragma omp parallel for schedule(static)
+        for (int i = 1; i <= nxs; i++)
+            for (int j = 1; j <= ny; j++) {
+                f->KMOM_dUWINDdz[MS(i, j, 0)] = 0.;
+                f->KMOM_dUWINDdz[MS(i, j, nz)] = 0.;
+                for (int k = 1; k < nz; k++)
+                    f->KMOM_dUWINDdz[MS(i, j, k)] = interp_KMOM_dUVWINDdz(
+                        U[M(i, j, k)], U[M(i, j, k - 1)], K[MS(i, j, k)], K[MS(i - 1, j, k)],
+                        K[MS(i, j - 1, k)], K[MS(i, j + 1, k)], K[MS(i - 1, j - 1, k)],
+                        K[MS(i - 1, j + 1, k)], R[MS(i, j, k)], R[MS(i - 1, j, k)],
+                        R[MS(i, j - 1, k)], R[MS(i, j + 1, k)], R[MS(i - 1, j - 1, k)],
+                        R[MS(i - 1, j + 1, k)], P[M(i, j, k)], P[M(i - 1, j, k)],
+                        P[M(i, j - 1, k)], P[M(i, j + 1, k)], P[M(i - 1, j - 1, k)],
+                        P[M(i - 1, j + 1, k)], P[M(i, j, k - 1)], P[M(i - 1, j, k - 1)],
+                        P[M(i, j - 1, k - 1)], P[M(i, j + 1, k - 1)], P[M(i - 1, j - 1, k - 1)],
+                        P[M(i - 1, j + 1, k - 1)], C[M2(i, j)], C[M2(i - 1, j)], C[M2(i, j - 1)],
+                        C[M2(i, j + 1)], C[M2(i - 1, j - 1)], C[M2(i - 1, j + 1)], A[M2(i, j)],
+                        A[M2(i - 1, j)], A[M2(i, j - 1)], A[M2(i, j + 1)], A[M2(i - 1, j - 1)],
+                        A[M2(i - 1, j + 1)], 1, j, ny);
+            }
+#pragma omp parallel for schedule(static)
+        for (int i = 1; i <= nx; i++)
+            for (int j = 1; j <= nys; j++) {
+                f->KMOM_dVWINDdz[YS(i, j, 0)] = 0.;
+                f->KMOM_dVWINDdz[YS(i, j, nz)] = 0.;
+                for (int k = 1; k < nz; k++)
+                    f->KMOM_dVWINDdz[YS(i, j, k)] = interp_KMOM_dUVWINDdz(
+                        V[Y(i, j, k)], V[Y(i, j, k - 1)], K[MS(i, j, k)], K[MS(i, j - 1, k)],
+                        K[MS(i - 1, j, k)], K[MS(i + 1, j, k)], K[MS(i - 1, j - 1, k)],
+                        K[MS(i + 1, j - 1, k)], R[MS(i, j, k)], R[MS(i, j - 1, k)],
+                        R[MS(i - 1, j, k)], R[MS(i + 1, j, k)], R[MS(i - 1, j - 1, k)],
+                        R[MS(i + 1, j - 1, k)], P[M(i, j, k)], P[M(i, j - 1, k)],
+                        P[M(i - 1, j, k)], P[M(i + 1, j, k)], P[M(i - 1, j - 1, k)],
+                        P[M(i + 1, j - 1, k)], P[M(i, j, k - 1)], P[M(i, j - 1, k - 1)],
+                        P[M(i - 1, j, k - 1)], P[M(i + 1, j, k - 1)], P[M(i - 1, j - 1, k - 1)],
+                        P[M(i + 1, j - 1, k - 1)], C[M2(i, j)], C[M2(i, j - 1)], C[M2(i - 1, j)],
+                        C[M2(i + 1, j)], C[M2(i - 1, j - 1)], C[M2(i + 1, j - 1)], A[M2(i, j)],
+                        A[M2(i, j - 1)], A[M2(i - 1, j)], A[M2(i + 1, j)], A[M2(i - 1, j - 1)],
+                        A[M2(i + 1, j - 1)], 0, i, nx);
+            }
+    }
 
     /* dyn_UVFLX_prepare.py:345-436 with dyn_functions.py:429-536; only the neighbours
      * each flux uses are loaded (the reference loads a full 3x3 block, part of it out of
@@ -376,6 +496,37 @@ static void orc_UFLX_tendency(const orc_grid *g, orc_fields *f)
                                       EFLX_im1_jp1, 1.);
                 d = d + ((f->WWIND_UWIND[MS(i, j, k)] - f->WWIND_UWIND[MS(i, j, k + 1)]) /
                          g->dsigma[k]);
+                if (g->i_coupling) { /* dyn_UFLX.py:136-170 */
+                    const double *PB = f->PHIVB, *RH = f->RHO, *SF = f->SMOMXFLX;
+                    const double ALTVB_is =
+                        interp_VAR_ds(PB[MS(i, j, k)], PB[MS(i - 1, j, k)], PB[MS(i, j - 1, k)],
+                                      PB[MS(i, j + 1, k)], PB[MS(i - 1, j - 1, k)],
+                                      PB[MS(i - 1, j + 1, k)], 1, j, ny) / con_g;
+                    const double ALTVB_kp1_is =
+                        interp_VAR_ds(PB[MS(i, j, k + 1)], PB[MS(i - 1, j, k + 1)],
+                                      PB[MS(i, j - 1, k + 1)], PB[MS(i, j + 1, k + 1)],
+                                      PB[MS(i - 1, j - 1, k + 1)], PB[MS(i - 1, j + 1, k + 1)], 1, j,
+                                      ny) / con_g;
+                    const double RHO_is =
+                        interp_VAR_ds(RH[M(i, j, k)], RH[M(i - 1, j, k)], RH[M(i, j - 1, k)],
+                                      RH[M(i, j + 1, k)], RH[M(i - 1, j - 1, k)],
+                                      RH[M(i - 1, j + 1, k)], 1, j, ny);
+                    const double SMOMXFLX_is =
+                        interp_VAR_ds(SF[M2(i, j)], SF[M2(i - 1, j)], SF[M2(i, j - 1)],
+                                      SF[M2(i, j + 1)], SF[M2(i - 1, j - 1)], SF[M2(i - 1, j + 1)],
+                                      1, j, ny);
+                    const double Kd = f->KMOM_dUWINDdz[MS(i, j, k)],
+                                 Kd_kp1 = f->KMOM_dUWINDdz[MS(i, j, k + 1)];
+                    double t;
+                    if (k == 0)
+                        t = ((0. - Kd_kp1) / ((ALTVB_is - ALTVB_kp1_is) * RHO_is));
+                    else if (k == nz - 1)
+                        t = ((Kd + SMOMXFLX_is) / ((ALTVB_is - ALTVB_kp1_is) * RHO_is));
+                    else
+                        t = ((Kd - Kd_kp1) / ((ALTVB_is - ALTVB_kp1_is) * RHO_is));
+                    f->dUFLXdt_TURB[M(i, j, k)] = t;
+                    d = d + t;
+                }
                 d = d + coriolis_and_spherical_UWIND(
                             f->COLP[M2(i, j)], f->COLP[M2(i - 1, j)], V[Y(i, j, k)],
                             V[Y(i - 1, j, k)], V[Y(i, j + 1, k)], V[Y(i - 1, j + 1, k)],
@@ -427,6 +578,37 @@ static void orc_VFLX_tendency(const orc_grid *g, orc_fields *f)
                                       TFLX_ip1_jm1, -1.);
                 d = d + ((f->WWIND_VWIND[YS(i, j, k)] - f->WWIND_VWIND[YS(i, j, k + 1)]) /
                          g->dsigma[k]);
+                if (g->i_coupling) { /* dyn_VFLX.py:134-166 */
+                    const double *PB = f->PHIVB, *RH = f->RHO, *SF = f->SMOMYFLX;
+                    const double ALTVB_js =
+                        interp_VAR_ds(PB[MS(i, j, k)], PB[MS(i, j - 1, k)], PB[MS(i - 1, j, k)],
+                                      PB[MS(i + 1, j, k)], PB[MS(i - 1, j - 1, k)],
+                                      PB[MS(i + 1, j - 1, k)], 0, i, nx) / con_g;
+                    const double ALTVB_kp1_js =
+                        interp_VAR_ds(PB[MS(i, j, k + 1)], PB[MS(i, j - 1, k + 1)],
+                                      PB[MS(i - 1, j, k + 1)], PB[MS(i + 1, j, k + 1)],
+                                      PB[MS(i - 1, j - 1, k + 1)], PB[MS(i + 1, j - 1, k + 1)], 0, i,
+                                      nx) / con_g;
+                    const double RHO_js =
+                        interp_VAR_ds(RH[M(i, j, k)], RH[M(i, j - 1, k)], RH[M(i - 1, j, k)],
+                                      RH[M(i + 1, j, k)], RH[M(i - 1, j - 1, k)],
+                                      RH[M(i + 1, j - 1, k)], 0, i, nx);
+                    const double SMOMYFLX_js =
+                        interp_VAR_ds(SF[M2(i, j)], SF[M2(i, j - 1)], SF[M2(i - 1, j)],
+                                      SF[M2(i + 1, j)], SF[M2(i - 1, j - 1)], SF[M2(i + 1, j - 1)],
+                                      0, i, nx);
+                    const double Kd = f->KMOM_dVWINDdz[YS(i, j, k)],
+                                 Kd_kp1 = f->KMOM_dVWINDdz[YS(i, j, k + 1)];
+                    double t;
+                    if (k == 0)
+                        t = ((0. - Kd_kp1) / ((ALTVB_js - ALTVB_kp1_js) * RHO_js));
+                    else if (k == nz - 1)
+                        t = ((Kd + SMOMYFLX_js) / ((ALTVB_js - ALTVB_kp1_js) * RHO_js));
+                    else
+                        t = ((Kd - Kd_kp1) / ((ALTVB_js - ALTVB_kp1_js) * RHO_js));
+                    f->dVFLXdt_TURB[Y(i, j, k)] = t;
+                    d = d + t;
+                }
                 d = d + coriolis_and_spherical_VWIND(
                             f->COLP[M2(i, j)], f->COLP[M2(i, j - 1)], U[M(i, j, k)],
                             U[M(i, j - 1, k)], U[M(i + 1, j, k)], U[M(i + 1, j - 1, k)],
@@ -451,7 +633,15 @@ static void orc_VFLX_tendency(const orc_grid *g, orc_fields *f)
 /* dyn_org_discretizations.py:121-249 (CPU branch; the KMOM/SMOM BCs act on zero fields) */
 void orc_momentum(const orc_grid *g, orc_fields *f)
 {
+    const int nx = g->nx, ny = g->ny, nz = g->nz;
+    if (g->i_coupling) orc_exchange_BC(g, f->KMOM, nx + 2, ny + 2, nz + 1);
     orc_UVFLX_prep_adv(g, f);
+    if (g->i_coupling) {
+        orc_exchange_BC(g, f->KMOM_dUWINDdz, nx + 3, ny + 2, nz + 1);
+        orc_exchange_BC(g, f->KMOM_dVWINDdz, nx + 2, ny + 3, nz + 1);
+        orc_exchange_BC(g, f->SMOMXFLX, nx + 2, ny + 2, 1);
+        orc_exchange_BC(g, f->SMOMYFLX, nx + 2, ny + 2, 1);
+    }
     orc_UFLX_tendency(g, f);
     orc_VFLX_tendency(g, f);
 }
@@ -499,6 +689,18 @@ void orc_temperature(const orc_grid *g, orc_fields *f)
                 d = d + vert_adv(f->POTTVB[MS(i, j, k)], f->POTTVB[MS(i, j, k + 1)],
                                  f->WWIND[MS(i, j, k)], f->WWIND[MS(i, j, k + 1)],
                                  f->COLP_NEW[M2(i, j)], g->dsigma[k], k);
+                if (g->i_coupling) { /* dyn_POTT.py:87-96 */
+                    const int km = k > 0 ? k - 1 : k, kp = k < nz - 1 ? k + 1 : k;
+                    const double t = turb_flux_tendency(
+                        f->PHI[M(i, j, k)], f->PHI[M(i, j, kp)], f->PHI[M(i, j, km)],
+                        f->PHIVB[MS(i, j, k)], f->PHIVB[MS(i, j, k + 1)], P[M(i, j, k)],
+                        P[M(i, j, kp)], P[M(i, j, km)], f->KHEAT[MS(i, j, k)],
+                        f->KHEAT[MS(i, j, k + 1)], f->RHO[M(i, j, k)], f->RHOVB[MS(i, j, k)],
+                        f->RHOVB[MS(i, j, k + 1)], C[M2(i, j)], f->SSHFLX[M2(i, j)] / con_cp, k,
+                        nz);
+                    d = d + t;
+                    f->dPOTTdt_TURB[M(i, j, k)] = t / C[M2(i, j)] * 3600.;
+                }
                 if (g->POTT_dif_coef[k] > 0.)
                     d = d + num_dif_pw(P[M(i, j, k)], P[M(i - 1, j, k)], P[M(i + 1, j, k)],
                                        P[M(i, j - 1, k)], P[M(i, j + 1, k)], C[M2(i, j)],
@@ -547,6 +749,17 @@ void orc_moisture(const orc_grid *g, orc_fields *f)
                     d = d + vert_adv(QVB, QVB_kp1, f->WWIND[MS(i, j, k)],
                                      f->WWIND[MS(i, j, k + 1)], f->COLP_NEW[M2(i, j)],
                                      g->dsigma[k], k);
+                    if (g->i_coupling) { /* dyn_moist.py:100-112 */
+                        const int km = k > 0 ? k - 1 : k, kp = k < nz - 1 ? k + 1 : k;
+                        const double tq = turb_flux_tendency(
+                            f->PHI[M(i, j, k)], f->PHI[M(i, j, kp)], f->PHI[M(i, j, km)],
+                            f->PHIVB[MS(i, j, k)], f->PHIVB[MS(i, j, k + 1)], Qk, Q[M(i, j, kp)],
+                            Q[M(i, j, km)], f->KHEAT[MS(i, j, k)], f->KHEAT[MS(i, j, k + 1)],
+                            f->RHO[M(i, j, k)], f->RHOVB[MS(i, j, k)], f->RHOVB[MS(i, j, k + 1)],
+                            C[M2(i, j)], t ? 0. : f->SLHFLX[M2(i, j)] / con_Lh, k, nz);
+                        d = d + tq;
+                        if (!t) f->dQVdt_TURB[M(i, j, k)] = tq;
+                    }
                     if (g->moist_dif_coef[k] > 0.)
                         d = d + num_dif_pw(Qk, Q[M(i - 1, j, k)], Q[M(i + 1, j, k)],
                                            Q[M(i, j - 1, k)], Q[M(i, j + 1, k)], C[M2(i, j)],

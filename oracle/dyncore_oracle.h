@@ -48,6 +48,10 @@ typedef struct {
     const double *sigma_vb;     /* (nz+1) */
     const double *dsigma;       /* (nz) */
     const double *UVFLX_dif_coef, *POTT_dif_coef, *moist_dif_coef; /* (nz) */
+    /* != 0: the physics coupling fields (KMOM, KHEAT, surface fluxes) enter the tendencies
+     * (the reference always evaluates these terms; with zero fields they are exactly 0,
+     * which is what i_coupling == 0 assumes) */
+    int i_coupling;
 } orc_grid;
 
 /* every model field the dry dyn core touches (main_fields.py:233-330) */
@@ -62,6 +66,11 @@ typedef struct {
     double *PHI, *PHIVB, *PVTF, *PVTFVB, *POTTVB;
     /* secondary diagnostics (dyn_diagnostics.py:199-222) */
     double *TAIR, *TAIRVB, *PAIR, *PAIRVB, *RHO, *RHOVB, *WINDX, *WINDY, *WIND;
+    /* physics coupling (inputs: main_fields.py KMOM, KHEAT (nzs), surface fluxes (2-D);
+     * outputs of the dyn core: KMOM_dUWINDdz / KMOM_dVWINDdz (nzs), *_TURB tendencies) */
+    double *KMOM, *KHEAT, *SMOMXFLX, *SMOMYFLX, *SSHFLX, *SLHFLX;
+    double *KMOM_dUWINDdz, *KMOM_dVWINDdz;
+    double *dUFLXdt_TURB, *dVFLXdt_TURB, *dPOTTdt_TURB, *dQVdt_TURB;
 } orc_fields;
 
 /* misc_boundaries.py:22-42 ; (fnx,fny,fnz) = shape of FIELD */

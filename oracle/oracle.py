@@ -38,6 +38,12 @@ FIELDS = {
     'TAIR': (0, 0, 'nz'), 'TAIRVB': (0, 0, 'nzs'), 'PAIR': (0, 0, 'nz'), 'PAIRVB': (0, 0, 'nzs'),
     'RHO': (0, 0, 'nz'), 'RHOVB': (0, 0, 'nzs'), 'WINDX': (0, 0, 'nz'), 'WINDY': (0, 0, 'nz'),
     'WIND': (0, 0, 'nz'),
+    # physics coupling (order = orc_fields)
+    'KMOM': (0, 0, 'nzs'), 'KHEAT': (0, 0, 'nzs'), 'SMOMXFLX': (0, 0, 1), 'SMOMYFLX': (0, 0, 1),
+    'SSHFLX': (0, 0, 1), 'SLHFLX': (0, 0, 1),
+    'KMOM_dUWINDdz': (1, 0, 'nzs'), 'KMOM_dVWINDdz': (0, 1, 'nzs'),
+    'dUFLXdt_TURB': (1, 0, 'nz'), 'dVFLXdt_TURB': (0, 1, 'nz'), 'dPOTTdt_TURB': (0, 0, 'nz'),
+    'dQVdt_TURB': (0, 0, 'nz'),
 }
 
 _dp = ctypes.POINTER(ctypes.c_double)
@@ -46,7 +52,8 @@ _dp = ctypes.POINTER(ctypes.c_double)
 class _Grid(ctypes.Structure):
     _fields_ = ([('nx', ctypes.c_int), ('ny', ctypes.c_int), ('nz', ctypes.c_int),
                  ('i_moist', ctypes.c_int), ('dt', ctypes.c_double),
-                 ('pair_top', ctypes.c_double)] + [(n, _dp) for n in GRID_FIELDS])
+                 ('pair_top', ctypes.c_double)] + [(n, _dp) for n in GRID_FIELDS] +
+                [('i_coupling', ctypes.c_int)])
 
 
 class _Fields(ctypes.Structure):
@@ -85,7 +92,7 @@ def field_shape(name, nx, ny, nz):
 class Oracle:
     """Holds a full set of model fields (reference layout) and runs the C oracle on them."""
 
-    def __init__(self, nx, ny, nz, dt, grid, i_moist=True, pair_top=10000.):
+    def __init__(self, nx, ny, nz, dt, grid, i_moist=True, pair_top=10000., i_coupling=False):
         self.nx, self.ny, self.nz = int(nx), int(ny), int(nz)
         self.dt = float(dt)
         self.grid = {n: np.ascontiguousarray(grid[n], dtype=np.float64) for n in GRID_FIELDS}
@@ -94,7 +101,7 @@ class Oracle:
             fill = 0.0 if n in ('WWIND', 'POTTVB') else np.nan   # io_initial_conditions.py:45-46
             self.F[n] = np.full(field_shape(n, nx, ny, nz), fill, dtype=np.float64)
         self._g = _Grid(nx=self.nx, ny=self.ny, nz=self.nz, i_moist=int(bool(i_moist)),
-                        dt=self.dt, pair_top=float(pair_top))
+                        dt=self.dt, pair_top=float(pair_top), i_coupling=int(bool(i_coupling)))
         for n in GRID_FIELDS:
             setattr(self._g, n, self.grid[n].ctypes.data_as(_dp))
         self._f = _Fields()

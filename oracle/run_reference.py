@@ -180,6 +180,8 @@ GRIDF = ['corf', 'corf_is', 'A', 'sigma_vb', 'dsigma', 'dxjs', 'dyis', 'lat_rad'
 STAGE1 = ['UFLX', 'VFLX', 'FLXDIV', 'dCOLPdt', 'COLP_NEW', 'WWIND', 'WWIND_UWIND',
           'WWIND_VWIND', 'BFLX', 'CFLX', 'DFLX', 'EFLX', 'RFLX', 'QFLX', 'SFLX', 'TFLX',
           'dUFLXdt', 'dVFLXdt', 'dPOTTdt', 'dQVdt', 'dQCdt']
+STAGE1_COUPLING = ['KMOM_dUWINDdz', 'KMOM_dVWINDdz', 'dUFLXdt_TURB', 'dVFLXdt_TURB',
+                   'dPOTTdt_TURB', 'dQVdt_TURB']
 DIAG = ['PHI', 'PHIVB', 'PVTF', 'PVTFVB', 'POTTVB']
 
 
@@ -197,6 +199,10 @@ def main():
     ap.add_argument('--stage1', action='store_true', help='dump stage-1 intermediates')
     ap.add_argument('--minimal', action='store_true',
                     help='dump only grid, inputs and prognostic states (small fixture)')
+    ap.add_argument('--coupling', action='store_true',
+                    help='fill the physics coupling fields (KMOM, KHEAT, surface fluxes) with '
+                         'seeded random values instead of zeros: exercises the turbulence / '
+                         'surface-flux terms of the dynamical core')
     ap.add_argument('--dump-diag', action='store_true',
                     help='also dump the primary diagnostics and WWIND after each step count')
     args = ap.parse_args()
@@ -218,6 +224,14 @@ def main():
     F = ModelFields(GR, gpu_enable)
     for n in COUPLING:
         F.host[n][:] = 0.0
+    if args.coupling:
+        # physically plausible magnitudes; the reference's own turbulence / surface modules
+        # stay off, the dynamical core only consumes these fields
+        rng = np.random.default_rng(2024)
+        for n, (lo, hi) in (('KMOM', (0.01, 0.2)), ('KHEAT', (0.05, 2.)),
+                            ('SMOMXFLX', (-0.02, 0.02)), ('SMOMYFLX', (-0.02, 0.02)),
+                            ('SSHFLX', (-5., 15.)), ('SLHFLX', (-5., 20.))):
+            F.host[n][:] = rng.uniform(lo, hi, size=F.host[n].shape)
     Diagnostics = DiagnosticsFactory(target=CPU)
 
     if args.perturb_ulp:
@@ -234,6 +248,9 @@ def main():
     for n in GRIDF:
         out['GR_' + n] = np.array(GR.GRF[CPU][n])
     out['IN_HSURF'] = F.host['HSURF'].copy()
+    if args.coupling:
+        for n in COUPLING:
+            out['IN_' + n] = F.host[n].copy()
     for n in STATE:
         out['IN_' + n] = F.host[n].copy()
 
@@ -254,7 +271,7 @@ def main():
         # calling it once before the first step leaves the trajectory unchanged.
         F.host['COLP_OLD'][:] = F.host['COLP'][:]
         compute_tendencies(GR, F)
-        for n in STAGE1:
+        for n in STAGE1 + (STAGE1_COUPLING if args.coupling else []):
             out['S1_' + n] = F.host[n].copy()
     print('init+jit %.1f s' % (time.time() - t0), flush=True)
 

@@ -14,6 +14,10 @@ outputs.  Nothing here is computed by this repository's code.
   ref_5deg.npz        BASELINE.json configs[0]: 5 deg x 8 levels, elev.1-deg topography,
                       Gaussian wind perturbation: grid, initial state, prognostic state
                       after 10 and 50 steps.
+  ref_10deg_coupled.npz  the 36x16x6 grid with NON-ZERO physics coupling fields (seeded random
+                      KMOM, KHEAT, SMOMXFLX, SMOMYFLX, SSHFLX, SLHFLX): inputs, every stage-1
+                      intermediate incl. KMOM_dUWINDdz / KMOM_dVWINDdz and the *_TURB
+                      tendencies, state after 1, 2 and 10 steps.
 """
 import os
 import subprocess
@@ -26,6 +30,8 @@ JOBS = [
     ('ref_10deg_rand.npz', ['--grid', '10deg_rand', '--steps', '1', '2', '10', '--stage1',
                             '--dump-diag']),
     ('ref_5deg.npz', ['--grid', '5deg', '--steps', '10', '50', '--minimal']),
+    ('ref_10deg_coupled.npz', ['--grid', '10deg_rand', '--steps', '1', '2', '10', '--stage1',
+                               '--coupling']),
 ]
 
 if __name__ == '__main__':

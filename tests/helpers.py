@@ -23,10 +23,17 @@ def golden_dims(g):
     return nx, ny, nz, dt
 
 
+COUPLING = ['KMOM', 'KHEAT', 'SMOMXFLX', 'SMOMYFLX', 'SSHFLX', 'SLHFLX']
+
+
 def oracle_from_golden(g, i_moist=True):
+    """the oracle on a golden fixture's grid and inputs; a fixture that carries the physics
+    coupling fields (ref_10deg_coupled.npz) switches their terms on"""
     nx, ny, nz, dt = golden_dims(g)
-    O = Oracle(nx, ny, nz, dt, {n: g['GR_' + n] for n in GRID_FIELDS}, i_moist=i_moist)
-    O.set(**{n: g['IN_' + n] for n in ['HSURF'] + STATE})
+    coupled = 'IN_KMOM' in g
+    O = Oracle(nx, ny, nz, dt, {n: g['GR_' + n] for n in GRID_FIELDS}, i_moist=i_moist,
+               i_coupling=coupled)
+    O.set(**{n: g['IN_' + n] for n in ['HSURF'] + STATE + (COUPLING if coupled else [])})
     return O
 
 

@@ -105,3 +105,45 @@ def test_thread_count_does_not_change_results(g10):
     b.set_num_threads(nthr)
     for n in STATE:
         _eq(a.F[n], b.F[n], n)
+
+
+# ---------------------------------------------------------------------------------------
+# physics coupling terms: vertical turbulent transport of momentum, heat and
+# moisture and the surface fluxes, with NON-ZERO KMOM / KHEAT / SMOM*FLX / SSHFLX / SLHFLX
+# ---------------------------------------------------------------------------------------
+@pytest.fixture(scope='module')
+def gc():
+    return load_golden('ref_10deg_coupled.npz')
+
+
+def test_coupled_stage1_intermediates_bit_exact(gc):
+    nx, ny, nz, _ = golden_dims(gc)
+    O = oracle_from_golden(gc)
+    O.primary_diag()
+    O.secondary_diag()
+    O.F['COLP_OLD'][:] = O.F['COLP']
+    O.compute_tendencies()
+    box = lambda i1, j1, j0=1: (slice(1, i1 + 1), slice(j0, j1 + 1), slice(None))
+    ranges = {
+        'KMOM_dUWINDdz': box(nx + 1, ny), 'KMOM_dVWINDdz': box(nx, ny + 1),
+        'dUFLXdt_TURB': box(nx, ny), 'dVFLXdt_TURB': box(nx, ny, 2),
+        'dPOTTdt_TURB': box(nx, ny), 'dQVdt_TURB': box(nx, ny),
+        'dUFLXdt': box(nx, ny), 'dVFLXdt': box(nx, ny, 2), 'dPOTTdt': box(nx, ny),
+        'dQVdt': box(nx, ny), 'dQCdt': box(nx, ny),
+    }
+    for n, sl in ranges.items():
+        _eq(O.F[n][sl], gc['S1_' + n][sl], n)
+    # the coupling terms are not a rounding-level effect in this fixture
+    assert np.nanmax(np.abs(gc['S1_dUFLXdt_TURB'])) > 1e-2 * np.nanmax(np.abs(gc['S1_dUFLXdt']))
+
+
+def test_coupled_step_matsuno_bit_exact(gc):
+    """secondary_diag + step_matsuno as the reference's time loop (solver.py:99-101, :70-73)"""
+    O = oracle_from_golden(gc)
+    O.primary_diag()
+    for ts in range(1, 11):
+        O.secondary_diag()
+        O.step_matsuno(1)
+        if ts in (1, 2, 10):
+            for n in STATE:
+                assert np.array_equal(O.F[n], gc['N%d_%s' % (ts, n)], equal_nan=True), (ts, n)
