@@ -18,6 +18,10 @@ GRID_FIELDS_2D = ['A', 'dxjs', 'dyis', 'corf', 'corf_is', 'lat_rad', 'lat_is_rad
 GRID_FIELDS_1D = ['sigma_vb', 'dsigma', 'UVFLX_dif_coef', 'POTT_dif_coef', 'moist_dif_coef']
 
 DC_NK_2D, DC_NK_NZ, DC_NK_NZS = 0, 1, 2
+# registry fields that only exist for the physics coupling terms (dc_grid_desc.i_coupling)
+COUPLING_ONLY_FIELDS = ['KMOM', 'KHEAT', 'SMOMXFLX', 'SMOMYFLX', 'SSHFLX', 'SLHFLX',
+                        'KMOM_dUWINDdz', 'KMOM_dVWINDdz', 'dUFLXdt_TURB', 'dVFLXdt_TURB',
+                        'dPOTTdt_TURB', 'dQVdt_TURB', 'dPOTTdt_RAD']
 DC_MODE_FUSED, DC_MODE_KERNELS = 0, 1
 DC_PART_ALL, DC_PART_CONT, DC_PART_BOUNDARY, DC_PART_INTERIOR, DC_PART_COLP = 0, 1, 2, 3, 4
 
@@ -27,7 +31,8 @@ class GridDesc(ctypes.Structure):
     _fields_ = ([('nx', ctypes.c_int), ('ny', ctypes.c_int), ('nz', ctypes.c_int),
                  ('j0', ctypes.c_int), ('j1', ctypes.c_int), ('i_moist', ctypes.c_int),
                  ('dt', ctypes.c_double), ('pair_top', ctypes.c_double)] +
-                [(n, _dp) for n in GRID_FIELDS_2D + GRID_FIELDS_1D])
+                [(n, _dp) for n in GRID_FIELDS_2D + GRID_FIELDS_1D] +
+                [('i_coupling', ctypes.c_int)])
 
 
 class DyncoreError(RuntimeError):

@@ -92,6 +92,16 @@ static const FieldInfo g_field_info[F_COUNT] = {
     // work field of this library (not a reference field): the per-column part of the
     // pressure-gradient term, written by the primary diagnostics (dc_kernels.h)
     {"PGCOL", 0, 0, DC_NK_NZ},
+    // physics coupling (dc_grid_desc.i_coupling): inputs from the physics modules ...
+    {"KMOM", 0, 0, DC_NK_NZS},      {"KHEAT", 0, 0, DC_NK_NZS},
+    {"SMOMXFLX", 0, 0, DC_NK_2D},   {"SMOMYFLX", 0, 0, DC_NK_2D},
+    {"SSHFLX", 0, 0, DC_NK_2D},     {"SLHFLX", 0, 0, DC_NK_2D},
+    // ... and what the dynamical core derives from them
+    {"KMOM_dUWINDdz", 1, 0, DC_NK_NZS}, {"KMOM_dVWINDdz", 0, 1, DC_NK_NZS},
+    {"dUFLXdt_TURB", 1, 0, DC_NK_NZ},   {"dVFLXdt_TURB", 0, 1, DC_NK_NZ},
+    {"dPOTTdt_TURB", 0, 0, DC_NK_NZ},   {"dQVdt_TURB", 0, 0, DC_NK_NZ},
+    // radiative heating rate [K s-1], input from the radiation module (dyn_POTT.py:107-108)
+    {"dPOTTdt_RAD", 0, 0, DC_NK_NZ},
 };
 
 }  // namespace dc
@@ -214,14 +224,29 @@ static int do_momentum(dc_handle *h, void *stream)
 {
     const Fields &f = h->f;
     const Geom &g = h->g;
+    // dyn_org_discretizations.py:121-249: the exchange_BC calls on the coupling fields
+    auto bc = [&](double *F, int kind, int nk) {
+        launch(h, "exchange_bc", ExchangeBCBody{g, F, kind, nk}, 1, g.nx, 1,
+               g.ny + ((kind & 2) ? 1 : 0), stream);
+    };
+    if (g.i_coupling) bc(f.KMOM, 0, g.nz + 1);
     PrepBody p{g,      f.UWIND, f.VWIND, f.WWIND, f.UFLX, f.VFLX, f.COLP_NEW, f.WWIND_UWIND,
-               f.WWIND_VWIND, f.BFLX, f.CFLX, f.DFLX, f.EFLX, f.RFLX, f.QFLX, f.SFLX, f.TFLX};
+               f.WWIND_VWIND, f.BFLX, f.CFLX, f.DFLX, f.EFLX, f.RFLX, f.QFLX, f.SFLX, f.TFLX,
+               f.KMOM, f.RHOVB, f.PHI, f.COLP, f.KMOM_dUWINDdz, f.KMOM_dVWINDdz};
     launch(h, "uvflx_prep", p, 1, g.nx + 1, 1, g.ny + 1, stream);
+    if (g.i_coupling) {
+        bc(f.KMOM_dUWINDdz, 1, g.nz + 1);
+        bc(f.KMOM_dVWINDdz, 2, g.nz + 1);
+        bc(f.SMOMXFLX, 0, 1);
+        bc(f.SMOMYFLX, 0, 1);
+    }
     UFLXTendencyBody u{g,      f.UFLX, f.UWIND, f.VWIND, f.BFLX,   f.CFLX,        f.DFLX, f.EFLX,
-                       f.PHI,  f.COLP, f.POTT,  f.PVTF,  f.PVTFVB, f.WWIND_UWIND, f.dUFLXdt};
+                       f.PHI,  f.COLP, f.POTT,  f.PVTF,  f.PVTFVB, f.WWIND_UWIND, f.dUFLXdt,
+                       f.PHIVB, f.RHO, f.SMOMXFLX, f.KMOM_dUWINDdz, f.dUFLXdt_TURB};
     launch(h, "uflx_tendency", u, 1, g.nx, 1, g.ny, stream);
     VFLXTendencyBody v{g,      f.VFLX, f.UWIND, f.VWIND, f.RFLX,   f.SFLX,        f.TFLX, f.QFLX,
-                       f.PHI,  f.COLP, f.POTT,  f.PVTF,  f.PVTFVB, f.WWIND_VWIND, f.dVFLXdt};
+                       f.PHI,  f.COLP, f.POTT,  f.PVTF,  f.PVTFVB, f.WWIND_VWIND, f.dVFLXdt,
+                       f.PHIVB, f.RHO, f.SMOMYFLX, f.KMOM_dVWINDdz, f.dVFLXdt_TURB};
     launch(h, "vflx_tendency", v, 1, g.nx, 2, g.ny, stream);
     return DC_OK;
 }
@@ -230,8 +255,9 @@ static int do_temperature(dc_handle *h, void *stream)
 {
     const Fields &f = h->f;
     const Geom &g = h->g;
-    POTTTendencyBody b{g, f.POTT, f.UFLX, f.VFLX, f.COLP, f.POTTVB, f.WWIND, f.COLP_NEW,
-                       f.dPOTTdt};
+    POTTTendencyBody b{g,     f.POTT,    f.UFLX,  f.VFLX,  f.COLP,  f.POTTVB, f.WWIND,
+                       f.COLP_NEW, f.dPOTTdt, f.PHI, f.PHIVB, f.KHEAT, f.RHO,   f.RHOVB,
+                       f.SSHFLX, f.dPOTTdt_TURB, f.dPOTTdt_RAD};
     launch(h, "pott_tendency", b, 1, g.nx, 1, g.ny, stream);
     return DC_OK;
 }
@@ -241,8 +267,9 @@ static int do_moisture(dc_handle *h, void *stream)
     const Fields &f = h->f;
     const Geom &g = h->g;
     if (!g.i_moist) return DC_OK;
-    MoistTendencyBody b{g, f.QV, f.QC, f.UFLX, f.VFLX, f.COLP, f.WWIND, f.COLP_NEW, f.dQVdt,
-                        f.dQCdt};
+    MoistTendencyBody b{g,       f.QV,  f.QC,    f.UFLX,  f.VFLX, f.COLP,  f.WWIND, f.COLP_NEW,
+                        f.dQVdt, f.dQCdt, f.PHI, f.PHIVB, f.KHEAT, f.RHO, f.RHOVB, f.SLHFLX,
+                        f.dQVdt_TURB};
     launch(h, "moist_tendency", b, 1, g.nx, 1, g.ny, stream);
     return DC_OK;
 }
@@ -406,6 +433,14 @@ static const std::vector<int> NEED_STEP_DRY = {
     F_dPOTTdt, F_UWIND, F_VWIND, F_POTT};
 static const std::vector<int> NEED_STEP_MOIST = {F_QV_OLD, F_dQVdt, F_QC_OLD, F_dQCdt,
                                                            F_QV,     F_QC};
+// dc_grid_desc.i_coupling: what the turbulence / surface-flux terms add to each entry
+static const std::vector<int> NEED_MOM_CPL = {F_KMOM, F_RHOVB, F_RHO, F_PHIVB, F_SMOMXFLX,
+                                              F_SMOMYFLX, F_KMOM_dUWINDdz, F_KMOM_dVWINDdz,
+                                              F_dUFLXdt_TURB, F_dVFLXdt_TURB};
+static const std::vector<int> NEED_TEMP_CPL = {F_PHI, F_PHIVB, F_KHEAT, F_RHO, F_RHOVB,
+                                               F_SSHFLX, F_dPOTTdt_TURB, F_dPOTTdt_RAD};
+static const std::vector<int> NEED_MOIST_CPL = {F_PHI, F_PHIVB, F_KHEAT, F_RHO, F_RHOVB,
+                                                F_SLHFLX, F_dQVdt_TURB};
 static const std::vector<int> NEED_DIAG = {F_COLP, F_POTT,  F_HSURF, F_PVTF, F_PVTFVB,
                                                      F_PHI,  F_PHIVB, F_POTTVB, F_PGCOL};
 
@@ -461,6 +496,7 @@ int dc_create(const dc_grid_desc *d, dc_handle **out)
     g.nx = nx; g.ny = ny; g.nz = nz;
     g.j0 = d->j0; g.j1 = d->j1;
     g.i_moist = d->i_moist ? 1 : 0;
+    g.i_coupling = d->i_coupling ? 1 : 0;
     g.dt = d->dt; g.pair_top = d->pair_top;
     g.NI = ((nx + 3) + 15) / 16 * 16;
     g.NJ = (g.j1 - g.j0 + 1) + 2 * HJ + 1;
@@ -688,7 +724,9 @@ int dc_momentum(dc_handle *h, void *stream)
 {
     DC_ENTRY_CHECK("dc_momentum");
     int rc;
-    if ((rc = need(h, "dc_momentum", NEED_MOM)) || (rc = refresh_diag(h, "dc_momentum", stream)))
+    if ((rc = need(h, "dc_momentum", NEED_MOM)) ||
+        (h->g.i_coupling && (rc = need(h, "dc_momentum", NEED_MOM_CPL))) ||
+        (rc = refresh_diag(h, "dc_momentum", stream)))
         return rc;
     do_momentum(h, stream);
     return backend_status("dc_momentum");
@@ -699,6 +737,9 @@ int dc_temperature(dc_handle *h, void *stream)
     DC_ENTRY_CHECK("dc_temperature");
     int rc;
     if ((rc = need(h, "dc_temperature", NEED_TEMP))) return rc;
+    if (h->g.i_coupling && ((rc = need(h, "dc_temperature", NEED_TEMP_CPL)) ||
+                            (rc = refresh_diag(h, "dc_temperature", stream))))
+        return rc;
     do_temperature(h, stream);
     return backend_status("dc_temperature");
 }
@@ -709,6 +750,9 @@ int dc_moisture(dc_handle *h, void *stream)
     int rc;
     if (!h->g.i_moist) return DC_OK;
     if ((rc = need(h, "dc_moisture", NEED_MOIST))) return rc;
+    if (h->g.i_coupling && ((rc = need(h, "dc_moisture", NEED_MOIST_CPL)) ||
+                            (rc = refresh_diag(h, "dc_moisture", stream))))
+        return rc;
     do_moisture(h, stream);
     return backend_status("dc_moisture");
 }
@@ -800,6 +844,10 @@ int dc_exchange_bc(dc_handle *h, int id, void *stream)
 static int check_fused_fields(dc_handle *h, const char *what)
 {
     int rc;
+    if (h->g.i_coupling)
+        return fail(DC_ERR_STATE, "%s: the physics coupling terms (i_coupling) run in the kernel "
+                                  "decomposition on one device (dc_step_matsuno or the "
+                                  "fine-grained entries), not in the fused stage entries", what);
     if ((rc = need(h, what, NEED_CONT)) || (rc = need(h, what, NEED_TEMP)) ||
         (rc = need(h, what, NEED_STEP_DRY)) || (rc = need(h, what, NEED_DIAG)))
         return rc;
@@ -940,10 +988,19 @@ int dc_step_matsuno(dc_handle *h, int nsteps, void *stream)
         return rc;
     const Fields &f = h->f;
     const size_t b2 = g.plane * sizeof(double), b3 = b2 * g.nz;
-    if (h->mode == DC_MODE_FUSED && g.nz > NZMAX)
+    if (g.i_coupling && ((rc = need(h, "dc_step_matsuno", NEED_MOM_CPL)) ||
+                         (rc = need(h, "dc_step_matsuno", NEED_TEMP_CPL)) ||
+                         (g.i_moist && (rc = need(h, "dc_step_matsuno", NEED_MOIST_CPL)))))
+        return rc;
+    // the coupled terms exist in the kernel decomposition only (the fused stage kernel is the
+    // dry-dynamics fast path): a handle with i_coupling steps through the kernels whatever
+    // the mode; RHO / RHOVB stay as the caller's last dc_secondary_diag left them
+    // (solver.py:99-101 calls it once per time step, not per Matsuno stage)
+    const bool fused = h->mode == DC_MODE_FUSED && !g.i_coupling;
+    if (fused && g.nz > NZMAX)
         return fail(DC_ERR_STATE, "dc_step_matsuno: the fused mode supports nz <= %d "
                                   "(use dc_set_mode(h, DC_MODE_KERNELS))", NZMAX);
-    if (h->mode == DC_MODE_FUSED) {
+    if (fused) {
         do_xhalo_fix(h, stream);
         for (int s = 0; s < nsteps; s++) {
             dcb_d2d_async(f.COLP_OLD, f.COLP, b2, stream);      // dyn_matsuno.py:34

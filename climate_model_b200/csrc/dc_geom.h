@@ -38,6 +38,7 @@ struct Geom {
     int jshift;        // device row = global j + jshift
     int j0, j1;        // global mass rows owned by this rank (1 <= j0 <= j1 <= ny)
     int i_moist;       // namelist.i_moist_main_switch
+    int i_coupling;    // physics coupling terms (KMOM, KHEAT, surface fluxes) are evaluated
     size_t plane;      // NI * NJ
     double dt;         // GR.dt
     double pair_top;   // namelist.pair_top
@@ -80,7 +81,10 @@ struct Geom {
     X(dUFLXdt) X(dVFLXdt) X(dPOTTdt) X(dQVdt) X(dQCdt)                                       \
     X(PHI) X(PHIVB) X(PVTF) X(PVTFVB) X(POTTVB)                                              \
     X(TAIR) X(TAIRVB) X(PAIR) X(PAIRVB) X(RHO) X(RHOVB) X(WINDX) X(WINDY) X(WIND)         \
-    X(PGCOL)
+    X(PGCOL)                                                                                 \
+    X(KMOM) X(KHEAT) X(SMOMXFLX) X(SMOMYFLX) X(SSHFLX) X(SLHFLX)                             \
+    X(KMOM_dUWINDdz) X(KMOM_dVWINDdz)                                                        \
+    X(dUFLXdt_TURB) X(dVFLXdt_TURB) X(dPOTTdt_TURB) X(dQVdt_TURB) X(dPOTTdt_RAD)
 
 struct Fields {
 #define X(n) double *n;

@@ -190,6 +190,23 @@ struct PrepBody {
     Geom g;
     const double *UWIND, *VWIND, *WWIND, *UFLX, *VFLX, *COLP_NEW;
     double *WWIND_UWIND, *WWIND_VWIND, *BFLX, *CFLX, *DFLX, *EFLX, *RFLX, *QFLX, *SFLX, *TFLX;
+    // physics coupling (g.i_coupling): dyn_UVFLX_prepare.py:298-343
+    const double *KMOM, *RHOVB, *PHI, *COLP;
+    double *KMOM_dUWINDdz, *KMOM_dVWINDdz;
+    // the six points around a u-point (rigid = true: d = i, p = j) or a v-point
+    DC_HD Six six3(const double *F, int i, int j, int k, bool u) const
+    {
+        if (u)
+            return Six{F[g.idx(i, j, k)],         F[g.idx(i - 1, j, k)],     F[g.idx(i, j - 1, k)],
+                       F[g.idx(i, j + 1, k)],     F[g.idx(i - 1, j - 1, k)], F[g.idx(i - 1, j + 1, k)]};
+        return Six{F[g.idx(i, j, k)],         F[g.idx(i, j - 1, k)],     F[g.idx(i - 1, j, k)],
+                   F[g.idx(i + 1, j, k)],     F[g.idx(i - 1, j - 1, k)], F[g.idx(i + 1, j - 1, k)]};
+    }
+    DC_HD Six sixA(int j, bool u) const
+    {
+        const double a = g.A[g.row(j)], am = g.A[g.row(j - 1)], ap = g.A[g.row(j + 1)];
+        return u ? Six{a, a, am, ap, am, ap} : Six{a, am, a, a, am, am};
+    }
     DC_HD double P(int i, int j, int k) const
     {
         return COLP_NEW[g.idx2(i, j)] * g.A[g.row(j)] * WWIND[g.idx(i, j, k)];
@@ -218,6 +235,28 @@ struct PrepBody {
                                 P(i - 1, j - 1, k), P(i + 1, j - 1, k), 0) *
                     interp_ks(VWIND[g.idx(i, j, k)], VWIND[g.idx(i, j, k - 1)], g.dsigma[k],
                               g.dsigma[k - 1], mkdiv(g.dsigma[k] + g.dsigma[k - 1], g.r_dss[k]));
+        }
+        if (g.i_coupling) {
+            if (j <= ny) {
+                KMOM_dUWINDdz[g.idx(i, j, 0)] = 0.;
+                KMOM_dUWINDdz[g.idx(i, j, nz)] = 0.;
+                const Six C = six3(COLP, i, j, 0, true), A = sixA(j, true);
+                for (int k = 1; k < nz; k++)
+                    KMOM_dUWINDdz[g.idx(i, j, k)] = interp_KMOM_dUVWINDdz(
+                        UWIND[g.idx(i, j, k)], UWIND[g.idx(i, j, k - 1)], six3(KMOM, i, j, k, true),
+                        six3(RHOVB, i, j, k, true), six3(PHI, i, j, k, true),
+                        six3(PHI, i, j, k - 1, true), C, A, true, j, ny);
+            }
+            if (i <= nx) {
+                KMOM_dVWINDdz[g.idx(i, j, 0)] = 0.;
+                KMOM_dVWINDdz[g.idx(i, j, nz)] = 0.;
+                const Six C = six3(COLP, i, j, 0, false), A = sixA(j, false);
+                for (int k = 1; k < nz; k++)
+                    KMOM_dVWINDdz[g.idx(i, j, k)] = interp_KMOM_dUVWINDdz(
+                        VWIND[g.idx(i, j, k)], VWIND[g.idx(i, j, k - 1)], six3(KMOM, i, j, k, false),
+                        six3(RHOVB, i, j, k, false), six3(PHI, i, j, k, false),
+                        six3(PHI, i, j, k - 1, false), C, A, false, i, nx);
+            }
         }
         for (int k = 0; k < nz; k++) {  // dyn_UVFLX_prepare.py:345-436
             CFLX[g.idx(i, j, k)] =
@@ -267,6 +306,14 @@ struct UFLXTendencyBody {
     const double *UFLX, *UWIND, *VWIND, *BFLX, *CFLX, *DFLX, *EFLX, *PHI, *COLP, *POTT, *PVTF,
         *PVTFVB, *WWIND_UWIND;
     double *dUFLXdt;
+    // physics coupling (g.i_coupling): dyn_UFLX.py:136-170
+    const double *PHIVB, *RHO, *SMOMXFLX, *KMOM_dUWINDdz;
+    double *dUFLXdt_TURB;
+    DC_HD Six six(const double *F, int i, int j, int k) const
+    {
+        return Six{F[g.idx(i, j, k)],     F[g.idx(i - 1, j, k)],     F[g.idx(i, j - 1, k)],
+                   F[g.idx(i, j + 1, k)], F[g.idx(i - 1, j - 1, k)], F[g.idx(i - 1, j + 1, k)]};
+    }
     DC_HD void operator()(int i, int j) const
     {
         const int nx = g.nx, ny = g.ny, nz = g.nz;
@@ -302,6 +349,16 @@ struct UFLXTendencyBody {
                                   eflx_im1_jp1, 1.);
             const Div ds = mkdiv(g.dsigma[k], g.r_dsigma[k]);
             d = d + ((WWIND_UWIND[g.idx(i, j, k)] - WWIND_UWIND[g.idx(i, j, k + 1)]) / ds);
+            if (g.i_coupling) {
+                const double t = turb_momentum(
+                    KMOM_dUWINDdz[g.idx(i, j, k)], KMOM_dUWINDdz[g.idx(i, j, k + 1)],
+                    interp_VAR_ds(six(SMOMXFLX, i, j, 0), true, j, ny),
+                    interp_VAR_ds(six(PHIVB, i, j, k), true, j, ny) / con_g,
+                    interp_VAR_ds(six(PHIVB, i, j, k + 1), true, j, ny) / con_g,
+                    interp_VAR_ds(six(RHO, i, j, k), true, j, ny), k, nz);
+                dUFLXdt_TURB[g.idx(i, j, k)] = t;
+                d = d + t;
+            }
             d = d + coriolis_UWIND(c, c_im1, V[g.idx(i, j, k)], V[g.idx(i - 1, j, k)],
                                    V[g.idx(i, j + 1, k)], V[g.idx(i - 1, j + 1, k)], u, u_im1,
                                    u_ip1, fcos_is, sinl, scale);
@@ -330,6 +387,14 @@ struct VFLXTendencyBody {
     const double *VFLX, *UWIND, *VWIND, *RFLX, *SFLX, *TFLX, *QFLX, *PHI, *COLP, *POTT, *PVTF,
         *PVTFVB, *WWIND_VWIND;
     double *dVFLXdt;
+    // physics coupling (g.i_coupling): dyn_VFLX.py:134-166
+    const double *PHIVB, *RHO, *SMOMYFLX, *KMOM_dVWINDdz;
+    double *dVFLXdt_TURB;
+    DC_HD Six six(const double *F, int i, int j, int k) const
+    {
+        return Six{F[g.idx(i, j, k)],     F[g.idx(i, j - 1, k)],     F[g.idx(i - 1, j, k)],
+                   F[g.idx(i + 1, j, k)], F[g.idx(i - 1, j - 1, k)], F[g.idx(i + 1, j - 1, k)]};
+    }
     DC_HD void operator()(int i, int j) const
     {
         const int nx = g.nx, nz = g.nz;
@@ -358,6 +423,16 @@ struct VFLXTendencyBody {
                                   tflx_ip1_jm1, -1.);
             const Div ds = mkdiv(g.dsigma[k], g.r_dsigma[k]);
             d = d + ((WWIND_VWIND[g.idx(i, j, k)] - WWIND_VWIND[g.idx(i, j, k + 1)]) / ds);
+            if (g.i_coupling) {
+                const double t = turb_momentum(
+                    KMOM_dVWINDdz[g.idx(i, j, k)], KMOM_dVWINDdz[g.idx(i, j, k + 1)],
+                    interp_VAR_ds(six(SMOMYFLX, i, j, 0), false, i, nx),
+                    interp_VAR_ds(six(PHIVB, i, j, k), false, i, nx) / con_g,
+                    interp_VAR_ds(six(PHIVB, i, j, k + 1), false, i, nx) / con_g,
+                    interp_VAR_ds(six(RHO, i, j, k), false, i, nx), k, g.nz);
+                dVFLXdt_TURB[g.idx(i, j, k)] = t;
+                d = d + t;
+            }
             d = d + coriolis_VWIND(c, c_jm1, U[g.idx(i, j, k)], U[g.idx(i, j - 1, k)],
                                    U[g.idx(i + 1, j, k)], U[g.idx(i + 1, j - 1, k)], fcos, sinl,
                                    fcos_jm1, sinl_jm1, scale);
@@ -384,6 +459,10 @@ struct POTTTendencyBody {
     Geom g;
     const double *POTT, *UFLX, *VFLX, *COLP, *POTTVB, *WWIND, *COLP_NEW;
     double *dPOTTdt;
+    // physics coupling (g.i_coupling): dyn_POTT.py:87-96
+    const double *PHI, *PHIVB, *KHEAT, *RHO, *RHOVB, *SSHFLX;
+    double *dPOTTdt_TURB;
+    const double *dPOTTdt_RAD;   // radiative heating rate, dyn_POTT.py:40-41, :107-108
     DC_HD void operator()(int i, int j) const
     {
         const int nz = g.nz;
@@ -403,10 +482,22 @@ struct POTTTendencyBody {
                             VFLX[g.idx(i, j + 1, k)], A);
             d = d + vert_adv(POTTVB[g.idx(i, j, k)], POTTVB[g.idx(i, j, k + 1)],
                              WWIND[g.idx(i, j, k)], WWIND[g.idx(i, j, k + 1)], cnew, ds, k);
+            if (g.i_coupling) {
+                const int km = k > 0 ? k - 1 : k, kp = k < nz - 1 ? k + 1 : k;
+                const double t = turb_flux_tendency(
+                    PHI[g.idx(i, j, k)], PHI[g.idx(i, j, kp)], PHI[g.idx(i, j, km)],
+                    PHIVB[g.idx(i, j, k)], PHIVB[g.idx(i, j, k + 1)], p, POTT[g.idx(i, j, kp)],
+                    POTT[g.idx(i, j, km)], KHEAT[g.idx(i, j, k)], KHEAT[g.idx(i, j, k + 1)],
+                    RHO[g.idx(i, j, k)], RHOVB[g.idx(i, j, k)], RHOVB[g.idx(i, j, k + 1)], c,
+                    SSHFLX[g.idx2(i, j)] / con_cp, k, nz);
+                d = d + t;
+                dPOTTdt_TURB[g.idx(i, j, k)] = t / c * 3600.;   // [K hr-1], dyn_POTT.py:97
+            }
             const double coef = g.POTT_dif_coef[k];
             if (coef > 0.)
                 d = d + num_dif_pw(p, p_im1, p_ip1, p_jm1, p_jp1, c, c_im1, c_ip1, c_jm1, c_jp1,
                                    coef);
+            if (g.i_coupling) d = d + (dPOTTdt_RAD[g.idx(i, j, k)] * c);
             dPOTTdt[g.idx(i, j, k)] = d;
         }
     }
@@ -421,6 +512,9 @@ struct MoistTendencyBody {
     Geom g;
     const double *QV, *QC, *UFLX, *VFLX, *COLP, *WWIND, *COLP_NEW;
     double *dQVdt, *dQCdt;
+    // physics coupling (g.i_coupling): dyn_moist.py:100-112
+    const double *PHI, *PHIVB, *KHEAT, *RHO, *RHOVB, *SLHFLX;
+    double *dQVdt_TURB;
     DC_HD void one(const double *Q, double *dQ, int i, int j) const
     {
         const int nz = g.nz;
@@ -442,6 +536,18 @@ struct MoistTendencyBody {
             const double qvb_kp1 = comp_VARVB_log(q_kp1, q);
             d = d + vert_adv(qvb, qvb_kp1, WWIND[g.idx(i, j, k)], WWIND[g.idx(i, j, k + 1)], cnew,
                              mkdiv(g.dsigma[k], g.r_dsigma[k]), k);
+            if (g.i_coupling) {
+                const int km = k > 0 ? k - 1 : k, kp = k < nz - 1 ? k + 1 : k;
+                const bool vap = (Q == QV);
+                const double t = turb_flux_tendency(
+                    PHI[g.idx(i, j, k)], PHI[g.idx(i, j, kp)], PHI[g.idx(i, j, km)],
+                    PHIVB[g.idx(i, j, k)], PHIVB[g.idx(i, j, k + 1)], q, Q[g.idx(i, j, kp)],
+                    Q[g.idx(i, j, km)], KHEAT[g.idx(i, j, k)], KHEAT[g.idx(i, j, k + 1)],
+                    RHO[g.idx(i, j, k)], RHOVB[g.idx(i, j, k)], RHOVB[g.idx(i, j, k + 1)], c,
+                    vap ? SLHFLX[g.idx2(i, j)] / con_Lh : 0., k, nz);
+                d = d + t;
+                if (vap) dQVdt_TURB[g.idx(i, j, k)] = t;
+            }
             const double coef = g.moist_dif_coef[k];
             if (coef > 0.)
                 d = d + num_dif_pw(q, q_im1, q_ip1, q_jm1, q_jp1, c, c_im1, c_ip1, c_jm1, c_jp1,

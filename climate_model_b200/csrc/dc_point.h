@@ -307,6 +307,81 @@ DC_HD double pow_kappa(double x, const PowCoef &c)
     return dc_with_hi_word(p, dc_hi_word(p) + ((int)kf << 20));
 }
 
+// ---------------------------------------------------------------------------------------
+// physics coupling terms (vertical turbulent transport, surface fluxes)
+// ---------------------------------------------------------------------------------------
+constexpr double con_Lh = 2264E3;   // io_constants.py:25
+
+// dyn_functions.py:276-377 (interior interfaces; 0 at k = 0 and nz).  K = KMOM, R = RHOVB,
+// P = PHI[k], Q = PHI[k-1], C = COLP, A = cell area; d = along the wind, p = perpendicular
+struct Six {
+    double c, dm1, pm1, pp1, pm1_dm1, pp1_dm1;
+};
+DC_HD double interp_KMOM_dUVWINDdz(double DWIND, double DWIND_km1, const Six &K, const Six &R,
+                                   const Six &P, const Six &Q, const Six &C, const Six &A,
+                                   bool rigid_wall, int p_ind, int np)
+{
+    double COLPAKMOM_ds_ks, ALT_ds_km1, ALT_ds;
+    if (rigid_wall && p_ind == 1) {
+        COLPAKMOM_ds_ks = 0.25 * (R.pp1_dm1 * C.pp1_dm1 * A.pp1_dm1 * K.pp1_dm1 +
+                                  R.pp1 * C.pp1 * A.pp1 * K.pp1 + R.dm1 * C.dm1 * A.dm1 * K.dm1 +
+                                  R.c * C.c * A.c * K.c);
+        ALT_ds_km1 = 0.25 * (Q.pp1_dm1 + Q.pp1 + Q.dm1 + Q.c) / con_g;
+        ALT_ds = 0.25 * (P.pp1_dm1 + P.pp1 + P.dm1 + P.c) / con_g;
+    } else if (rigid_wall && p_ind == np) {
+        COLPAKMOM_ds_ks = 0.25 * (R.dm1 * C.dm1 * A.dm1 * K.dm1 + R.c * C.c * A.c * K.c +
+                                  R.pm1_dm1 * C.pm1_dm1 * A.pm1_dm1 * K.pm1_dm1 +
+                                  R.pm1 * C.pm1 * A.pm1 * K.pm1);
+        ALT_ds_km1 = 0.25 * (Q.dm1 + Q.c + Q.pm1_dm1 + Q.pm1) / con_g;
+        ALT_ds = 0.25 * (P.dm1 + P.c + P.pm1_dm1 + P.pm1) / con_g;
+    } else {
+        COLPAKMOM_ds_ks =
+            0.125 * (R.pp1_dm1 * C.pp1_dm1 * A.pp1_dm1 * K.pp1_dm1 + R.pp1 * C.pp1 * A.pp1 * K.pp1 +
+                     2. * R.dm1 * C.dm1 * A.dm1 * K.dm1 + 2. * R.c * C.c * A.c * K.c +
+                     R.pm1_dm1 * C.pm1_dm1 * A.pm1_dm1 * K.pm1_dm1 + R.pm1 * C.pm1 * A.pm1 * K.pm1);
+        ALT_ds_km1 =
+            0.125 * (Q.pp1_dm1 + Q.pp1 + 2. * Q.dm1 + 2. * Q.c + Q.pm1_dm1 + Q.pm1) / con_g;
+        ALT_ds = 0.125 * (P.pp1_dm1 + P.pp1 + 2. * P.dm1 + 2. * P.c + P.pm1_dm1 + P.pm1) / con_g;
+    }
+    const double dDWINDdz_ks = ((DWIND_km1 - DWIND) / (ALT_ds_km1 - ALT_ds));
+    return COLPAKMOM_ds_ks * dDWINDdz_ks;
+}
+// dyn_functions.py:383-422.  The division by con_g belongs to the reference function whatever
+// VAR is (it is also applied to RHO and the surface momentum fluxes, and a second time to
+// PHIVB by the callers): reproduced as is.
+DC_HD double interp_VAR_ds(const Six &V, bool rigid_wall, int p_ind, int np)
+{
+    if (rigid_wall && p_ind == 1) return 0.25 * (V.pp1_dm1 + V.pp1 + V.dm1 + V.c) / con_g;
+    if (rigid_wall && p_ind == np) return 0.25 * (V.dm1 + V.c + V.pm1_dm1 + V.pm1) / con_g;
+    return 0.125 * (V.pp1_dm1 + V.pp1 + 2. * V.dm1 + 2. * V.c + V.pm1_dm1 + V.pm1) / con_g;
+}
+// dyn_UFLX.py:136-170, dyn_VFLX.py:134-166: vertical turbulent transport of momentum
+DC_HD double turb_momentum(double Kd, double Kd_kp1, double SMOMFLX_s, double ALTVB_s,
+                           double ALTVB_kp1_s, double RHO_s, int k, int nz)
+{
+    if (k == 0) return ((0. - Kd_kp1) / ((ALTVB_s - ALTVB_kp1_s) * RHO_s));
+    if (k == nz - 1) return ((Kd + SMOMFLX_s) / ((ALTVB_s - ALTVB_kp1_s) * RHO_s));
+    return ((Kd - Kd_kp1) / ((ALTVB_s - ALTVB_kp1_s) * RHO_s));
+}
+// dyn_functions.py:26-67
+DC_HD double turb_flux_tendency(double PHI, double PHI_kp1, double PHI_km1, double PHIVB,
+                                double PHIVB_kp1, double VAR, double VAR_kp1, double VAR_km1,
+                                double KVAR, double KVAR_kp1, double RHO, double RHOVB,
+                                double RHOVB_kp1, double COLP, double surf_flux_VAR, int k, int nz)
+{
+    const double ALT = PHI / con_g, ALT_kp1 = PHI_kp1 / con_g, ALT_km1 = PHI_km1 / con_g;
+    const double ALTVB = PHIVB / con_g, ALTVB_kp1 = PHIVB_kp1 / con_g;
+    if (k == 0)
+        return COLP * ((+0. - ((VAR - VAR_kp1) / (ALT - ALT_kp1) * RHOVB_kp1 * KVAR_kp1)) /
+                       ((ALTVB - ALTVB_kp1) * RHO));
+    if (k == nz - 1)
+        return COLP * ((+((VAR_km1 - VAR) / (ALT_km1 - ALT) * RHOVB * KVAR) + surf_flux_VAR) /
+                       ((ALTVB - ALTVB_kp1) * RHO));
+    return COLP * ((+((VAR_km1 - VAR) / (ALT_km1 - ALT) * RHOVB * KVAR) -
+                    ((VAR - VAR_kp1) / (ALT - ALT_kp1) * RHOVB_kp1 * KVAR_kp1)) /
+                   ((ALTVB - ALTVB_kp1) * RHO));
+}
+
 // dyn_timestep.py:34-38
 DC_HD double euler_forward_pw(double VAR, double dVARdt, Div COLP, double COLP_OLD, double dt)
 {

@@ -41,8 +41,8 @@ class _Factory:
             self._table = _lib.field_table()
         stream = 0
         for n, t in fields.items():
-            if n not in self._table:
-                continue                      # coupling field: zero in the dry configuration
+            if t is None or n not in self._table:
+                continue       # coupling field of a grid without i_coupling: identically zero
             if not isinstance(t, torch.Tensor):
                 raise TypeError('field %s: target B200 needs the device tensor (F.device), got %s'
                                 % (n, type(t).__name__))
@@ -78,21 +78,26 @@ class TendencyFactory(_Factory):
             dUFLXdt=dUFLXdt, dVFLXdt=dVFLXdt, UWIND=UWIND, VWIND=VWIND, WWIND=WWIND, UFLX=UFLX,
             VFLX=VFLX, CFLX=CFLX, QFLX=QFLX, DFLX=DFLX, EFLX=EFLX, SFLX=SFLX, TFLX=TFLX,
             BFLX=BFLX, RFLX=RFLX, PHI=PHI, PHIVB=PHIVB, COLP=COLP, COLP_NEW=COLP_NEW, POTT=POTT,
-            PVTF=PVTF, PVTFVB=PVTFVB, WWIND_UWIND=WWIND_UWIND, WWIND_VWIND=WWIND_VWIND))
+            PVTF=PVTF, PVTFVB=PVTFVB, WWIND_UWIND=WWIND_UWIND, WWIND_VWIND=WWIND_VWIND,
+            KMOM_dUWINDdz=KMOM_dUWINDdz, KMOM_dVWINDdz=KMOM_dVWINDdz, KMOM=KMOM, RHOVB=RHOVB,
+            RHO=RHO, dUFLXdt_TURB=dUFLXdt_TURB, dVFLXdt_TURB=dVFLXdt_TURB, SMOMXFLX=SMOMXFLX,
+            SMOMYFLX=SMOMYFLX))
 
     def temperature(self, GRF, dPOTTdt, POTT, UFLX, VFLX, COLP, POTTVB, WWIND, COLP_NEW,
                     PHI=None, PHIVB=None, KHEAT=None, RHO=None, RHOVB=None, SSHFLX=None,
                     dPOTTdt_TURB=None, dPOTTdt_RAD=None):
         self._run('dc_temperature', dict(
             dPOTTdt=dPOTTdt, POTT=POTT, UFLX=UFLX, VFLX=VFLX, COLP=COLP, POTTVB=POTTVB,
-            WWIND=WWIND, COLP_NEW=COLP_NEW))
+            WWIND=WWIND, COLP_NEW=COLP_NEW, PHI=PHI, PHIVB=PHIVB, KHEAT=KHEAT, RHO=RHO,
+            RHOVB=RHOVB, SSHFLX=SSHFLX, dPOTTdt_TURB=dPOTTdt_TURB, dPOTTdt_RAD=dPOTTdt_RAD))
 
     def moisture(self, GRF, dQVdt, QV, dQCdt, QC, UFLX, VFLX, COLP, WWIND, COLP_NEW,
                  dQVdt_TURB=None, PHI=None, PHIVB=None, KHEAT=None, RHO=None, RHOVB=None,
                  SLHFLX=None):
         self._run('dc_moisture', dict(
             dQVdt=dQVdt, QV=QV, dQCdt=dQCdt, QC=QC, UFLX=UFLX, VFLX=VFLX, COLP=COLP,
-            WWIND=WWIND, COLP_NEW=COLP_NEW))
+            WWIND=WWIND, COLP_NEW=COLP_NEW, dQVdt_TURB=dQVdt_TURB, PHI=PHI, PHIVB=PHIVB,
+            KHEAT=KHEAT, RHO=RHO, RHOVB=RHOVB, SLHFLX=SLHFLX))
 
 
 class DiagnosticsFactory(_Factory):

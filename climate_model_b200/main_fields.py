@@ -3,8 +3,10 @@ in the reference layout (i, j, k) and device buffers in the B200 layout F[k][jd]
 (longitude fastest, see csrc/dc_geom.h), with the reference's get/set/copy API.
 
 Device buffers are torch tensors (PyTorch owns the memory); the C library only keeps their
-pointers.  Only the dyn-core fields have device buffers; the physics coupling fields exist
-on the host for API compatibility and must be zero (dry configuration).
+pointers.  Only the dyn-core fields have device buffers.  The physics coupling fields (KMOM,
+KHEAT, surface fluxes and the *_TURB tendencies) get device buffers when the grid was made
+with i_coupling=1; otherwise they exist on the host for API compatibility and must be zero
+(dry configuration).
 """
 import weakref
 
@@ -16,13 +18,7 @@ from .io_initial_conditions import initialize_fields
 from .io_read_namelist import B200, CPU, GPU, wp
 
 # host-only coupling / physics fields the reference's factories name (stgx, stgy, dimz)
-_HOST_ONLY = {
-    'PSURF': (0, 0, 1), 'KHEAT': (0, 0, 'nzs'), 'KMOM': (0, 0, 'nzs'),
-    'KMOM_dUWINDdz': (1, 0, 'nzs'), 'KMOM_dVWINDdz': (0, 1, 'nzs'),
-    'SMOMXFLX': (0, 0, 1), 'SMOMYFLX': (0, 0, 1), 'SSHFLX': (0, 0, 1), 'SLHFLX': (0, 0, 1),
-    'dPOTTdt_RAD': (0, 0, 'nz'), 'dUFLXdt_TURB': (1, 0, 'nz'), 'dVFLXdt_TURB': (0, 1, 'nz'),
-    'dPOTTdt_TURB': (0, 0, 'nz'), 'dQVdt_TURB': (0, 0, 'nz'),
-}
+_HOST_ONLY = {'PSURF': (0, 0, 1)}
 # device-buffer address -> Grid that owns the handle the buffer is bound to; lets the
 # factories keep the reference's signatures (which carry no grid object)
 OWNERS = weakref.WeakValueDictionary()
@@ -108,6 +104,8 @@ class ModelFields:
         L = _lib.lib()
         self.table = _lib.field_table()
         for n, (fid, sx, sy, nkk) in self.table.items():
+            if n in _lib.COUPLING_ONLY_FIELDS and not GR.i_coupling:
+                continue      # 8 more 3-D fields that the dry configuration never touches
             nk = {_lib.DC_NK_2D: 1, _lib.DC_NK_NZ: int(GR.nz), _lib.DC_NK_NZS: int(GR.nz) + 1}[nkk]
             t = torch.zeros((nk, GR.NJ, GR.NI), dtype=torch.float64, device=self.torch_device)
             self.device[n] = t

@@ -48,6 +48,10 @@ class Grid:
             'CFL', 'i_out_nth_hour', 'i_sim_n_days', 'i_restart_nth_day', 'pair_top',
             'POTT_dif_coef', 'moist_dif_coef', 'i_moist_main_switch')}
         P['UVFLX_dif_coef'] = None
+        # physics coupling terms of the dynamical core (turbulent transport with KMOM / KHEAT,
+        # surface fluxes): needed as soon as a physics module fills those fields; the
+        # reference always evaluates them (on zero fields when its physics is off)
+        P['i_coupling'] = int(bool(nl.i_turbulence or nl.i_surface_scheme))
         for k, v in overrides.items():
             if k not in P:
                 raise KeyError('unknown grid parameter %r' % k)
@@ -61,6 +65,10 @@ class Grid:
         self.params = P
         self.pair_top = P['pair_top']
         self.i_moist_main_switch = int(P['i_moist_main_switch'])
+        self.i_coupling = int(bool(P['i_coupling']))
+        if self.i_coupling and int(band[1]) > 1:
+            raise NotImplementedError('the physics coupling terms are not available with '
+                                      'latitude bands')
         self.band = (int(band[0]), int(band[1]))
         self._dc = None
         self._dc_device = None
@@ -245,7 +253,7 @@ class Grid:
             d = _lib.GridDesc(nx=int(self.nx), ny=int(self.ny), nz=int(self.nz),
                               j0=int(self.j0), j1=int(self.j1),
                               i_moist=self.i_moist_main_switch, dt=float(self.dt),
-                              pair_top=float(self.pair_top))
+                              pair_top=float(self.pair_top), i_coupling=self.i_coupling)
             self._keep = []
             for n in _lib.GRID_FIELDS_2D + _lib.GRID_FIELDS_1D:
                 a = np.ascontiguousarray(self.GRF[B200][n], dtype=np.float64)

@@ -68,6 +68,17 @@ typedef struct {
     const double *sigma_vb;  /* (nz+1)                                                   */
     const double *dsigma;    /* (nz)                                                     */
     const double *UVFLX_dif_coef, *POTT_dif_coef, *moist_dif_coef; /* (nz)               */
+    int i_coupling;          /* != 0: the physics coupling fields enter the tendencies:
+                                vertical turbulent transport of momentum / heat / moisture
+                                with KMOM, KHEAT (dyn_functions.py:26-67, :276-422,
+                                dyn_UFLX.py:136-170, dyn_VFLX.py:134-166) and the surface
+                                fluxes SMOMXFLX, SMOMYFLX, SSHFLX, SLHFLX.  The reference
+                                always evaluates these terms; with zero fields they are
+                                exactly 0, which is what i_coupling == 0 assumes.  The
+                                coupled terms run in the kernel decomposition
+                                (DC_MODE_KERNELS) on one device; RHO / RHOVB are the
+                                caller's (dc_secondary_diag once per time step, as
+                                solver.py:99-101).                                       */
 } dc_grid_desc;
 
 /* kind of vertical extent of a field (dc_field_info) */

@@ -706,6 +706,8 @@ void orc_temperature(const orc_grid *g, orc_fields *f)
                                        P[M(i, j - 1, k)], P[M(i, j + 1, k)], C[M2(i, j)],
                                        C[M2(i - 1, j)], C[M2(i + 1, j)], C[M2(i, j - 1)],
                                        C[M2(i, j + 1)], g->POTT_dif_coef[k]);
+                if (g->i_coupling) /* dyn_POTT.py:40-41, :107-108 (radiation_py) */
+                    d = d + (f->dPOTTdt_RAD[M(i, j, k)] * C[M2(i, j)]);
                 f->dPOTTdt[M(i, j, k)] = d;
             }
 }

@@ -71,6 +71,8 @@ typedef struct {
     double *KMOM, *KHEAT, *SMOMXFLX, *SMOMYFLX, *SSHFLX, *SLHFLX;
     double *KMOM_dUWINDdz, *KMOM_dVWINDdz;
     double *dUFLXdt_TURB, *dVFLXdt_TURB, *dPOTTdt_TURB, *dQVdt_TURB;
+    /* radiative heating rate [K s-1], input from the radiation module (dyn_POTT.py:107-108) */
+    double *dPOTTdt_RAD;
 } orc_fields;
 
 /* misc_boundaries.py:22-42 ; (fnx,fny,fnz) = shape of FIELD */

@@ -43,7 +43,7 @@ FIELDS = {
     'SSHFLX': (0, 0, 1), 'SLHFLX': (0, 0, 1),
     'KMOM_dUWINDdz': (1, 0, 'nzs'), 'KMOM_dVWINDdz': (0, 1, 'nzs'),
     'dUFLXdt_TURB': (1, 0, 'nz'), 'dVFLXdt_TURB': (0, 1, 'nz'), 'dPOTTdt_TURB': (0, 0, 'nz'),
-    'dQVdt_TURB': (0, 0, 'nz'),
+    'dQVdt_TURB': (0, 0, 'nz'), 'dPOTTdt_RAD': (0, 0, 'nz'),
 }
 
 _dp = ctypes.POINTER(ctypes.c_double)

@@ -93,7 +93,7 @@ def sub1(text, pattern, repl, count=0, must=True):
     return new
 
 
-def prepare_scratch(grid):
+def prepare_scratch(grid, coupling=False):
     """copy reference *.py + data/ to a scratch dir and apply shims/patches"""
     d = tempfile.mkdtemp(prefix='cm_ref_')
     for f in os.listdir(REF):
@@ -149,6 +149,16 @@ def prepare_scratch(grid):
         if key in grid:
             t = sub1(t, r'^%s\s*=.*$' % key, '%s = %r' % (key, grid[key]))
     open(p, 'w').write(t)
+
+    if coupling:
+        # (7) io_read_namelist.py:66-67 switches the radiative-heating term of dyn_POTT.py
+        # (:107-108) off when the radiation MODULE is off; the coupling fixture feeds the
+        # dynamical core a seeded dPOTTdt_RAD directly, so the term is kept compiled in,
+        # exactly as it is when i_radiation = 1
+        p = os.path.join(d, 'io_read_namelist.py')
+        t = open(p).read()
+        t = sub1(t, r'^if i_POTT_radiation and not i_radiation:$', 'if False:')
+        open(p, 'w').write(t)
     return d
 
 
@@ -200,7 +210,7 @@ def main():
     ap.add_argument('--minimal', action='store_true',
                     help='dump only grid, inputs and prognostic states (small fixture)')
     ap.add_argument('--coupling', action='store_true',
-                    help='fill the physics coupling fields (KMOM, KHEAT, surface fluxes) with '
+                    help='fill the physics coupling fields (KMOM, KHEAT, surface fluxes, dPOTTdt_RAD) with '
                          'seeded random values instead of zeros: exercises the turbulence / '
                          'surface-flux terms of the dynamical core')
     ap.add_argument('--dump-diag', action='store_true',
@@ -209,7 +219,7 @@ def main():
 
     import numpy as np
     grid = GRIDS[args.grid]
-    d = prepare_scratch(grid)
+    d = prepare_scratch(grid, coupling=args.coupling)
     os.chdir(d)
     sys.path.insert(0, d)
     import _interp2d_shim  # noqa: F401  (must precede io_initial_conditions import)
@@ -230,7 +240,8 @@ def main():
         rng = np.random.default_rng(2024)
         for n, (lo, hi) in (('KMOM', (0.01, 0.2)), ('KHEAT', (0.05, 2.)),
                             ('SMOMXFLX', (-0.02, 0.02)), ('SMOMYFLX', (-0.02, 0.02)),
-                            ('SSHFLX', (-5., 15.)), ('SLHFLX', (-5., 20.))):
+                            ('SSHFLX', (-5., 15.)), ('SLHFLX', (-5., 20.)),
+                            ('dPOTTdt_RAD', (-2e-5, 2e-5))):
             F.host[n][:] = rng.uniform(lo, hi, size=F.host[n].shape)
     Diagnostics = DiagnosticsFactory(target=CPU)
 

@@ -23,7 +23,7 @@ def golden_dims(g):
     return nx, ny, nz, dt
 
 
-COUPLING = ['KMOM', 'KHEAT', 'SMOMXFLX', 'SMOMYFLX', 'SSHFLX', 'SLHFLX']
+COUPLING = ['KMOM', 'KHEAT', 'SMOMXFLX', 'SMOMYFLX', 'SSHFLX', 'SLHFLX', 'dPOTTdt_RAD']
 
 
 def oracle_from_golden(g, i_moist=True):
@@ -93,6 +93,8 @@ def grid_from_golden(g, band=(0, 1), **kw):
     nx, ny, nz, dt = golden_dims(g)
     arrays = {n: g['GR_' + n] for n in GRID_FIELDS}
     arrays.update(nx=nx, ny=ny, nz=nz, dt=dt)
+    if 'IN_KMOM' in g:          # fixture with non-zero physics coupling fields
+        kw.setdefault('i_coupling', 1)
     return Grid(band=band, from_arrays=arrays, **kw)
 
 
@@ -101,6 +103,8 @@ def fields_from_golden(GR, g, prefix='IN_', names=('HSURF',) + tuple(STATE)):
     WWIND / POTTVB zero as io_initial_conditions.py:45-46 leaves them"""
     from climate_model_b200.main_fields import ModelFields
     F = ModelFields(GR, gpu_enable=True, initialize=False)
+    if GR.i_coupling and prefix + 'KMOM' in g:
+        names = tuple(names) + tuple(COUPLING)
     for n in names:
         F.host[n][...] = g[prefix + n]
     F.host['WWIND'][...] = 0.

@@ -366,3 +366,131 @@ def test_run_diagnostics_on_device_match_reference_formulas(g10):
     F.device['UWIND'][1, GR.jshift + 3, 5] = float('nan')
     with pytest.raises(ValueError, match='MODEL CRASH'):
         print_ts_info(GR, F, force=True)
+
+
+# ---------------------------------------------------------------------------------------
+# physics coupling terms: NON-ZERO KMOM / KHEAT / surface fluxes / dPOTTdt_RAD,
+# compared with the REAL reference's outputs (tests/golden/ref_10deg_coupled.npz)
+# ---------------------------------------------------------------------------------------
+@pytest.fixture(scope='module')
+def gc():
+    return load_golden('ref_10deg_coupled.npz')
+
+
+def _coupled_setup(gc):
+    from climate_model_b200.dyn_matsuno import Diagnostics
+    from climate_model_b200.io_read_namelist import B200
+    GR = grid_from_golden(gc)
+    assert GR.i_coupling == 1
+    F = fields_from_golden(GR, gc)
+    assert 'KMOM' in F.device and 'dPOTTdt_RAD' in F.device
+    Diagnostics.primary_diag(GR.GRF[B200], **F.get(Diagnostics.fields_primary_diag, target=B200))
+    return GR, F
+
+
+def test_coupled_factories_stage1_bit_exact(gc):
+    """compute_tendencies through the factories (= dc_continuity / dc_momentum /
+    dc_temperature / dc_moisture) with the coupling fields bound"""
+    from climate_model_b200.dyn_matsuno import Diagnostics
+    from climate_model_b200.dyn_tendencies import compute_tendencies
+    from climate_model_b200.io_read_namelist import B200
+    nx, ny, nz, _ = golden_dims(gc)
+    GR, F = _coupled_setup(gc)
+    Diagnostics.secondary_diag(**F.get(Diagnostics.fields_secondary_diag, target=B200))
+    F.device['COLP_OLD'].copy_(F.device['COLP'])
+    compute_tendencies(GR, F)
+    F.copy_device_to_host(GR, F.ALL_FIELDS)
+    box = lambda i1, j1, j0=1: (slice(1, i1 + 1), slice(j0, j1 + 1), slice(None))
+    ranges = {
+        'KMOM_dUWINDdz': box(nx + 1, ny), 'KMOM_dVWINDdz': box(nx, ny + 1),
+        'dUFLXdt_TURB': box(nx, ny), 'dVFLXdt_TURB': box(nx, ny, 2),
+        'dPOTTdt_TURB': box(nx, ny), 'dQVdt_TURB': box(nx, ny),
+        'dUFLXdt': box(nx, ny), 'dVFLXdt': box(nx, ny, 2), 'dPOTTdt': box(nx, ny),
+        'dQVdt': box(nx, ny), 'dQCdt': box(nx, ny),
+    }
+    for n, sl in ranges.items():
+        _eq(F.host[n][sl], gc['S1_' + n][sl], n)
+    # the exchange_BC images of the factory (dyn_org_discretizations.py:121-249)
+    for n in ['KMOM', 'SMOMXFLX', 'SMOMYFLX']:
+        a = F.host[n]
+        _eq(a[0], a[nx], n + ' x image')
+        _eq(a[:, 0], a[:, 1], n + ' y image')
+    GR.close()
+
+
+@pytest.mark.parametrize('mode', ['fused', 'kernels'])
+def test_coupled_step_matsuno_against_reference_golden(gc, mode):
+    """secondary_diag + step_matsuno as the reference's time loop (solver.py:99-101, :70-73);
+    a handle with i_coupling steps through the kernel decomposition whatever the mode"""
+    from climate_model_b200.dyn_matsuno import Diagnostics, set_mode, step_matsuno
+    from climate_model_b200.io_read_namelist import B200
+    GR, F = _coupled_setup(gc)
+    set_mode(GR, mode)
+    for ts in range(1, 11):
+        Diagnostics.secondary_diag(**F.get(Diagnostics.fields_secondary_diag, target=B200))
+        step_matsuno(GR, F)
+        if ts in (1, 2, 10):
+            F.copy_device_to_host(GR, F.PROGNOSTIC_FIELDS)
+            for n in STATE:
+                _eq(F.host[n], gc['N%d_%s' % (ts, n)], 'N%d %s' % (ts, n))
+    GR.close()
+
+
+def test_coupled_fast_math_mode_within_tolerance(gc):
+    from helpers import TOL, state_err
+    from climate_model_b200 import _lib
+    from climate_model_b200.dyn_matsuno import Diagnostics, step_matsuno
+    from climate_model_b200.io_read_namelist import B200
+    strict = _lib.library_path()
+    _lib.use_library(build_emu(fast=True))
+    try:
+        GR, F = _coupled_setup(gc)
+        for ts in range(1, 11):
+            Diagnostics.secondary_diag(**F.get(Diagnostics.fields_secondary_diag, target=B200))
+            step_matsuno(GR, F)
+        F.copy_device_to_host(GR, F.PROGNOSTIC_FIELDS)
+        ref = {n: gc['N10_' + n] for n in STATE}
+        for n in STATE:
+            e = state_err(n, F.host, ref)
+            assert e <= TOL[n], 'N10 %s: %.3e > %.0e' % (n, e, TOL[n])
+        GR.close()
+    finally:
+        _lib.use_library(strict)
+
+
+def test_coupled_zero_fields_equal_the_dry_path(g10):
+    """i_coupling with all coupling fields zero reproduces the dry configuration bit for bit
+    (what the reference computes when its physics modules are off)"""
+    from climate_model_b200.dyn_matsuno import Diagnostics, set_mode, step_matsuno
+    from climate_model_b200.io_read_namelist import B200
+    out = []
+    for cpl in (0, 1):
+        GR = grid_from_golden(g10, i_coupling=cpl)
+        F = fields_from_golden(GR, g10)
+        set_mode(GR, 'kernels')
+        Diagnostics.primary_diag(GR.GRF[B200],
+                                 **F.get(Diagnostics.fields_primary_diag, target=B200))
+        for _ in range(2):
+            Diagnostics.secondary_diag(**F.get(Diagnostics.fields_secondary_diag, target=B200))
+            step_matsuno(GR, F)
+        F.copy_device_to_host(GR, F.PROGNOSTIC_FIELDS)
+        out.append({n: F.host[n].copy() for n in STATE})
+        GR.close()
+    for n in STATE:
+        _eq(out[0][n], out[1][n], n)
+
+
+def test_coupled_errors_are_loud(gc):
+    from climate_model_b200 import _lib
+    from climate_model_b200.main_grid import Grid
+    GR, F = _coupled_setup(gc)
+    L = _lib.lib()
+    with pytest.raises(_lib.DyncoreError, match='kernel decomposition'):
+        _lib.check(L.dc_stage_compute(GR.dyncore(), 0, _lib.DC_PART_ALL, 0))
+    # a coupling field that was never bound
+    _lib.check(L.dc_bind_field(GR.dyncore(), F.table['KHEAT'][0], 0, 0))
+    with pytest.raises(_lib.DyncoreError, match='KHEAT is not bound'):
+        _lib.check(L.dc_temperature(GR.dyncore(), 0))
+    with pytest.raises(NotImplementedError, match='latitude bands'):
+        Grid(band=(0, 2), i_coupling=1)
+    GR.close()

@@ -340,3 +340,65 @@ def test_run_diagnostics_on_device(g10):
     F.device['UWIND'][3, js + 7, 11] = float('nan')
     with pytest.raises(ValueError, match='MODEL CRASH'):
         print_ts_info(GR, F, force=True)
+
+
+# ---------------------------------------------------------------------------------------
+# physics coupling terms with NON-ZERO KMOM / KHEAT / surface fluxes /
+# dPOTTdt_RAD against the REAL reference's outputs (tests/golden/ref_10deg_coupled.npz)
+# ---------------------------------------------------------------------------------------
+@pytest.fixture(scope='module')
+def gc():
+    return load_golden('ref_10deg_coupled.npz')
+
+
+def test_coupled_kernels_bit_exact_given_oracle_diagnostics(gc, strict_library):
+    """STRICT build: with the oracle's primary and secondary diagnostics on the device (no
+    pow involved), the turbulence / surface-flux / radiation terms and the tendencies that
+    contain them reproduce the reference's stage-1 fields bit for bit"""
+    from climate_model_b200.dyn_tendencies import compute_tendencies
+    nx, ny, nz, _ = golden_dims(gc)
+    GR = grid_from_golden(gc)
+    F = fields_from_golden(GR, gc)
+    O = oracle_from_golden(gc)
+    O.primary_diag()
+    O.secondary_diag()
+    for n in ['PVTF', 'PVTFVB', 'PHI', 'PHIVB', 'POTTVB', 'RHO', 'RHOVB']:
+        F.host[n][...] = O.F[n]
+        F.to_device(GR, n)
+    F.device['COLP_OLD'].copy_(F.device['COLP'])
+    compute_tendencies(GR, F)
+    F.copy_device_to_host(GR, F.ALL_FIELDS)
+    box = lambda i1, j1, j0=1: (slice(1, i1 + 1), slice(j0, j1 + 1), slice(None))
+    exact = {
+        'KMOM_dUWINDdz': box(nx + 1, ny), 'KMOM_dVWINDdz': box(nx, ny + 1),
+        'dUFLXdt_TURB': box(nx, ny), 'dVFLXdt_TURB': box(nx, ny, 2),
+        'dPOTTdt_TURB': box(nx, ny), 'dUFLXdt': box(nx, ny), 'dVFLXdt': box(nx, ny, 2),
+        'dPOTTdt': box(nx, ny),
+    }
+    for n, sl in exact.items():
+        _eq(F.host[n][sl], gc['S1_' + n][sl], n)
+    for n in ['dQVdt_TURB', 'dQVdt', 'dQCdt']:     # device log() vs glibc log() in dQ*dt
+        assert rel_err(F.host[n][box(nx, ny)], gc['S1_' + n][box(nx, ny)]) <= 1e-12, n
+    assert np.nanmax(np.abs(gc['S1_dUFLXdt_TURB'])) > 1e-2 * np.nanmax(np.abs(gc['S1_dUFLXdt']))
+
+
+@pytest.mark.parametrize('build', ['production', 'strict'])
+def test_coupled_step_matsuno_against_reference_golden(gc, build, request):
+    """secondary_diag + step_matsuno as the reference's time loop (solver.py:99-101, :70-73),
+    10 steps, both arithmetic modes, parity tolerances"""
+    from climate_model_b200.dyn_matsuno import Diagnostics, step_matsuno
+    from climate_model_b200.io_read_namelist import B200
+    if build == 'strict':
+        request.getfixturevalue('strict_library')
+    GR = grid_from_golden(gc)
+    F = fields_from_golden(GR, gc)
+    _diag(GR, F)
+    for ts in range(1, 11):
+        Diagnostics.secondary_diag(**F.get(Diagnostics.fields_secondary_diag, target=B200))
+        step_matsuno(GR, F)
+        if ts in (1, 2, 10):
+            F.copy_device_to_host(GR, F.PROGNOSTIC_FIELDS)
+            ref = {n: gc['N%d_%s' % (ts, n)] for n in STATE}
+            for n in STATE:
+                e = state_err(n, F.host, ref)
+                assert e <= TOL[n], 'N%d %s: %.3e > %.0e' % (ts, n, e, TOL[n])
