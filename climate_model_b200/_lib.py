@@ -45,7 +45,8 @@ _lib = None
 _lib_path = None
 
 _ENTRIES = ['dc_continuity', 'dc_momentum', 'dc_temperature', 'dc_moisture',
-            'dc_compute_tendencies', 'dc_euler_forward', 'dc_primary_diag', 'dc_secondary_diag']
+            'dc_compute_tendencies', 'dc_euler_forward', 'dc_primary_diag', 'dc_secondary_diag',
+            'dc_compute_turbulence']
 
 
 def _declare(lib):

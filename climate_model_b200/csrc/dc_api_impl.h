@@ -801,6 +801,21 @@ int dc_secondary_diag(dc_handle *h, void *stream)
     return backend_status("dc_secondary_diag");
 }
 
+int dc_compute_turbulence(dc_handle *h, void *stream)
+{
+    DC_ENTRY_CHECK("dc_compute_turbulence");
+    int rc;
+    if ((rc = need(h, "dc_compute_turbulence", {F_KMOM, F_KHEAT, F_PHIVB, F_HSURF, F_PHI, F_QV,
+                                                F_WINDX, F_WINDY, F_POTTVB, F_POTT})))
+        return rc;
+    if ((rc = refresh_diag(h, "dc_compute_turbulence", stream))) return rc;   // PHIVB
+    const Fields &f = h->f;
+    TurbulenceBody b{h->g,    f.PHIVB,  f.HSURF, f.PHI,  f.QV,   f.WINDX,
+                     f.WINDY, f.POTTVB, f.POTT,  f.KMOM, f.KHEAT};
+    launch(h, "turbulence", b, 0, h->g.nx + 1, 0, h->g.ny + 1, stream);
+    return backend_status("dc_compute_turbulence");
+}
+
 int dc_run_diag_bytes(const dc_handle *h, size_t *nbytes)
 {
     if (!h || !nbytes) return fail(DC_ERR_ARG, "dc_run_diag_bytes: NULL argument");

@@ -862,6 +862,56 @@ struct SecondaryDiagBody {
 };
 
 // ---------------------------------------------------------------------------------------
+// turbulence module: turb_compute.py:190-204 (launcher) + :53-145 (bulk_richardson_py,
+// compute_K_coefs_py, run_all_py) + misc_meteo_utilities.py:36-49.  KMOM / KHEAT from the
+// bulk Richardson number and a Blackadar mixing length on the interior interfaces
+// k in [1, nz-1] of every column incl. the halo.  threads: i in [0, nx+1], j in [0, ny+1]
+// Mind the launcher's argument mapping: "PHI_k" = PHIVB[k], "POTT_k" = POTTVB[k], km05 = the
+// full level above the interface (k-1), kp05 = the full level below it (k).
+// 10 field accesses per interface; the full-level values of level k are kept for k+1.
+// ---------------------------------------------------------------------------------------
+struct TurbulenceBody {
+    Geom g;
+    const double *PHIVB, *HSURF, *PHI, *QV, *WINDX, *WINDY, *POTTVB, *POTT;
+    double *KMOM, *KHEAT;
+    DC_HD void operator()(int i, int j) const
+    {
+        const double Ri_c = 1.0, free_mix_len = 200., con_k = 0.35, con_Pr = 0.72;
+        const double min_wind_diff = 0.0001, min_KMOM = 0.000001, max_KMOM = 0.01;
+        const int nz = g.nz;
+        const double hsurf = HSURF[g.idx2(i, j)];
+        double phi_m = PHI[g.idx(i, j, 0)], qv_m = QV[g.idx(i, j, 0)], wx_m = WINDX[g.idx(i, j, 0)],
+               wy_m = WINDY[g.idx(i, j, 0)], pott_m = POTT[g.idx(i, j, 0)];
+        for (int k = 1; k < nz; k++) {
+            const double phi_p = PHI[g.idx(i, j, k)], qv_p = QV[g.idx(i, j, k)],
+                         wx_p = WINDX[g.idx(i, j, k)], wy_p = WINDY[g.idx(i, j, k)],
+                         pott_p = POTT[g.idx(i, j, k)];
+            double WINDX_km05 = wx_m, WINDY_km05 = wy_m;
+            if (WINDX_km05 == wx_p) WINDX_km05 += min_wind_diff;
+            if (WINDY_km05 == wy_p) WINDY_km05 += min_wind_diff;
+            const double ALT_k = PHIVB[g.idx(i, j, k)] / con_g;
+            const double ALT_km05 = phi_m / con_g, ALT_kp05 = phi_p / con_g;
+            const double HGT_k = ALT_k - hsurf;
+            const double mix_len = con_k * HGT_k / (1. + con_k * HGT_k / free_mix_len);
+            const double QV_k = comp_VARVB_log(qv_p, qv_m);
+            const double POTT_v_k = POTTVB[g.idx(i, j, k)] * (1. + QV_k / 0.622) / (1. + QV_k);
+            const double dx = WINDX_km05 - wx_p, dy = WINDY_km05 - wy_p;
+            const double dalt = ALT_km05 - ALT_kp05;
+            const double Ri_b_k =
+                ((con_g / POTT_v_k * (pott_m - pott_p) * dalt) / (dx * dx + dy * dy));
+            const double sx = dx / dalt, sy = dy / dalt;
+            const double shear_term = sqrt(sx * sx + sy * sy);
+            double KMOM_k = mix_len * mix_len * shear_term * (Ri_c - Ri_b_k) / Ri_c;
+            if (KMOM_k < min_KMOM) KMOM_k = min_KMOM;
+            if (KMOM_k > max_KMOM) KMOM_k = max_KMOM;
+            KMOM[g.idx(i, j, k)] = KMOM_k;
+            KHEAT[g.idx(i, j, k)] = KMOM_k / con_Pr;
+            phi_m = phi_p; qv_m = qv_p; wx_m = wx_p; wy_m = wy_p; pott_m = pott_p;
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------
 // run-time diagnostics on the device (io_functions.py:70-114: diagnose_print_diag_fields and
 // the crash check of print_ts_info): vmax, mass-weighted mean wind and potential temperature,
 // area-weighted mean column pressure, NaN / over-speed check of UWIND.  The reference copies

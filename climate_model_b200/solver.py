@@ -6,8 +6,10 @@ Builds Grid and ModelFields from the namelist (plus `name=value` overrides of gr
 condition parameters), runs one primary_diag, then per time step: print-diagnostics every
 `nth_ts_print_diag` steps (vmax, mean wind / temperature / COLP, NaN / over-speed crash check,
 reference io_functions.py:70-114, reduced on the device: io_functions.py), secondary_diag,
-step_matsuno -- all on the device.  The physics
-modules, NetCDF output and restart files of the reference are out of scope.
+turbulence (KMOM / KHEAT, with `i_turbulence=1`: turb_main.py; the grid is then made with
+i_coupling=1 and the step runs the kernel decomposition with the turbulent-transport terms),
+step_matsuno -- all on the device.  The other physics modules (surface, radiation,
+microphysics) of the reference are out of scope.
 """
 import argparse
 import time
@@ -23,14 +25,20 @@ from .main_fields import ModelFields
 from .main_grid import Grid
 
 GRID_KEYS = ('nz', 'lat0_deg', 'lat1_deg', 'dlat_deg', 'dlon_deg', 'i_out_nth_hour',
-             'i_sim_n_days', 'CFL', 'pair_top', 'i_moist_main_switch')
+             'i_sim_n_days', 'CFL', 'pair_top', 'i_moist_main_switch', 'i_coupling')
 
 
-def run(nsteps=None, verbose=True, ic=None, **overrides):
+def run(nsteps=None, verbose=True, ic=None, i_turbulence=None, **overrides):
     """returns (GR, F) after the run; `overrides`: grid parameters, `ic`: initial-condition
-    parameters (initialize_fields)"""
+    parameters (initialize_fields); `i_turbulence`: namelist.i_turbulence override"""
+    i_turbulence = int(nl.i_turbulence if i_turbulence is None else i_turbulence)
+    if i_turbulence:
+        overrides.setdefault('i_coupling', 1)
     GR = Grid(**{k: v for k, v in overrides.items() if k in GRID_KEYS})
     F = ModelFields(GR, **(ic or {}))
+    if i_turbulence:
+        from .turb_main import Turbulence
+        F.TURB = Turbulence(GR, target=B200)      # main_fields.py:84-86
     Diagnostics.primary_diag(GR.GRF[B200], **F.get(Diagnostics.fields_primary_diag, target=B200))
     nts = int(GR.nts) if nsteps is None else int(nsteps)
     t0 = time.time()
@@ -43,6 +51,10 @@ def run(nsteps=None, verbose=True, ic=None, **overrides):
         GR.timer.start('diag')
         Diagnostics.secondary_diag(**F.get(Diagnostics.fields_secondary_diag, target=B200))
         GR.timer.stop('diag')
+        if i_turbulence:                          # solver.py:106-112
+            GR.timer.start('turb')
+            F.TURB.compute_turbulence(GR, **F.get(F.TURB.fields_main, target=B200))
+            GR.timer.stop('turb')
         step_matsuno(GR, F)
         GR.timer.stop('total')
     if F.torch_device.type == 'cuda':
@@ -65,7 +77,8 @@ def main():
     ov, ic = {}, {}
     for s in a.overrides:
         k, v = s.split('=', 1)
-        (ov if k in GRID_KEYS else ic)[k] = float(v) if '.' in v or 'e' in v.lower() else int(v)
+        v = float(v) if '.' in v or 'e' in v.lower() else int(v)
+        (ov if k in GRID_KEYS or k == 'i_turbulence' else ic)[k] = v
     run(nsteps=a.nsteps, ic=ic, **ov)
 
 

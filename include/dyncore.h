@@ -123,6 +123,10 @@ int dc_euler_forward(dc_handle *h, void *stream);
 int dc_primary_diag(dc_handle *h, void *stream);
 /* DiagnosticsFactory.secondary_diag (:329-346)                                          */
 int dc_secondary_diag(dc_handle *h, void *stream);
+/* Turbulence.compute_turbulence (turb_main.py:38-50, turb_compute.py:53-204): KMOM, KHEAT
+ * on the interior interfaces from PHIVB, HSURF, PHI, QV, WINDX, WINDY, POTTVB, POTT (call
+ * after dc_secondary_diag, as solver.py:99-112); feeds the i_coupling terms               */
+int dc_compute_turbulence(dc_handle *h, void *stream);
 /* misc_boundaries.exchange_BC (misc_boundaries.py:22-42) on one bound field             */
 int dc_exchange_bc(dc_handle *h, int field_id, void *stream);
 

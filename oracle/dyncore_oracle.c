@@ -945,6 +945,46 @@ void orc_secondary_diag(const orc_grid *g, orc_fields *f)
         }
 }
 
+/* turb_compute.py:190-204 (launch_numba_cpu) + :53-145 (bulk_richardson_py, compute_K_coefs_py,
+ * run_all_py) + misc_meteo_utilities.py:36-49 (calc_virtual_temperature_py): the reference's
+ * turbulence module, KMOM / KHEAT on the interior interfaces of every column incl. the halo.
+ * Mind the launcher's argument mapping: "PHI_k" = PHIVB[k], "POTT_k" = POTTVB[k], km05 = the
+ * full level above the interface (k-1), kp05 = the full level below it (k). */
+void orc_compute_turbulence(const orc_grid *g, orc_fields *f)
+{
+    const int nx = g->nx, ny = g->ny, nz = g->nz;
+    const double Ri_c = 1.0, free_mix_len = 200., con_k = 0.35, con_Pr = 0.72;
+    const double min_wind_diff = 0.0001, min_KMOM = 0.000001, max_KMOM = 0.01;
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < nx + 2; i++)
+        for (int j = 0; j < ny + 2; j++)
+            for (int k = 1; k < nz; k++) {
+                double WINDX_km05 = f->WINDX[M(i, j, k - 1)], WINDX_kp05 = f->WINDX[M(i, j, k)];
+                double WINDY_km05 = f->WINDY[M(i, j, k - 1)], WINDY_kp05 = f->WINDY[M(i, j, k)];
+                if (WINDX_km05 == WINDX_kp05) WINDX_km05 += min_wind_diff;
+                if (WINDY_km05 == WINDY_kp05) WINDY_km05 += min_wind_diff;
+                const double ALT_k = f->PHIVB[MS(i, j, k)] / con_g;
+                const double ALT_km05 = f->PHI[M(i, j, k - 1)] / con_g;
+                const double ALT_kp05 = f->PHI[M(i, j, k)] / con_g;
+                const double HGT_k = ALT_k - f->HSURF[M2(i, j)];
+                const double mix_len = con_k * HGT_k / (1. + con_k * HGT_k / free_mix_len);
+                const double QV_k = comp_VARVB_log(f->QV[M(i, j, k)], f->QV[M(i, j, k - 1)]);
+                const double POTT_v_k = f->POTTVB[MS(i, j, k)] * (1. + QV_k / 0.622) / (1. + QV_k);
+                const double dx = WINDX_km05 - WINDX_kp05, dy = WINDY_km05 - WINDY_kp05;
+                const double dalt = ALT_km05 - ALT_kp05;
+                const double Ri_b_k =
+                    ((con_g / POTT_v_k * (f->POTT[M(i, j, k - 1)] - f->POTT[M(i, j, k)]) * dalt) /
+                     (dx * dx + dy * dy));
+                const double sx = dx / dalt, sy = dy / dalt;
+                const double shear_term = sqrt(sx * sx + sy * sy);
+                double KMOM_k = mix_len * mix_len * shear_term * (Ri_c - Ri_b_k) / Ri_c;
+                if (KMOM_k < min_KMOM) KMOM_k = min_KMOM;
+                if (KMOM_k > max_KMOM) KMOM_k = max_KMOM;
+                f->KMOM[MS(i, j, k)] = KMOM_k;
+                f->KHEAT[MS(i, j, k)] = KMOM_k / con_Pr;
+            }
+}
+
 /* dyn_matsuno.py:28-129 (step_matsuno, i_comp_mode == 1) */
 void orc_step_matsuno(const orc_grid *g, orc_fields *f)
 {

@@ -94,6 +94,8 @@ void orc_euler_forward(const orc_grid *g, orc_fields *f);
 void orc_primary_diag(const orc_grid *g, orc_fields *f);
 /* dyn_diagnostics.py:199-222 */
 void orc_secondary_diag(const orc_grid *g, orc_fields *f);
+/* turb_main.py:38-50 / turb_compute.py:190-204: KMOM, KHEAT (the reference's turbulence module) */
+void orc_compute_turbulence(const orc_grid *g, orc_fields *f);
 /* dyn_matsuno.py:28-129 */
 void orc_step_matsuno(const orc_grid *g, orc_fields *f);
 

@@ -75,7 +75,7 @@ def lib():
         _LIB = ctypes.CDLL(build())
         for fn in ('orc_continuity', 'orc_momentum', 'orc_temperature', 'orc_moisture',
                    'orc_compute_tendencies', 'orc_euler_forward', 'orc_primary_diag',
-                   'orc_secondary_diag', 'orc_step_matsuno'):
+                   'orc_secondary_diag', 'orc_step_matsuno', 'orc_compute_turbulence'):
             getattr(_LIB, fn).argtypes = [ctypes.POINTER(_Grid), ctypes.POINTER(_Fields)]
             getattr(_LIB, fn).restype = None
         _LIB.orc_num_threads.restype = ctypes.c_int
@@ -140,6 +140,9 @@ class Oracle:
 
     def secondary_diag(self):
         self._call('orc_secondary_diag')
+
+    def compute_turbulence(self):
+        self._call('orc_compute_turbulence')
 
     def step_matsuno(self, nsteps=1):
         for _ in range(nsteps):

@@ -213,6 +213,11 @@ def main():
                     help='fill the physics coupling fields (KMOM, KHEAT, surface fluxes, dPOTTdt_RAD) with '
                          'seeded random values instead of zeros: exercises the turbulence / '
                          'surface-flux terms of the dynamical core')
+    ap.add_argument('--turbulence', action='store_true',
+                    help='run the reference turbulence module (turb_compute.py: KMOM, KHEAT from '
+                         'the bulk Richardson number) after secondary_diag in every time step, as '
+                         'solver.py:106-112 does with i_turbulence = 1; dumps KMOM / KHEAT of '
+                         'the first call')
     ap.add_argument('--dump-diag', action='store_true',
                     help='also dump the primary diagnostics and WWIND after each step count')
     args = ap.parse_args()
@@ -244,6 +249,18 @@ def main():
                             ('dPOTTdt_RAD', (-2e-5, 2e-5))):
             F.host[n][:] = rng.uniform(lo, hi, size=F.host[n].shape)
     Diagnostics = DiagnosticsFactory(target=CPU)
+    if args.turbulence:
+        from turb_compute import compute_turbulence_cpu
+        TURB_FIELDS = ['KMOM', 'KHEAT', 'PHIVB', 'HSURF', 'PHI', 'QV', 'WINDX', 'WINDY',
+                       'POTTVB', 'POTT']          # turb_main.py:41-42
+
+    if args.turbulence:
+        # The module clamps KMOM to [1e-6, 0.01] and the default initial state is so stably
+        # stratified that every value sits on the lower clamp.  Compress the vertical
+        # potential-temperature gradient (x 0.02 around the lowest level) so that the bulk
+        # Richardson number straddles its critical value and both clamps occur.
+        P = F.host['POTT']
+        P[:] = P[:, :, -1:] + 0.02 * (P - P[:, :, -1:])
 
     if args.perturb_ulp:
         rng = np.random.default_rng(12345)
@@ -277,6 +294,32 @@ def main():
         for n in ('RHO', 'RHOVB', 'TAIR', 'PAIR', 'WIND'):
             out['IN_' + n] = F.host[n].copy()
 
+    if args.turbulence:
+        compute_turbulence_cpu(*[F.host[n] for n in TURB_FIELDS])
+        out['T1_KMOM'] = F.host['KMOM'].copy()
+        out['T1_KHEAT'] = F.host['KHEAT'].copy()
+        # known-answer vectors of the kernel itself: seeded synthetic inputs a few
+        # centimetres above the surface with metre-scale layers, where the mixing length is
+        # small enough for KMOM to fall BETWEEN the clamps (it never does on model states)
+        rng = np.random.default_rng(77)
+        kat = {n: np.full_like(F.host[n], np.nan) for n in TURB_FIELDS}
+        shp, shps = F.host['PHI'].shape, F.host['PHIVB'].shape
+        kat['HSURF'] = rng.uniform(0., 2000., size=F.host['HSURF'].shape)
+        kat['PHIVB'] = 9.81 * (kat['HSURF'] + rng.uniform(0.01, 0.08, size=shps))
+        kat['PHI'] = 9.81 * (kat['HSURF'] + np.cumsum(rng.uniform(0.5, 2., size=shp)[:, :, ::-1],
+                                                       axis=2)[:, :, ::-1])
+        kat['QV'] = rng.uniform(0., 0.02, size=shp)
+        kat['QV'][::3, ::2, 1] = kat['QV'][::3, ::2, 2]          # equal-argument branch of the log mean
+        kat['WINDX'] = rng.uniform(-3., 3., size=shp)
+        kat['WINDY'] = rng.uniform(-3., 3., size=shp)
+        kat['WINDX'][::2, ::3, 3] = kat['WINDX'][::2, ::3, 2]    # min_wind_diff branch
+        kat['WINDY'][1::4, :, 1] = kat['WINDY'][1::4, :, 0]
+        kat['POTT'] = rng.uniform(280., 320., size=shp)
+        kat['POTTVB'] = rng.uniform(280., 320., size=shps)
+        compute_turbulence_cpu(*[kat[n] for n in TURB_FIELDS])
+        for n in TURB_FIELDS:
+            out['KAT_' + n] = kat[n]
+
     if args.stage1:
         # stage-1 intermediates: compute_tendencies only writes derived fields, so
         # calling it once before the first step leaves the trajectory unchanged.
@@ -289,9 +332,12 @@ def main():
     nmax = max(args.steps)
     for ts in range(1, nmax + 1):
         Diagnostics.secondary_diag(**F.get(Diagnostics.fields_secondary_diag, target=CPU))
+        if args.turbulence:
+            compute_turbulence_cpu(*[F.host[n] for n in TURB_FIELDS])
         step_matsuno(GR, F)
         if ts in args.steps:
-            for n in STATE + (DIAG + ['WWIND'] if args.dump_diag else []):
+            for n in (STATE + (DIAG + ['WWIND'] if args.dump_diag else []) +
+                      (['KMOM', 'KHEAT'] if args.turbulence else [])):
                 out['N%d_%s' % (ts, n)] = F.host[n].copy()
     if args.time_steps:
         ts_t = []

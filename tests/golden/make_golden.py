@@ -18,6 +18,10 @@ outputs.  Nothing here is computed by this repository's code.
                       KMOM, KHEAT, SMOMXFLX, SMOMYFLX, SSHFLX, SLHFLX): inputs, every stage-1
                       intermediate incl. KMOM_dUWINDdz / KMOM_dVWINDdz and the *_TURB
                       tendencies, state after 1, 2 and 10 steps.
+  ref_10deg_turb.npz  the 36x16x6 grid with the reference's turbulence module
+                      (turb_compute.py) called after secondary_diag in every time step
+                      (solver.py:106-112): KMOM / KHEAT of the first call, state and
+                      KMOM / KHEAT after 1, 2 and 10 steps.
 """
 import os
 import subprocess
@@ -32,6 +36,8 @@ JOBS = [
     ('ref_5deg.npz', ['--grid', '5deg', '--steps', '10', '50', '--minimal']),
     ('ref_10deg_coupled.npz', ['--grid', '10deg_rand', '--steps', '1', '2', '10', '--stage1',
                                '--coupling']),
+    ('ref_10deg_turb.npz', ['--grid', '10deg_rand', '--steps', '1', '2', '10', '--minimal',
+                            '--turbulence']),
 ]
 
 if __name__ == '__main__':

@@ -31,9 +31,13 @@ def oracle_from_golden(g, i_moist=True):
     coupling fields (ref_10deg_coupled.npz) switches their terms on"""
     nx, ny, nz, dt = golden_dims(g)
     coupled = 'IN_KMOM' in g
+    turb = 'T1_KMOM' in g        # fixture made with the reference's turbulence module
     O = Oracle(nx, ny, nz, dt, {n: g['GR_' + n] for n in GRID_FIELDS}, i_moist=i_moist,
-               i_coupling=coupled)
+               i_coupling=coupled or turb)
     O.set(**{n: g['IN_' + n] for n in ['HSURF'] + STATE + (COUPLING if coupled else [])})
+    if turb:
+        for n in COUPLING:
+            O.F[n][:] = 0.
     return O
 
 
@@ -93,7 +97,7 @@ def grid_from_golden(g, band=(0, 1), **kw):
     nx, ny, nz, dt = golden_dims(g)
     arrays = {n: g['GR_' + n] for n in GRID_FIELDS}
     arrays.update(nx=nx, ny=ny, nz=nz, dt=dt)
-    if 'IN_KMOM' in g:          # fixture with non-zero physics coupling fields
+    if 'IN_KMOM' in g or 'T1_KMOM' in g:    # fixture with non-zero physics coupling fields
         kw.setdefault('i_coupling', 1)
     return Grid(band=band, from_arrays=arrays, **kw)
 

@@ -494,3 +494,68 @@ def test_coupled_errors_are_loud(gc):
     with pytest.raises(NotImplementedError, match='latitude bands'):
         Grid(band=(0, 2), i_coupling=1)
     GR.close()
+
+
+# ---------------------------------------------------------------------------------------
+# turbulence module (turb_main.py / turb_compute.py) in the time loop, against the real
+# reference run with its own turbulence module (tests/golden/ref_10deg_turb.npz)
+# ---------------------------------------------------------------------------------------
+def test_turbulence_module_against_reference_golden():
+    from climate_model_b200.dyn_matsuno import Diagnostics, step_matsuno
+    from climate_model_b200.io_read_namelist import B200
+    from climate_model_b200.turb_main import Turbulence
+    gt = load_golden('ref_10deg_turb.npz')
+    GR = grid_from_golden(gt)
+    F = fields_from_golden(GR, gt)
+    TURB = Turbulence(GR, target=B200)
+    assert TURB.fields_main == ['KMOM', 'KHEAT', 'PHIVB', 'HSURF', 'PHI', 'QV', 'WINDX', 'WINDY',
+                                'POTTVB', 'POTT']               # turb_main.py:41-42
+    Diagnostics.primary_diag(GR.GRF[B200], **F.get(Diagnostics.fields_primary_diag, target=B200))
+    for ts in range(1, 11):
+        Diagnostics.secondary_diag(**F.get(Diagnostics.fields_secondary_diag, target=B200))
+        TURB.compute_turbulence(GR, **F.get(TURB.fields_main, target=B200))
+        if ts == 1:
+            for n in ('KMOM', 'KHEAT'):
+                F.to_host(GR, n)
+                assert np.array_equal(F.host[n][:, :, 1:-1], gt['T1_' + n][:, :, 1:-1],
+                                      equal_nan=True), 'T1 ' + n
+        step_matsuno(GR, F)
+        if ts in (1, 2, 10):
+            F.copy_device_to_host(GR, F.PROGNOSTIC_FIELDS)
+            for n in STATE:
+                _eq(F.host[n], gt['N%d_%s' % (ts, n)], 'N%d %s' % (ts, n))
+    GR.close()
+
+
+def test_turbulence_kernel_known_answers_bit_exact():
+    """the reference kernel's outputs on seeded synthetic inputs that leave KMOM between its
+    clamps (tests/golden/ref_10deg_turb.npz KAT_*)"""
+    from climate_model_b200.io_read_namelist import B200
+    from climate_model_b200.turb_main import Turbulence
+    gt = load_golden('ref_10deg_turb.npz')
+    GR = grid_from_golden(gt)
+    F = fields_from_golden(GR, gt)
+    TURB = Turbulence(GR, target=B200)
+    for n in TURB.fields_main[2:]:
+        F.host[n][...] = gt['KAT_' + n]
+        F.to_device(GR, n)
+    TURB.compute_turbulence(GR, **F.get(TURB.fields_main, target=B200))
+    for n in ('KMOM', 'KHEAT'):
+        F.to_host(GR, n)
+        _eq(F.host[n][:, :, 1:-1], gt['KAT_' + n][:, :, 1:-1], 'KAT ' + n)
+    GR.close()
+
+
+def test_solver_with_turbulence_runs_and_stays_finite(capsys):
+    from climate_model_b200 import solver
+    GR, F = solver.run(nsteps=3, verbose=False, i_turbulence=1, nz=6, lat0_deg=-80, lat1_deg=80,
+                       dlat_deg=10, dlon_deg=10)
+    assert GR.i_coupling == 1
+    F.copy_device_to_host(GR, F.PROGNOSTIC_FIELDS)
+    F.to_host(GR, 'KMOM')
+    nx, ny = int(GR.nx), int(GR.ny)
+    for n in STATE:
+        assert np.isfinite(F.host[n][interior(n, nx, ny)]).all(), n
+    k = F.host['KMOM'][1:-1, 1:-1, 1:-1]
+    assert k.min() >= 1e-6 and k.max() <= 0.01
+    GR.close()

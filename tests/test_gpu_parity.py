@@ -402,3 +402,57 @@ def test_coupled_step_matsuno_against_reference_golden(gc, build, request):
             for n in STATE:
                 e = state_err(n, F.host, ref)
                 assert e <= TOL[n], 'N%d %s: %.3e > %.0e' % (ts, n, e, TOL[n])
+
+
+# ---------------------------------------------------------------------------------------
+# turbulence module (turb_main.py / turb_compute.py; tests/golden/ref_10deg_turb.npz)
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize('build', ['production', 'strict'])
+def test_turbulence_kernel_known_answers(build, request):
+    """the reference kernel's outputs on seeded synthetic inputs that leave KMOM between its
+    clamps; the device log() of the humidity mean differs from glibc's by <= 2 ulp"""
+    from climate_model_b200.io_read_namelist import B200
+    from climate_model_b200.turb_main import Turbulence
+    if build == 'strict':
+        request.getfixturevalue('strict_library')
+    gt = load_golden('ref_10deg_turb.npz')
+    GR = grid_from_golden(gt)
+    F = fields_from_golden(GR, gt)
+    TURB = Turbulence(GR, target=B200)
+    for n in TURB.fields_main[2:]:
+        F.host[n][...] = gt['KAT_' + n]
+        F.to_device(GR, n)
+    TURB.compute_turbulence(GR, **F.get(TURB.fields_main, target=B200))
+    for n in ('KMOM', 'KHEAT'):
+        F.to_host(GR, n)
+        a, b = F.host[n][:, :, 1:-1], gt['KAT_' + n][:, :, 1:-1]
+        assert np.max(np.abs(a - b) / np.abs(b)) <= 1e-12, n
+
+
+@pytest.mark.parametrize('build', ['production', 'strict'])
+def test_turbulence_in_the_time_loop_against_reference_golden(build, request):
+    """secondary_diag -> turbulence -> step_matsuno for 10 steps against the real reference
+    run with its own turbulence module (solver.py:99-112)"""
+    from climate_model_b200.dyn_matsuno import Diagnostics, step_matsuno
+    from climate_model_b200.io_read_namelist import B200
+    from climate_model_b200.turb_main import Turbulence
+    if build == 'strict':
+        request.getfixturevalue('strict_library')
+    gt = load_golden('ref_10deg_turb.npz')
+    GR = grid_from_golden(gt)
+    F = fields_from_golden(GR, gt)
+    TURB = Turbulence(GR, target=B200)
+    _diag(GR, F)
+    for ts in range(1, 11):
+        Diagnostics.secondary_diag(**F.get(Diagnostics.fields_secondary_diag, target=B200))
+        TURB.compute_turbulence(GR, **F.get(TURB.fields_main, target=B200))
+        step_matsuno(GR, F)
+        if ts in (1, 2, 10):
+            F.copy_device_to_host(GR, F.PROGNOSTIC_FIELDS)
+            ref = {n: gt['N%d_%s' % (ts, n)] for n in STATE}
+            for n in STATE:
+                e = state_err(n, F.host, ref)
+                assert e <= TOL[n], 'N%d %s: %.3e > %.0e' % (ts, n, e, TOL[n])
+    F.to_host(GR, 'KMOM')
+    k, kr = F.host['KMOM'][1:-1, 1:-1, 1:-1], gt['N10_KMOM'][1:-1, 1:-1, 1:-1]
+    assert np.array_equal(k, kr)          # every cell on the same clamp as the reference

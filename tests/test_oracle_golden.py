@@ -147,3 +147,53 @@ def test_coupled_step_matsuno_bit_exact(gc):
         if ts in (1, 2, 10):
             for n in STATE:
                 assert np.array_equal(O.F[n], gc['N%d_%s' % (ts, n)], equal_nan=True), (ts, n)
+
+
+# ---------------------------------------------------------------------------------------
+# turbulence module (turb_compute.py): KMOM / KHEAT computed by the reference itself
+# ---------------------------------------------------------------------------------------
+@pytest.fixture(scope='module')
+def gt():
+    return load_golden('ref_10deg_turb.npz')
+
+
+TURB_IN = ['PHIVB', 'HSURF', 'PHI', 'QV', 'WINDX', 'WINDY', 'POTTVB', 'POTT']
+
+
+def test_turbulence_kernel_known_answers_bit_exact(gt):
+    """the reference kernel run on seeded synthetic inputs where KMOM falls BETWEEN its clamps
+    (on model states it never does: mixing length^2 x shear is ~1e4 times the upper clamp)"""
+    O = oracle_from_golden(gt)
+    O.set(**{n: gt['KAT_' + n] for n in TURB_IN})
+    O.compute_turbulence()
+    for n in ('KMOM', 'KHEAT'):
+        assert np.array_equal(O.F[n][:, :, 1:-1], gt['KAT_' + n][:, :, 1:-1]), n
+    k = gt['KAT_KMOM'][:, :, 1:-1]
+    assert ((k > 1e-6) & (k < 0.01)).mean() > 0.9
+
+
+def test_turbulence_coefficients_bit_exact(gt):
+    O = oracle_from_golden(gt)
+    O.primary_diag()
+    O.secondary_diag()
+    O.compute_turbulence()
+    for n in ('KMOM', 'KHEAT'):
+        assert np.array_equal(O.F[n][:, :, 1:-1], gt['T1_' + n][:, :, 1:-1], equal_nan=True), n
+    k = gt['T1_KMOM'][1:-1, 1:-1, 1:-1]
+    assert (k == 1e-6).any() and (k == 0.01).any()            # both regimes occur
+
+
+def test_turbulence_in_the_time_loop_bit_exact(gt):
+    """secondary_diag -> turbulence -> step_matsuno (solver.py:99-112, :70-73)"""
+    O = oracle_from_golden(gt)
+    O.primary_diag()
+    for ts in range(1, 11):
+        O.secondary_diag()
+        O.compute_turbulence()
+        O.step_matsuno(1)
+        if ts in (1, 2, 10):
+            for n in STATE:
+                assert np.array_equal(O.F[n], gt['N%d_%s' % (ts, n)], equal_nan=True), (ts, n)
+            for n in ('KMOM', 'KHEAT'):
+                assert np.array_equal(O.F[n][:, :, 1:-1], gt['N%d_%s' % (ts, n)][:, :, 1:-1],
+                                      equal_nan=True), (ts, n)
