@@ -1,0 +1,131 @@
+"""NetCDF output, restart files and the testsuite comparison (reference
+io_nc_output.py, io_restart.py, testsuite.py), on the host emulation of the library."""
+import os
+
+import numpy as np
+import pytest
+from scipy.io import netcdf_file
+
+from helpers import STATE, build_emu
+
+GRID = dict(nz=6, lat0_deg=-80, lat1_deg=80, dlat_deg=10, dlon_deg=10, i_out_nth_hour=0.5)
+
+
+@pytest.fixture(scope='module', autouse=True)
+def emu_library():
+    from climate_model_b200 import _lib
+    prev = _lib.library_path()
+    _lib.use_library(build_emu())
+    yield
+    if prev:
+        _lib.use_library(prev)
+
+
+def _run(tmp_path, nsteps, sub='out', **kw):
+    from climate_model_b200 import solver
+    ic = dict(UWIND_random_pert=2.0, VWIND_random_pert=2.0, POTT_random_pert=1.0,
+              QV_random_pert=0.0005, COLP_random_pert=100.)
+    return solver.run(nsteps=nsteps, verbose=False, ic=ic, output_path=str(tmp_path / sub),
+                      restart_dir=str(tmp_path / 'restart'), **GRID, **kw)
+
+
+def test_netcdf_output_names_dimensions_and_values(tmp_path):
+    GR, F = _run(tmp_path, None, i_sim_n_days=1. / 24)
+    assert GR.i_out_nth_ts * GR.dt == 1800 and GR.ts == 2 * GR.i_out_nth_ts
+    assert GR.nc_output_count == 2
+    out = tmp_path / 'out'
+    assert sorted(os.listdir(out)) == ['constants.nc', 'out0001.nc', 'out0002.nc']
+    nx, ny, nz = int(GR.nx), int(GR.ny), int(GR.nz)
+    F.copy_device_to_host(GR, F.ALL_FIELDS)
+    with netcdf_file(str(out / 'out0002.nc'), 'r', mmap=False) as nc:
+        assert {n: d for n, d in nc.dimensions.items()} == {
+            'time': None, 'lon': nx, 'lons': nx + 1, 'lat': ny, 'lats': ny + 1, 'level': nz,
+            'levels': nz + 1}
+        v = nc.variables
+        # namelist.py:150-205 selection, fields of the out-of-scope physics modules aside
+        for n in ['UWIND', 'VWIND', 'WIND', 'WWIND', 'VORT', 'TAIR', 'PHI', 'COLP', 'PSURF', 'QV',
+                  'QC', 'dQVdt', 'UWINDprof', 'VWINDprof', 'WWINDprof', 'TAIRprof', 'QVprof']:
+            assert n in v, n
+        assert 'POTT' not in v and 'RHO' not in v            # output_fields[...] == 0
+        assert v['UWIND'].dimensions == ('time', 'level', 'lat', 'lons')
+        assert v['VWIND'].dimensions == ('time', 'level', 'lats', 'lon')
+        assert v['WWIND'].dimensions == ('time', 'levels', 'lat', 'lon')
+        assert v['COLP'].dimensions == ('time', 'lat', 'lon')
+        assert v['UWINDprof'].dimensions == ('time', 'level', 'lat')
+        assert v['UWIND'].data.dtype == np.dtype('>f4')
+        assert v['time'][0] == GR.sim_time_sec / 3600 / 24
+        f4 = lambda a: np.asarray(a, dtype=np.float32)
+        assert np.array_equal(v['UWIND'][0], f4(F.host['UWIND'][1:-1, 1:-1, :].T))
+        assert np.array_equal(v['VWIND'][0], f4(F.host['VWIND'][1:-1, 1:-1, :].T))
+        assert np.array_equal(v['COLP'][0], f4(F.host['COLP'][1:-1, 1:-1, 0].T))
+        assert np.array_equal(v['PSURF'][0], f4(F.host['COLP'][1:-1, 1:-1, 0].T + GR.pair_top))
+        assert np.array_equal(v['WWIND'][0],
+                              f4((F.host['WWIND'] * F.host['COLP'])[1:-1, 1:-1, :].T))
+        # zonal-mean profile, level axis reversed (io_nc_output.py:189-213)
+        prof = np.mean(F.host['TAIR'][1:-1, 1:-1, :], axis=0).T[::-1]
+        assert np.array_equal(v['TAIRprof'][0], f4(prof))
+        # vorticity against a direct evaluation of io_functions.py:27-41 at one point
+        U, V = F.host['UWIND'], F.host['VWIND']
+        i, j, k = 7, 5, 2
+        ref = (((V[i + 1, j, k] + V[i + 1, j + 1, k]) / 2 - (V[i - 1, j, k] + V[i - 1, j + 1, k]) / 2)
+               / (2 * GR.dx[i, j, 0])
+               - ((U[i, j + 1, k] + U[i + 1, j + 1, k]) / 2 - (U[i, j - 1, k] + U[i + 1, j - 1, k]) / 2)
+               / (2 * GR.dy[i, j, 0]))
+        assert v['VORT'][0, k, j - 1, i - 1] == np.float32(ref)
+    with netcdf_file(str(out / 'constants.nc'), 'r', mmap=False) as nc:
+        assert np.array_equal(nc.variables['HSURF'][:],
+                              np.asarray(F.host['HSURF'][1:-1, 1:-1, 0].T, dtype=np.float32))
+        assert nc.variables['lat'][:].shape == (ny,)
+    GR.close()
+
+
+def test_restart_continues_bit_for_bit(tmp_path):
+    from climate_model_b200.io_restart import restart_file_name, write_restart
+    GR, F = _run(tmp_path, 3)
+    fn = write_restart(GR, F, directory=str(tmp_path / 'restart'), verbose=False)
+    assert fn == restart_file_name(10, 10, 6, str(tmp_path / 'restart')) and os.path.exists(fn)
+    from climate_model_b200 import solver           # uninterrupted: 2 more steps
+    for _ in range(2):
+        GR.ts += 1
+        from climate_model_b200.dyn_matsuno import Diagnostics, step_matsuno
+        from climate_model_b200.io_read_namelist import B200
+        Diagnostics.secondary_diag(**F.get(Diagnostics.fields_secondary_diag, target=B200))
+        step_matsuno(GR, F)
+    F.copy_device_to_host(GR, F.PROGNOSTIC_FIELDS)
+    want = {n: F.host[n].copy() for n in STATE}
+    GR.close()
+    GR2, F2 = _run(tmp_path, 2, sub='out2', i_load_from_restart=1)
+    assert GR2.ts == 5 and GR2.sim_time_sec == 5 * GR2.dt
+    F2.copy_device_to_host(GR2, F2.PROGNOSTIC_FIELDS)
+    for n in STATE:
+        assert np.array_equal(F2.host[n], want[n], equal_nan=True), n
+    GR2.close()
+    with pytest.raises(ValueError, match='does not exist'):
+        solver.run(nsteps=1, verbose=False, restart_dir=str(tmp_path / 'nowhere'),
+                   i_load_from_restart=1, **GRID)
+
+
+def test_restart_written_by_the_time_loop(tmp_path):
+    GR, F = _run(tmp_path, None, i_sim_n_days=1. / 24, i_restart_nth_day=0.5 / 24,
+                 i_save_to_restart=1)
+    assert GR.i_restart_nth_ts == GR.i_out_nth_ts
+    assert os.listdir(tmp_path / 'restart') == ['10_10_006.pkl']
+    GR.close()
+
+
+def test_testsuite_comparison(tmp_path, capsys):
+    from climate_model_b200.testsuite import compare_outputs
+    GRa, Fa = _run(tmp_path, None, sub='a', i_sim_n_days=0.5 / 24)
+    GRb, Fb = _run(tmp_path, None, sub='b', i_sim_n_days=0.5 / 24)
+    a, b = str(tmp_path / 'a' / 'out0001.nc'), str(tmp_path / 'b' / 'out0001.nc')
+    failed, dev_sum, devs = compare_outputs(a, b)
+    assert not failed and dev_sum == 0 and 'Bitwise identical' in capsys.readouterr().out
+    assert set(devs) == {'UWIND', 'VWIND', 'WWIND', 'COLP', 'PHI', 'QV', 'QC'}
+    # a different run (other perturbation seed -> other state) must fail the comparison
+    from climate_model_b200 import solver
+    GRc, Fc = solver.run(nsteps=None, verbose=False, output_path=str(tmp_path / 'c'),
+                         ic=dict(UWIND_random_pert=2.1), i_sim_n_days=0.5 / 24, **GRID)
+    failed, _, devs = compare_outputs(a, str(tmp_path / 'c' / 'out0001.nc'), verbose=False)
+    assert failed and devs['UWIND'] > 1e-4
+    for g in (GRa, GRb, GRc):
+        g.close()
