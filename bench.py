@@ -178,6 +178,9 @@ def main():
     ap.add_argument('--moist', action='store_true')
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--e2e-steps', type=int, default=3)
+    ap.add_argument('--e2e-members', type=int, default=12,
+                    help='1 GPU: host-resident states streamed through ensemble_stream.MemberStream '
+                         'for the e2e number (0: only the one-state-at-a-time sequence)')
     ap.add_argument('--mode', default='fused', choices=['fused', 'kernels'],
                     help='fused stage kernel (default) or one kernel per reference kernel')
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -300,6 +303,34 @@ def main():
         t = torch.tensor([e2e_sec], device=F.torch_device, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_sec = float(t.item())
+    e2e_what = ('pinned host state -> device (+layout transpose), primary_diag, 1 Matsuno step, '
+                'device -> host state')
+    e2e_extra = {}
+    if world == 1 and args.e2e_members > 0:
+        # host-resident states (ensemble members) streamed through the device: every member's
+        # upload, step and download are inside the timed region; the upload of member m+1 and
+        # the download of member m-1 overlap the step of member m (ensemble_stream.py)
+        from climate_model_b200.ensemble_stream import MemberStream, pinned_member
+        sets = []
+        for _ in range(3):
+            mem = pinned_member(F, names)
+            for n in names:
+                mem[n][...] = F.host[n]
+            sets.append(mem)
+        stream = MemberStream(GR, F, names=names, depth=2)
+        stream.advance(sets, nsteps=1)                       # warm-up: one pass over the sets
+        barrier()
+        t0 = time.perf_counter()
+        n_mem = stream.advance([sets[m % 3] for m in range(args.e2e_members)], nsteps=1)
+        barrier()
+        stream_sec = (time.perf_counter() - t0) / n_mem
+        e2e_extra = {'members': n_mem, 'one_state_at_a_time_ms': e2e_sec * 1e3,
+                     'finite': bool(all(np.isfinite(m['POTT']).all() for m in sets))}
+        e2e_sec = stream_sec
+        e2e_what = ('%d host-resident states (pinned, reference layout) streamed through the '
+                    'device, each: H2D, layout transpose, primary_diag, 1 Matsuno step, '
+                    'transpose, D2H; upload / step / download of consecutive states overlap '
+                    '(ensemble_stream.MemberStream); wall clock / states' % n_mem)
 
     if rank == 0:
         peak, peak_src = peak_hbm_gbs()
@@ -343,9 +374,7 @@ def main():
             'kernels_ms_per_step': {k: v[0] / args.steps for k, v in sorted(kern.items())},
             'e2e': {'value': cells / e2e_sec, 'unit': 'cell-updates/s',
                     'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': h2d,
-                    'ms_per_step': e2e_sec * 1e3,
-                    'what': 'pinned host state -> device (+layout transpose), primary_diag, '
-                            '1 Matsuno step, device -> host state'},
+                    'ms_per_step': e2e_sec * 1e3, 'what': e2e_what, **e2e_extra},
             'gpu_launches': int(launches),
             'clocks': clocks,
         }

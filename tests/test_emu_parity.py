@@ -559,3 +559,40 @@ def test_solver_with_turbulence_runs_and_stays_finite(capsys):
     k = F.host['KMOM'][1:-1, 1:-1, 1:-1]
     assert k.min() >= 1e-6 and k.max() <= 0.01
     GR.close()
+
+
+def test_member_stream_equals_one_member_at_a_time(g10):
+    """ensemble_stream.MemberStream (upload / step / download pipelined over members) against
+    the plain to_device -> primary_diag -> step_matsuno -> to_host sequence, bit for bit"""
+    from climate_model_b200.dyn_matsuno import Diagnostics, step_matsuno
+    from climate_model_b200.ensemble_stream import MemberStream, pinned_member
+    from climate_model_b200.io_read_namelist import B200
+    GR = grid_from_golden(g10)
+    F = fields_from_golden(GR, g10)
+    rng = np.random.default_rng(5)
+    names = STATE
+    members, want = [], []
+    for m in range(5):
+        mem = pinned_member(F, names)
+        for n in names:
+            mem[n][...] = g10['IN_' + n]
+        # distinct members: perturb the interior temperature, keep the boundary images
+        mem['POTT'][1:-1, 1:-1, :] += rng.uniform(-0.5, 0.5, size=mem['POTT'][1:-1, 1:-1, :].shape)
+        mem['POTT'][...] = GR.exchange_BC(mem['POTT'])
+        members.append(mem)
+    for mem in members:                                   # one member at a time
+        for n in names:
+            F.host[n][...] = mem[n]
+            F.to_device(GR, n)
+        Diagnostics.primary_diag(GR.GRF[B200],
+                                 **F.get(Diagnostics.fields_primary_diag, target=B200))
+        step_matsuno(GR, F, 2)
+        F.copy_device_to_host(GR, F.PROGNOSTIC_FIELDS)
+        want.append({n: F.host[n].copy() for n in names})
+    ms = MemberStream(GR, F, names=names, depth=2)
+    assert ms.advance(members, nsteps=2) == 5
+    for mem, w in zip(members, want):
+        for n in names:
+            _eq(mem[n], w[n], n)
+    assert not np.array_equal(want[0]['POTT'], want[1]['POTT'])
+    GR.close()

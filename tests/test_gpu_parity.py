@@ -456,3 +456,38 @@ def test_turbulence_in_the_time_loop_against_reference_golden(build, request):
     F.to_host(GR, 'KMOM')
     k, kr = F.host['KMOM'][1:-1, 1:-1, 1:-1], gt['N10_KMOM'][1:-1, 1:-1, 1:-1]
     assert np.array_equal(k, kr)          # every cell on the same clamp as the reference
+
+
+def test_member_stream_equals_one_member_at_a_time(g10):
+    """ensemble_stream.MemberStream: upload / step / download of consecutive host-resident
+    states overlapped on three CUDA streams, bitwise equal to the plain to_device ->
+    primary_diag -> step_matsuno -> to_host sequence; host buffers reused while in flight"""
+    from climate_model_b200.dyn_matsuno import step_matsuno
+    from climate_model_b200.ensemble_stream import MemberStream, pinned_member
+    GR = grid_from_golden(g10)
+    F = fields_from_golden(GR, g10)
+    rng = np.random.default_rng(5)
+    members, want = [], []
+    for m in range(3):
+        mem = pinned_member(F, STATE)
+        for n in STATE:
+            mem[n][...] = g10['IN_' + n]
+        mem['POTT'][1:-1, 1:-1, :] += rng.uniform(-0.5, 0.5, size=mem['POTT'][1:-1, 1:-1, :].shape)
+        mem['POTT'][...] = GR.exchange_BC(mem['POTT'])
+        members.append(mem)
+    for mem in members:                                   # one member at a time, 2 x 2 steps
+        for n in STATE:
+            F.host[n][...] = mem[n]
+            F.to_device(GR, n)
+        for _ in range(2):
+            _diag(GR, F)
+            step_matsuno(GR, F, 2)
+        F.copy_device_to_host(GR, F.PROGNOSTIC_FIELDS)
+        want.append({n: F.host[n].copy() for n in STATE})
+    ms = MemberStream(GR, F, names=STATE, depth=2)
+    # every host set passes twice: the second upload of a set must wait for its first download
+    assert ms.advance(members + members, nsteps=2) == 6
+    for mem, w in zip(members, want):
+        for n in STATE:
+            _eq(mem[n], w[n], n)
+    assert not np.array_equal(want[0]['POTT'], want[1]['POTT'])
