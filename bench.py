@@ -60,6 +60,13 @@ KERNEL_ACCESSES = {
 }
 
 
+# with the physics coupling terms (i_coupling): + KMOM, RHOVB, PHI reads and 2 writes in the
+# preparation; + PHIVB, RHO, KMOM_d*WINDdz reads and the *_TURB write in the tendencies
+KERNEL_ACCESSES_COUPLED = {
+    'uvflx_prep': 20, 'uflx_tendency': 17, 'vflx_tendency': 17, 'pott_tendency': 13,
+    'moist_tendency': 14, 'secondary_diag': 15, 'turbulence': 9,
+}
+
 # DRAM bytes per launch of the dominant kernel (dram__bytes_read.sum + dram__bytes_write.sum of one
 # `ncu --set full` capture, profiles/r1_final_ncu_full_summary.csv): valid for that workload on one
 # GPU only; anything else reports null
@@ -183,6 +190,11 @@ def main():
                          'for the e2e number (0: only the one-state-at-a-time sequence)')
     ap.add_argument('--mode', default='fused', choices=['fused', 'kernels'],
                     help='fused stage kernel (default) or one kernel per reference kernel')
+    ap.add_argument('--turbulence', action='store_true',
+                    help='secondary line, not the headline: the reference time loop with its '
+                         'turbulence module on (secondary_diag -> compute_turbulence -> '
+                         'step_matsuno with the turbulent-transport terms, SURVEY 8f-2); runs '
+                         'the kernel decomposition')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-kernel-events', action='store_true',
                     help='do not bracket the kernels with CUDA events in the timed region (no '
@@ -235,8 +247,20 @@ def main():
     assert world == args.gpus, '--gpus %d but WORLD_SIZE=%d (launch with torchrun)' % (
         args.gpus, world)
 
-    GR = Grid(band=(rank, world), i_moist_main_switch=int(moist), **wl['grid'])
+    GR = Grid(band=(rank, world), i_moist_main_switch=int(moist),
+              i_coupling=int(args.turbulence), **wl['grid'])
     F = ModelFields(GR, **wl['ic'])
+    if args.turbulence:
+        from climate_model_b200.turb_main import Turbulence
+        F.TURB = Turbulence(GR, target=B200)
+        args.e2e_members = 0
+        args.no_cpu_baseline = True          # the CPU sample below times the dry step
+
+    def one_step():
+        if args.turbulence:                  # solver.py:99-112
+            Diagnostics.secondary_diag(**F.get(Diagnostics.fields_secondary_diag, target=B200))
+            F.TURB.compute_turbulence(GR, **F.get(F.TURB.fields_main, target=B200))
+        step_matsuno(GR, F, 1)
     if world > 1:
         from climate_model_b200.parallel_bands import attach_communicator
         attach_communicator(GR, F)
@@ -251,29 +275,39 @@ def main():
         torch.cuda.synchronize()
 
     for _ in range(args.warmup):
-        step_matsuno(GR, F, 1)
+        one_step()
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
+    def timed(kernel_events):
+        """K steps between barriers, CUDA events on the launching stream, max over ranks"""
+        _lib.check(L.dc_profile_enable(h, 1 if kernel_events else 0))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            one_step()
+        e1.record()
+        barrier()
+        t_ms = e0.elapsed_time(e1)
+        p = _lib.profile_read(h) if kernel_events else {}
+        _lib.check(L.dc_profile_enable(h, 0))
+        if world > 1:
+            t = torch.tensor([t_ms], device=F.torch_device, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t_ms = float(t.item())
+        return t_ms, p
+
+    # Two timed regions of K steps each, back to back: the first carries a CUDA-event bracket
+    # around every kernel launch (the roofline's launch durations; the brackets cost a few
+    # per cent of the step because a timing event keeps consecutive kernels from overlapping
+    # their tail and head), the second is the plain step loop a user runs = `value`.
+    ms_events, prof = (None, {}) if args.no_kernel_events else timed(True)
     launches0 = L.dc_launch_count(h)
-    _lib.check(L.dc_profile_enable(h, 0 if args.no_kernel_events else 1))
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        step_matsuno(GR, F, 1)
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    prof = _lib.profile_read(h)
-    _lib.check(L.dc_profile_enable(h, 0))
+    ms, _ = timed(False)
     launches = L.dc_launch_count(h) - launches0
     clocks = sampler.stop() if sampler else None
-    if world > 1:
-        t = torch.tensor([ms], device=F.torch_device, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
     ms_per_step = ms / args.steps
     value = cells / (ms_per_step * 1e-3)
     js = GR.jshift   # owned rows, interior columns (halo cells beyond are never read)
@@ -293,7 +327,7 @@ def main():
             F.to_device(GR, n)
         Diagnostics.primary_diag(GR.GRF[B200],
                                  **F.get(Diagnostics.fields_primary_diag, target=B200))
-        step_matsuno(GR, F, 1)
+        one_step()
         for n in names:
             F.to_host(GR, n)
         barrier()
@@ -342,6 +376,8 @@ def main():
             key = top + '_fused' if (top in ('continuity', 'primary_diag') and
                                      args.mode == 'fused') else top
             acc = KERNEL_ACCESSES.get(key, (0, 0))[1 if moist else 0]
+            if args.turbulence:
+                acc = KERNEL_ACCESSES_COUPLED.get(top, acc)
             k_ms = kern[top][0] / kern[top][1]
             cells_launch = cells // world
             bytes_launch = acc * 8 * cells_launch
@@ -360,11 +396,15 @@ def main():
             **({'emu': True} if args.emu else {}),
             'metric': 'dyn-core cell-updates/s', 'value': value, 'unit': 'cell-updates/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-            'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'strong',
+            'ms_per_step': ms_per_step,
+            'ms_per_step_with_kernel_events': None if ms_events is None else ms_events / args.steps,
+            'higher_is_better': True, 'scaling': 'strong',
             'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
             'config': {'workload': wl['name'], 'nx': int(GR.nx), 'ny': int(GR.ny),
                        'nz': int(GR.nz), 'dt_s': int(GR.dt), 'moist': moist,
-                       'parallelism': 'latitude bands x%d' % world, 'mode': args.mode,
+                       'parallelism': 'latitude bands x%d' % world,
+                       'mode': 'kernels + turbulence module (coupled terms)' if args.turbulence
+                       else args.mode,
                        'l2': 'inputs larger than L2 (%.1f GB state)' % (h2d / 1e9),
                        'finite': ok},
             'roofline': roof,
