@@ -56,8 +56,6 @@ class ModelFields:
             raise RuntimeError('libdyncore runs on CUDA devices only; there is no CPU fallback')
         if initialize:
             initialize_fields(GR, self.host, **ic_overrides)
-            for n in COUPLING_FIELDS:
-                self.host[n][:] = 0.
         self._bound = {}
         if gpu_enable:
             self.allocate_device(GR)
@@ -153,11 +151,12 @@ class _LazyHost(dict):
     name is used (the reference allocates all 93 up front, main_fields.py:477-485; at
     0.25 deg x 64 levels that would be 0.5 GB per field of host memory never touched)"""
 
-    def __init__(self, shapes, pin=False):
+    def __init__(self, shapes, pin=False, zero=()):
         super().__init__()
         self._shapes = shapes
         self._pin = pin
         self._pinned = {}
+        self._zero = set(zero)      # names that start as 0 instead of NaN
 
     def __missing__(self, n):
         if n not in self._shapes:
@@ -165,11 +164,11 @@ class _LazyHost(dict):
         if self._pin:
             # page-locked host memory: H2D / D2H copies run asynchronously at full PCIe rate
             t = torch.empty(self._shapes[n], dtype=torch.float64, pin_memory=True)
-            t.fill_(float('nan'))
+            t.fill_(0. if n in self._zero else float('nan'))
             self._pinned[n] = t
             a = t.numpy()
         else:
-            a = np.full(self._shapes[n], np.nan, dtype=wp)
+            a = np.full(self._shapes[n], 0. if n in self._zero else np.nan, dtype=wp)
         self[n] = a
         return a
 
@@ -200,4 +199,7 @@ def allocate_fields(GR):
     for n, (sx, sy, dz) in table.items():
         fdict[n] = {'stgx': sx, 'stgy': sy, 'dimz': nzmap[dz], 'dtype': wp}
         shapes[n] = (int(GR.nx) + 2 + sx, int(GR.ny) + 2 + sy, nzmap[dz])
-    return _LazyHost(shapes, pin=_lib.is_cuda() and torch.cuda.is_available()), fdict
+    # the physics coupling inputs are zero until a physics module (or the caller) fills them
+    # (the reference zeroes them when its modules are off)
+    return _LazyHost(shapes, pin=_lib.is_cuda() and torch.cuda.is_available(),
+                     zero=COUPLING_FIELDS), fdict
