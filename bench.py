@@ -154,6 +154,24 @@ def cpu_sample(wl, moist, steps, warmup=1):
     return cells, ts, O.num_threads(), sample
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """stdout carries ONE line, the JSON result: everything else a library writes to file
+    descriptor 1 (NCCL prints its version there) is sent to stderr; emit() writes the line"""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.write(_JSON_FD if _JSON_FD is not None else 1, (json.dumps(line) + '\n').encode())
+
+
 def run_reference(args, wl, moist):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
@@ -173,7 +191,7 @@ def run_reference(args, wl, moist):
                 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -203,12 +221,16 @@ def main():
                     help='debug the bench LOGIC on a box without a GPU against the host emulation '
                          '(tests/emu); the line is tagged "emu": true and is never a measurement')
     args = ap.parse_args()
+    claim_stdout()
     wl = WORKLOADS[args.workload]
     moist = bool(args.moist or wl.get('moist', False))
     if args.impl == 'reference':
         return run_reference(args, wl, moist)
 
-    os.environ['NCCL_DEBUG'] = os.environ.get('DC_NCCL_DEBUG', 'WARN')   # keep stdout = the JSON line
+    if 'DC_NCCL_DEBUG' in os.environ:
+        os.environ['NCCL_DEBUG'] = os.environ['DC_NCCL_DEBUG']
+    else:
+        os.environ.pop('NCCL_DEBUG', None)
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -423,7 +445,7 @@ def main():
             sec = sum(ts) / len(ts)
             line['cpu_baseline'] = {'value': c_cells / sec, 'unit': 'cell-updates/s',
                                     'cores': threads, 'kind': 'port', 'sample': sample}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
