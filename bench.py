@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- dyn-core throughput on B200: cell-updates/s and fraction of the HBM roofline.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg4|cfg2|cfg3|cfg1]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg4|cfg2|cfg3|cfg1|cfg5]
                   [--moist] [--impl reference]
 
 One "step" = one full Matsuno predictor/corrector step of the dynamical core
@@ -40,6 +40,15 @@ WORKLOADS = {
     'cfg4': dict(name='0.25deg x 64 levels, synthetic initial state (no topography), dry dyn core',
                  grid=dict(nz=64, lat0_deg=-84, lat1_deg=84, dlat_deg=0.25, dlon_deg=0.25,
                            i_out_nth_hour=1.0), ic=dict(i_use_topo=0)),
+    # BASELINE.json configs[4], WEAK scaling: every rank holds 210 latitude rows of the 0.1 deg
+    # grid (72.6 M cells, the per-rank share of the full 3600 x 1680 x 96 grid on 8 GPUs), so
+    # N ranks cover lat +-10.5 N deg and N = 8 is the whole configs[4] grid (lat +-84 deg).
+    # Every rank builds the whole grid's initial state on the host before keeping its band:
+    # ~30 GB of host memory per rank at N = 8.
+    'cfg5': dict(name='0.1deg x 96 levels, synthetic initial state, 210 rows per GPU (weak scaling; '
+                      'N = 8 is the full 3600 x 1680 x 96 grid)',
+                 grid=dict(nz=96, lat0_deg=-10.5, lat1_deg=10.5, dlat_deg=0.1, dlon_deg=0.1,
+                           i_out_nth_hour=1.0), ic=dict(i_use_topo=0), weak=True),
     # development proxy (not a BASELINE config): two ranks of this grid each hold the 84 rows a
     # rank of cfg4 holds at N = 8
     'cfg4_band8x2': dict(name='0.25deg x 64 levels, +-21 deg (2 x 84 rows: per-rank size of cfg4 at N = 8)',
@@ -183,8 +192,8 @@ def run_reference(args, wl, moist):
         'impl': 'reference', 'metric': 'dyn-core cell-updates/s', 'value': value,
         'unit': 'cell-updates/s', 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True,
-        'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': wl['name'], 'moist': moist},
+        'scaling': 'weak' if wl.get('weak') else 'strong', 'vs_baseline': None, 'dtype': 'f64',
+        'data': 'synthetic', 'config': {'workload': wl['name'], 'moist': moist},
         'cpu_baseline': {'value': value, 'unit': 'cell-updates/s', 'cores': threads,
                          'kind': 'port', 'sample': sample},
         'e2e': {'value': value, 'unit': 'cell-updates/s', 'h2d_bytes_per_step': 0,
@@ -222,7 +231,10 @@ def main():
                          '(tests/emu); the line is tagged "emu": true and is never a measurement')
     args = ap.parse_args()
     claim_stdout()
-    wl = WORKLOADS[args.workload]
+    wl = dict(WORKLOADS[args.workload])
+    if wl.get('weak'):            # per-GPU work fixed: the latitude range grows with N
+        wl['grid'] = dict(wl['grid'], lat0_deg=wl['grid']['lat0_deg'] * args.gpus,
+                          lat1_deg=wl['grid']['lat1_deg'] * args.gpus)
     moist = bool(args.moist or wl.get('moist', False))
     if args.impl == 'reference':
         return run_reference(args, wl, moist)
@@ -420,7 +432,7 @@ def main():
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms_per_step,
             'ms_per_step_with_kernel_events': None if ms_events is None else ms_events / args.steps,
-            'higher_is_better': True, 'scaling': 'strong',
+            'higher_is_better': True, 'scaling': 'weak' if wl.get('weak') else 'strong',
             'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
             'config': {'workload': wl['name'], 'nx': int(GR.nx), 'ny': int(GR.ny),
                        'nz': int(GR.nz), 'dt_s': int(GR.dt), 'moist': moist,

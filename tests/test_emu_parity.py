@@ -311,7 +311,10 @@ def test_boundary_interior_split_equals_whole_stage(fixture):
         _eq(out[0][n], out[1][n], n)
 
 
-@pytest.mark.parametrize('dlon,dlat,nz', [(8.0, 7.0, 5), (2.4, 5.0, 9), (1.25, 3.0, 7)])
+# the last three: sigma columns of BASELINE configs[4] (96 levels), a level count that is not a
+# multiple of the continuity kernel's 16 levels per thread, and the maximum (128)
+@pytest.mark.parametrize('dlon,dlat,nz', [(8.0, 7.0, 5), (2.4, 5.0, 9), (1.25, 3.0, 7),
+                                          (10.0, 11.0, 96), (10.0, 11.0, 100), (12.0, 14.0, 128)])
 def test_ragged_grids_fused_equals_kernel_mode(dlon, dlat, nz):
     """odd nx (the second column of the last thread pair is masked), tile rows and columns that
     do not divide the grid, odd ny: fused path against the one-kernel-per-reference-kernel mode"""
