@@ -70,6 +70,9 @@ struct ExchangeBCBody {
     {
         // threads cover i in [1, nx(+1)], j in [1, ny(+1)]
         const bool xs = kind & 1, ys = kind & 2;
+        // only the cells next to a boundary have images (or are wall rows): every other
+        // thread leaves without touching memory
+        if (i > 2 && i != g.nx && j != 1 && j < g.ny) return;
         for (int k = 0; k < nk; k++) {
             double v = F[g.idx(i, j, k)];
             if (ys) {
@@ -237,25 +240,40 @@ struct PrepBody {
                               g.dsigma[k - 1], mkdiv(g.dsigma[k] + g.dsigma[k - 1], g.r_dss[k]));
         }
         if (g.i_coupling) {
+            // the altitude and the wind of level k are carried to interface k+1
             if (j <= ny) {
                 KMOM_dUWINDdz[g.idx(i, j, 0)] = 0.;
                 KMOM_dUWINDdz[g.idx(i, j, nz)] = 0.;
                 const Six C = six3(COLP, i, j, 0, true), A = sixA(j, true);
-                for (int k = 1; k < nz; k++)
-                    KMOM_dUWINDdz[g.idx(i, j, k)] = interp_KMOM_dUVWINDdz(
-                        UWIND[g.idx(i, j, k)], UWIND[g.idx(i, j, k - 1)], six3(KMOM, i, j, k, true),
-                        six3(RHOVB, i, j, k, true), six3(PHI, i, j, k, true),
-                        six3(PHI, i, j, k - 1, true), C, A, true, j, ny);
+                double alt_km1 = interp_VAR_ds(six3(PHI, i, j, 0, true), true, j, ny);
+                double w_km1 = UWIND[g.idx(i, j, 0)];
+                for (int k = 1; k < nz; k++) {
+                    const double alt = interp_VAR_ds(six3(PHI, i, j, k, true), true, j, ny);
+                    const double w = UWIND[g.idx(i, j, k)];
+                    KMOM_dUWINDdz[g.idx(i, j, k)] = kmom_dwinddz(
+                        colpakmom_ds(six3(KMOM, i, j, k, true), six3(RHOVB, i, j, k, true), C, A,
+                                     true, j, ny),
+                        w, w_km1, alt_km1, alt);
+                    alt_km1 = alt;
+                    w_km1 = w;
+                }
             }
             if (i <= nx) {
                 KMOM_dVWINDdz[g.idx(i, j, 0)] = 0.;
                 KMOM_dVWINDdz[g.idx(i, j, nz)] = 0.;
                 const Six C = six3(COLP, i, j, 0, false), A = sixA(j, false);
-                for (int k = 1; k < nz; k++)
-                    KMOM_dVWINDdz[g.idx(i, j, k)] = interp_KMOM_dUVWINDdz(
-                        VWIND[g.idx(i, j, k)], VWIND[g.idx(i, j, k - 1)], six3(KMOM, i, j, k, false),
-                        six3(RHOVB, i, j, k, false), six3(PHI, i, j, k, false),
-                        six3(PHI, i, j, k - 1, false), C, A, false, i, nx);
+                double alt_km1 = interp_VAR_ds(six3(PHI, i, j, 0, false), false, i, nx);
+                double w_km1 = VWIND[g.idx(i, j, 0)];
+                for (int k = 1; k < nz; k++) {
+                    const double alt = interp_VAR_ds(six3(PHI, i, j, k, false), false, i, nx);
+                    const double w = VWIND[g.idx(i, j, k)];
+                    KMOM_dVWINDdz[g.idx(i, j, k)] = kmom_dwinddz(
+                        colpakmom_ds(six3(KMOM, i, j, k, false), six3(RHOVB, i, j, k, false), C,
+                                     A, false, i, nx),
+                        w, w_km1, alt_km1, alt);
+                    alt_km1 = alt;
+                    w_km1 = w;
+                }
             }
         }
         for (int k = 0; k < nz; k++) {  // dyn_UVFLX_prepare.py:345-436
@@ -323,6 +341,14 @@ struct UFLXTendencyBody {
         const double sinl = g.sin_lat_is[g.row(j)];
         const double scale = cor_scale(g.dlon_rad, g.dlat_rad);
         const double *U = UWIND, *V = VWIND;
+        // coupled terms: surface momentum flux, and the interface altitude / K dU/dz of the
+        // level's upper interface, carried down the column
+        double smomflx_s = 0., altvb = 0., kd = 0.;
+        if (g.i_coupling) {
+            smomflx_s = interp_VAR_ds(six(SMOMXFLX, i, j, 0), true, j, ny);
+            altvb = interp_VAR_ds(six(PHIVB, i, j, 0), true, j, ny) / div_g();
+            kd = KMOM_dUWINDdz[g.idx(i, j, 0)];
+        }
         for (int k = 0; k < nz; k++) {
             double bflx = BFLX[g.idx(i, j, k)], cflx = CFLX[g.idx(i, j, k)];
             double eflx = EFLX[g.idx(i, j, k)], dflx_jp1 = DFLX[g.idx(i, j + 1, k)];
@@ -350,14 +376,16 @@ struct UFLXTendencyBody {
             const Div ds = mkdiv(g.dsigma[k], g.r_dsigma[k]);
             d = d + ((WWIND_UWIND[g.idx(i, j, k)] - WWIND_UWIND[g.idx(i, j, k + 1)]) / ds);
             if (g.i_coupling) {
-                const double t = turb_momentum(
-                    KMOM_dUWINDdz[g.idx(i, j, k)], KMOM_dUWINDdz[g.idx(i, j, k + 1)],
-                    interp_VAR_ds(six(SMOMXFLX, i, j, 0), true, j, ny),
-                    interp_VAR_ds(six(PHIVB, i, j, k), true, j, ny) / con_g,
-                    interp_VAR_ds(six(PHIVB, i, j, k + 1), true, j, ny) / con_g,
-                    interp_VAR_ds(six(RHO, i, j, k), true, j, ny), k, nz);
+                const double altvb_kp1 =
+                    interp_VAR_ds(six(PHIVB, i, j, k + 1), true, j, ny) / div_g();
+                const double kd_kp1 = KMOM_dUWINDdz[g.idx(i, j, k + 1)];
+                const double t =
+                    turb_momentum(kd, kd_kp1, smomflx_s, altvb, altvb_kp1,
+                                  interp_VAR_ds(six(RHO, i, j, k), true, j, ny), k, nz);
                 dUFLXdt_TURB[g.idx(i, j, k)] = t;
                 d = d + t;
+                altvb = altvb_kp1;      // carried down the column
+                kd = kd_kp1;
             }
             d = d + coriolis_UWIND(c, c_im1, V[g.idx(i, j, k)], V[g.idx(i - 1, j, k)],
                                    V[g.idx(i, j + 1, k)], V[g.idx(i - 1, j + 1, k)], u, u_im1,
@@ -406,6 +434,12 @@ struct VFLXTendencyBody {
         const double scale = cor_scale(g.dlon_rad, g.dlat_rad);
         const double dxjs = g.dxjs[g.row(j)];
         const double *U = UWIND, *V = VWIND;
+        double smomflx_s = 0., altvb = 0., kd = 0.;   // coupled terms, as in UFLXTendencyBody
+        if (g.i_coupling) {
+            smomflx_s = interp_VAR_ds(six(SMOMYFLX, i, j, 0), false, i, nx);
+            altvb = interp_VAR_ds(six(PHIVB, i, j, 0), false, i, nx) / div_g();
+            kd = KMOM_dVWINDdz[g.idx(i, j, 0)];
+        }
         for (int k = 0; k < nz; k++) {
             const double rflx = RFLX[g.idx(i, j, k)], qflx = QFLX[g.idx(i, j, k)];
             const double tflx = TFLX[g.idx(i, j, k)], rflx_jm1 = RFLX[g.idx(i, j - 1, k)];
@@ -424,14 +458,16 @@ struct VFLXTendencyBody {
             const Div ds = mkdiv(g.dsigma[k], g.r_dsigma[k]);
             d = d + ((WWIND_VWIND[g.idx(i, j, k)] - WWIND_VWIND[g.idx(i, j, k + 1)]) / ds);
             if (g.i_coupling) {
-                const double t = turb_momentum(
-                    KMOM_dVWINDdz[g.idx(i, j, k)], KMOM_dVWINDdz[g.idx(i, j, k + 1)],
-                    interp_VAR_ds(six(SMOMYFLX, i, j, 0), false, i, nx),
-                    interp_VAR_ds(six(PHIVB, i, j, k), false, i, nx) / con_g,
-                    interp_VAR_ds(six(PHIVB, i, j, k + 1), false, i, nx) / con_g,
-                    interp_VAR_ds(six(RHO, i, j, k), false, i, nx), k, g.nz);
+                const double altvb_kp1 =
+                    interp_VAR_ds(six(PHIVB, i, j, k + 1), false, i, nx) / div_g();
+                const double kd_kp1 = KMOM_dVWINDdz[g.idx(i, j, k + 1)];
+                const double t =
+                    turb_momentum(kd, kd_kp1, smomflx_s, altvb, altvb_kp1,
+                                  interp_VAR_ds(six(RHO, i, j, k), false, i, nx), k, g.nz);
                 dVFLXdt_TURB[g.idx(i, j, k)] = t;
                 d = d + t;
+                altvb = altvb_kp1;      // carried down the column
+                kd = kd_kp1;
             }
             d = d + coriolis_VWIND(c, c_jm1, U[g.idx(i, j, k)], U[g.idx(i, j - 1, k)],
                                    U[g.idx(i + 1, j, k)], U[g.idx(i + 1, j - 1, k)], fcos, sinl,
@@ -471,6 +507,12 @@ struct POTTTendencyBody {
         const double c_jm1 = COLP[g.idx2(i, j - 1)], c_jp1 = COLP[g.idx2(i, j + 1)];
         const double cnew = COLP_NEW[g.idx2(i, j)];
         const Div A = mkdiv(g.A[g.row(j)], g.r_A[g.row(j)]);
+        TurbMarch tm{0., 0., 0.};
+        double surf = 0.;
+        if (g.i_coupling) {
+            tm = TurbMarch::top(PHI[g.idx(i, j, 0)], PHIVB[g.idx(i, j, 0)]);
+            surf = SSHFLX[g.idx2(i, j)] / con_cp;
+        }
         for (int k = 0; k < nz; k++) {
             const Div ds = mkdiv(g.dsigma[k], g.r_dsigma[k]);
             const double p = POTT[g.idx(i, j, k)];
@@ -483,13 +525,11 @@ struct POTTTendencyBody {
             d = d + vert_adv(POTTVB[g.idx(i, j, k)], POTTVB[g.idx(i, j, k + 1)],
                              WWIND[g.idx(i, j, k)], WWIND[g.idx(i, j, k + 1)], cnew, ds, k);
             if (g.i_coupling) {
-                const int km = k > 0 ? k - 1 : k, kp = k < nz - 1 ? k + 1 : k;
-                const double t = turb_flux_tendency(
-                    PHI[g.idx(i, j, k)], PHI[g.idx(i, j, kp)], PHI[g.idx(i, j, km)],
-                    PHIVB[g.idx(i, j, k)], PHIVB[g.idx(i, j, k + 1)], p, POTT[g.idx(i, j, kp)],
-                    POTT[g.idx(i, j, km)], KHEAT[g.idx(i, j, k)], KHEAT[g.idx(i, j, k + 1)],
-                    RHO[g.idx(i, j, k)], RHOVB[g.idx(i, j, k)], RHOVB[g.idx(i, j, k + 1)], c,
-                    SSHFLX[g.idx2(i, j)] / con_cp, k, nz);
+                const int kp = k < nz - 1 ? k + 1 : k;
+                const double t =
+                    tm.step(p, POTT[g.idx(i, j, kp)], PHI[g.idx(i, j, kp)],
+                            PHIVB[g.idx(i, j, k + 1)], RHOVB[g.idx(i, j, k + 1)],
+                            KHEAT[g.idx(i, j, k + 1)], RHO[g.idx(i, j, k)], c, surf, k, nz);
                 d = d + t;
                 dPOTTdt_TURB[g.idx(i, j, k)] = t / c * 3600.;   // [K hr-1], dyn_POTT.py:97
             }
@@ -525,6 +565,13 @@ struct MoistTendencyBody {
         const Div A = mkdiv(g.A[g.row(j)], g.r_A[g.row(j)]);
         double q = Q[g.idx(i, j, 0)];
         double qvb = q;  // unused at k = 0
+        const bool vap = (Q == QV);
+        TurbMarch tm{0., 0., 0.};
+        double surf = 0.;
+        if (g.i_coupling) {
+            tm = TurbMarch::top(PHI[g.idx(i, j, 0)], PHIVB[g.idx(i, j, 0)]);
+            surf = vap ? SLHFLX[g.idx2(i, j)] / con_Lh : 0.;
+        }
         for (int k = 0; k < nz; k++) {
             const double q_kp1 = (k + 1 < nz) ? Q[g.idx(i, j, k + 1)] : q;
             const double q_im1 = Q[g.idx(i - 1, j, k)], q_ip1 = Q[g.idx(i + 1, j, k)];
@@ -537,14 +584,11 @@ struct MoistTendencyBody {
             d = d + vert_adv(qvb, qvb_kp1, WWIND[g.idx(i, j, k)], WWIND[g.idx(i, j, k + 1)], cnew,
                              mkdiv(g.dsigma[k], g.r_dsigma[k]), k);
             if (g.i_coupling) {
-                const int km = k > 0 ? k - 1 : k, kp = k < nz - 1 ? k + 1 : k;
-                const bool vap = (Q == QV);
-                const double t = turb_flux_tendency(
-                    PHI[g.idx(i, j, k)], PHI[g.idx(i, j, kp)], PHI[g.idx(i, j, km)],
-                    PHIVB[g.idx(i, j, k)], PHIVB[g.idx(i, j, k + 1)], q, Q[g.idx(i, j, kp)],
-                    Q[g.idx(i, j, km)], KHEAT[g.idx(i, j, k)], KHEAT[g.idx(i, j, k + 1)],
-                    RHO[g.idx(i, j, k)], RHOVB[g.idx(i, j, k)], RHOVB[g.idx(i, j, k + 1)], c,
-                    vap ? SLHFLX[g.idx2(i, j)] / con_Lh : 0., k, nz);
+                const int kp = k < nz - 1 ? k + 1 : k;
+                const double t =
+                    tm.step(q, q_kp1, PHI[g.idx(i, j, kp)], PHIVB[g.idx(i, j, k + 1)],
+                            RHOVB[g.idx(i, j, k + 1)], KHEAT[g.idx(i, j, k + 1)],
+                            RHO[g.idx(i, j, k)], c, surf, k, nz);
                 d = d + t;
                 if (vap) dQVdt_TURB[g.idx(i, j, k)] = t;
             }

@@ -317,43 +317,50 @@ constexpr double con_Lh = 2264E3;   // io_constants.py:25
 struct Six {
     double c, dm1, pm1, pp1, pm1_dm1, pp1_dm1;
 };
-DC_HD double interp_KMOM_dUVWINDdz(double DWIND, double DWIND_km1, const Six &K, const Six &R,
-                                   const Six &P, const Six &Q, const Six &C, const Six &A,
-                                   bool rigid_wall, int p_ind, int np)
+// division by the gravity constant: an IEEE division in the strict build, a multiplication by
+// the compile-time reciprocal in the production build
+DC_HD Div div_g() { return mkdiv(con_g, 1. / con_g); }
+// the six-point average of dyn_functions.py:276-422 around a u- or v-point (rigid walls in
+// the perpendicular direction at p_ind == 1 and p_ind == np when rigid_wall)
+DC_HD double six_avg(const Six &V, bool rigid_wall, int p_ind, int np)
 {
-    double COLPAKMOM_ds_ks, ALT_ds_km1, ALT_ds;
-    if (rigid_wall && p_ind == 1) {
-        COLPAKMOM_ds_ks = 0.25 * (R.pp1_dm1 * C.pp1_dm1 * A.pp1_dm1 * K.pp1_dm1 +
-                                  R.pp1 * C.pp1 * A.pp1 * K.pp1 + R.dm1 * C.dm1 * A.dm1 * K.dm1 +
-                                  R.c * C.c * A.c * K.c);
-        ALT_ds_km1 = 0.25 * (Q.pp1_dm1 + Q.pp1 + Q.dm1 + Q.c) / con_g;
-        ALT_ds = 0.25 * (P.pp1_dm1 + P.pp1 + P.dm1 + P.c) / con_g;
-    } else if (rigid_wall && p_ind == np) {
-        COLPAKMOM_ds_ks = 0.25 * (R.dm1 * C.dm1 * A.dm1 * K.dm1 + R.c * C.c * A.c * K.c +
-                                  R.pm1_dm1 * C.pm1_dm1 * A.pm1_dm1 * K.pm1_dm1 +
-                                  R.pm1 * C.pm1 * A.pm1 * K.pm1);
-        ALT_ds_km1 = 0.25 * (Q.dm1 + Q.c + Q.pm1_dm1 + Q.pm1) / con_g;
-        ALT_ds = 0.25 * (P.dm1 + P.c + P.pm1_dm1 + P.pm1) / con_g;
-    } else {
-        COLPAKMOM_ds_ks =
-            0.125 * (R.pp1_dm1 * C.pp1_dm1 * A.pp1_dm1 * K.pp1_dm1 + R.pp1 * C.pp1 * A.pp1 * K.pp1 +
-                     2. * R.dm1 * C.dm1 * A.dm1 * K.dm1 + 2. * R.c * C.c * A.c * K.c +
-                     R.pm1_dm1 * C.pm1_dm1 * A.pm1_dm1 * K.pm1_dm1 + R.pm1 * C.pm1 * A.pm1 * K.pm1);
-        ALT_ds_km1 =
-            0.125 * (Q.pp1_dm1 + Q.pp1 + 2. * Q.dm1 + 2. * Q.c + Q.pm1_dm1 + Q.pm1) / con_g;
-        ALT_ds = 0.125 * (P.pp1_dm1 + P.pp1 + 2. * P.dm1 + 2. * P.c + P.pm1_dm1 + P.pm1) / con_g;
-    }
-    const double dDWINDdz_ks = ((DWIND_km1 - DWIND) / (ALT_ds_km1 - ALT_ds));
-    return COLPAKMOM_ds_ks * dDWINDdz_ks;
+    if (rigid_wall && p_ind == 1) return 0.25 * (V.pp1_dm1 + V.pp1 + V.dm1 + V.c);
+    if (rigid_wall && p_ind == np) return 0.25 * (V.dm1 + V.c + V.pm1_dm1 + V.pm1);
+    return 0.125 * (V.pp1_dm1 + V.pp1 + 2. * V.dm1 + 2. * V.c + V.pm1_dm1 + V.pm1);
 }
 // dyn_functions.py:383-422.  The division by con_g belongs to the reference function whatever
 // VAR is (it is also applied to RHO and the surface momentum fluxes, and a second time to
 // PHIVB by the callers): reproduced as is.
 DC_HD double interp_VAR_ds(const Six &V, bool rigid_wall, int p_ind, int np)
 {
-    if (rigid_wall && p_ind == 1) return 0.25 * (V.pp1_dm1 + V.pp1 + V.dm1 + V.c) / con_g;
-    if (rigid_wall && p_ind == np) return 0.25 * (V.dm1 + V.c + V.pm1_dm1 + V.pm1) / con_g;
-    return 0.125 * (V.pp1_dm1 + V.pp1 + 2. * V.dm1 + 2. * V.c + V.pm1_dm1 + V.pm1) / con_g;
+    return six_avg(V, rigid_wall, p_ind, np) / div_g();
+}
+// dyn_functions.py:276-377 (interior interfaces; 0 at k = 0 and nz), split in its three
+// factors so that a column march can carry the altitude of level k to interface k+1:
+//   colpakmom_ds   six-point average of RHOVB*COLP*A*KMOM (R, C, A, K)
+//   interp_VAR_ds  of PHI[k-1] and PHI[k] = ALT_ds_km1, ALT_ds (same expression as the
+//                  reference's inline averages / con_g)
+//   kmom_dwinddz   COLPAKMOM_ds_ks * (DWIND_km1 - DWIND) / (ALT_ds_km1 - ALT_ds)
+DC_HD double colpakmom_ds(const Six &K, const Six &R, const Six &C, const Six &A, bool rigid_wall,
+                          int p_ind, int np)
+{
+    if (rigid_wall && p_ind == 1)
+        return 0.25 * (R.pp1_dm1 * C.pp1_dm1 * A.pp1_dm1 * K.pp1_dm1 +
+                       R.pp1 * C.pp1 * A.pp1 * K.pp1 + R.dm1 * C.dm1 * A.dm1 * K.dm1 +
+                       R.c * C.c * A.c * K.c);
+    if (rigid_wall && p_ind == np)
+        return 0.25 * (R.dm1 * C.dm1 * A.dm1 * K.dm1 + R.c * C.c * A.c * K.c +
+                       R.pm1_dm1 * C.pm1_dm1 * A.pm1_dm1 * K.pm1_dm1 +
+                       R.pm1 * C.pm1 * A.pm1 * K.pm1);
+    return 0.125 * (R.pp1_dm1 * C.pp1_dm1 * A.pp1_dm1 * K.pp1_dm1 + R.pp1 * C.pp1 * A.pp1 * K.pp1 +
+                    2. * R.dm1 * C.dm1 * A.dm1 * K.dm1 + 2. * R.c * C.c * A.c * K.c +
+                    R.pm1_dm1 * C.pm1_dm1 * A.pm1_dm1 * K.pm1_dm1 + R.pm1 * C.pm1 * A.pm1 * K.pm1);
+}
+DC_HD double kmom_dwinddz(double COLPAKMOM_ds_ks, double DWIND, double DWIND_km1,
+                          double ALT_ds_km1, double ALT_ds)
+{
+    const double dDWINDdz_ks = ((DWIND_km1 - DWIND) / (ALT_ds_km1 - ALT_ds));
+    return COLPAKMOM_ds_ks * dDWINDdz_ks;
 }
 // dyn_UFLX.py:136-170, dyn_VFLX.py:134-166: vertical turbulent transport of momentum
 DC_HD double turb_momentum(double Kd, double Kd_kp1, double SMOMFLX_s, double ALTVB_s,
@@ -363,24 +370,52 @@ DC_HD double turb_momentum(double Kd, double Kd_kp1, double SMOMFLX_s, double AL
     if (k == nz - 1) return ((Kd + SMOMFLX_s) / ((ALTVB_s - ALTVB_kp1_s) * RHO_s));
     return ((Kd - Kd_kp1) / ((ALTVB_s - ALTVB_kp1_s) * RHO_s));
 }
-// dyn_functions.py:26-67
-DC_HD double turb_flux_tendency(double PHI, double PHI_kp1, double PHI_km1, double PHIVB,
-                                double PHIVB_kp1, double VAR, double VAR_kp1, double VAR_km1,
-                                double KVAR, double KVAR_kp1, double RHO, double RHOVB,
-                                double RHOVB_kp1, double COLP, double surf_flux_VAR, int k, int nz)
+// dyn_functions.py:26-67 (turb_flux_tendency_py), split for a column march:
+//   turb_iface_flux(k)  = (VAR[k-1] - VAR[k]) / (ALT[k-1] - ALT[k]) * RHOVB[k] * KVAR[k]
+// is the first term at level k and, evaluated at k+1, the second term at level k -- the same
+// expression on the same operands, so a march computes it once per interface.
+DC_HD double turb_iface_flux(double VAR_km1, double VAR, double ALT_km1, double ALT, double RHOVB,
+                             double KVAR)
 {
-    const double ALT = PHI / con_g, ALT_kp1 = PHI_kp1 / con_g, ALT_km1 = PHI_km1 / con_g;
-    const double ALTVB = PHIVB / con_g, ALTVB_kp1 = PHIVB_kp1 / con_g;
-    if (k == 0)
-        return COLP * ((+0. - ((VAR - VAR_kp1) / (ALT - ALT_kp1) * RHOVB_kp1 * KVAR_kp1)) /
-                       ((ALTVB - ALTVB_kp1) * RHO));
-    if (k == nz - 1)
-        return COLP * ((+((VAR_km1 - VAR) / (ALT_km1 - ALT) * RHOVB * KVAR) + surf_flux_VAR) /
-                       ((ALTVB - ALTVB_kp1) * RHO));
-    return COLP * ((+((VAR_km1 - VAR) / (ALT_km1 - ALT) * RHOVB * KVAR) -
-                    ((VAR - VAR_kp1) / (ALT - ALT_kp1) * RHOVB_kp1 * KVAR_kp1)) /
-                   ((ALTVB - ALTVB_kp1) * RHO));
+    return ((VAR_km1 - VAR) / (ALT_km1 - ALT) * RHOVB * KVAR);
 }
+// flux_k / flux_kp1: turb_iface_flux at the interfaces k and k+1 (ignored at the model top /
+// at the surface, where the reference puts +0 / the surface flux)
+DC_HD double turb_flux_tendency(double flux_k, double flux_kp1, double ALTVB, double ALTVB_kp1,
+                                double RHO, double COLP, double surf_flux_VAR, int k, int nz)
+{
+    if (k == 0) return COLP * ((+0. - flux_kp1) / ((ALTVB - ALTVB_kp1) * RHO));
+    if (k == nz - 1) return COLP * ((+flux_k + surf_flux_VAR) / ((ALTVB - ALTVB_kp1) * RHO));
+    return COLP * ((+flux_k - flux_kp1) / ((ALTVB - ALTVB_kp1) * RHO));
+}
+
+// what a column march carries for turb_flux_tendency: altitude of the level and of its upper
+// interface, turbulent flux through that interface (unused at the model top)
+struct TurbMarch {
+    double alt, altvb, flux;
+    DC_HD static TurbMarch top(double PHI_0, double PHIVB_0)
+    {
+        return TurbMarch{PHI_0 / div_g(), PHIVB_0 / div_g(), 0.};
+    }
+    // tendency of level k; VAR = VAR[k]; the *_kp1 arguments are only read for k < nz-1 except
+    // PHIVB_kp1.  Advances the state to level k+1.
+    DC_HD double step(double VAR, double VAR_kp1, double PHI_kp1, double PHIVB_kp1, double RHOVB_kp1,
+                      double KVAR_kp1, double RHO, double COLP, double surf_flux_VAR, int k, int nz)
+    {
+        const double altvb_kp1 = PHIVB_kp1 / div_g();
+        double alt_kp1 = alt, flux_kp1 = 0.;
+        if (k < nz - 1) {
+            alt_kp1 = PHI_kp1 / div_g();
+            flux_kp1 = turb_iface_flux(VAR, VAR_kp1, alt, alt_kp1, RHOVB_kp1, KVAR_kp1);
+        }
+        const double t =
+            turb_flux_tendency(flux, flux_kp1, altvb, altvb_kp1, RHO, COLP, surf_flux_VAR, k, nz);
+        alt = alt_kp1;
+        altvb = altvb_kp1;
+        flux = flux_kp1;
+        return t;
+    }
+};
 
 // dyn_timestep.py:34-38
 DC_HD double euler_forward_pw(double VAR, double dVARdt, Div COLP, double COLP_OLD, double dt)

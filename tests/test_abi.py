@@ -43,3 +43,22 @@ def test_product_binding_refuses_to_run_without_the_cuda_library(tmp_path, monke
     monkeypatch.setattr(_lib, 'DEFAULT_LIBRARY', str(tmp_path / 'libdyncore.so'))
     with pytest.raises(ImportError, match='no CPU fallback'):
         _lib.lib()
+
+
+def test_grid_descriptor_layout_matches_the_header(tmp_path):
+    """the ctypes mirror of dc_grid_desc (climate_model_b200/_lib.py) against the C compiler's
+    view of include/dyncore.h: size and the offset of every member"""
+    import subprocess
+    from climate_model_b200._lib import GridDesc
+    members = [n for n, _ in GridDesc._fields_]
+    prog = ['#include <stdio.h>', '#include <stddef.h>', '#include "dyncore.h"', 'int main(void) {',
+            '  printf("%zu\\n", sizeof(dc_grid_desc));']
+    prog += ['  printf("%%zu\\n", offsetof(dc_grid_desc, %s));' % n for n in members]
+    prog += ['  return 0; }']
+    src, exe = tmp_path / 'layout.c', tmp_path / 'layout'
+    src.write_text('\n'.join(prog))
+    subprocess.check_call(['gcc', '-I', os.path.join(ROOT, 'include'), '-o', str(exe), str(src)])
+    out = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    assert out[0] == ctypes.sizeof(GridDesc)
+    for n, off in zip(members, out[1:]):
+        assert getattr(GridDesc, n).offset == off, n
