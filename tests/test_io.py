@@ -84,11 +84,11 @@ def test_restart_continues_bit_for_bit(tmp_path):
     GR, F = _run(tmp_path, 3)
     fn = write_restart(GR, F, directory=str(tmp_path / 'restart'), verbose=False)
     assert fn == restart_file_name(10, 10, 6, str(tmp_path / 'restart')) and os.path.exists(fn)
-    from climate_model_b200 import solver           # uninterrupted: 2 more steps
-    for _ in range(2):
+    from climate_model_b200 import solver
+    from climate_model_b200.dyn_matsuno import Diagnostics, step_matsuno
+    from climate_model_b200.io_read_namelist import B200
+    for _ in range(2):                              # uninterrupted: 2 more steps
         GR.ts += 1
-        from climate_model_b200.dyn_matsuno import Diagnostics, step_matsuno
-        from climate_model_b200.io_read_namelist import B200
         Diagnostics.secondary_diag(**F.get(Diagnostics.fields_secondary_diag, target=B200))
         step_matsuno(GR, F)
     F.copy_device_to_host(GR, F.PROGNOSTIC_FIELDS)
