@@ -17,7 +17,7 @@ from . import _lib
 from .io_initial_conditions import initialize_fields
 from .io_read_namelist import B200, CPU, GPU, wp
 
-# host-only coupling / physics fields the reference's factories name (stgx, stgy, dimz)
+# host-only fields the reference's factories name (stgx, stgy, dimz)
 _HOST_ONLY = {'PSURF': (0, 0, 1)}
 # device-buffer address -> Grid that owns the handle the buffer is bound to; lets the
 # factories keep the reference's signatures (which carry no grid object)

@@ -62,7 +62,9 @@ i_moist_microphys = 1
 i_use_topo = 1
 n_topo_smooth = 10
 
-# PHYSICS MODULES: out of scope of this package (always off)
+# PHYSICS MODULES.  The turbulence module is built (turb_main.py; i_turbulence = 1 makes the
+# grid evaluate the coupled terms); the surface, radiation and microphysics modules are out
+# of scope of this package (always off): their fields enter through the coupling inputs
 i_surface_scheme = 0
 i_radiation = 0
 i_microphysics = 0

@@ -12,10 +12,12 @@
  * committed under tests/golden/ (tests/test_oracle_golden.py): stage-1 intermediates of
  * every kernel plus the prognostic state after 1, 2 and 10 Matsuno steps.
  *
- * Scope: the "dry" configuration of SURVEY.md section 0.4 -- every namelist dyn switch
- * = 1, physics modules off, coupling fields (KMOM, KHEAT, SMOM[XY]FLX, SSHFLX, SLHFLX,
- * dPOTTdt_RAD) exactly 0.  With zero coupling fields the turbulence/radiation terms of
- * the reference evaluate to exactly +-0.0 and are omitted here.
+ * Scope: every namelist dyn switch = 1.  orc_grid.i_coupling == 0 is the "dry" configuration
+ * of SURVEY.md section 0.4: physics modules off, coupling fields (KMOM, KHEAT, SMOM[XY]FLX,
+ * SSHFLX, SLHFLX, dPOTTdt_RAD) exactly 0; the turbulence / radiation terms of the reference
+ * evaluate to exactly +-0.0 then and are skipped.  With i_coupling != 0 they are evaluated on
+ * the given fields (pinned on tests/golden/ref_10deg_coupled.npz), and orc_compute_turbulence
+ * is the reference's turbulence module (pinned on ref_10deg_turb.npz).
  *
  * All arrays are in the REFERENCE layout: C-contiguous (i=lon, j=lat, k=level), k fastest,
  * one halo cell (nb=1) each side in i and j (main_fields.py:477-485):
