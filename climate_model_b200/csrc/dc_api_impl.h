@@ -118,6 +118,8 @@ struct dc_handle {
     int stage_kchunks;    // sigma-column chunks of the stage kernel (0 = by launch size)
     int cont_impl;        // 2 = single-pass tile kernel (default), 1 = two-sweep column kernel
     int stage_impl;       // fused mode: 3 = dc_stage3.h (default), 2 = dc_fused.h (DC_STAGE_IMPL=2)
+    int coupled_impl;     // i_coupling: 1 = kernel decomposition (default), 2 = fused dry stage
+                          // kernel + coupled increments (DC_COUPLED_IMPL=2, experimental)
     void *tma_state;      // backend-owned descriptor cache
     double **slot(int id) { return reinterpret_cast<double **>(&f) + id; }
     double *const *slot(int id) const { return reinterpret_cast<double *const *>(&f) + id; }
@@ -285,12 +287,12 @@ static int do_euler_forward(dc_handle *h, void *stream)
     return DC_OK;
 }
 
-static int do_primary_diag(dc_handle *h, void *stream)
+static int do_primary_diag(dc_handle *h, void *stream, const double *POTT = nullptr)
 {
     const Fields &f = h->f;
     const Geom &g = h->g;
     const int lo = g.j0 - HJ < 0 ? 0 : g.j0 - HJ, hi = g.j1 + HJ > g.ny + 1 ? g.ny + 1 : g.j1 + HJ;
-    PrimaryDiagBody<0> b{g,        f.COLP, f.POTT,  f.HSURF,  f.PVTF,  f.PVTFVB,
+    PrimaryDiagBody<0> b{g,        f.COLP, POTT ? POTT : f.POTT,  f.HSURF,  f.PVTF,  f.PVTFVB,
                          f.PHI,    f.PHIVB, f.POTTVB, f.PGCOL, lo,      hi,
                          make_pow_coef(con_kappa)};
     h->diag_partial = 0;
@@ -383,6 +385,40 @@ static void do_stage_fused(dc_handle *h, int stage, int part, void *stream)
     }
     if (part == DC_PART_ALL || part == DC_PART_COLP)
         dcb_d2d_async(f.COLP, f.COLP_NEW, g.plane * sizeof(double), stream);  // dyn_matsuno.py:64-67
+}
+
+// One Matsuno stage with the physics coupling terms beside the fused dry path
+// (coupled_impl == 2): continuity (+ moisture stage kernel) -> K dU/dz, K dV/dz of the input
+// state -> dry stage kernel -> coupled increments on its output -> COLP <- COLP_NEW -> full
+// primary diagnostics (the coupled terms read PHIVB, which the partial sweep does not store).
+static void do_stage_coupled(dc_handle *h, int stage, void *stream)
+{
+    const Fields &f = h->f;
+    const Geom &g = h->g;
+    const bool s0 = stage == 0;
+    const double *U = s0 ? f.UWIND : f.UWIND_OLD, *V = s0 ? f.VWIND : f.VWIND_OLD,
+                 *T = s0 ? f.POTT : f.POTT_OLD, *QV = s0 ? f.QV : f.QV_OLD,
+                 *QC = s0 ? f.QC : f.QC_OLD;
+    double *Uo = s0 ? f.UWIND_OLD : f.UWIND, *Vo = s0 ? f.VWIND_OLD : f.VWIND,
+           *To = s0 ? f.POTT_OLD : f.POTT, *QVo = s0 ? f.QV_OLD : f.QV,
+           *QCo = s0 ? f.QC_OLD : f.QC;
+    do_stage_fused(h, stage, DC_PART_CONT, stream);
+    PrepBody p{};
+    p.g = g;
+    p.UWIND = U; p.VWIND = V;
+    p.KMOM = f.KMOM; p.RHOVB = f.RHOVB; p.PHI = f.PHI; p.COLP = f.COLP;
+    p.KMOM_dUWINDdz = f.KMOM_dUWINDdz; p.KMOM_dVWINDdz = f.KMOM_dVWINDdz;
+    launch(h, "turb_prep", TurbPrepBody{p}, 1, g.nx + 1, 1, g.ny + 1, stream);
+    do_stage_fused(h, stage, DC_PART_BOUNDARY, stream);
+    do_stage_fused(h, stage, DC_PART_INTERIOR, stream);
+    TurbApplyBody a{g,       T,          QV,        QC,         f.COLP,     f.COLP_NEW,
+                    f.PHI,   f.PHIVB,    f.KMOM_dUWINDdz, f.KMOM_dVWINDdz, f.KHEAT, f.RHO,
+                    f.RHOVB, f.SMOMXFLX, f.SMOMYFLX, f.SSHFLX,  f.SLHFLX,   f.dPOTTdt_RAD,
+                    Uo,      Vo,         To,        QVo,        QCo,        f.dUFLXdt_TURB,
+                    f.dVFLXdt_TURB, f.dPOTTdt_TURB, f.dQVdt_TURB};
+    launch(h, "turb_apply", a, 1, g.nx, 1, g.ny, stream);
+    do_stage_fused(h, stage, DC_PART_COLP, stream);
+    do_primary_diag(h, stream, To);
 }
 
 // the TMA-staged stage kernel reads the periodic image UWIND[nx+2] = UWIND[2], which an
@@ -598,6 +634,8 @@ int dc_create(const dc_grid_desc *d, dc_handle **out)
     h->stage_impl = (impl && impl[0] == '2') ? 2 : 3;
     const char *kch = getenv("DC_STAGE_KCHUNKS");
     h->stage_kchunks = kch ? atoi(kch) : 0;
+    const char *cpl = getenv("DC_COUPLED_IMPL");
+    h->coupled_impl = (cpl && cpl[0] == '2') ? 2 : 1;
     const char *cimpl = getenv("DC_CONT_IMPL");
     h->cont_impl = (cimpl && cimpl[0] == '1') ? 1 : 2;
     *out = h;
@@ -1015,6 +1053,21 @@ int dc_step_matsuno(dc_handle *h, int nsteps, void *stream)
     if (fused && g.nz > NZMAX)
         return fail(DC_ERR_STATE, "dc_step_matsuno: the fused mode supports nz <= %d "
                                   "(use dc_set_mode(h, DC_MODE_KERNELS))", NZMAX);
+    if (g.i_coupling && h->mode == DC_MODE_FUSED && h->coupled_impl == 2 && g.nz <= NZMAX &&
+        h->stage_impl == 3) {
+        if ((rc = refresh_diag(h, "dc_step_matsuno", stream))) return rc;   // PHIVB
+        do_xhalo_fix(h, stream);
+        for (int s = 0; s < nsteps; s++) {
+            // boundary images of the coupling inputs (dyn_org_discretizations.py:121-249)
+            launch(h, "exchange_bc", ExchangeBCBody{g, f.KMOM, 0, g.nz + 1}, 1, g.nx, 1, g.ny,
+                   stream);
+            launch(h, "exchange_bc", ExchangeBCBody{g, f.SMOMXFLX, 0, 1}, 1, g.nx, 1, g.ny, stream);
+            launch(h, "exchange_bc", ExchangeBCBody{g, f.SMOMYFLX, 0, 1}, 1, g.nx, 1, g.ny, stream);
+            dcb_d2d_async(f.COLP_OLD, f.COLP, b2, stream);      // dyn_matsuno.py:34
+            for (int stage = 0; stage < 2; stage++) do_stage_coupled(h, stage, stream);
+        }
+        return backend_status("dc_step_matsuno");
+    }
     if (fused) {
         do_xhalo_fix(h, stream);
         for (int s = 0; s < nsteps; s++) {

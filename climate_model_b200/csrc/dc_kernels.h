@@ -217,7 +217,6 @@ struct PrepBody {
     DC_HD void operator()(int i, int j) const
     {
         const int nx = g.nx, ny = g.ny, nz = g.nz;
-        const double *u = UFLX, *v = VFLX;
         if (j <= ny) {  // dyn_UVFLX_prepare.py:262-278
             const int wall = (j == 1) ? -1 : ((j == ny) ? 1 : 0);
             WWIND_UWIND[g.idx(i, j, 0)] = 0.;
@@ -239,7 +238,15 @@ struct PrepBody {
                     interp_ks(VWIND[g.idx(i, j, k)], VWIND[g.idx(i, j, k - 1)], g.dsigma[k],
                               g.dsigma[k - 1], mkdiv(g.dsigma[k] + g.dsigma[k - 1], g.r_dss[k]));
         }
-        if (g.i_coupling) {
+        if (g.i_coupling) coupling(i, j);
+        prep_rest(i, j);
+    }
+    // K dU/dz, K dV/dz on the interfaces (dyn_UVFLX_prepare.py:298-343); also the whole job of
+    // TurbPrepBody.  threads as operator()
+    DC_HD void coupling(int i, int j) const
+    {
+        const int nx = g.nx, ny = g.ny, nz = g.nz;
+        {
             // the altitude and the wind of level k are carried to interface k+1
             if (j <= ny) {
                 KMOM_dUWINDdz[g.idx(i, j, 0)] = 0.;
@@ -276,6 +283,11 @@ struct PrepBody {
                 }
             }
         }
+    }
+    DC_HD void prep_rest(int i, int j) const
+    {
+        const int nx = g.nx, ny = g.ny, nz = g.nz;
+        const double *u = UFLX, *v = VFLX;
         for (int k = 0; k < nz; k++) {  // dyn_UVFLX_prepare.py:345-436
             CFLX[g.idx(i, j, k)] =
                 calc_CFLX(v[g.idx(i - 1, j - 1, k)], v[g.idx(i, j - 1, k)], v[g.idx(i - 1, j, k)],
@@ -901,6 +913,129 @@ struct SecondaryDiagBody {
             WINDX[g.idx(i, j, k)] = wx;
             WINDY[g.idx(i, j, k)] = wy;
             WIND[g.idx(i, j, k)] = sqrt(wx * wx + wy * wy);
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------
+// coupled terms BESIDE the fused dry stage kernel (dc_handle::coupled_impl == 2; experimental,
+// off by default).  The stage kernel advances U, V, POTT with the dry tendencies; these two
+// kernels add what the physics coupling fields contribute:
+//   TurbPrepBody   K dU/dz, K dV/dz on the interfaces from the stage's INPUT state (= the
+//                  coupling part of PrepBody).  threads: i in [1, nx+1], j in [1, ny+1]
+//   TurbApplyBody  X_out += dt * dX_turb / C_new for U, V, POTT (QV, QC) and the boundary
+//                  images of the updated cells; dX_turb as in dyn_UFLX.py:136-170,
+//                  dyn_VFLX.py:134-166, dyn_POTT.py:87-108, dyn_moist.py:100-112, C_new as in the
+//                  Euler step (dyn_timestep.py:34-79).  threads: i in [1, nx], j in [1, ny]
+// The reference adds these terms INSIDE the tendency sum; adding them after the Euler step is
+// the same arithmetic in another order (differences at rounding level, tests: tolerances).
+// ---------------------------------------------------------------------------------------
+struct TurbPrepBody {
+    PrepBody p;
+    DC_HD void operator()(int i, int j) const { p.coupling(i, j); }
+};
+
+struct TurbApplyBody {
+    Geom g;
+    const double *POTT_in, *QV_in, *QC_in;     // the stage's input state (vertical gradients)
+    const double *COLP, *COLP_NEW;             // column pressure of the input state / new
+    const double *PHI, *PHIVB, *KMOM_dUWINDdz, *KMOM_dVWINDdz, *KHEAT, *RHO, *RHOVB, *SMOMXFLX,
+        *SMOMYFLX, *SSHFLX, *SLHFLX, *dPOTTdt_RAD;
+    double *U_out, *V_out, *T_out, *QV_out, *QC_out;
+    double *dUFLXdt_TURB, *dVFLXdt_TURB, *dPOTTdt_TURB, *dQVdt_TURB;
+    DC_HD Six six_u(const double *F, int i, int j, int k) const
+    {
+        return Six{F[g.idx(i, j, k)],     F[g.idx(i - 1, j, k)],     F[g.idx(i, j - 1, k)],
+                   F[g.idx(i, j + 1, k)], F[g.idx(i - 1, j - 1, k)], F[g.idx(i - 1, j + 1, k)]};
+    }
+    DC_HD Six six_v(const double *F, int i, int j, int k) const
+    {
+        return Six{F[g.idx(i, j, k)],     F[g.idx(i, j - 1, k)],     F[g.idx(i - 1, j, k)],
+                   F[g.idx(i + 1, j, k)], F[g.idx(i - 1, j - 1, k)], F[g.idx(i + 1, j - 1, k)]};
+    }
+    DC_HD void tracer(const double *Q_in, double *Q_out, double *TURB, double surf, double c,
+                      Div d_c, int i, int j) const
+    {
+        const int nz = g.nz;
+        TurbMarch tm = TurbMarch::top(PHI[g.idx(i, j, 0)], PHIVB[g.idx(i, j, 0)]);
+        double q = Q_in[g.idx(i, j, 0)];
+        for (int k = 0; k < nz; k++) {
+            const int kp = k < nz - 1 ? k + 1 : k;
+            const double q_kp1 = Q_in[g.idx(i, j, kp)];
+            const double t = tm.step(q, q_kp1, PHI[g.idx(i, j, kp)], PHIVB[g.idx(i, j, k + 1)],
+                                     RHOVB[g.idx(i, j, k + 1)], KHEAT[g.idx(i, j, k + 1)],
+                                     RHO[g.idx(i, j, k)], c, surf, k, nz);
+            if (TURB) TURB[g.idx(i, j, k)] = t;
+            put_mass(g, Q_out, i, j, k, Q_out[g.idx(i, j, k)] + g.dt * t / d_c);
+            q = q_kp1;
+        }
+    }
+    DC_HD void operator()(int i, int j) const
+    {
+        const int nx = g.nx, ny = g.ny, nz = g.nz;
+        const double A = g.A[g.row(j)], A_jm1 = g.A[g.row(j - 1)], A_jp1 = g.A[g.row(j + 1)];
+        const double *CN = COLP_NEW;
+        const double c = COLP[g.idx2(i, j)], cn = CN[g.idx2(i, j)];
+        const Div d_c = mkdiv(cn);
+        {   // U
+            const Div d_is = mkdiv(interp_COLPA_is(
+                cn, CN[g.idx2(i - 1, j)], CN[g.idx2(i, j - 1)], CN[g.idx2(i, j + 1)],
+                CN[g.idx2(i - 1, j + 1)], CN[g.idx2(i - 1, j - 1)], A, A_jm1, A_jp1, j, ny));
+            const double smomflx_s = interp_VAR_ds(six_u(SMOMXFLX, i, j, 0), true, j, ny);
+            double altvb = interp_VAR_ds(six_u(PHIVB, i, j, 0), true, j, ny) / div_g();
+            double kd = KMOM_dUWINDdz[g.idx(i, j, 0)];
+            for (int k = 0; k < nz; k++) {
+                const double altvb_kp1 =
+                    interp_VAR_ds(six_u(PHIVB, i, j, k + 1), true, j, ny) / div_g();
+                const double kd_kp1 = KMOM_dUWINDdz[g.idx(i, j, k + 1)];
+                const double t =
+                    turb_momentum(kd, kd_kp1, smomflx_s, altvb, altvb_kp1,
+                                  interp_VAR_ds(six_u(RHO, i, j, k), true, j, ny), k, nz);
+                dUFLXdt_TURB[g.idx(i, j, k)] = t;
+                put_xstag(g, U_out, i, j, k, U_out[g.idx(i, j, k)] + g.dt * t / d_is);
+                altvb = altvb_kp1;
+                kd = kd_kp1;
+            }
+        }
+        if (j >= 2) {   // V (rows 1 and ny+1 are walls: 0)
+            const Div d_js = mkdiv(interp_COLPA_js(
+                cn, CN[g.idx2(i, j - 1)], CN[g.idx2(i - 1, j)], CN[g.idx2(i + 1, j)],
+                CN[g.idx2(i + 1, j - 1)], CN[g.idx2(i - 1, j - 1)], A, A_jm1));
+            const double smomflx_s = interp_VAR_ds(six_v(SMOMYFLX, i, j, 0), false, i, nx);
+            double altvb = interp_VAR_ds(six_v(PHIVB, i, j, 0), false, i, nx) / div_g();
+            double kd = KMOM_dVWINDdz[g.idx(i, j, 0)];
+            for (int k = 0; k < nz; k++) {
+                const double altvb_kp1 =
+                    interp_VAR_ds(six_v(PHIVB, i, j, k + 1), false, i, nx) / div_g();
+                const double kd_kp1 = KMOM_dVWINDdz[g.idx(i, j, k + 1)];
+                const double t =
+                    turb_momentum(kd, kd_kp1, smomflx_s, altvb, altvb_kp1,
+                                  interp_VAR_ds(six_v(RHO, i, j, k), false, i, nx), k, nz);
+                dVFLXdt_TURB[g.idx(i, j, k)] = t;
+                put_ystag(g, V_out, i, j, k, V_out[g.idx(i, j, k)] + g.dt * t / d_js);
+                altvb = altvb_kp1;
+                kd = kd_kp1;
+            }
+        }
+        {   // POTT: turbulent transport + surface sensible heat flux + radiative heating
+            TurbMarch tm = TurbMarch::top(PHI[g.idx(i, j, 0)], PHIVB[g.idx(i, j, 0)]);
+            const double surf = SSHFLX[g.idx2(i, j)] / con_cp;
+            double p = POTT_in[g.idx(i, j, 0)];
+            for (int k = 0; k < nz; k++) {
+                const int kp = k < nz - 1 ? k + 1 : k;
+                const double p_kp1 = POTT_in[g.idx(i, j, kp)];
+                const double t = tm.step(p, p_kp1, PHI[g.idx(i, j, kp)], PHIVB[g.idx(i, j, k + 1)],
+                                         RHOVB[g.idx(i, j, k + 1)], KHEAT[g.idx(i, j, k + 1)],
+                                         RHO[g.idx(i, j, k)], c, surf, k, nz);
+                dPOTTdt_TURB[g.idx(i, j, k)] = t / c * 3600.;   // [K hr-1], dyn_POTT.py:97
+                const double d = t + (dPOTTdt_RAD[g.idx(i, j, k)] * c);
+                put_mass(g, T_out, i, j, k, T_out[g.idx(i, j, k)] + g.dt * d / d_c);
+                p = p_kp1;
+            }
+        }
+        if (g.i_moist) {
+            tracer(QV_in, QV_out, dQVdt_TURB, SLHFLX[g.idx2(i, j)] / con_Lh, c, d_c, i, j);
+            tracer(QC_in, QC_out, nullptr, 0., c, d_c, i, j);
         }
     }
 };

@@ -599,3 +599,50 @@ def test_member_stream_equals_one_member_at_a_time(g10):
             _eq(mem[n], w[n], n)
     assert not np.array_equal(want[0]['POTT'], want[1]['POTT'])
     GR.close()
+
+
+# ---------------------------------------------------------------------------------------
+# experimental: coupled terms beside the fused dry stage kernel (DC_COUPLED_IMPL=2)
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize('fast', [False, True])
+@pytest.mark.parametrize('fixture', ['ref_10deg_coupled.npz', 'ref_10deg_turb.npz'])
+def test_coupled_increments_beside_the_fused_stage_kernel(fixture, fast, monkeypatch):
+    """fused dry stage kernel + TurbPrepBody / TurbApplyBody (X += dt * dX_turb / C after the
+    Euler step instead of inside the tendency sum): not the reference's summation order, so the
+    comparison with the real reference's outputs uses the parity tolerances, in both arithmetic
+    modes; the kernel decomposition stays the default"""
+    from helpers import TOL, state_err
+    from climate_model_b200 import _lib
+    from climate_model_b200.dyn_matsuno import Diagnostics, step_matsuno
+    from climate_model_b200.io_read_namelist import B200
+    from climate_model_b200.turb_main import Turbulence
+    monkeypatch.setenv('DC_COUPLED_IMPL', '2')
+    strict = _lib.library_path()
+    _lib.use_library(build_emu(fast=fast))
+    try:
+        g = load_golden(fixture)
+        turb = 'T1_KMOM' in g
+        GR = grid_from_golden(g)
+        F = fields_from_golden(GR, g)
+        TURB = Turbulence(GR, target=B200)
+        Diagnostics.primary_diag(GR.GRF[B200],
+                                 **F.get(Diagnostics.fields_primary_diag, target=B200))
+        launches = _lib.lib().dc_launch_count(GR.dyncore())
+        for ts in range(1, 11):
+            Diagnostics.secondary_diag(**F.get(Diagnostics.fields_secondary_diag, target=B200))
+            if turb:
+                TURB.compute_turbulence(GR, **F.get(TURB.fields_main, target=B200))
+            step_matsuno(GR, F)
+            if ts == 1:   # 3 BC + 2 x (continuity, moisture, prep, stage, apply, diagnostics) + xhalo
+                n = _lib.lib().dc_launch_count(GR.dyncore()) - launches - 1 - int(turb)
+                assert n == 3 + 2 * 6 + 1, n
+            if ts in (1, 2, 10):
+                F.copy_device_to_host(GR, F.PROGNOSTIC_FIELDS)
+                ref = {n: g['N%d_%s' % (ts, n)] for n in STATE}
+                for n in STATE:
+                    e = state_err(n, F.host, ref)
+                    assert e <= TOL[n], 'N%d %s: %.3e > %.0e' % (ts, n, e, TOL[n])
+                    assert e <= 1e-2 * TOL[n], (n, e)    # actual level: 1e-15 .. 1e-12
+        GR.close()
+    finally:
+        _lib.use_library(strict)
