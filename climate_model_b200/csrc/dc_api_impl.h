@@ -825,7 +825,7 @@ int dc_primary_diag(dc_handle *h, void *stream)
 
 int dc_secondary_diag(dc_handle *h, void *stream)
 {
-    DC_ENTRY_CHECK("dc_secondary_diag");
+    if (!h) return fail(DC_ERR_ARG, "dc_secondary_diag: NULL handle");   // column-local: bands ok
     int rc;
     if ((rc = need(h, "dc_secondary_diag",
                    {F_POTTVB, F_PVTFVB, F_POTT, F_PVTF, F_UWIND, F_VWIND, F_TAIRVB, F_PAIRVB,
@@ -835,7 +835,10 @@ int dc_secondary_diag(dc_handle *h, void *stream)
     const Fields &f = h->f;
     SecondaryDiagBody b{h->g,  f.POTTVB, f.PVTFVB, f.POTT, f.PVTF, f.UWIND, f.VWIND, f.TAIRVB,
                         f.PAIRVB, f.RHOVB, f.TAIR, f.PAIR, f.RHO,  f.WINDX, f.WINDY, f.WIND};
-    launch(h, "secondary_diag", b, 0, h->g.nx + 1, 0, h->g.ny + 1, stream);
+    // every held row (WINDY reads VWIND one row further north, which a band holds too)
+    const Geom &g = h->g;
+    const int lo = g.j0 - HJ < 0 ? 0 : g.j0 - HJ, hi = g.j1 + HJ > g.ny + 1 ? g.ny + 1 : g.j1 + HJ;
+    launch(h, "secondary_diag", b, 0, g.nx + 1, lo, hi, stream);
     return backend_status("dc_secondary_diag");
 }
 

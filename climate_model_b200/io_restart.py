@@ -32,18 +32,21 @@ def _grid_key(GR):
 
 
 def write_restart(GR, F, directory='../restart', verbose=True):
-    """io_restart.py:23-60; copies the state from the device first"""
-    if GR.band[1] > 1:
-        raise NotImplementedError('restart files of a latitude-band run: gather the bands on '
-                                  'one rank first')
+    """io_restart.py:23-60; copies the state from the device first.  Latitude bands: the bands
+    are gathered on rank 0, which writes the same single file a one-device run writes (a
+    restart file does not depend on the number of ranks)"""
+    from .parallel_bands import gather_field
+    names = STATE_FIELDS + (COUPLING_INPUTS if GR.i_coupling else [])
+    for n in names:
+        gather_field(GR, F, n)
+    filename = restart_file_name(*_grid_key(GR), directory=directory)
+    if GR.band[0] != 0:
+        return filename
     if verbose:
         print('###########################################')
         print('WRITE RESTART')
         print('###########################################')
-    names = STATE_FIELDS + (COUPLING_INPUTS if GR.i_coupling else [])
-    for n in names:
-        F.to_host(GR, n)
-    grid = {'params': dict(GR.params), 'band': GR.band, 'ts': GR.ts,
+    grid = {'params': dict(GR.params), 'ts': GR.ts,
             'sim_time_sec': GR.sim_time_sec, 'nc_output_count': GR.nc_output_count,
             'from_arrays': None}
     if not hasattr(GR, 'lon_rad'):        # a grid made from dumped GRF arrays (tests/golden)
@@ -52,7 +55,6 @@ def write_restart(GR, F, directory='../restart', verbose=True):
         grid['from_arrays'] = a
     out = {'GR': grid, 'F': {n: np.array(F.host[n]) for n in names}}
     os.makedirs(directory, exist_ok=True)
-    filename = restart_file_name(*_grid_key(GR), directory=directory)
     with open(filename + '.tmp', 'wb') as f:
         pickle.dump(out, f, protocol=pickle.HIGHEST_PROTOCOL)
     os.replace(filename + '.tmp', filename)      # never leave a half-written restart file
@@ -66,10 +68,11 @@ def _load(filename):
         return pickle.load(f)
 
 
-def load_restart_grid(dlat_deg, dlon_deg, nz, directory='../restart'):
-    """io_restart.py:64-75: the grid of the interrupted run incl. its time-step counter"""
+def load_restart_grid(dlat_deg, dlon_deg, nz, directory='../restart', band=(0, 1)):
+    """io_restart.py:64-75: the grid of the interrupted run incl. its time-step counter;
+    `band` = (rank, nranks) of the run that continues (need not be that of the writer)"""
     g = _load(restart_file_name(dlat_deg, dlon_deg, nz, directory))['GR']
-    GR = Grid(band=g['band'], from_arrays=g['from_arrays'], **g['params'])
+    GR = Grid(band=band, from_arrays=g['from_arrays'], **g['params'])
     GR.ts, GR.sim_time_sec, GR.nc_output_count = g['ts'], g['sim_time_sec'], g['nc_output_count']
     return GR
 

@@ -14,6 +14,7 @@ exchanged longitude slabs at four points per stage.
 """
 import ctypes
 
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -110,3 +111,67 @@ def step_matsuno_banded(GR, F, nsteps, stream):
         _lib.check(L.dc_step_begin(h, stream))
         for stage in (0, 1):
             comm.stage(stage, stream)
+
+
+# ---------------------------------------------------------------------------------------
+# process set-up and gathers for the drivers (solver.py, io_nc_output.py, io_restart.py)
+# ---------------------------------------------------------------------------------------
+def init_bands():
+    """(rank, nranks) of this process.  Under torchrun (WORLD_SIZE > 1) the process group is
+    created here: NCCL with one GPU per rank when the library runs on CUDA, gloo for the host
+    emulation of the tests; a plain `python -m climate_model_b200.solver` is (0, 1)."""
+    import os
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if world == 1:
+        return 0, 1
+    if not dist.is_initialized():
+        if _lib.is_cuda():
+            local = int(os.environ.get('LOCAL_RANK', '0'))
+            torch.cuda.set_device(local)
+            dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+        else:
+            dist.init_process_group('gloo')
+    return dist.get_rank(), dist.get_world_size()
+
+
+def owned_rows(GR, fny):
+    """rows [ja, jb] of a reference-layout field with fny rows that THIS rank's results are
+    authoritative for: its band, plus the wall-side halo rows on the first and last rank"""
+    rank, nranks = GR.band
+    return (0 if rank == 0 else int(GR.j0)), (fny - 1 if rank == nranks - 1 else int(GR.j1))
+
+
+def gather_field(GR, F, name, dst=0):
+    """device -> host on every rank (F.to_host), then the owned rows of all bands are
+    collected in F.host[name] of rank `dst`: that host array is then the whole field, as on
+    one device.  Point-to-point sends in rank order (output / restart path, not the step)."""
+    F.to_host(GR, name)
+    rank, nranks = GR.band
+    if nranks == 1:
+        return
+    group = getattr(getattr(GR, 'comm', None), 'group', None)
+    host = F.host[name]
+    fny = host.shape[1]
+    on_gpu = F.torch_device.type == 'cuda'
+
+    def wire(a):        # NCCL moves device memory, gloo host memory
+        t = torch.from_numpy(np.ascontiguousarray(a))
+        return t.to(F.torch_device) if on_gpu else t
+
+    if rank == dst:
+        for src in range(nranks):
+            if src == dst:
+                continue
+            j0, j1 = band_rows_of(GR, src)
+            ja, jb = (0 if src == 0 else j0), (fny - 1 if src == nranks - 1 else j1)
+            buf = wire(np.empty((host.shape[0], jb - ja + 1, host.shape[2]), dtype=host.dtype))
+            dist.recv(buf, src=src, group=group)
+            host[:, ja:jb + 1, :] = buf.cpu().numpy()
+    else:
+        ja, jb = owned_rows(GR, fny)
+        dist.send(wire(host[:, ja:jb + 1, :]), dst=dst, group=group)
+
+
+def band_rows_of(GR, rank):
+    from .main_grid import band_rows
+    return band_rows(int(GR.ny), rank, GR.band[1])

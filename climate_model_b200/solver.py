@@ -3,6 +3,8 @@
     python -m climate_model_b200.solver [--nsteps N] [--output DIR | --no-output]
                                         [--restart-dir DIR] [--save-restart] [--load-restart]
                                         [name=value ...]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        -m climate_model_b200.solver ...          # N latitude bands, one GPU each
 
 Builds Grid and ModelFields from the namelist (plus `name=value` overrides of grid / initial
 condition parameters), runs one primary_diag, then per time step: print-diagnostics every
@@ -41,6 +43,7 @@ def run(nsteps=None, verbose=True, ic=None, i_turbulence=None, output_path=None,
     `nsteps`: number of steps of THIS call (default: up to GR.nts)"""
     from .io_nc_output import constant_fields_to_NC, fields_for_output, output_to_NC
     from .io_restart import load_existing_fields, load_restart_grid, write_restart
+    from .parallel_bands import attach_communicator, gather_field, init_bands
     i_turbulence = int(nl.i_turbulence if i_turbulence is None else i_turbulence)
     i_save_to_restart = int(nl.i_save_to_restart if i_save_to_restart is None
                             else i_save_to_restart)
@@ -48,15 +51,20 @@ def run(nsteps=None, verbose=True, ic=None, i_turbulence=None, output_path=None,
                               else i_load_from_restart)
     if i_turbulence:
         overrides.setdefault('i_coupling', 1)
+    band = init_bands()                           # (0, 1) unless launched by torchrun
+    diag = verbose                                # collective with bands: every rank calls it
+    verbose = verbose and band[0] == 0
     if i_load_from_restart:                       # main_grid.py:88-90, main_fields.py:61-62
         GR = load_restart_grid(overrides.get('dlat_deg', nl.dlat_deg),
                                overrides.get('dlon_deg', nl.dlon_deg),
-                               overrides.get('nz', nl.nz), directory=restart_dir)
+                               overrides.get('nz', nl.nz), directory=restart_dir, band=band)
         F = load_existing_fields(GR, directory=restart_dir)
     else:
-        GR = Grid(**{k: v for k, v in overrides.items() if k in GRID_KEYS})
+        GR = Grid(band=band, **{k: v for k, v in overrides.items() if k in GRID_KEYS})
         F = ModelFields(GR, **(ic or {}))
-    if output_path is not None:
+    if band[1] > 1:
+        attach_communicator(GR, F)
+    if output_path is not None and band[0] == 0:
         constant_fields_to_NC(GR, F, output_path=output_path)     # solver.py:66
     if i_turbulence:
         from .turb_main import Turbulence
@@ -69,7 +77,7 @@ def run(nsteps=None, verbose=True, ic=None, i_turbulence=None, output_path=None,
         GR.timer.start('total')
         GR.ts += 1
         GR.sim_time_sec = GR.ts * GR.dt
-        if verbose:
+        if diag:
             print_ts_info(GR, F, force=(GR.ts == 1))
         GR.timer.start('diag')
         Diagnostics.secondary_diag(**F.get(Diagnostics.fields_secondary_diag, target=B200))
@@ -82,9 +90,10 @@ def run(nsteps=None, verbose=True, ic=None, i_turbulence=None, output_path=None,
         if output_path is not None and GR.i_out_nth_ts and GR.ts % GR.i_out_nth_ts == 0:
             GR.timer.start('IO')                  # solver.py:152-164
             for n in fields_for_output(F, output_fields):
-                F.to_host(GR, n)
+                gather_field(GR, F, n)            # bands: collected on rank 0
             GR.nc_output_count += 1
-            output_to_NC(GR, F, fields=output_fields, output_path=output_path)
+            if band[0] == 0:
+                output_to_NC(GR, F, fields=output_fields, output_path=output_path)
             GR.timer.stop('IO')
         if i_save_to_restart and GR.i_restart_nth_ts and GR.ts % GR.i_restart_nth_ts == 0:
             GR.timer.start('IO')                  # solver.py:170-176
@@ -93,8 +102,9 @@ def run(nsteps=None, verbose=True, ic=None, i_turbulence=None, output_path=None,
         GR.timer.stop('total')
     if F.torch_device.type == 'cuda':
         torch.cuda.synchronize()
-    if verbose:
+    if diag:
         print_ts_info(GR, F, force=True)
+    if verbose:
         cells = int(GR.nx) * int(GR.ny) * int(GR.nz)
         dt = time.time() - t0
         n = GR.ts - ts0

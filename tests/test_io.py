@@ -129,3 +129,56 @@ def test_testsuite_comparison(tmp_path, capsys):
     assert failed and devs['UWIND'] > 1e-4
     for g in (GRa, GRb, GRc):
         g.close()
+
+
+def _torchrun_solver(world, port, **cfg):
+    import json
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, MASTER_ADDR='127.0.0.1', OMP_NUM_THREADS='1')
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1',
+           '--nproc-per-node=%d' % world, '--master-addr', '127.0.0.1', '--master-port', str(port),
+           os.path.join(here, 'solver_worker.py'), json.dumps(cfg)]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    return r.stdout
+
+
+def test_banded_solver_writes_the_same_output_and_restart(tmp_path):
+    """the solver time loop on 3 latitude bands (torchrun, gloo): rank 0 gathers the bands and
+    writes the same NetCDF file and the same restart file as the one-device run; a restart
+    written by 3 ranks continues on 2 ranks bit for bit"""
+    from climate_model_b200.testsuite import compare_outputs
+    ic = dict(UWIND_random_pert=2.0, VWIND_random_pert=2.0, POTT_random_pert=1.0,
+              QV_random_pert=0.0005, COLP_random_pert=100.)
+    common = dict(verbose=True, ic=ic, i_sim_n_days=0.5 / 24, i_restart_nth_day=0.5 / 24,
+                  i_save_to_restart=1, **GRID)
+    GR, F = _run(tmp_path, None, sub='one', i_sim_n_days=0.5 / 24)
+    nts = GR.ts
+    GR.close()
+    out = _torchrun_solver(3, 29731, output_path=str(tmp_path / 'three'),
+                           restart_dir=str(tmp_path / 'restart3'), **common)
+    assert out.count('vmax') >= 2 and 'WRITE RESTART' in out          # printed by rank 0 only
+    one, three = str(tmp_path / 'one' / 'out0001.nc'), str(tmp_path / 'three' / 'out0001.nc')
+    with netcdf_file(one, 'r', mmap=False) as a, netcdf_file(three, 'r', mmap=False) as b:
+        assert sorted(a.variables) == sorted(b.variables)
+        for n in a.variables:
+            assert np.array_equal(a.variables[n][:], b.variables[n][:], equal_nan=True), n
+    failed, dev_sum, _ = compare_outputs(one, three, verbose=False)
+    assert not failed and dev_sum == 0
+    # continue to the next output time: 2 bands from the 3-band restart == one device from the
+    # same file == the uninterrupted one-device run
+    from climate_model_b200 import solver
+    cont = dict(nsteps=nts, verbose=False, i_load_from_restart=1, i_save_to_restart=0,
+                restart_dir=str(tmp_path / 'restart3'), **GRID)
+    _torchrun_solver(2, 29732, output_path=str(tmp_path / 'cont2'), **cont)
+    GR1, F1 = solver.run(output_path=str(tmp_path / 'cont1'), **cont)
+    assert GR1.ts == 2 * nts and GR1.nc_output_count == 2
+    GR1.close()
+    GR2, F2 = _run(tmp_path, None, sub='straight', i_sim_n_days=1. / 24)
+    GR2.close()
+    files = [str(tmp_path / d / 'out0002.nc') for d in ('cont2', 'cont1', 'straight')]
+    for other in files[1:]:
+        failed, dev_sum, devs = compare_outputs(files[0], other, verbose=False)
+        assert not failed and dev_sum == 0 and len(devs) == 7, (other, devs)
