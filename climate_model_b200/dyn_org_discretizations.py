@@ -10,7 +10,7 @@ and then runs the matching fine-grained entry of include/dyncore.h.
 import torch
 
 from . import _lib
-from .io_read_namelist import B200, CPU, GPU
+from .io_read_namelist import B200
 from .misc_utilities import function_input_fields
 
 

@@ -10,7 +10,7 @@ import numpy as np
 from scipy.interpolate import RectBivariateSpline, interp1d
 
 from . import namelist as nl
-from .io_constants import con_cp, con_g, con_kappa, con_Rd, wp
+from .io_constants import con_kappa, wp
 
 _DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'data', 'ic_data.npz')
 _cache = {}

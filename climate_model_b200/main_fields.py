@@ -15,7 +15,7 @@ import torch
 
 from . import _lib
 from .io_initial_conditions import initialize_fields
-from .io_read_namelist import B200, CPU, GPU, wp
+from .io_read_namelist import CPU, wp
 
 # host-only fields the reference's factories name (stgx, stgy, dimz)
 _HOST_ONLY = {'PSURF': (0, 0, 1)}

@@ -19,7 +19,6 @@ physics modules (surface, radiation, microphysics) of the reference are out of s
 import argparse
 import time
 
-import numpy as np
 import torch
 
 from . import namelist as nl
