@@ -1,0 +1,49 @@
+"""bench.py's output contract, checked without a GPU: `--impl reference` (the oracle port on
+the host cores, the real reference arm) and the LOGIC of the B200 arm against the host
+emulation (`--emu`; that line is tagged "emu": true and is never a measurement).  Exactly one
+line on stdout, valid JSON, every key the driver reads."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BASE_KEYS = {'metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step',
+             'higher_is_better', 'scaling', 'vs_baseline', 'dtype', 'data', 'config', 'e2e'}
+
+
+def _bench(*args):
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py')] + list(args),
+                       capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = r.stdout.splitlines()
+    assert len(lines) == 1, lines          # ONE JSON line, nothing else on stdout
+    return json.loads(lines[0])
+
+
+def test_reference_arm_line():
+    d = _bench('--impl', 'reference', '--workload', 'cfg1', '--steps', '2', '--warmup', '1')
+    assert BASE_KEYS <= set(d) and d['impl'] == 'reference'
+    assert d['metric'] == 'dyn-core cell-updates/s' and d['unit'] == 'cell-updates/s'
+    assert d['value'] > 0 and d['higher_is_better'] is True and d['vs_baseline'] is None
+    assert d['dtype'] == 'f64' and d['data'] == 'synthetic' and 'workload' in d['config']
+    cb = d['cpu_baseline']
+    assert cb['kind'] == 'port' and cb['cores'] >= 1 and cb['value'] == d['value'] and cb['sample']
+    assert d['e2e'] == {'value': d['value'], 'unit': d['unit'], 'h2d_bytes_per_step': 0,
+                        'd2h_bytes_per_step': 0}
+
+
+def test_b200_arm_logic_on_the_host_emulation():
+    d = _bench('--emu', '--workload', 'cfg1', '--steps', '2', '--warmup', '1')
+    assert d['emu'] is True                      # never mistaken for a measurement
+    assert BASE_KEYS | {'roofline', 'step_roofline', 'gpu_launches', 'clocks', 'cpu_baseline',
+                        'kernels_ms_per_step', 'ms_per_step_with_kernel_events'} <= set(d)
+    assert d['n_gpus'] == 1 and d['steps'] == 2 and d['warmup'] == 1 and d['scaling'] == 'strong'
+    assert d['config']['workload'].startswith('5deg') and d['config']['finite'] is True
+    # 2 steps x (COLP_OLD copy aside) 2 stages x (continuity, stage kernel, diagnostics) + x-halo fix
+    assert d['gpu_launches'] == 2 * (2 * 3 + 1)
+    e = d['e2e']
+    assert e['members'] == 12 and e['h2d_bytes_per_step'] == e['d2h_bytes_per_step'] > 0
+    assert e['value'] > 0 and e['finite'] is True and e['one_state_at_a_time_ms'] > 0
+    assert d['step_roofline']['algorithmic_bytes_per_cell_update'] == 216
+    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['value'] > 0
