@@ -154,6 +154,13 @@ int dc_run_diag(dc_handle *h, void *scratch, size_t nbytes, void *stream);
  *   intermediate field written as the reference does (same result, bit for bit). */
 enum { DC_MODE_FUSED = 0, DC_MODE_KERNELS = 1 };
 int dc_set_mode(dc_handle *h, int mode);
+/* Development switches, read from the environment by dc_create (defaults = the measured best):
+ *   DC_STAGE_IMPL=2     second-generation fused stage kernel (csrc/dc_fused.h) instead of the
+ *                       TMA-staged one (csrc/dc_stage3.h)
+ *   DC_STAGE_KCHUNKS=n  sigma-column chunks of the stage kernel (default: by launch size)
+ *   DC_CONT_IMPL=1      two-sweep column continuity kernel instead of the single-pass tile kernel
+ *   DC_COUPLED_IMPL=2   i_coupling: coupled terms as increments beside the fused dry stage
+ *                       kernel instead of the kernel decomposition (experimental) */
 int dc_step_matsuno(dc_handle *h, int nsteps, void *stream);
 
 /* ---- latitude-band decomposition (one handle per rank, dc_grid_desc.j0 / j1) ----------
