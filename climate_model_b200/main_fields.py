@@ -146,6 +146,60 @@ class ModelFields:
             torch.cuda.current_stream(self.torch_device).synchronize()
 
 
+    # ------------------------------------------------------------ latitude bands: band-shaped I/O
+    # The reference-layout host arrays cover the whole grid on every rank.  A caller that only
+    # owns its band (e2e leg of bench.py on N GPUs) moves just the rows this rank holds:
+    # a contiguous (fnx, rows, nk) pinned buffer <-> device, and a strided device-side copy
+    # between that and the reference-layout staging that dc_import_field / dc_export_field
+    # work on (torch copies only, no extra kernels of this library).
+    def field_shape(self, n):
+        d = self.fdict[n]
+        GR = OWNERS.get(self.device[n].data_ptr())
+        return (int(GR.nx) + 2 + d['stgx'], int(GR.ny) + 2 + d['stgy'], int(d['dimz']))
+
+    def held_rows(self, GR, n):
+        """rows [ja, jb] of field n (reference layout) this rank holds: its band and the halo
+        rows beside it (csrc/dc_api_impl.h: held_rows)"""
+        fny = self.field_shape(n)[1]
+        return max(0, int(GR.j0) - 2), min(int(GR.j1) + 3, fny - 1)
+
+    def band_buffer(self, GR, n):
+        """page-locked host tensor (fnx, held rows, nk) for to_device_band / to_host_band"""
+        fnx, _, nk = self.field_shape(n)
+        ja, jb = self.held_rows(GR, n)
+        pin = self.torch_device.type == 'cuda'
+        return torch.empty((fnx, jb - ja + 1, nk), dtype=torch.float64, pin_memory=pin)
+
+    def _stage_band(self, nelem):
+        if getattr(self, '_staging_b', None) is None or self._staging_b.numel() < nelem:
+            self._staging_b = torch.empty(nelem, dtype=torch.float64, device=self.torch_device)
+        return self._staging_b[:nelem]
+
+    def to_device_band(self, GR, n, hb):
+        fnx, fny, nk = self.field_shape(n)
+        ja, jb = self.held_rows(GR, n)
+        assert tuple(hb.shape) == (fnx, jb - ja + 1, nk), (n, tuple(hb.shape))
+        sb = self._stage_band(hb.numel())
+        sb.copy_(hb.view(-1), non_blocking=True)
+        st = self._stage(fnx * fny * nk)
+        st.view(fnx, fny, nk)[:, ja:jb + 1, :].copy_(sb.view(fnx, jb - ja + 1, nk))
+        _lib.check(_lib.lib().dc_import_field(GR.dyncore(), self.table[n][0], st.data_ptr(),
+                                              st.numel() * 8, self._stream()))
+
+    def to_host_band(self, GR, n, hb):
+        fnx, fny, nk = self.field_shape(n)
+        ja, jb = self.held_rows(GR, n)
+        assert tuple(hb.shape) == (fnx, jb - ja + 1, nk), (n, tuple(hb.shape))
+        st = self._stage(fnx * fny * nk)
+        _lib.check(_lib.lib().dc_export_field(GR.dyncore(), self.table[n][0], st.data_ptr(),
+                                              st.numel() * 8, self._stream()))
+        sb = self._stage_band(hb.numel())
+        sb.view(fnx, jb - ja + 1, nk).copy_(st.view(fnx, fny, nk)[:, ja:jb + 1, :])
+        hb.view(-1).copy_(sb, non_blocking=True)
+        if self.torch_device.type == 'cuda':
+            torch.cuda.current_stream(self.torch_device).synchronize()
+
+
 class _LazyHost(dict):
     """host field dict that allocates a NaN-filled reference-layout array the first time a
     name is used (the reference allocates all 93 up front, main_fields.py:477-485; at

@@ -9,6 +9,18 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
+def _held_equal(F, GR, n, before):
+    """device rows of the held range only (rows outside it are never touched by an import)"""
+    ja, jb = F.held_rows(GR, n)
+    js = int(GR.jshift)
+    fnx = F.field_shape(n)[0]
+    a = F.device[n][:, ja + js:jb + js + 1, :fnx]
+    b = before[:, ja + js:jb + js + 1, :fnx]
+    import torch
+    return bool(torch.equal(a, b) or torch.equal(torch.nan_to_num(a, nan=1e300),
+                                                 torch.nan_to_num(b, nan=1e300)))
+
+
 def main():
     fixture, nsteps, outdir, moist = sys.argv[1], int(sys.argv[2]), sys.argv[3], int(sys.argv[4])
     import torch.distributed as dist
@@ -40,6 +52,17 @@ def main():
     for n in STATE + ['PHI', 'WWIND']:
         F.to_host(GR, n)
         out[n] = F.host[n]
+    # band-shaped host I/O (ModelFields.to_host_band / to_device_band): the same rows as the
+    # whole-grid path, and a lossless round trip into the device fields
+    for n in ['UWIND', 'VWIND', 'POTT', 'COLP']:
+        ja, jb = F.held_rows(GR, n)
+        hb = F.band_buffer(GR, n)
+        F.to_host_band(GR, n, hb)
+        assert np.array_equal(hb.numpy(), F.host[n][:, ja:jb + 1, :], equal_nan=True), n
+        before = F.device[n].clone()
+        F.device[n].fill_(-3.)
+        F.to_device_band(GR, n, hb)
+        assert _held_equal(F, GR, n, before), n
     np.savez(os.path.join(outdir, 'band%d.npz' % rank), **out)
     dist.barrier()
     dist.destroy_process_group()

@@ -47,3 +47,26 @@ def test_b200_arm_logic_on_the_host_emulation():
     assert e['value'] > 0 and e['finite'] is True and e['one_state_at_a_time_ms'] > 0
     assert d['step_roofline']['algorithmic_bytes_per_cell_update'] == 216
     assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['value'] > 0
+
+
+def test_two_rank_line_under_torchrun_gloo():
+    """the N > 1 arm exactly as the driver launches it (torchrun, one JSON line from rank 0),
+    on the host emulation over gloo: latitude bands, max-over-ranks timing, band-shaped e2e"""
+    env = dict(os.environ, MASTER_ADDR='127.0.0.1', OMP_NUM_THREADS='1')
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+           '--master-addr', '127.0.0.1', '--master-port', '29671', os.path.join(ROOT, 'bench.py'),
+           '--gpus', '2', '--emu', '--workload', 'cfg1', '--steps', '2', '--warmup', '1',
+           '--no-cpu-baseline']
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT, env=env)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = r.stdout.splitlines()
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert BASE_KEYS <= set(d) and d['n_gpus'] == 2 and d['emu'] is True
+    assert d['config']['parallelism'] == 'latitude bands x2' and d['config']['finite'] is True
+    e = d['e2e']
+    assert e['what'].startswith('every rank: pinned band-shaped host state') and e['finite'] is True
+    # the bands' rows plus two halo rows a side: a little more than the whole grid once
+    whole = 8 * (75 * 34 * 8 + 74 * 35 * 8 + 74 * 34 * 8 + 74 * 34)
+    assert whole < e['h2d_bytes_per_step'] < 1.3 * whole
+    assert 'cpu_baseline' not in d
