@@ -350,6 +350,7 @@ static void do_stage_fused(dc_handle *h, int stage, int part, void *stream)
         sb.g = g;
         sb.COLP = f.COLP; sb.COLP_NEW = f.COLP_NEW; sb.COLP_OLD = f.COLP_OLD;
         sb.WWIND = f.WWIND; sb.POTTVB = f.POTTVB;
+        sb.U_in = U; sb.V_in = V;
         sb.UWIND_out = Uo; sb.VWIND_out = Vo; sb.POTT_out = To;
         sb.j_lo = ranges[0].lo; sb.j_hi = ranges[0].hi;
         sb.nby0 = (ranges[0].hi - ranges[0].lo + S3_TY) / S3_TY;
@@ -727,8 +728,14 @@ int dc_import_field(dc_handle *h, int id, const void *ref, size_t nbytes, void *
     return do_transpose(h, id, const_cast<void *>(ref), nbytes, 1, stream, "dc_import_field");
 }
 
+static int refresh_diag(dc_handle *h, const char *what, void *stream);
 int dc_export_field(dc_handle *h, int id, void *ref, size_t nbytes, void *stream)
 {
+    // the fused stages skip PVTF / PVTFVB / PHIVB (diag_partial): bring them up to date first
+    if (h && (id == F_PVTF || id == F_PVTFVB || id == F_PHIVB)) {
+        const int rc = refresh_diag(h, "dc_export_field", stream);
+        if (rc) return rc;
+    }
     return do_transpose(h, id, ref, nbytes, 0, stream, "dc_export_field");
 }
 

@@ -58,8 +58,16 @@ constexpr int S3_NQ = (S3_NP + S3_NT - 1) / S3_NT;   // staged pairs per thread
 // 16-byte aligned (an odd fp64 column raises "illegal instruction"), and I0 - 1 is even
 constexpr int S3_OW = S3_TX + 2;
 constexpr int S3_OWN = S3_OW * S3_TY;
-constexpr int S3_NBUF = 3;                           // level k computes, k+1 has landed (its
-                                                     // own U, V are read), k+2 is in flight
+// TMA ring depth.  3: level k computes, k+1 has landed (its own U, V close the interface
+// below level k), k+2 is in flight.  2: level k computes, k+1 is in flight; the own U, V of
+// level k+1 are read from global memory (L2 hits: the ring is fetching the same lines), which
+// shrinks the block to ~68 KB of shared memory = 3 resident blocks per SM.
+#ifndef DC_S3_NBUF
+#define DC_S3_NBUF 3
+#endif
+constexpr int S3_NBUF = DC_S3_NBUF;
+constexpr int S3_PF = S3_NBUF - 1;                   // prefetch distance in levels
+constexpr int S3_NEED = S3_NBUF >= 3 ? 1 : 0;        // levels beyond k that must have landed
 
 // ---- TMA descriptor -------------------------------------------------------------------
 #if defined(__CUDACC__)
@@ -170,20 +178,27 @@ DC_HD void s3_mbar_expect(unsigned long long *bar, unsigned bytes)
     (void)bar; (void)bytes;
 #endif
 }
+// Bounded wait: a wrong expect_tx byte count or a failed TMA copy must not hang the GPU.  Each
+// try_wait blocks for a hardware-defined time slice; 2^24 unsuccessful slices (seconds) trap, which
+// surfaces as a launch failure through dc_last_error.
 DC_HD void s3_mbar_wait(unsigned long long *bar, unsigned parity)
 {
 #if defined(__CUDA_ARCH__)
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "S3_WAIT:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra S3_DONE;\n\t"
-        "bra S3_WAIT;\n\t"
-        "S3_DONE:\n\t"
-        "}" ::"r"(s3_smem_u32(bar)),
-        "r"(parity)
-        : "memory");
+    const unsigned addr = s3_smem_u32(bar);
+    for (int spin = 0; spin < (1 << 24); spin++) {
+        unsigned done;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) return;
+    }
+    __trap();
 #else
     (void)bar; (void)parity;
 #endif
@@ -255,6 +270,7 @@ struct Stage3Body {
     TmaMap mTB, mUo, mVo, mTo;               // boxes S3_OW x S3_TY x 1
     const double *COLP, *COLP_NEW, *COLP_OLD;
     const double *WWIND, *POTTVB;            // set-up reads of interface 0
+    const double *U_in, *V_in;               // the stage's input winds (own columns, S3_NBUF == 2)
     double *UWIND_out, *VWIND_out, *POTT_out;
     // global mass rows to advance: tile rows [0, nby0) cover j_lo .. j_hi, tile rows from nby0
     // on cover j_lo2 .. j_hi2 (the two boundary tile rows of a band in ONE launch)
@@ -362,9 +378,9 @@ struct Stage3Body {
             }
         S3_PHASE_END
         S3_PHASE
-            if (tid == 0) {   // levels 0 and 1 fly while the column constants are gathered
-                issue(s, ks, ks, x0, y0);
-                if (ks + 1 <= ke) issue(s, ks + 1, ks, x0, y0);
+            if (tid == 0) {   // the first levels fly while the column constants are gathered
+                for (int n = 0; n < S3_PF; n++)
+                    if (ks + n <= ke) issue(s, ks + n, ks, x0, y0);
             }
             // 1) coefficient planes of the staged region
             for (int n = tid; n < S3_PL; n += S3_NT) {
@@ -482,9 +498,13 @@ struct Stage3Body {
             // ---- ring: issue level k+2, make sure level k+1 (own U, V of the interface
             //      interpolation) has landed; level k was awaited one iteration ago ---------
             S3_PHASE
-                // level k+2 -> the slot level k-1 has released (trailing barrier of level k-1)
-                if (tid == 0 && k + 2 <= ke) issue(s, k + 2, ks, x0, y0);
-                if (!last) s3_mbar_wait(&s.full[b1], ((k + 1 - ks) / S3_NBUF) & 1);
+                // level k+PF -> the slot level k-1 has released (trailing barrier of level k-1)
+                if (tid == 0 && k + S3_PF <= ke) issue(s, k + S3_PF, ks, x0, y0);
+                if (S3_NEED) {
+                    if (!last) s3_mbar_wait(&s.full[b1], ((k + 1 - ks) / S3_NBUF) & 1);
+                } else {
+                    s3_mbar_wait(&s.full[b], ((k - ks) / S3_NBUF) & 1);
+                }
             S3_PHASE_END_NOSYNC
             // ---- C: fluxes, tendencies, Euler step, stores ------------------------------
             S3_PHASE
@@ -567,8 +587,15 @@ struct Stage3Body {
                         const double ds_kp1 = s.lev[0][k + 1];
                         const Div dss_d = mkdiv(ds_kp1 + ds, s.lev[5][k + 1]);
                         const int wall = wall_s ? -1 : (wall_n ? 1 : 0);
-                        const double u1[2] = {s.rU[b1][b0 + 1], s.rU[b1][b0 + 2]};
-                        const double v1[2] = {s.rV[b1][b0 + 1], s.rV[b1][b0 + 2]};
+                        double u1[2], v1[2];
+                        if (S3_NEED) {
+                            u1[0] = s.rU[b1][b0 + 1]; u1[1] = s.rU[b1][b0 + 2];
+                            v1[0] = s.rV[b1][b0 + 1]; v1[1] = s.rV[b1][b0 + 2];
+                        } else {
+                            const size_t o1 = ko + plane + S3_P(off0);
+                            u1[0] = U_in[o1]; u1[1] = U_in[o1 + 1];
+                            v1[0] = V_in[o1]; v1[1] = V_in[o1 + 1];
+                        }
                         wwu_kp1[0] = colpa_wwind(P_0.a, P_0.m1, P_m.a, P_p.a, P_m.m1, P_p.m1, wall) *
                                      interp_ks(u1[0], u[0], ds_kp1, ds, dss_d);
                         wwu_kp1[1] = colpa_wwind(P_0.b, P_0.a, P_m.b, P_p.b, P_m.a, P_p.a, wall) *

@@ -98,7 +98,10 @@ static void dcb_launch_stage(const dc::StageBody &b, int nbx, int nby, void *str
 struct dc_handle;
 namespace dc {
 struct Stage3Ptrs;
-__global__ void __launch_bounds__(S3_NT, 2) k_stage3(const __grid_constant__ Stage3Body b)
+#ifndef DC_S3_MINBLOCKS
+#define DC_S3_MINBLOCKS 2
+#endif
+__global__ void __launch_bounds__(S3_NT, DC_S3_MINBLOCKS) k_stage3(const __grid_constant__ Stage3Body b)
 {
     extern __shared__ unsigned char stage3_smem[];
     // the TMA destinations need 128-byte alignment

@@ -18,14 +18,9 @@ Diagnostics = DiagnosticsFactory(target=B200)
 
 
 def _bind_all(GR, F):
-    """bind F.device to the handle once per (handle, buffer set)"""
-    key = tuple(t.data_ptr() for t in F.device.values())
-    if F._bound.get('key') != key:
-        L = _lib.lib()
-        h = GR.dyncore()
-        for n, t in F.device.items():
-            _lib.check(L.dc_bind_field(h, F.table[n][0], t.data_ptr(), t.numel() * 8))
-        F._bound['key'] = key
+    """bind F.device to the handle of GR (main_fields.bind_all: the key lives on the handle)"""
+    from .main_fields import bind_all
+    bind_all(GR, F)
 
 
 def set_mode(GR, mode):
@@ -34,11 +29,13 @@ def set_mode(GR, mode):
     (dc_set_mode, include/dyncore.h)"""
     code = {'fused': _lib.DC_MODE_FUSED, 'kernels': _lib.DC_MODE_KERNELS}[mode]
     _lib.check(_lib.lib().dc_set_mode(GR.dyncore(), code))
+    GR._mode = mode
 
 
 def step_matsuno(GR, F, nsteps=1):
     GR.timer.start('step')
     _bind_all(GR, F)
+    GR._state_version = getattr(GR, '_state_version', 0) + 1
     t = F.device['UWIND']
     stream = torch.cuda.current_stream(t.device).cuda_stream if t.is_cuda else 0
     if GR.band[1] > 1:

@@ -33,10 +33,15 @@ class _Factory:
         """bind `fields` ({name: torch tensor}) and enqueue `entry` on the current stream.
         The grid (and with it the library handle) is found through the tensors: ModelFields
         registers every device buffer it allocates (main_fields.OWNERS)."""
-        from .main_fields import owner_of
+        from .main_fields import bind_all, fields_owner_of, owner_of
         L = _lib.lib()
         GR = owner_of(fields)
         h = GR.dyncore()
+        # the whole field set the tensors come from first (library work fields such as PGCOL
+        # follow it), then the tensors actually passed; a foreign tensor invalidates the key
+        F = fields_owner_of(fields)
+        if F is not None:
+            bind_all(GR, F)
         if self._table is None:
             self._table = _lib.field_table()
         stream = 0
@@ -48,8 +53,11 @@ class _Factory:
                                 % (n, type(t).__name__))
             if _lib.is_cuda() and not t.is_cuda:
                 raise RuntimeError('field %s is not on a CUDA device; there is no CPU fallback' % n)
-            _lib.check(L.dc_bind_field(h, self._table[n][0], t.data_ptr(), t.numel() * 8))
+            if F is None or F.device.get(n) is not t:
+                _lib.check(L.dc_bind_field(h, self._table[n][0], t.data_ptr(), t.numel() * 8))
+                GR._bound_key = None
             stream = _stream(t)
+        GR._state_version = getattr(GR, '_state_version', 0) + 1
         _lib.check(getattr(L, entry)(h, stream))
 
 

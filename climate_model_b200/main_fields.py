@@ -22,6 +22,31 @@ _HOST_ONLY = {'PSURF': (0, 0, 1)}
 # device-buffer address -> Grid that owns the handle the buffer is bound to; lets the
 # factories keep the reference's signatures (which carry no grid object)
 OWNERS = weakref.WeakValueDictionary()
+# device-buffer address -> the ModelFields the buffer belongs to (the factories bind the WHOLE
+# field set a tensor comes from, so that library work fields like PGCOL follow it)
+FOWNERS = weakref.WeakValueDictionary()
+
+
+def bind_all(GR, F):
+    """Point the handle of GR at the device buffers of F.  The bindings live on the HANDLE, so
+    the "already bound" key is kept on the Grid: two ModelFields on one Grid, or a factory call
+    with foreign tensors in between, always end up advancing the field set they were given."""
+    key = (id(F),) + tuple(t.data_ptr() for t in F.device.values())
+    if getattr(GR, '_bound_key', None) != key:
+        L = _lib.lib()
+        h = GR.dyncore()
+        for n, t in F.device.items():
+            _lib.check(L.dc_bind_field(h, F.table[n][0], t.data_ptr(), t.numel() * 8))
+        GR._bound_key = key
+
+
+def fields_owner_of(fields):
+    for t in fields.values():
+        if isinstance(t, torch.Tensor):
+            F = FOWNERS.get(t.data_ptr())
+            if F is not None:
+                return F
+    return None
 
 
 def owner_of(fields):
@@ -108,7 +133,10 @@ class ModelFields:
             t = torch.zeros((nk, GR.NJ, GR.NI), dtype=torch.float64, device=self.torch_device)
             self.device[n] = t
             OWNERS[t.data_ptr()] = GR
+            FOWNERS[t.data_ptr()] = self
             _lib.check(L.dc_bind_field(h, fid, t.data_ptr(), t.numel() * 8))
+        GR._bound_key = None
+        bind_all(GR, self)
 
     def _stage(self, nelem):
         """device scratch holding one field in the reference layout (raw copy of the host
@@ -126,6 +154,7 @@ class ModelFields:
         """host (i, j, k) -> device F[k][jd][i]: one contiguous H2D copy (asynchronous when the
         host array is pinned) + an on-device tiled transpose (dc_import_field)"""
         h = self.host[n]
+        bind_all(GR, self)
         src = torch.from_numpy(h).view(-1)
         st = self._stage(src.numel())
         st.copy_(src, non_blocking=True)
@@ -135,6 +164,8 @@ class ModelFields:
     def to_host(self, GR, n):
         """device -> host, the reverse of to_device; synchronises the stream at the end"""
         h = self.host[n]
+        bind_all(GR, self)
+        self._refresh_for_export(GR, n)
         dst = torch.from_numpy(h).view(-1)
         st = self._stage(dst.numel())
         if GR.band[1] > 1:
@@ -145,6 +176,32 @@ class ModelFields:
         if self.torch_device.type == 'cuda':
             torch.cuda.current_stream(self.torch_device).synchronize()
 
+
+    # fields the fused step does not keep up to date: the fluxes / tendencies of the reference's
+    # kernel decomposition (the fused stage kernel forms them in registers)
+    KERNEL_MODE_ONLY = ('UFLX', 'VFLX', 'FLXDIV', 'BFLX', 'CFLX', 'DFLX', 'EFLX', 'RFLX', 'QFLX',
+                        'SFLX', 'TFLX', 'WWIND_UWIND', 'WWIND_VWIND', 'dUFLXdt', 'dVFLXdt',
+                        'dPOTTdt', 'dQVdt', 'dQCdt', 'dCOLPdt')
+
+    def _refresh_for_export(self, GR, n):
+        """An export of a flux / tendency field after fused steps first evaluates the
+        tendencies of the CURRENT state with the kernel decomposition (dc_compute_tendencies:
+        it only writes derived fields, the trajectory is unchanged), once per state.  The
+        library itself brings PVTF / PVTFVB / PHIVB up to date inside dc_export_field."""
+        if (n not in self.KERNEL_MODE_ONLY or GR.band[1] > 1 or GR.i_coupling or
+                getattr(GR, '_mode', 'fused') != 'fused'):
+            return
+        ver = getattr(GR, '_state_version', 0)
+        if getattr(self, '_tend_version', None) == ver:
+            return
+        d = self.device
+        # fields of the stepping path that the evaluation overwrites keep their values
+        keep = {m: d[m].clone() for m in ('COLP_OLD', 'COLP_NEW', 'WWIND')}
+        d['COLP_OLD'].copy_(d['COLP'])
+        _lib.check(_lib.lib().dc_compute_tendencies(GR.dyncore(), self._stream()))
+        for m, v in keep.items():
+            d[m].copy_(v)
+        self._tend_version = ver
 
     # ------------------------------------------------------------ latitude bands: band-shaped I/O
     # The reference-layout host arrays cover the whole grid on every rank.  A caller that only

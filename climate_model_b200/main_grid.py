@@ -48,6 +48,9 @@ class Grid:
             'CFL', 'i_out_nth_hour', 'i_sim_n_days', 'i_restart_nth_day', 'pair_top',
             'POTT_dif_coef', 'moist_dif_coef', 'i_moist_main_switch')}
         P['UVFLX_dif_coef'] = None
+        # time step override [s]: a latitude window of a finer global grid keeps the global
+        # grid's time step (the rule of main_grid.py:258-275 looks at the window's own rows)
+        P['dt'] = None
         # physics coupling terms of the dynamical core (turbulent transport with KMOM / KHEAT,
         # surface fluxes): needed as soon as a physics module fills those fields; the
         # reference always evaluates them (on zero fields when its physics is off)
@@ -156,6 +159,8 @@ class Grid:
         self.dt = int(self.CFL * mindx / 400)
         while self.i_out_nth_hour * 3600 % self.dt > 0:
             self.dt -= 1
+        if P['dt'] is not None:
+            self.dt = int(P['dt'])
         self._time_bookkeeping(P)
 
         # NUMERICAL DIFFUSION (main_grid.py:279-292)

@@ -78,16 +78,19 @@ CUDA_LIB_STRICT = os.path.join(os.path.dirname(EMU_DIR), '..', 'climate_model_b2
 def build_emu(fast=False):
     """compile tests/emu/libdyncore_emu[_fast].so (host emulation of the kernel bodies);
     same tiling as the CUDA build; `fast` = the production arithmetic mode (DC_FAST_MATH +
-    FMA contraction), default = strict (IEEE divisions, no FMA)"""
+    FMA contraction), default = strict (IEEE divisions, no FMA).  DC_EMU_FLAGS / DC_EMU_TAG in
+    the environment build a tagged variant with extra -D switches (development only)."""
     import subprocess
-    so = os.path.join(EMU_DIR, 'libdyncore_emu_fast.so' if fast else 'libdyncore_emu.so')
+    tag = os.environ.get('DC_EMU_TAG', '')
+    extra = os.environ.get('DC_EMU_FLAGS', '').split()
+    so = os.path.join(EMU_DIR, 'libdyncore_emu%s%s.so' % ('_fast' if fast else '', tag))
     srcs = [os.path.join(EMU_DIR, 'emu_dyncore.cpp')]
     csrc = os.path.join(os.path.dirname(EMU_DIR), '..', 'climate_model_b200', 'csrc')
     srcs += [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith('.h')]
     if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
         mode = (['-DDC_FAST_MATH', '-mfma', '-ffp-contract=fast'] if fast
                 else ['-ffp-contract=off'])
-        subprocess.check_call(['g++', '-O2', '-std=c++17', '-fPIC', '-shared', '-DDC_TY=4'] + mode +
+        subprocess.check_call(['g++', '-O2', '-std=c++17', '-fPIC', '-shared', '-DDC_TY=4'] + mode + extra +
                               ['-o', so, srcs[0]])
     return so
 

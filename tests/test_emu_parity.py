@@ -132,20 +132,59 @@ def test_fused_mode_equals_kernel_mode(g10, moist):
         Diagnostics.primary_diag(GR.GRF[B200],
                                  **F.get(Diagnostics.fields_primary_diag, target=B200))
         step_matsuno(GR, F, 3)
+        # the fused stages keep PHI / POTTVB / PGCOL only: the export itself brings PVTF,
+        # PVTFVB and PHIVB up to date (dc_export_field), and evaluates the tendencies of the
+        # current state for a flux / tendency field (ModelFields._refresh_for_export)
         F.copy_device_to_host(GR, F.ALL_FIELDS)
         out[mode] = {n: F.host[n].copy() for n in STATE + ['PHI', 'POTTVB', 'PGCOL', 'WWIND',
-                                                           'dUFLXdt'] if n in F.host}
-        # the fused stages keep PHI / POTTVB / PGCOL only; the factory entry brings PVTF,
-        # PVTFVB and PHIVB up to date on demand
-        Diagnostics.primary_diag(GR.GRF[B200],
-                                 **F.get(Diagnostics.fields_primary_diag, target=B200))
-        F.copy_device_to_host(GR, F.ALL_FIELDS)
-        out[mode].update({n: F.host[n].copy() for n in ('PVTF', 'PVTFVB', 'PHIVB')})
+                                                           'dUFLXdt', 'dQVdt', 'PVTF', 'PVTFVB',
+                                                           'PHIVB'] if n in F.host}
+        if mode == 'fused':
+            # reference for the on-demand tendencies: the kernel decomposition on the same state
+            from climate_model_b200.dyn_tendencies import compute_tendencies
+            F.device['COLP_OLD'].copy_(F.device['COLP'])
+            set_mode(GR, 'kernels')
+            compute_tendencies(GR, F)
+            F.copy_device_to_host(GR, F.ALL_FIELDS)
+            tend = {n: F.host[n].copy() for n in ('dUFLXdt', 'dQVdt')}
     for n in STATE[:4] + (STATE[4:] if moist else []) + ['PHI', 'POTTVB', 'WWIND', 'PVTF',
                                                          'PVTFVB', 'PHIVB']:
         _eq(out['fused'][n], out['kernels'][n], n)
-    # the fused path never materialises the tendencies
-    assert np.all(out['fused']['dUFLXdt'] == 0.) and np.any(out['kernels']['dUFLXdt'] != 0.)
+    # the fused path does not keep the tendencies; an export evaluates them at the current state
+    assert np.any(out['fused']['dUFLXdt'] != 0.)
+    _eq(out['fused']['dUFLXdt'], tend['dUFLXdt'], 'on-demand dUFLXdt')
+    if moist:
+        assert np.nanmax(np.abs(out['fused']['dQVdt'])) > 0.
+        _eq(out['fused']['dQVdt'], tend['dQVdt'], 'on-demand dQVdt')
+
+
+def test_two_field_sets_on_one_grid(g10):
+    """the bindings live on the handle: stepping F1, F2, F1 on ONE grid must advance the set
+    that was passed, and a factory call on F2 must not leave F2's PGCOL behind"""
+    from climate_model_b200.dyn_matsuno import Diagnostics, step_matsuno
+    from climate_model_b200.io_read_namelist import B200
+    GR = grid_from_golden(g10)
+    F1 = fields_from_golden(GR, g10)
+    F2 = fields_from_golden(GR, g10)
+    F2.device['POTT'].add_(0.5)
+    ref = {}
+    for tag, F, n in (('a', F1, 2), ('b', F2, 1)):      # each set alone on a fresh grid
+        G = grid_from_golden(g10)
+        X = fields_from_golden(G, g10)
+        if tag == 'b':
+            X.device['POTT'].add_(0.5)
+        Diagnostics.primary_diag(G.GRF[B200], **X.get(Diagnostics.fields_primary_diag, target=B200))
+        step_matsuno(G, X, n)
+        ref[tag] = {m: X.device[m].clone() for m in STATE[:4]}
+    Diagnostics.primary_diag(GR.GRF[B200], **F1.get(Diagnostics.fields_primary_diag, target=B200))
+    step_matsuno(GR, F1, 1)
+    Diagnostics.primary_diag(GR.GRF[B200], **F2.get(Diagnostics.fields_primary_diag, target=B200))
+    step_matsuno(GR, F2, 1)
+    step_matsuno(GR, F1, 1)
+    import torch
+    for m in STATE[:4]:
+        assert torch.equal(F1.device[m], ref['a'][m]), m
+        assert torch.equal(F2.device[m], ref['b'][m]), m
 
 
 @pytest.mark.parametrize('kchunks', [2, 3])
