@@ -131,24 +131,84 @@ class ClockSampler(threading.Thread):
                 'samples': len(self.rows), 'reasons': sorted(reasons)}
 
 
-def cpu_sample(wl, moist, steps, warmup=1):
-    """the oracle port on a bounded sample of the workload: the SAME grid spacing, levels and
-    initial-state recipe restricted to an equatorial band of <= 84 rows"""
-    import numpy as np
-    from climate_model_b200.main_fields import ModelFields
-    from climate_model_b200.main_grid import Grid
-    from oracle.oracle import GRID_FIELDS, Oracle
+def sample_grid(wl):
+    """bounded sample of the workload for the CPU arm: the SAME grid spacing, levels and
+    initial-state recipe restricted to an equatorial band of <= 84 rows (the per-rank band of
+    the 8-GPU run)"""
     g = dict(wl['grid'])
     ny_full = int(round((g['lat1_deg'] - g['lat0_deg']) / g['dlat_deg']))
     rows = min(ny_full, 84)
     half = rows * g['dlat_deg'] / 2
     if rows < ny_full:
         g['lat0_deg'], g['lat1_deg'] = -half, half
+    return g, rows < ny_full, half
+
+
+def host_threads():
+    """host cores this process may use (torchrun exports OMP_NUM_THREADS=1: not a limit of
+    the box, so the CPU arm sets its thread count itself)"""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_sample_numba(wl, moist, steps, warmup=1):
+    """the reference's own numba-CPU step (oracle/_ref, prepared by oracle/build_ref.py from
+    /root/reference in the build container) timed in a subprocess on all host threads.
+    Returns None when the prepared tree or numba is not there (the port is timed instead)."""
+    ref = os.path.join(ROOT, 'oracle', '_ref')
+    if not os.path.exists(os.path.join(ref, 'dyn_matsuno.py')):
+        return None
+    g, banded, half = sample_grid(wl)
+    env = dict(os.environ)
+    nthr = host_threads()
+    env.update(CMREF_NZ=str(g['nz']), CMREF_LAT0_DEG=repr(float(g['lat0_deg'])),
+               CMREF_LAT1_DEG=repr(float(g['lat1_deg'])), CMREF_DLAT_DEG=repr(float(g['dlat_deg'])),
+               CMREF_DLON_DEG=repr(float(g['dlon_deg'])),
+               CMREF_USE_TOPO=str(int(wl['ic'].get('i_use_topo', 1))),
+               NUMBA_NUM_THREADS=str(nthr), OMP_NUM_THREADS=str(nthr),
+               NUMBA_CACHE_DIR=os.path.join(ROOT, 'oracle', '_ref', '.numba_cache'))
+    for k in ('RANK', 'LOCAL_RANK', 'WORLD_SIZE', 'MASTER_ADDR', 'MASTER_PORT'):
+        env.pop(k, None)
+    try:
+        out = subprocess.run([sys.executable, os.path.join(ROOT, 'oracle', 'ref_bench.py'),
+                              '--steps', str(steps), '--warmup', str(warmup)], env=env,
+                             capture_output=True, text=True, timeout=1500)
+        d = json.loads(out.stdout.strip().splitlines()[-1])
+        if 'sec_per_step' not in d or not d.get('finite'):
+            raise RuntimeError(str(d))
+    except Exception as exc:                                     # noqa: BLE001
+        print('numba reference arm failed, timing the C port instead: %r' % (exc,),
+              file=sys.stderr)
+        return None
+    cells = d['nx'] * d['ny'] * d['nz']
+    sample = ('%dx%dx%d band (lat +-%.4g deg) of the workload grid, %d Matsuno steps of the '
+              'reference numba-CPU dyn core (moisture tracers always on in the reference), '
+              'numba %s, JIT + set-up %.0f s not timed' % (
+                  d['nx'], d['ny'], d['nz'], half if banded else g['lat1_deg'], steps,
+                  d['numba'], d['setup_and_jit_s']))
+    return cells, d['sec_per_step'], d['threads'], sample, (d['nx'], d['ny'], d['nz']), 'reference'
+
+
+def cpu_sample(wl, moist, steps, warmup=1):
+    """the oracle port (oracle/dyncore_oracle.c, OpenMP) on the same bounded sample.  The
+    state is built with the host-side Python of the package (grid + initial conditions, pure
+    numpy); the product library libdyncore.so is NOT loaded by this arm."""
+    import numpy as np
+    from climate_model_b200.io_initial_conditions import initialize_fields
+    from climate_model_b200.main_grid import Grid
+    from oracle.oracle import FIELDS, GRID_FIELDS, Oracle, field_shape
+    g, banded, half = sample_grid(wl)
     GR = Grid(i_moist_main_switch=int(moist), **g)
-    F = ModelFields(GR, gpu_enable=False, device='cpu', **wl['ic'])
-    O = Oracle(GR.nx, GR.ny, GR.nz, GR.dt, {n: GR.GRF['CPU'][n] for n in GRID_FIELDS},
-               i_moist=moist)
-    O.set(**{n: F.host[n] for n in ['HSURF', 'UWIND', 'VWIND', 'POTT', 'COLP', 'QV', 'QC']})
+    nx, ny, nz = int(GR.nx), int(GR.ny), int(GR.nz)
+    names = ['POTTVB', 'WWIND', 'HSURF', 'COLP', 'PVTF', 'PVTFVB', 'POTT', 'UWIND', 'VWIND',
+             'QV', 'QC']
+    host = {n: np.full(field_shape(n, nx, ny, nz), np.nan) for n in names}
+    initialize_fields(GR, host, **wl['ic'])
+    Oracle.set_num_threads(host_threads())
+    O = Oracle(nx, ny, nz, GR.dt, {n: GR.GRF['CPU'][n] for n in GRID_FIELDS}, i_moist=moist)
+    O.set(**{n: host[n] for n in ['HSURF', 'UWIND', 'VWIND', 'POTT', 'COLP', 'QV', 'QC']})
     O.primary_diag()
     O.step_matsuno(warmup)
     ts = []
@@ -156,11 +216,16 @@ def cpu_sample(wl, moist, steps, warmup=1):
         t0 = time.perf_counter()
         O.step_matsuno(1)
         ts.append(time.perf_counter() - t0)
-    cells = int(GR.nx) * int(GR.ny) * int(GR.nz)
+    cells = nx * ny * nz
     assert np.isfinite(O.F['UWIND'][1:-2, 1:-1]).all()
     sample = '%dx%dx%d band (lat +-%.4g deg) of the workload grid, %d Matsuno steps' % (
-        GR.nx, GR.ny, GR.nz, half if rows < ny_full else g['lat1_deg'], steps)
-    return cells, ts, O.num_threads(), sample
+        nx, ny, nz, half if banded else g['lat1_deg'], steps)
+    return cells, ts, O.num_threads(), sample, (nx, ny, nz), 'port'
+
+
+def cpu_arm(wl, moist, steps, warmup=1, prefer_numba=True):
+    r = cpu_sample_numba(wl, moist, steps, warmup) if prefer_numba else None
+    return r if r is not None else cpu_sample(wl, moist, steps, warmup)
 
 
 _JSON_FD = None
@@ -182,10 +247,14 @@ def emit(line):
 
 
 def run_reference(args, wl, moist):
+    """`--impl reference`: the reference's CPU implementation of the path on the box's host
+    cores.  Under torchrun only rank 0 works; the other ranks exit 0."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    cells, ts, threads, sample = cpu_sample(wl, moist, args.steps, max(1, min(args.warmup, 2)))
+    cells, ts, threads, sample, dims, kind = cpu_arm(wl, moist, args.steps,
+                                                     max(1, min(args.warmup, 2)),
+                                                     prefer_numba=not args.port)
     sec = sum(ts) / len(ts)
     value = cells / sec
     line = {
@@ -193,14 +262,67 @@ def run_reference(args, wl, moist):
         'unit': 'cell-updates/s', 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True,
         'scaling': 'weak' if wl.get('weak') else 'strong', 'vs_baseline': None, 'dtype': 'f64',
-        'data': 'synthetic', 'config': {'workload': wl['name'], 'moist': moist},
+        'data': 'synthetic',
+        'config': {'workload': wl['name'], 'moist': moist, 'sample_nx': dims[0],
+                   'sample_ny': dims[1], 'sample_nz': dims[2],
+                   'note': 'bounded sample: an equatorial latitude band of the workload grid; '
+                           'cell-updates/s does not depend on the number of rows'},
         'cpu_baseline': {'value': value, 'unit': 'cell-updates/s', 'cores': threads,
-                         'kind': 'port', 'sample': sample},
+                         'kind': kind, 'sample': sample},
         'e2e': {'value': value, 'unit': 'cell-updates/s', 'h2d_bytes_per_step': 0,
                 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
     emit(line)
+
+
+PARITY_FIELDS = ['UWIND', 'VWIND', 'POTT', 'COLP']
+
+
+def band_hash(F, GR, j0, j1):
+    """exact hash of the owned rows j0..j1 (interior columns) of the prognostic fields"""
+    import torch
+    out = []
+    js, nx = GR.jshift, int(GR.nx)
+    for n in PARITY_FIELDS:
+        a = F.device[n][:, j0 + js:j1 + js + 1, 1:nx + 1].contiguous()
+        out.append(a.view(torch.int64).sum())
+    return torch.stack(out)
+
+
+def banded_parity(GR, F, wl, moist, steps_done, rank, world, cells):
+    import torch
+    import torch.distributed as dist
+    from climate_model_b200.dyn_matsuno import Diagnostics, step_matsuno
+    from climate_model_b200.io_read_namelist import B200
+    from climate_model_b200.main_fields import ModelFields
+    from climate_model_b200.main_grid import Grid, band_rows
+    if cells > 120e6:
+        return {'checked': False, 'why': 'the whole grid does not fit the replay on one GPU'}
+    mine = band_hash(F, GR, int(GR.j0), int(GR.j1))
+    allh = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(allh, mine)
+    res = torch.zeros(1, dtype=torch.int64, device=F.torch_device)
+    if rank == 0:
+        G1 = Grid(band=(0, 1), i_moist_main_switch=int(moist), **wl['grid'])
+        F1 = ModelFields(G1, **wl['ic'])
+        Diagnostics.primary_diag(G1.GRF[B200],
+                                 **F1.get(Diagnostics.fields_primary_diag, target=B200))
+        step_matsuno(G1, F1, steps_done)
+        bad = 0
+        for r in range(world):
+            a, b = band_rows(int(G1.ny), r, world)
+            if not torch.equal(band_hash(F1, G1, a, b), allh[r]):
+                bad += 1
+        res[0] = bad
+        del F1
+        G1.close()
+        torch.cuda.empty_cache()
+    dist.broadcast(res, 0)
+    return {'checked': True, 'bitwise_equal': int(res.item()) == 0, 'bands_differing': int(res.item()),
+            'steps': steps_done, 'fields': PARITY_FIELDS,
+            'how': 'int64-sum hash of the owned rows of every band vs a single-GPU replay of '
+                   'the whole grid on rank 0'}
 
 
 def main():
@@ -211,6 +333,9 @@ def main():
     ap.add_argument('--workload', default='cfg4', choices=sorted(WORKLOADS))
     ap.add_argument('--moist', action='store_true')
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--port', action='store_true',
+                    help='CPU arm: time the C/OpenMP oracle port even when the numba reference '
+                         '(oracle/_ref) is available')
     ap.add_argument('--e2e-steps', type=int, default=3)
     ap.add_argument('--e2e-members', type=int, default=12,
                     help='1 GPU: host-resident states streamed through ensemble_stream.MemberStream '
@@ -239,10 +364,6 @@ def main():
     if args.impl == 'reference':
         return run_reference(args, wl, moist)
 
-    if 'DC_NCCL_DEBUG' in os.environ:
-        os.environ['NCCL_DEBUG'] = os.environ['DC_NCCL_DEBUG']
-    else:
-        os.environ.pop('NCCL_DEBUG', None)
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -350,6 +471,15 @@ def main():
     ok = bool(torch.isfinite(F.device['UWIND'][:, GR.j0 + js:GR.j1 + js + 1, 1:int(GR.nx) + 1])
               .all().item())
 
+    # ---- N > 1: the banded result must equal the single-device result BITWISE.
+    # Rank 0 replays the same number of steps on the whole grid on its own GPU; every rank
+    # hashes the rows it owns (sum of the fp64 bit patterns as int64, wrapping) and the
+    # hashes are compared field by field, band by band.
+    parity = None
+    steps_done = args.warmup + args.steps * (1 if args.no_kernel_events else 2)
+    if world > 1 and not args.turbulence:
+        parity = banded_parity(GR, F, wl, moist, steps_done, rank, world, cells)
+
     # ---- end to end through the public field API: host state -> device -> step -> host
     names = ['UWIND', 'VWIND', 'POTT', 'COLP'] + (['QV', 'QC'] if moist else [])
     F.copy_device_to_host(GR, F.PROGNOSTIC_FIELDS)
@@ -368,7 +498,8 @@ def main():
             F.to_host(GR, n)
         barrier()
         t_e2e.append(time.perf_counter() - t0)
-    e2e_sec = min(t_e2e) if t_e2e else float('nan')
+    e2e_sec = sum(t_e2e) / len(t_e2e) if t_e2e else float('nan')
+    e2e_min = min(t_e2e) if t_e2e else float('nan')
     if world > 1:
         t = torch.tensor([e2e_sec], device=F.torch_device, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -409,7 +540,8 @@ def main():
                     F.to_host_band(GR, n, bufs[n])
                 barrier()
                 t_band.append(time.perf_counter() - t0)
-            t = torch.tensor([min(t_band)], device=F.torch_device, dtype=torch.float64)
+            t = torch.tensor([sum(t_band) / len(t_band)], device=F.torch_device,
+                             dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             b = torch.tensor([float(band_bytes)], device=F.torch_device, dtype=torch.float64)
             dist.all_reduce(b, op=dist.ReduceOp.SUM)
@@ -445,13 +577,15 @@ def main():
         n_mem = stream.advance([sets[m % 3] for m in range(args.e2e_members)], nsteps=1)
         barrier()
         stream_sec = (time.perf_counter() - t0) / n_mem
-        e2e_extra = {'members': n_mem, 'one_state_at_a_time_ms': e2e_sec * 1e3,
-                     'finite': bool(all(np.isfinite(m['POTT']).all() for m in sets))}
-        e2e_sec = stream_sec
-        e2e_what = ('%d host-resident states (pinned, reference layout) streamed through the '
+        # the headline e2e stays the ONE-state sequence above (what the reference does: it
+        # advances one state); the streamed ensemble is reported beside it
+        e2e_extra = {'streamed': {
+            'value': cells / stream_sec, 'ms_per_state': stream_sec * 1e3, 'members': n_mem,
+            'finite': bool(all(np.isfinite(m['POTT']).all() for m in sets)),
+            'what': '%d host-resident states (pinned, reference layout) streamed through the '
                     'device, each: H2D, layout transpose, primary_diag, 1 Matsuno step, '
                     'transpose, D2H; upload / step / download of consecutive states overlap '
-                    '(ensemble_stream.MemberStream); wall clock / states' % n_mem)
+                    '(ensemble_stream.MemberStream); wall clock / states' % n_mem}}
 
     if rank == 0:
         peak, peak_src = peak_hbm_gbs()
@@ -465,7 +599,14 @@ def main():
             acc = KERNEL_ACCESSES.get(key, (0, 0))[1 if moist else 0]
             if args.turbulence:
                 acc = KERNEL_ACCESSES_COUPLED.get(top, acc)
-            k_ms = kern[top][0] / kern[top][1]
+            # one "launch" of the roofline = one pass of the kernel over the band: with latitude
+            # bands the stage kernel runs as two launches per stage (boundary tile rows on the
+            # side stream, interior on the main stream), whose times are SUMMED here (they
+            # overlap in wall time, so the sum overstates the elapsed time)
+            passes = kern[top][1]
+            if world > 1 and top == 'stage_fused':
+                passes = 2 * args.steps
+            k_ms = kern[top][0] / passes
             cells_launch = cells // world
             bytes_launch = acc * 8 * cells_launch
             ach = bytes_launch / (k_ms * 1e-3) / 1e9
@@ -501,15 +642,19 @@ def main():
             'kernels_ms_per_step': {k: v[0] / args.steps for k, v in sorted(kern.items())},
             'e2e': {'value': cells / e2e_sec, 'unit': 'cell-updates/s',
                     'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': h2d,
-                    'ms_per_step': e2e_sec * 1e3, 'what': e2e_what, **e2e_extra},
+                    'ms_per_step': e2e_sec * 1e3, 'ms_per_step_min': e2e_min * 1e3,
+                    'repeats': args.e2e_steps, 'what': e2e_what, **e2e_extra},
             'gpu_launches': int(launches),
             'clocks': clocks,
         }
+        if parity is not None:
+            line['parity_vs_1gpu'] = parity
         if not args.no_cpu_baseline and world == 1:
-            c_cells, ts, threads, sample = cpu_sample(wl, moist, steps=3)
+            c_cells, ts, threads, sample, _dims, kind = cpu_arm(wl, moist, steps=3,
+                                                                prefer_numba=not args.port)
             sec = sum(ts) / len(ts)
             line['cpu_baseline'] = {'value': c_cells / sec, 'unit': 'cell-updates/s',
-                                    'cores': threads, 'kind': 'port', 'sample': sample}
+                                    'cores': threads, 'kind': kind, 'sample': sample}
         emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -294,7 +294,7 @@ static int do_primary_diag(dc_handle *h, void *stream, const double *POTT = null
     const int lo = g.j0 - HJ < 0 ? 0 : g.j0 - HJ, hi = g.j1 + HJ > g.ny + 1 ? g.ny + 1 : g.j1 + HJ;
     PrimaryDiagBody<0> b{g,        f.COLP, POTT ? POTT : f.POTT,  f.HSURF,  f.PVTF,  f.PVTFVB,
                          f.PHI,    f.PHIVB, f.POTTVB, f.PGCOL, lo,      hi,
-                         make_pow_coef(con_kappa)};
+                         make_pow_coef(con_kappa, g.powtab)};
     h->diag_partial = 0;
     launch(h, "primary_diag", b, 0, g.nx + 1, 0, (hi - lo) / b.NC, stream);   // every held row
     return DC_OK;
@@ -444,13 +444,13 @@ static void do_diag_fused(dc_handle *h, int stage, void *stream)
     if (h->stage_impl == 3) {
         PrimaryDiagBody<1> b{g,     f.COLP,  T,        f.HSURF, f.PVTF, f.PVTFVB,
                              f.PHI, f.PHIVB, f.POTTVB, f.PGCOL, lo,     hi,
-                             make_pow_coef(con_kappa)};
+                             make_pow_coef(con_kappa, g.powtab)};
         launch(h, "primary_diag", b, 0, g.nx + 1, 0, (hi - lo) / b.NC, stream);
         h->diag_partial = 1;
     } else {
         PrimaryDiagBody<2> b{g,     f.COLP,  T,        f.HSURF, f.PVTF, f.PVTFVB,
                              f.PHI, f.PHIVB, f.POTTVB, f.PGCOL, lo,     hi,
-                             make_pow_coef(con_kappa)};
+                             make_pow_coef(con_kappa, g.powtab)};
         launch(h, "primary_diag", b, 0, g.nx + 1, 0, (hi - lo) / b.NC, stream);
     }
 }
@@ -564,7 +564,10 @@ int dc_create(const dc_grid_desc *d, dc_handle **out)
     // per-row arrays (device row = global j + jshift), per-level arrays
     const int NJ = g.NJ;
     const size_t n_row = 9, n_lev = 7;
-    std::vector<double> host(n_row * NJ + n_lev * (nz + 1), 0.);
+    // (even, so that the {r, T} pairs of the power table are 16-byte aligned)
+    const size_t n_geo = (n_row * NJ + n_lev * (nz + 1) + 1) & ~(size_t)1, n_pow = 2 * POW_NE * POW_NJ;
+    std::vector<double> host(n_geo + n_pow, 0.);
+    make_pow_table(con_kappa, &host[n_geo]);
     double *A = &host[0 * NJ], *dxjs = &host[1 * NJ], *corf = &host[2 * NJ],
            *corf_is = &host[3 * NJ], *cl = &host[4 * NJ], *sl = &host[5 * NJ],
            *cl_is = &host[6 * NJ], *sl_is = &host[7 * NJ], *rA = &host[8 * NJ];
@@ -625,6 +628,7 @@ int dc_create(const dc_grid_desc *d, dc_handle **out)
     g.sigma_vb = dl; g.dsigma = dl + (nz + 1); g.UVFLX_dif_coef = dl + 2 * (nz + 1);
     g.POTT_dif_coef = dl + 3 * (nz + 1); g.moist_dif_coef = dl + 4 * (nz + 1);
     g.r_A = db + 8 * NJ; g.r_dsigma = dl + 5 * (nz + 1); g.r_dss = dl + 6 * (nz + 1);
+    g.powtab = db + n_geo;
     h->launches = 0;
     h->profiling = 0;
     h->mode = DC_MODE_FUSED;

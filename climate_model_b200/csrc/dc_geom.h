@@ -60,6 +60,7 @@ struct Geom {
     const double *r_A;        // 1 / A[row]
     const double *r_dsigma;   // 1 / dsigma[k]
     const double *r_dss;      // 1 / (dsigma[k] + dsigma[k-1]),  k >= 1
+    const double *powtab;     // table of pow_kappa_tab (dc_point.h), DC_FAST_MATH only
 
     DC_HD size_t idx(int i, int j, int k) const
     {

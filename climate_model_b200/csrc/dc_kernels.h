@@ -792,7 +792,7 @@ struct PrimaryDiagBody {
     // production build: pow_kappa (dc_point.h) instead of pow(x, kappa)
     DC_HD double exner(double p) const
     {
-        return DC_FAST ? pow_kappa(p * 1e-5, pc) : pow(p / 100000., con_kappa);
+        return DC_FAST ? pow_kappa_tab(p * 1e-5, pc) : pow(p / 100000., con_kappa);
     }
     // One BOTTOM-UP sweep: the hydrostatic integral needs that direction, everything else is
     // level-local or couples two neighbouring levels, so POTT is read once and nothing the

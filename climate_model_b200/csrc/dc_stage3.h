@@ -24,7 +24,10 @@
 //     coefficient planes built once per block: no derived planes, no second phase, ONE block
 //     barrier per level (the ring-slot release).
 //
-// Per level: TMA wait -> everything in registers -> barrier.  Every expression keeps the
+// Per level: TMA wait -> everything in registers -> barrier (the ring-slot release; a
+// barrier-free hand-over through `empty` mbarriers exists behind DC_S3_SYNC=0 and measured
+// slower).  The refill of a slot is issued by one lane of warp k mod 4, so the ~130
+// instructions of the ten descriptors rotate over the warps.  Every expression keeps the
 // reference's evaluation order, so the strict build stays bit-identical to the
 // one-kernel-per-reference-kernel mode.  The periodic longitude images are read from the x
 // halo cells of the inputs (valid by construction: every producer stores its boundary
@@ -67,7 +70,34 @@ constexpr int S3_OWN = S3_OW * S3_TY;
 #endif
 constexpr int S3_NBUF = DC_S3_NBUF;
 constexpr int S3_PF = S3_NBUF - 1;                   // prefetch distance in levels
-constexpr int S3_NEED = S3_NBUF >= 3 ? 1 : 0;        // levels beyond k that must have landed
+// 1: the own U, V of level k+1 are read from the ring (level k+1 must have landed when level k
+// starts); 0: they are read from global memory (L2) and the ring runs one level further ahead
+#ifndef DC_S3_NEED
+#define DC_S3_NEED (DC_S3_NBUF >= 3 ? 1 : 0)
+#endif
+constexpr int S3_NEED = DC_S3_NEED;
+// where in level k the ring slot of level k-1 is refilled: 0 = at the top of the level (longest
+// lead for the copy), 1 = between the U and the V part (more slack for straggling warps)
+#ifndef DC_S3_REFILL_MID
+#define DC_S3_REFILL_MID 0
+#endif
+constexpr int S3_REFILL_MID = DC_S3_REFILL_MID;
+// How a ring slot is handed back.  1 (default): one block barrier per level, the refill follows
+// it at the top of the next level.  0: no block barrier -- every warp arrives on an `empty`
+// mbarrier and the refilling lane waits for it.  Measured on B200 (0.25 deg x 64 levels,
+// profiles/r2_stage_variants.md): the barrier-free ring is SLOWER (3.19-3.99 ms/step against
+// 3.06): the warps of a block drift apart, and the ring's lead time, not the barrier, is what
+// the level loop is sensitive to.
+#ifndef DC_S3_SYNC
+#define DC_S3_SYNC 1
+#endif
+constexpr int S3_SYNC = DC_S3_SYNC;
+// which warp issues the refill of level k: 1 = warp k mod 4 (the ~130 instructions of the ten
+// descriptors rotate over the warps), 0 = always warp 0
+#ifndef DC_S3_ROTATE
+#define DC_S3_ROTATE 1
+#endif
+constexpr int S3_ROTATE = DC_S3_ROTATE;
 
 // ---- TMA descriptor -------------------------------------------------------------------
 #if defined(__CUDACC__)
@@ -113,10 +143,11 @@ struct alignas(128) Stage3Smem {
     // flux coefficients of the staged cells (level independent):
     //   CU = (COLP[i-1,j] + COLP[i,j]) / 2, CV = (COLP[i,j-1] + COLP[i,j]) / 2, CP = COLP_NEW*A
     double CU[S3_PL], CV[S3_PL], CP[S3_PL];
-    double lev[6][NZMAX + 1];   // as StageSmem::lev
+    double lev[7][NZMAX + 1];   // per-level tables (see the set-up phase)
     double row[7][S3_TY + 1];   // as StageSmem::row
     double dxr[S3_SH + 1];      // dxjs of the staged rows rj = -1 .. TY+1
-    unsigned long long full[S3_NBUF];   // mbarriers: "level has landed"
+    unsigned long long full[S3_NBUF];   // mbarriers: "level has landed" (TMA transaction bytes)
+    unsigned long long empty[S3_NBUF];  // mbarriers: "every warp is done with the slot"
 };
 
 // ---- SPMD layer for this kernel (1-D block of S3_NT threads) ----------------------------
@@ -131,7 +162,12 @@ struct alignas(128) Stage3Smem {
     }                \
     __syncthreads();
 #define S3_PHASE_END_NOSYNC }
+#define S3_PHASE_END_MAYBE_SYNC \
+    }                           \
+    if (S3_SYNC) __syncthreads();
+#define S3_SYNCWARP() __syncwarp()
 #else
+#define S3_SYNCWARP()
 #define S3_PRIV(type, name) type name[S3_NT]
 #define S3_PRIVN(type, name, n) type name[S3_NT][n]
 #define S3_PRIVNN(type, name, n, m) type name[S3_NT][n][m]
@@ -139,6 +175,7 @@ struct alignas(128) Stage3Smem {
 #define S3_PHASE for (int tid = 0; tid < S3_NT; tid++) {
 #define S3_PHASE_END }
 #define S3_PHASE_END_NOSYNC }
+#define S3_PHASE_END_MAYBE_SYNC }
 #endif
 
 #if defined(__CUDACC__)
@@ -168,6 +205,14 @@ DC_HD void s3_mbar_init_fence()
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 #endif
 }
+DC_HD void s3_mbar_arrive(unsigned long long *bar)
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s3_smem_u32(bar)) : "memory");
+#else
+    (void)bar;
+#endif
+}
 DC_HD void s3_mbar_expect(unsigned long long *bar, unsigned bytes)
 {
 #if defined(__CUDA_ARCH__)
@@ -185,6 +230,7 @@ DC_HD void s3_mbar_wait(unsigned long long *bar, unsigned parity)
 {
 #if defined(__CUDA_ARCH__)
     const unsigned addr = s3_smem_u32(bar);
+#pragma unroll 1
     for (int spin = 0; spin < (1 << 24); spin++) {
         unsigned done;
         asm volatile(
@@ -219,6 +265,7 @@ DC_HD void s3_tma_load(void *dst, const TmaMap *map, int x, int y, int z, unsign
 #else
 inline void s3_mbar_init(unsigned long long *, int) {}
 inline void s3_mbar_init_fence() {}
+inline void s3_mbar_arrive(unsigned long long *) {}
 inline void s3_mbar_expect(unsigned long long *, unsigned) {}
 inline void s3_mbar_wait(unsigned long long *, unsigned) {}
 inline void s3_tma_load(void *dst, const TmaMap *m, int x, int y, int z, unsigned long long *)
@@ -322,6 +369,17 @@ struct Stage3Body {
         }
     }
 
+    // Refill of the ring during level k: level k + PF goes into the slot level k-1 used, as
+    // soon as every warp has reported that slot free.  One lane of warp k mod (warps per block).
+    DC_HD void refill(Stage3Smem &s, int tid, int k, int ks, int ke, int x0, int y0) const
+    {
+        if (k + S3_PF > ke) return;
+        if (tid != (S3_ROTATE ? (k % (S3_NT / 32)) * 32 : 0)) return;
+        if (!S3_SYNC && k > ks)
+            s3_mbar_wait(&s.empty[(k - 1 - ks) % S3_NBUF], ((k - 1 - ks) / S3_NBUF) & 1);
+        issue(s, k + S3_PF, ks, x0, y0);
+    }
+
     template <bool EDGE>
     DC_HD void run(int bx, int by, int bz, int j_lo, int j_hi, Stage3Smem &s) const
     {
@@ -369,11 +427,30 @@ struct Stage3Body {
         S3_PRIVN(double, wwv_k, 2);
         S3_PRIVN(double, w_k, 2);           // WWIND[k]
         S3_PRIVN(double, pottvb_k, 2);
+        // production arithmetic (dc_stage3_fast.inc): per-column factors with everything that
+        // does not depend on the level folded in (dead in the strict build)
+        S3_PRIVN(double, q_cs, 4);          // scale/2 * COLP at ia-1, ia, ia+1, ia+2 of row j
+        S3_PRIVN(double, q_csm, 2);         // ... at row j-1, j+1 of the own columns
+        S3_PRIVN(double, q_csp, 2);
+        S3_PRIVN(double, q_ru, 2);          // Euler step: x_old * q_r* + tendency * q_d*
+        S3_PRIVN(double, q_du, 2);
+        S3_PRIVN(double, q_rv, 2);
+        S3_PRIVN(double, q_dv, 2);
+        S3_PRIVN(double, q_rt, 2);
+        S3_PRIVN(double, q_dtt, 2);
+        S3_PRIVN(double, q_px1, 2);         // pressure gradient along x / y
+        S3_PRIVN(double, q_px2, 2);
+        S3_PRIVN(double, q_py1, 2);
+        S3_PRIVN(double, q_py2, 2);
+        S3_PRIVN(double, q_tf, 2);          // WWIND * POTTVB at interface k (carried)
 
         // ---- set-up -----------------------------------------------------------------------
         S3_PHASE
             if (tid == 0) {
-                for (int n = 0; n < S3_NBUF; n++) s3_mbar_init(&s.full[n], 1);
+                for (int n = 0; n < S3_NBUF; n++) {
+                    s3_mbar_init(&s.full[n], 1);
+                    s3_mbar_init(&s.empty[n], S3_NT / 32);
+                }
                 s3_mbar_init_fence();
             }
         S3_PHASE_END
@@ -398,12 +475,13 @@ struct Stage3Body {
                 // UFLX = (C[i-1] + C[i])/2 * U * dyis     (dyn_continuity.py:40-41)
                 // (production build: dyis / dxjs are folded into the planes, one multiplication
                 // less per flux value in the level loop)
-                s.CU[n] = (COLP[g.idx2(iwm, jm)] + COLP[g.idx2(iw, jm)]) / 2. * (DC_FAST ? dyis : 1.);
+                s.CU[n] = (COLP[g.idx2(iwm, jm)] + COLP[g.idx2(iw, jm)]) / 2. *
+                          (DC_FAST ? dyis * (1. / 48.) : 1.);
                 // VFLX = (C[j-1] + C[j])/2 * V * dxjs     (dyn_continuity.py:43-44)
                 s.CV[n] = (COLP[g.idx2(iw, jcm)] + COLP[g.idx2(iw, jc)]) / 2. *
-                          (DC_FAST ? g.dxjs[g.row(jy)] : 1.);
+                          (DC_FAST ? g.dxjs[g.row(jy)] * (1. / 48.) : 1.);
                 // COLP_NEW * A * WWIND                    (dyn_functions.py:254-260)
-                s.CP[n] = COLP_NEW[g.idx2(iw, jm)] * g.A[g.row(jm)];
+                s.CP[n] = COLP_NEW[g.idx2(iw, jm)] * g.A[g.row(jm)] * (DC_FAST ? 0.125 : 1.);
             }
             if (tid <= S3_SH) {
                 int j = J0 - 1 + tid;
@@ -465,27 +543,57 @@ struct Stage3Body {
                     S3_P(w_k)[e] = WWIND[(size_t)ks * plane + S3_P(off0) + e];
                     S3_P(pottvb_k)[e] = POTTVB[(size_t)ks * plane + S3_P(off0) + e];
                 }
+                if (DC_FAST) {
+                    const double sc2 = scale / 2., dxj = g.dxjs[g.row(jj)];
+                    S3_P(q_cs)[0] = sc2 * S3_P(c_m1); S3_P(q_cs)[1] = sc2 * S3_P(c_a);
+                    S3_P(q_cs)[2] = sc2 * S3_P(c_b);  S3_P(q_cs)[3] = sc2 * S3_P(c_p1);
+                    for (int e = 0; e < 2; e++) {
+                        S3_P(q_csm)[e] = sc2 * S3_P(c_jm1)[e];
+                        S3_P(q_csp)[e] = sc2 * S3_P(c_jp1)[e];
+                        S3_P(q_ru)[e] = S3_P(colpa_old_is)[e] / S3_P(colpa_is)[e];
+                        S3_P(q_du)[e] = dt / S3_P(colpa_is)[e];
+                        S3_P(q_rv)[e] = S3_P(colpa_old_js)[e] / S3_P(colpa_js)[e];
+                        S3_P(q_dv)[e] = dt / S3_P(colpa_js)[e];
+                        S3_P(q_rt)[e] = S3_P(cold)[e] / S3_P(cnew)[e];
+                        S3_P(q_dtt)[e] = dt / S3_P(cnew)[e];
+                        S3_P(q_px1)[e] = -dyis * S3_P(csx)[e] / 2.;
+                        S3_P(q_px2)[e] = -dyis * S3_P(cdx)[e];
+                        S3_P(q_py1)[e] = -dxj * S3_P(csy)[e] / 2.;
+                        S3_P(q_py2)[e] = -dxj * S3_P(cdy)[e];
+                        // WWIND[0] = 0: the flux through the model top is exactly 0
+                        S3_P(q_tf)[e] = ks == 0 ? 0. : S3_P(w_k)[e] * S3_P(pottvb_k)[e];
+                    }
+                }
             }
             // constant tables
             for (int k = tid; k <= nz; k += S3_NT) {
                 s.lev[0][k] = k < nz ? g.dsigma[k] : 0.;
                 s.lev[1][k] = k < nz ? g.r_dsigma[k] : 0.;
                 s.lev[2][k] = g.sigma_vb[k];
-                s.lev[3][k] = k < nz ? g.UVFLX_dif_coef[k] : 0.;
-                s.lev[4][k] = k < nz ? g.POTT_dif_coef[k] : 0.;
-                s.lev[5][k] = k < nz ? g.r_dss[k] : 0.;
+                if (DC_FAST) {
+                    // UFLX, VFLX travel scaled by 1/48, COLP by scale/2; interp_ks as two weights
+                    s.lev[3][k] = k < nz ? g.UVFLX_dif_coef[k] * 48. : 0.;
+                    s.lev[4][k] = k < nz ? g.POTT_dif_coef[k] / (scale / 2.) : 0.;
+                    s.lev[5][k] = (k >= 1 && k < nz) ? g.dsigma[k] * g.r_dss[k] : 0.;
+                    s.lev[6][k] = (k >= 1 && k < nz) ? g.dsigma[k - 1] * g.r_dss[k] : 0.;
+                } else {
+                    s.lev[3][k] = k < nz ? g.UVFLX_dif_coef[k] : 0.;
+                    s.lev[4][k] = k < nz ? g.POTT_dif_coef[k] : 0.;
+                    s.lev[5][k] = k < nz ? g.r_dss[k] : 0.;
+                    s.lev[6][k] = 0.;
+                }
             }
             if (tid <= S3_TY) {
                 int j = J0 - 1 + tid;
                 if (j > j_max_m) j = j_max_m;
                 const int r = g.row(j);
                 s.row[0][tid] = cor_fcos(g.corf_is[r], g.cos_lat_is[r]);
-                s.row[1][tid] = g.sin_lat_is[r];
+                s.row[1][tid] = g.sin_lat_is[r] * (DC_FAST ? 0.5 : 1.);
                 s.row[2][tid] = cor_fcos(g.corf[r], g.cos_lat[r]);
-                s.row[3][tid] = g.sin_lat[r];
+                s.row[3][tid] = g.sin_lat[r] * (DC_FAST ? 0.5 : 1.);
                 s.row[4][tid] = g.dxjs[r];
                 s.row[5][tid] = g.A[r];
-                s.row[6][tid] = g.r_A[r];
+                s.row[6][tid] = g.r_A[r] * (DC_FAST ? 24. : 1.);
             }
             s3_mbar_wait(&s.full[0], 0);   // the first level has landed
         S3_PHASE_END
@@ -495,11 +603,9 @@ struct Stage3Body {
             const bool warm = k < k0;   // warm-up level of a chunk: nothing is stored
             const size_t ko = (size_t)k * plane;
             const bool last = (k + 1 == nz);
-            // ---- ring: issue level k+2, make sure level k+1 (own U, V of the interface
-            //      interpolation) has landed; level k was awaited one iteration ago ---------
+            // ---- ring: make sure the levels this iteration reads have landed ----------------
             S3_PHASE
-                // level k+PF -> the slot level k-1 has released (trailing barrier of level k-1)
-                if (tid == 0 && k + S3_PF <= ke) issue(s, k + S3_PF, ks, x0, y0);
+                if (EDGE || !S3_REFILL_MID) refill(s, tid, k, ks, ke, x0, y0);
                 if (S3_NEED) {
                     if (!last) s3_mbar_wait(&s.full[b1], ((k + 1 - ks) / S3_NBUF) & 1);
                 } else {
@@ -518,7 +624,10 @@ struct Stage3Body {
                 const R4 W_0 = ld4(&s.rW[b][b0]);
                 const double w_kp1[2] = {W_0.a, W_0.b};
                 const int fl = S3_P(flags);
-                if (!EDGE || (fl & 3)) {
+                if (DC_FAST && (!EDGE || (fl & 3))) {
+#include "dc_stage3_fast.inc"
+                }
+                if (!DC_FAST && (!EDGE || (fl & 3))) {
                     const bool wall_s = EDGE && (j == 1), wall_n = EDGE && (j == ny);
                     // raw winds around the pair and, from them, UFLX / VFLX
                     // (calc_UFLX, calc_VFLX: dyn_continuity.py:40-47)
@@ -717,6 +826,7 @@ struct Stage3Body {
                             }
                         }
                     }
+                    if (!EDGE && S3_REFILL_MID) refill(s, tid, k, ks, ke, x0, y0);
                     // ---------------- dVFLXdt (dyn_VFLX.py:67-198) ----------------
                     if (!EDGE || j >= 2) {
                         double R_a, R_b, R_a_jm1, R_b_jm1, Q_a, Q_b, Q_p1, S_a_jm1, S_b_jm1, S_b,
@@ -874,7 +984,13 @@ struct Stage3Body {
                     S3_P(w_k)[e] = w_kp1[e];
                     S3_P(pottvb_k)[e] = pottvb_kp1[e];
                 }
-            S3_PHASE_END
+                // this warp is done with the slot of level k (its reads are complete: their
+                // values were consumed above); the refill of level k+1 waits for all warps
+                if (!S3_SYNC && k + 1 + S3_PF <= ke) {
+                    S3_SYNCWARP();
+                    if ((tid & 31) == 0) s3_mbar_arrive(&s.empty[b]);
+                }
+            S3_PHASE_END_MAYBE_SYNC
         }
     }
 };

@@ -93,9 +93,22 @@ def sub1(text, pattern, repl, count=0, must=True):
     return new
 
 
-def prepare_scratch(grid, coupling=False):
-    """copy reference *.py + data/ to a scratch dir and apply shims/patches"""
-    d = tempfile.mkdtemp(prefix='cm_ref_')
+def _env(name, default):
+    """namelist value that the environment may override at import time (oracle/_ref)"""
+    return "type(%r)(__import__('os').environ.get('CMREF_%s', %r))" % (default, name, default)
+
+
+def prepare_scratch(grid, coupling=False, dest=None, env_grid=False):
+    """copy reference *.py + data/ to a scratch dir (or `dest`) and apply shims/patches;
+    env_grid: the grid parameters of the patched namelist read CMREF_NZ, CMREF_LAT0_DEG,
+    CMREF_LAT1_DEG, CMREF_DLAT_DEG, CMREF_DLON_DEG, CMREF_USE_TOPO from the environment
+    (defaults = `grid`), so that one prepared tree serves every sample grid"""
+    if dest is None:
+        d = tempfile.mkdtemp(prefix='cm_ref_')
+    else:
+        d = dest
+        shutil.rmtree(d, ignore_errors=True)
+        os.makedirs(d)
     for f in os.listdir(REF):
         if f.endswith('.py'):
             shutil.copy(os.path.join(REF, f), os.path.join(d, f))
@@ -135,14 +148,18 @@ def prepare_scratch(grid, coupling=False):
     for name in ('i_surface_scheme', 'i_turbulence', 'i_radiation', 'i_microphysics'):
         t = sub1(t, r'^(\s*)%s = 1$' % name, r'\g<1>%s = 0' % name)
     # grid of the "longtime run" preset block
-    t = sub1(t, r'^    nz = 32$', '    nz = %d' % grid['nz'])
-    t = sub1(t, r'^    lat0_deg = -84$', '    lat0_deg = %r' % grid['lat0_deg'])
-    t = sub1(t, r'^    lat1_deg = 84$', '    lat1_deg = %r' % grid['lat1_deg'])
-    t = sub1(t, r'^    dlat_deg = 1\.0$', '    dlat_deg = %r' % grid['dlat_deg'])
-    t = sub1(t, r'^    dlon_deg = 1\.0$', '    dlon_deg = %r' % grid['dlon_deg'])
+    val = (lambda k, cast: _env(k.upper(), cast(grid[k]))) if env_grid else \
+          (lambda k, cast: repr(grid[k]))
+    t = sub1(t, r'^    nz = 32$', '    nz = %s' % val('nz', int))
+    t = sub1(t, r'^    lat0_deg = -84$', '    lat0_deg = %s' % val('lat0_deg', float))
+    t = sub1(t, r'^    lat1_deg = 84$', '    lat1_deg = %s' % val('lat1_deg', float))
+    t = sub1(t, r'^    dlat_deg = 1\.0$', '    dlat_deg = %s' % val('dlat_deg', float))
+    t = sub1(t, r'^    dlon_deg = 1\.0$', '    dlon_deg = %s' % val('dlon_deg', float))
     t = sub1(t, r'^    i_out_nth_hour = 1/2\*24$',
              '    i_out_nth_hour = %r' % grid.get('i_out_nth_hour', 12.0))
-    if not grid.get('use_topo', True):
+    if env_grid:
+        t = sub1(t, r'^i_use_topo = 1$', 'i_use_topo = %s' % _env('USE_TOPO', 1))
+    elif not grid.get('use_topo', True):
         t = sub1(t, r'^i_use_topo = 1$', 'i_use_topo = 0')
     for key in ('UWIND_random_pert', 'VWIND_random_pert', 'POTT_random_pert',
                 'QV_random_pert', 'COLP_random_pert'):

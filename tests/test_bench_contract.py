@@ -22,7 +22,8 @@ def _bench(*args):
 
 
 def test_reference_arm_line():
-    d = _bench('--impl', 'reference', '--workload', 'cfg1', '--steps', '2', '--warmup', '1')
+    d = _bench('--impl', 'reference', '--port', '--workload', 'cfg1', '--steps', '2',
+               '--warmup', '1')
     assert BASE_KEYS <= set(d) and d['impl'] == 'reference'
     assert d['metric'] == 'dyn-core cell-updates/s' and d['unit'] == 'cell-updates/s'
     assert d['value'] > 0 and d['higher_is_better'] is True and d['vs_baseline'] is None
@@ -31,10 +32,34 @@ def test_reference_arm_line():
     assert cb['kind'] == 'port' and cb['cores'] >= 1 and cb['value'] == d['value'] and cb['sample']
     assert d['e2e'] == {'value': d['value'], 'unit': d['unit'], 'h2d_bytes_per_step': 0,
                         'd2h_bytes_per_step': 0}
+    c = d['config']
+    assert (c['sample_nx'], c['sample_ny'], c['sample_nz']) == (72, 32, 8)
+
+
+def test_reference_arm_runs_the_numba_reference_when_prepared():
+    """with oracle/_ref prepared (build container: oracle/build_ref.py from /root/reference) the
+    arm times the reference's own numba-CPU step, on every host thread even when the launcher
+    exports OMP_NUM_THREADS=1 (torchrun does)"""
+    import pytest
+    if not os.path.exists(os.path.join(ROOT, 'oracle', '_ref', 'dyn_matsuno.py')):
+        pytest.skip('oracle/_ref is not prepared')
+    env = dict(os.environ, OMP_NUM_THREADS='1')
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference',
+                        '--workload', 'cfg1', '--steps', '2', '--warmup', '2'],
+                       capture_output=True, text=True, timeout=1500, cwd=ROOT, env=env)
+    assert r.returncode == 0, r.stderr[-3000:]
+    d = json.loads(r.stdout.splitlines()[-1])
+    cb = d['cpu_baseline']
+    assert cb['kind'] == 'reference' and 'numba' in cb['sample'] and d['value'] > 0
+    assert cb['cores'] == len(os.sched_getaffinity(0))
+    # no product library in the reference arm's address space: it is a separate interpreter
+    # that imports only oracle/ref_bench.py and the prepared reference tree
+    src = open(os.path.join(ROOT, 'oracle', 'ref_bench.py')).read()
+    assert 'climate_model_b200' not in src.replace('MEASUREMENT', '')
 
 
 def test_b200_arm_logic_on_the_host_emulation():
-    d = _bench('--emu', '--workload', 'cfg1', '--steps', '2', '--warmup', '1')
+    d = _bench('--emu', '--port', '--workload', 'cfg1', '--steps', '2', '--warmup', '1')
     assert d['emu'] is True                      # never mistaken for a measurement
     assert BASE_KEYS | {'roofline', 'step_roofline', 'gpu_launches', 'clocks', 'cpu_baseline',
                         'kernels_ms_per_step', 'ms_per_step_with_kernel_events'} <= set(d)
@@ -43,8 +68,11 @@ def test_b200_arm_logic_on_the_host_emulation():
     # 2 steps x (COLP_OLD copy aside) 2 stages x (continuity, stage kernel, diagnostics) + x-halo fix
     assert d['gpu_launches'] == 2 * (2 * 3 + 1)
     e = d['e2e']
-    assert e['members'] == 12 and e['h2d_bytes_per_step'] == e['d2h_bytes_per_step'] > 0
-    assert e['value'] > 0 and e['finite'] is True and e['one_state_at_a_time_ms'] > 0
+    # the headline e2e advances ONE host-resident state; the streamed ensemble is an extra
+    assert e['h2d_bytes_per_step'] == e['d2h_bytes_per_step'] > 0 and e['value'] > 0
+    assert e['what'].startswith('pinned host state') and e['repeats'] == 3
+    st = e['streamed']
+    assert st['members'] == 12 and st['value'] > 0 and st['finite'] is True
     assert d['step_roofline']['algorithmic_bytes_per_cell_update'] == 216
     assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['value'] > 0
 
