@@ -21,6 +21,19 @@
 //   void dcb_profile_begin(dc_handle *h, const char *name, void *stream);
 //   void dcb_profile_end(dc_handle *h, void *stream);
 //   int  dcb_profile_read(dc_handle *h, int max, const char **names, double *ms, long long *n);
+//   in-library halo exchange (CUDA backend: NCCL; the host emulation has none and returns
+//   DC_ERR_NO_DEVICE from dcb_comm_init):
+//   int  dcb_comm_unique_id(void *id128);
+//   int  dcb_comm_init(dc_handle *h, const void *id128, int rank, int nranks, size_t halo_elems);
+//   void dcb_comm_release(dc_handle *h);
+//   double *dcb_comm_buffer(dc_handle *h, int which);   // 0 send_s, 1 recv_s, 2 send_n, 3 recv_n
+//   int  dcb_comm_sendrecv(dc_handle *h, void *stream); // grouped send/recv with both neighbours
+//   void *dcb_side_stream(dc_handle *h);
+//   void dcb_event_record(dc_handle *h, int ev, void *stream);
+//   void dcb_stream_wait(dc_handle *h, int ev, void *stream);
+//   int  dcb_graph_step(dc_handle *h, int nsteps, void *stream, void (*enqueue)(dc_handle *, void *));
+//        // capture one step enqueued by `enqueue` into a CUDA graph (once per binding
+//        // version) and launch it nsteps times; returns 0 if it ran, 1 if graphs are unavailable
 #pragma once
 #include <math.h>
 #include <stdarg.h>
@@ -121,6 +134,10 @@ struct dc_handle {
     int coupled_impl;     // i_coupling: 1 = kernel decomposition (default), 2 = fused dry stage
                           // kernel + coupled increments (DC_COUPLED_IMPL=2, experimental)
     void *tma_state;      // backend-owned descriptor cache
+    void *comm_state;     // backend-owned: NCCL communicator, side stream, events, buffers
+    int comm_rank, comm_nranks;
+    long long bind_version;   // bumped whenever a bound pointer changes (CUDA-graph cache key)
+    int band_graph;       // replay the banded step from a CUDA graph (DC_BAND_GRAPH, default 1)
     double **slot(int id) { return reinterpret_cast<double **>(&f) + id; }
     double *const *slot(int id) const { return reinterpret_cast<double *const *>(&f) + id; }
 };
@@ -432,12 +449,12 @@ static void do_xhalo_fix(dc_handle *h, void *stream)
     launch(h, "xhalo_fix", XHaloFixBody{g, h->f.UWIND}, 0, g.nz - 1, lo, hi, stream);
 }
 
-// primary diagnostics of the state a stage produced, on every row this rank holds
-static void do_diag_fused(dc_handle *h, int stage, void *stream)
+// primary diagnostics of the state a stage produced, on the held rows [lo, hi]
+static void do_diag_rows(dc_handle *h, int stage, int lo, int hi, void *stream)
 {
     const Fields &f = h->f;
     const Geom &g = h->g;
-    const int lo = g.j0 - HJ < 0 ? 0 : g.j0 - HJ, hi = g.j1 + HJ > g.ny + 1 ? g.ny + 1 : g.j1 + HJ;
+    if (hi < lo) return;
     // the stage kernel reads PHI, POTTVB and PGCOL only: PVTF, PVTFVB and PHIVB are not
     // stored between stages (dc_primary_diag refreshes them on demand)
     const double *T = stage == 0 ? f.POTT_OLD : f.POTT;
@@ -453,6 +470,14 @@ static void do_diag_fused(dc_handle *h, int stage, void *stream)
                              make_pow_coef(con_kappa, g.powtab)};
         launch(h, "primary_diag", b, 0, g.nx + 1, 0, (hi - lo) / b.NC, stream);
     }
+}
+
+// ... on every row this rank holds
+static void do_diag_fused(dc_handle *h, int stage, void *stream)
+{
+    const Geom &g = h->g;
+    const int lo = g.j0 - HJ < 0 ? 0 : g.j0 - HJ, hi = g.j1 + HJ > g.ny + 1 ? g.ny + 1 : g.j1 + HJ;
+    do_diag_rows(h, stage, lo, hi, stream);
 }
 
 static const std::vector<int> NEED_CONT = {F_UWIND, F_VWIND, F_COLP, F_COLP_OLD, F_UFLX,
@@ -634,6 +659,14 @@ int dc_create(const dc_grid_desc *d, dc_handle **out)
     h->mode = DC_MODE_FUSED;
     h->profile_state = nullptr;
     h->tma_state = nullptr;
+    h->comm_state = nullptr;
+    h->comm_rank = 0;
+    h->comm_nranks = 1;
+    h->bind_version = 0;
+    {
+        const char *bg = getenv("DC_BAND_GRAPH");
+        h->band_graph = (bg && bg[0] == '0') ? 0 : 1;
+    }
     h->diag_partial = 0;
     const char *impl = getenv("DC_STAGE_IMPL");
     h->stage_impl = (impl && impl[0] == '2') ? 2 : 3;
@@ -650,6 +683,7 @@ int dc_create(const dc_grid_desc *d, dc_handle **out)
 int dc_destroy(dc_handle *h)
 {
     if (!h) return DC_OK;
+    dcb_comm_release(h);
     if (h->geom_buf) dcb_free(h->geom_buf);
     dcb_tma_release(h);
     delete h;
@@ -673,6 +707,7 @@ int dc_bind_field(dc_handle *h, int id, void *devptr, size_t nbytes)
     if (devptr && nbytes < need_bytes)
         return fail(DC_ERR_SHAPE, "dc_bind_field: %s needs %zu bytes, got %zu",
                     g_field_info[id].name, need_bytes, nbytes);
+    if (*h->slot(id) != static_cast<double *>(devptr)) h->bind_version++;
     *h->slot(id) = static_cast<double *>(devptr);
     return DC_OK;
 }
@@ -1029,6 +1064,109 @@ int dc_halo_unpack(dc_handle *h, int stage, const void *recv_south, const void *
                      "dc_halo_unpack");
 }
 
+// ---------------------------------------------------------------------------------------
+// in-library halo exchange and the banded step (include/dyncore.h)
+// ---------------------------------------------------------------------------------------
+int dc_comm_unique_id(void *id, size_t nbytes)
+{
+    if (!id || nbytes < DC_COMM_ID_BYTES)
+        return fail(DC_ERR_ARG, "dc_comm_unique_id: need a %d-byte buffer", DC_COMM_ID_BYTES);
+    const int e = dcb_comm_unique_id(id);
+    if (e) return fail(e, "dc_comm_unique_id: %s", dcb_comm_error());
+    return DC_OK;
+}
+
+int dc_set_comm(dc_handle *h, const void *id, size_t nbytes, int rank, int nranks)
+{
+    if (!h || !id || nbytes < DC_COMM_ID_BYTES || nranks < 1 || rank < 0 || rank >= nranks)
+        return fail(DC_ERR_ARG, "dc_set_comm: bad argument");
+    size_t hb = 0;
+    dc_halo_bytes(h, &hb);
+    dcb_comm_release(h);
+    const int e = dcb_comm_init(h, id, rank, nranks, hb / sizeof(double));
+    if (e) return fail(e, "dc_set_comm: %s", dcb_comm_error());
+    h->comm_rank = rank;
+    h->comm_nranks = nranks;
+    return DC_OK;
+}
+
+int dc_has_comm(const dc_handle *h) { return h && h->comm_state ? 1 : 0; }
+
+int dc_halo_exchange(dc_handle *h, int stage, void *stream)
+{
+    if (!h || stage < 0 || stage > 1) return fail(DC_ERR_ARG, "dc_halo_exchange: bad argument");
+    if (!h->comm_state) return fail(DC_ERR_STATE, "dc_halo_exchange: no communicator (dc_set_comm)");
+    const bool south = h->comm_rank > 0, north = h->comm_rank < h->comm_nranks - 1;
+    int rc;
+    if ((rc = halo_move(h, stage, south ? dcb_comm_buffer(h, 0) : nullptr,
+                        north ? dcb_comm_buffer(h, 2) : nullptr, 1, stream, "dc_halo_exchange")))
+        return rc;
+    const int e = dcb_comm_sendrecv(h, stream);
+    if (e) return fail(e, "dc_halo_exchange: %s", dcb_comm_error());
+    return halo_move(h, stage, south ? dcb_comm_buffer(h, 1) : nullptr,
+                     north ? dcb_comm_buffer(h, 3) : nullptr, 0, stream, "dc_halo_exchange");
+}
+
+enum { EV_CONT = 0, EV_BDONE = 1, EV_RECV = 2, EV_COUNT = 3 };
+
+// One Matsuno step on a latitude band with the exchange inside the library (stream M = the
+// caller's, S = the handle's high-priority side stream).  Per stage:
+//   M: continuity (rows j0-1 .. j1+1)                          S: waits for it, then
+//   M: stage kernel on the interior tile rows                  S: stage kernel on the first and
+//                                                                 last tile row, pack, NCCL
+//   M: COLP <- COLP_NEW (after both stage-kernel launches)        send/recv with both neighbours
+//   M: diagnostics of the rows that need no neighbour data  -- the halo is in flight meanwhile
+//   M: waits for the receive, unpack, diagnostics of the halo rows
+// so that the exchange hides behind the interior tile rows AND the diagnostics sweep.
+static void enqueue_band_step(dc_handle *h, void *M)
+{
+    const Fields &f = h->f;
+    const Geom &g = h->g;
+    void *S = dcb_side_stream(h);
+    const bool south = h->comm_rank > 0, north = h->comm_rank < h->comm_nranks - 1;
+    const int lo = g.j0 - HJ < 0 ? 0 : g.j0 - HJ, hi = g.j1 + HJ > g.ny + 1 ? g.ny + 1 : g.j1 + HJ;
+    const int own_lo = south ? g.j0 : lo, own_hi = north ? g.j1 : hi;
+    dcb_d2d_async(f.COLP_OLD, f.COLP, g.plane * sizeof(double), M);      // dyn_matsuno.py:34
+    for (int stage = 0; stage < 2; stage++) {
+        do_stage_fused(h, stage, DC_PART_CONT, M);
+        dcb_event_record(h, EV_CONT, M);
+        dcb_stream_wait(h, EV_CONT, S);
+        do_stage_fused(h, stage, DC_PART_BOUNDARY, S);
+        dcb_event_record(h, EV_BDONE, S);
+        halo_move(h, stage, south ? dcb_comm_buffer(h, 0) : nullptr,
+                  north ? dcb_comm_buffer(h, 2) : nullptr, 1, S, "dc_step_matsuno");
+        dcb_comm_sendrecv(h, S);
+        dcb_event_record(h, EV_RECV, S);
+        do_stage_fused(h, stage, DC_PART_INTERIOR, M);
+        dcb_stream_wait(h, EV_BDONE, M);             // both launches have read COLP
+        do_stage_fused(h, stage, DC_PART_COLP, M);
+        do_diag_rows(h, stage, own_lo, own_hi, M);
+        dcb_stream_wait(h, EV_RECV, M);
+        halo_move(h, stage, south ? dcb_comm_buffer(h, 1) : nullptr,
+                  north ? dcb_comm_buffer(h, 3) : nullptr, 0, M, "dc_step_matsuno");
+        if (south) do_diag_rows(h, stage, lo, g.j0 - 1, M);
+        if (north) do_diag_rows(h, stage, g.j1 + 1, hi, M);
+    }
+}
+
+static int step_matsuno_banded(dc_handle *h, int nsteps, void *stream)
+{
+    int rc;
+    if ((rc = check_fused_fields(h, "dc_step_matsuno"))) return rc;
+    const Geom &g = h->g;
+    if (g.i_coupling || h->mode != DC_MODE_FUSED || g.nz > NZMAX || h->stage_impl != 3)
+        return fail(DC_ERR_STATE, "dc_step_matsuno: a latitude band runs the fused dry / moist "
+                                  "path only (nz <= %d)", NZMAX);
+    if (g.j1 - g.j0 + 1 < HJ)
+        return fail(DC_ERR_STATE, "dc_step_matsuno: a band needs at least %d rows", HJ);
+    do_xhalo_fix(h, stream);
+    // the per-kernel event brackets of dc_profile_enable cannot be captured: plain enqueue then
+    if (!h->band_graph || h->profiling || dcb_graph_step(h, nsteps, stream, enqueue_band_step))
+        for (int s = 0; s < nsteps; s++) enqueue_band_step(h, stream);
+    if (dcb_comm_error()[0]) return fail(DC_ERR_STATE, "dc_step_matsuno: %s", dcb_comm_error());
+    return backend_status("dc_step_matsuno");
+}
+
 int dc_set_mode(dc_handle *h, int mode)
 {
     if (!h) return fail(DC_ERR_ARG, "dc_set_mode: NULL handle");
@@ -1040,9 +1178,17 @@ int dc_set_mode(dc_handle *h, int mode)
 
 int dc_step_matsuno(dc_handle *h, int nsteps, void *stream)
 {
-    DC_ENTRY_CHECK("dc_step_matsuno");  // a band needs the halo exchange between stages:
-                                        // dc_step_begin / dc_stage_compute / dc_halo_* / dc_stage_diag
+    if (!h) return fail(DC_ERR_ARG, "dc_step_matsuno: NULL handle");
     if (nsteps < 0) return fail(DC_ERR_ARG, "dc_step_matsuno: nsteps < 0");
+    if (h->g.j0 != 1 || h->g.j1 != h->g.ny) {
+        // a band needs the halo exchange between the stages: with a communicator attached
+        // (dc_set_comm) the library runs it; without, the caller drives dc_step_begin /
+        // dc_stage_compute / dc_halo_pack / dc_halo_unpack / dc_stage_diag itself
+        if (!h->comm_state)
+            return fail(DC_ERR_STATE, "dc_step_matsuno: a latitude band needs dc_set_comm (or the "
+                                      "piecewise band entries)");
+        return step_matsuno_banded(h, nsteps, stream);
+    }
     int rc;
     if ((rc = need(h, "dc_step_matsuno", NEED_CONT)) || (rc = need(h, "dc_step_matsuno", NEED_MOM)) ||
         (rc = need(h, "dc_step_matsuno", NEED_TEMP)) ||

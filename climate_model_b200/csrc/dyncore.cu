@@ -221,7 +221,237 @@ static void dcb_profile_begin(dc_handle *h, const char *name, void *stream);
 static void dcb_profile_end(dc_handle *h, void *stream);
 static int dcb_profile_read(dc_handle *h, int max, const char **names, double *ms, long long *n);
 
+// in-library halo exchange: NCCL communicator, side stream, events, CUDA graph (defined below)
+static int dcb_comm_unique_id(void *id128);
+static int dcb_comm_init(dc_handle *h, const void *id128, int rank, int nranks, size_t halo_elems);
+static void dcb_comm_release(dc_handle *h);
+static double *dcb_comm_buffer(dc_handle *h, int which);
+static int dcb_comm_sendrecv(dc_handle *h, void *stream);
+static void *dcb_side_stream(dc_handle *h);
+static void dcb_event_record(dc_handle *h, int ev, void *stream);
+static void dcb_stream_wait(dc_handle *h, int ev, void *stream);
+static int dcb_graph_step(dc_handle *h, int nsteps, void *stream,
+                          void (*enqueue)(dc_handle *, void *));
+static const char *dcb_comm_error();
+
 #include "dc_api_impl.h"
+
+// ---------------------------------------------------------------------------------------
+// NCCL, loaded on first use: a single-GPU process never touches it, and a process that has
+// torch.distributed loaded gets the very same libnccl.so.2 (same SONAME).  Only the eight entry
+// points below are used; their prototypes follow nccl.h (2.x ABI).
+// ---------------------------------------------------------------------------------------
+#include <dlfcn.h>
+namespace dc {
+struct NcclUniqueId { char internal[128]; };
+typedef void *NcclComm;
+struct NcclApi {
+    void *lib = nullptr;
+    int (*GetUniqueId)(NcclUniqueId *) = nullptr;
+    int (*CommInitRank)(NcclComm *, int, NcclUniqueId, int) = nullptr;
+    int (*CommDestroy)(NcclComm) = nullptr;
+    int (*Send)(const void *, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+    int (*Recv)(void *, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+constexpr int NCCL_FLOAT64 = 8;   // ncclDataType_t::ncclFloat64
+static thread_local std::string g_comm_error;
+static NcclApi *nccl_api()
+{
+    static NcclApi api;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) {
+            g_comm_error = std::string("cannot load libnccl.so.2: ") + dlerror();
+            return nullptr;
+        }
+        api.lib = lib;
+#define DC_NCCL_SYM(field, name) \
+        *reinterpret_cast<void **>(&api.field) = dlsym(lib, name); \
+        if (!api.field) { g_comm_error = std::string("libnccl: missing symbol ") + name; api.lib = nullptr; }
+        DC_NCCL_SYM(GetUniqueId, "ncclGetUniqueId")
+        DC_NCCL_SYM(CommInitRank, "ncclCommInitRank")
+        DC_NCCL_SYM(CommDestroy, "ncclCommDestroy")
+        DC_NCCL_SYM(Send, "ncclSend")
+        DC_NCCL_SYM(Recv, "ncclRecv")
+        DC_NCCL_SYM(GroupStart, "ncclGroupStart")
+        DC_NCCL_SYM(GroupEnd, "ncclGroupEnd")
+        DC_NCCL_SYM(GetErrorString, "ncclGetErrorString")
+#undef DC_NCCL_SYM
+    }
+    return api.lib ? &api : nullptr;
+}
+struct CommState {
+    NcclComm comm = nullptr;
+    int rank = 0, nranks = 1;
+    size_t nelem = 0;
+    double *buf[4] = {nullptr, nullptr, nullptr, nullptr};   // send_s, recv_s, send_n, recv_n
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev[8] = {};
+    cudaGraphExec_t graph = nullptr;
+    long long graph_version = -1;
+    long long launches_per_step = 0;
+    bool warmed = false;   // one plain step has run (NCCL connections, kernel attributes)
+    int error = 0;
+};
+}  // namespace dc
+static const char *dcb_comm_error() { return dc::g_comm_error.c_str(); }
+static int nccl_fail(const char *what, int code)
+{
+    dc::NcclApi *a = dc::nccl_api();
+    dc::g_comm_error = std::string(what) + ": " +
+                       (a && a->GetErrorString ? a->GetErrorString(code) : "NCCL error");
+    return code > 0 ? code : 1;
+}
+static int dcb_comm_unique_id(void *id128)
+{
+    dc::g_comm_error.clear();
+    dc::NcclApi *a = dc::nccl_api();
+    if (!a) return DC_ERR_NO_DEVICE;
+    dc::NcclUniqueId id;
+    const int e = a->GetUniqueId(&id);
+    if (e) return nccl_fail("ncclGetUniqueId", e);
+    memcpy(id128, &id, sizeof id);
+    return 0;
+}
+static int dcb_comm_init(dc_handle *h, const void *id128, int rank, int nranks, size_t halo_elems)
+{
+    dc::g_comm_error.clear();
+    dc::NcclApi *a = dc::nccl_api();
+    if (!a) return DC_ERR_NO_DEVICE;
+    dc::CommState *c = new dc::CommState();
+    c->rank = rank;
+    c->nranks = nranks;
+    c->nelem = halo_elems;
+    dc::NcclUniqueId id;
+    memcpy(&id, id128, sizeof id);
+    int e = a->CommInitRank(&c->comm, nranks, id, rank);
+    if (e) {
+        delete c;
+        return nccl_fail("ncclCommInitRank", e);
+    }
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);   // hi = numerically lowest = highest priority
+    cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, hi);
+    for (auto &ev : c->ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    for (int n = 0; n < 4; n++) {
+        const bool present = (n < 2) ? rank > 0 : rank < nranks - 1;
+        if (present && cudaMalloc(&c->buf[n], halo_elems * sizeof(double)) != cudaSuccess) {
+            dc::g_comm_error = "cudaMalloc of the halo buffers failed";
+            h->comm_state = c;
+            dcb_comm_release(h);
+            return (int)cudaErrorMemoryAllocation;
+        }
+    }
+    h->comm_state = c;
+    return 0;
+}
+static void dcb_comm_release(dc_handle *h)
+{
+    dc::CommState *c = static_cast<dc::CommState *>(h->comm_state);
+    if (!c) return;
+    cudaDeviceSynchronize();
+    if (c->graph) cudaGraphExecDestroy(c->graph);
+    for (double *b : c->buf)
+        if (b) cudaFree(b);
+    for (auto &ev : c->ev)
+        if (ev) cudaEventDestroy(ev);
+    if (c->side) cudaStreamDestroy(c->side);
+    dc::NcclApi *a = dc::nccl_api();
+    if (a && c->comm) a->CommDestroy(c->comm);
+    delete c;
+    h->comm_state = nullptr;
+}
+static double *dcb_comm_buffer(dc_handle *h, int which)
+{
+    return static_cast<dc::CommState *>(h->comm_state)->buf[which];
+}
+static int dcb_comm_sendrecv(dc_handle *h, void *stream)
+{
+    dc::CommState *c = static_cast<dc::CommState *>(h->comm_state);
+    dc::NcclApi *a = dc::nccl_api();
+    cudaStream_t st = (cudaStream_t)stream;
+    int e = a->GroupStart();
+    if (!e && c->rank > 0) {
+        e = a->Send(c->buf[0], c->nelem, dc::NCCL_FLOAT64, c->rank - 1, c->comm, st);
+        if (!e) e = a->Recv(c->buf[1], c->nelem, dc::NCCL_FLOAT64, c->rank - 1, c->comm, st);
+    }
+    if (!e && c->rank < c->nranks - 1) {
+        e = a->Send(c->buf[2], c->nelem, dc::NCCL_FLOAT64, c->rank + 1, c->comm, st);
+        if (!e) e = a->Recv(c->buf[3], c->nelem, dc::NCCL_FLOAT64, c->rank + 1, c->comm, st);
+    }
+    const int e2 = a->GroupEnd();
+    if (e || e2) {
+        c->error = e ? e : e2;
+        return nccl_fail("ncclSend/ncclRecv", c->error);
+    }
+    h->launches++;
+    return 0;
+}
+static void *dcb_side_stream(dc_handle *h)
+{
+    return static_cast<dc::CommState *>(h->comm_state)->side;
+}
+static void dcb_event_record(dc_handle *h, int ev, void *stream)
+{
+    cudaEventRecord(static_cast<dc::CommState *>(h->comm_state)->ev[ev], (cudaStream_t)stream);
+}
+static void dcb_stream_wait(dc_handle *h, int ev, void *stream)
+{
+    cudaStreamWaitEvent((cudaStream_t)stream, static_cast<dc::CommState *>(h->comm_state)->ev[ev], 0);
+}
+// One banded step captured into a CUDA graph (stream capture of `enqueue`, which forks to the
+// side stream and joins again through events) and replayed: one cudaGraphLaunch per step
+// instead of ~16 kernel launches, 6 event operations and 2 NCCL groups.
+static int dcb_graph_step(dc_handle *h, int nsteps, void *stream,
+                          void (*enqueue)(dc_handle *, void *))
+{
+    dc::CommState *c = static_cast<dc::CommState *>(h->comm_state);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!c->warmed) {   // lazy NCCL connection set-up and cudaFuncSetAttribute must not be captured
+        c->warmed = true;
+        return 1;
+    }
+    if (!c->graph || c->graph_version != h->bind_version) {
+        if (c->graph) {
+            cudaGraphExecDestroy(c->graph);
+            c->graph = nullptr;
+        }
+        cudaGraph_t g = nullptr;
+        const long long launches0 = h->launches;
+        if (cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+            cudaGetLastError();
+            return 1;
+        }
+        enqueue(h, stream);
+        const cudaError_t e = cudaStreamEndCapture(st, &g);
+        c->launches_per_step = h->launches - launches0;
+        h->launches = launches0;
+        if (e != cudaSuccess || !g) {
+            cudaGetLastError();
+            return 1;
+        }
+        if (cudaGraphInstantiate(&c->graph, g, 0) != cudaSuccess) {
+            cudaGraphDestroy(g);
+            cudaGetLastError();
+            c->graph = nullptr;
+            return 1;
+        }
+        cudaGraphDestroy(g);
+        c->graph_version = h->bind_version;
+        c->error = 0;
+    }
+    for (int s = 0; s < nsteps; s++) {
+        if (cudaGraphLaunch(c->graph, st) != cudaSuccess) return 1;
+        h->launches += c->launches_per_step;
+    }
+    return 0;
+}
 
 static dc::ProfileState *pstate(dc_handle *h)
 {

@@ -99,14 +99,42 @@ class BandCommunicator:
         _lib.check(L.dc_stage_diag(h, stage, stream))
 
 
-def attach_communicator(GR, F, group=None):
-    """make step_matsuno(GR, F) run the banded step (call once after dist.init_process_group)"""
+def attach_communicator(GR, F, group=None, in_library=None):
+    """make step_matsuno(GR, F) run the banded step (call once after dist.init_process_group).
+
+    On CUDA the library gets its OWN NCCL communicator (dc_set_comm): rank 0 draws the unique
+    id (dc_comm_unique_id), torch.distributed broadcasts its 128 bytes, every rank joins.  The
+    banded step is then ONE C call per step_matsuno (dc_step_matsuno: exchange, overlap and
+    CUDA-graph replay inside the library).  `in_library=False` (or the host emulation, which
+    has no NCCL) keeps the exchange in Python: dc_halo_pack -> torch.distributed
+    batch_isend_irecv -> dc_halo_unpack, the piecewise band entries of include/dyncore.h."""
+    import os
     GR.comm = BandCommunicator(GR, F, group)
+    if in_library is None:
+        in_library = _lib.is_cuda() and os.environ.get('DC_BAND_IN_LIBRARY', '1') != '0'
+    GR.comm.in_library = False
+    if in_library:
+        L, h = _lib.lib(), GR.dyncore()
+        nbytes = _lib.DC_COMM_ID_BYTES
+        ident = torch.zeros(nbytes, dtype=torch.uint8)
+        if GR.band[0] == 0:
+            buf = (ctypes.c_ubyte * nbytes)()
+            _lib.check(L.dc_comm_unique_id(buf, nbytes))
+            ident = torch.tensor(list(buf), dtype=torch.uint8)
+        ident = ident.to(F.torch_device)
+        src = dist.get_global_rank(group, 0) if group is not None else 0
+        dist.broadcast(ident, src=src, group=group)
+        raw = bytes(ident.cpu().tolist())
+        _lib.check(L.dc_set_comm(h, raw, nbytes, GR.band[0], GR.band[1]))
+        GR.comm.in_library = True
     return GR.comm
 
 
 def step_matsuno_banded(GR, F, nsteps, stream):
     L, h, comm = _lib.lib(), GR.dyncore(), GR.comm
+    if getattr(comm, 'in_library', False):
+        _lib.check(L.dc_step_matsuno(h, int(nsteps), stream))
+        return
     for _ in range(int(nsteps)):
         _lib.check(L.dc_step_begin(h, stream))
         for stage in (0, 1):

@@ -187,6 +187,27 @@ int dc_halo_pack(dc_handle *h, int stage, void *send_south, void *send_north, vo
 int dc_halo_unpack(dc_handle *h, int stage, const void *recv_south, const void *recv_north,
                    void *stream);
 
+/* ---- in-library halo exchange (dc_set_comm / dc_halo_exchange) -----------
+ * The library owns an NCCL communicator over the ranks of the band decomposition (libnccl.so.2
+ * is loaded on first use; a single-GPU process never needs it).  Rank 0 obtains a unique id
+ * with dc_comm_unique_id, the caller distributes its DC_COMM_ID_BYTES bytes to every rank by
+ * any means (torch.distributed.broadcast in parallel_bands.py) and every rank calls
+ * dc_set_comm -- a collective call.  With a communicator attached
+ *   - dc_halo_exchange(h, stage, stream) = pack -> grouped ncclSend/ncclRecv with the south
+ *     and north neighbours -> unpack, all enqueued on `stream`;
+ *   - dc_step_matsuno works on a band: per stage, continuity -> the boundary tile rows, the
+ *     packing and the NCCL exchange on an internal high-priority stream while the interior
+ *     tile rows run on `stream` -> COLP <- COLP_NEW -> diagnostics of the rows that do not
+ *     depend on the neighbours WHILE the halo is in flight -> unpack -> diagnostics of the
+ *     halo rows.  No host round trip, no Python between the stages.  After the first step
+ *     the sequence of one step is replayed from a CUDA graph (DC_BAND_GRAPH=0 disables).
+ * The result is bitwise identical to the single-device run. */
+#define DC_COMM_ID_BYTES 128
+int dc_comm_unique_id(void *id, size_t nbytes);
+int dc_set_comm(dc_handle *h, const void *id, size_t nbytes, int rank, int nranks);
+int dc_has_comm(const dc_handle *h);
+int dc_halo_exchange(dc_handle *h, int stage, void *stream);
+
 /* ---- layout conversion on the device (F.copy_host_to_device / copy_device_to_host,
  *      main_fields.py:204-215): `ref` is a DEVICE buffer holding the field in the
  *      reference layout (fnx, fny, nk) with k fastest, i.e. a raw byte copy of the host

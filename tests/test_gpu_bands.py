@@ -18,8 +18,12 @@ def _ngpus():
     return torch.cuda.device_count() if torch.cuda.is_available() else 0
 
 
+@pytest.mark.parametrize('path', ['library', 'python'])
 @pytest.mark.parametrize('world', [2, 4, 8])
-def test_nccl_banded_run_equals_single_gpu_bitwise(tmp_path, world):
+def test_nccl_banded_run_equals_single_gpu_bitwise(tmp_path, world, path):
+    """path = 'library': the exchange, its overlap and the CUDA-graph replay run inside
+    libdyncore (dc_set_comm + dc_step_matsuno on a band); 'python': dc_halo_pack -> torch
+    NCCL send/recv -> dc_halo_unpack through the piecewise band entries"""
     if _ngpus() < world:
         pytest.skip('needs %d GPUs' % world)
     from climate_model_b200 import _lib
@@ -34,10 +38,11 @@ def test_nccl_banded_run_equals_single_gpu_bitwise(tmp_path, world):
     step_matsuno(GR, F, nsteps)
     F.copy_device_to_host(GR, F.ALL_FIELDS)
     ref = {n: F.host[n].copy() for n in STATE + ['PHI', 'WWIND']}
-    env = dict(os.environ, MASTER_ADDR='127.0.0.1', BAND_BACKEND='nccl')
+    env = dict(os.environ, MASTER_ADDR='127.0.0.1', BAND_BACKEND='nccl',
+               DC_BAND_IN_LIBRARY='1' if path == 'library' else '0')
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1',
            '--nproc-per-node=%d' % world, '--master-addr', '127.0.0.1', '--master-port',
-           str(29700 + world), os.path.join(HERE, 'band_worker.py'), fixture, str(nsteps),
+           str(29700 + world + (10 if path == 'python' else 0)), os.path.join(HERE, 'band_worker.py'), fixture, str(nsteps),
            str(tmp_path), str(moist)]
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]

@@ -6,6 +6,6 @@ mkdir -p gpurun_out
 : > gpurun_out/kbench_batch.log
 for so in build/variants/*.so; do
     for rep in 1 2; do
-        timeout 120 python tools/kbench.py --lib "$so" "$@" 2>&1 | tail -1 | tee -a gpurun_out/kbench_batch.log
+        timeout 120 python tools/kbench.py --lib "$so" "$@" 2>&1 | tail -3 | tee -a gpurun_out/kbench_batch.log
     done
 done
