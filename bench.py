@@ -406,7 +406,8 @@ def main():
 
     GR = Grid(band=(rank, world), i_moist_main_switch=int(moist),
               i_coupling=int(args.turbulence), **wl['grid'])
-    F = ModelFields(GR, **wl['ic'])
+    # latitude bands: host arrays and the initial-state builder cover the rank's rows only
+    F = ModelFields(GR, band_local=world > 1, **wl['ic'])
     if args.turbulence:
         from climate_model_b200.turb_main import Turbulence
         F.TURB = Turbulence(GR, target=B200)
@@ -508,57 +509,22 @@ def main():
                 'device -> host state')
     e2e_extra = {}
     if world > 1:
-        # Latitude bands: the sequence above moves the WHOLE grid's arrays on every rank.  A rank
-        # only needs the rows it holds: band-shaped pinned buffers (ModelFields.to_device_band /
-        # to_host_band).  A pre-flight without collectives runs first and all ranks agree on its
-        # outcome, so that no rank can enter the collective step alone; on any failure the
-        # whole-grid number above stands.
-        pre_ok, band_bytes, bufs = 1, 0, {}
-        try:
-            for n in names:
-                bufs[n] = F.band_buffer(GR, n)
-                F.to_host_band(GR, n, bufs[n])
-                F.to_device_band(GR, n, bufs[n])
-                band_bytes += bufs[n].numel() * 8
-            torch.cuda.synchronize()
-        except Exception as exc:                                  # noqa: BLE001
-            pre_ok = 0
-            print('band-shaped e2e pre-flight failed on rank %d: %r' % (rank, exc), file=sys.stderr)
-        t = torch.tensor([pre_ok, -pre_ok], device=F.torch_device, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MIN)
-        if int(t[0].item()) == 1:
-            t_band = []
-            for _ in range(args.e2e_steps):
-                barrier()
-                t0 = time.perf_counter()
-                for n in names:
-                    F.to_device_band(GR, n, bufs[n])
-                Diagnostics.primary_diag(GR.GRF[B200],
-                                         **F.get(Diagnostics.fields_primary_diag, target=B200))
-                one_step()
-                for n in names:
-                    F.to_host_band(GR, n, bufs[n])
-                barrier()
-                t_band.append(time.perf_counter() - t0)
-            t = torch.tensor([sum(t_band) / len(t_band)], device=F.torch_device,
-                             dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            b = torch.tensor([float(band_bytes)], device=F.torch_device, dtype=torch.float64)
-            dist.all_reduce(b, op=dist.ReduceOp.SUM)
-            # owned rows, interior columns of the mass field (halo cells may hold the NaN the
-            # reference leaves in cells nothing reads)
-            ja = F.held_rows(GR, 'POTT')[0]
-            own = bufs['POTT'][1:int(GR.nx) + 1, int(GR.j0) - ja:int(GR.j1) - ja + 1]
-            fin = torch.tensor([float(bool(torch.isfinite(own).all()))],
-                               device=F.torch_device, dtype=torch.float64)
-            dist.all_reduce(fin, op=dist.ReduceOp.MIN)
-            if fin.item() == 1.0:
-                e2e_extra = {'whole_grid_arrays_on_every_rank_ms': e2e_sec * 1e3, 'finite': True}
-                e2e_sec = float(t.item())
-                h2d = int(b.item())
-                e2e_what = ('every rank: pinned band-shaped host state (its rows + 2 halo rows a '
-                            'side) -> device, layout transpose, primary_diag, 1 banded Matsuno '
-                            'step (NCCL halos), transpose, device -> host; bytes summed over ranks')
+        # latitude bands: every rank's host arrays hold only the rows it holds
+        # (ModelFields(band_local=True)), so the sequence above moved band rows only; the bytes
+        # are summed over the ranks
+        b = torch.tensor([float(h2d)], device=F.torch_device, dtype=torch.float64)
+        dist.all_reduce(b, op=dist.ReduceOp.SUM)
+        h2d = int(b.item())
+        e2e_what = ('every rank: pinned band-shaped host state (its rows + 2 halo rows a side) -> '
+                    'device (+layout transpose), primary_diag, 1 banded Matsuno step (NCCL halos '
+                    'inside the library), device -> host; bytes summed over ranks, mean of the '
+                    'slowest rank')
+        ja = F._rows_of(GR)('POTT')[0]
+        own = F.host['POTT'][1:int(GR.nx) + 1, int(GR.j0) - ja:int(GR.j1) - ja + 1]
+        fin = torch.tensor([float(bool(np.isfinite(own).all()))], device=F.torch_device,
+                           dtype=torch.float64)
+        dist.all_reduce(fin, op=dist.ReduceOp.MIN)
+        e2e_extra = {'finite': fin.item() == 1.0}
     if world == 1 and args.e2e_members > 0:
         # host-resident states (ensemble members) streamed through the device: every member's
         # upload, step and download are inside the timed region; the upload of member m+1 and

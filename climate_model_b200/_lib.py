@@ -82,6 +82,10 @@ def _declare(lib):
     lib.dc_run_diag.argtypes = [vp, vp, ctypes.c_size_t, vp]
     lib.dc_import_field.argtypes = [vp, ctypes.c_int, vp, ctypes.c_size_t, vp]
     lib.dc_export_field.argtypes = [vp, ctypes.c_int, vp, ctypes.c_size_t, vp]
+    lib.dc_import_rows.argtypes = [vp, ctypes.c_int, vp, ctypes.c_size_t, ctypes.c_int,
+                                   ctypes.c_int, vp]
+    lib.dc_export_rows.argtypes = [vp, ctypes.c_int, vp, ctypes.c_size_t, ctypes.c_int,
+                                   ctypes.c_int, vp]
     lib.dc_profile_enable.argtypes = [vp, ctypes.c_int]
     lib.dc_profile_read.argtypes = [vp, ctypes.c_int, ctypes.POINTER(ctypes.c_char_p),
                                     ctypes.POINTER(ctypes.c_double),

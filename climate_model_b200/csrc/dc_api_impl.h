@@ -449,12 +449,16 @@ static void do_xhalo_fix(dc_handle *h, void *stream)
     launch(h, "xhalo_fix", XHaloFixBody{g, h->f.UWIND}, 0, g.nz - 1, lo, hi, stream);
 }
 
-// primary diagnostics of the state a stage produced, on the held rows [lo, hi]
-static void do_diag_rows(dc_handle *h, int stage, int lo, int hi, void *stream)
+// primary diagnostics of the state a stage produced, on the held rows [lo, hi] without the
+// rows [gap_lo, gap_hi] (gap_hi < gap_lo: no gap)
+static void do_diag_rows(dc_handle *h, int stage, int lo, int hi, void *stream, int gap_lo = 0,
+                         int gap_hi = -1)
 {
     const Fields &f = h->f;
     const Geom &g = h->g;
-    if (hi < lo) return;
+    const int gap = gap_hi >= gap_lo ? gap_hi - gap_lo + 1 : 0;
+    const int nrows = hi - lo + 1 - gap;
+    if (nrows <= 0) return;
     // the stage kernel reads PHI, POTTVB and PGCOL only: PVTF, PVTFVB and PHIVB are not
     // stored between stages (dc_primary_diag refreshes them on demand)
     const double *T = stage == 0 ? f.POTT_OLD : f.POTT;
@@ -462,13 +466,15 @@ static void do_diag_rows(dc_handle *h, int stage, int lo, int hi, void *stream)
         PrimaryDiagBody<1> b{g,     f.COLP,  T,        f.HSURF, f.PVTF, f.PVTFVB,
                              f.PHI, f.PHIVB, f.POTTVB, f.PGCOL, lo,     hi,
                              make_pow_coef(con_kappa, g.powtab)};
-        launch(h, "primary_diag", b, 0, g.nx + 1, 0, (hi - lo) / b.NC, stream);
+        if (gap) { b.j_split = gap_lo; b.j_skip = gap; }
+        launch(h, "primary_diag", b, 0, g.nx + 1, 0, nrows - 1, stream);
         h->diag_partial = 1;
     } else {
         PrimaryDiagBody<2> b{g,     f.COLP,  T,        f.HSURF, f.PVTF, f.PVTFVB,
                              f.PHI, f.PHIVB, f.POTTVB, f.PGCOL, lo,     hi,
                              make_pow_coef(con_kappa, g.powtab)};
-        launch(h, "primary_diag", b, 0, g.nx + 1, 0, (hi - lo) / b.NC, stream);
+        if (gap) { b.j_split = gap_lo; b.j_skip = gap; }
+        launch(h, "primary_diag", b, 0, g.nx + 1, 0, nrows - 1, stream);
     }
 }
 
@@ -738,8 +744,9 @@ static void held_rows(const Geom &g, int fny, int *j_lo, int *j_hi)
     *j_hi = g.j1 + HJ + 1 > fny - 1 ? fny - 1 : g.j1 + HJ + 1;
 }
 
+// ref: reference-layout rows ja..jb (whole field: ja = 0, jb = fny - 1)
 static int do_transpose(dc_handle *h, int id, void *ref, size_t nbytes, int to_device,
-                        void *stream, const char *what)
+                        void *stream, const char *what, int ja = 0, int jb = -1)
 {
     if (!h || !ref) return fail(DC_ERR_ARG, "%s: NULL argument", what);
     if (id < 0 || id >= F_COUNT) return fail(DC_ERR_ARG, "%s: bad field id %d", what, id);
@@ -748,15 +755,23 @@ static int do_transpose(dc_handle *h, int id, void *ref, size_t nbytes, int to_d
     const Geom &g = h->g;
     const FieldInfo &fi = g_field_info[id];
     const int fnx = g.nx + 2 + fi.stgx, fny = g.ny + 2 + fi.stgy, nk = nk_of(g, id);
-    const size_t need_bytes = (size_t)fnx * fny * nk * sizeof(double);
+    if (jb < 0) jb = fny - 1;
+    if (ja < 0 || jb >= fny || jb < ja)
+        return fail(DC_ERR_ARG, "%s: bad row window [%d, %d] of %s (%d rows)", what, ja, jb,
+                    fi.name, fny);
+    const int nrows = jb - ja + 1;
+    const size_t need_bytes = (size_t)fnx * nrows * nk * sizeof(double);
     if (nbytes < need_bytes)
         return fail(DC_ERR_SHAPE, "%s: %s needs a %zu-byte reference-layout buffer, got %zu",
                     what, fi.name, need_bytes, nbytes);
     int j_lo, j_hi;
     held_rows(g, fny, &j_lo, &j_hi);
+    if (j_lo < ja) j_lo = ja;
+    if (j_hi > jb) j_hi = jb;
     if (h->profiling) dcb_profile_begin(h, to_device ? "import_field" : "export_field", stream);
-    dcb_transpose(g, static_cast<double *>(ref), *h->slot(id), fnx, fny, nk, j_lo, j_hi,
-                  to_device, stream);
+    // the kernel addresses ref[(i * rows + j) * nk + k] with the GLOBAL row j: shift the base
+    dcb_transpose(g, static_cast<double *>(ref) - (size_t)ja * nk, *h->slot(id), fnx, nrows, nk,
+                  j_lo, j_hi, to_device, stream);
     if (h->profiling) dcb_profile_end(h, stream);
     h->launches++;
     return backend_status(what);
@@ -776,6 +791,22 @@ int dc_export_field(dc_handle *h, int id, void *ref, size_t nbytes, void *stream
         if (rc) return rc;
     }
     return do_transpose(h, id, ref, nbytes, 0, stream, "dc_export_field");
+}
+
+int dc_import_rows(dc_handle *h, int id, const void *ref, size_t nbytes, int ja, int jb,
+                   void *stream)
+{
+    return do_transpose(h, id, const_cast<void *>(ref), nbytes, 1, stream, "dc_import_rows", ja,
+                        jb);
+}
+
+int dc_export_rows(dc_handle *h, int id, void *ref, size_t nbytes, int ja, int jb, void *stream)
+{
+    if (h && (id == F_PVTF || id == F_PVTFVB || id == F_PHIVB)) {
+        const int rc = refresh_diag(h, "dc_export_rows", stream);
+        if (rc) return rc;
+    }
+    return do_transpose(h, id, ref, nbytes, 0, stream, "dc_export_rows", ja, jb);
 }
 
 #define DC_ENTRY_CHECK(name)                                                     \
@@ -1107,17 +1138,21 @@ int dc_halo_exchange(dc_handle *h, int stage, void *stream)
                      north ? dcb_comm_buffer(h, 3) : nullptr, 0, stream, "dc_halo_exchange");
 }
 
-enum { EV_CONT = 0, EV_BDONE = 1, EV_RECV = 2, EV_COUNT = 3 };
+enum { EV_CONT = 0, EV_BDONE = 1, EV_RECV = 2, EV_UNPACK = 3, EV_JOIN = 4, EV_COUNT = 5 };
 
 // One Matsuno step on a latitude band with the exchange inside the library (stream M = the
 // caller's, S = the handle's high-priority side stream).  Per stage:
-//   M: continuity (rows j0-1 .. j1+1)                          S: waits for it, then
-//   M: stage kernel on the interior tile rows                  S: stage kernel on the first and
-//                                                                 last tile row, pack, NCCL
-//   M: COLP <- COLP_NEW (after both stage-kernel launches)        send/recv with both neighbours
-//   M: diagnostics of the rows that need no neighbour data  -- the halo is in flight meanwhile
-//   M: waits for the receive, unpack, diagnostics of the halo rows
-// so that the exchange hides behind the interior tile rows AND the diagnostics sweep.
+//   M: continuity (rows j0-1 .. j1+1)          S: diagnostics of the HALO rows of the previous
+//                                                 stage (needs its unpack only), then waits for
+//                                                 the continuity
+//   M: stage kernel, interior tile rows        S: stage kernel on the first and last tile row,
+//                                                 pack, NCCL send/recv with both neighbours
+//   M: COLP <- COLP_NEW (after both stage-kernel launches)
+//   M: diagnostics of the rows that need no neighbour data -- the halo is in flight meanwhile
+//   M: waits for the receive, unpack
+// so the exchange hides behind the interior tile rows and the own-row diagnostics, and the
+// halo-row diagnostics (a launch as long as one thread's march up the column) behind the next
+// continuity.  Every kernel of a band is short: what is serial on M is what the step costs.
 static void enqueue_band_step(dc_handle *h, void *M)
 {
     const Fields &f = h->f;
@@ -1130,7 +1165,7 @@ static void enqueue_band_step(dc_handle *h, void *M)
     for (int stage = 0; stage < 2; stage++) {
         do_stage_fused(h, stage, DC_PART_CONT, M);
         dcb_event_record(h, EV_CONT, M);
-        dcb_stream_wait(h, EV_CONT, S);
+        dcb_stream_wait(h, EV_CONT, S);              // S: after the halo diagnostics, if any
         do_stage_fused(h, stage, DC_PART_BOUNDARY, S);
         dcb_event_record(h, EV_BDONE, S);
         halo_move(h, stage, south ? dcb_comm_buffer(h, 0) : nullptr,
@@ -1144,9 +1179,13 @@ static void enqueue_band_step(dc_handle *h, void *M)
         dcb_stream_wait(h, EV_RECV, M);
         halo_move(h, stage, south ? dcb_comm_buffer(h, 1) : nullptr,
                   north ? dcb_comm_buffer(h, 3) : nullptr, 0, M, "dc_step_matsuno");
-        if (south) do_diag_rows(h, stage, lo, g.j0 - 1, M);
-        if (north) do_diag_rows(h, stage, g.j1 + 1, hi, M);
+        // halo rows [lo, own_lo) and (own_hi, hi] in ONE launch on S, beside the next continuity
+        dcb_event_record(h, EV_UNPACK, M);
+        dcb_stream_wait(h, EV_UNPACK, S);
+        do_diag_rows(h, stage, lo, hi, S, own_lo, own_hi);
     }
+    dcb_event_record(h, EV_JOIN, S);                 // the step ends when both streams have
+    dcb_stream_wait(h, EV_JOIN, M);
 }
 
 static int step_matsuno_banded(dc_handle *h, int nsteps, void *stream)

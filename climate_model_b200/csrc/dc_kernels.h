@@ -808,12 +808,15 @@ struct PrimaryDiagBody {
     static constexpr int NC = 1;
     int j_lo, j_hi;
     PowCoef pc;
+    // rows from j_split on are shifted by j_skip: [j_lo, j_split) and [j_split + j_skip, j_hi]
+    int j_split = 1 << 30, j_skip = 0;
     DC_HD void operator()(int i, int jj) const
     {
         constexpr bool PV = MODE != 1, PHB = MODE == 0, PG = MODE != 2;
         const int nz = g.nz;
         const size_t plane = g.plane;
-        const int j0 = j_lo + NC * jj;
+        int j0 = j_lo + NC * jj;
+        if (j0 >= j_split) j0 += j_skip;   // two row ranges in one launch (halo rows of a band)
         const int nc = (j0 + NC - 1 <= j_hi) ? NC : j_hi - j0 + 1;   // ragged last thread row
         double colp[NC], p_kp12[NC], pw_kp12[NC], phivb[NC], pvtf_kp1[NC], pott_kp1[NC];
         size_t o[NC];   // one running offset per column serves every field

@@ -206,3 +206,163 @@ def initialize_fields(GR, host, **pert):
     host['QV'] = GR.exchange_BC(QV)
     host['PVTF'], host['PVTFVB'] = PVTF, PVTFVB
     return host
+
+
+# ---------------------------------------------------------------------------------------
+# band-local initial state (latitude-band runs, SURVEY.md 8e / BASELINE configs[4])
+# ---------------------------------------------------------------------------------------
+def _bc_window(GR, F, ja, jb, stgx, stgy):
+    """misc_boundaries.py:22-42 / main_grid.py:319-358 on a ROW WINDOW [ja, jb] (global rows) of
+    a reference-layout array: periodic images in x on every row, wall rows if the window holds
+    them"""
+    nx, ny, nys = int(GR.nx), int(GR.ny), int(GR.nys)
+    if stgx:
+        F[0] = F[nx]            # = nxs - 1
+        F[nx + 1] = F[1]        # = nxs        (index nxs + 1 stays unset, like the reference)
+    else:
+        F[0] = F[nx]
+        F[nx + 1] = F[1]
+    if stgy:
+        for j in (0, 1, nys, nys + 1):
+            if ja <= j <= jb:
+                F[:, j - ja] = 0.
+    else:
+        if ja <= 0 and jb >= 1:
+            F[:, 0 - ja] = F[:, 1 - ja]
+        if ja <= ny and jb >= ny + 1:
+            F[:, ny + 1 - ja] = F[:, ny - ja]
+    return F
+
+
+def initialize_fields_band(GR, host, rows_of, **pert):
+    """initialize_fields for ONE latitude band: `host[n]` holds the rows rows_of(n) = (ja, jb)
+    of field n only, shape (fnx, jb-ja+1, nk).  Everything 2-D (topography, its smoothing, the
+    surface pressure, COLP and its perturbations, the random-number draws) is built for the
+    whole grid -- a 2-D field is small at any resolution -- and every 3-D field directly on the
+    band's rows: at 0.1 deg x 96 levels a rank of an 8-GPU run builds 217 of 1682 rows
+    (0.6 GB per field instead of 4.6 GB).  Same expressions, element by element, as
+    initialize_fields (tests/test_ic_builder.py compares the two)."""
+    P = {k: getattr(nl, k) for k in (
+        'uwind_0', 'vwind_0', 'UWIND_gaussian_pert', 'UWIND_random_pert', 'VWIND_gaussian_pert',
+        'VWIND_random_pert', 'COLP_gaussian_pert', 'COLP_random_pert', 'POTT_gaussian_pert',
+        'POTT_random_pert', 'QV_gaussian_pert', 'QV_random_pert', 'gaussian_dlon',
+        'gaussian_dlat', 'i_use_topo')}
+    for k, v in pert.items():
+        if k not in P:
+            raise KeyError('unknown initial-condition parameter %r' % k)
+        P[k] = v
+    pair_top = wp(GR.pair_top)
+    nx, ny, nz, nzs, nb = int(GR.nx), int(GR.ny), int(GR.nz), int(GR.nzs), int(GR.nb)
+    ii, jj = GR.ii, GR.jj
+    np.random.seed(seed=3)
+    shape2 = (nx + 2 * nb, ny + 2 * nb, 1)
+    HSURF = np.full(shape2, np.nan, dtype=wp)
+    if P['i_use_topo']:
+        HSURF = load_topo(GR, HSURF)
+    else:
+        HSURF[:] = 0.
+    profile = _data()['profile']
+    PSURF = np.full_like(HSURF, np.nan)
+    PSURF[ii, jj, 0] = np.interp(HSURF[ii, jj, 0], profile[:, 0], profile[:, 2])
+    COLP0 = np.full_like(HSURF, np.nan)                     # before its perturbations
+    COLP0[ii, jj, 0] = PSURF[ii, jj, 0] - pair_top
+    g = (np.pi * 3 / 4, 0, P['gaussian_dlon'], P['gaussian_dlat'])
+    COLP = COLP0.copy()
+    COLP[:, :, 0] = _gaussian2D(GR, COLP[:, :, 0], P['COLP_gaussian_pert'], *g)
+    COLP[:, :, 0] = _random2D(COLP[:, :, 0], P['COLP_random_pert'])
+    COLP = GR.exchange_BC(COLP)
+    any_random = any(P[k] != 0 for k in ('UWIND_random_pert', 'VWIND_random_pert',
+                                         'POTT_random_pert', 'QV_random_pert'))
+
+    def window(n):
+        ja, jb = rows_of(n)
+        return ja, jb, max(1, ja), min(ny if n != 'VWIND' else ny + 1, jb)   # + interior rows
+
+    def pvt(colp_rows):
+        """_pvt_factor on rows: colp_rows (nx, rows) -> PVTF (nx, rows, nz), PVTFVB (.., nzs)"""
+        sig = np.asarray(GR.sigma_vb).reshape(-1)
+        PAIRVB = pair_top + sig[None, None, :] * colp_rows[:, :, None]
+        PVTFVB = np.power(PAIRVB / 100000., con_kappa)
+        PVTF = 1 / (1 + con_kappa) * (PVTFVB[:, :, 1:] * PAIRVB[:, :, 1:] -
+                                      PVTFVB[:, :, :-1] * PAIRVB[:, :, :-1]) / (
+            PAIRVB[:, :, 1:] - PAIRVB[:, :, :-1])
+        return PVTF, PVTFVB
+
+    def gauss(lon, lat, amp):
+        return amp * np.exp(- np.power(lon - g[0], 2) / (2 * g[2] ** 2)
+                            - np.power(lat - g[1], 2) / (2 * g[3] ** 2))
+
+    i = np.arange(nb, nx + nb)
+    i_s = np.arange(nb, nx + 1 + nb)
+    kfac = np.array([(1 - (k + 1) / nz) ** (1 / 2) for k in range(nz)])   # as the scalar loop
+    # random draws, in the order initialize_fields makes them (whole-grid 2-D arrays per
+    # level and field): only needed when a random perturbation is switched on
+    rnd = {}
+    if any_random:
+        for k in range(nz):
+            for n, shp in (('UWIND', (nx + 3, ny + 2)), ('VWIND', (nx + 2, ny + 3)),
+                           ('POTT', (nx + 2, ny + 2)), ('QV', (nx + 2, ny + 2))):
+                ja, jb = rows_of(n)
+                rnd[(n, k)] = np.random.rand(*shp)[:, ja:jb + 1]
+
+    # ---- mass fields: POTT, QV, QC, PVTF, PVTFVB -------------------------------------------
+    ja, jb, j0, j1 = window('POTT')
+    j = np.arange(j0, j1 + 1)
+    PVTF0, _ = pvt(COLP0[np.ix_(i, j)][:, :, 0])
+    PAIR = 100000. * np.power(PVTF0, 1 / con_kappa)
+    TAIR = interp1d(profile[:, 2], profile[:, 3])(PAIR)
+    POTT_in = TAIR * np.power(100000. / PAIR, con_kappa)
+    lon = GR.lon_rad[np.ix_(i, j)][:, :, 0]
+    lat = GR.lat_rad[np.ix_(i, j)][:, :, 0]
+    POTT_in = POTT_in + gauss(lon, lat, P['POTT_gaussian_pert'])[:, :, None]
+    POTT = np.full((nx + 2, jb - ja + 1, nz), np.nan, dtype=wp)
+    POTT[np.ix_(i, j - ja)] = POTT_in
+    if any_random:
+        for k in range(nz):
+            POTT[:, :, k] = POTT[:, :, k] + P['POTT_random_pert'] * rnd[('POTT', k)]
+    host['POTT'][...] = _bc_window(GR, POTT, ja, jb, 0, 0)
+    PVTF1, PVTFVB1 = pvt(COLP[np.ix_(i, j)][:, :, 0])
+    TAIR1 = POTT[np.ix_(i, j - ja)] * PVTF1
+    PAIR1 = 100000 * np.power(PVTF1, 1 / con_kappa)
+    QV = np.full_like(POTT, np.nan)
+    QV[np.ix_(i, j - ja)] = calc_specific_humidity(TAIR1, wp(60), PAIR1)
+    host['QV'][...] = _bc_window(GR, QV, ja, jb, 0, 0)
+    QC = np.full_like(POTT, np.nan)
+    QC[np.ix_(i, j - ja)] = 0.
+    host['QC'][...] = _bc_window(GR, QC, ja, jb, 0, 0)
+    for n, a in (('PVTF', PVTF1), ('PVTFVB', PVTFVB1)):
+        out = host[n]
+        out[...] = np.nan
+        out[np.ix_(i, j - ja)] = a
+    for n in ('COLP', 'HSURF'):
+        ja2, jb2 = rows_of(n)
+        host[n][...] = (COLP if n == 'COLP' else HSURF)[:, ja2:jb2 + 1]
+    host['POTTVB'][...] = 0.
+    host['WWIND'][...] = 0.
+
+    # ---- UWIND (x-staggered) -------------------------------------------------------------------
+    ja, jb, j0, j1 = window('UWIND')
+    j = np.arange(j0, j1 + 1)
+    lon = GR.lon_is_rad[np.ix_(i_s, j)][:, :, 0]
+    lat = GR.lat_is_rad[np.ix_(i_s, j)][:, :, 0]
+    base = P['uwind_0'] + gauss(lon, lat, P['UWIND_gaussian_pert'])
+    U = np.full((nx + 3, jb - ja + 1, nz), np.nan, dtype=wp)
+    U[np.ix_(i_s, j - ja)] = base[:, :, None] * kfac[None, None, :]
+    if any_random:
+        for k in range(nz):
+            U[:, :, k] = U[:, :, k] + P['UWIND_random_pert'] * rnd[('UWIND', k)]
+    host['UWIND'][...] = _bc_window(GR, U, ja, jb, 1, 0)
+
+    # ---- VWIND (y-staggered) -------------------------------------------------------------------
+    ja, jb, j0, j1 = window('VWIND')
+    j = np.arange(j0, j1 + 1)
+    lon = GR.lon_js_rad[np.ix_(i, j)][:, :, 0]
+    lat = GR.lat_js_rad[np.ix_(i, j)][:, :, 0]
+    base = P['vwind_0'] + gauss(lon, lat, P['VWIND_gaussian_pert'])
+    V = np.full((nx + 2, jb - ja + 1, nz), np.nan, dtype=wp)
+    V[np.ix_(i, j - ja)] = base[:, :, None] * kfac[None, None, :]
+    if any_random:
+        for k in range(nz):
+            V[:, :, k] = V[:, :, k] + P['VWIND_random_pert'] * rnd[('VWIND', k)]
+    host['VWIND'][...] = _bc_window(GR, V, ja, jb, 0, 1)
+    return host

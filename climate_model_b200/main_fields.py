@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .io_initial_conditions import initialize_fields
+from .io_initial_conditions import initialize_fields, initialize_fields_band
 from .io_read_namelist import CPU, wp
 
 # host-only fields the reference's factories name (stgx, stgy, dimz)
@@ -69,9 +69,17 @@ class ModelFields:
     NC_OUT_DIAG_FIELDS = 'nc_out_diag_fields'
     PROGNOSTIC_FIELDS = 'prognostic_fields'
 
-    def __init__(self, GR, gpu_enable=True, device=None, initialize=True, **ic_overrides):
+    def __init__(self, GR, gpu_enable=True, device=None, initialize=True, band_local=False,
+                 **ic_overrides):
+        """band_local=True (latitude-band runs): F.host[n] holds only the rows this rank holds
+        -- shape (fnx, held rows, nk), rows self.held_rows(GR, n) of the reference layout --
+        the initial state is built band by band (initialize_fields_band) and host <-> device
+        copies move those rows (dc_import_rows / dc_export_rows): nothing whole-grid sized in 3-D
+        is allocated on any rank.  Default: the reference's whole-grid host arrays."""
         self.gpu_enable = gpu_enable
-        self.host, self.fdict = allocate_fields(GR)
+        self.band_local = bool(band_local)
+        self._GR_ref = weakref.ref(GR)
+        self.host, self.fdict = allocate_fields(GR, self._rows_of(GR) if band_local else None)
         self.device = {}
         self.set_field_groups()
         if device is None:
@@ -79,7 +87,9 @@ class ModelFields:
         self.torch_device = torch.device(device)
         if gpu_enable and _lib.is_cuda() and self.torch_device.type != 'cuda':
             raise RuntimeError('libdyncore runs on CUDA devices only; there is no CPU fallback')
-        if initialize:
+        if initialize and self.band_local:
+            initialize_fields_band(GR, self.host, self._rows_of(GR), **ic_overrides)
+        elif initialize:
             initialize_fields(GR, self.host, **ic_overrides)
         self._bound = {}
         if gpu_enable:
@@ -150,11 +160,30 @@ class ModelFields:
             return torch.cuda.current_stream(self.torch_device).cuda_stream
         return 0
 
+    def _rows_of(self, GR):
+        """name -> (ja, jb): rows of the reference layout this rank holds (band + halo rows)"""
+        j0, j1, ny = int(GR.j0), int(GR.j1), int(GR.ny)
+        table = dict(_lib.field_table())
+        table.update({k: (None, v[0], v[1], v[2]) for k, v in _HOST_ONLY.items()})
+
+        def rows(n):
+            fny = ny + 2 + table[n][2]
+            return max(0, j0 - 2), min(j1 + 3, fny - 1)
+        return rows
+
     def to_device(self, GR, n):
         """host (i, j, k) -> device F[k][jd][i]: one contiguous H2D copy (asynchronous when the
         host array is pinned) + an on-device tiled transpose (dc_import_field)"""
         h = self.host[n]
         bind_all(GR, self)
+        if self.band_local:
+            ja, jb = self._rows_of(GR)(n)
+            src = torch.from_numpy(h).view(-1)
+            st = self._stage(src.numel())
+            st.copy_(src, non_blocking=True)
+            _lib.check(_lib.lib().dc_import_rows(GR.dyncore(), self.table[n][0], st.data_ptr(),
+                                                 st.numel() * 8, ja, jb, self._stream()))
+            return
         src = torch.from_numpy(h).view(-1)
         st = self._stage(src.numel())
         st.copy_(src, non_blocking=True)
@@ -166,6 +195,17 @@ class ModelFields:
         h = self.host[n]
         bind_all(GR, self)
         self._refresh_for_export(GR, n)
+        if self.band_local:
+            ja, jb = self._rows_of(GR)(n)
+            dst = torch.from_numpy(h).view(-1)
+            st = self._stage(dst.numel())
+            st.copy_(dst, non_blocking=True)     # rows outside the held range keep their values
+            _lib.check(_lib.lib().dc_export_rows(GR.dyncore(), self.table[n][0], st.data_ptr(),
+                                                 st.numel() * 8, ja, jb, self._stream()))
+            dst.copy_(st, non_blocking=True)
+            if self.torch_device.type == 'cuda':
+                torch.cuda.current_stream(self.torch_device).synchronize()
+            return
         dst = torch.from_numpy(h).view(-1)
         st = self._stage(dst.numel())
         if GR.band[1] > 1:
@@ -299,8 +339,9 @@ class _LazyHost(dict):
         return self._shapes.keys()
 
 
-def allocate_fields(GR):
-    """host arrays in the reference layout, NaN-filled (main_fields.py:218-487)"""
+def allocate_fields(GR, rows_of=None):
+    """host arrays in the reference layout, NaN-filled (main_fields.py:218-487); with
+    `rows_of` (name -> (ja, jb)) only that row window of every field"""
     fdict, shapes = {}, {}
     nzmap = {'nz': int(GR.nz), 'nzs': int(GR.nzs), 1: 1}
     table = {}
@@ -309,7 +350,11 @@ def allocate_fields(GR):
     table.update(_HOST_ONLY)
     for n, (sx, sy, dz) in table.items():
         fdict[n] = {'stgx': sx, 'stgy': sy, 'dimz': nzmap[dz], 'dtype': wp}
-        shapes[n] = (int(GR.nx) + 2 + sx, int(GR.ny) + 2 + sy, nzmap[dz])
+        fny = int(GR.ny) + 2 + sy
+        if rows_of is not None:
+            ja, jb = rows_of(n)
+            fny = jb - ja + 1
+        shapes[n] = (int(GR.nx) + 2 + sx, fny, nzmap[dz])
     # the physics coupling inputs are zero until a physics module (or the caller) fills them
     # (the reference zeroes them when its modules are off)
     return _LazyHost(shapes, pin=_lib.is_cuda() and torch.cuda.is_available(),

@@ -215,6 +215,15 @@ int dc_halo_exchange(dc_handle *h, int stage, void *stream);
  *      does the reverse.  nbytes = size of `ref`. ---- */
 int dc_import_field(dc_handle *h, int field_id, const void *ref, size_t nbytes, void *stream);
 int dc_export_field(dc_handle *h, int field_id, void *ref, size_t nbytes, void *stream);
+/* The same for a ROW WINDOW of the reference layout: `ref` holds rows ja..jb only, shape
+ * (fnx, jb-ja+1, nk) with k fastest.  A rank of a latitude-band run keeps just the rows it
+ * holds on the host (ModelFields(band_local=True)): nothing whole-grid sized is ever
+ * allocated, on the host or on the device.  Rows of the window this rank does not hold are
+ * left untouched. */
+int dc_import_rows(dc_handle *h, int field_id, const void *ref, size_t nbytes, int ja, int jb,
+                   void *stream);
+int dc_export_rows(dc_handle *h, int field_id, void *ref, size_t nbytes, int ja, int jb,
+                   void *stream);
 
 /* number of kernel launches this handle has enqueued so far (bench.py: gpu_launches) */
 long long dc_launch_count(const dc_handle *h);

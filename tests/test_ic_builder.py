@@ -57,3 +57,56 @@ def test_initial_state_matches_reference(fixture):
         scale = max(np.max(np.abs(b[m])), 1e-300)
         assert np.max(np.abs(a[m] - b[m])) / scale <= 1e-13, '%s: %g' % (
             n, np.max(np.abs(a[m] - b[m])) / scale)
+
+
+@pytest.mark.parametrize('kw', [dict(), dict(i_use_topo=0),
+                                dict(UWIND_random_pert=2.0, VWIND_random_pert=2.0,
+                                     POTT_random_pert=1.0, COLP_random_pert=100.,
+                                     POTT_gaussian_pert=3.0, COLP_gaussian_pert=500.)])
+def test_band_local_builder_equals_whole_grid_builder(kw):
+    """ModelFields(band_local=True) builds, on every rank, only the rows the rank holds
+    (io_initial_conditions.initialize_fields_band): bit-identical to the same rows of the
+    whole-grid builder, for 1 and for 3 latitude bands (host side only, no stepping)"""
+    from helpers import build_emu
+    from climate_model_b200 import _lib
+    from climate_model_b200.main_fields import ModelFields
+    from climate_model_b200.main_grid import Grid
+    _lib.use_library(build_emu())
+    grid = dict(nz=10, lat0_deg=-78, lat1_deg=78, dlat_deg=3.0, dlon_deg=3.0)
+    G0 = Grid(**grid)
+    F0 = ModelFields(G0, gpu_enable=False, device='cpu', **kw)
+    names = ['HSURF', 'COLP', 'UWIND', 'VWIND', 'POTT', 'QV', 'QC', 'PVTF', 'PVTFVB', 'POTTVB',
+             'WWIND']
+    for world in (1, 3):
+        for rank in range(world):
+            G = Grid(band=(rank, world), **grid)
+            F = ModelFields(G, gpu_enable=False, device='cpu', band_local=True, **kw)
+            for n in names:
+                ja, jb = F._rows_of(G)(n)
+                assert F.host[n].shape[1] == jb - ja + 1
+                assert np.array_equal(F.host[n], F0.host[n][:, ja:jb + 1], equal_nan=True), \
+                    (world, rank, n)
+
+
+def test_band_local_fields_step_like_whole_grid_fields():
+    """band-local host arrays through dc_import_rows / dc_export_rows (host emulation, one
+    band = the whole grid): same device state and same result after a step"""
+    from helpers import STATE, build_emu
+    from climate_model_b200 import _lib
+    from climate_model_b200.dyn_matsuno import Diagnostics, step_matsuno
+    from climate_model_b200.io_read_namelist import B200
+    from climate_model_b200.main_fields import ModelFields
+    from climate_model_b200.main_grid import Grid
+    import torch
+    _lib.use_library(build_emu())
+    grid = dict(nz=6, lat0_deg=-80, lat1_deg=80, dlat_deg=10, dlon_deg=10)
+    out = []
+    for band_local in (False, True):
+        G = Grid(**grid)
+        F = ModelFields(G, band_local=band_local, UWIND_random_pert=1.0)
+        Diagnostics.primary_diag(G.GRF[B200], **F.get(Diagnostics.fields_primary_diag, target=B200))
+        step_matsuno(G, F, 2)
+        F.copy_device_to_host(G, F.PROGNOSTIC_FIELDS)
+        out.append({n: F.host[n].copy() for n in STATE})
+    for n in STATE:
+        assert np.array_equal(out[0][n], out[1][n], equal_nan=True), n
