@@ -16,6 +16,8 @@
 //   void dcb_launch_stage(const dc::StageBody &b, int nbx, int nby, void *stream);
 //   void dcb_launch_stage3(dc_handle *h, dc::Stage3Body &b, const dc::Stage3Ptrs &p, int nbx,
 //                          int nby, void *stream);   // fills b's TMA descriptors from p
+//   void dcb_launch_moist3(dc_handle *h, dc::Moist3Body &b, const dc::Moist3Ptrs &p, int nbx,
+//                          int nby, void *stream);
 //   void dcb_transpose(const dc::Geom &g, double *ref, double *dev, int fnx, int fny,
 //                      int nk, int j_lo, int j_hi, int to_device, void *stream);
 //   void dcb_profile_begin(dc_handle *h, const char *name, void *stream);
@@ -56,6 +58,11 @@ namespace dc {
 struct Stage3Ptrs {
     const double *U, *V, *W, *PHI, *T, *G;         // staged boxes; W: nz+1 interfaces
     const double *TB, *Uo, *Vo, *To;               // own-column boxes; TB: nz+1 interfaces
+};
+
+struct Moist3Ptrs {
+    const double *U, *V, *Q[2];      // staged boxes
+    const double *W, *Qo[2];         // own-column boxes; W: nz+1 interfaces
 };
 
 static thread_local std::string g_last_error;
@@ -131,6 +138,7 @@ struct dc_handle {
     int stage_kchunks;    // sigma-column chunks of the stage kernel (0 = by launch size)
     int cont_impl;        // 2 = single-pass tile kernel (default), 1 = two-sweep column kernel
     int stage_impl;       // fused mode: 3 = dc_stage3.h (default), 2 = dc_fused.h (DC_STAGE_IMPL=2)
+    int moist_impl;       // fused mode: 3 = dc_moist3.h tile kernel (default), 1 = column kernel
     int coupled_impl;     // i_coupling: 1 = kernel decomposition (default), 2 = fused dry stage
                           // kernel + coupled increments (DC_COUPLED_IMPL=2, experimental)
     void *tma_state;      // backend-owned descriptor cache
@@ -343,24 +351,62 @@ static void do_stage_fused(dc_handle *h, int stage, int part, void *stream)
         if (g.i_moist) {
             const double *QV = stage == 0 ? f.QV : f.QV_OLD, *QC = stage == 0 ? f.QC : f.QC_OLD;
             double *QVo = stage == 0 ? f.QV_OLD : f.QV, *QCo = stage == 0 ? f.QC_OLD : f.QC;
-            MoistStageBody m{g,       QV,         QC,         U,    V,    f.COLP,
-                             f.WWIND, f.COLP_NEW, f.COLP_OLD, f.QV, f.QC, QVo,    QCo};
-            launch(h, "moist_stage", m, 1, g.nx, g.j0, g.j1, stream);
+            if (h->moist_impl == 3 && h->stage_impl == 3) {
+                Moist3Body mb;
+                mb.g = g;
+                mb.COLP = f.COLP; mb.COLP_NEW = f.COLP_NEW; mb.COLP_OLD = f.COLP_OLD;
+                mb.WWIND = f.WWIND;
+                mb.Q_in[0] = QV; mb.Q_in[1] = QC;
+                mb.Q_out[0] = QVo; mb.Q_out[1] = QCo;
+                mb.j_lo = g.j0; mb.j_hi = g.j1;
+                mb.jt = 1 + (g.j0 - 1) / S3_TY * S3_TY;     // tiles of the global tiling
+                mb.have_old = stage == 0 ? 0 : 1;
+                mb.lc = make_log_coef();
+                const int nbx3 = (g.nx + S3_TX - 1) / S3_TX,
+                          nby3 = (g.j1 - 1) / S3_TY - (g.j0 - 1) / S3_TY + 1;
+                int nkc = h->stage_kchunks;
+                if (nkc <= 0) {
+                    const int slots = 3 * 148;
+                    nkc = nbx3 * nby3 >= 4 * slots ? 1 : (nbx3 * nby3 >= slots ? 2 : 4);
+                    while (nkc > 1 && (g.nz + nkc - 1) / nkc < 8) nkc--;
+                }
+                if (nkc > g.nz) nkc = g.nz;
+                while ((nkc - 1) * ((g.nz + nkc - 1) / nkc) >= g.nz) nkc--;
+                mb.nkc = nkc;
+                const Moist3Ptrs mp{U, V, {QV, QC}, f.WWIND, {f.QV, f.QC}};
+                if (h->profiling) dcb_profile_begin(h, "moist_stage", stream);
+                dcb_launch_moist3(h, mb, mp, nbx3, nby3, stream);
+                if (h->profiling) dcb_profile_end(h, stream);
+                h->launches++;
+            } else {
+                MoistStageBody m{g,       QV,         QC,         U,    V,    f.COLP,
+                                 f.WWIND, f.COLP_NEW, f.COLP_OLD, f.QV, f.QC, QVo,    QCo};
+                launch(h, "moist_stage", m, 1, g.nx, g.j0, g.j1, stream);
+            }
         }
     }
-    // tile rows of the band: [j0, j1] in steps of TY; boundary = first and last tile row
+    // tile rows of the band, cut from the GLOBAL tiling (origins at rows 1 + m * TY, see
+    // Stage3Body): tiles t0 .. t1 hold the rows [j0, j1]; boundary = first and last of them
     const int TY = h->stage_impl == 3 ? S3_TY : dc::TY;
-    const int ntr = (g.j1 - g.j0 + TY) / TY;
+    const bool aligned = h->stage_impl == 3;
+    const int t0 = aligned ? (g.j0 - 1) / TY : 0;
+    const int t1 = aligned ? (g.j1 - 1) / TY : (g.j1 - g.j0) / TY;
+    const int org = aligned ? 1 : g.j0;                      // row of tile 0
+    const int ntr = t1 - t0 + 1;
     const bool can_split = ntr >= 4;
-    struct Range { int lo, hi; } ranges[2];
+    struct Range { int lo, hi, t_first, nt; } ranges[2];     // rows advanced, tiles covering them
     int nr = 0;
+    auto clip = [&](int ta, int tb) {
+        const int lo = org + ta * TY, hi = org + (tb + 1) * TY - 1;
+        return Range{lo < g.j0 ? g.j0 : lo, hi > g.j1 ? g.j1 : hi, ta, tb - ta + 1};
+    };
     if (part == DC_PART_ALL || (part == DC_PART_BOUNDARY && !can_split)) {
-        ranges[nr++] = Range{g.j0, g.j1};
+        ranges[nr++] = clip(t0, t1);
     } else if (part == DC_PART_BOUNDARY) {
-        ranges[nr++] = Range{g.j0, g.j0 + TY - 1};
-        ranges[nr++] = Range{g.j0 + (ntr - 1) * TY, g.j1};
+        ranges[nr++] = clip(t0, t0);
+        ranges[nr++] = clip(t1, t1);
     } else if (part == DC_PART_INTERIOR && can_split) {
-        ranges[nr++] = Range{g.j0 + TY, g.j0 + (ntr - 1) * TY - 1};
+        ranges[nr++] = clip(t0 + 1, t1 - 1);
     }
     if (nr && h->stage_impl == 3) {   // both row ranges (if two) in ONE launch
         Stage3Body sb;
@@ -370,9 +416,11 @@ static void do_stage_fused(dc_handle *h, int stage, int part, void *stream)
         sb.U_in = U; sb.V_in = V;
         sb.UWIND_out = Uo; sb.VWIND_out = Vo; sb.POTT_out = To;
         sb.j_lo = ranges[0].lo; sb.j_hi = ranges[0].hi;
-        sb.nby0 = (ranges[0].hi - ranges[0].lo + S3_TY) / S3_TY;
+        sb.jt = org + ranges[0].t_first * S3_TY;
+        sb.nby0 = ranges[0].nt;
         sb.j_lo2 = nr > 1 ? ranges[1].lo : 0; sb.j_hi2 = nr > 1 ? ranges[1].hi : -1;
-        const int nby1 = nr > 1 ? (ranges[1].hi - ranges[1].lo + S3_TY) / S3_TY : 0;
+        sb.jt2 = nr > 1 ? org + ranges[1].t_first * S3_TY : 0;
+        const int nby1 = nr > 1 ? ranges[1].nt : 0;
         sb.have_old = stage == 0 ? 0 : 1;   // stage 1 evaluates the step-start state itself
         // sigma-column chunks: only when the launch has too few blocks to keep the 2 x 148
         // block slots of a B200 busy (a latitude band at N = 8); DC_STAGE_KCHUNKS overrides
@@ -680,6 +728,10 @@ int dc_create(const dc_grid_desc *d, dc_handle **out)
     h->stage_kchunks = kch ? atoi(kch) : 0;
     const char *cpl = getenv("DC_COUPLED_IMPL");
     h->coupled_impl = (cpl && cpl[0] == '2') ? 2 : 1;
+    {
+        const char *mi = getenv("DC_MOIST_IMPL");
+        h->moist_impl = (mi && mi[0] == '1') ? 1 : 3;
+    }
     const char *cimpl = getenv("DC_CONT_IMPL");
     h->cont_impl = (cimpl && cimpl[0] == '1') ? 1 : 2;
     *out = h;

@@ -389,6 +389,43 @@ DC_HD double pow_kappa_tab(double x, const PowCoef &c)
     return dc_fma(T, q * tt, T);
 }
 
+// Table-driven natural logarithm for the production build (moisture interface values,
+// comp_VARVB_log): x = 2^e * m, t = fma(m, r_j, -1) as in pow_kappa_tab,
+//   log x = e ln2 + log(1 / r_j) + log1p(t),   log1p(t) = t - t^2/2 + ... - t^8/8  (|t| <= 2^-7)
+// with ln2 split so that e * ln2_hi is exact.  ~1 ulp away from x = 1 (tracer mixing ratios are
+// < 0.1).  The table {r_j, log(1/r_j)} travels in the kernel parameter block (2 KB).
+struct LogCoef {
+    double ln2_hi, ln2_lo;
+    double c[9];                   // (-1)^(n+1) / n, n = 1..8 (c[0] unused)
+    double tab[POW_NJ][2];         // r_j, log(1 / r_j) from the rounded r_j
+};
+inline LogCoef make_log_coef()
+{
+    LogCoef L;
+    L.ln2_hi = 6.93147180369123816490e-01;
+    L.ln2_lo = 1.90821492927058770002e-10;
+    L.c[0] = 0.;
+    for (int n = 1; n < 9; n++) L.c[n] = ((n & 1) ? 1. : -1.) / n;
+    for (int j = 0; j < POW_NJ; j++) {
+        const double r = 1. / (1. + (j + 0.5) / POW_NJ);
+        L.tab[j][0] = r;
+        L.tab[j][1] = (double)logl(1.0L / (long double)r);
+    }
+    return L;
+}
+DC_HD double log_tab(double x, const LogCoef &L)
+{
+    const int hi = dc_hi_word(x);
+    const int e = (hi >> 20) - 1023;
+    const int j = (hi >> (20 - POW_JBITS)) & (POW_NJ - 1);
+    const double m = dc_from_words((hi & 0x000fffff) | 0x3ff00000, dc_lo_word(x));
+    const double t = dc_fma(m, L.tab[j][0], -1.);
+    double p = L.c[8];
+    for (int n = 7; n >= 1; n--) p = dc_fma(p, t, L.c[n]);
+    const double de = (double)e;
+    return dc_fma(de, L.ln2_hi, L.tab[j][1] + dc_fma(de, L.ln2_lo, p * t));
+}
+
 // ---------------------------------------------------------------------------------------
 // physics coupling terms (vertical turbulent transport, surface fluxes)
 // ---------------------------------------------------------------------------------------

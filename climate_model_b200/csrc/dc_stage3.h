@@ -319,9 +319,14 @@ struct Stage3Body {
     const double *WWIND, *POTTVB;            // set-up reads of interface 0
     const double *U_in, *V_in;               // the stage's input winds (own columns, S3_NBUF == 2)
     double *UWIND_out, *VWIND_out, *POTT_out;
-    // global mass rows to advance: tile rows [0, nby0) cover j_lo .. j_hi, tile rows from nby0
-    // on cover j_lo2 .. j_hi2 (the two boundary tile rows of a band in ONE launch)
-    int j_lo, j_hi, nby0, j_lo2, j_hi2;
+    // Tiles are cut from the GLOBAL tiling (tile rows start at global rows 1 + m * S3_TY)
+    // whatever rows a launch advances: a cell is computed in the same tile footprint, by the same
+    // template instantiation and hence with the same FMA contraction, on one GPU and on any
+    // number of latitude bands -- the production build stays BITWISE identical across
+    // decompositions.  Tile rows [0, nby0) start at global row jt and advance the rows
+    // j_lo .. j_hi that fall into them; tile rows from nby0 on start at jt2 and advance
+    // j_lo2 .. j_hi2 (the two boundary tile rows of a band in ONE launch).
+    int j_lo, j_hi, nby0, j_lo2, j_hi2, jt, jt2;
     int have_old;     // 0: the step-start state is the state the tendencies are evaluated at
     // Small grids (a latitude band at N = 8) do not fill the 2 x 148 block slots for long: the
     // sigma column is then cut into nkc chunks, one block each (blockIdx.z).  A chunk that does
@@ -336,15 +341,16 @@ struct Stage3Body {
     {
         const bool second = by >= nby0;
         const int jl = second ? j_lo2 : j_lo, jh = second ? j_hi2 : j_hi;
+        const int jo = second ? jt2 : jt;
         if (second) by -= nby0;
-        const int I0 = 1 + bx * S3_TX, J0 = jl + by * S3_TY;
-        const int j_top = (jh < g.ny - 1) ? jh : g.ny - 1;
+        const int I0 = 1 + bx * S3_TX, J0 = jo + by * S3_TY;
+        // the footprint decides, not the rows advanced (see above)
         const bool interior = (I0 >= 3) && (I0 + S3_TX - 1 <= g.nx - 1) && (J0 >= 2) &&
-                              (J0 + S3_TY - 1 <= j_top);
+                              (J0 + S3_TY - 1 <= g.ny - 1);
         if (interior)
-            run<false>(bx, by, bz, jl, jh, s);
+            run<false>(bx, J0, bz, jl, jh, s);
         else
-            run<true>(bx, by, bz, jl, jh, s);
+            run<true>(bx, J0, bz, jl, jh, s);
     }
 
     // issue the TMA copies of level kp into ring slot (kp - ks) % NBUF (one thread)
@@ -381,16 +387,15 @@ struct Stage3Body {
     }
 
     template <bool EDGE>
-    DC_HD void run(int bx, int by, int bz, int j_lo, int j_hi, Stage3Smem &s) const
+    DC_HD void run(int bx, int J0, int bz, int j_lo, int j_hi, Stage3Smem &s) const
     {
-        (void)j_lo;
         const int nx = g.nx, ny = g.ny, nz = g.nz;
         // levels of this block: k0 .. k1-1, marched from ks (= k0 - 1 for a warm-up level);
         // planes are needed up to level ke (the own U, V of level k1 close the last interface)
         const int kcl = (nz + nkc - 1) / nkc;
         const int k0 = bz * kcl, k1 = (k0 + kcl < nz) ? k0 + kcl : nz;
         const int ks = k0 > 0 ? k0 - 1 : 0, ke = k1 < nz ? k1 : nz - 1;
-        const int I0 = 1 + bx * S3_TX, J0 = j_lo + by * S3_TY;
+        const int I0 = 1 + bx * S3_TX;
         const size_t plane = g.plane;
         const double dyis = g.dyis, dt = g.dt;
         const double scale = cor_scale(g.dlon_rad, g.dlat_rad);
@@ -493,9 +498,10 @@ struct Stage3Body {
             {
                 const int tx = tid % S3_NTX, ty = tid / S3_NTX;
                 const int ia = I0 + 2 * tx, j = J0 + ty;
-                const int va = (ia <= nx) && (j <= j_hi), vb = (ia + 1 <= nx) && (j <= j_hi);
+                const int vj = (j >= j_lo) && (j <= j_hi);
+                const int va = (ia <= nx) && vj, vb = (ia + 1 <= nx) && vj;
                 // masked pairs read a safe in-domain neighbourhood
-                const int ii = ia > nx ? nx - 1 : ia, jj = j <= j_hi ? j : j_hi;
+                const int ii = ia > nx ? nx - 1 : ia, jj = j < j_lo ? j_lo : (j <= j_hi ? j : j_hi);
                 const int ea = (ia <= 2) || (ia == nx) || (jj == 1) || (jj == ny);
                 const int eb = (ia + 1 <= 2) || (ia + 1 == nx) || (jj == 1) || (jj == ny);
                 S3_P(flags) = va | (vb << 1) | (ea << 2) | (eb << 3);
@@ -585,6 +591,7 @@ struct Stage3Body {
             }
             if (tid <= S3_TY) {
                 int j = J0 - 1 + tid;
+                if (j < j_min) j = j_min;       // tile clipped by the band: rows nobody advances
                 if (j > j_max_m) j = j_max_m;
                 const int r = g.row(j);
                 s.row[0][tid] = cor_fcos(g.corf_is[r], g.cos_lat_is[r]);
@@ -624,10 +631,10 @@ struct Stage3Body {
                 const R4 W_0 = ld4(&s.rW[b][b0]);
                 const double w_kp1[2] = {W_0.a, W_0.b};
                 const int fl = S3_P(flags);
-                if (DC_FAST && (!EDGE || (fl & 3))) {
+                if (DC_FAST && (fl & 3)) {
 #include "dc_stage3_fast.inc"
                 }
-                if (!DC_FAST && (!EDGE || (fl & 3))) {
+                if (!DC_FAST && (fl & 3)) {
                     const bool wall_s = EDGE && (j == 1), wall_n = EDGE && (j == ny);
                     // raw winds around the pair and, from them, UFLX / VFLX
                     // (calc_UFLX, calc_VFLX: dyn_continuity.py:40-47)
@@ -821,7 +828,7 @@ struct Stage3Body {
                                     else
                                         UWIND_out[ko + S3_P(off0) + e] = un;
                                 }
-                            } else {
+                            } else if (fl & (1 << e)) {   // rows outside the launch's range are masked
                                 UWIND_out[ko + S3_P(off0) + e] = un;
                             }
                         }
@@ -919,7 +926,7 @@ struct Stage3Body {
                                     else
                                         VWIND_out[ko + S3_P(off0) + e] = vn;
                                 }
-                            } else {
+                            } else if (fl & (1 << e)) {   // rows outside the launch's range are masked
                                 VWIND_out[ko + S3_P(off0) + e] = vn;
                             }
                         }
@@ -970,7 +977,7 @@ struct Stage3Body {
                                     else
                                         POTT_out[ko + S3_P(off0) + e] = tn;
                                 }
-                            } else {
+                            } else if (fl & (1 << e)) {   // rows outside the launch's range are masked
                                 POTT_out[ko + S3_P(off0) + e] = tn;
                             }
                         }

@@ -109,6 +109,17 @@ __global__ void __launch_bounds__(S3_NT, DC_S3_MINBLOCKS) k_stage3(const __grid_
     Stage3Smem &s = *reinterpret_cast<Stage3Smem *>(stage3_smem + ((128u - (a & 127u)) & 127u));
     b.run_block(blockIdx.x, blockIdx.y, blockIdx.z, s);
 }
+}  // namespace dc
+#include "dc_moist3.h"
+namespace dc {
+struct Moist3Ptrs;
+__global__ void __launch_bounds__(S3_NT, 3) k_moist3(const __grid_constant__ Moist3Body b)
+{
+    extern __shared__ unsigned char moist3_smem[];
+    const unsigned a = (unsigned)__cvta_generic_to_shared(moist3_smem);
+    Moist3Smem &s = *reinterpret_cast<Moist3Smem *>(moist3_smem + ((128u - (a & 127u)) & 127u));
+    b.run_block(blockIdx.x, blockIdx.y, blockIdx.z, s);
+}
 struct TmaState {
     std::map<std::pair<const void *, int>, CUtensorMap> maps;   // (field base, own box?)
 };
@@ -132,6 +143,8 @@ static EncodeTiledFn encode_tiled()
 static void dcb_launch_stage3(dc_handle *h, dc::Stage3Body &b, const dc::Stage3Ptrs &p, int nbx,
                               int nby, void *stream);
 static void dcb_tma_release(dc_handle *h);
+static void dcb_launch_moist3(dc_handle *h, dc::Moist3Body &b, const dc::Moist3Ptrs &p, int nbx,
+                              int nby, void *stream);
 
 // ---------------------------------------------------------------------------------------
 // layout conversion: reference (i, j, k) k-fastest  <->  device F[k][jd][i] i-fastest.
@@ -553,4 +566,29 @@ static void dcb_launch_stage3(dc_handle *h, dc::Stage3Body &b, const dc::Stage3P
         *w.dst = *m;
     }
     k_stage3<<<dim3(nbx, nby, b.nkc), dim3(S3_NT), smem, (cudaStream_t)stream>>>(b);
+}
+
+static void dcb_launch_moist3(dc_handle *h, dc::Moist3Body &b, const dc::Moist3Ptrs &p, int nbx,
+                              int nby, void *stream)
+{
+    using namespace dc;
+    static bool configured = false;
+    const int smem = (int)sizeof(Moist3Smem) + 128;
+    if (!configured) {
+        cudaFuncSetAttribute(k_moist3, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(k_moist3, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        configured = true;
+    }
+    const int nz = h->g.nz;
+    struct { CUtensorMap *dst; const double *base; int nk; bool own; } want[] = {
+        {&b.mU, p.U, nz, false},      {&b.mV, p.V, nz, false},
+        {&b.mQ[0], p.Q[0], nz, false}, {&b.mQ[1], p.Q[1], nz, false},
+        {&b.mW, p.W, nz + 1, true},   {&b.mQo[0], p.Qo[0], nz, true},
+        {&b.mQo[1], p.Qo[1], nz, true}};
+    for (auto &w : want) {
+        const CUtensorMap *m = stage3_map(h, w.base, w.nk, w.own);
+        if (!m) return;
+        *w.dst = *m;
+    }
+    k_moist3<<<dim3(nbx, nby, b.nkc), dim3(S3_NT), smem, (cudaStream_t)stream>>>(b);
 }

@@ -51,11 +51,15 @@ static void dcb_launch_stage(const dc::StageBody &b, int nbx, int nby, void *)
         }
 }
 #include "../../climate_model_b200/csrc/dc_stage3.h"
+#include "../../climate_model_b200/csrc/dc_moist3.h"
 struct dc_handle;
 namespace dc { struct Stage3Ptrs; }
 static void dcb_launch_stage3(dc_handle *h, dc::Stage3Body &b, const dc::Stage3Ptrs &p, int nbx,
                               int nby, void *);
 static void dcb_tma_release(dc_handle *) {}
+namespace dc { struct Moist3Ptrs; }
+static void dcb_launch_moist3(dc_handle *h, dc::Moist3Body &b, const dc::Moist3Ptrs &p, int nbx,
+                              int nby, void *);
 static void dcb_transpose(const dc::Geom &g, double *ref, double *dev, int fnx, int fny, int nk,
                           int j_lo, int j_hi, int to_device, void *)
 {
@@ -109,6 +113,30 @@ static void dcb_launch_stage3(dc_handle *, dc::Stage3Body &b, const dc::Stage3Pt
             for (int bx = nbx - 1; bx >= 0; bx--) {
                 for (size_t n = 0; n < sizeof(s) / sizeof(double); n++)
                     reinterpret_cast<double *>(&s)[n] = 0.0 / 0.0;   // stale smem must not be read
+                b.run_block(bx, by, bz, s);
+            }
+}
+
+static void dcb_launch_moist3(dc_handle *, dc::Moist3Body &b, const dc::Moist3Ptrs &p, int nbx,
+                              int nby, void *)
+{
+    using namespace dc;
+    const Geom &g = b.g;
+    auto mk = [&](TmaMap &m, const double *base, int nk, bool own) {
+        m.base = base;
+        m.dim[0] = g.NI; m.dim[1] = g.NJ; m.dim[2] = nk;
+        m.box[0] = own ? S3_OW : S3_SW; m.box[1] = own ? S3_TY : S3_SH; m.box[2] = 1;
+    };
+    mk(b.mU, p.U, g.nz, false); mk(b.mV, p.V, g.nz, false);
+    mk(b.mQ[0], p.Q[0], g.nz, false); mk(b.mQ[1], p.Q[1], g.nz, false);
+    mk(b.mW, p.W, g.nz + 1, true); mk(b.mQo[0], p.Qo[0], g.nz, true);
+    mk(b.mQo[1], p.Qo[1], g.nz, true);
+    static Moist3Smem s;
+    for (int bz = 0; bz < b.nkc; bz++)
+        for (int by = nby - 1; by >= 0; by--)
+            for (int bx = nbx - 1; bx >= 0; bx--) {
+                for (size_t n = 0; n < sizeof(s) / sizeof(double); n++)
+                    reinterpret_cast<double *>(&s)[n] = 0.0 / 0.0;
                 b.run_block(bx, by, bz, s);
             }
 }
