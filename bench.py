@@ -279,12 +279,35 @@ def run_reference(args, wl, moist):
 PARITY_FIELDS = ['UWIND', 'VWIND', 'POTT', 'COLP']
 
 
+def band_timeline(GR, F, L, h, rank, world, path):
+    """--timeline: per-stream event timeline of ONE banded step (in-library exchange) on every
+    rank, written as JSON; shows which segment of the step is exposed"""
+    import torch
+    import torch.distributed as dist
+    from climate_model_b200 import _lib
+    from climate_model_b200.dyn_matsuno import step_matsuno
+    step_matsuno(GR, F, 1)
+    dist.barrier()
+    torch.cuda.synchronize()
+    _lib.check(L.dc_profile_enable(h, 2))
+    step_matsuno(GR, F, 1)
+    marks = _lib.timeline_read(h)
+    _lib.check(L.dc_profile_enable(h, 0))
+    allm = [None] * world
+    dist.all_gather_object(allm, marks)
+    if rank == 0:
+        with open(path, 'w') as f:
+            json.dump({'what': 'one banded Matsuno step, ms since the step began on each rank '
+                               '(M = main stream, S = side stream)', 'ranks': allm}, f, indent=1)
+
+
+
 def band_hash(F, GR, j0, j1):
     """exact hash of the owned rows j0..j1 (interior columns) of the prognostic fields"""
     import torch
     out = []
     js, nx = GR.jshift, int(GR.nx)
-    for n in PARITY_FIELDS:
+    for n in PARITY_FIELDS + (['QV', 'QC'] if GR.i_moist_main_switch else []):
         a = F.device[n][:, j0 + js:j1 + js + 1, 1:nx + 1].contiguous()
         out.append(a.view(torch.int64).sum())
     return torch.stack(out)
@@ -351,6 +374,8 @@ def main():
     ap.add_argument('--no-kernel-events', action='store_true',
                     help='do not bracket the kernels with CUDA events in the timed region (no '
                          'roofline object); checks that the brackets do not perturb the step')
+    ap.add_argument('--timeline', default=None,
+                    help='N > 1: write the per-stream event timeline of one banded step to this file')
     ap.add_argument('--emu', action='store_true',
                     help='debug the bench LOGIC on a box without a GPU against the host emulation '
                          '(tests/emu); the line is tagged "emu": true and is never a measurement')
@@ -466,6 +491,10 @@ def main():
     ms, _ = timed(False)
     launches = L.dc_launch_count(h) - launches0
     clocks = sampler.stop() if sampler else None
+    timeline_steps = 0
+    if args.timeline and world > 1 and getattr(GR.comm, 'in_library', False):
+        band_timeline(GR, F, L, h, rank, world, args.timeline)
+        timeline_steps = 2
     ms_per_step = ms / args.steps
     value = cells / (ms_per_step * 1e-3)
     js = GR.jshift   # owned rows, interior columns (halo cells beyond are never read)
@@ -477,7 +506,7 @@ def main():
     # hashes the rows it owns (sum of the fp64 bit patterns as int64, wrapping) and the
     # hashes are compared field by field, band by band.
     parity = None
-    steps_done = args.warmup + args.steps * (1 if args.no_kernel_events else 2)
+    steps_done = args.warmup + args.steps * (1 if args.no_kernel_events else 2) + timeline_steps
     if world > 1 and not args.turbulence:
         parity = banded_parity(GR, F, wl, moist, steps_done, rank, world, cells)
 

@@ -139,6 +139,16 @@ def field_table():
     return out
 
 
+def timeline_read(handle, max_entries=256):
+    """[(mark name, ms since the first mark)] of the banded steps enqueued while
+    dc_profile_enable(h, 2) was on (include/dyncore.h)"""
+    names = (ctypes.c_char_p * max_entries)()
+    ms = (ctypes.c_double * max_entries)()
+    n = (ctypes.c_longlong * max_entries)()
+    cnt = lib().dc_profile_read(handle, max_entries, names, ms, n)
+    return [(names[i].decode(), ms[i]) for i in range(cnt)]
+
+
 def profile_read(handle, max_entries=64):
     """{kernel name: (total ms, launches)} since the last read (dc_profile_read)"""
     names = (ctypes.c_char_p * max_entries)()

@@ -23,6 +23,7 @@
 //   void dcb_profile_begin(dc_handle *h, const char *name, void *stream);
 //   void dcb_profile_end(dc_handle *h, void *stream);
 //   int  dcb_profile_read(dc_handle *h, int max, const char **names, double *ms, long long *n);
+//   void dcb_mark(dc_handle *h, const char *name, void *stream);   // timeline mark (profiling == 2)
 //   in-library halo exchange (CUDA backend: NCCL; the host emulation has none and returns
 //   DC_ERR_NO_DEVICE from dcb_comm_init):
 //   int  dcb_comm_unique_id(void *id128);
@@ -183,9 +184,9 @@ static void launch(dc_handle *h, const char *name, const Body &b, int i0, int i1
                    void *stream)
 {
     if (i1 < i0 || j1 < j0) return;
-    if (h->profiling) dcb_profile_begin(h, name, stream);
+    if (h->profiling == 1) dcb_profile_begin(h, name, stream);
     dcb_launch(b, i0, i1, j0, j1, stream);
-    if (h->profiling) dcb_profile_end(h, stream);
+    if (h->profiling == 1) dcb_profile_end(h, stream);
     h->launches++;
 }
 
@@ -231,10 +232,10 @@ static void launch_continuity(dc_handle *h, const double *U, const double *V, vo
     if (hi < lo) return;
     ContinuityTileBody<MODE> b{g,      U,        V,       f.COLP,     f.COLP_OLD, f.UFLX,
                                f.VFLX, f.FLXDIV, f.WWIND, f.COLP_NEW, f.dCOLPdt, lo};
-    if (h->profiling) dcb_profile_begin(h, "continuity", stream);
+    if (h->profiling == 1) dcb_profile_begin(h, "continuity", stream);
     dcb_launch_blocks<ContinuityTileBody<MODE>, ContinuitySmem>(
         b, (g.nx + CT_TX - 1) / CT_TX, hi - lo + 1, (g.nz + CT_L - 1) / CT_L * CT_TX, stream);
-    if (h->profiling) dcb_profile_end(h, stream);
+    if (h->profiling == 1) dcb_profile_end(h, stream);
     h->launches++;
 }
 
@@ -374,9 +375,9 @@ static void do_stage_fused(dc_handle *h, int stage, int part, void *stream)
                 while ((nkc - 1) * ((g.nz + nkc - 1) / nkc) >= g.nz) nkc--;
                 mb.nkc = nkc;
                 const Moist3Ptrs mp{U, V, {QV, QC}, f.WWIND, {f.QV, f.QC}};
-                if (h->profiling) dcb_profile_begin(h, "moist_stage", stream);
+                if (h->profiling == 1) dcb_profile_begin(h, "moist_stage", stream);
                 dcb_launch_moist3(h, mb, mp, nbx3, nby3, stream);
-                if (h->profiling) dcb_profile_end(h, stream);
+                if (h->profiling == 1) dcb_profile_end(h, stream);
                 h->launches++;
             } else {
                 MoistStageBody m{g,       QV,         QC,         U,    V,    f.COLP,
@@ -434,19 +435,19 @@ static void do_stage_fused(dc_handle *h, int stage, int part, void *stream)
         while ((nkc - 1) * ((g.nz + nkc - 1) / nkc) >= g.nz) nkc--;   // no empty chunk
         sb.nkc = nkc;
         const Stage3Ptrs sp{U, V, f.WWIND, f.PHI, T, f.PGCOL, f.POTTVB, f.UWIND, f.VWIND, f.POTT};
-        if (h->profiling) dcb_profile_begin(h, "stage_fused", stream);
+        if (h->profiling == 1) dcb_profile_begin(h, "stage_fused", stream);
         dcb_launch_stage3(h, sb, sp, nbx3, sb.nby0 + nby1, stream);
-        if (h->profiling) dcb_profile_end(h, stream);
+        if (h->profiling == 1) dcb_profile_end(h, stream);
         h->launches++;
     }
     for (int r = 0; r < nr && h->stage_impl != 3; r++) {
         StageBody sb{g,       U,      V,          T,          f.PHI,   f.PVTF,  f.PVTFVB, f.POTTVB,
                      f.WWIND, f.COLP, f.COLP_NEW, f.COLP_OLD, f.UWIND, f.VWIND, f.POTT,
                      Uo,      Vo,     To,         ranges[r].lo, ranges[r].hi};
-        if (h->profiling) dcb_profile_begin(h, "stage_fused", stream);
+        if (h->profiling == 1) dcb_profile_begin(h, "stage_fused", stream);
         dcb_launch_stage(sb, (g.nx + TX - 1) / TX, (ranges[r].hi - ranges[r].lo + dc::TY) / dc::TY,
                          stream);
-        if (h->profiling) dcb_profile_end(h, stream);
+        if (h->profiling == 1) dcb_profile_end(h, stream);
         h->launches++;
     }
     if (part == DC_PART_ALL || part == DC_PART_COLP)
@@ -775,7 +776,7 @@ long long dc_launch_count(const dc_handle *h) { return h ? h->launches : 0; }
 int dc_profile_enable(dc_handle *h, int on)
 {
     if (!h) return fail(DC_ERR_ARG, "dc_profile_enable: NULL handle");
-    h->profiling = on ? 1 : 0;
+    h->profiling = on == 2 ? 2 : (on ? 1 : 0);   // 2: timeline marks of the banded step
     return DC_OK;
 }
 
@@ -820,11 +821,11 @@ static int do_transpose(dc_handle *h, int id, void *ref, size_t nbytes, int to_d
     held_rows(g, fny, &j_lo, &j_hi);
     if (j_lo < ja) j_lo = ja;
     if (j_hi > jb) j_hi = jb;
-    if (h->profiling) dcb_profile_begin(h, to_device ? "import_field" : "export_field", stream);
+    if (h->profiling == 1) dcb_profile_begin(h, to_device ? "import_field" : "export_field", stream);
     // the kernel addresses ref[(i * rows + j) * nk + k] with the GLOBAL row j: shift the base
     dcb_transpose(g, static_cast<double *>(ref) - (size_t)ja * nk, *h->slot(id), fnx, nrows, nk,
                   j_lo, j_hi, to_device, stream);
-    if (h->profiling) dcb_profile_end(h, stream);
+    if (h->profiling == 1) dcb_profile_end(h, stream);
     h->launches++;
     return backend_status(what);
 }
@@ -1213,29 +1214,42 @@ static void enqueue_band_step(dc_handle *h, void *M)
     const bool south = h->comm_rank > 0, north = h->comm_rank < h->comm_nranks - 1;
     const int lo = g.j0 - HJ < 0 ? 0 : g.j0 - HJ, hi = g.j1 + HJ > g.ny + 1 ? g.ny + 1 : g.j1 + HJ;
     const int own_lo = south ? g.j0 : lo, own_hi = north ? g.j1 : hi;
+    const bool tl = h->profiling == 2;   // timeline marks (dc_profile_enable(h, 2))
+#define DC_MARK(name, st) if (tl) dcb_mark(h, name, st)
+    DC_MARK("M step begin", M);
     dcb_d2d_async(f.COLP_OLD, f.COLP, g.plane * sizeof(double), M);      // dyn_matsuno.py:34
     for (int stage = 0; stage < 2; stage++) {
         do_stage_fused(h, stage, DC_PART_CONT, M);
+        DC_MARK("M continuity done", M);
         dcb_event_record(h, EV_CONT, M);
         dcb_stream_wait(h, EV_CONT, S);              // S: after the halo diagnostics, if any
+        DC_MARK("S boundary begin", S);
         do_stage_fused(h, stage, DC_PART_BOUNDARY, S);
+        DC_MARK("S boundary done", S);
         dcb_event_record(h, EV_BDONE, S);
         halo_move(h, stage, south ? dcb_comm_buffer(h, 0) : nullptr,
                   north ? dcb_comm_buffer(h, 2) : nullptr, 1, S, "dc_step_matsuno");
+        DC_MARK("S pack done", S);
         dcb_comm_sendrecv(h, S);
+        DC_MARK("S sendrecv done", S);
         dcb_event_record(h, EV_RECV, S);
         do_stage_fused(h, stage, DC_PART_INTERIOR, M);
+        DC_MARK("M interior done", M);
         dcb_stream_wait(h, EV_BDONE, M);             // both launches have read COLP
         do_stage_fused(h, stage, DC_PART_COLP, M);
         do_diag_rows(h, stage, own_lo, own_hi, M);
+        DC_MARK("M own-row diag done", M);
         dcb_stream_wait(h, EV_RECV, M);
         halo_move(h, stage, south ? dcb_comm_buffer(h, 1) : nullptr,
                   north ? dcb_comm_buffer(h, 3) : nullptr, 0, M, "dc_step_matsuno");
+        DC_MARK("M unpack done", M);
         // halo rows [lo, own_lo) and (own_hi, hi] in ONE launch on S, beside the next continuity
         dcb_event_record(h, EV_UNPACK, M);
         dcb_stream_wait(h, EV_UNPACK, S);
         do_diag_rows(h, stage, lo, hi, S, own_lo, own_hi);
+        DC_MARK("S halo-row diag done", S);
     }
+#undef DC_MARK
     dcb_event_record(h, EV_JOIN, S);                 // the step ends when both streams have
     dcb_stream_wait(h, EV_JOIN, M);
 }
@@ -1252,7 +1266,10 @@ static int step_matsuno_banded(dc_handle *h, int nsteps, void *stream)
         return fail(DC_ERR_STATE, "dc_step_matsuno: a band needs at least %d rows", HJ);
     do_xhalo_fix(h, stream);
     // the per-kernel event brackets of dc_profile_enable cannot be captured: plain enqueue then
-    if (!h->band_graph || h->profiling || dcb_graph_step(h, nsteps, stream, enqueue_band_step))
+    int gs = 1;
+    if (h->band_graph && !h->profiling) gs = dcb_graph_step(h, nsteps, stream, enqueue_band_step);
+    if (gs == 2) return fail(DC_ERR_STATE, "dc_step_matsuno: cudaGraphLaunch failed");
+    if (gs == 1)
         for (int s = 0; s < nsteps; s++) enqueue_band_step(h, stream);
     if (dcb_comm_error()[0]) return fail(DC_ERR_STATE, "dc_step_matsuno: %s", dcb_comm_error());
     return backend_status("dc_step_matsuno");
@@ -1333,7 +1350,7 @@ int dc_step_matsuno(dc_handle *h, int nsteps, void *stream)
     if ((rc = refresh_diag(h, "dc_step_matsuno", stream))) return rc;
     for (int s = 0; s < nsteps; s++) {
         // dyn_matsuno.py:34-49: OLD <- current
-        if (h->profiling) dcb_profile_begin(h, "copy_old", stream);
+        if (h->profiling == 1) dcb_profile_begin(h, "copy_old", stream);
         dcb_d2d_async(f.COLP_OLD, f.COLP, b2, stream);
         dcb_d2d_async(f.UWIND_OLD, f.UWIND, b3, stream);
         dcb_d2d_async(f.VWIND_OLD, f.VWIND, b3, stream);
@@ -1342,7 +1359,7 @@ int dc_step_matsuno(dc_handle *h, int nsteps, void *stream)
             dcb_d2d_async(f.QV_OLD, f.QV, b3, stream);
             dcb_d2d_async(f.QC_OLD, f.QC, b3, stream);
         }
-        if (h->profiling) dcb_profile_end(h, stream);
+        if (h->profiling == 1) dcb_profile_end(h, stream);
         for (int stage = 0; stage < 2; stage++) {  // estimate, final
             do_continuity(h, false, stream);
             do_momentum(h, stream);

@@ -217,6 +217,7 @@ struct ProfileState {
     std::vector<ProfileRec> recs;
     std::vector<cudaEvent_t> pool;
     std::vector<std::string> names;  // storage for dc_profile_read's returned strings
+    std::vector<std::pair<const char *, cudaEvent_t>> marks;   // timeline (dc_profile_enable(h, 2))
     cudaEvent_t get()
     {
         if (!pool.empty()) {
@@ -232,6 +233,7 @@ struct ProfileState {
 }  // namespace dc
 static void dcb_profile_begin(dc_handle *h, const char *name, void *stream);
 static void dcb_profile_end(dc_handle *h, void *stream);
+static void dcb_mark(dc_handle *h, const char *name, void *stream);
 static int dcb_profile_read(dc_handle *h, int max, const char **names, double *ms, long long *n);
 
 // in-library halo exchange: NCCL communicator, side stream, events, CUDA graph (defined below)
@@ -305,6 +307,8 @@ struct CommState {
     size_t nelem = 0;
     double *buf[4] = {nullptr, nullptr, nullptr, nullptr};   // send_s, recv_s, send_n, recv_n
     cudaStream_t side = nullptr;
+    cudaStream_t main = nullptr;   // stands in for the caller's stream when that is the legacy
+                                   // default stream, which cannot be captured
     cudaEvent_t ev[8] = {};
     cudaGraphExec_t graph = nullptr;
     long long graph_version = -1;
@@ -351,6 +355,7 @@ static int dcb_comm_init(dc_handle *h, const void *id128, int rank, int nranks, 
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);   // hi = numerically lowest = highest priority
     cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, hi);
+    cudaStreamCreateWithFlags(&c->main, cudaStreamNonBlocking);
     for (auto &ev : c->ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     for (int n = 0; n < 4; n++) {
         const bool present = (n < 2) ? rank > 0 : rank < nranks - 1;
@@ -375,6 +380,7 @@ static void dcb_comm_release(dc_handle *h)
     for (auto &ev : c->ev)
         if (ev) cudaEventDestroy(ev);
     if (c->side) cudaStreamDestroy(c->side);
+    if (c->main) cudaStreamDestroy(c->main);
     dc::NcclApi *a = dc::nccl_api();
     if (a && c->comm) a->CommDestroy(c->comm);
     delete c;
@@ -425,11 +431,16 @@ static int dcb_graph_step(dc_handle *h, int nsteps, void *stream,
                           void (*enqueue)(dc_handle *, void *))
 {
     dc::CommState *c = static_cast<dc::CommState *>(h->comm_state);
-    cudaStream_t st = (cudaStream_t)stream;
+    cudaStream_t caller = (cudaStream_t)stream;
     if (!c->warmed) {   // lazy NCCL connection set-up and cudaFuncSetAttribute must not be captured
         c->warmed = true;
         return 1;
     }
+    // the legacy default stream (torch's default current stream) cannot be captured: run on the
+    // handle's own stream between two events on the caller's
+    const bool legacy = caller == nullptr || caller == cudaStreamLegacy ||
+                        caller == cudaStreamPerThread;
+    cudaStream_t st = legacy ? c->main : caller;
     if (!c->graph || c->graph_version != h->bind_version) {
         if (c->graph) {
             cudaGraphExecDestroy(c->graph);
@@ -441,7 +452,7 @@ static int dcb_graph_step(dc_handle *h, int nsteps, void *stream,
             cudaGetLastError();
             return 1;
         }
-        enqueue(h, stream);
+        enqueue(h, st);
         const cudaError_t e = cudaStreamEndCapture(st, &g);
         c->launches_per_step = h->launches - launches0;
         h->launches = launches0;
@@ -459,11 +470,20 @@ static int dcb_graph_step(dc_handle *h, int nsteps, void *stream,
         c->graph_version = h->bind_version;
         c->error = 0;
     }
-    for (int s = 0; s < nsteps; s++) {
-        if (cudaGraphLaunch(c->graph, st) != cudaSuccess) return 1;
+    if (legacy) {
+        cudaEventRecord(c->ev[6], caller);
+        cudaStreamWaitEvent(c->main, c->ev[6], 0);
+    }
+    int rc = 0;
+    for (int s = 0; s < nsteps && !rc; s++) {
+        if (cudaGraphLaunch(c->graph, st) != cudaSuccess) rc = 1;
         h->launches += c->launches_per_step;
     }
-    return 0;
+    if (legacy) {
+        cudaEventRecord(c->ev[7], c->main);
+        cudaStreamWaitEvent(caller, c->ev[7], 0);
+    }
+    return rc ? 2 : 0;   // 2: a launch failed after steps were enqueued (reported by the caller)
 }
 
 static dc::ProfileState *pstate(dc_handle *h)
@@ -482,10 +502,42 @@ static void dcb_profile_end(dc_handle *h, void *stream)
 {
     cudaEventRecord(pstate(h)->recs.back().b, (cudaStream_t)stream);
 }
+static void dcb_mark(dc_handle *h, const char *name, void *stream)
+{
+    dc::ProfileState *p = pstate(h);
+    cudaEvent_t e = p->get();
+    cudaEventRecord(e, (cudaStream_t)stream);
+    p->marks.push_back({name, e});
+}
 static int dcb_profile_read(dc_handle *h, int max, const char **names, double *ms, long long *n)
 {
     dc::ProfileState *p = pstate(h);
     cudaDeviceSynchronize();
+    if (!p->marks.empty()) {
+        // timeline mode: one entry per mark, in enqueue order; ms = time since the first mark,
+        // launches = the index of the mark
+        p->names.clear();
+        for (auto &m : p->marks) p->names.push_back(m.first);
+        int i = 0;
+        for (auto &m : p->marks) {
+            float t = 0.f;
+            cudaEventElapsedTime(&t, p->marks[0].second, m.second);
+            if (i < max) {
+                names[i] = p->names[i].c_str();
+                ms[i] = t;
+                n[i] = i;
+                i++;
+            }
+            p->pool.push_back(m.second);
+        }
+        p->marks.clear();
+        for (const dc::ProfileRec &r : p->recs) {
+            p->pool.push_back(r.a);
+            p->pool.push_back(r.b);
+        }
+        p->recs.clear();
+        return i;
+    }
     std::map<std::string, std::pair<double, long long>> acc;
     for (const dc::ProfileRec &r : p->recs) {
         float t = 0.f;

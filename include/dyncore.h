@@ -231,7 +231,12 @@ long long dc_launch_count(const dc_handle *h);
 /* ---- per-kernel device timing (bench.py roofline): when enabled, every kernel launch is
  *      bracketed by CUDA events on its stream.  dc_profile_read synchronises the device,
  *      adds up the elapsed times per kernel and resets the event list.
- *      names[i] / ms[i] / launches[i] for i < return value (<= max_entries). ---- */
+ *      names[i] / ms[i] / launches[i] for i < return value (<= max_entries).
+ *      dc_profile_enable(h, 2) = timeline mode for the banded dc_step_matsuno: instead of the
+ *      brackets, a timing event is recorded at every hand-over of the step (after the
+ *      continuity, the boundary tile rows, the pack, the NCCL group, ...) on the stream it
+ *      happens on; dc_profile_read then returns the marks in enqueue order with ms[i] = time
+ *      since the first mark (launches[i] = i). ---- */
 int dc_profile_enable(dc_handle *h, int on);
 int dc_profile_read(dc_handle *h, int max_entries, const char **names, double *ms,
                     long long *launches);

@@ -74,6 +74,7 @@ static void dcb_transpose(const dc::Geom &g, double *ref, double *dev, int fnx, 
 struct dc_handle;
 static void dcb_profile_begin(dc_handle *, const char *, void *) {}
 static void dcb_profile_end(dc_handle *, void *) {}
+static void dcb_mark(dc_handle *, const char *, void *) {}
 static int dcb_profile_read(dc_handle *, int, const char **, double *, long long *) { return 0; }
 
 // the host emulation has no in-library communicator: the CPU tests drive the exchange through
