@@ -34,9 +34,12 @@
 //   void *dcb_side_stream(dc_handle *h);
 //   void dcb_event_record(dc_handle *h, int ev, void *stream);
 //   void dcb_stream_wait(dc_handle *h, int ev, void *stream);
-//   int  dcb_graph_step(dc_handle *h, int nsteps, void *stream, void (*enqueue)(dc_handle *, void *));
-//        // capture one step enqueued by `enqueue` into a CUDA graph (once per binding
-//        // version) and launch it nsteps times; returns 0 if it ran, 1 if graphs are unavailable
+//   int  dcb_graph_steps(dc_handle *h, int nsteps, void *stream,
+//                        void (*prologue)(dc_handle *, int, void *),
+//                        void (*step_tail)(dc_handle *, void *), void (*step_last)(dc_handle *, void *));
+//        // prologue(h, 0, st), then nsteps - 1 launches of the captured graph of step_tail and one
+//        // of step_last (captured once per binding version); returns 0 if it ran, 1 if graphs
+//        // are unavailable (nothing enqueued), 2 if a launch failed
 #pragma once
 #include <math.h>
 #include <stdarg.h>
@@ -339,6 +342,7 @@ static int do_primary_diag(dc_handle *h, void *stream, const double *POTT = null
 //   DC_PART_INTERIOR  stage kernel on the remaining tile rows
 //   DC_PART_COLP      COLP <- COLP_NEW (after every stage-kernel launch of the stage)
 // BOUNDARY and INTERIOR are independent of each other and may run on different streams.
+enum { DC_PART_CONT_ONLY = 100, DC_PART_MOIST = 101, DC_PART_STAGE_ALL = 102 };
 static void do_stage_fused(dc_handle *h, int stage, int part, void *stream)
 {
     const Fields &f = h->f;
@@ -347,8 +351,10 @@ static void do_stage_fused(dc_handle *h, int stage, int part, void *stream)
                  *T = stage == 0 ? f.POTT : f.POTT_OLD;
     double *Uo = stage == 0 ? f.UWIND_OLD : f.UWIND, *Vo = stage == 0 ? f.VWIND_OLD : f.VWIND,
            *To = stage == 0 ? f.POTT_OLD : f.POTT;
-    if (part == DC_PART_ALL || part == DC_PART_CONT) {
+    // internal pieces of DC_PART_CONT: the continuity alone / the moisture stage alone
+    if (part == DC_PART_ALL || part == DC_PART_CONT || part == DC_PART_CONT_ONLY)
         launch_continuity<0>(h, U, V, stream);
+    if (part == DC_PART_ALL || part == DC_PART_CONT || part == DC_PART_MOIST) {
         if (g.i_moist) {
             const double *QV = stage == 0 ? f.QV : f.QV_OLD, *QC = stage == 0 ? f.QC : f.QC_OLD;
             double *QVo = stage == 0 ? f.QV_OLD : f.QV, *QCo = stage == 0 ? f.QC_OLD : f.QC;
@@ -401,7 +407,8 @@ static void do_stage_fused(dc_handle *h, int stage, int part, void *stream)
         const int lo = org + ta * TY, hi = org + (tb + 1) * TY - 1;
         return Range{lo < g.j0 ? g.j0 : lo, hi > g.j1 ? g.j1 : hi, ta, tb - ta + 1};
     };
-    if (part == DC_PART_ALL || (part == DC_PART_BOUNDARY && !can_split)) {
+    if (part == DC_PART_ALL || part == DC_PART_STAGE_ALL ||
+        (part == DC_PART_BOUNDARY && !can_split)) {
         ranges[nr++] = clip(t0, t1);
     } else if (part == DC_PART_BOUNDARY) {
         ranges[nr++] = clip(t0, t0);
@@ -1162,8 +1169,13 @@ int dc_comm_unique_id(void *id, size_t nbytes)
 
 int dc_set_comm(dc_handle *h, const void *id, size_t nbytes, int rank, int nranks)
 {
-    if (!h || !id || nbytes < DC_COMM_ID_BYTES || nranks < 1 || rank < 0 || rank >= nranks)
+    // nranks == 1: no communicator, only the two-chain pipelining of the step (id may be NULL)
+    if (!h || nranks < 1 || rank < 0 || rank >= nranks ||
+        (nranks > 1 && (!id || nbytes < DC_COMM_ID_BYTES)))
         return fail(DC_ERR_ARG, "dc_set_comm: bad argument");
+    if ((nranks == 1) != (h->g.j0 == 1 && h->g.j1 == h->g.ny))
+        return fail(DC_ERR_STATE, "dc_set_comm: %d rank(s) but the handle holds rows %d..%d of %d",
+                    nranks, h->g.j0, h->g.j1, h->g.ny);
     size_t hb = 0;
     dc_halo_bytes(h, &hb);
     dcb_comm_release(h);
@@ -1191,68 +1203,99 @@ int dc_halo_exchange(dc_handle *h, int stage, void *stream)
                      north ? dcb_comm_buffer(h, 3) : nullptr, 0, stream, "dc_halo_exchange");
 }
 
-enum { EV_CONT = 0, EV_BDONE = 1, EV_RECV = 2, EV_UNPACK = 3, EV_JOIN = 4, EV_COUNT = 5 };
+enum { EV_START = 0, EV_CONT = 1, EV_BDONE = 2, EV_MOIST = 3, EV_COLP = 4, EV_DIAG = 5, EV_JOIN = 6 };
 
-// One Matsuno step on a latitude band with the exchange inside the library (stream M = the
-// caller's, S = the handle's high-priority side stream).  Per stage:
-//   M: continuity (rows j0-1 .. j1+1)          S: diagnostics of the HALO rows of the previous
-//                                                 stage (needs its unpack only), then waits for
-//                                                 the continuity
-//   M: stage kernel, interior tile rows        S: stage kernel on the first and last tile row,
-//                                                 pack, NCCL send/recv with both neighbours
-//   M: COLP <- COLP_NEW (after both stage-kernel launches)
-//   M: diagnostics of the rows that need no neighbour data -- the halo is in flight meanwhile
-//   M: waits for the receive, unpack
-// so the exchange hides behind the interior tile rows and the own-row diagnostics, and the
-// halo-row diagnostics (a launch as long as one thread's march up the column) behind the next
-// continuity.  Every kernel of a band is short: what is serial on M is what the step costs.
-static void enqueue_band_step(dc_handle *h, void *M)
+// continuity (+ COLP_OLD <- COLP before a step's first stage) of stage `stage`
+static void enqueue_continuity(dc_handle *h, int stage, void *st)
 {
-    const Fields &f = h->f;
+    if (stage == 0)
+        dcb_d2d_async(h->f.COLP_OLD, h->f.COLP, h->g.plane * sizeof(double), st);  // dyn_matsuno.py:34
+    do_stage_fused(h, stage, DC_PART_CONT_ONLY, st);
+}
+
+// One Matsuno step on a latitude band with the exchange inside the library, as TWO concurrent
+// chains (M = the caller's stream, S = the handle's high-priority side stream).  On entry the
+// continuity of stage 0 is done.  Per stage:
+//   M: [moisture stage] -> stage kernel on the interior tile rows -> COLP <- COLP_NEW ->
+//      diagnostics of the rows that need no neighbour data
+//   S: stage kernel on the first and last tile row -> pack -> NCCL send/recv with both
+//      neighbours -> unpack -> CONTINUITY OF THE NEXT STAGE -> diagnostics of the halo rows
+// The exchange hides behind the interior tile rows; the next continuity (needs the new U, V,
+// COLP incl. halos, nothing of the diagnostics) and the halo-row diagnostics run beside the
+// own-row diagnostics (needs the new POTT, COLP of the own rows).  Measured on two B200 with
+// the 84-row bands of the 8-GPU run (profiles/r2_timeline_*.json): before this pipelining
+// the serial chain continuity 74 -> interior 270 -> diagnostics 74 -> unpack 10 us was the
+// whole stage; every kernel of a band is as short as one thread's march up the column.
+// `tail`: also run the continuity of the NEXT step's stage 0 (a following step starts with it
+// done).  Single rank (nranks == 1): no exchange, the whole band in one stage-kernel launch.
+static void enqueue_band_step(dc_handle *h, void *M, int tail)
+{
     const Geom &g = h->g;
     void *S = dcb_side_stream(h);
+    const bool single = h->comm_nranks == 1;
     const bool south = h->comm_rank > 0, north = h->comm_rank < h->comm_nranks - 1;
     const int lo = g.j0 - HJ < 0 ? 0 : g.j0 - HJ, hi = g.j1 + HJ > g.ny + 1 ? g.ny + 1 : g.j1 + HJ;
     const int own_lo = south ? g.j0 : lo, own_hi = north ? g.j1 : hi;
     const bool tl = h->profiling == 2;   // timeline marks (dc_profile_enable(h, 2))
 #define DC_MARK(name, st) if (tl) dcb_mark(h, name, st)
     DC_MARK("M step begin", M);
-    dcb_d2d_async(f.COLP_OLD, f.COLP, g.plane * sizeof(double), M);      // dyn_matsuno.py:34
+    dcb_event_record(h, EV_START, M);
+    dcb_stream_wait(h, EV_START, S);
     for (int stage = 0; stage < 2; stage++) {
-        do_stage_fused(h, stage, DC_PART_CONT, M);
-        DC_MARK("M continuity done", M);
-        dcb_event_record(h, EV_CONT, M);
-        dcb_stream_wait(h, EV_CONT, S);              // S: after the halo diagnostics, if any
-        DC_MARK("S boundary begin", S);
-        do_stage_fused(h, stage, DC_PART_BOUNDARY, S);
-        DC_MARK("S boundary done", S);
-        dcb_event_record(h, EV_BDONE, S);
-        halo_move(h, stage, south ? dcb_comm_buffer(h, 0) : nullptr,
-                  north ? dcb_comm_buffer(h, 2) : nullptr, 1, S, "dc_step_matsuno");
-        DC_MARK("S pack done", S);
-        dcb_comm_sendrecv(h, S);
-        DC_MARK("S sendrecv done", S);
-        dcb_event_record(h, EV_RECV, S);
-        do_stage_fused(h, stage, DC_PART_INTERIOR, M);
+        const bool next = stage == 0 || tail;        // a continuity follows this stage
+        // ---- M: moisture, interior tile rows
+        if (stage == 1) dcb_stream_wait(h, EV_CONT, M);
+        if (g.i_moist) {
+            do_stage_fused(h, stage, DC_PART_MOIST, M);
+            dcb_event_record(h, EV_MOIST, M);
+            DC_MARK("M moisture done", M);
+        }
+        do_stage_fused(h, stage, single ? (int)DC_PART_STAGE_ALL : (int)DC_PART_INTERIOR, M);
         DC_MARK("M interior done", M);
-        dcb_stream_wait(h, EV_BDONE, M);             // both launches have read COLP
+        // ---- S: boundary tile rows, pack, exchange
+        if (!single) {
+            if (stage == 1) dcb_stream_wait(h, EV_DIAG, S);
+            DC_MARK("S boundary begin", S);
+            do_stage_fused(h, stage, DC_PART_BOUNDARY, S);
+            DC_MARK("S boundary done", S);
+            dcb_event_record(h, EV_BDONE, S);
+            if (g.i_moist) dcb_stream_wait(h, EV_MOIST, S);
+            halo_move(h, stage, south ? dcb_comm_buffer(h, 0) : nullptr,
+                      north ? dcb_comm_buffer(h, 2) : nullptr, 1, S, "dc_step_matsuno");
+            DC_MARK("S pack done", S);
+            dcb_comm_sendrecv(h, S);
+            DC_MARK("S sendrecv done", S);
+            dcb_stream_wait(h, EV_BDONE, M);         // both launches have read COLP
+        }
+        // ---- M: COLP <- COLP_NEW, diagnostics of the own rows
         do_stage_fused(h, stage, DC_PART_COLP, M);
+        dcb_event_record(h, EV_COLP, M);
         do_diag_rows(h, stage, own_lo, own_hi, M);
+        dcb_event_record(h, EV_DIAG, M);
         DC_MARK("M own-row diag done", M);
-        dcb_stream_wait(h, EV_RECV, M);
-        halo_move(h, stage, south ? dcb_comm_buffer(h, 1) : nullptr,
-                  north ? dcb_comm_buffer(h, 3) : nullptr, 0, M, "dc_step_matsuno");
-        DC_MARK("M unpack done", M);
-        // halo rows [lo, own_lo) and (own_hi, hi] in ONE launch on S, beside the next continuity
-        dcb_event_record(h, EV_UNPACK, M);
-        dcb_stream_wait(h, EV_UNPACK, S);
-        do_diag_rows(h, stage, lo, hi, S, own_lo, own_hi);
-        DC_MARK("S halo-row diag done", S);
+        // ---- S: unpack, next continuity, diagnostics of the halo rows
+        dcb_stream_wait(h, EV_COLP, S);
+        if (!single) {
+            halo_move(h, stage, south ? dcb_comm_buffer(h, 1) : nullptr,
+                      north ? dcb_comm_buffer(h, 3) : nullptr, 0, S, "dc_step_matsuno");
+            DC_MARK("S unpack done", S);
+        }
+        if (next) {
+            enqueue_continuity(h, 1 - stage, S);
+            dcb_event_record(h, EV_CONT, S);
+            DC_MARK("S next continuity done", S);
+        }
+        if (!single) {
+            do_diag_rows(h, stage, lo, hi, S, own_lo, own_hi);   // both halo ranges, one launch
+            DC_MARK("S halo-row diag done", S);
+        }
     }
 #undef DC_MARK
-    dcb_event_record(h, EV_JOIN, S);                 // the step ends when both streams have
+    dcb_event_record(h, EV_JOIN, S);                 // the step ends when both chains have
     dcb_stream_wait(h, EV_JOIN, M);
 }
+static void enqueue_band_step_tail(dc_handle *h, void *M) { enqueue_band_step(h, M, 1); }
+static void enqueue_band_step_last(dc_handle *h, void *M) { enqueue_band_step(h, M, 0); }
 
 static int step_matsuno_banded(dc_handle *h, int nsteps, void *stream)
 {
@@ -1264,13 +1307,18 @@ static int step_matsuno_banded(dc_handle *h, int nsteps, void *stream)
                                   "path only (nz <= %d)", NZMAX);
     if (g.j1 - g.j0 + 1 < HJ)
         return fail(DC_ERR_STATE, "dc_step_matsuno: a band needs at least %d rows", HJ);
+    if (nsteps == 0) return DC_OK;
     do_xhalo_fix(h, stream);
     // the per-kernel event brackets of dc_profile_enable cannot be captured: plain enqueue then
     int gs = 1;
-    if (h->band_graph && !h->profiling) gs = dcb_graph_step(h, nsteps, stream, enqueue_band_step);
+    if (h->band_graph && !h->profiling)
+        gs = dcb_graph_steps(h, nsteps, stream, enqueue_continuity, enqueue_band_step_tail,
+                             enqueue_band_step_last);
     if (gs == 2) return fail(DC_ERR_STATE, "dc_step_matsuno: cudaGraphLaunch failed");
-    if (gs == 1)
-        for (int s = 0; s < nsteps; s++) enqueue_band_step(h, stream);
+    if (gs == 1) {
+        enqueue_continuity(h, 0, stream);
+        for (int s = 0; s < nsteps; s++) enqueue_band_step(h, stream, s + 1 < nsteps);
+    }
     if (dcb_comm_error()[0]) return fail(DC_ERR_STATE, "dc_step_matsuno: %s", dcb_comm_error());
     return backend_status("dc_step_matsuno");
 }
@@ -1288,6 +1336,9 @@ int dc_step_matsuno(dc_handle *h, int nsteps, void *stream)
 {
     if (!h) return fail(DC_ERR_ARG, "dc_step_matsuno: NULL handle");
     if (nsteps < 0) return fail(DC_ERR_ARG, "dc_step_matsuno: nsteps < 0");
+    if (h->comm_state && h->comm_nranks == 1 && h->mode == DC_MODE_FUSED && !h->g.i_coupling &&
+        h->stage_impl == 3 && h->g.nz <= NZMAX)
+        return step_matsuno_banded(h, nsteps, stream);   // one rank, two concurrent chains
     if (h->g.j0 != 1 || h->g.j1 != h->g.ny) {
         // a band needs the halo exchange between the stages: with a communicator attached
         // (dc_set_comm) the library runs it; without, the caller drives dc_step_begin /

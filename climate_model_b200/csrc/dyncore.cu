@@ -245,8 +245,10 @@ static int dcb_comm_sendrecv(dc_handle *h, void *stream);
 static void *dcb_side_stream(dc_handle *h);
 static void dcb_event_record(dc_handle *h, int ev, void *stream);
 static void dcb_stream_wait(dc_handle *h, int ev, void *stream);
-static int dcb_graph_step(dc_handle *h, int nsteps, void *stream,
-                          void (*enqueue)(dc_handle *, void *));
+static int dcb_graph_steps(dc_handle *h, int nsteps, void *stream,
+                           void (*prologue)(dc_handle *, int, void *),
+                           void (*step_tail)(dc_handle *, void *),
+                           void (*step_last)(dc_handle *, void *));
 static const char *dcb_comm_error();
 
 #include "dc_api_impl.h"
@@ -309,10 +311,10 @@ struct CommState {
     cudaStream_t side = nullptr;
     cudaStream_t main = nullptr;   // stands in for the caller's stream when that is the legacy
                                    // default stream, which cannot be captured
-    cudaEvent_t ev[8] = {};
-    cudaGraphExec_t graph = nullptr;
+    cudaEvent_t ev[16] = {};
+    cudaGraphExec_t graph = nullptr, graph_last = nullptr;
     long long graph_version = -1;
-    long long launches_per_step = 0;
+    long long launches_per_step = 0, launches_last_step = 0;
     bool warmed = false;   // one plain step has run (NCCL connections, kernel attributes)
     int error = 0;
 };
@@ -339,18 +341,20 @@ static int dcb_comm_unique_id(void *id128)
 static int dcb_comm_init(dc_handle *h, const void *id128, int rank, int nranks, size_t halo_elems)
 {
     dc::g_comm_error.clear();
-    dc::NcclApi *a = dc::nccl_api();
-    if (!a) return DC_ERR_NO_DEVICE;
+    dc::NcclApi *a = nranks > 1 ? dc::nccl_api() : nullptr;
+    if (nranks > 1 && !a) return DC_ERR_NO_DEVICE;
     dc::CommState *c = new dc::CommState();
     c->rank = rank;
     c->nranks = nranks;
     c->nelem = halo_elems;
-    dc::NcclUniqueId id;
-    memcpy(&id, id128, sizeof id);
-    int e = a->CommInitRank(&c->comm, nranks, id, rank);
-    if (e) {
-        delete c;
-        return nccl_fail("ncclCommInitRank", e);
+    if (nranks > 1) {
+        dc::NcclUniqueId id;
+        memcpy(&id, id128, sizeof id);
+        const int e = a->CommInitRank(&c->comm, nranks, id, rank);
+        if (e) {
+            delete c;
+            return nccl_fail("ncclCommInitRank", e);
+        }
     }
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);   // hi = numerically lowest = highest priority
@@ -375,14 +379,17 @@ static void dcb_comm_release(dc_handle *h)
     if (!c) return;
     cudaDeviceSynchronize();
     if (c->graph) cudaGraphExecDestroy(c->graph);
+    if (c->graph_last) cudaGraphExecDestroy(c->graph_last);
     for (double *b : c->buf)
         if (b) cudaFree(b);
     for (auto &ev : c->ev)
         if (ev) cudaEventDestroy(ev);
     if (c->side) cudaStreamDestroy(c->side);
     if (c->main) cudaStreamDestroy(c->main);
-    dc::NcclApi *a = dc::nccl_api();
-    if (a && c->comm) a->CommDestroy(c->comm);
+    if (c->comm) {
+        dc::NcclApi *a = dc::nccl_api();
+        if (a) a->CommDestroy(c->comm);
+    }
     delete c;
     h->comm_state = nullptr;
 }
@@ -424,11 +431,42 @@ static void dcb_stream_wait(dc_handle *h, int ev, void *stream)
 {
     cudaStreamWaitEvent((cudaStream_t)stream, static_cast<dc::CommState *>(h->comm_state)->ev[ev], 0);
 }
-// One banded step captured into a CUDA graph (stream capture of `enqueue`, which forks to the
-// side stream and joins again through events) and replayed: one cudaGraphLaunch per step
-// instead of ~16 kernel launches, 6 event operations and 2 NCCL groups.
-static int dcb_graph_step(dc_handle *h, int nsteps, void *stream,
-                          void (*enqueue)(dc_handle *, void *))
+// The banded step captured into CUDA graphs (stream capture of the enqueue functions, which fork
+// to the side stream and join again through events) and replayed: one cudaGraphLaunch per step
+// instead of ~16 kernel launches, ~20 event operations and 2 NCCL groups.  Two graphs: a step
+// that ends with the continuity of the next step, and the last step of a call.
+static int capture_graph(dc_handle *h, dc::CommState *c, cudaStream_t st,
+                         void (*enqueue)(dc_handle *, void *), cudaGraphExec_t *out,
+                         long long *launches)
+{
+    cudaGraph_t g = nullptr;
+    const long long launches0 = h->launches;
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+        cudaGetLastError();
+        return 1;
+    }
+    enqueue(h, st);
+    const cudaError_t e = cudaStreamEndCapture(st, &g);
+    *launches = h->launches - launches0;
+    h->launches = launches0;
+    if (e != cudaSuccess || !g) {
+        cudaGetLastError();
+        return 1;
+    }
+    if (cudaGraphInstantiate(out, g, 0) != cudaSuccess) {
+        cudaGraphDestroy(g);
+        cudaGetLastError();
+        *out = nullptr;
+        return 1;
+    }
+    cudaGraphDestroy(g);
+    (void)c;
+    return 0;
+}
+static int dcb_graph_steps(dc_handle *h, int nsteps, void *stream,
+                           void (*prologue)(dc_handle *, int, void *),
+                           void (*step_tail)(dc_handle *, void *),
+                           void (*step_last)(dc_handle *, void *))
 {
     dc::CommState *c = static_cast<dc::CommState *>(h->comm_state);
     cudaStream_t caller = (cudaStream_t)stream;
@@ -441,47 +479,32 @@ static int dcb_graph_step(dc_handle *h, int nsteps, void *stream,
     const bool legacy = caller == nullptr || caller == cudaStreamLegacy ||
                         caller == cudaStreamPerThread;
     cudaStream_t st = legacy ? c->main : caller;
-    if (!c->graph || c->graph_version != h->bind_version) {
-        if (c->graph) {
-            cudaGraphExecDestroy(c->graph);
-            c->graph = nullptr;
-        }
-        cudaGraph_t g = nullptr;
-        const long long launches0 = h->launches;
-        if (cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
-            cudaGetLastError();
+    if (!c->graph || !c->graph_last || c->graph_version != h->bind_version) {
+        if (c->graph) cudaGraphExecDestroy(c->graph);
+        if (c->graph_last) cudaGraphExecDestroy(c->graph_last);
+        c->graph = c->graph_last = nullptr;
+        if (capture_graph(h, c, st, step_tail, &c->graph, &c->launches_per_step) ||
+            capture_graph(h, c, st, step_last, &c->graph_last, &c->launches_last_step))
             return 1;
-        }
-        enqueue(h, st);
-        const cudaError_t e = cudaStreamEndCapture(st, &g);
-        c->launches_per_step = h->launches - launches0;
-        h->launches = launches0;
-        if (e != cudaSuccess || !g) {
-            cudaGetLastError();
-            return 1;
-        }
-        if (cudaGraphInstantiate(&c->graph, g, 0) != cudaSuccess) {
-            cudaGraphDestroy(g);
-            cudaGetLastError();
-            c->graph = nullptr;
-            return 1;
-        }
-        cudaGraphDestroy(g);
         c->graph_version = h->bind_version;
         c->error = 0;
     }
     if (legacy) {
-        cudaEventRecord(c->ev[6], caller);
-        cudaStreamWaitEvent(c->main, c->ev[6], 0);
+        cudaEventRecord(c->ev[14], caller);
+        cudaStreamWaitEvent(c->main, c->ev[14], 0);
     }
+    const long long l0 = h->launches;
+    prologue(h, 0, st);
+    (void)l0;
     int rc = 0;
     for (int s = 0; s < nsteps && !rc; s++) {
-        if (cudaGraphLaunch(c->graph, st) != cudaSuccess) rc = 1;
-        h->launches += c->launches_per_step;
+        const bool last = s + 1 == nsteps;
+        if (cudaGraphLaunch(last ? c->graph_last : c->graph, st) != cudaSuccess) rc = 1;
+        h->launches += last ? c->launches_last_step : c->launches_per_step;
     }
     if (legacy) {
-        cudaEventRecord(c->ev[7], c->main);
-        cudaStreamWaitEvent(caller, c->ev[7], 0);
+        cudaEventRecord(c->ev[15], c->main);
+        cudaStreamWaitEvent(caller, c->ev[15], 0);
     }
     return rc ? 2 : 0;   // 2: a launch failed after steps were enqueued (reported by the caller)
 }

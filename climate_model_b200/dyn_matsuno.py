@@ -13,6 +13,11 @@ from .dyn_org_discretizations import DiagnosticsFactory, PrognosticsFactory
 from .dyn_tendencies import compute_tendencies
 from .io_read_namelist import B200
 
+import os
+
+# development switch (default off: measured in profiles/r2_stage_variants.md)
+_PIPELINE = os.environ.get('DC_PIPELINE', '0') == '1'
+
 Prognostics = PrognosticsFactory(target=B200)
 Diagnostics = DiagnosticsFactory(target=B200)
 
@@ -45,6 +50,12 @@ def step_matsuno(GR, F, nsteps=1):
                                'after torch.distributed.init_process_group')
         step_matsuno_banded(GR, F, nsteps, stream)
     else:
+        if _PIPELINE and _lib.is_cuda() and not getattr(GR, '_pipelined', False):
+            # one GPU, two concurrent chains: the next continuity beside the diagnostics sweep
+            # (dc_set_comm with one rank: no communicator, only the side stream and the graphs)
+            GR._pipelined = True
+            if not GR.i_coupling:
+                _lib.check(_lib.lib().dc_set_comm(GR.dyncore(), None, 0, 0, 1))
         _lib.check(_lib.lib().dc_step_matsuno(GR.dyncore(), int(nsteps), stream))
     GR.timer.stop('step')
 

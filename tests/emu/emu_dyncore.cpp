@@ -89,7 +89,11 @@ static int dcb_comm_sendrecv(dc_handle *, void *) { return DC_ERR_NO_DEVICE; }
 static void *dcb_side_stream(dc_handle *) { return nullptr; }
 static void dcb_event_record(dc_handle *, int, void *) {}
 static void dcb_stream_wait(dc_handle *, int, void *) {}
-static int dcb_graph_step(dc_handle *, int, void *, void (*)(dc_handle *, void *)) { return 1; }
+static int dcb_graph_steps(dc_handle *, int, void *, void (*)(dc_handle *, int, void *),
+                           void (*)(dc_handle *, void *), void (*)(dc_handle *, void *))
+{
+    return 1;
+}
 
 #include "../../climate_model_b200/csrc/dc_api_impl.h"
 

@@ -9,7 +9,22 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 STATE = ['UWIND', 'VWIND', 'POTT', 'COLP', 'QV', 'QC']
 
 # parity tolerances, metric max|a-b|/max|b| over the interior (testsuite.py:48-54 of the
-# reference); SURVEY.md section 8(c): >= 20x the measured 1-ulp-perturbation floor
+# reference); SURVEY.md section 8(c): >= 20x the measured 1-ulp-perturbation floor at 5 deg / 1 deg.
+#
+# 1-ulp-perturbation floor of the reference algorithm ITSELF on the benchmarked shapes (the
+# oracle run twice, U, V, POTT perturbed by +-1 ulp; tools/ulp_floor.py, this round):
+#   shape                        steps  UWIND    VWIND    POTT     COLP     QV
+#   1 deg x 32 (360x168x32)        10   2.3e-11  4.1e-12  1.8e-15  6.4e-16  1.0e-14
+#   1 deg x 32                     50   3.0e-11  8.3e-12  4.3e-15  1.7e-15  1.1e-13
+#   0.25 deg x 64 band 1440x84     10   1.2e-11  1.7e-11  1.9e-15  9.5e-16  3.2e-15
+#   0.25 deg x 64 band 1440x84     50   1.0e-10  8.0e-11  6.5e-15  2.3e-15  1.5e-14
+#   0.1 deg x 96 band 3600x32      10   4.3e-11  4.0e-11  4.2e-15  1.1e-15  8.0e-15
+# and the CUDA builds against the oracle on the same shapes (tests/test_gpu_bench_shapes.py,
+# profiles/r2_parity_bench_shapes.json), 0.25 deg band after 50 steps: production UWIND 1.1e-10,
+# VWIND 9.6e-11, POTT 7.7e-15, COLP 4.8e-15; strict 7.6e-11, 8.2e-11, 4.4e-15, 2.2e-15 -- both
+# builds sit AT the floor: no implementation of this scheme can be closer to the reference.  At
+# 0.25 deg the wind tolerance is therefore 10x the floor (not 20x as on the coarse grids); it is
+# kept at 1e-9 because every case passes it with that margin.
 TOL = {'UWIND': 1e-9, 'VWIND': 1e-9, 'POTT': 1e-12, 'COLP': 1e-12, 'QV': 1e-11, 'QC': 1e-11}
 
 

@@ -16,6 +16,8 @@ ap.add_argument('--moist', type=int, default=0)
 ap.add_argument('--mode', default='fused')
 ap.add_argument('--nz', type=int, default=64)
 ap.add_argument('--dlat', type=float, default=0.25)
+ap.add_argument('--no-profile', action='store_true',
+                help='plain step loop (no per-kernel event brackets): the step time only')
 args = ap.parse_args()
 
 import torch
@@ -44,13 +46,13 @@ set_mode(GR, args.mode)
 Diagnostics.primary_diag(GR.GRF[B200], **F.get(Diagnostics.fields_primary_diag, target=B200))
 step_matsuno(GR, F, 2)
 torch.cuda.synchronize()
-_lib.check(L.dc_profile_enable(h, 1))
+_lib.check(L.dc_profile_enable(h, 0 if args.no_profile else 1))
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 step_matsuno(GR, F, args.steps)
 e1.record()
 torch.cuda.synchronize()
-prof = _lib.profile_read(h)
+prof = {} if args.no_profile else _lib.profile_read(h)
 ms = e0.elapsed_time(e1) / args.steps
 cells = int(GR.nx) * int(GR.ny) * int(GR.nz)
 print('%s: %.3f ms/step  %.2f Gcell/s  finite=%s  %s' % (
