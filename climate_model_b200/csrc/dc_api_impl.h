@@ -31,7 +31,7 @@
 //   void dcb_comm_release(dc_handle *h);
 //   double *dcb_comm_buffer(dc_handle *h, int which);   // 0 send_s, 1 recv_s, 2 send_n, 3 recv_n
 //   int  dcb_comm_sendrecv(dc_handle *h, void *stream); // grouped send/recv with both neighbours
-//   void *dcb_side_stream(dc_handle *h);
+//   void *dcb_side_stream(dc_handle *h, int which = 0);
 //   void dcb_event_record(dc_handle *h, int ev, void *stream);
 //   void dcb_stream_wait(dc_handle *h, int ev, void *stream);
 //   int  dcb_graph_steps(dc_handle *h, int nsteps, void *stream,
@@ -1203,7 +1203,8 @@ int dc_halo_exchange(dc_handle *h, int stage, void *stream)
                      north ? dcb_comm_buffer(h, 3) : nullptr, 0, stream, "dc_halo_exchange");
 }
 
-enum { EV_START = 0, EV_CONT = 1, EV_BDONE = 2, EV_MOIST = 3, EV_COLP = 4, EV_DIAG = 5, EV_JOIN = 6 };
+enum { EV_START = 0, EV_CONT = 1, EV_BDONE = 2, EV_MOIST = 3, EV_COLP = 4, EV_DIAG = 5, EV_JOIN = 6,
+       EV_UNPACK = 7, EV_HDIAG = 8, EV_JOIN2 = 9 };
 
 // continuity (+ COLP_OLD <- COLP before a step's first stage) of stage `stage`
 static void enqueue_continuity(dc_handle *h, int stage, void *st)
@@ -1219,7 +1220,9 @@ static void enqueue_continuity(dc_handle *h, int stage, void *st)
 //   M: [moisture stage] -> stage kernel on the interior tile rows -> COLP <- COLP_NEW ->
 //      diagnostics of the rows that need no neighbour data
 //   S: stage kernel on the first and last tile row -> pack -> NCCL send/recv with both
-//      neighbours -> unpack -> CONTINUITY OF THE NEXT STAGE -> diagnostics of the halo rows
+//      neighbours -> unpack -> CONTINUITY OF THE NEXT STAGE
+//   T: (third stream) diagnostics of the halo rows, after the unpack -- a launch as long as one
+//      thread's march up the column (~70 us), which would otherwise delay S's next boundary rows
 // The exchange hides behind the interior tile rows; the next continuity (needs the new U, V,
 // COLP incl. halos, nothing of the diagnostics) and the halo-row diagnostics run beside the
 // own-row diagnostics (needs the new POTT, COLP of the own rows).  Measured on two B200 with
@@ -1231,7 +1234,7 @@ static void enqueue_continuity(dc_handle *h, int stage, void *st)
 static void enqueue_band_step(dc_handle *h, void *M, int tail)
 {
     const Geom &g = h->g;
-    void *S = dcb_side_stream(h);
+    void *S = dcb_side_stream(h), *T = dcb_side_stream(h, 1);
     const bool single = h->comm_nranks == 1;
     const bool south = h->comm_rank > 0, north = h->comm_rank < h->comm_nranks - 1;
     const int lo = g.j0 - HJ < 0 ? 0 : g.j0 - HJ, hi = g.j1 + HJ > g.ny + 1 ? g.ny + 1 : g.j1 + HJ;
@@ -1254,7 +1257,10 @@ static void enqueue_band_step(dc_handle *h, void *M, int tail)
         DC_MARK("M interior done", M);
         // ---- S: boundary tile rows, pack, exchange
         if (!single) {
-            if (stage == 1) dcb_stream_wait(h, EV_DIAG, S);
+            if (stage == 1) {
+                dcb_stream_wait(h, EV_DIAG, S);      // PHI, PGCOL, POTTVB of the own rows (M)
+                dcb_stream_wait(h, EV_HDIAG, S);     // ... and of the halo rows (T)
+            }
             DC_MARK("S boundary begin", S);
             do_stage_fused(h, stage, DC_PART_BOUNDARY, S);
             DC_MARK("S boundary done", S);
@@ -1278,6 +1284,8 @@ static void enqueue_band_step(dc_handle *h, void *M, int tail)
         if (!single) {
             halo_move(h, stage, south ? dcb_comm_buffer(h, 1) : nullptr,
                       north ? dcb_comm_buffer(h, 3) : nullptr, 0, S, "dc_step_matsuno");
+            dcb_event_record(h, EV_UNPACK, S);
+            dcb_stream_wait(h, EV_UNPACK, T);
             DC_MARK("S unpack done", S);
         }
         if (next) {
@@ -1286,13 +1294,18 @@ static void enqueue_band_step(dc_handle *h, void *M, int tail)
             DC_MARK("S next continuity done", S);
         }
         if (!single) {
-            do_diag_rows(h, stage, lo, hi, S, own_lo, own_hi);   // both halo ranges, one launch
-            DC_MARK("S halo-row diag done", S);
+            do_diag_rows(h, stage, lo, hi, T, own_lo, own_hi);   // both halo ranges, one launch
+            dcb_event_record(h, EV_HDIAG, T);
+            DC_MARK("T halo-row diag done", T);
         }
     }
 #undef DC_MARK
-    dcb_event_record(h, EV_JOIN, S);                 // the step ends when both chains have
+    dcb_event_record(h, EV_JOIN, S);                 // the step ends when all chains have
     dcb_stream_wait(h, EV_JOIN, M);
+    if (!single) {
+        dcb_event_record(h, EV_JOIN2, T);
+        dcb_stream_wait(h, EV_JOIN2, M);
+    }
 }
 static void enqueue_band_step_tail(dc_handle *h, void *M) { enqueue_band_step(h, M, 1); }
 static void enqueue_band_step_last(dc_handle *h, void *M) { enqueue_band_step(h, M, 0); }

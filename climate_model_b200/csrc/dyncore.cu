@@ -242,7 +242,7 @@ static int dcb_comm_init(dc_handle *h, const void *id128, int rank, int nranks, 
 static void dcb_comm_release(dc_handle *h);
 static double *dcb_comm_buffer(dc_handle *h, int which);
 static int dcb_comm_sendrecv(dc_handle *h, void *stream);
-static void *dcb_side_stream(dc_handle *h);
+static void *dcb_side_stream(dc_handle *h, int which = 0);
 static void dcb_event_record(dc_handle *h, int ev, void *stream);
 static void dcb_stream_wait(dc_handle *h, int ev, void *stream);
 static int dcb_graph_steps(dc_handle *h, int nsteps, void *stream,
@@ -308,7 +308,7 @@ struct CommState {
     int rank = 0, nranks = 1;
     size_t nelem = 0;
     double *buf[4] = {nullptr, nullptr, nullptr, nullptr};   // send_s, recv_s, send_n, recv_n
-    cudaStream_t side = nullptr;
+    cudaStream_t side = nullptr, side2 = nullptr;
     cudaStream_t main = nullptr;   // stands in for the caller's stream when that is the legacy
                                    // default stream, which cannot be captured
     cudaEvent_t ev[16] = {};
@@ -359,6 +359,7 @@ static int dcb_comm_init(dc_handle *h, const void *id128, int rank, int nranks, 
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);   // hi = numerically lowest = highest priority
     cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, hi);
+    cudaStreamCreateWithPriority(&c->side2, cudaStreamNonBlocking, hi);
     cudaStreamCreateWithFlags(&c->main, cudaStreamNonBlocking);
     for (auto &ev : c->ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     for (int n = 0; n < 4; n++) {
@@ -385,6 +386,7 @@ static void dcb_comm_release(dc_handle *h)
     for (auto &ev : c->ev)
         if (ev) cudaEventDestroy(ev);
     if (c->side) cudaStreamDestroy(c->side);
+    if (c->side2) cudaStreamDestroy(c->side2);
     if (c->main) cudaStreamDestroy(c->main);
     if (c->comm) {
         dc::NcclApi *a = dc::nccl_api();
@@ -419,9 +421,10 @@ static int dcb_comm_sendrecv(dc_handle *h, void *stream)
     h->launches++;
     return 0;
 }
-static void *dcb_side_stream(dc_handle *h)
+static void *dcb_side_stream(dc_handle *h, int which)
 {
-    return static_cast<dc::CommState *>(h->comm_state)->side;
+    dc::CommState *c = static_cast<dc::CommState *>(h->comm_state);
+    return which ? c->side2 : c->side;
 }
 static void dcb_event_record(dc_handle *h, int ev, void *stream)
 {

@@ -86,7 +86,7 @@ static int dcb_comm_init(dc_handle *, const void *, int, int, size_t) { return D
 static void dcb_comm_release(dc_handle *) {}
 static double *dcb_comm_buffer(dc_handle *, int) { return nullptr; }
 static int dcb_comm_sendrecv(dc_handle *, void *) { return DC_ERR_NO_DEVICE; }
-static void *dcb_side_stream(dc_handle *) { return nullptr; }
+static void *dcb_side_stream(dc_handle *, int = 0) { return nullptr; }
 static void dcb_event_record(dc_handle *, int, void *) {}
 static void dcb_stream_wait(dc_handle *, int, void *) {}
 static int dcb_graph_steps(dc_handle *, int, void *, void (*)(dc_handle *, int, void *),
