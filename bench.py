@@ -43,12 +43,12 @@ WORKLOADS = {
     # BASELINE.json configs[4], WEAK scaling: every rank holds 210 latitude rows of the 0.1 deg
     # grid (72.6 M cells, the per-rank share of the full 3600 x 1680 x 96 grid on 8 GPUs), so
     # N ranks cover lat +-10.5 N deg and N = 8 is the whole configs[4] grid (lat +-84 deg).
-    # Every rank builds the whole grid's initial state on the host before keeping its band:
-    # ~30 GB of host memory per rank at N = 8.
+    # Every rank builds and keeps only its own rows (ModelFields(band_local=True)); dt = the
+    # full grid's 2 s at every N.
     'cfg5': dict(name='0.1deg x 96 levels, synthetic initial state, 210 rows per GPU (weak scaling; '
                       'N = 8 is the full 3600 x 1680 x 96 grid)',
                  grid=dict(nz=96, lat0_deg=-10.5, lat1_deg=10.5, dlat_deg=0.1, dlon_deg=0.1,
-                           i_out_nth_hour=1.0), ic=dict(i_use_topo=0), weak=True),
+                           i_out_nth_hour=1.0, dt=2), ic=dict(i_use_topo=0), weak=True),
     # development proxy (not a BASELINE config): two ranks of this grid each hold the 84 rows a
     # rank of cfg4 holds at N = 8
     'cfg4_band8x2': dict(name='0.25deg x 64 levels, +-21 deg (2 x 84 rows: per-rank size of cfg4 at N = 8)',

@@ -234,7 +234,7 @@ def _bc_window(GR, F, ja, jb, stgx, stgy):
     return F
 
 
-def initialize_fields_band(GR, host, rows_of, **pert):
+def initialize_fields_band(GR, host, rows_of, diagnostics=True, **pert):
     """initialize_fields for ONE latitude band: `host[n]` holds the rows rows_of(n) = (ja, jb)
     of field n only, shape (fnx, jb-ja+1, nk).  Everything 2-D (topography, its smoothing, the
     surface pressure, COLP and its perturbations, the random-number draws) is built for the
@@ -330,15 +330,20 @@ def initialize_fields_band(GR, host, rows_of, **pert):
     QC = np.full_like(POTT, np.nan)
     QC[np.ix_(i, j - ja)] = 0.
     host['QC'][...] = _bc_window(GR, QC, ja, jb, 0, 0)
-    for n, a in (('PVTF', PVTF1), ('PVTFVB', PVTFVB1)):
-        out = host[n]
-        out[...] = np.nan
-        out[np.ix_(i, j - ja)] = a
+    if diagnostics:
+        # PVTF / PVTFVB of the initial state and the zeros of POTTVB / WWIND
+        # (io_initial_conditions.py:45-46): the device recomputes / already holds them, so a
+        # band-local run skips these four host arrays (0.6 GB each at 0.1 deg x 96 levels)
+        for n, a in (('PVTF', PVTF1), ('PVTFVB', PVTFVB1)):
+            out = host[n]
+            out[...] = np.nan
+            out[np.ix_(i, j - ja)] = a
+        host['POTTVB'][...] = 0.
+        host['WWIND'][...] = 0.
+    del PVTF0, PVTF1, PVTFVB1, PAIR, PAIR1, TAIR, TAIR1, POTT_in, QV, QC
     for n in ('COLP', 'HSURF'):
         ja2, jb2 = rows_of(n)
         host[n][...] = (COLP if n == 'COLP' else HSURF)[:, ja2:jb2 + 1]
-    host['POTTVB'][...] = 0.
-    host['WWIND'][...] = 0.
 
     # ---- UWIND (x-staggered) -------------------------------------------------------------------
     ja, jb, j0, j1 = window('UWIND')

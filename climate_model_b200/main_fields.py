@@ -88,7 +88,9 @@ class ModelFields:
         if gpu_enable and _lib.is_cuda() and self.torch_device.type != 'cuda':
             raise RuntimeError('libdyncore runs on CUDA devices only; there is no CPU fallback')
         if initialize and self.band_local:
-            initialize_fields_band(GR, self.host, self._rows_of(GR), **ic_overrides)
+            # (device POTTVB / WWIND start as zeros, PVTF / PVTFVB are diagnostics: no host copies)
+            initialize_fields_band(GR, self.host, self._rows_of(GR),
+                                   diagnostics=not gpu_enable, **ic_overrides)
         elif initialize:
             initialize_fields(GR, self.host, **ic_overrides)
         self._bound = {}
