@@ -837,15 +837,22 @@ struct PrimaryDiagBody {
         double svb_kp1 = g.sigma_vb[nz];
         // POTT of the next level is requested one iteration ahead: its latency hides behind the
         // exp / log / division chain of the current level (ncu: 60 % of the stalls were this load)
-        double pott_next[NC];
-        for (int c = 0; c < NC; c++) pott_next[c] = POTT[o[c] - plane];
+        // (round 2: with the table-driven Exner power a level is shorter than a DRAM round trip,
+        // ncu showed 64 % of the stalls on this load again: three levels ahead now)
+        constexpr int PF = 3;
+        double pott_q[NC][PF];
+        for (int c = 0; c < NC; c++)
+            for (int n = 0; n < PF; n++)
+                pott_q[c][n] = nz - 1 - n >= 0 ? POTT[o[c] - (size_t)(n + 1) * plane] : 0.;
         for (int k = nz - 1; k >= 0; k--) {
             const double svb = g.sigma_vb[k];
             const Div ds = mkdiv(g.dsigma[k], g.r_dsigma[k]);
             for (int c = 0; c < NC; c++) {
                 o[c] -= plane;
-                const double pott = pott_next[c];
-                if (k > 0) pott_next[c] = POTT[o[c] - plane];
+                const double pott = pott_q[c][0];
+#pragma unroll
+                for (int n = 0; n + 1 < PF; n++) pott_q[c][n] = pott_q[c][n + 1];
+                if (k - PF >= 0) pott_q[c][PF - 1] = POTT[o[c] - (size_t)PF * plane];
                 const double p_km12 = g.pair_top + svb * colp[c];
                 const double pw_km12 = exner(p_km12);
                 const double pvtf = fdiv(1. / (1. + con_kappa) *

@@ -32,6 +32,7 @@ struct alignas(128) Moist3Smem {
     double lev[3][NZMAX + 1];       // dsigma, 1/dsigma, moist_dif_coef
     double dxr[S3_SH + 1];          // dxjs of the staged rows
     double rowA[2][S3_TY + 1];      // A, 1/A of the tile rows
+    double ltab[POW_NJ][2];         // log_tab's table (dc_point.h)
     unsigned long long full[S3_NBUF];
 };
 
@@ -80,11 +81,11 @@ struct Moist3Body {
     }
 
     // clamped value, its logarithm and reciprocal (comp_VARVB_log, dyn_functions.py:70-95)
-    DC_HD void clr(double q, double *qc, double *lq, double *rq) const
+    DC_HD void clr(const Moist3Smem &s, double q, double *qc, double *lq, double *rq) const
     {
         const double min_val = 0.0000001;
         *qc = fmax(q, min_val);
-        *lq = DC_FAST ? log_tab(*qc, lc) : log(*qc);
+        *lq = DC_FAST ? log_tab(*qc, lc, s.ltab) : log(*qc);
         *rq = DC_FAST ? dc_rcp(*qc) : 1. / *qc;
     }
 
@@ -126,6 +127,10 @@ struct Moist3Body {
             if (tid == 0) {
                 for (int n = 0; n < S3_NBUF; n++) s3_mbar_init(&s.full[n], 1);
                 s3_mbar_init_fence();
+            }
+            for (int n = tid; n < POW_NJ; n += S3_NT) {   // the set-up below already takes logs
+                s.ltab[n][0] = lc.tab[n][0];
+                s.ltab[n][1] = lc.tab[n][1];
             }
         S3_PHASE_END
         S3_PHASE
@@ -178,7 +183,7 @@ struct Moist3Body {
                         // state of interface ks: formed from levels ks - 1 and ks by the warm-up
                         // level of a chunk; at the model top the interface value is never used
                         const double q = Q_in[t][(size_t)ks * plane + S3_P(off0) + e];
-                        clr(q, &S3_P(qc)[t][e], &S3_P(lq)[t][e], &S3_P(rq)[t][e]);
+                        clr(s, q, &S3_P(qc)[t][e], &S3_P(lq)[t][e], &S3_P(rq)[t][e]);
                         S3_P(qvb)[t][e] = q;
                     }
                 }
@@ -266,7 +271,7 @@ struct Moist3Body {
                                 qc1 = fmax(q_kp1[e], min_val);
                                 lq1 = S3_P(lq)[t][e]; rq1 = S3_P(rq)[t][e]; qvb1 = qc1;
                                 if (qc1 != S3_P(qc)[t][e]) {
-                                    clr(q_kp1[e], &qc1, &lq1, &rq1);
+                                    clr(s, q_kp1[e], &qc1, &lq1, &rq1);
                                     const double num = S3_P(lq)[t][e] - lq1, den = rq1 - S3_P(rq)[t][e];
                                     qvb1 = DC_FAST ? num * dc_rcp(den) : (num / den);
                                 }

@@ -413,17 +413,21 @@ inline LogCoef make_log_coef()
     }
     return L;
 }
-DC_HD double log_tab(double x, const LogCoef &L)
+// `tab` = L.tab or a copy of it in shared memory: a constant-bank read with a per-thread index is
+// replayed once per distinct address (ncu: 45 % of the moisture kernel's stalls), a shared-memory
+// read is not
+DC_HD double log_tab(double x, const LogCoef &L, const double (*tab)[2])
 {
     const int hi = dc_hi_word(x);
     const int e = (hi >> 20) - 1023;
     const int j = (hi >> (20 - POW_JBITS)) & (POW_NJ - 1);
     const double m = dc_from_words((hi & 0x000fffff) | 0x3ff00000, dc_lo_word(x));
-    const double t = dc_fma(m, L.tab[j][0], -1.);
+    const double r = tab[j][0], lm = tab[j][1];
+    const double t = dc_fma(m, r, -1.);
     double p = L.c[8];
     for (int n = 7; n >= 1; n--) p = dc_fma(p, t, L.c[n]);
     const double de = (double)e;
-    return dc_fma(de, L.ln2_hi, L.tab[j][1] + dc_fma(de, L.ln2_lo, p * t));
+    return dc_fma(de, L.ln2_hi, lm + dc_fma(de, L.ln2_lo, p * t));
 }
 
 // ---------------------------------------------------------------------------------------
