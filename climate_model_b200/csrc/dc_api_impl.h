@@ -1246,16 +1246,14 @@ static void enqueue_band_step(dc_handle *h, void *M, int tail)
     dcb_stream_wait(h, EV_START, S);
     for (int stage = 0; stage < 2; stage++) {
         const bool next = stage == 0 || tail;        // a continuity follows this stage
-        // ---- M: moisture, interior tile rows
+        // ---- S first: boundary tile rows (what the neighbours wait for; enqueued BEFORE the
+        //      interior launch so that its blocks get the first free slots), pack, exchange
         if (stage == 1) dcb_stream_wait(h, EV_CONT, M);
         if (g.i_moist) {
             do_stage_fused(h, stage, DC_PART_MOIST, M);
             dcb_event_record(h, EV_MOIST, M);
             DC_MARK("M moisture done", M);
         }
-        do_stage_fused(h, stage, single ? (int)DC_PART_STAGE_ALL : (int)DC_PART_INTERIOR, M);
-        DC_MARK("M interior done", M);
-        // ---- S: boundary tile rows, pack, exchange
         if (!single) {
             if (stage == 1) {
                 dcb_stream_wait(h, EV_DIAG, S);      // PHI, PGCOL, POTTVB of the own rows (M)
@@ -1265,6 +1263,11 @@ static void enqueue_band_step(dc_handle *h, void *M, int tail)
             do_stage_fused(h, stage, DC_PART_BOUNDARY, S);
             DC_MARK("S boundary done", S);
             dcb_event_record(h, EV_BDONE, S);
+        }
+        // ---- M: interior tile rows
+        do_stage_fused(h, stage, single ? (int)DC_PART_STAGE_ALL : (int)DC_PART_INTERIOR, M);
+        DC_MARK("M interior done", M);
+        if (!single) {
             if (g.i_moist) dcb_stream_wait(h, EV_MOIST, S);
             halo_move(h, stage, south ? dcb_comm_buffer(h, 0) : nullptr,
                       north ? dcb_comm_buffer(h, 2) : nullptr, 1, S, "dc_step_matsuno");

@@ -837,9 +837,10 @@ struct PrimaryDiagBody {
         double svb_kp1 = g.sigma_vb[nz];
         // POTT of the next level is requested one iteration ahead: its latency hides behind the
         // exp / log / division chain of the current level (ncu: 60 % of the stalls were this load)
-        // (round 2: with the table-driven Exner power a level is shorter than a DRAM round trip,
-        // ncu showed 64 % of the stalls on this load again: three levels ahead now)
-        constexpr int PF = 3;
+        // (round 2, with the table-driven Exner power: requesting three levels ahead instead of
+        // one measured 2 % SLOWER, 0.985 against 0.967 ms per step -- the sweep waits on the
+        // table lookup of its own level, not on POTT)
+        constexpr int PF = 1;
         double pott_q[NC][PF];
         for (int c = 0; c < NC; c++)
             for (int n = 0; n < PF; n++)

@@ -77,13 +77,23 @@ __global__ void __launch_bounds__(NT, DC_MINBLOCKS) k_stage(const StageBody b)
     b.run_block(blockIdx.x, blockIdx.y, *reinterpret_cast<StageSmem *>(stage_smem));
 }
 }  // namespace dc
+// cudaFuncSetAttribute is per device: remember which devices a kernel has been configured on
+static bool first_use_on_device(unsigned long long *mask)
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (*mask & bit) return false;
+    *mask |= bit;
+    return true;
+}
 static void dcb_launch_stage(const dc::StageBody &b, int nbx, int nby, void *stream)
 {
-    static bool configured = false;
+    static unsigned long long done = 0;
+    const bool configured = !first_use_on_device(&done);
     if (!configured) {
         cudaFuncSetAttribute(dc::k_stage, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)sizeof(dc::StageSmem));
-        configured = true;
     }
     dc::k_stage<<<dim3(nbx, nby), dim3(dc::TX, dc::TY), sizeof(dc::StageSmem),
                   (cudaStream_t)stream>>>(b);
@@ -625,12 +635,12 @@ static void dcb_launch_stage3(dc_handle *h, dc::Stage3Body &b, const dc::Stage3P
                               int nby, void *stream)
 {
     using namespace dc;
-    static bool configured = false;
+    static unsigned long long done = 0;
+    const bool configured = !first_use_on_device(&done);
     const int smem = (int)sizeof(Stage3Smem) + 128;
     if (!configured) {
         cudaFuncSetAttribute(k_stage3, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         cudaFuncSetAttribute(k_stage3, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        configured = true;
     }
     const int nz = h->g.nz;
     struct { CUtensorMap *dst; const double *base; int nk; bool own; } want[] = {
@@ -650,12 +660,12 @@ static void dcb_launch_moist3(dc_handle *h, dc::Moist3Body &b, const dc::Moist3P
                               int nby, void *stream)
 {
     using namespace dc;
-    static bool configured = false;
+    static unsigned long long done = 0;
+    const bool configured = !first_use_on_device(&done);
     const int smem = (int)sizeof(Moist3Smem) + 128;
     if (!configured) {
         cudaFuncSetAttribute(k_moist3, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         cudaFuncSetAttribute(k_moist3, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        configured = true;
     }
     const int nz = h->g.nz;
     struct { CUtensorMap *dst; const double *base; int nk; bool own; } want[] = {

@@ -56,15 +56,16 @@ def diagnose_print_diag_fields(GR, F):
             float(maxs[1]), nans)
 
 
-def print_ts_info(GR, F, force=False):
+def print_ts_info(GR, F, force=False, quiet=False):
     """io_functions.py:95-135: the diagnostics line every nth_ts_print_diag steps and the crash
-    check (NaN in UWIND or UWIND > 500 m/s -> ValueError('MODEL CRASH'))"""
+    check (NaN in UWIND or UWIND > 500 m/s -> ValueError('MODEL CRASH')); `quiet` only suppresses
+    the line, never the check (the reference checks unconditionally)"""
     if not force and GR.ts % nl.nth_ts_print_diag != 0:
         return None
     GR.timer.start('diag')
     vmax, mean_wind, mean_temp, mean_colp, umax, nans = diagnose_print_diag_fields(GR, F)
     GR.timer.stop('diag')
-    if GR.band[0] == 0:
+    if GR.band[0] == 0 and not quiet:
         print(str(GR.ts) + '  ' + str(np.round(GR.sim_time_sec / 3600 / 24, 3)) + '\t days' +
               ' vmax: ' + str(np.round(vmax, 1)) + '  m/s vmean: ' + str(np.round(mean_wind, 3)) +
               ' m/s Tmean: ' + str(np.round(mean_temp, 7)) + '  K  COLP: ' +

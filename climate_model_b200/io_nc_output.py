@@ -40,6 +40,13 @@ _PROFILES = ['UWIND', 'VWIND', 'WWIND', 'VORT', 'POTT', 'TAIR', 'QV', 'QC']
 
 
 def _wanted(F, name, fields):
+    # the fused stepper forms the fluxes / tendencies of the reference's kernel decomposition in
+    # registers and never stores them: such a field (dQVdt is in the default selection) is left
+    # out of the file instead of being written as zeros; set_mode(GR, 'kernels') produces them
+    GR = F._GR_ref() if getattr(F, '_GR_ref', None) else None
+    if (name in F.KERNEL_MODE_ONLY and GR is not None and not GR.i_coupling and
+            getattr(GR, '_mode', 'fused') == 'fused'):
+        return 0
     return fields.get(name, 0) and (name in F.device or name in ('PSURF', 'VORT', 'WVP', 'CWP'))
 
 

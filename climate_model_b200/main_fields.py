@@ -174,8 +174,10 @@ class ModelFields:
         return rows
 
     def to_device(self, GR, n):
-        """host (i, j, k) -> device F[k][jd][i]: one contiguous H2D copy (asynchronous when the
-        host array is pinned) + an on-device tiled transpose (dc_import_field)"""
+        """host (i, j, k) -> device F[k][jd][i]: one contiguous H2D copy + an on-device tiled
+        transpose (dc_import_field).  The copy from a pinned host array is asynchronous on the
+        current stream: do not modify F.host[n] before the stream has passed it (any later
+        to_host / synchronize does)"""
         h = self.host[n]
         bind_all(GR, self)
         if self.band_local:
@@ -208,10 +210,18 @@ class ModelFields:
             if self.torch_device.type == 'cuda':
                 torch.cuda.current_stream(self.torch_device).synchronize()
             return
+        if GR.band[1] > 1:
+            # only the rows this rank holds cross the bus (dc_export_rows); the rows of the other
+            # ranks keep their host values
+            ja, jb = self._rows_of(GR)(n)
+            fnx, _, nk = h.shape
+            st = self._stage(fnx * (jb - ja + 1) * nk)
+            _lib.check(_lib.lib().dc_export_rows(GR.dyncore(), self.table[n][0], st.data_ptr(),
+                                                 st.numel() * 8, ja, jb, self._stream()))
+            h[:, ja:jb + 1, :] = st.view(fnx, jb - ja + 1, nk).cpu().numpy()
+            return
         dst = torch.from_numpy(h).view(-1)
         st = self._stage(dst.numel())
-        if GR.band[1] > 1:
-            st.copy_(dst, non_blocking=True)      # rows of other ranks keep their host values
         _lib.check(_lib.lib().dc_export_field(GR.dyncore(), self.table[n][0], st.data_ptr(),
                                               st.numel() * 8, self._stream()))
         dst.copy_(st, non_blocking=True)

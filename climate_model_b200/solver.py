@@ -51,7 +51,7 @@ def run(nsteps=None, verbose=True, ic=None, i_turbulence=None, output_path=None,
     if i_turbulence:
         overrides.setdefault('i_coupling', 1)
     band = init_bands()                           # (0, 1) unless launched by torchrun
-    diag = verbose                                # collective with bands: every rank calls it
+    quiet = not verbose                           # the crash check runs whatever `verbose` is
     verbose = verbose and band[0] == 0
     if i_load_from_restart:                       # main_grid.py:88-90, main_fields.py:61-62
         GR = load_restart_grid(overrides.get('dlat_deg', nl.dlat_deg),
@@ -76,8 +76,7 @@ def run(nsteps=None, verbose=True, ic=None, i_turbulence=None, output_path=None,
         GR.timer.start('total')
         GR.ts += 1
         GR.sim_time_sec = GR.ts * GR.dt
-        if diag:
-            print_ts_info(GR, F, force=(GR.ts == 1))
+        print_ts_info(GR, F, force=(GR.ts == 1), quiet=quiet)   # collective with bands
         GR.timer.start('diag')
         Diagnostics.secondary_diag(**F.get(Diagnostics.fields_secondary_diag, target=B200))
         GR.timer.stop('diag')
@@ -101,8 +100,7 @@ def run(nsteps=None, verbose=True, ic=None, i_turbulence=None, output_path=None,
         GR.timer.stop('total')
     if F.torch_device.type == 'cuda':
         torch.cuda.synchronize()
-    if diag:
-        print_ts_info(GR, F, force=True)
+    print_ts_info(GR, F, force=True, quiet=quiet)
     if verbose:
         cells = int(GR.nx) * int(GR.ny) * int(GR.nz)
         dt = time.time() - t0
