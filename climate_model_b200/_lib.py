@@ -24,6 +24,7 @@ COUPLING_ONLY_FIELDS = ['KMOM', 'KHEAT', 'SMOMXFLX', 'SMOMYFLX', 'SSHFLX', 'SLHF
                         'dPOTTdt_TURB', 'dQVdt_TURB', 'dPOTTdt_RAD']
 DC_MODE_FUSED, DC_MODE_KERNELS = 0, 1
 DC_COMM_ID_BYTES = 128
+DC_P2P_HANDLE_BYTES = 256
 DC_PART_ALL, DC_PART_CONT, DC_PART_BOUNDARY, DC_PART_INTERIOR, DC_PART_COLP = 0, 1, 2, 3, 4
 
 
@@ -77,6 +78,8 @@ def _declare(lib):
     lib.dc_comm_unique_id.argtypes = [vp, ctypes.c_size_t]
     lib.dc_set_comm.argtypes = [vp, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int]
     lib.dc_has_comm.argtypes = [vp]
+    lib.dc_comm_p2p_handles.argtypes = [vp, vp, ctypes.c_size_t]
+    lib.dc_comm_p2p_connect.argtypes = [vp, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t]
     lib.dc_halo_exchange.argtypes = [vp, ctypes.c_int, vp]
     lib.dc_run_diag_bytes.argtypes = [vp, ctypes.POINTER(ctypes.c_size_t)]
     lib.dc_run_diag.argtypes = [vp, vp, ctypes.c_size_t, vp]

@@ -29,8 +29,11 @@
 //   int  dcb_comm_unique_id(void *id128);
 //   int  dcb_comm_init(dc_handle *h, const void *id128, int rank, int nranks, size_t halo_elems);
 //   void dcb_comm_release(dc_handle *h);
-//   double *dcb_comm_buffer(dc_handle *h, int which);   // 0 send_s, 1 recv_s, 2 send_n, 3 recv_n
-//   int  dcb_comm_sendrecv(dc_handle *h, void *stream); // grouped send/recv with both neighbours
+//   double *dcb_comm_buffer(dc_handle *h, int which, int stage);   // 0 send_s, 1 recv_s, 2 send_n, 3 recv_n
+//   int  dcb_comm_sendrecv(dc_handle *h, int stage, void *stream); // exchange with both neighbours
+//   void dcb_comm_consumed(dc_handle *h, int stage, void *stream); // after the unpack of `stage`
+//   int  dcb_comm_p2p_handles(dc_handle *h, void *out);  int dcb_comm_p2p_connect(dc_handle *h,
+//        const void *south, const void *north);          // peer-memory exchange (CUDA IPC)
 //   void *dcb_side_stream(dc_handle *h, int which = 0);
 //   void dcb_event_record(dc_handle *h, int ev, void *stream);
 //   void dcb_stream_wait(dc_handle *h, int ev, void *stream);
@@ -1194,13 +1197,38 @@ int dc_halo_exchange(dc_handle *h, int stage, void *stream)
     if (!h->comm_state) return fail(DC_ERR_STATE, "dc_halo_exchange: no communicator (dc_set_comm)");
     const bool south = h->comm_rank > 0, north = h->comm_rank < h->comm_nranks - 1;
     int rc;
-    if ((rc = halo_move(h, stage, south ? dcb_comm_buffer(h, 0) : nullptr,
-                        north ? dcb_comm_buffer(h, 2) : nullptr, 1, stream, "dc_halo_exchange")))
+    if ((rc = halo_move(h, stage, south ? dcb_comm_buffer(h, 0, stage) : nullptr,
+                        north ? dcb_comm_buffer(h, 2, stage) : nullptr, 1, stream, "dc_halo_exchange")))
         return rc;
-    const int e = dcb_comm_sendrecv(h, stream);
+    const int e = dcb_comm_sendrecv(h, stage, stream);
     if (e) return fail(e, "dc_halo_exchange: %s", dcb_comm_error());
-    return halo_move(h, stage, south ? dcb_comm_buffer(h, 1) : nullptr,
-                     north ? dcb_comm_buffer(h, 3) : nullptr, 0, stream, "dc_halo_exchange");
+    rc = halo_move(h, stage, south ? dcb_comm_buffer(h, 1, stage) : nullptr,
+                   north ? dcb_comm_buffer(h, 3, stage) : nullptr, 0, stream, "dc_halo_exchange");
+    dcb_comm_consumed(h, stage, stream);
+    return rc;
+}
+
+int dc_comm_p2p_handles(dc_handle *h, void *out, size_t nbytes)
+{
+    if (!h || !out || nbytes < DC_P2P_HANDLE_BYTES)
+        return fail(DC_ERR_ARG, "dc_comm_p2p_handles: need a %d-byte buffer", DC_P2P_HANDLE_BYTES);
+    if (!h->comm_state) return fail(DC_ERR_STATE, "dc_comm_p2p_handles: no communicator");
+    const int e = dcb_comm_p2p_handles(h, out);
+    if (e) return fail(e, "dc_comm_p2p_handles: %s", dcb_comm_error());
+    return DC_OK;
+}
+
+int dc_comm_p2p_connect(dc_handle *h, const void *south, const void *north, size_t nbytes)
+{
+    if (!h || nbytes < DC_P2P_HANDLE_BYTES) return fail(DC_ERR_ARG, "dc_comm_p2p_connect: bad argument");
+    if (!h->comm_state) return fail(DC_ERR_STATE, "dc_comm_p2p_connect: no communicator");
+    if ((h->comm_rank > 0) != (south != nullptr) ||
+        (h->comm_rank < h->comm_nranks - 1) != (north != nullptr))
+        return fail(DC_ERR_ARG, "dc_comm_p2p_connect: pass the handles of exactly the existing "
+                                "neighbours");
+    const int e = dcb_comm_p2p_connect(h, south, north);
+    if (e) return fail(e, "dc_comm_p2p_connect: %s", dcb_comm_error());
+    return DC_OK;
 }
 
 enum { EV_START = 0, EV_CONT = 1, EV_BDONE = 2, EV_MOIST = 3, EV_COLP = 4, EV_DIAG = 5, EV_JOIN = 6,
@@ -1269,10 +1297,10 @@ static void enqueue_band_step(dc_handle *h, void *M, int tail)
         DC_MARK("M interior done", M);
         if (!single) {
             if (g.i_moist) dcb_stream_wait(h, EV_MOIST, S);
-            halo_move(h, stage, south ? dcb_comm_buffer(h, 0) : nullptr,
-                      north ? dcb_comm_buffer(h, 2) : nullptr, 1, S, "dc_step_matsuno");
+            halo_move(h, stage, south ? dcb_comm_buffer(h, 0, stage) : nullptr,
+                      north ? dcb_comm_buffer(h, 2, stage) : nullptr, 1, S, "dc_step_matsuno");
             DC_MARK("S pack done", S);
-            dcb_comm_sendrecv(h, S);
+            dcb_comm_sendrecv(h, stage, S);
             DC_MARK("S sendrecv done", S);
             dcb_stream_wait(h, EV_BDONE, M);         // both launches have read COLP
         }
@@ -1285,8 +1313,9 @@ static void enqueue_band_step(dc_handle *h, void *M, int tail)
         // ---- S: unpack, next continuity, diagnostics of the halo rows
         dcb_stream_wait(h, EV_COLP, S);
         if (!single) {
-            halo_move(h, stage, south ? dcb_comm_buffer(h, 1) : nullptr,
-                      north ? dcb_comm_buffer(h, 3) : nullptr, 0, S, "dc_step_matsuno");
+            halo_move(h, stage, south ? dcb_comm_buffer(h, 1, stage) : nullptr,
+                      north ? dcb_comm_buffer(h, 3, stage) : nullptr, 0, S, "dc_step_matsuno");
+            dcb_comm_consumed(h, stage, S);
             dcb_event_record(h, EV_UNPACK, S);
             dcb_stream_wait(h, EV_UNPACK, T);
             DC_MARK("S unpack done", S);

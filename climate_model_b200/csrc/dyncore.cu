@@ -250,8 +250,11 @@ static int dcb_profile_read(dc_handle *h, int max, const char **names, double *m
 static int dcb_comm_unique_id(void *id128);
 static int dcb_comm_init(dc_handle *h, const void *id128, int rank, int nranks, size_t halo_elems);
 static void dcb_comm_release(dc_handle *h);
-static double *dcb_comm_buffer(dc_handle *h, int which);
-static int dcb_comm_sendrecv(dc_handle *h, void *stream);
+static double *dcb_comm_buffer(dc_handle *h, int which, int stage);
+static int dcb_comm_sendrecv(dc_handle *h, int stage, void *stream);
+static void dcb_comm_consumed(dc_handle *h, int stage, void *stream);
+static int dcb_comm_p2p_handles(dc_handle *h, void *out);
+static int dcb_comm_p2p_connect(dc_handle *h, const void *south, const void *north);
 static void *dcb_side_stream(dc_handle *h, int which = 0);
 static void dcb_event_record(dc_handle *h, int ev, void *stream);
 static void dcb_stream_wait(dc_handle *h, int ev, void *stream);
@@ -318,6 +321,13 @@ struct CommState {
     int rank = 0, nranks = 1;
     size_t nelem = 0;
     double *buf[4] = {nullptr, nullptr, nullptr, nullptr};   // send_s, recv_s, send_n, recv_n
+                                                             // (recv: two slots, by stage parity)
+    // peer-memory exchange (CUDA IPC): the neighbours' receive buffers and flags mapped here
+    bool p2p = false;
+    unsigned *flags = nullptr;                 // [from south, from north][slot]: 1 = landed
+    double *peer_recv[2] = {nullptr, nullptr}; // south neighbour's recv_n, north neighbour's recv_s
+    unsigned *peer_flags[2] = {nullptr, nullptr};
+    void *peer_base[4] = {nullptr, nullptr, nullptr, nullptr};   // cudaIpcOpenMemHandle results
     cudaStream_t side = nullptr, side2 = nullptr;
     cudaStream_t main = nullptr;   // stands in for the caller's stream when that is the legacy
                                    // default stream, which cannot be captured
@@ -374,13 +384,16 @@ static int dcb_comm_init(dc_handle *h, const void *id128, int rank, int nranks, 
     for (auto &ev : c->ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     for (int n = 0; n < 4; n++) {
         const bool present = (n < 2) ? rank > 0 : rank < nranks - 1;
-        if (present && cudaMalloc(&c->buf[n], halo_elems * sizeof(double)) != cudaSuccess) {
+        const size_t slots = (n & 1) ? 2 : 1;
+        if (present && cudaMalloc(&c->buf[n], slots * halo_elems * sizeof(double)) != cudaSuccess) {
             dc::g_comm_error = "cudaMalloc of the halo buffers failed";
             h->comm_state = c;
             dcb_comm_release(h);
             return (int)cudaErrorMemoryAllocation;
         }
     }
+    if (cudaMalloc(&c->flags, 4 * sizeof(unsigned)) == cudaSuccess)
+        cudaMemset(c->flags, 0, 4 * sizeof(unsigned));
     h->comm_state = c;
     return 0;
 }
@@ -391,6 +404,9 @@ static void dcb_comm_release(dc_handle *h)
     cudaDeviceSynchronize();
     if (c->graph) cudaGraphExecDestroy(c->graph);
     if (c->graph_last) cudaGraphExecDestroy(c->graph_last);
+    for (void *p : c->peer_base)
+        if (p) cudaIpcCloseMemHandle(p);
+    if (c->flags) cudaFree(c->flags);
     for (double *b : c->buf)
         if (b) cudaFree(b);
     for (auto &ev : c->ev)
@@ -405,15 +421,137 @@ static void dcb_comm_release(dc_handle *h)
     delete c;
     h->comm_state = nullptr;
 }
-static double *dcb_comm_buffer(dc_handle *h, int which)
-{
-    return static_cast<dc::CommState *>(h->comm_state)->buf[which];
-}
-static int dcb_comm_sendrecv(dc_handle *h, void *stream)
+static double *dcb_comm_buffer(dc_handle *h, int which, int stage)
 {
     dc::CommState *c = static_cast<dc::CommState *>(h->comm_state);
-    dc::NcclApi *a = dc::nccl_api();
+    // receive buffers: slot = stage parity with the peer-memory exchange, slot 0 with NCCL
+    return c->buf[which] + (((which & 1) && c->p2p) ? (size_t)(stage & 1) * c->nelem : 0);
+}
+// stream memory operations of the driver API (no kernel, no SM): write / wait on a 32-bit word
+typedef CUresult (*StreamMemOpFn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+static StreamMemOpFn stream_memop(const char *name)
+{
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+        return nullptr;
+    return reinterpret_cast<StreamMemOpFn>(p);
+}
+static StreamMemOpFn write_value32()
+{
+    static StreamMemOpFn fn = stream_memop("cuStreamWriteValue32");
+    return fn;
+}
+static StreamMemOpFn wait_value32()
+{
+    static StreamMemOpFn fn = stream_memop("cuStreamWaitValue32");
+    return fn;
+}
+// fallback signal (DC_BAND_P2P_SIGNAL=kernel): a one-thread kernel stores the flag
+__global__ void k_signal(volatile unsigned *flag, unsigned v)
+{
+    __threadfence_system();
+    *flag = v;
+}
+static bool signal_by_kernel()
+{
+    static int mode = -1;
+    if (mode < 0) {
+        const char *e = getenv("DC_BAND_P2P_SIGNAL");
+        mode = (e && e[0] == 'k') ? 1 : 0;
+    }
+    return mode == 1;
+}
+static void memop_check(dc::CommState *c, CUresult r, const char *what)
+{
+    if (r != CUDA_SUCCESS && !c->error) {
+        c->error = (int)r;
+        dc::g_comm_error = std::string(what) + " failed (CUresult " + std::to_string((int)r) + ")";
+    }
+}
+static int dcb_comm_p2p_handles(dc_handle *h, void *out)
+{
+    dc::CommState *c = static_cast<dc::CommState *>(h->comm_state);
+    dc::g_comm_error.clear();
+    // [0..63] recv_s, [64..127] recv_n, [128..191] flags (zeros where a buffer does not exist)
+    unsigned char *o = static_cast<unsigned char *>(out);
+    memset(o, 0, DC_P2P_HANDLE_BYTES);
+    void *ptrs[3] = {c->buf[1], c->buf[3], c->flags};
+    for (int n = 0; n < 3; n++) {
+        if (!ptrs[n]) continue;
+        cudaIpcMemHandle_t hd;
+        if (cudaIpcGetMemHandle(&hd, ptrs[n]) != cudaSuccess) {
+            dc::g_comm_error = "cudaIpcGetMemHandle failed";
+            return (int)cudaGetLastError();
+        }
+        memcpy(o + 64 * n, &hd, sizeof hd);
+    }
+    return 0;
+}
+static int dcb_comm_p2p_connect(dc_handle *h, const void *south, const void *north)
+{
+    dc::CommState *c = static_cast<dc::CommState *>(h->comm_state);
+    dc::g_comm_error.clear();
+    if (!write_value32() || !wait_value32()) {
+        dc::g_comm_error = "cuStreamWriteValue32 / cuStreamWaitValue32 are not available";
+        return DC_ERR_NO_DEVICE;
+    }
+    auto open = [&](const void *blob, int which, void **out) {
+        cudaIpcMemHandle_t hd;
+        memcpy(&hd, static_cast<const unsigned char *>(blob) + 64 * which, sizeof hd);
+        return cudaIpcOpenMemHandle(out, hd, cudaIpcMemLazyEnablePeerAccess);
+    };
+    // my message to the SOUTH neighbour lands in ITS "from north" buffer (recv_n) and flags
+    // [from north]; my message to the NORTH neighbour in its recv_s / flags[from south]
+    if (south) {
+        if (open(south, 1, &c->peer_base[0]) != cudaSuccess ||
+            open(south, 2, &c->peer_base[1]) != cudaSuccess) {
+            dc::g_comm_error = "cudaIpcOpenMemHandle (south neighbour) failed";
+            return (int)cudaGetLastError();
+        }
+        c->peer_recv[0] = static_cast<double *>(c->peer_base[0]);
+        c->peer_flags[0] = static_cast<unsigned *>(c->peer_base[1]) + 2;   // [from north][slot]
+    }
+    if (north) {
+        if (open(north, 0, &c->peer_base[2]) != cudaSuccess ||
+            open(north, 2, &c->peer_base[3]) != cudaSuccess) {
+            dc::g_comm_error = "cudaIpcOpenMemHandle (north neighbour) failed";
+            return (int)cudaGetLastError();
+        }
+        c->peer_recv[1] = static_cast<double *>(c->peer_base[2]);
+        c->peer_flags[1] = static_cast<unsigned *>(c->peer_base[3]) + 0;   // [from south][slot]
+    }
+    c->p2p = true;
+    c->graph_version = -1;     // captured graphs hold the NCCL exchange
+    return 0;
+}
+static int dcb_comm_sendrecv(dc_handle *h, int stage, void *stream)
+{
+    dc::CommState *c = static_cast<dc::CommState *>(h->comm_state);
     cudaStream_t st = (cudaStream_t)stream;
+    if (c->p2p) {
+        const int slot = stage & 1;
+        const size_t bytes = c->nelem * sizeof(double);
+        for (int d = 0; d < 2; d++) {     // 0: to the south neighbour, 1: to the north
+            if (!c->peer_recv[d]) continue;
+            cudaMemcpyAsync(c->peer_recv[d] + (size_t)slot * c->nelem, c->buf[d == 0 ? 0 : 2], bytes,
+                            cudaMemcpyDefault, st);
+            if (signal_by_kernel())
+                k_signal<<<1, 1, 0, st>>>(c->peer_flags[d] + slot, 1u);
+            else
+                memop_check(c, write_value32()((CUstream)st, (CUdeviceptr)(c->peer_flags[d] + slot), 1, 0),
+                            "cuStreamWriteValue32 (peer flag)");
+        }
+        for (int d = 0; d < 2; d++) {     // 0: from the south neighbour, 1: from the north
+            if (!c->buf[d == 0 ? 1 : 3]) continue;
+            memop_check(c, wait_value32()((CUstream)st, (CUdeviceptr)(c->flags + 2 * d + slot), 1,
+                                          CU_STREAM_WAIT_VALUE_GEQ), "cuStreamWaitValue32");
+        }
+        h->launches++;
+        return c->error ? 1 : 0;
+    }
+    dc::NcclApi *a = dc::nccl_api();
     int e = a->GroupStart();
     if (!e && c->rank > 0) {
         e = a->Send(c->buf[0], c->nelem, dc::NCCL_FLOAT64, c->rank - 1, c->comm, st);
@@ -430,6 +568,19 @@ static int dcb_comm_sendrecv(dc_handle *h, void *stream)
     }
     h->launches++;
     return 0;
+}
+// the receive slot of `stage` has been unpacked: hand it back (the neighbour writes it again two
+// stages later, after it has received this rank's next message -- see include/dyncore.h)
+static void dcb_comm_consumed(dc_handle *h, int stage, void *stream)
+{
+    dc::CommState *c = static_cast<dc::CommState *>(h->comm_state);
+    if (!c->p2p) return;
+    const int slot = stage & 1;
+    for (int d = 0; d < 2; d++)
+        if (c->buf[d == 0 ? 1 : 3])
+            memop_check(c, write_value32()((CUstream)(cudaStream_t)stream,
+                                           (CUdeviceptr)(c->flags + 2 * d + slot), 0, 0),
+                        "cuStreamWriteValue32 (own flag)");
 }
 static void *dcb_side_stream(dc_handle *h, int which)
 {

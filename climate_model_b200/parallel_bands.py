@@ -127,6 +127,23 @@ def attach_communicator(GR, F, group=None, in_library=None):
         raw = bytes(ident.cpu().tolist())
         _lib.check(L.dc_set_comm(h, raw, nbytes, GR.band[0], GR.band[1]))
         GR.comm.in_library = True
+        GR.comm.p2p = False
+        if os.environ.get('DC_BAND_P2P', '1') != '0':
+            # peer-memory exchange: every rank publishes the CUDA IPC handles of its receive
+            # buffers and flags, the neighbours map them (dc_comm_p2p_connect); the boundary rows
+            # then travel by copy engine + stream memory operations, NCCL stays as the fallback
+            nb = _lib.DC_P2P_HANDLE_BYTES
+            mine = (ctypes.c_ubyte * nb)()
+            _lib.check(L.dc_comm_p2p_handles(h, mine, nb))
+            t = torch.tensor(list(mine), dtype=torch.uint8, device=F.torch_device)
+            allh = [torch.zeros_like(t) for _ in range(GR.band[1])]
+            dist.all_gather(allh, t, group=group)
+            rank, nranks = GR.band
+            south = bytes(allh[rank - 1].cpu().tolist()) if rank > 0 else None
+            north = bytes(allh[rank + 1].cpu().tolist()) if rank < nranks - 1 else None
+            _lib.check(L.dc_comm_p2p_connect(h, south, north, nb))
+            dist.barrier(group=group)          # every rank's flags are zero and mapped
+            GR.comm.p2p = True
     return GR.comm
 
 

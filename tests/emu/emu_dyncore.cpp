@@ -84,8 +84,11 @@ static const char *dcb_comm_error() { return ""; }
 static int dcb_comm_unique_id(void *) { return DC_ERR_NO_DEVICE; }
 static int dcb_comm_init(dc_handle *, const void *, int, int, size_t) { return DC_ERR_NO_DEVICE; }
 static void dcb_comm_release(dc_handle *) {}
-static double *dcb_comm_buffer(dc_handle *, int) { return nullptr; }
-static int dcb_comm_sendrecv(dc_handle *, void *) { return DC_ERR_NO_DEVICE; }
+static double *dcb_comm_buffer(dc_handle *, int, int) { return nullptr; }
+static int dcb_comm_sendrecv(dc_handle *, int, void *) { return DC_ERR_NO_DEVICE; }
+static void dcb_comm_consumed(dc_handle *, int, void *) {}
+static int dcb_comm_p2p_handles(dc_handle *, void *) { return DC_ERR_NO_DEVICE; }
+static int dcb_comm_p2p_connect(dc_handle *, const void *, const void *) { return DC_ERR_NO_DEVICE; }
 static void *dcb_side_stream(dc_handle *, int = 0) { return nullptr; }
 static void dcb_event_record(dc_handle *, int, void *) {}
 static void dcb_stream_wait(dc_handle *, int, void *) {}
