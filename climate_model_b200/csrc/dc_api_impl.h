@@ -222,13 +222,15 @@ static void continuity_rows(const Geom &g, int *lo, int *hi)
     *hi = g.j1 + 1 > g.ny ? g.ny : g.j1 + 1;
 }
 
+// rows [lo, hi] without the rows [gap_lo, gap_hi] (defaults: every row the stage kernel needs)
 template <int MODE>
-static void launch_continuity(dc_handle *h, const double *U, const double *V, void *stream)
+static void launch_continuity(dc_handle *h, const double *U, const double *V, void *stream,
+                              int lo = 0, int hi = -1, int gap_lo = 0, int gap_hi = -1)
 {
     const Fields &f = h->f;
     const Geom &g = h->g;
-    int lo, hi;
-    continuity_rows(g, &lo, &hi);
+    if (hi < lo) continuity_rows(g, &lo, &hi);
+    const int gap = gap_hi >= gap_lo ? gap_hi - gap_lo + 1 : 0;
     if (h->cont_impl == 1) {   // two-sweep column kernel (DC_CONT_IMPL=1)
         ContinuityBody<MODE> b{g,      U,        V,       f.COLP,     f.COLP_OLD, f.UFLX,
                                f.VFLX, f.FLXDIV, f.WWIND, f.COLP_NEW, f.dCOLPdt};
@@ -236,11 +238,13 @@ static void launch_continuity(dc_handle *h, const double *U, const double *V, vo
         return;
     }
     if (hi < lo) return;
+    if (hi - lo + 1 - gap <= 0) return;
     ContinuityTileBody<MODE> b{g,      U,        V,       f.COLP,     f.COLP_OLD, f.UFLX,
                                f.VFLX, f.FLXDIV, f.WWIND, f.COLP_NEW, f.dCOLPdt, lo};
+    if (gap) { b.j_split = gap_lo; b.j_skip = gap; }
     if (h->profiling == 1) dcb_profile_begin(h, "continuity", stream);
     dcb_launch_blocks<ContinuityTileBody<MODE>, ContinuitySmem>(
-        b, (g.nx + CT_TX - 1) / CT_TX, hi - lo + 1, (g.nz + CT_L - 1) / CT_L * CT_TX, stream);
+        b, (g.nx + CT_TX - 1) / CT_TX, hi - lo + 1 - gap, (g.nz + CT_L - 1) / CT_L * CT_TX, stream);
     if (h->profiling == 1) dcb_profile_end(h, stream);
     h->launches++;
 }
@@ -1232,14 +1236,49 @@ int dc_comm_p2p_connect(dc_handle *h, const void *south, const void *north, size
 }
 
 enum { EV_START = 0, EV_CONT = 1, EV_BDONE = 2, EV_MOIST = 3, EV_COLP = 4, EV_DIAG = 5, EV_JOIN = 6,
-       EV_UNPACK = 7, EV_HDIAG = 8, EV_JOIN2 = 9 };
+       EV_UNPACK = 7, EV_HDIAG = 8, EV_JOIN2 = 9, EV_PACK = 10, EV_CONTI = 11 };
 
-// continuity (+ COLP_OLD <- COLP before a step's first stage) of stage `stage`
-static void enqueue_continuity(dc_handle *h, int stage, void *st)
+// continuity (+ COLP_OLD <- COLP before a step's first stage) of stage `stage`.
+// rows: 0 = every row the stage kernel needs (j0-1 .. j1+1); 1 = the rows that do not depend on
+// the neighbours' new boundary rows (j0+1 .. j1-1, and up to the wall where the band ends at
+// one); 2 = the band-edge rows (the rest), in one launch
+static void enqueue_continuity(dc_handle *h, int stage, void *st, int rows)
 {
-    if (stage == 0)
-        dcb_d2d_async(h->f.COLP_OLD, h->f.COLP, h->g.plane * sizeof(double), st);  // dyn_matsuno.py:34
-    do_stage_fused(h, stage, DC_PART_CONT_ONLY, st);
+    const Fields &f = h->f;
+    const Geom &g = h->g;
+    const double *U = stage == 0 ? f.UWIND : f.UWIND_OLD, *V = stage == 0 ? f.VWIND : f.VWIND_OLD;
+    const bool south = h->comm_rank > 0, north = h->comm_rank < h->comm_nranks - 1;
+    int lo, hi;
+    continuity_rows(g, &lo, &hi);
+    const int in_lo = south ? g.j0 + 1 : lo, in_hi = north ? g.j1 - 1 : hi;
+    if (stage == 0) {                                                    // dyn_matsuno.py:34
+        // the own rows of the new COLP are final after COLP <- COLP_NEW, the halo rows after
+        // the unpack: copied with the part that needs them
+        const int a = rows == 2 ? 0 : (rows == 1 ? g.row(g.j0) : 0);
+        const size_t NI = (size_t)g.NI;
+        if (rows == 0) {
+            dcb_d2d_async(f.COLP_OLD, f.COLP, g.plane * sizeof(double), st);
+        } else if (rows == 1) {
+            dcb_d2d_async(f.COLP_OLD + a * NI, f.COLP + a * NI,
+                          (size_t)(g.j1 - g.j0 + 1) * NI * sizeof(double), st);
+        } else {
+            const int r0 = g.row(g.j0), r1 = g.row(g.j1) + 1;
+            if (r0 > 0) dcb_d2d_async(f.COLP_OLD, f.COLP, (size_t)r0 * NI * sizeof(double), st);
+            if (r1 < g.NJ)
+                dcb_d2d_async(f.COLP_OLD + r1 * NI, f.COLP + r1 * NI,
+                              (size_t)(g.NJ - r1) * NI * sizeof(double), st);
+        }
+    }
+    if (rows == 0)
+        launch_continuity<0>(h, U, V, st);
+    else if (rows == 1)
+        launch_continuity<0>(h, U, V, st, in_lo, in_hi);
+    else
+        launch_continuity<0>(h, U, V, st, lo, hi, in_lo, in_hi);
+}
+static void enqueue_continuity_all(dc_handle *h, int stage, void *st)
+{
+    enqueue_continuity(h, stage, st, 0);
 }
 
 // One Matsuno step on a latitude band with the exchange inside the library, as TWO concurrent
@@ -1247,10 +1286,11 @@ static void enqueue_continuity(dc_handle *h, int stage, void *st)
 // continuity of stage 0 is done.  Per stage:
 //   M: [moisture stage] -> stage kernel on the interior tile rows -> COLP <- COLP_NEW ->
 //      diagnostics of the rows that need no neighbour data
-//   S: stage kernel on the first and last tile row -> pack -> NCCL send/recv with both
-//      neighbours -> unpack -> CONTINUITY OF THE NEXT STAGE
-//   T: (third stream) diagnostics of the halo rows, after the unpack -- a launch as long as one
-//      thread's march up the column (~70 us), which would otherwise delay S's next boundary rows
+//   S: stage kernel on the first and last tile row -> pack -> exchange with both neighbours
+//      (peer-memory copies, or one NCCL group) -> unpack -> NEXT CONTINUITY, band-edge rows
+//   T: NEXT CONTINUITY on the rows that need nothing from the neighbours (after COLP <-
+//      COLP_NEW), then, after the unpack, the diagnostics of the halo rows -- a launch as long
+//      as one thread's march up the column (~70 us) that would otherwise delay S
 // The exchange hides behind the interior tile rows; the next continuity (needs the new U, V,
 // COLP incl. halos, nothing of the diagnostics) and the halo-row diagnostics run beside the
 // own-row diagnostics (needs the new POTT, COLP of the own rows).  Measured on two B200 with
@@ -1267,6 +1307,10 @@ static void enqueue_band_step(dc_handle *h, void *M, int tail)
     const bool south = h->comm_rank > 0, north = h->comm_rank < h->comm_nranks - 1;
     const int lo = g.j0 - HJ < 0 ? 0 : g.j0 - HJ, hi = g.j1 + HJ > g.ny + 1 ? g.ny + 1 : g.j1 + HJ;
     const int own_lo = south ? g.j0 : lo, own_hi = north ? g.j1 : hi;
+    // the interior tile rows read WWIND / COLP_NEW one row beyond themselves: rows of the edge
+    // continuity only if the band's first or last tile holds a single own row
+    const int jI = 1 + ((g.j0 - 1) / S3_TY + 1) * S3_TY, jE = (g.j1 - 1) / S3_TY * S3_TY;
+    const bool edge_rows_feed_interior = (south && jI - g.j0 < 2) || (north && g.j1 - jE < 2);
     const bool tl = h->profiling == 2;   // timeline marks (dc_profile_enable(h, 2))
 #define DC_MARK(name, st) if (tl) dcb_mark(h, name, st)
     DC_MARK("M step begin", M);
@@ -1276,8 +1320,12 @@ static void enqueue_band_step(dc_handle *h, void *M, int tail)
         const bool next = stage == 0 || tail;        // a continuity follows this stage
         // ---- S first: boundary tile rows (what the neighbours wait for; enqueued BEFORE the
         //      interior launch so that its blocks get the first free slots), pack, exchange
-        if (stage == 1) dcb_stream_wait(h, EV_CONT, M);
+        if (stage == 1) {
+            if (!single) dcb_stream_wait(h, EV_CONTI, M);   // continuity of the rows the interior reads
+            if (single || edge_rows_feed_interior) dcb_stream_wait(h, EV_CONT, M);
+        }
         if (g.i_moist) {
+            if (stage == 1 && !single) dcb_stream_wait(h, EV_CONT, M);   // moisture: all rows
             do_stage_fused(h, stage, DC_PART_MOIST, M);
             dcb_event_record(h, EV_MOIST, M);
             DC_MARK("M moisture done", M);
@@ -1286,6 +1334,7 @@ static void enqueue_band_step(dc_handle *h, void *M, int tail)
             if (stage == 1) {
                 dcb_stream_wait(h, EV_DIAG, S);      // PHI, PGCOL, POTTVB of the own rows (M)
                 dcb_stream_wait(h, EV_HDIAG, S);     // ... and of the halo rows (T)
+                dcb_stream_wait(h, EV_CONTI, S);     // WWIND, COLP_NEW of the inner rows (T)
             }
             DC_MARK("S boundary begin", S);
             do_stage_fused(h, stage, DC_PART_BOUNDARY, S);
@@ -1299,6 +1348,7 @@ static void enqueue_band_step(dc_handle *h, void *M, int tail)
             if (g.i_moist) dcb_stream_wait(h, EV_MOIST, S);
             halo_move(h, stage, south ? dcb_comm_buffer(h, 0, stage) : nullptr,
                       north ? dcb_comm_buffer(h, 2, stage) : nullptr, 1, S, "dc_step_matsuno");
+            dcb_event_record(h, EV_PACK, S);
             DC_MARK("S pack done", S);
             dcb_comm_sendrecv(h, stage, S);
             DC_MARK("S sendrecv done", S);
@@ -1307,6 +1357,15 @@ static void enqueue_band_step(dc_handle *h, void *M, int tail)
         // ---- M: COLP <- COLP_NEW, diagnostics of the own rows
         do_stage_fused(h, stage, DC_PART_COLP, M);
         dcb_event_record(h, EV_COLP, M);
+        if (next && !single) {
+            // T: the next continuity on the rows that need nothing from the neighbours, as soon
+            // as COLP is final (and the pack has read COLP_NEW) -- beside the diagnostics
+            dcb_stream_wait(h, EV_COLP, T);
+            dcb_stream_wait(h, EV_PACK, T);
+            enqueue_continuity(h, 1 - stage, T, 1);
+            dcb_event_record(h, EV_CONTI, T);
+            DC_MARK("T next continuity (inner rows) done", T);
+        }
         do_diag_rows(h, stage, own_lo, own_hi, M);
         dcb_event_record(h, EV_DIAG, M);
         DC_MARK("M own-row diag done", M);
@@ -1317,15 +1376,19 @@ static void enqueue_band_step(dc_handle *h, void *M, int tail)
                       north ? dcb_comm_buffer(h, 3, stage) : nullptr, 0, S, "dc_step_matsuno");
             dcb_comm_consumed(h, stage, S);
             dcb_event_record(h, EV_UNPACK, S);
-            dcb_stream_wait(h, EV_UNPACK, T);
             DC_MARK("S unpack done", S);
         }
-        if (next) {
-            enqueue_continuity(h, 1 - stage, S);
+        if (next && single) {
+            enqueue_continuity(h, 1 - stage, S, 0);
             dcb_event_record(h, EV_CONT, S);
-            DC_MARK("S next continuity done", S);
+        } else if (next) {
+            // S: the band-edge rows of the next continuity, after the unpack
+            enqueue_continuity(h, 1 - stage, S, 2);
+            dcb_event_record(h, EV_CONT, S);
+            DC_MARK("S next continuity (edge rows) done", S);
         }
         if (!single) {
+            dcb_stream_wait(h, EV_UNPACK, T);
             do_diag_rows(h, stage, lo, hi, T, own_lo, own_hi);   // both halo ranges, one launch
             dcb_event_record(h, EV_HDIAG, T);
             DC_MARK("T halo-row diag done", T);
@@ -1357,11 +1420,11 @@ static int step_matsuno_banded(dc_handle *h, int nsteps, void *stream)
     // the per-kernel event brackets of dc_profile_enable cannot be captured: plain enqueue then
     int gs = 1;
     if (h->band_graph && !h->profiling)
-        gs = dcb_graph_steps(h, nsteps, stream, enqueue_continuity, enqueue_band_step_tail,
+        gs = dcb_graph_steps(h, nsteps, stream, enqueue_continuity_all, enqueue_band_step_tail,
                              enqueue_band_step_last);
     if (gs == 2) return fail(DC_ERR_STATE, "dc_step_matsuno: cudaGraphLaunch failed");
     if (gs == 1) {
-        enqueue_continuity(h, 0, stream);
+        enqueue_continuity(h, 0, stream, 0);
         for (int s = 0; s < nsteps; s++) enqueue_band_step(h, stream, s + 1 < nsteps);
     }
     if (dcb_comm_error()[0]) return fail(DC_ERR_STATE, "dc_step_matsuno: %s", dcb_comm_error());

@@ -1225,11 +1225,14 @@ struct ContinuityTileBody {
     const double *UWIND, *VWIND, *COLP, *COLP_OLD;
     double *UFLX, *VFLX, *FLXDIV, *WWIND, *COLP_NEW, *dCOLPdt;
     int j_lo;   // first row of the launch; block (bx, by) owns columns 1+32*bx.., row j_lo+by
+    // rows from j_split on are shifted by j_skip (two row ranges in one launch: the band-edge
+    // rows of the pipelined band step)
+    int j_split = 1 << 30, j_skip = 0;
 
     DC_HD void run_block(int bx, int by, ContinuitySmem &s) const
     {
         const int nz = g.nz, nw = (nz + CT_L - 1) / CT_L, nt = nw * CT_TX;
-        const int j = j_lo + by;
+        const int j = (j_lo + by >= j_split) ? j_lo + by + j_skip : j_lo + by;
         CT_PRIVN(double, fd, CT_L);   // flux divergence, then running sum, of the own levels
         // ---- flux divergences of the own levels -------------------------------------------
         CT_PHASE(nt)

@@ -543,6 +543,7 @@ static int dcb_comm_sendrecv(dc_handle *h, int stage, void *stream)
                 memop_check(c, write_value32()((CUstream)st, (CUdeviceptr)(c->peer_flags[d] + slot), 1, 0),
                             "cuStreamWriteValue32 (peer flag)");
         }
+        if (h->profiling == 2) dcb_mark(h, "S p2p copies + flags done", stream);
         for (int d = 0; d < 2; d++) {     // 0: from the south neighbour, 1: from the north
             if (!c->buf[d == 0 ? 1 : 3]) continue;
             memop_check(c, wait_value32()((CUstream)st, (CUdeviceptr)(c->flags + 2 * d + slot), 1,
