@@ -153,6 +153,7 @@ struct dc_handle {
     int comm_rank, comm_nranks;
     long long bind_version;   // bumped whenever a bound pointer changes (CUDA-graph cache key)
     int band_graph;       // replay the banded step from a CUDA graph (DC_BAND_GRAPH, default 1)
+    int band_split_cont;  // next continuity split into inner / band-edge rows (DC_BAND_SPLIT_CONT)
     double **slot(int id) { return reinterpret_cast<double **>(&f) + id; }
     double *const *slot(int id) const { return reinterpret_cast<double *const *>(&f) + id; }
 };
@@ -735,6 +736,8 @@ int dc_create(const dc_grid_desc *d, dc_handle **out)
     {
         const char *bg = getenv("DC_BAND_GRAPH");
         h->band_graph = (bg && bg[0] == '0') ? 0 : 1;
+        const char *sc = getenv("DC_BAND_SPLIT_CONT");
+        h->band_split_cont = (sc && sc[0] == '1') ? 1 : 0;
     }
     h->diag_partial = 0;
     const char *impl = getenv("DC_STAGE_IMPL");
@@ -1321,11 +1324,13 @@ static void enqueue_band_step(dc_handle *h, void *M, int tail)
         // ---- S first: boundary tile rows (what the neighbours wait for; enqueued BEFORE the
         //      interior launch so that its blocks get the first free slots), pack, exchange
         if (stage == 1) {
-            if (!single) dcb_stream_wait(h, EV_CONTI, M);   // continuity of the rows the interior reads
-            if (single || edge_rows_feed_interior) dcb_stream_wait(h, EV_CONT, M);
+            const bool split = !single && h->band_split_cont;
+            if (split) dcb_stream_wait(h, EV_CONTI, M);   // continuity of the rows the interior reads
+            if (!split || edge_rows_feed_interior) dcb_stream_wait(h, EV_CONT, M);
         }
         if (g.i_moist) {
-            if (stage == 1 && !single) dcb_stream_wait(h, EV_CONT, M);   // moisture: all rows
+            if (stage == 1 && !single && h->band_split_cont)
+                dcb_stream_wait(h, EV_CONT, M);      // moisture: all rows
             do_stage_fused(h, stage, DC_PART_MOIST, M);
             dcb_event_record(h, EV_MOIST, M);
             DC_MARK("M moisture done", M);
@@ -1334,7 +1339,8 @@ static void enqueue_band_step(dc_handle *h, void *M, int tail)
             if (stage == 1) {
                 dcb_stream_wait(h, EV_DIAG, S);      // PHI, PGCOL, POTTVB of the own rows (M)
                 dcb_stream_wait(h, EV_HDIAG, S);     // ... and of the halo rows (T)
-                dcb_stream_wait(h, EV_CONTI, S);     // WWIND, COLP_NEW of the inner rows (T)
+                if (h->band_split_cont)
+                    dcb_stream_wait(h, EV_CONTI, S); // WWIND, COLP_NEW of the inner rows (T)
             }
             DC_MARK("S boundary begin", S);
             do_stage_fused(h, stage, DC_PART_BOUNDARY, S);
@@ -1357,7 +1363,7 @@ static void enqueue_band_step(dc_handle *h, void *M, int tail)
         // ---- M: COLP <- COLP_NEW, diagnostics of the own rows
         do_stage_fused(h, stage, DC_PART_COLP, M);
         dcb_event_record(h, EV_COLP, M);
-        if (next && !single) {
+        if (next && !single && h->band_split_cont) {
             // T: the next continuity on the rows that need nothing from the neighbours, as soon
             // as COLP is final (and the pack has read COLP_NEW) -- beside the diagnostics
             dcb_stream_wait(h, EV_COLP, T);
@@ -1378,9 +1384,10 @@ static void enqueue_band_step(dc_handle *h, void *M, int tail)
             dcb_event_record(h, EV_UNPACK, S);
             DC_MARK("S unpack done", S);
         }
-        if (next && single) {
+        if (next && (single || !h->band_split_cont)) {
             enqueue_continuity(h, 1 - stage, S, 0);
             dcb_event_record(h, EV_CONT, S);
+            DC_MARK("S next continuity done", S);
         } else if (next) {
             // S: the band-edge rows of the next continuity, after the unpack
             enqueue_continuity(h, 1 - stage, S, 2);

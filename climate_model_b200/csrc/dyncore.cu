@@ -454,6 +454,27 @@ __global__ void k_signal(volatile unsigned *flag, unsigned v)
     __threadfence_system();
     *flag = v;
 }
+// wait for a flag with a one-thread spin kernel: a stream wait-value operation took ~120 us to
+// notice the flag on this system (timeline r2_timeline_proxy5: copies done at 0.179 ms, wait over
+// at 0.300 ms on both ranks), a polling thread notices it within a microsecond once it runs.
+// Bounded: ~2 s of polling, then the kernel traps (surfaces as a launch failure).
+__global__ void k_wait_flag(const volatile unsigned *flag, unsigned v)
+{
+    const long long t0 = clock64();
+    while (*flag < v) {
+        if (clock64() - t0 > 4000000000ll) __trap();
+    }
+    __threadfence_system();
+}
+static bool wait_by_memop()
+{
+    static int mode = -1;
+    if (mode < 0) {
+        const char *e = getenv("DC_BAND_P2P_WAIT");
+        mode = (e && e[0] == 'm') ? 1 : 0;
+    }
+    return mode == 1;
+}
 static bool signal_by_kernel()
 {
     static int mode = -1;
@@ -546,8 +567,11 @@ static int dcb_comm_sendrecv(dc_handle *h, int stage, void *stream)
         if (h->profiling == 2) dcb_mark(h, "S p2p copies + flags done", stream);
         for (int d = 0; d < 2; d++) {     // 0: from the south neighbour, 1: from the north
             if (!c->buf[d == 0 ? 1 : 3]) continue;
-            memop_check(c, wait_value32()((CUstream)st, (CUdeviceptr)(c->flags + 2 * d + slot), 1,
-                                          CU_STREAM_WAIT_VALUE_GEQ), "cuStreamWaitValue32");
+            if (wait_by_memop())
+                memop_check(c, wait_value32()((CUstream)st, (CUdeviceptr)(c->flags + 2 * d + slot), 1,
+                                              CU_STREAM_WAIT_VALUE_GEQ), "cuStreamWaitValue32");
+            else
+                k_wait_flag<<<1, 1, 0, st>>>(c->flags + 2 * d + slot, 1u);
         }
         h->launches++;
         return c->error ? 1 : 0;
