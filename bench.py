@@ -77,10 +77,11 @@ KERNEL_ACCESSES_COUPLED = {
 }
 
 # DRAM bytes per launch of the dominant kernel (dram__bytes_read.sum + dram__bytes_write.sum of one
-# `ncu --set full` capture, profiles/r1_final_ncu_full_summary.csv): valid for that workload on one
+# `ncu --set full` capture, profiles/r2_ncu_full_summary.csv): valid for that workload on one
 # GPU only; anything else reports null
 NCU_TRAFFIC = {
-    ('cfg4', 1, False, 'stage_fused'): 0.5 * ((4.050476 + 1.484360) + (5.584172 + 1.481632)) * 1e9,
+    ('cfg4', 1, False, 'stage_fused'): 0.5 * ((4.030787 + 1.483990) + (5.546863 + 1.481524)) * 1e9,
+    ('cfg4', 1, True, 'stage_fused'): 0.5 * ((4.030787 + 1.483990) + (5.546863 + 1.481524)) * 1e9,
 }
 
 
@@ -614,7 +615,7 @@ def main():
                     'frac': ach / peak,
                     'traffic': NCU_TRAFFIC.get((args.workload, world, moist, top))
                     if args.mode == 'fused' else None,
-                    'traffic_source': 'ncu --set full, profiles/r1_final_ncu_full_summary.csv '
+                    'traffic_source': 'ncu --set full, profiles/r2_ncu_full_summary.csv '
                                       '(mean of the stage-1 and stage-2 launch)',
                     'peak_source': peak_src,
                     'algorithmic_bytes_per_launch': bytes_launch, 'avg_launch_ms': k_ms,
