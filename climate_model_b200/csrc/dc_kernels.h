@@ -790,9 +790,9 @@ struct PrimaryDiagBody {
     // production build: a / b as a * (correctly rounded reciprocal of b), <= 1 ulp off
     DC_HD static double fdiv(double a, double b) { return DC_FAST ? a * dc_rcp(b) : a / b; }
     // production build: pow_kappa (dc_point.h) instead of pow(x, kappa)
-    DC_HD double exner(double p) const
+    DC_HD double exner(double p, const double *tab, bool shared) const
     {
-        return DC_FAST ? pow_kappa_tab(p * 1e-5, pc) : pow(p / 100000., con_kappa);
+        return DC_FAST ? pow_kappa_tab(p * 1e-5, pc, tab, shared) : pow(p / 100000., con_kappa);
     }
     // One BOTTOM-UP sweep: the hydrostatic integral needs that direction, everything else is
     // level-local or couples two neighbouring levels, so POTT is read once and nothing the
@@ -810,8 +810,17 @@ struct PrimaryDiagBody {
     PowCoef pc;
     // rows from j_split on are shifted by j_skip: [j_lo, j_split) and [j_split + j_skip, j_hi]
     int j_split = 1 << 30, j_skip = 0;
-    DC_HD void operator()(int i, int jj) const
+    DC_HD void operator()(int i, int jj) const { march(i, jj, pc.tab, false, nullptr); }
+    // `tab` = the power table: pc.tab (global memory) or the kernel's copy in shared memory
+    // (k_diag in dyncore.cu; ncu: with the table behind the read-only path 64 % of the sweep's
+    // stalls were this lookup, which sits on the level's dependent chain)
+    // `lev`: sigma_vb | dsigma | r_dsigma, (nz+1) entries each, staged by the kernel (or NULL:
+    // read from the geometry vectors in global memory)
+    DC_HD void march(int i, int jj, const double *tab, bool shared, const double *lev) const
     {
+        const double *sig = lev ? lev : g.sigma_vb;
+        const double *dsg = lev ? lev + (g.nz + 1) : g.dsigma;
+        const double *rds = lev ? lev + 2 * (g.nz + 1) : g.r_dsigma;
         constexpr bool PV = MODE != 1, PHB = MODE == 0, PG = MODE != 2;
         const int nz = g.nz;
         const size_t plane = g.plane;
@@ -823,8 +832,8 @@ struct PrimaryDiagBody {
         for (int c = 0; c < NC; c++) {
             const int j = c < nc ? j0 + c : j0;   // a masked second column shadows the first
             colp[c] = COLP[g.idx2(i, j)];
-            p_kp12[c] = g.pair_top + g.sigma_vb[nz] * colp[c];
-            pw_kp12[c] = exner(p_kp12[c]);
+            p_kp12[c] = g.pair_top + sig[nz] * colp[c];
+            pw_kp12[c] = exner(p_kp12[c], tab, shared);
             o[c] = g.idx(i, j, nz);
             phivb[c] = HSURF[g.idx2(i, j)] * con_g;
             pvtf_kp1[c] = 0.;
@@ -834,7 +843,7 @@ struct PrimaryDiagBody {
                 if (PHB) PHIVB[o[c]] = phivb[c];
             }
         }
-        double svb_kp1 = g.sigma_vb[nz];
+        double svb_kp1 = sig[nz];
         // POTT of the next level is requested one iteration ahead: its latency hides behind the
         // exp / log / division chain of the current level (ncu: 60 % of the stalls were this load)
         // (round 2, with the table-driven Exner power: requesting three levels ahead instead of
@@ -846,8 +855,8 @@ struct PrimaryDiagBody {
             for (int n = 0; n < PF; n++)
                 pott_q[c][n] = nz - 1 - n >= 0 ? POTT[o[c] - (size_t)(n + 1) * plane] : 0.;
         for (int k = nz - 1; k >= 0; k--) {
-            const double svb = g.sigma_vb[k];
-            const Div ds = mkdiv(g.dsigma[k], g.r_dsigma[k]);
+            const double svb = sig[k];
+            const Div ds = mkdiv(dsg[k], rds[k]);
             for (int c = 0; c < NC; c++) {
                 o[c] -= plane;
                 const double pott = pott_q[c][0];
@@ -855,7 +864,7 @@ struct PrimaryDiagBody {
                 for (int n = 0; n + 1 < PF; n++) pott_q[c][n] = pott_q[c][n + 1];
                 if (k - PF >= 0) pott_q[c][PF - 1] = POTT[o[c] - (size_t)PF * plane];
                 const double p_km12 = g.pair_top + svb * colp[c];
-                const double pw_km12 = exner(p_km12);
+                const double pw_km12 = exner(p_km12, tab, shared);
                 const double pvtf = fdiv(1. / (1. + con_kappa) *
                                              (pw_kp12[c] * p_kp12[c] - pw_km12 * p_km12),
                                          p_kp12[c] - p_km12);

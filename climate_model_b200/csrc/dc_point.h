@@ -369,25 +369,35 @@ inline
 double pow_kappa_cold(double x, double kappa) { return pow(x, kappa); }
 // x^kappa through the table of make_pow_table (see PowCoef); arguments outside the tabulated
 // binades (or a handle without a table) take the library pow
-DC_HD double pow_kappa_tab(double x, const PowCoef &c)
+// `tab`: c.tab (global memory, read through the read-only path) or a copy of it in shared
+// memory (`shared` = true: plain loads)
+DC_HD double pow_kappa_tab(double x, const PowCoef &c, const double *tab, bool shared)
 {
     const int hi = dc_hi_word(x);
     const int te = (hi >> 20) - (1023 + POW_EMIN);
-    if (c.tab == nullptr || (unsigned)te >= (unsigned)POW_NE) return pow_kappa_cold(x, c.kappa);
+    if (tab == nullptr || (unsigned)te >= (unsigned)POW_NE) return pow_kappa_cold(x, c.kappa);
     const int j = (hi >> (20 - POW_JBITS)) & (POW_NJ - 1);
     const double m = dc_from_words((hi & 0x000fffff) | 0x3ff00000, dc_lo_word(x));
-    const double *rt = c.tab + 2 * (te * POW_NJ + j);
+    const double *rt = tab + 2 * (te * POW_NJ + j);
+    double r, T;
 #if defined(__CUDA_ARCH__)
-    const double2 v = __ldg(reinterpret_cast<const double2 *>(rt));
-    const double r = v.x, T = v.y;
+    if (shared) {
+        const double2 v = *reinterpret_cast<const double2 *>(rt);
+        r = v.x; T = v.y;
+    } else {
+        const double2 v = __ldg(reinterpret_cast<const double2 *>(rt));
+        r = v.x; T = v.y;
+    }
 #else
-    const double r = rt[0], T = rt[1];
+    (void)shared;
+    r = rt[0]; T = rt[1];
 #endif
     const double tt = dc_fma(m, r, -1.);
     double q = c.b[8];
     for (int n = 7; n >= 1; n--) q = dc_fma(q, tt, c.b[n]);
     return dc_fma(T, q * tt, T);
 }
+DC_HD double pow_kappa_tab(double x, const PowCoef &c) { return pow_kappa_tab(x, c, c.tab, false); }
 
 // Table-driven natural logarithm for the production build (moisture interface values,
 // comp_VARVB_log): x = 2^e * m, t = fma(m, r_j, -1) as in pow_kappa_tab,

@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include "dc_geom.h"
+#include "dc_point.h"
 
 #define DC_BACKEND_IS_CUDA 1
 
@@ -53,6 +54,41 @@ static void dcb_launch(const Body &b, int i0, int i1, int j0, int j1, void *stre
     dim3 block(dc::BX, dc::BY);
     dim3 grid((i1 - i0 + dc::BX) / dc::BX, (j1 - j0 + dc::BY) / dc::BY);
     dc::k_columns<Body><<<grid, block, 0, (cudaStream_t)stream>>>(b, i0, i1, j0, j1);
+}
+
+// primary diagnostics: the column march of PrimaryDiagBody with the Exner power table staged in
+// shared memory (7 KB) instead of read through the read-only path on every level
+namespace dc {
+template <class Body>
+__global__ void __launch_bounds__(BX *BY) k_diag(const Body b, int i0, int i1, int j0, int j1)
+{
+    __shared__ __align__(16) double tab[2 * POW_NE * POW_NJ];
+    constexpr int LEV_NZMAX = 128;                  // more levels: tables stay in global memory
+    __shared__ double lev[3 * (LEV_NZMAX + 1)];
+    const bool have = DC_FAST && b.pc.tab != nullptr;
+    const int nz = b.g.nz, tid = threadIdx.y * BX + threadIdx.x;
+    const bool have_lev = nz <= LEV_NZMAX;
+    if (have)
+        for (int n = tid; n < 2 * POW_NE * POW_NJ; n += BX * BY) tab[n] = b.pc.tab[n];
+    if (have_lev)
+        for (int n = tid; n <= nz; n += BX * BY) {
+            lev[n] = b.g.sigma_vb[n];
+            lev[(nz + 1) + n] = n < nz ? b.g.dsigma[n] : 0.;
+            lev[2 * (nz + 1) + n] = n < nz ? b.g.r_dsigma[n] : 0.;
+        }
+    __syncthreads();
+    const int i = i0 + blockIdx.x * BX + threadIdx.x;
+    const int j = j0 + blockIdx.y * BY + threadIdx.y;
+    if (i <= i1 && j <= j1)
+        b.march(i, j, have ? tab : b.pc.tab, have, have_lev ? lev : nullptr);
+}
+}  // namespace dc
+template <class Body>
+static void dcb_launch_diag(const Body &b, int i0, int i1, int j0, int j1, void *stream)
+{
+    dim3 block(dc::BX, dc::BY);
+    dim3 grid((i1 - i0 + dc::BX) / dc::BX, (j1 - j0 + dc::BY) / dc::BY);
+    dc::k_diag<Body><<<grid, block, 0, (cudaStream_t)stream>>>(b, i0, i1, j0, j1);
 }
 
 namespace dc {

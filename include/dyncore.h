@@ -159,8 +159,9 @@ int dc_set_mode(dc_handle *h, int mode);
  *                       TMA-staged one (csrc/dc_stage3.h)
  *   DC_STAGE_KCHUNKS=n  sigma-column chunks of the stage kernel (default: by launch size)
  *   DC_CONT_IMPL=1      two-sweep column continuity kernel instead of the single-pass tile kernel
- *   DC_COUPLED_IMPL=2   i_coupling: coupled terms as increments beside the fused dry stage
- *                       kernel instead of the kernel decomposition (experimental) */
+ *   DC_COUPLED_IMPL=1|2 i_coupling: 1 = kernel decomposition (reference summation order; default
+ *                       of the strict build), 2 = coupled terms as increments beside the fused
+ *                       dry stage kernel (default of the production build) */
 int dc_step_matsuno(dc_handle *h, int nsteps, void *stream);
 
 /* ---- latitude-band decomposition (one handle per rank, dc_grid_desc.j0 / j1) ----------

@@ -56,6 +56,11 @@ struct dc_handle;
 namespace dc { struct Stage3Ptrs; }
 static void dcb_launch_stage3(dc_handle *h, dc::Stage3Body &b, const dc::Stage3Ptrs &p, int nbx,
                               int nby, void *);
+template <class Body>
+static void dcb_launch_diag(const Body &b, int i0, int i1, int j0, int j1, void *stream)
+{
+    dcb_launch(b, i0, i1, j0, j1, stream);
+}
 static void dcb_tma_release(dc_handle *) {}
 namespace dc { struct Moist3Ptrs; }
 static void dcb_launch_moist3(dc_handle *h, dc::Moist3Body &b, const dc::Moist3Ptrs &p, int nbx,
