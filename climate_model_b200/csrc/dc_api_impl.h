@@ -15,7 +15,6 @@
 //                                         int nthreads, void *stream);  // b.run_block(bx, by, smem)
 //   template <class Body> void dcb_launch_diag(const Body &b, int i0, int i1, int j0, int j1,
 //                                         void *stream);   // PrimaryDiagBody: b.march(i, j, table, shared)
-//   void dcb_launch_stage(const dc::StageBody &b, int nbx, int nby, void *stream);
 //   void dcb_launch_stage3(dc_handle *h, dc::Stage3Body &b, const dc::Stage3Ptrs &p, int nbx,
 //                          int nby, void *stream);   // fills b's TMA descriptors from p
 //   void dcb_launch_moist3(dc_handle *h, dc::Moist3Body &b, const dc::Moist3Ptrs &p, int nbx,
@@ -57,7 +56,6 @@
 
 #include "../../include/dyncore.h"
 #include "dc_geom.h"
-#include "dc_fused.h"
 #include "dc_kernels.h"
 #include "dc_stage3.h"
 
@@ -146,7 +144,6 @@ struct dc_handle {
     int diag_partial;     // 1: the last diagnostics pass skipped PVTF / PVTFVB / PHIVB
     int stage_kchunks;    // sigma-column chunks of the stage kernel (0 = by launch size)
     int cont_impl;        // 2 = single-pass tile kernel (default), 1 = two-sweep column kernel
-    int stage_impl;       // fused mode: 3 = dc_stage3.h (default), 2 = dc_fused.h (DC_STAGE_IMPL=2)
     int moist_impl;       // fused mode: 3 = dc_moist3.h tile kernel (default), 1 = column kernel
     int coupled_impl;     // i_coupling: 1 = kernel decomposition (strict build), 2 = fused dry
                           // stage kernel + coupled increments (production build)
@@ -378,7 +375,7 @@ static void do_stage_fused(dc_handle *h, int stage, int part, void *stream)
         if (g.i_moist) {
             const double *QV = stage == 0 ? f.QV : f.QV_OLD, *QC = stage == 0 ? f.QC : f.QC_OLD;
             double *QVo = stage == 0 ? f.QV_OLD : f.QV, *QCo = stage == 0 ? f.QC_OLD : f.QC;
-            if (h->moist_impl == 3 && h->stage_impl == 3) {
+            if (h->moist_impl == 3) {
                 Moist3Body mb;
                 mb.g = g;
                 mb.COLP = f.COLP; mb.COLP_NEW = f.COLP_NEW; mb.COLP_OLD = f.COLP_OLD;
@@ -414,11 +411,9 @@ static void do_stage_fused(dc_handle *h, int stage, int part, void *stream)
     }
     // tile rows of the band, cut from the GLOBAL tiling (origins at rows 1 + m * TY, see
     // Stage3Body): tiles t0 .. t1 hold the rows [j0, j1]; boundary = first and last of them
-    const int TY = h->stage_impl == 3 ? S3_TY : dc::TY;
-    const bool aligned = h->stage_impl == 3;
-    const int t0 = aligned ? (g.j0 - 1) / TY : 0;
-    const int t1 = aligned ? (g.j1 - 1) / TY : (g.j1 - g.j0) / TY;
-    const int org = aligned ? 1 : g.j0;                      // row of tile 0
+    const int TY = S3_TY;
+    const int t0 = (g.j0 - 1) / TY, t1 = (g.j1 - 1) / TY;
+    const int org = 1;                                       // row of tile 0
     const int ntr = t1 - t0 + 1;
     const bool can_split = ntr >= 4;
     struct Range { int lo, hi, t_first, nt; } ranges[2];     // rows advanced, tiles covering them
@@ -436,7 +431,7 @@ static void do_stage_fused(dc_handle *h, int stage, int part, void *stream)
     } else if (part == DC_PART_INTERIOR && can_split) {
         ranges[nr++] = clip(t0 + 1, t1 - 1);
     }
-    if (nr && h->stage_impl == 3) {   // both row ranges (if two) in ONE launch
+    if (nr) {   // both row ranges (if two) in ONE launch
         Stage3Body sb;
         sb.g = g;
         sb.COLP = f.COLP; sb.COLP_NEW = f.COLP_NEW; sb.COLP_OLD = f.COLP_OLD;
@@ -464,16 +459,6 @@ static void do_stage_fused(dc_handle *h, int stage, int part, void *stream)
         const Stage3Ptrs sp{U, V, f.WWIND, f.PHI, T, f.PGCOL, f.POTTVB, f.UWIND, f.VWIND, f.POTT};
         if (h->profiling == 1) dcb_profile_begin(h, "stage_fused", stream);
         dcb_launch_stage3(h, sb, sp, nbx3, sb.nby0 + nby1, stream);
-        if (h->profiling == 1) dcb_profile_end(h, stream);
-        h->launches++;
-    }
-    for (int r = 0; r < nr && h->stage_impl != 3; r++) {
-        StageBody sb{g,       U,      V,          T,          f.PHI,   f.PVTF,  f.PVTFVB, f.POTTVB,
-                     f.WWIND, f.COLP, f.COLP_NEW, f.COLP_OLD, f.UWIND, f.VWIND, f.POTT,
-                     Uo,      Vo,     To,         ranges[r].lo, ranges[r].hi};
-        if (h->profiling == 1) dcb_profile_begin(h, "stage_fused", stream);
-        dcb_launch_stage(sb, (g.nx + TX - 1) / TX, (ranges[r].hi - ranges[r].lo + dc::TY) / dc::TY,
-                         stream);
         if (h->profiling == 1) dcb_profile_end(h, stream);
         h->launches++;
     }
@@ -519,7 +504,6 @@ static void do_stage_coupled(dc_handle *h, int stage, void *stream)
 // imported initial state does not carry (dc_stage3.h: XHaloFixBody)
 static void do_xhalo_fix(dc_handle *h, void *stream)
 {
-    if (h->stage_impl != 3) return;
     const Geom &g = h->g;
     const int lo = g.j0 - HJ < 0 ? 0 : g.j0 - HJ, hi = g.j1 + HJ > g.ny + 1 ? g.ny + 1 : g.j1 + HJ;
     launch(h, "xhalo_fix", XHaloFixBody{g, h->f.UWIND}, 0, g.nz - 1, lo, hi, stream);
@@ -538,20 +522,12 @@ static void do_diag_rows(dc_handle *h, int stage, int lo, int hi, void *stream, 
     // the stage kernel reads PHI, POTTVB and PGCOL only: PVTF, PVTFVB and PHIVB are not
     // stored between stages (dc_primary_diag refreshes them on demand)
     const double *T = stage == 0 ? f.POTT_OLD : f.POTT;
-    if (h->stage_impl == 3) {
-        PrimaryDiagBody<1> b{g,     f.COLP,  T,        f.HSURF, f.PVTF, f.PVTFVB,
-                             f.PHI, f.PHIVB, f.POTTVB, f.PGCOL, lo,     hi,
-                             make_pow_coef(con_kappa, g.powtab)};
-        if (gap) { b.j_split = gap_lo; b.j_skip = gap; }
-        launch_diag(h, b, 0, g.nx + 1, 0, nrows - 1, stream);
-        h->diag_partial = 1;
-    } else {
-        PrimaryDiagBody<2> b{g,     f.COLP,  T,        f.HSURF, f.PVTF, f.PVTFVB,
-                             f.PHI, f.PHIVB, f.POTTVB, f.PGCOL, lo,     hi,
-                             make_pow_coef(con_kappa, g.powtab)};
-        if (gap) { b.j_split = gap_lo; b.j_skip = gap; }
-        launch_diag(h, b, 0, g.nx + 1, 0, nrows - 1, stream);
-    }
+    PrimaryDiagBody<1> b{g,     f.COLP,  T,        f.HSURF, f.PVTF, f.PVTFVB,
+                         f.PHI, f.PHIVB, f.POTTVB, f.PGCOL, lo,     hi,
+                         make_pow_coef(con_kappa, g.powtab)};
+    if (gap) { b.j_split = gap_lo; b.j_skip = gap; }
+    launch_diag(h, b, 0, g.nx + 1, 0, nrows - 1, stream);
+    h->diag_partial = 1;
 }
 
 // ... on every row this rank holds
@@ -752,8 +728,6 @@ int dc_create(const dc_grid_desc *d, dc_handle **out)
         h->band_split_cont = (sc && sc[0] == '1') ? 1 : 0;
     }
     h->diag_partial = 0;
-    const char *impl = getenv("DC_STAGE_IMPL");
-    h->stage_impl = (impl && impl[0] == '2') ? 2 : 3;
     const char *kch = getenv("DC_STAGE_KCHUNKS");
     h->stage_kchunks = kch ? atoi(kch) : 0;
     const char *cpl = getenv("DC_COUPLED_IMPL");
@@ -1433,7 +1407,7 @@ static int step_matsuno_banded(dc_handle *h, int nsteps, void *stream)
     int rc;
     if ((rc = check_fused_fields(h, "dc_step_matsuno"))) return rc;
     const Geom &g = h->g;
-    if (g.i_coupling || h->mode != DC_MODE_FUSED || g.nz > NZMAX || h->stage_impl != 3)
+    if (g.i_coupling || h->mode != DC_MODE_FUSED || g.nz > NZMAX)
         return fail(DC_ERR_STATE, "dc_step_matsuno: a latitude band runs the fused dry / moist "
                                   "path only (nz <= %d)", NZMAX);
     if (g.j1 - g.j0 + 1 < HJ)
@@ -1468,7 +1442,7 @@ int dc_step_matsuno(dc_handle *h, int nsteps, void *stream)
     if (!h) return fail(DC_ERR_ARG, "dc_step_matsuno: NULL handle");
     if (nsteps < 0) return fail(DC_ERR_ARG, "dc_step_matsuno: nsteps < 0");
     if (h->comm_state && h->comm_nranks == 1 && h->mode == DC_MODE_FUSED && !h->g.i_coupling &&
-        h->stage_impl == 3 && h->g.nz <= NZMAX)
+        h->g.nz <= NZMAX)
         return step_matsuno_banded(h, nsteps, stream);   // one rank, two concurrent chains
     if (h->g.j0 != 1 || h->g.j1 != h->g.ny) {
         // a band needs the halo exchange between the stages: with a communicator attached
@@ -1503,8 +1477,7 @@ int dc_step_matsuno(dc_handle *h, int nsteps, void *stream)
     if (fused && g.nz > NZMAX)
         return fail(DC_ERR_STATE, "dc_step_matsuno: the fused mode supports nz <= %d "
                                   "(use dc_set_mode(h, DC_MODE_KERNELS))", NZMAX);
-    if (g.i_coupling && h->mode == DC_MODE_FUSED && h->coupled_impl == 2 && g.nz <= NZMAX &&
-        h->stage_impl == 3) {
+    if (g.i_coupling && h->mode == DC_MODE_FUSED && h->coupled_impl == 2 && g.nz <= NZMAX) {
         if ((rc = refresh_diag(h, "dc_step_matsuno", stream))) return rc;   // PHIVB
         do_xhalo_fix(h, stream);
         for (int s = 0; s < nsteps; s++) {

@@ -1,6 +1,6 @@
 // dc_stage3.h -- the fused stage kernel of the Matsuno step, third generation.
 //
-// Same job as dc_fused.h (one launch advances U, V and POTT by one Matsuno stage: momentum-flux
+// One launch advances U, V and POTT by one Matsuno stage (momentum-flux
 // preparation dyn_UVFLX_prepare.py:249-439, dUFLXdt dyn_UFLX.py:69-199, dVFLXdt
 // dyn_VFLX.py:67-198, dPOTTdt dyn_POTT.py:55-110, pressure-weighted Euler step
 // dyn_timestep.py:212-296, boundary images misc_boundaries.py:22-42), re-designed around the
@@ -38,12 +38,13 @@
 #pragma once
 #include <stdlib.h>
 
-#include "dc_fused.h"
 #include "dc_geom.h"
 #include "dc_kernels.h"
 #include "dc_point.h"
 
 namespace dc {
+
+constexpr int NZMAX = 128;   // the fused path holds per-level tables in shared memory: nz <= NZMAX
 
 #ifndef DC_S3_TY
 #define DC_S3_TY 8

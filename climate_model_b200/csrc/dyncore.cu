@@ -56,39 +56,13 @@ static void dcb_launch(const Body &b, int i0, int i1, int j0, int j1, void *stre
     dc::k_columns<Body><<<grid, block, 0, (cudaStream_t)stream>>>(b, i0, i1, j0, j1);
 }
 
-// primary diagnostics: the column march of PrimaryDiagBody with the Exner power table staged in
-// shared memory (7 KB) instead of read through the read-only path on every level
-namespace dc {
-template <class Body>
-__global__ void __launch_bounds__(BX *BY) k_diag(const Body b, int i0, int i1, int j0, int j1)
-{
-    __shared__ __align__(16) double tab[2 * POW_NE * POW_NJ];
-    constexpr int LEV_NZMAX = 128;                  // more levels: tables stay in global memory
-    __shared__ double lev[3 * (LEV_NZMAX + 1)];
-    const bool have = DC_FAST && b.pc.tab != nullptr;
-    const int nz = b.g.nz, tid = threadIdx.y * BX + threadIdx.x;
-    const bool have_lev = nz <= LEV_NZMAX;
-    if (have)
-        for (int n = tid; n < 2 * POW_NE * POW_NJ; n += BX * BY) tab[n] = b.pc.tab[n];
-    if (have_lev)
-        for (int n = tid; n <= nz; n += BX * BY) {
-            lev[n] = b.g.sigma_vb[n];
-            lev[(nz + 1) + n] = n < nz ? b.g.dsigma[n] : 0.;
-            lev[2 * (nz + 1) + n] = n < nz ? b.g.r_dsigma[n] : 0.;
-        }
-    __syncthreads();
-    const int i = i0 + blockIdx.x * BX + threadIdx.x;
-    const int j = j0 + blockIdx.y * BY + threadIdx.y;
-    if (i <= i1 && j <= j1)
-        b.march(i, j, have ? tab : b.pc.tab, have, have_lev ? lev : nullptr);
-}
-}  // namespace dc
+// primary diagnostics: the generic column launch.  A dedicated kernel that staged the Exner power
+// table (7 KB) and the per-level vectors in shared memory was measured and dropped: 0.978-0.995
+// against 0.967 ms per step -- the sweep's `long_scoreboard` stalls are not those look-ups.
 template <class Body>
 static void dcb_launch_diag(const Body &b, int i0, int i1, int j0, int j1, void *stream)
 {
-    dim3 block(dc::BX, dc::BY);
-    dim3 grid((i1 - i0 + dc::BX) / dc::BX, (j1 - j0 + dc::BY) / dc::BY);
-    dc::k_diag<Body><<<grid, block, 0, (cudaStream_t)stream>>>(b, i0, i1, j0, j1);
+    dcb_launch(b, i0, i1, j0, j1, stream);
 }
 
 namespace dc {
@@ -105,14 +79,6 @@ static void dcb_launch_blocks(const Body &b, int nbx, int nby, int nthreads, voi
     dc::k_blocks<Body, Smem><<<dim3(nbx, nby), dim3(nthreads), 0, (cudaStream_t)stream>>>(b);
 }
 
-#include "dc_fused.h"
-namespace dc {
-__global__ void __launch_bounds__(NT, DC_MINBLOCKS) k_stage(const StageBody b)
-{
-    extern __shared__ __align__(16) unsigned char stage_smem[];
-    b.run_block(blockIdx.x, blockIdx.y, *reinterpret_cast<StageSmem *>(stage_smem));
-}
-}  // namespace dc
 // cudaFuncSetAttribute is per device: remember which devices a kernel has been configured on
 static bool first_use_on_device(unsigned long long *mask)
 {
@@ -122,17 +88,6 @@ static bool first_use_on_device(unsigned long long *mask)
     if (*mask & bit) return false;
     *mask |= bit;
     return true;
-}
-static void dcb_launch_stage(const dc::StageBody &b, int nbx, int nby, void *stream)
-{
-    static unsigned long long done = 0;
-    const bool configured = !first_use_on_device(&done);
-    if (!configured) {
-        cudaFuncSetAttribute(dc::k_stage, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)sizeof(dc::StageSmem));
-    }
-    dc::k_stage<<<dim3(nbx, nby), dim3(dc::TX, dc::TY), sizeof(dc::StageSmem),
-                  (cudaStream_t)stream>>>(b);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -155,8 +155,6 @@ int dc_run_diag(dc_handle *h, void *scratch, size_t nbytes, void *stream);
 enum { DC_MODE_FUSED = 0, DC_MODE_KERNELS = 1 };
 int dc_set_mode(dc_handle *h, int mode);
 /* Development switches, read from the environment by dc_create (defaults = the measured best):
- *   DC_STAGE_IMPL=2     second-generation fused stage kernel (csrc/dc_fused.h) instead of the
- *                       TMA-staged one (csrc/dc_stage3.h)
  *   DC_STAGE_KCHUNKS=n  sigma-column chunks of the stage kernel (default: by launch size)
  *   DC_CONT_IMPL=1      two-sweep column continuity kernel instead of the single-pass tile kernel
  *   DC_COUPLED_IMPL=1|2 i_coupling: 1 = kernel decomposition (reference summation order; default

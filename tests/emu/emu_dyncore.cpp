@@ -39,17 +39,6 @@ static void dcb_launch_blocks(const Body &b, int nbx, int nby, int, void *)
         }
 }
 
-#include "../../climate_model_b200/csrc/dc_fused.h"
-static void dcb_launch_stage(const dc::StageBody &b, int nbx, int nby, void *)
-{
-    static dc::StageSmem s;   // one "block" at a time
-    for (int by = nby - 1; by >= 0; by--)
-        for (int bx = nbx - 1; bx >= 0; bx--) {
-            for (size_t n = 0; n < sizeof(s) / sizeof(double); n++)
-                reinterpret_cast<double *>(&s)[n] = 0.0 / 0.0;   // stale smem must not be read
-            b.run_block(bx, by, s);
-        }
-}
 #include "../../climate_model_b200/csrc/dc_stage3.h"
 #include "../../climate_model_b200/csrc/dc_moist3.h"
 struct dc_handle;

@@ -105,7 +105,7 @@ def build_emu(fast=False):
     if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
         mode = (['-DDC_FAST_MATH', '-mfma', '-ffp-contract=fast'] if fast
                 else ['-ffp-contract=off'])
-        subprocess.check_call(['g++', '-O2', '-std=c++17', '-fPIC', '-shared', '-DDC_TY=4'] + mode + extra +
+        subprocess.check_call(['g++', '-O2', '-std=c++17', '-fPIC', '-shared'] + mode + extra +
                               ['-o', so, srcs[0]])
     return so
 
