@@ -153,6 +153,7 @@ struct dc_handle {
     long long bind_version;   // bumped whenever a bound pointer changes (CUDA-graph cache key)
     int band_graph;       // replay the banded step from a CUDA graph (DC_BAND_GRAPH, default 1)
     int band_split_cont;  // next continuity split into inner / band-edge rows (DC_BAND_SPLIT_CONT)
+    int moist_concurrent; // moisture kernel on a side stream beside the stage kernel (DC_MOIST_STREAM)
     double **slot(int id) { return reinterpret_cast<double **>(&f) + id; }
     double *const *slot(int id) const { return reinterpret_cast<double *const *>(&f) + id; }
 };
@@ -726,6 +727,8 @@ int dc_create(const dc_grid_desc *d, dc_handle **out)
         h->band_graph = (bg && bg[0] == '0') ? 0 : 1;
         const char *sc = getenv("DC_BAND_SPLIT_CONT");
         h->band_split_cont = (sc && sc[0] == '1') ? 1 : 0;
+        const char *ms = getenv("DC_MOIST_STREAM");
+        h->moist_concurrent = (ms && ms[0] == '1') ? 1 : 0;
     }
     h->diag_partial = 0;
     const char *kch = getenv("DC_STAGE_KCHUNKS");
@@ -1318,7 +1321,15 @@ static void enqueue_band_step(dc_handle *h, void *M, int tail)
             if (split) dcb_stream_wait(h, EV_CONTI, M);   // continuity of the rows the interior reads
             if (!split || edge_rows_feed_interior) dcb_stream_wait(h, EV_CONT, M);
         }
-        if (g.i_moist) {
+        if (g.i_moist && h->moist_concurrent) {
+            // the moisture kernel on the third stream, beside the stage kernel: both only need
+            // the continuity of this stage, both are latency-bound with different footprints
+            // (160 registers x 3 blocks against 242 x 2)
+            dcb_stream_wait(h, stage == 0 ? EV_START : EV_CONT, T);
+            do_stage_fused(h, stage, DC_PART_MOIST, T);
+            dcb_event_record(h, EV_MOIST, T);
+            DC_MARK("T moisture done", T);
+        } else if (g.i_moist) {
             if (stage == 1 && !single && h->band_split_cont)
                 dcb_stream_wait(h, EV_CONT, M);      // moisture: all rows
             do_stage_fused(h, stage, DC_PART_MOIST, M);
@@ -1351,6 +1362,7 @@ static void enqueue_band_step(dc_handle *h, void *M, int tail)
             dcb_stream_wait(h, EV_BDONE, M);         // both launches have read COLP
         }
         // ---- M: COLP <- COLP_NEW, diagnostics of the own rows
+        if (g.i_moist && h->moist_concurrent) dcb_stream_wait(h, EV_MOIST, M);   // it reads COLP
         do_stage_fused(h, stage, DC_PART_COLP, M);
         dcb_event_record(h, EV_COLP, M);
         if (next && !single && h->band_split_cont) {
@@ -1394,7 +1406,7 @@ static void enqueue_band_step(dc_handle *h, void *M, int tail)
 #undef DC_MARK
     dcb_event_record(h, EV_JOIN, S);                 // the step ends when all chains have
     dcb_stream_wait(h, EV_JOIN, M);
-    if (!single) {
+    if (!single || (g.i_moist && h->moist_concurrent)) {
         dcb_event_record(h, EV_JOIN2, T);
         dcb_stream_wait(h, EV_JOIN2, M);
     }
