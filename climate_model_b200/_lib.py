@@ -80,6 +80,7 @@ def _declare(lib):
     lib.dc_has_comm.argtypes = [vp]
     lib.dc_comm_p2p_handles.argtypes = [vp, vp, ctypes.c_size_t]
     lib.dc_comm_p2p_connect.argtypes = [vp, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t]
+    lib.dc_comm_p2p_enable.argtypes = [vp, ctypes.c_int]
     lib.dc_halo_exchange.argtypes = [vp, ctypes.c_int, vp]
     lib.dc_run_diag_bytes.argtypes = [vp, ctypes.POINTER(ctypes.c_size_t)]
     lib.dc_run_diag.argtypes = [vp, vp, ctypes.c_size_t, vp]

@@ -1231,6 +1231,14 @@ int dc_comm_p2p_connect(dc_handle *h, const void *south, const void *north, size
     return DC_OK;
 }
 
+int dc_comm_p2p_enable(dc_handle *h, int on)
+{
+    if (!h || !h->comm_state) return fail(DC_ERR_STATE, "dc_comm_p2p_enable: no communicator");
+    const int e = dcb_comm_p2p_enable(h, on);
+    if (e) return fail(e, "dc_comm_p2p_enable: %s", dcb_comm_error());
+    return DC_OK;
+}
+
 enum { EV_START = 0, EV_CONT = 1, EV_BDONE = 2, EV_MOIST = 3, EV_COLP = 4, EV_DIAG = 5, EV_JOIN = 6,
        EV_UNPACK = 7, EV_HDIAG = 8, EV_JOIN2 = 9, EV_PACK = 10, EV_CONTI = 11 };
 

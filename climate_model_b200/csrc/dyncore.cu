@@ -246,6 +246,7 @@ static int dcb_comm_sendrecv(dc_handle *h, int stage, void *stream);
 static void dcb_comm_consumed(dc_handle *h, int stage, void *stream);
 static int dcb_comm_p2p_handles(dc_handle *h, void *out);
 static int dcb_comm_p2p_connect(dc_handle *h, const void *south, const void *north);
+static int dcb_comm_p2p_enable(dc_handle *h, int on);
 static void *dcb_side_stream(dc_handle *h, int which = 0);
 static void dcb_event_record(dc_handle *h, int ev, void *stream);
 static void dcb_stream_wait(dc_handle *h, int ev, void *stream);
@@ -314,7 +315,7 @@ struct CommState {
     double *buf[4] = {nullptr, nullptr, nullptr, nullptr};   // send_s, recv_s, send_n, recv_n
                                                              // (recv: two slots, by stage parity)
     // peer-memory exchange (CUDA IPC): the neighbours' receive buffers and flags mapped here
-    bool p2p = false;
+    bool p2p = false, p2p_connected = false;
     unsigned *flags = nullptr;                 // [from south, from north][slot]: 1 = landed
     double *peer_recv[2] = {nullptr, nullptr}; // south neighbour's recv_n, north neighbour's recv_s
     unsigned *peer_flags[2] = {nullptr, nullptr};
@@ -534,8 +535,18 @@ static int dcb_comm_p2p_connect(dc_handle *h, const void *south, const void *nor
         c->peer_recv[1] = static_cast<double *>(c->peer_base[2]);
         c->peer_flags[1] = static_cast<unsigned *>(c->peer_base[3]) + 0;   // [from south][slot]
     }
-    c->p2p = true;
-    c->graph_version = -1;     // captured graphs hold the NCCL exchange
+    c->p2p_connected = true;   // switched on by dcb_comm_p2p_enable once EVERY rank is connected
+    return 0;
+}
+static int dcb_comm_p2p_enable(dc_handle *h, int on)
+{
+    dc::CommState *c = static_cast<dc::CommState *>(h->comm_state);
+    if (on && !c->p2p_connected) {
+        dc::g_comm_error = "the neighbours' buffers are not mapped (dc_comm_p2p_connect)";
+        return DC_ERR_STATE;
+    }
+    c->p2p = on != 0;
+    c->graph_version = -1;     // captured graphs hold the other exchange
     return 0;
 }
 static int dcb_comm_sendrecv(dc_handle *h, int stage, void *stream)

@@ -134,16 +134,25 @@ def attach_communicator(GR, F, group=None, in_library=None):
             # then travel by copy engine + stream memory operations, NCCL stays as the fallback
             nb = _lib.DC_P2P_HANDLE_BYTES
             mine = (ctypes.c_ubyte * nb)()
-            _lib.check(L.dc_comm_p2p_handles(h, mine, nb))
+            ok = L.dc_comm_p2p_handles(h, mine, nb) == 0
             t = torch.tensor(list(mine), dtype=torch.uint8, device=F.torch_device)
             allh = [torch.zeros_like(t) for _ in range(GR.band[1])]
             dist.all_gather(allh, t, group=group)
             rank, nranks = GR.band
             south = bytes(allh[rank - 1].cpu().tolist()) if rank > 0 else None
             north = bytes(allh[rank + 1].cpu().tolist()) if rank < nranks - 1 else None
-            _lib.check(L.dc_comm_p2p_connect(h, south, north, nb))
-            dist.barrier(group=group)          # every rank's flags are zero and mapped
-            GR.comm.p2p = True
+            ok = ok and L.dc_comm_p2p_connect(h, south, north, nb) == 0
+            # all or nothing: a rank that cannot map its neighbours keeps everybody on NCCL
+            # (the all-reduce is also the barrier after which every rank's flags are mapped)
+            flag = torch.tensor([1.0 if ok else 0.0], device=F.torch_device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            if flag.item() == 1.0:
+                _lib.check(L.dc_comm_p2p_enable(h, 1))
+                GR.comm.p2p = True
+            elif rank == 0:
+                import sys
+                print('peer-memory halo exchange unavailable (%s): using NCCL send/recv'
+                      % L.dc_last_error().decode(), file=sys.stderr)
     return GR.comm
 
 

@@ -213,11 +213,14 @@ int dc_halo_exchange(dc_handle *h, int stage, void *stream);
  * the stage kernel (measured on 8 B200: 170 us per NCCL group under load, the longest link of
  * the band step's critical chain).  Every rank publishes dc_comm_p2p_handles (DC_P2P_HANDLE_BYTES
  * bytes), the caller distributes them, every rank connects to its neighbours' (NULL where the
- * band ends at a wall).  Receive buffers and flags are double-buffered by stage parity, so the
+ * band ends at a wall) and, once all ranks report success, switches it on (dc_comm_p2p_enable).  Receive buffers and flags are double-buffered by stage parity, so the
  * constant flag values 1 / 0 suffice and the step can be replayed from a CUDA graph. */
 #define DC_P2P_HANDLE_BYTES 256
 int dc_comm_p2p_handles(dc_handle *h, void *out, size_t nbytes);
 int dc_comm_p2p_connect(dc_handle *h, const void *south, const void *north, size_t nbytes);
+/* switch the peer-memory exchange on (after EVERY rank has connected: the caller agrees on that
+ * collectively, a rank that could not map its neighbours must make all ranks stay on NCCL) or off */
+int dc_comm_p2p_enable(dc_handle *h, int on);
 
 /* ---- layout conversion on the device (F.copy_host_to_device / copy_device_to_host,
  *      main_fields.py:204-215): `ref` is a DEVICE buffer holding the field in the

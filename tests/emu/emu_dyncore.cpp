@@ -83,6 +83,7 @@ static int dcb_comm_sendrecv(dc_handle *, int, void *) { return DC_ERR_NO_DEVICE
 static void dcb_comm_consumed(dc_handle *, int, void *) {}
 static int dcb_comm_p2p_handles(dc_handle *, void *) { return DC_ERR_NO_DEVICE; }
 static int dcb_comm_p2p_connect(dc_handle *, const void *, const void *) { return DC_ERR_NO_DEVICE; }
+static int dcb_comm_p2p_enable(dc_handle *, int) { return DC_ERR_NO_DEVICE; }
 static void *dcb_side_stream(dc_handle *, int = 0) { return nullptr; }
 static void dcb_event_record(dc_handle *, int, void *) {}
 static void dcb_stream_wait(dc_handle *, int, void *) {}
