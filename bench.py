@@ -344,7 +344,7 @@ def banded_parity(GR, F, wl, moist, steps_done, rank, world, cells):
         torch.cuda.empty_cache()
     dist.broadcast(res, 0)
     return {'checked': True, 'bitwise_equal': int(res.item()) == 0, 'bands_differing': int(res.item()),
-            'steps': steps_done, 'fields': PARITY_FIELDS,
+            'steps': steps_done, 'fields': PARITY_FIELDS + (['QV', 'QC'] if moist else []),
             'how': 'int64-sum hash of the owned rows of every band vs a single-GPU replay of '
                    'the whole grid on rank 0'}
 

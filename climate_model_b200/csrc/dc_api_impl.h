@@ -448,7 +448,12 @@ static void do_stage_fused(dc_handle *h, int stage, int part, void *stream)
         sb.have_old = stage == 0 ? 0 : 1;   // stage 1 evaluates the step-start state itself
         // sigma-column chunks: only when the launch has too few blocks to keep the 2 x 148
         // block slots of a B200 busy (a latitude band at N = 8); DC_STAGE_KCHUNKS overrides
-        const int nbx3 = (g.nx + S3_TX - 1) / S3_TX, nblocks = nbx3 * (sb.nby0 + nby1);
+        // The boundary and the interior launch of a band run beside each other: the chunking
+        // follows the blocks of the WHOLE band (the boundary launch alone would be cut into 4
+        // chunks with a set-up phase each: 131 us beside the interior at N = 8).
+        const int nbx3 = (g.nx + S3_TX - 1) / S3_TX;
+        const int nblocks = nbx3 * ((part == DC_PART_BOUNDARY || part == DC_PART_INTERIOR) && can_split
+                                        ? ntr : sb.nby0 + nby1);
         int nkc = h->stage_kchunks;
         if (nkc <= 0) {
             nkc = nblocks >= 4 * 296 ? 1 : (nblocks >= 296 ? 2 : 4);
