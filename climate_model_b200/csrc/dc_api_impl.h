@@ -447,7 +447,10 @@ static void do_stage_fused(dc_handle *h, int stage, int part, void *stream)
         const int nby1 = nr > 1 ? ranges[1].nt : 0;
         sb.have_old = stage == 0 ? 0 : 1;   // stage 1 evaluates the step-start state itself
         // sigma-column chunks: only when the launch has too few blocks to keep the 2 x 148
-        // block slots of a B200 busy (a latitude band at N = 8); DC_STAGE_KCHUNKS overrides
+        // block slots of a B200 busy (a latitude band at N = 8); DC_STAGE_KCHUNKS overrides.
+        // Per LAUNCH: the boundary launch of a band (2 tile rows) gets 4 chunks, the interior 2;
+        // chunking both by the whole band's block count was measured slower (0.747 against
+        // 0.703 ms/step on 84-row bands): the boundary rows must finish early
         // The boundary and the interior launch of a band run beside each other: the chunking
         // follows the blocks of the WHOLE band (the boundary launch alone would be cut into 4
         // chunks with a set-up phase each: 131 us beside the interior at N = 8).
