@@ -451,12 +451,7 @@ static void do_stage_fused(dc_handle *h, int stage, int part, void *stream)
         // Per LAUNCH: the boundary launch of a band (2 tile rows) gets 4 chunks, the interior 2;
         // chunking both by the whole band's block count was measured slower (0.747 against
         // 0.703 ms/step on 84-row bands): the boundary rows must finish early
-        // The boundary and the interior launch of a band run beside each other: the chunking
-        // follows the blocks of the WHOLE band (the boundary launch alone would be cut into 4
-        // chunks with a set-up phase each: 131 us beside the interior at N = 8).
-        const int nbx3 = (g.nx + S3_TX - 1) / S3_TX;
-        const int nblocks = nbx3 * ((part == DC_PART_BOUNDARY || part == DC_PART_INTERIOR) && can_split
-                                        ? ntr : sb.nby0 + nby1);
+        const int nbx3 = (g.nx + S3_TX - 1) / S3_TX, nblocks = nbx3 * (sb.nby0 + nby1);
         int nkc = h->stage_kchunks;
         if (nkc <= 0) {
             nkc = nblocks >= 4 * 296 ? 1 : (nblocks >= 296 ? 2 : 4);
