@@ -143,3 +143,22 @@ static void dcb_launch_moist3(dc_handle *, dc::Moist3Body &b, const dc::Moist3Pt
                 b.run_block(bx, by, bz, s);
             }
 }
+
+// ---- test hooks (host emulation only): the table-driven power / logarithm of the production
+//      build, evaluated on the host with the same code the kernels inline ----
+extern "C" double emu_pow_kappa_tab(double x)
+{
+    static std::vector<double> tab;
+    static dc::PowCoef c;
+    if (tab.empty()) {
+        tab.resize(2 * dc::POW_NE * dc::POW_NJ);
+        dc::make_pow_table(dc::con_kappa, tab.data());
+        c = dc::make_pow_coef(dc::con_kappa, tab.data());
+    }
+    return dc::pow_kappa_tab(x, c);
+}
+extern "C" double emu_log_tab(double x)
+{
+    static const dc::LogCoef L = dc::make_log_coef();
+    return dc::log_tab(x, L, L.tab);
+}

@@ -86,3 +86,33 @@ def test_band_rows_partition_the_latitude_range(ny, nranks):
     sizes = [j1 - j0 + 1 for j0, j1 in rows]
     assert all(b[0] == a[1] + 1 for a, b in zip(rows, rows[1:]))      # contiguous, no overlap
     assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
+
+
+def test_table_driven_power_and_logarithm_are_within_two_ulp():
+    """pow_kappa_tab (Exner function) and log_tab (tracer interface values) of the production
+    build (csrc/dc_point.h) against extended-precision references over the arguments the model
+    produces: pressures 3 kPa .. 130 kPa, mixing ratios 1e-7 .. 0.1"""
+    import ctypes
+    import numpy as np
+    from helpers import build_emu
+    lib = ctypes.CDLL(build_emu(fast=True))
+    lib.emu_pow_kappa_tab.restype = ctypes.c_double
+    lib.emu_pow_kappa_tab.argtypes = [ctypes.c_double]
+    lib.emu_log_tab.restype = ctypes.c_double
+    lib.emu_log_tab.argtypes = [ctypes.c_double]
+    rng = np.random.default_rng(7)
+    kappa = np.longdouble(287.058) / np.longdouble(1005.)
+    kappa = np.longdouble(np.float64(287.058 / 1005.))         # the double the kernels use
+    worst_pow = worst_log = 0.
+    for x in rng.uniform(0.03, 1.3, size=20000):
+        ref = np.power(np.longdouble(x), kappa)
+        got = lib.emu_pow_kappa_tab(float(x))
+        worst_pow = max(worst_pow, float(abs(np.longdouble(got) - ref) / np.spacing(np.float64(ref))))
+    for x in np.exp(rng.uniform(np.log(1e-7), np.log(0.1), size=20000)):
+        ref = np.log(np.longdouble(x))
+        got = lib.emu_log_tab(float(x))
+        worst_log = max(worst_log, float(abs(np.longdouble(got) - ref) / np.spacing(np.float64(abs(ref)))))
+    assert worst_pow <= 2.0 and worst_log <= 2.0, (worst_pow, worst_log)
+    # outside the tabulated binades the power falls back to the library pow
+    for x in (1e-3, 7.5):
+        assert abs(lib.emu_pow_kappa_tab(x) - x ** (287.058 / 1005.)) <= 4 * np.spacing(x ** 0.2856)
