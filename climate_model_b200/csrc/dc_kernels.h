@@ -810,13 +810,22 @@ struct PrimaryDiagBody {
     PowCoef pc;
     // rows from j_split on are shifted by j_skip: [j_lo, j_split) and [j_split + j_skip, j_hi]
     int j_split = 1 << 30, j_skip = 0;
-    DC_HD void operator()(int i, int jj) const { march(i, jj, pc.tab, false, nullptr); }
+    DC_HD void operator()(int i, int jj) const { march(i, jj, pc.tab, false, nullptr, nullptr, 0); }
     // `tab` = the power table: pc.tab (global memory) or the kernel's copy in shared memory
     // (k_diag in dyncore.cu; ncu: with the table behind the read-only path 64 % of the sweep's
     // stalls were this lookup, which sits on the level's dependent chain)
     // `lev`: sigma_vb | dsigma | r_dsigma, (nz+1) entries each, staged by the kernel (or NULL:
     // read from the geometry vectors in global memory)
-    DC_HD void march(int i, int jj, const double *tab, bool shared, const double *lev) const
+    // `ring`: this thread's slot of a shared-memory ring (DIAG_SLOTS slots, `rstride` doubles
+    // apart) that POTT is copied into DIAG_PF levels ahead with cp.async (k_diag in dyncore.cu);
+    // NULL: POTT through a register, one level ahead.  Why not registers: ptxas put the per-level
+    // r_dsigma load and the POTT load of the NEXT level on the same scoreboard (decoded from the
+    // control bits of the shipped kernel), so the first use of r_dsigma waited for the POTT
+    // request issued 60 instructions earlier -- every level paid the full DRAM latency (ncu: 60 %
+    // of all warp samples on that one DMUL) whatever the prefetch distance in the source was.
+    // An asynchronous copy has no scoreboard: its only wait is the explicit wait_group.
+    DC_HD void march(int i, int jj, const double *tab, bool shared, const double *lev,
+                     double *ring, int rstride) const
     {
         const double *sig = lev ? lev : g.sigma_vb;
         const double *dsg = lev ? lev + (g.nz + 1) : g.dsigma;
@@ -851,6 +860,17 @@ struct PrimaryDiagBody {
         // table lookup of its own level, not on POTT)
         constexpr int PF = 1;
         double pott_q[NC][PF];
+#if defined(__CUDA_ARCH__)
+        int slot_rd = 0, slot_wr = DIAG_PF & (DIAG_SLOTS - 1);
+        if (ring) {
+#pragma unroll
+            for (int n = 0; n < DIAG_PF; n++) {
+                if (nz - 1 - n >= 0)
+                    dc_cp_async8(ring + n * rstride, POTT + (o[0] - (size_t)(n + 1) * plane));
+                dc_cp_commit();
+            }
+        } else
+#endif
         for (int c = 0; c < NC; c++)
             for (int n = 0; n < PF; n++)
                 pott_q[c][n] = nz - 1 - n >= 0 ? POTT[o[c] - (size_t)(n + 1) * plane] : 0.;
@@ -859,10 +879,25 @@ struct PrimaryDiagBody {
             const Div ds = mkdiv(dsg[k], rds[k]);
             for (int c = 0; c < NC; c++) {
                 o[c] -= plane;
-                const double pott = pott_q[c][0];
+                double pott;
+#if defined(__CUDA_ARCH__)
+                if (ring) {
+                    // the slot written now was read one level ago and its value consumed since
+                    dc_cp_wait<DIAG_PF - 1>();
+                    pott = ring[slot_rd * rstride];
+                    if (k - DIAG_PF >= 0)
+                        dc_cp_async8(ring + slot_wr * rstride, POTT + (o[c] - (size_t)DIAG_PF * plane));
+                    dc_cp_commit();
+                    slot_rd = (slot_rd + 1) & (DIAG_SLOTS - 1);
+                    slot_wr = (slot_wr + 1) & (DIAG_SLOTS - 1);
+                } else
+#endif
+                {
+                pott = pott_q[c][0];
 #pragma unroll
                 for (int n = 0; n + 1 < PF; n++) pott_q[c][n] = pott_q[c][n + 1];
                 if (k - PF >= 0) pott_q[c][PF - 1] = POTT[o[c] - (size_t)PF * plane];
+                }
                 const double p_km12 = g.pair_top + svb * colp[c];
                 const double pw_km12 = exner(p_km12, tab, shared);
                 const double pvtf = fdiv(1. / (1. + con_kappa) *

@@ -576,4 +576,25 @@ DC_HD double interp_COLPA_is(double COLP, double COLP_im1, double COLP_jm1, doub
                       2. * COLP * A + COLP_im1_jm1 * A_jm1 + COLP_jm1 * A_jm1);
 }
 
+// POTT ring of the diagnostics sweep (see PrimaryDiagBody::march): levels in flight and slots
+#ifndef DC_DIAG_PF
+#define DC_DIAG_PF 3
+#endif
+constexpr int DIAG_PF = DC_DIAG_PF > 0 ? DC_DIAG_PF : 1;
+constexpr int DIAG_SLOTS = DIAG_PF < 2 ? 2 : DIAG_PF < 4 ? 4 : DIAG_PF < 8 ? 8 : 16;
+static_assert(DIAG_PF < DIAG_SLOTS, "ring: one slot more than levels in flight");
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ void dc_cp_async8(double *s, const double *gp)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(s);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gp) : "memory");
+}
+__device__ __forceinline__ void dc_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void dc_cp_wait()
+{
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+#endif
+
 }  // namespace dc

@@ -56,18 +56,49 @@ static void dcb_launch(const Body &b, int i0, int i1, int j0, int j1, void *stre
     dc::k_columns<Body><<<grid, block, 0, (cudaStream_t)stream>>>(b, i0, i1, j0, j1);
 }
 
-// primary diagnostics: the generic column launch.  A dedicated kernel that staged the Exner power
-// table (7 KB) and the per-level vectors in shared memory was measured and dropped: 0.978-0.995
-// against 0.967 ms per step -- the sweep's `long_scoreboard` stalls are not those look-ups.
+// primary diagnostics: thread per column like k_columns, with its own block shape and register
+// budget (DC_DIAG_BY rows of 64 longitudes per block, DC_DIAG_MINB blocks per SM): the sweep is
+// bound by latency, so resident warps are what the build switches trade against spills.
+// A dedicated kernel that staged the Exner power table (7 KB) and the per-level vectors in
+// shared memory was measured and dropped: 0.978-0.995 against 0.967 ms per step -- the sweep's
+// `long_scoreboard` stalls are not those look-ups.
+#ifndef DC_DIAG_BY
+#define DC_DIAG_BY 4
+#endif
+#ifndef DC_DIAG_MINB
+#define DC_DIAG_MINB 4
+#endif
+namespace dc {
+template <class Body>
+__global__ void __launch_bounds__(BX *DC_DIAG_BY, DC_DIAG_MINB)
+    k_diag(const Body b, int i0, int i1, int j0, int j1)
+{
+    const int i = i0 + blockIdx.x * BX + threadIdx.x;
+    const int j = j0 + blockIdx.y * DC_DIAG_BY + threadIdx.y;
+#if DC_DIAG_PF > 0
+    __shared__ double ring[DIAG_SLOTS][BX * DC_DIAG_BY];
+    if (i <= i1 && j <= j1)
+        b.march(i, j, b.pc.tab, false, nullptr, &ring[0][threadIdx.y * BX + threadIdx.x],
+                BX * DC_DIAG_BY);
+#else
+    if (i <= i1 && j <= j1) b(i, j);
+#endif
+}
+}  // namespace dc
 template <class Body>
 static void dcb_launch_diag(const Body &b, int i0, int i1, int j0, int j1, void *stream)
 {
-    dcb_launch(b, i0, i1, j0, j1, stream);
+    dim3 block(dc::BX, DC_DIAG_BY);
+    dim3 grid((i1 - i0 + dc::BX) / dc::BX, (j1 - j0 + DC_DIAG_BY) / DC_DIAG_BY);
+    dc::k_diag<Body><<<grid, block, 0, (cudaStream_t)stream>>>(b, i0, i1, j0, j1);
 }
 
 namespace dc {
+#ifndef DC_CT_MINB
+#define DC_CT_MINB 2
+#endif
 template <class Body, class Smem>
-__global__ void __launch_bounds__(256, 2) k_blocks(const Body b)
+__global__ void __launch_bounds__(256, DC_CT_MINB) k_blocks(const Body b)
 {
     __shared__ Smem s;
     b.run_block(blockIdx.x, blockIdx.y, s);
