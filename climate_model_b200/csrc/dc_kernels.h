@@ -1238,6 +1238,9 @@ constexpr int CT_TX = DC_CT_TX;   // longitudes per block
 #define DC_CT_L 16
 #endif
 constexpr int CT_L = DC_CT_L;     // levels per thread
+// (measured and dropped, round 2: per-warp running sums joined after ONE barrier instead of the
+// chain through nw barriers -- 1.07 against 0.71 ms per step: two more live doubles per thread
+// spill at the 128-register budget the 64 loads in flight need)
 constexpr int CT_MAXW = 128 / CT_L;   // nz <= 128
 
 #if defined(__CUDA_ARCH__)
@@ -1278,11 +1281,15 @@ struct ContinuityTileBody {
         const int nz = g.nz, nw = (nz + CT_L - 1) / CT_L, nt = nw * CT_TX;
         const int j = (j_lo + by >= j_split) ? j_lo + by + j_skip : j_lo + by;
         CT_PRIVN(double, fd, CT_L);   // flux divergence, then running sum, of the own levels
+        // COLP_OLD of the column, requested with the winds: its first use comes after the
+        // prefix sums, where a fresh request cost 8 % of the kernel's warp samples (ncu)
+        CT_PRIV(double, c_old);
         // ---- flux divergences of the own levels -------------------------------------------
         CT_PHASE(nt)
             const int w = tid / CT_TX, i = 1 + bx * CT_TX + tid % CT_TX;
             if (i <= g.nx) {
                 const double c = COLP[g.idx2(i, j)];
+                CT_P(c_old) = COLP_OLD[g.idx2(i, j)];
                 const double c_im1 = COLP[g.idx2(i - 1, j)], c_ip1 = COLP[g.idx2(i + 1, j)];
                 const double c_jm1 = COLP[g.idx2(i, j - 1)], c_jp1 = COLP[g.idx2(i, j + 1)];
                 const double dxjs = g.dxjs[g.row(j)], dxjs_jp1 = g.dxjs[g.row(j + 1)];
@@ -1343,7 +1350,7 @@ struct ContinuityTileBody {
             const int w = tid / CT_TX, lane = tid % CT_TX, i = 1 + bx * CT_TX + lane;
             if (i <= g.nx) {
                 const double dcdt = -s.tot[nw - 1][lane];
-                const double cnew = COLP_OLD[g.idx2(i, j)] + g.dt * dcdt;
+                const double cnew = CT_P(c_old) + g.dt * dcdt;
                 if (w == 0) {
                     dCOLPdt[g.idx2(i, j)] = dcdt;
                     put_mass(g, COLP_NEW, i, j, 0, cnew);
