@@ -17,11 +17,12 @@ oracle/dyncore_oracle.c, OpenMP over all host cores) on a bounded sample of the 
 workload and prints the same JSON line with "impl": "reference".
 """
 import argparse
+import datetime
 import json
 import os
 import subprocess
 import sys
-import threading
+import tempfile
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -95,41 +96,65 @@ def peak_hbm_gbs():
     return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region"""
-    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region: ONE `nvidia-smi -lms`
+    process (the recipe of B200_PROFILING.md) started before the warm-up, so that its start-up
+    (NVML initialisation, device attach) does not fall into the timed region; the rows whose
+    time stamp lies between begin() and stop() are the ones reported.  (A fresh nvidia-smi
+    process every 200 ms, as in the first version, perturbed the run it observed: when a
+    start-up landed on the 90 ms timed region the step came out 0.2 ms longer.)"""
+    Q = ('timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
          'clocks_event_reasons.sw_power_cap')
 
-    def __init__(self, index=0):
-        super().__init__(daemon=True)
-        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+    def __init__(self, index=0, period_ms=50):
+        self.t0 = self.t1 = None
+        self.out = tempfile.TemporaryFile(mode='w+')
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(index), '--query-gpu=' + self.Q,
+                 '--format=csv,noheader,nounits', '-lms', str(period_ms)],
+                stdout=self.out, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
 
-    def run(self):
-        while not self._stop_evt.is_set():
-            try:
-                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                      '--format=csv,noheader,nounits'], capture_output=True,
-                                     text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(',')])
-            except Exception:
-                pass
-            self._stop_evt.wait(0.2)
+    def begin(self):
+        self.t0 = time.time()
 
     def stop(self):
-        self._stop_evt.set()
-        self.join(timeout=6)
-        sm = sorted(float(r[0]) for r in self.rows if r[0].replace('.', '').isdigit())
+        self.t1 = time.time()
+        time.sleep(0.06)                      # one more period: a row stamped inside the region
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+        self.out.seek(0)
+        rows, inside = [], []
+        for line in self.out.read().splitlines():
+            r = [x.strip() for x in line.split(',')]
+            if len(r) < 8 or not r[1].replace('.', '').isdigit():
+                continue
+            rows.append(r)
+            try:
+                ts = datetime.datetime.strptime(r[0], '%Y/%m/%d %H:%M:%S.%f').timestamp()
+                if self.t0 is not None and self.t0 <= ts <= self.t1 + 0.05:
+                    inside.append(r)
+            except ValueError:
+                pass
+        self.out.close()
+        use = inside or rows[-2:]             # no stamp inside a very short region: the last rows
+        sm = sorted(float(r[1]) for r in use)
         reasons = set()
-        for r in self.rows:
+        for r in use:
             for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
-                                'sw_power_cap'), r[3:7]):
+                                'sw_power_cap'), r[4:8]):
                 if v.lower().startswith('active'):
                     reasons.add(name)
         return {'sm_mhz': sm[len(sm) // 2] if sm else None,
-                'sm_max_mhz': float(self.rows[0][1]) if self.rows else None,
-                'samples': len(self.rows), 'reasons': sorted(reasons)}
+                'sm_max_mhz': float(use[0][2]) if use else None,
+                'samples': len(use), 'in_timed_region': len(inside), 'reasons': sorted(reasons)}
 
 
 def sample_grid(wl):
@@ -458,12 +483,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(args.warmup):
         one_step()
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
-        sampler.start()
+        sampler.begin()
     def timed(kernel_events):
         """K steps between barriers, CUDA events on the launching stream, max over ranks"""
         _lib.check(L.dc_profile_enable(h, 1 if kernel_events else 0))
