@@ -81,8 +81,8 @@ KERNEL_ACCESSES_COUPLED = {
 # `ncu --set full` capture, profiles/r2_ncu_full_summary.csv): valid for that workload on one
 # GPU only; anything else reports null
 NCU_TRAFFIC = {
-    ('cfg4', 1, False, 'stage_fused'): 0.5 * ((4.030787 + 1.483990) + (5.546863 + 1.481524)) * 1e9,
-    ('cfg4', 1, True, 'stage_fused'): 0.5 * ((4.030787 + 1.483990) + (5.546863 + 1.481524)) * 1e9,
+    ('cfg4', 1, False, 'stage_fused'): 0.5 * ((4.03218 + 1.48306) + (5.54234 + 1.48088)) * 1e9,
+    ('cfg4', 1, True, 'stage_fused'): 0.5 * ((4.03218 + 1.48306) + (5.54234 + 1.48088)) * 1e9,
 }
 
 
