@@ -811,11 +811,10 @@ struct PrimaryDiagBody {
     // rows from j_split on are shifted by j_skip: [j_lo, j_split) and [j_split + j_skip, j_hi]
     int j_split = 1 << 30, j_skip = 0;
     DC_HD void operator()(int i, int jj) const { march(i, jj, pc.tab, false, nullptr, nullptr, 0); }
-    // `tab` = the power table: pc.tab (global memory) or the kernel's copy in shared memory
-    // (k_diag in dyncore.cu; ncu: with the table behind the read-only path 64 % of the sweep's
-    // stalls were this lookup, which sits on the level's dependent chain)
-    // `lev`: sigma_vb | dsigma | r_dsigma, (nz+1) entries each, staged by the kernel (or NULL:
-    // read from the geometry vectors in global memory)
+    // `tab` = the power table: pc.tab (global memory) or a copy in shared memory; `lev`:
+    // sigma_vb | dsigma | r_dsigma, (nz+1) entries each, in shared memory (or NULL: the geometry
+    // vectors in global memory).  The shipped kernel passes pc.tab and NULL: staging both in
+    // shared memory measured no gain (the L1 serves them)
     // `ring`: this thread's slot of a shared-memory ring (DIAG_SLOTS slots, `rstride` doubles
     // apart) that POTT is copied into DIAG_PF levels ahead with cp.async (k_diag in dyncore.cu);
     // NULL: POTT through a register, one level ahead.  Why not registers: ptxas put the per-level
@@ -853,11 +852,8 @@ struct PrimaryDiagBody {
             }
         }
         double svb_kp1 = sig[nz];
-        // POTT of the next level is requested one iteration ahead: its latency hides behind the
-        // exp / log / division chain of the current level (ncu: 60 % of the stalls were this load)
-        // (round 2, with the table-driven Exner power: requesting three levels ahead instead of
-        // one measured 2 % SLOWER, 0.985 against 0.967 ms per step -- the sweep waits on the
-        // table lookup of its own level, not on POTT)
+        // without a ring (host emulation, DC_DIAG_PF=0): POTT of the next level through a
+        // register, requested one iteration ahead
         constexpr int PF = 1;
         double pott_q[NC][PF];
 #if defined(__CUDA_ARCH__)
