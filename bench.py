@@ -152,8 +152,10 @@ class ClockSampler:
                                 'sw_power_cap'), r[4:8]):
                 if v.lower().startswith('active'):
                     reasons.add(name)
+        pw = sorted(float(r[3]) for r in use if r[3].replace('.', '').isdigit())
         return {'sm_mhz': sm[len(sm) // 2] if sm else None,
                 'sm_max_mhz': float(use[0][2]) if use else None,
+                'power_w': pw[len(pw) // 2] if pw else None,
                 'samples': len(use), 'in_timed_region': len(inside), 'reasons': sorted(reasons)}
 
 
