@@ -99,3 +99,31 @@ def test_two_rank_line_under_torchrun_gloo():
     whole = 8 * (75 * 34 * 8 + 74 * 35 * 8 + 74 * 34 * 8 + 74 * 34)
     assert whole < e['h2d_bytes_per_step'] < 1.3 * whole
     assert 'cpu_baseline' not in d
+
+
+def test_clock_sampler_reports_the_rows_stamped_inside_the_timed_region():
+    """the nvidia-smi log of the long-running sampler: only rows between begin() and stop()
+    count; clocks, board power and throttle reasons come from those"""
+    import datetime
+    import importlib.util
+    import tempfile
+    import time
+    spec = importlib.util.spec_from_file_location('bench_mod', os.path.join(ROOT, 'bench.py'))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    s = bench.ClockSampler.__new__(bench.ClockSampler)
+    s.out, s.proc = tempfile.TemporaryFile(mode='w+'), None
+    now = time.time()
+    s.t0 = now - 0.2
+    stamp = lambda t: datetime.datetime.fromtimestamp(t).strftime('%Y/%m/%d %H:%M:%S.%f')[:-3]
+    idle = 'Not Active, Not Active, Not Active, Not Active'
+    s.out.write('%s, 1965, 1965, 400.5, %s\n' % (stamp(now - 1.0), idle))        # warm-up
+    s.out.write('%s, 1867, 1965, 990.1, Not Active, Not Active, Not Active, Active\n'
+                % stamp(now - 0.1))
+    s.out.write('%s, 1845, 1965, 995.0, Not Active, Not Active, Not Active, Active\n'
+                % stamp(now - 0.05))
+    s.out.flush()
+    c = s.stop()
+    assert c['in_timed_region'] == 2 and c['samples'] == 2
+    assert c['sm_mhz'] in (1845.0, 1867.0) and c['sm_max_mhz'] == 1965.0
+    assert c['reasons'] == ['sw_power_cap'] and c['power_w'] > 900
