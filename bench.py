@@ -457,6 +457,8 @@ def main():
     assert world == args.gpus, '--gpus %d but WORLD_SIZE=%d (launch with torchrun)' % (
         args.gpus, world)
 
+    # started here, seconds before the warm-up: its start-up must not touch the timed regions
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     GR = Grid(band=(rank, world), i_moist_main_switch=int(moist),
               i_coupling=int(args.turbulence), **wl['grid'])
     # latitude bands: host arrays and the initial-state builder cover the rank's rows only
@@ -485,7 +487,6 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(args.warmup):
         one_step()
     barrier()
